@@ -1,0 +1,185 @@
+/* vidx_b200.h -- C ABI of libvidx_b200.so: the B200 (sm_100a) implementation of the
+ * IVF search + k-means hot path of the Rust crate `vector_indexer`
+ * (NirajNair/vector-indexer).  Plain pointers and sizes only; no torch / C++ types.
+ *
+ * Every entry point names the reference interface it replaces (file:line relative
+ * to the reference tree).  Return value: 0 on success, otherwise one of the
+ * VIDX_ERR_* codes, which map 1:1 onto the std::io::ErrorKind values the reference
+ * returns for the same condition.  vidx_last_error() gives the message.
+ *
+ * Threading: a handle may be searched from several threads (calls on one handle
+ * are serialised internally); build/load must not race with anything.
+ * There is NO CPU fallback: every compute entry point fails with VIDX_ERR_CUDA when
+ * no sm_100 device is usable.
+ */
+#ifndef VIDX_B200_H
+#define VIDX_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VIDX_OK 0
+#define VIDX_ERR_INVALID_INPUT 1 /* io::ErrorKind::InvalidInput */
+#define VIDX_ERR_NOT_FOUND 2     /* io::ErrorKind::NotFound     */
+#define VIDX_ERR_INVALID_DATA 3  /* io::ErrorKind::InvalidData  */
+#define VIDX_ERR_OTHER 4         /* io::ErrorKind::Other        */
+#define VIDX_ERR_CUDA 5          /* device / driver failure (no reference counterpart) */
+#define VIDX_ERR_UNSUPPORTED 6   /* valid in the reference, outside this build's limits */
+
+typedef struct vidx_index vidx_index;
+
+/* ---- lifecycle -------------------------------------------------------------------- */
+
+/* VectorIndexer::new(VectorIndexerConfig::new(dimension))          src/api.rs:33-43, :103-106
+ * `device` is the CUDA ordinal this handle lives on. */
+int vidx_create(uint32_t dimension, int device, vidx_index** out);
+void vidx_free(vidx_index* idx);
+/* Message of the last failing call on this thread (never NULL). */
+const char* vidx_last_error(void);
+
+/* VectorIndexerConfig defaults / clamps                             src/api.rs:38-41, :189-190 */
+int vidx_set_limits(vidx_index* idx, uint64_t default_k, uint64_t default_n_probe, uint64_t max_k,
+                    uint64_t max_n_probe);
+
+/* ---- build = train + add ---------------------------------------------------------- */
+
+/* VectorIndexer::build_from_records -> IvfIndex::fit_with_paths    src/api.rs:115-146, src/ivf_index.rs:58-177
+ * data: n x dimension row-major fp32 (VectorStore::get_vectors, src/vector_store.rs:48-58).
+ * ext_ids: n external ids, NULL => row index (bindings/python/src/lib.rs:256-262).
+ * timestamps: n values, NULL or 0 => now (src/vector_store.rs:36-40).
+ * seed: 42 in the reference (src/api.rs:143).  nlist / max_iters: 0 => the reference
+ * heuristics (src/utils.rs:9-26); non-zero overrides them (BASELINE configs fix nlist).
+ * n == 0 => VIDX_ERR_INVALID_INPUT ("no vectors provided", src/api.rs:116-118). */
+int vidx_build(vidx_index* idx, const float* data, const uint64_t* ext_ids, const uint64_t* timestamps, uint64_t n,
+               uint64_t seed, uint64_t nlist, uint64_t max_iters);
+
+/* The two halves of fit_with_paths, exposed separately (north_star "build/train, add"):
+ * train  = mini-batch k-means + super-centroid shard assignment    src/ivf_index.rs:59-77, :103-109
+ * add    = list assignment by the trained centroids, list build,
+ *          empty-list filter + renumbering                          src/ivf_index.rs:79-164
+ * vidx_train keeps the final labels of the training vectors; vidx_add with the same
+ * `data` pointer contents reproduces vidx_build exactly. */
+int vidx_train(vidx_index* idx, const float* data, uint64_t n, uint64_t seed, uint64_t nlist, uint64_t max_iters);
+int vidx_add(vidx_index* idx, const float* data, const uint64_t* ext_ids, const uint64_t* timestamps, uint64_t n);
+
+/* Build the device-resident lists from caller-supplied centroids and labels (no
+ * training); the list-build half of src/ivf_index.rs:79-164 on its own. */
+int vidx_build_from_labels(vidx_index* idx, const float* data, const uint64_t* ext_ids, uint64_t n,
+                           const float* centroids, uint64_t k, const uint64_t* labels, const uint64_t* centroid_shard);
+
+/* ---- search ----------------------------------------------------------------------- */
+
+/* PyVectorIndex.search_blocking(xq, k, n_probe) -> (D, I)           bindings/python/src/lib.rs:123-203
+ *   = for each row: VectorIndexer::search -> IvfIndex::search_with_paths
+ *                                                                   src/api.rs:188-222, src/ivf_index.rs:190-267
+ * xq: nq x dimension fp32 HOST memory.  D: nq x k squared-L2 distances, ascending,
+ * padded with +inf.  I: nq x k external ids as i64, padded with -1.
+ * k == 0 or n_probe == 0 => VIDX_ERR_INVALID_INPUT (src/ivf_index.rs:197-202);
+ * k / n_probe above max_k / max_n_probe are clamped (src/api.rs:189-190); the output
+ * stride stays the caller's k. */
+int vidx_search(vidx_index* idx, const float* xq, uint64_t nq, uint64_t k, uint64_t n_probe, float* D, int64_t* I);
+
+/* Same with DEVICE pointers (queries already in HBM, results left in HBM) on the given
+ * CUDA stream (cudaStream_t cast to void*, NULL = the handle's own stream).  Returns
+ * after enqueueing; results are ready when the stream reaches this point. */
+int vidx_search_device(vidx_index* idx, const float* d_xq, uint64_t nq, uint64_t k, uint64_t n_probe, float* d_D,
+                       int64_t* d_I, void* stream);
+
+/* SearchRequest::with_include_vectors(true)                          src/api.rs:83-86, :213-217
+ * As vidx_search, additionally V: nq x k x dimension fp32 payloads (rows of missing
+ * results are zero). */
+int vidx_search_with_vectors(vidx_index* idx, const float* xq, uint64_t nq, uint64_t k, uint64_t n_probe, float* D,
+                             int64_t* I, float* V);
+
+/* Coarse quantization only: the n_probe nearest lists per query, in the order the
+ * reference's stable sort yields (src/ivf_index.rs:205-220).  lists: nq x n_probe
+ * (padded with UINT32_MAX when n_probe > nlist), dists likewise (+inf). */
+int vidx_coarse_probes(vidx_index* idx, const float* xq, uint64_t nq, uint64_t n_probe, uint32_t* lists,
+                       float* dists);
+
+/* ---- introspection (what IvfIndex / Shard hold after fit)   src/ivf_index.rs:36-41, :174-176 */
+uint32_t vidx_dimension(const vidx_index* idx);
+uint64_t vidx_ntotal(const vidx_index* idx);
+uint64_t vidx_nlist(const vidx_index* idx);      /* non-empty lists (src/ivf_index.rs:122-146) */
+uint64_t vidx_num_shards(const vidx_index* idx); /* ceil(sqrt(k)) (src/ivf_index.rs:104) */
+uint64_t vidx_k_trained(const vidx_index* idx);  /* k before the empty-list filter */
+int vidx_get_centroids(const vidx_index* idx, float* out /* nlist x dim */);
+int vidx_get_centroids_to_shard(const vidx_index* idx, uint64_t* out /* nlist */);
+int vidx_get_list_sizes(const vidx_index* idx, uint64_t* out /* nlist */);
+/* internal ids (= build row index, src/vector_store.rs:33) of one list, ascending */
+int vidx_get_list_members(const vidx_index* idx, uint64_t list, uint64_t* out);
+int vidx_get_train_labels(const vidx_index* idx, uint64_t* out /* n, unfiltered numbering */);
+int vidx_get_train_centroids(const vidx_index* idx, float* out /* k_trained x dim */);
+
+/* ---- k-means (the functions src/kmeans.rs exports) -------------------------------- */
+
+/* run_kmeans_mini_batch(data, k, max_iters, early_stop_threshold, seed)   src/kmeans.rs:64-150
+ * tol < 0 => None => 1e-4.  n == 0 => VIDX_ERR_INVALID_INPUT (src/kmeans.rs:72-77).
+ * out_labels are usize in the reference => u64 here.  iters_run may be NULL. */
+int vidx_kmeans_mini_batch(int device, const float* data, uint64_t n, uint64_t dim, uint64_t k, uint64_t max_iters,
+                           float tol, uint64_t seed, float* out_centroids, uint64_t* out_labels, uint64_t* iters_run);
+/* run_kmeans_parallel (full-batch Lloyd)                                   src/kmeans.rs:15-60 */
+int vidx_kmeans_parallel(int device, const float* data, uint64_t n, uint64_t dim, uint64_t k, uint64_t max_iters,
+                         float tol, uint64_t seed, float* out_centroids, uint64_t* out_labels, uint64_t* iters_run);
+/* assign_points_simd_parallel: brute force for k <= 100, hierarchical above
+ *                                                                          src/kmeans.rs:445-581 */
+int vidx_assign_points(int device, const float* data, uint64_t n, uint64_t dim, const float* centroids, uint64_t k,
+                       uint64_t seed, uint64_t* out_labels);
+/* kmeans_plus_plus_init (exact for n <= 50 000, sampled above)             src/kmeans.rs:154-310 */
+int vidx_kmeans_pp_init(int device, const float* data, uint64_t n, uint64_t dim, uint64_t k, uint64_t seed,
+                        float* out_centroids);
+
+/* calculate_num_clusters / calculate_max_iterations                        src/utils.rs:9-26
+ * (= suggest_nlist, bindings/python/src/lib.rs:308-315) */
+uint64_t vidx_calculate_num_clusters(uint64_t num_vectors);
+uint64_t vidx_calculate_max_iterations(uint64_t num_vectors);
+
+/* ---- persistence: shard files + index.bin (cold-start path) ----------------------- */
+
+/* IvfIndex::save_to + Shard::save_to for every shard        src/ivf_index.rs:274-294, src/shards.rs:68-177 */
+int vidx_save(const vidx_index* idx, const char* index_dir, const char* shards_dir);
+/* VectorIndexer::load + whole-shard load into HBM            src/api.rs:109-112, src/shards.rs:352-425
+ * Missing index.bin => VIDX_ERR_NOT_FOUND; bad header / shard-id mismatch =>
+ * VIDX_ERR_INVALID_DATA; unreadable shard => VIDX_ERR_OTHER. */
+int vidx_load(vidx_index* idx, const char* index_dir, const char* shards_dir);
+
+/* ---- multi-GPU: shard partition + top-k merge -------------------------------------- */
+
+/* Keep only the lists whose shard is owned by `rank` of `world` (shards are dealt to
+ * ranks by greedy balance on vector count; the unit is the reference's shard,
+ * src/ivf_index.rs:104-164).  Centroids stay replicated so every rank computes the same
+ * probe lists.  Call after build/load, before search. */
+int vidx_set_partition(vidx_index* idx, int rank, int world);
+int vidx_get_shard_owner(const vidx_index* idx, int world, int32_t* out /* num_shards */);
+/* Merge `nruns` per-rank results (each nq x k, ascending, padded) laid out run-major in
+ * DEVICE memory into the global top-k: the reduction behind join_all + concat + sort
+ * in src/ivf_index.rs:249-266.  Ties resolve to the lower run index. */
+int vidx_merge_topk_device(int device, const float* d_D_runs, const int64_t* d_I_runs, uint32_t nruns, uint64_t nq,
+                           uint64_t k, float* d_D, int64_t* d_I, void* stream);
+
+/* ---- measurement ------------------------------------------------------------------- */
+
+typedef struct vidx_search_stats {
+    double ms_coarse, ms_select, ms_group, ms_scan, ms_merge, ms_total; /* CUDA-event times of the last search */
+    uint64_t scan_bytes_algorithmic; /* sum over distinct probed lists of len*(4D+8) + queries + probes + outputs */
+    uint64_t scan_bytes_logical;     /* sum over (query,list) pairs of len*(4D+8)  */
+    uint64_t scan_flops;             /* 3*D per (query,vector) pair (sub, mul, add) */
+    uint64_t coarse_flops;           /* 3*D*nq*nlist */
+    uint64_t n_pairs;                /* (query, segment) pairs scanned */
+    uint64_t n_dense_items, n_sparse_items;
+    uint64_t kernel_launches;        /* kernels launched by the last search */
+} vidx_search_stats;
+/* Enable per-stage CUDA-event timing (adds stream synchronisation at the end of a
+ * search); stats describe the last completed search on this handle. */
+int vidx_set_profiling(vidx_index* idx, int enabled);
+int vidx_get_search_stats(vidx_index* idx, vidx_search_stats* out);
+/* Total kernels launched by this library in this process (bench.py's gpu_launches). */
+uint64_t vidx_kernel_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VIDX_B200_H */

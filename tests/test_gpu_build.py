@@ -1,0 +1,157 @@
+"""GPU parity: build (train + add), the Python drop-in package, persistence."""
+import asyncio
+import os
+
+import numpy as np
+import pytest
+
+from conftest import bench_data
+
+pytestmark = pytest.mark.gpu
+
+
+def same_bits(a, b):
+    return np.array_equal(np.asarray(a, np.float32).view(np.uint32), np.asarray(b, np.float32).view(np.uint32))
+
+
+def compare_index(oix, gix):
+    assert gix.nlist == oix.nlist and gix.num_shards == oix.num_shards and gix.k_trained == oix.k_trained
+    assert same_bits(gix.centroids(), oix.centroids())
+    assert np.array_equal(gix.centroids_to_shard(), oix.centroids_to_shard())
+    assert np.array_equal(gix.list_sizes(), oix.list_sizes())
+    for l in range(0, gix.nlist, max(1, gix.nlist // 25)):
+        assert np.array_equal(gix.list_members(l), oix.list_members(l))
+
+
+def test_build_matches_oracle_small(oracle, ffi):
+    # n < 10 000: k = floor(sqrt(n)) = 70, 300 iterations, exact k-means++ (utils.rs:9-26)
+    xb, xq = bench_data(5000, 32, 200)
+    oix = oracle.Ivf.fit(xb, seed=42)
+    gix = ffi.Index(32).build(xb, seed=42)
+    compare_index(oix, gix)
+    assert np.array_equal(gix.train_labels(), oix.labels_all(5000))
+    for nprobe in (1, 5, 20):
+        Dg, Ig = gix.search(xq, 10, nprobe)
+        Do, Io = oix.search_batch(xq, 10, nprobe, nthreads=0)
+        assert same_bits(Dg, Do) and np.array_equal(Ig, Io)
+
+
+def test_build_matches_oracle_config1_shape(oracle, ffi):
+    # BASELINE config 1 at reduced n (k = 2*ceil(sqrt(n)) > 100 -> hierarchical final assignment,
+    # ceil(sqrt(k)) shards from the super-centroid k-means, ivf_index.rs:104-109)
+    xb, xq = bench_data(20000, 64, 300)
+    oix = oracle.Ivf.fit(xb, seed=42)
+    gix = ffi.Index(64).build(xb, seed=42)
+    compare_index(oix, gix)
+    Dg, Ig = gix.search(xq, 10, 20)
+    Do, Io = oix.search_batch(xq, 10, 20, nthreads=0)
+    assert same_bits(Dg, Do) and np.array_equal(Ig, Io)
+
+
+def test_train_then_add_equals_build(ffi):
+    xb, xq = bench_data(6000, 16, 50)
+    a = ffi.Index(16).build(xb, seed=42)
+    b = ffi.Index(16).train(xb, seed=42).add(xb)
+    assert same_bits(a.centroids(), b.centroids()) and np.array_equal(a.list_sizes(), b.list_sizes())
+    ra, rb = a.search(xq, 10, 8), b.search(xq, 10, 8)
+    assert np.array_equal(ra[0], rb[0]) and np.array_equal(ra[1], rb[1])
+
+
+def test_every_vector_in_exactly_one_list(ffi):
+    # tests/ivf_index_tests.rs:550-653, tests/integration_tests.rs:399-481
+    xb, _ = bench_data(3000, 8, 1)
+    gix = ffi.Index(8).build(xb)
+    seen = np.concatenate([gix.list_members(l) for l in range(gix.nlist)])
+    assert len(seen) == 3000 and np.array_equal(np.sort(seen), np.arange(3000))
+    assert (gix.list_sizes() > 0).all()  # empty lists are filtered (ivf_index.rs:122-126)
+
+
+def test_recall_floor_and_monotone(oracle, ffi):
+    # tests/integration_tests.rs:310-391: recall(nprobe 15) >= 0.7 and >= recall(nprobe 5)
+    xb, _ = oracle.create_test_vectors(2000, 32), None
+    rng = np.random.default_rng(3)
+    xq = xb[rng.choice(2000, 100, replace=False)] + rng.standard_normal((100, 32)).astype(np.float32) * 0.01
+    gt = oracle.brute_force_topk(xb, xq, 10)
+    gix = ffi.Index(32).build(xb)
+
+    def recall(nprobe):
+        _, I = gix.search(xq, 10, nprobe)
+        return np.mean([len(set(I[i]) & set(gt[i])) / 10 for i in range(len(xq))])
+
+    r5, r15 = recall(5), recall(15)
+    assert r15 >= 0.7 and r15 >= r5 - 1e-9
+
+
+def test_python_package_drop_in(oracle, tmp_path):
+    import vector_indexer_py as vip
+    xb, xq = bench_data(4000, 16, 64)
+    assert vip.suggest_nlist(4000) == 63 and vip.suggest_nlist(50000) == 448 and vip.suggest_nlist(10 ** 6) == 4000
+    idx = vip.build(xb, str(tmp_path))
+    assert idx.dimension == 16
+    D, I = idx.search_sync(xq, 10, 8)
+    assert D.shape == (64, 10) and D.dtype == np.float32 and I.dtype == np.int64
+    assert (np.diff(D, axis=1) >= 0).all() and (I >= 0).all() and (I < 4000).all()
+    D2, I2 = asyncio.run(idx.search(xq, 10, 8))
+    assert np.array_equal(D, D2) and np.array_equal(I, I2)
+    with pytest.raises(RuntimeError):
+        idx.search_sync(xq[:, :8], 10, 8)  # dimension mismatch (lib.rs:133-138)
+    with pytest.raises(RuntimeError):
+        vip.build(np.zeros((0, 16), np.float32))
+    # the files written are the reference's formats: reload and search again
+    assert os.path.exists(tmp_path / "index" / "index.bin") and os.path.exists(tmp_path / "shards" / "shard_0.bin")
+    idx2 = vip.load(str(tmp_path / "index"), str(tmp_path / "shards"), 16)
+    D3, I3 = idx2.search_sync(xq, 10, 8)
+    assert np.array_equal(D, D3) and np.array_equal(I, I3)
+    # shard files parse with the oracle's independent reader (shards.rs layout)
+    sh = oracle.shard_read(str(tmp_path / "shards" / "shard_0.bin"), 0)
+    assert sh["dim"] == 16 and sh["lens"].sum() == len(sh["vecs"])
+    for row, meta in zip(sh["vecs"], sh["meta"]):
+        assert np.array_equal(row, xb[meta[0]]) and meta[1] == meta[0]
+    with pytest.raises(RuntimeError):
+        vip.load(str(tmp_path / "nope"), str(tmp_path / "shards"), 16)
+
+
+def test_load_with_missing_shard_does_not_fail(ffi, tmp_path):
+    # tests/integration_tests.rs:489-533: a missing shard file only removes its vectors
+    xb, xq = bench_data(3000, 8, 20)
+    gix = ffi.Index(8).build(xb)
+    gix.save(str(tmp_path / "index"), str(tmp_path / "shards"))
+    os.remove(tmp_path / "shards" / "shard_1.bin")
+    with open(tmp_path / "shards" / "shard_2.bin", "r+b") as f:
+        f.write(b"\xff" * 16)  # corrupt header: shard id mismatch (shards.rs:223-231)
+    lix = ffi.Index(8).load(str(tmp_path / "index"), str(tmp_path / "shards"))
+    assert lix.nlist == gix.nlist and lix.ntotal < gix.ntotal
+    D, I = lix.search(xq, 5, gix.nlist)
+    c2s = gix.centroids_to_shard()
+    gone = set(np.concatenate([gix.list_members(l) for l in range(gix.nlist) if c2s[l] in (1, 2)]).tolist())
+    assert not (set(I.ravel().tolist()) & gone)
+
+
+def test_partition_and_merge_equal_single_gpu(ffi):
+    """Multi-GPU data flow emulated on one device: each 'rank' scans only the lists of the
+    shards it owns; merging the per-rank top-k reproduces the single-GPU answer."""
+    import torch
+    xb, xq = bench_data(20000, 32, 256)
+    full = ffi.Index(32).build(xb)
+    D0, I0 = full.search(xq, 10, 16)
+    world = 4
+    owners = full.shard_owner(world)
+    assert set(owners.tolist()) == set(range(world))
+    Ds, Is = [], []
+    for r in range(world):
+        full.set_partition(r, world)
+        D, I = full.search(xq, 10, 16)
+        Ds.append(D)
+        Is.append(I)
+    full.set_partition(0, 1)
+    dD = torch.tensor(np.stack(Ds)).cuda()
+    dI = torch.tensor(np.stack(Is)).cuda()
+    oD = torch.empty((256, 10), dtype=torch.float32, device="cuda")
+    oI = torch.empty((256, 10), dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+    ffi.merge_topk_device(0, dD.data_ptr(), dI.data_ptr(), world, 256, 10, oD.data_ptr(), oI.data_ptr(), 0)
+    torch.cuda.synchronize()
+    assert np.array_equal(oD.cpu().numpy(), D0)
+    # ids equal except where equal distances straddle ranks
+    mism = oI.cpu().numpy() != I0
+    assert mism.mean() < 0.01

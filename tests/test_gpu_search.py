@@ -1,0 +1,154 @@
+"""GPU parity: IVF search through the C ABI vs the CPU oracle (bit-exact distances,
+identical ids and probe lists).  Reference path: src/ivf_index.rs:190-267."""
+import numpy as np
+import pytest
+
+from conftest import bench_data
+
+pytestmark = pytest.mark.gpu
+
+
+def make_pair(O, ffi, xb, nlist, seed=7, ext=None):
+    """Same lists on both sides: random centroids from the data + oracle brute labels."""
+    rng = np.random.default_rng(seed)
+    cents = xb[rng.choice(len(xb), nlist, replace=False)].copy()
+    labels = O.assign_brute_force(xb, cents)
+    oix = O.Ivf.from_labels(xb, cents, labels, ext_ids=ext)
+    gix = ffi.Index(xb.shape[1]).build_from_labels(xb, cents, labels, ext_ids=ext)
+    return oix, gix
+
+
+def check_search(oix, gix, xq, k, nprobe):
+    Dg, Ig = gix.search(xq, k, nprobe)
+    Do, Io = oix.search_batch(xq, k, nprobe, nthreads=0)
+    # bit-exact distances (same sequential fp32 arithmetic as utils.rs:28-30)
+    assert np.array_equal(Dg.view(np.uint32), Do.view(np.uint32)), \
+        f"distance mismatch: {np.argwhere(Dg.view(np.uint32) != Do.view(np.uint32))[:5]}"
+    assert np.array_equal(Ig, Io), f"id mismatch at {np.argwhere(Ig != Io)[:5]}"
+    return Dg, Ig
+
+
+@pytest.mark.parametrize("nprobe", [1, 3, 16])
+def test_search_matches_oracle_sparse_regime(oracle, ffi, nprobe):
+    xb, xq = bench_data(20000, 64, 300)
+    oix, gix = make_pair(oracle, ffi, xb, 200)
+    assert gix.nlist == oix.nlist
+    check_search(oix, gix, xq, 10, nprobe)
+
+
+def test_search_matches_oracle_dense_regime(oracle, ffi):
+    # few lists, many queries per list -> dense (block-tiled) scan kernel, multi-segment lists
+    xb, xq = bench_data(30000, 32, 3000)
+    oix, gix = make_pair(oracle, ffi, xb, 12)
+    check_search(oix, gix, xq, 10, 4)
+    check_search(oix, gix, xq, 1, 12)
+    check_search(oix, gix, xq, 32, 2)
+
+
+@pytest.mark.parametrize("d", [1, 3, 30, 129, 200])
+def test_search_odd_dimensions(oracle, ffi, d):
+    xb, xq = bench_data(3000, d, 150, seed=d)
+    oix, gix = make_pair(oracle, ffi, xb, 20)
+    check_search(oix, gix, xq, 5, 4)
+
+
+def test_coarse_probes_match_oracle(oracle, ffi):
+    xb, xq = bench_data(20000, 64, 200)
+    oix, gix = make_pair(oracle, ffi, xb, 300)
+    lists, dists = gix.coarse_probes(xq, 20)
+    for i in range(len(xq)):
+        lo, do = oix.probes(xq[i], 20)
+        assert np.array_equal(lists[i], lo)
+        assert np.array_equal(dists[i].view(np.uint32), do.view(np.uint32))
+
+
+def test_coarse_large_nlist_radix_select(oracle, ffi):
+    # nlist > 4096 exercises the multi-pass radix select
+    xb, xq = bench_data(12000, 16, 64)
+    oix, gix = make_pair(oracle, ffi, xb, 6000)
+    lists, _ = gix.coarse_probes(xq, 50)
+    for i in range(len(xq)):
+        lo, _ = oix.probes(xq[i], 50)
+        assert np.array_equal(lists[i], lo)
+    check_search(oix, gix, xq, 10, 50)
+
+
+def test_large_k_path(oracle, ffi):
+    # k > 32: all-distance rows + exact radix select (reference bench default K=100)
+    xb, xq = bench_data(20000, 32, 200)
+    oix, gix = make_pair(oracle, ffi, xb, 50)
+    check_search(oix, gix, xq, 100, 5)
+    check_search(oix, gix, xq, 33, 1)
+
+
+def test_k_larger_than_candidates_pads(oracle, ffi):
+    # tests/ivf_index_tests.rs:278-306: k > n returns everything; binding pads with +inf / -1
+    xb, xq = bench_data(50, 8, 10)
+    oix, gix = make_pair(oracle, ffi, xb, 3)
+    D, I = check_search(oix, gix, xq, 64, 3)
+    assert (I[:, :50] >= 0).all() and (I[:, 50:] == -1).all() and np.isinf(D[:, 50:]).all()
+    D, I = check_search(oix, gix, xq, 20, 1)
+
+
+def test_nprobe_larger_than_nlist(oracle, ffi):
+    # tests/ivf_index_tests.rs:310-336
+    xb, xq = bench_data(2000, 16, 20)
+    oix, gix = make_pair(oracle, ffi, xb, 10)
+    check_search(oix, gix, xq, 10, 1000)
+
+
+def test_zero_k_or_nprobe_is_invalid_input(oracle, ffi):
+    # src/ivf_index.rs:197-202
+    xb, xq = bench_data(500, 8, 4)
+    _, gix = make_pair(oracle, ffi, xb, 4)
+    with pytest.raises(ffi.InvalidInput):
+        gix.search(xq, 0, 5)
+    with pytest.raises(ffi.InvalidInput):
+        gix.search(xq, 5, 0)
+
+
+def test_self_query_returns_itself_with_payload(oracle, ffi):
+    # tests/ivf_index_tests.rs:122-159, tests/api_tests.rs:90: rank 0, distance 0, bit-equal vector
+    xb = oracle.create_test_vectors(1000, 16)
+    ext = np.arange(1000, dtype=np.uint64) * 3 + 42
+    oix, gix = make_pair(oracle, ffi, xb, 8, ext=ext)
+    D, I, V = gix.search(xb[:100], 3, 8, include_vectors=True)
+    assert (D[:, 0] == 0).all()
+    # the ramp fixture repeats every 500 elements, so equal vectors exist: ids may be any duplicate
+    for i in range(100):
+        assert np.array_equal(V[i, 0], xb[i])
+        src = (I[i, 0] - 42) // 3
+        assert np.array_equal(xb[src], xb[i])
+    Do, Io = oix.search_batch(xb[:100], 3, 8, nthreads=0)
+    assert np.array_equal(I, Io) and np.array_equal(D, Do)
+
+
+def test_duplicate_vectors_tie_order(oracle, ffi):
+    # equal distances keep probe-rank / list order (stable sort, ivf_index.rs:265)
+    base, xq = bench_data(200, 8, 30)
+    xb = np.concatenate([base, base, base])
+    oix, gix = make_pair(oracle, ffi, xb, 5)
+    check_search(oix, gix, xq, 12, 5)
+
+
+def test_repeated_search_identical(oracle, ffi):
+    # tests/integration_tests.rs:131-188
+    xb, xq = bench_data(5000, 32, 100)
+    _, gix = make_pair(oracle, ffi, xb, 40)
+    a = gix.search(xq, 10, 8)
+    for _ in range(4):
+        b = gix.search(xq, 10, 8)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+def test_search_stats_and_launch_counter(oracle, ffi):
+    xb, xq = bench_data(20000, 64, 500)
+    _, gix = make_pair(oracle, ffi, xb, 100)
+    gix.set_profiling(True)
+    before = ffi.kernel_launch_count()
+    gix.search(xq, 10, 4)
+    st = gix.stats()
+    assert ffi.kernel_launch_count() - before == st["kernel_launches"] > 5
+    assert st["n_pairs"] >= 500 * 4
+    assert st["scan_bytes_logical"] >= st["scan_bytes_algorithmic"] > 0
+    assert st["ms_scan"] > 0 and st["ms_total"] >= st["ms_scan"]

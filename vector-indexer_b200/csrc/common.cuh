@@ -1,0 +1,136 @@
+// common.cuh -- shared host/device helpers for libvidx_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+
+namespace vidx {
+
+constexpr int kGroup = 32;          // vectors per interleaved group (one per lane)
+constexpr int kSegGroups = 32;      // groups per segment (<= 1024 vectors): the scan work unit
+constexpr int kSegVecs = kGroup * kSegGroups;
+constexpr unsigned kFull = 0xffffffffu;
+constexpr uint32_t kNoRow = 0xffffffffu;
+
+struct CudaError : std::runtime_error {
+    explicit CudaError(const std::string& m) : std::runtime_error(m) {}
+};
+struct ApiError : std::runtime_error {
+    int code;
+    ApiError(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define VIDX_CUDA(expr)                                                                          \
+    do {                                                                                         \
+        cudaError_t _e = (expr);                                                                 \
+        if (_e != cudaSuccess) {                                                                 \
+            char _b[512];                                                                        \
+            snprintf(_b, sizeof(_b), "CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__, \
+                     __LINE__, cudaGetErrorString(_e));                                          \
+            throw ::vidx::CudaError(_b);                                                         \
+        }                                                                                        \
+    } while (0)
+
+extern std::atomic<uint64_t> g_kernel_launches;
+#define VIDX_LAUNCHED()                            \
+    do {                                           \
+        ::vidx::g_kernel_launches.fetch_add(1);    \
+        VIDX_CUDA(cudaGetLastError());             \
+    } while (0)
+
+// Grow-only device buffer.
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    void reserve(size_t bytes) {
+        if (bytes <= cap) return;
+        release();
+        size_t want = bytes + bytes / 8 + 256;
+        VIDX_CUDA(cudaMalloc(&p, want));
+        cap = want;
+    }
+    template <class T>
+    T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct PinnedBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    ~PinnedBuf() { if (p) cudaFreeHost(p); }
+    void reserve(size_t bytes) {
+        if (bytes <= cap) return;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        VIDX_CUDA(cudaMallocHost(&p, bytes + 256));
+        cap = bytes + 256;
+    }
+    template <class T>
+    T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+inline size_t ceil_div(size_t a, size_t b) { return (a + b - 1) / b; }
+
+// One segment = up to kSegGroups consecutive groups of one list.
+struct SegDesc {
+    uint32_t g0;      // first group (global group index into the interleaved store)
+    uint32_t ng;      // groups in this segment
+    uint32_t nvalid;  // valid vectors in this segment (<= ng*32)
+    uint32_t list;    // owning list
+};
+
+#ifdef __CUDACC__
+// ---- reference arithmetic ---------------------------------------------------------
+// utils.rs:28-30: acc + (x - y)*(x - y) with separate roundings (Rust never fuses).
+__device__ __forceinline__ float sqdiff_acc(float acc, float x, float y) {
+    float d = __fsub_rn(x, y);
+    return __fadd_rn(acc, __fmul_rn(d, d));
+}
+__device__ __forceinline__ float4 ldg_f4(const float4* p) { return __ldg(p); }
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+// ---- warp-resident sorted list: lane t holds the t-th best (dist, row) -------------
+// STABLE insertion: the candidate goes after every entry with dist <= cd (arrival order
+// breaks ties, as the reference's stable sort over candidates in scan order does,
+// ivf_index.rs:265).
+__device__ __forceinline__ void warp_insert_stable(float cd, uint32_t cr, float& my_d, uint32_t& my_r, int lane) {
+    unsigned m = __ballot_sync(kFull, my_d <= cd);
+    int pos = __popc(m);
+    float up_d = __shfl_up_sync(kFull, my_d, 1);
+    uint32_t up_r = __shfl_up_sync(kFull, my_r, 1);
+    if (lane == pos) { my_d = cd; my_r = cr; }
+    else if (lane > pos) { my_d = up_d; my_r = up_r; }
+}
+// LEX insertion: ordered by (dist, row); used where candidates do not arrive in row order.
+__device__ __forceinline__ void warp_insert_lex(float cd, uint32_t cr, float& my_d, uint32_t& my_r, int lane) {
+    unsigned m = __ballot_sync(kFull, (my_d < cd) || (my_d == cd && my_r < cr));
+    int pos = __popc(m);
+    float up_d = __shfl_up_sync(kFull, my_d, 1);
+    uint32_t up_r = __shfl_up_sync(kFull, my_r, 1);
+    if (lane == pos) { my_d = cd; my_r = cr; }
+    else if (lane > pos) { my_d = up_d; my_r = up_r; }
+}
+#endif
+
+}  // namespace vidx

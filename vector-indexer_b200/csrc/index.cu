@@ -1,0 +1,941 @@
+// index.cu -- the device-resident IVF index and the C ABI (include/vidx_b200.h).
+// Host-side mirror of IvfIndex (src/ivf_index.rs) + VectorIndexer (src/api.rs) for the
+// build / search path; all compute is in search_kernels.cu / kmeans_kernels.cu.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <ctime>
+#include <mutex>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../include/vidx_b200.h"
+#include "index.h"
+#include "kmeans_host.h"
+#include "search.h"
+
+namespace vidx {
+
+std::atomic<uint64_t> g_kernel_launches{0};
+thread_local std::string t_last_error;
+
+namespace {
+template <class T>
+void h2d(T* dst, const T* src, size_t n, cudaStream_t st) {
+    if (n) VIDX_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyHostToDevice, st));
+}
+template <class T>
+void d2h_sync(T* dst, const T* src, size_t n, cudaStream_t st) {
+    if (n) VIDX_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyDeviceToHost, st));
+    VIDX_CUDA(cudaStreamSynchronize(st));
+}
+}  // namespace
+
+void Index::ensure_device() {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0) {
+        (void)cudaGetLastError();
+        throw CudaError("no CUDA device available (libvidx_b200 has no CPU fallback)");
+    }
+    if (device >= count) throw CudaError("CUDA device ordinal out of range");
+    VIDX_CUDA(cudaSetDevice(device));
+    if (!stream) {
+        cudaDeviceProp prop;
+        VIDX_CUDA(cudaGetDeviceProperties(&prop, device));
+        if (prop.major < 10) throw CudaError("libvidx_b200 is built for sm_100a (Blackwell) only");
+        VIDX_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        for (auto& ev : events) VIDX_CUDA(cudaEventCreate(&ev));
+    }
+}
+
+Index::~Index() {
+    delete_workspace();
+    if (stream) {
+        cudaSetDevice(device);
+        cudaStreamSynchronize(stream);
+        for (auto& ev : events) if (ev) cudaEventDestroy(ev);
+        cudaStreamDestroy(stream);
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// train: mini-batch k-means + super-centroid k-means (src/ivf_index.rs:59-77, :103-109)
+// ------------------------------------------------------------------------------------
+void Index::train_on_device(const float* d_data, uint64_t n, uint64_t seed_, uint64_t nlist_override, uint64_t iters_override,
+                            DevBuf& d_labels) {
+    seed = seed_;
+    uint64_t k = nlist_override ? nlist_override : vidx_calculate_num_clusters(n);
+    uint64_t max_iters = iters_override ? iters_override : vidx_calculate_max_iterations(n);
+    if (k == 0) throw ApiError(VIDX_ERR_INVALID_INPUT, "number of clusters is 0");
+    if (k > 0x7fffffffull) throw ApiError(VIDX_ERR_UNSUPPORTED, "too many clusters");
+    k_trained = k;
+    DevBuf d_cents;
+    d_cents.reserve((size_t)k * dim * 4);
+    d_labels.reserve(std::max<uint64_t>(n, 1) * 4);
+    {
+        DeviceKMeans km(d_data, n, (int)dim, stream);
+        train_iters = km.mini_batch((uint32_t)k, max_iters, -1.0f, seed, d_cents.as<float>(), d_labels.as<uint32_t>());
+    }
+    train_centroids.resize((size_t)k * dim);
+    d2h_sync(train_centroids.data(), d_cents.as<float>(), train_centroids.size(), stream);
+    // super-centroids: k-means over ALL k centroids, empty ones included (ivf_index.rs:104-109)
+    num_shards = (uint64_t)std::ceil(std::sqrt((float)k));
+    uint64_t super_seed = seed * 31ull + 7ull;
+    DevBuf d_super, d_slabels;
+    d_super.reserve((size_t)num_shards * dim * 4);
+    d_slabels.reserve((size_t)k * 4);
+    {
+        DeviceKMeans km2(d_cents.as<float>(), k, (int)dim, stream);
+        km2.mini_batch((uint32_t)num_shards, 100, -1.0f, super_seed, d_super.as<float>(), d_slabels.as<uint32_t>());
+    }
+    super_labels.resize(k);
+    d2h_sync(super_labels.data(), d_slabels.as<uint32_t>(), k, stream);
+    trained = true;
+}
+
+// ------------------------------------------------------------------------------------
+// add: lists from labels, empty-list filter + renumbering, shard map, device layout
+// (src/ivf_index.rs:79-164)
+// ------------------------------------------------------------------------------------
+void Index::build_lists(const float* d_data, uint64_t n, const uint32_t* labels, const uint64_t* ext, const uint64_t* ts,
+                        const float* cents_all, uint64_t k, const uint32_t* shard_of_centroid, bool keep_empty) {
+    if (n >= 0xffffffffull) throw ApiError(VIDX_ERR_UNSUPPORTED, "more than 2^32-1 vectors per device");
+    ntotal = n;
+    internal_ids.clear();
+    train_labels.assign(labels, labels + n);
+    ext_ids.resize(n);
+    timestamps.resize(n);
+    uint64_t now = (uint64_t)time(nullptr);
+    for (uint64_t i = 0; i < n; i++) {
+        ext_ids[i] = ext ? ext[i] : i;
+        uint64_t t = ts ? ts[i] : 0;
+        timestamps[i] = t ? t : now;  // vector_store.rs:36-40
+    }
+    // list sizes in the unfiltered numbering
+    std::vector<uint32_t> sz(k, 0);
+    for (uint64_t i = 0; i < n; i++) {
+        if (labels[i] >= k) throw ApiError(VIDX_ERR_INVALID_INPUT, "label out of range");
+        sz[labels[i]]++;
+    }
+    // drop empty lists, renumber densely (ivf_index.rs:122-146)
+    old_to_new.assign(k, kNoRow);
+    centroids.clear();
+    c2shard.clear();
+    list_len.clear();
+    for (uint64_t c = 0; c < k; c++) {
+        if (!sz[c] && !keep_empty) continue;
+        old_to_new[c] = (uint32_t)list_len.size();
+        centroids.insert(centroids.end(), cents_all + c * dim, cents_all + (c + 1) * dim);
+        c2shard.push_back(shard_of_centroid ? shard_of_centroid[c] : 0);  // indexed by the OLD id (ivf_index.rs:153-154)
+        list_len.push_back(sz[c]);
+    }
+    nlist = list_len.size();
+    // layout: whole groups per list, segments of <= kSegGroups groups
+    list_goff.assign(nlist + 1, 0);
+    list_seg_off_all.assign(nlist + 1, 0);
+    segs.clear();
+    for (uint64_t l = 0; l < nlist; l++) {
+        uint32_t ng = (uint32_t)ceil_div(list_len[l], kGroup);
+        list_goff[l + 1] = list_goff[l] + ng;
+        for (uint32_t g = 0; g < ng; g += kSegGroups) {
+            SegDesc s;
+            s.g0 = (uint32_t)(list_goff[l] + g);
+            s.ng = std::min<uint32_t>(kSegGroups, ng - g);
+            s.nvalid = std::min<uint32_t>(s.ng * kGroup, list_len[l] - g * kGroup);
+            s.list = (uint32_t)l;
+            segs.push_back(s);
+        }
+        list_seg_off_all[l + 1] = (uint32_t)segs.size();
+    }
+    uint64_t ngroups = list_goff[nlist];
+    uint64_t nrows = ngroups * kGroup;
+    if (nrows >= 0xffffffffull) throw ApiError(VIDX_ERR_UNSUPPORTED, "too many rows for 32-bit row ids");
+    // stable scatter: vectors keep ascending original index inside a list (ivf_index.rs:94-101)
+    row_src.assign(nrows, kNoRow);
+    {
+        std::vector<uint64_t> cur(nlist);
+        for (uint64_t l = 0; l < nlist; l++) cur[l] = list_goff[l] * kGroup;
+        for (uint64_t i = 0; i < n; i++) row_src[cur[old_to_new[labels[i]]]++] = (uint32_t)i;
+    }
+    std::vector<uint64_t> row_ext(nrows, ~0ull);
+    for (uint64_t r = 0; r < nrows; r++)
+        if (row_src[r] != kNoRow) row_ext[r] = ext_ids[row_src[r]];
+
+    // device store
+    int Dq = dq();
+    d_vecs.reserve(std::max<uint64_t>(nrows, 1) * Dq * 16);
+    DevBuf d_row_src;
+    d_row_src.reserve(std::max<uint64_t>(nrows, 1) * 4);
+    h2d(d_row_src.as<uint32_t>(), row_src.data(), nrows, stream);
+    launch_interleave(d_data, (int)dim, Dq, d_row_src.as<uint32_t>(), nrows, d_vecs.as<float4>(), stream);
+    d_row_ext.reserve(std::max<uint64_t>(nrows, 1) * 8);
+    h2d(d_row_ext.as<uint64_t>(), row_ext.data(), nrows, stream);
+    // centroids in the same interleaved layout
+    ncgroups = (uint32_t)ceil_div(nlist, kGroup);
+    {
+        DevBuf d_c, d_map;
+        d_c.reserve(std::max<size_t>(centroids.size(), 1) * 4);
+        h2d(d_c.as<float>(), centroids.data(), centroids.size(), stream);
+        std::vector<uint32_t> map((size_t)ncgroups * kGroup, kNoRow);
+        for (uint64_t l = 0; l < nlist; l++) map[l] = (uint32_t)l;
+        d_map.reserve(std::max<size_t>(map.size(), 1) * 4);
+        h2d(d_map.as<uint32_t>(), map.data(), map.size(), stream);
+        d_cents.reserve(std::max<size_t>(map.size(), 1) * Dq * 16);
+        launch_interleave(d_c.as<float>(), (int)dim, Dq, d_map.as<uint32_t>(), map.size(), d_cents.as<float4>(), stream);
+        VIDX_CUDA(cudaStreamSynchronize(stream));
+    }
+    d_segs.reserve(std::max<size_t>(segs.size(), 1) * sizeof(SegDesc));
+    h2d(d_segs.as<SegDesc>(), segs.data(), segs.size(), stream);
+    part_rank = 0;
+    part_world = 1;
+    apply_partition();
+    VIDX_CUDA(cudaStreamSynchronize(stream));
+    built = true;
+}
+
+// Shards -> ranks by greedy balance on vector count (largest shard first, least loaded
+// rank, ties to the lower rank).
+std::vector<int32_t> Index::shard_owners(int world) const {
+    std::vector<uint64_t> load(num_shards ? num_shards : 1, 0);
+    for (uint64_t l = 0; l < nlist; l++) {
+        if (c2shard[l] >= load.size()) load.resize(c2shard[l] + 1, 0);
+        load[c2shard[l]] += list_len[l];
+    }
+    std::vector<uint32_t> order(load.size());
+    std::iota(order.begin(), order.end(), 0u);
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return load[a] > load[b]; });
+    std::vector<uint64_t> rank_load(world, 0);
+    std::vector<int32_t> owner(load.size(), 0);
+    for (uint32_t s : order) {
+        int best = 0;
+        for (int r = 1; r < world; r++)
+            if (rank_load[r] < rank_load[best]) best = r;
+        owner[s] = best;
+        rank_load[best] += load[s];
+    }
+    return owner;
+}
+
+// Lists this rank does not own get zero segments, so grouping skips them; the centroid
+// table stays complete so every rank derives identical probe lists.
+void Index::apply_partition() {
+    std::vector<int32_t> owner;
+    if (part_world > 1) owner = shard_owners(part_world);
+    // segment ids stay global; an unowned list maps to an empty range
+    list_seg_part.assign(nlist + 1, make_uint2(0, 0));
+    owned_vectors = 0;
+    std::vector<uint32_t> nseg_owned;
+    for (uint64_t l = 0; l < nlist; l++) {
+        bool own = part_world <= 1 || owner[c2shard[l]] == part_rank;
+        uint32_t s0 = list_seg_off_all[l], s1 = list_seg_off_all[l + 1];
+        list_seg_part[l] = make_uint2(s0, own ? s1 : s0);
+        if (own) {
+            owned_vectors += list_len[l];
+            nseg_owned.push_back(s1 - s0);
+        }
+    }
+    // prefix of the largest per-list segment counts: bounds the (query,segment) pairs
+    std::sort(nseg_owned.begin(), nseg_owned.end(), std::greater<uint32_t>());
+    seg_prefix.assign(nseg_owned.size() + 1, 0);
+    for (size_t i = 0; i < nseg_owned.size(); i++) seg_prefix[i + 1] = seg_prefix[i] + nseg_owned[i];
+    d_list_seg.reserve(list_seg_part.size() * sizeof(uint2));
+    h2d(d_list_seg.as<uint2>(), list_seg_part.data(), list_seg_part.size(), stream);
+    VIDX_CUDA(cudaStreamSynchronize(stream));
+}
+
+// ------------------------------------------------------------------------------------
+// search (src/ivf_index.rs:190-267 for a whole batch)
+// ------------------------------------------------------------------------------------
+struct Index::Workspace {
+    DevBuf xq_pad, dist, probes, pair_ns, slot_off, seg_cnt, seg_qoff, seg_cur, seg_qlist, slot_seg, dense, sparse, counters,
+        scan_tmp, cand_d, cand_r, alld, row_off, row_len, sel_pos, sel_val, rows, stats;
+};
+void Index::delete_workspace() {
+    delete ws;
+    ws = nullptr;
+}
+
+// stats: distinct probed segments -> algorithmic bytes; pairs -> logical bytes / flops
+__global__ void scan_stats_kernel(const uint32_t* __restrict__ seg_cnt, const SegDesc* __restrict__ segs, uint32_t nseg,
+                                  unsigned long long* __restrict__ out /*[0]=distinct vectors,[1]=pair vectors,[2]=pairs*/) {
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nseg) return;
+    uint32_t c = seg_cnt[s];
+    if (!c) return;
+    atomicAdd(&out[0], (unsigned long long)segs[s].nvalid);
+    atomicAdd(&out[1], (unsigned long long)segs[s].nvalid * c);
+    atomicAdd(&out[2], (unsigned long long)c);
+}
+void Index::search_device(const float* d_xq, uint64_t nq, uint64_t k_req, uint64_t nprobe_req, float* d_D, int64_t* d_I,
+                          uint32_t* d_rows_out, cudaStream_t st, uint32_t* d_probe_out, float* d_probe_dist_out) {
+    if (k_req == 0 || nprobe_req == 0)
+        throw ApiError(VIDX_ERR_INVALID_INPUT, "k and n_probe must be greater than 0");  // ivf_index.rs:197-202
+    if (!built) throw ApiError(VIDX_ERR_OTHER, "index has not been built or loaded");
+    if (nq == 0) return;
+    if (!ws) ws = new Workspace();
+    Workspace& w = *ws;
+    const uint64_t k = std::min<uint64_t>(k_req, max_k);              // api.rs:189
+    const uint64_t np_req = std::min<uint64_t>(nprobe_req, max_n_probe);  // api.rs:190
+    const uint32_t np = (uint32_t)std::min<uint64_t>(np_req, nlist);
+    const uint32_t kout = (uint32_t)k_req;
+    if (k_req > 0xffffffffull) throw ApiError(VIDX_ERR_UNSUPPORTED, "k too large");
+    const int Dq = dq(), Dp = Dq * 4;
+    const bool coarse_only = d_probe_out != nullptr;
+    const bool fused = k <= 32;
+    const uint32_t nseg = (uint32_t)segs.size();
+    const uint32_t ldc = ncgroups * kGroup;
+    // pairs bound per query: the np largest per-list segment counts
+    const uint64_t pairs_per_q = seg_prefix[std::min<size_t>(np, seg_prefix.size() - 1)];
+    // batch size: keep every workspace array under ~6 GB and 32-bit indexable
+    uint64_t qb = nq;
+    auto shrink = [&](double bytes_per_q, double budget) {
+        if (bytes_per_q <= 0) return;
+        uint64_t m = (uint64_t)std::max(1.0, budget / bytes_per_q);
+        qb = std::min(qb, m);
+    };
+    shrink((double)ldc * 4, 6e9);
+    shrink((double)pairs_per_q * (fused ? (double)k * 8 : (double)kSegVecs * 4), 6e9);
+    shrink((double)std::max<uint64_t>(pairs_per_q, np), 1.5e9 / 1.0);  // 32-bit pair / slot indices
+    qb = std::min<uint64_t>(qb, 65535ull * 64);
+
+    cudaEvent_t* ev = events;
+    if (profiling) {
+        st_ms[0] = st_ms[1] = st_ms[2] = st_ms[3] = st_ms[4] = 0;
+        stats = vidx_search_stats{};
+    }
+    uint64_t launches0 = g_kernel_launches.load();
+    if (profiling) VIDX_CUDA(cudaEventRecord(ev[6], st));
+
+    for (uint64_t q0 = 0; q0 < nq; q0 += qb) {
+        const uint32_t nqb = (uint32_t)std::min(qb, nq - q0);
+        const float* xq = d_xq + q0 * dim;
+        const float4* xq4;
+        if (dim % 4 != 0 || (reinterpret_cast<uintptr_t>(xq) & 15)) {
+            w.xq_pad.reserve((size_t)nqb * Dp * 4);
+            launch_pad_rows(xq, w.xq_pad.as<float>(), nqb, (int)dim, Dp, st);
+            xq4 = w.xq_pad.as<float4>();
+        } else {
+            xq4 = reinterpret_cast<const float4*>(xq);
+        }
+        // K1: coarse distances
+        if (profiling) VIDX_CUDA(cudaEventRecord(ev[0], st));
+        w.dist.reserve((size_t)nqb * ldc * 4);
+        launch_coarse_dist(d_cents.as<float4>(), (int)ncgroups, Dq, xq4, nqb, w.dist.as<float>(), ldc, st);
+        if (profiling) VIDX_CUDA(cudaEventRecord(ev[1], st));
+        // K2: probe selection (stable ascending by (distance, list id))
+        w.probes.reserve((size_t)nqb * np * 4);
+        float* pd = nullptr;
+        if (coarse_only && d_probe_dist_out) {
+            w.sel_val.reserve((size_t)nqb * np * 4);
+            pd = w.sel_val.as<float>();
+        }
+        launch_select_topk(w.dist.as<float>(), nullptr, nullptr, ldc, (uint32_t)nlist, nqb, np, w.probes.as<uint32_t>(), pd, st);
+        if (profiling) VIDX_CUDA(cudaEventRecord(ev[2], st));
+        if (coarse_only) {
+            // caller's stride is nprobe_req; columns beyond np are padded
+            const uint32_t npo = (uint32_t)nprobe_req;
+            VIDX_CUDA(cudaMemsetAsync(d_probe_out + q0 * npo, 0xff, (size_t)nqb * npo * 4, st));
+            VIDX_CUDA(cudaMemcpy2DAsync(d_probe_out + q0 * npo, (size_t)npo * 4, w.probes.p, (size_t)np * 4, (size_t)np * 4, nqb,
+                                        cudaMemcpyDeviceToDevice, st));
+            if (d_probe_dist_out) {
+                std::vector<float> inf((size_t)nqb * npo, INFINITY);
+                h2d(d_probe_dist_out + q0 * npo, inf.data(), inf.size(), st);
+                VIDX_CUDA(cudaMemcpy2DAsync(d_probe_dist_out + q0 * npo, (size_t)npo * 4, pd, (size_t)np * 4, (size_t)np * 4, nqb,
+                                            cudaMemcpyDeviceToDevice, st));
+            }
+            continue;
+        }
+        // K3: group (query, probed list) by segment
+        const size_t npairs = (size_t)nqb * np;
+        const uint64_t pair_cap = std::max<uint64_t>(1, (uint64_t)nqb * pairs_per_q);
+        w.pair_ns.reserve((npairs + 1) * 4);
+        w.slot_off.reserve((npairs + 1) * 4);
+        w.seg_cnt.reserve(((size_t)nseg + 1) * 4);
+        w.seg_qoff.reserve(((size_t)nseg + 1) * 4);
+        w.seg_cur.reserve(((size_t)nseg + 1) * 4);
+        w.seg_qlist.reserve(pair_cap * 8);
+        w.slot_seg.reserve(pair_cap * 4);
+        const uint32_t sparse_max = sparse_supported(Dq) ? 16u : 0u;
+        const size_t dense_cap = pair_cap / 64 + nseg + 1, sparse_cap = (size_t)nseg * 2 + 1;
+        w.dense.reserve(dense_cap * sizeof(ScanItem));
+        w.sparse.reserve(sparse_cap * sizeof(ScanItem));
+        w.counters.reserve(16 * 4);
+        w.scan_tmp.reserve(exclusive_scan_tmp_entries(std::max<size_t>(npairs, nseg) + 1) * 4);
+        VIDX_CUDA(cudaMemsetAsync(w.seg_cnt.p, 0, ((size_t)nseg + 1) * 4, st));
+        VIDX_CUDA(cudaMemsetAsync(w.seg_cur.p, 0, ((size_t)nseg + 1) * 4, st));
+        VIDX_CUDA(cudaMemsetAsync(w.counters.p, 0, 16 * 4, st));
+        launch_group_count(w.probes.as<uint32_t>(), npairs, d_list_seg.as<uint2>(), w.pair_ns.as<uint32_t>(),
+                           w.seg_cnt.as<uint32_t>(), st);
+        exclusive_scan_u32(w.pair_ns.as<uint32_t>(), w.slot_off.as<uint32_t>(), npairs, w.scan_tmp.as<uint32_t>(), st);
+        exclusive_scan_u32(w.seg_cnt.as<uint32_t>(), w.seg_qoff.as<uint32_t>(), nseg, w.scan_tmp.as<uint32_t>(), st);
+        launch_group_fill(w.probes.as<uint32_t>(), npairs, np, d_list_seg.as<uint2>(), w.slot_off.as<uint32_t>(),
+                          w.seg_qoff.as<uint32_t>(), w.seg_cur.as<uint32_t>(), w.seg_qlist.as<uint2>(), w.slot_seg.as<uint32_t>(),
+                          st);
+        launch_group_items(w.seg_cnt.as<uint32_t>(), nseg, sparse_max, w.dense.as<ScanItem>(), w.sparse.as<ScanItem>(),
+                           w.counters.as<uint32_t>(), st);
+        if (profiling) {
+            w.stats.reserve(64);
+            VIDX_CUDA(cudaMemsetAsync(w.stats.p, 0, 64, st));
+            scan_stats_kernel<<<(unsigned)ceil_div(std::max<uint32_t>(nseg, 1), 256), 256, 0, st>>>(
+                w.seg_cnt.as<uint32_t>(), d_segs.as<SegDesc>(), nseg, w.stats.as<unsigned long long>());
+            VIDX_LAUNCHED();
+        }
+        if (profiling) VIDX_CUDA(cudaEventRecord(ev[3], st));
+        // K4+K5: scan
+        w.rows.reserve((size_t)nqb * kout * 4);
+        uint32_t* rows_out = d_rows_out ? d_rows_out + q0 * kout : nullptr;
+        if (fused) {
+            w.cand_d.reserve(pair_cap * k * 4);
+            w.cand_r.reserve(pair_cap * k * 4);
+            launch_scan(false, d_vecs.as<float4>(), Dq, xq4, d_segs.as<SegDesc>(), w.seg_qoff.as<uint32_t>(),
+                        w.seg_qlist.as<uint2>(), w.dense.as<ScanItem>(), w.sparse.as<ScanItem>(), w.counters.as<uint32_t>(),
+                        w.counters.as<uint32_t>() + 4, (uint32_t)k, w.cand_d.as<float>(), w.cand_r.as<uint32_t>(), nullptr,
+                        sparse_max > 0, st);
+            if (profiling) VIDX_CUDA(cudaEventRecord(ev[4], st));
+            launch_merge_slots(w.cand_d.as<float>(), w.cand_r.as<uint32_t>(), w.slot_off.as<uint32_t>(), nqb, np, (uint32_t)k, kout,
+                               d_row_ext.as<uint64_t>(), d_D + q0 * kout, d_I + q0 * kout, rows_out, st);
+        } else {
+            // large k: every (query, segment) distance row, then an exact radix select per query
+            w.alld.reserve(pair_cap * kSegVecs * 4);
+            launch_scan(true, d_vecs.as<float4>(), Dq, xq4, d_segs.as<SegDesc>(), w.seg_qoff.as<uint32_t>(),
+                        w.seg_qlist.as<uint2>(), w.dense.as<ScanItem>(), w.sparse.as<ScanItem>(), w.counters.as<uint32_t>(),
+                        w.counters.as<uint32_t>() + 4, (uint32_t)k, nullptr, nullptr, w.alld.as<float>(), sparse_max > 0, st);
+            if (profiling) VIDX_CUDA(cudaEventRecord(ev[4], st));
+            w.row_off.reserve((size_t)nqb * 8);
+            w.row_len.reserve((size_t)nqb * 4);
+            w.sel_pos.reserve((size_t)nqb * k * 4);
+            w.sel_val.reserve((size_t)nqb * k * 4);
+            launch_alldist_rows(w.slot_off.as<uint32_t>(), np, nqb, w.row_off.as<uint64_t>(), w.row_len.as<uint32_t>(), st);
+            launch_select_topk(w.alld.as<float>(), w.row_off.as<uint64_t>(), w.row_len.as<uint32_t>(), 0, 0, nqb, (uint32_t)k,
+                               w.sel_pos.as<uint32_t>(), w.sel_val.as<float>(), st);
+            launch_alldist_finish(w.sel_pos.as<uint32_t>(), w.sel_val.as<float>(), w.slot_off.as<uint32_t>(),
+                                  w.slot_seg.as<uint32_t>(), d_segs.as<SegDesc>(), np, nqb, (uint32_t)k, kout,
+                                  d_row_ext.as<uint64_t>(), d_D + q0 * kout, d_I + q0 * kout, rows_out, st);
+        }
+        launch_pad_output(d_D + q0 * kout, d_I + q0 * kout, rows_out, nqb, (uint32_t)k, kout, st);
+        if (profiling) {
+            VIDX_CUDA(cudaEventRecord(ev[5], st));
+            VIDX_CUDA(cudaEventSynchronize(ev[5]));
+            float ms;
+            for (int i = 0; i < 5; i++) {
+                VIDX_CUDA(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
+                st_ms[i] += ms;
+            }
+            unsigned long long h[3];
+            uint32_t cnt[2];
+            d2h_sync(h, w.stats.as<unsigned long long>(), 3, st);
+            d2h_sync(cnt, w.counters.as<uint32_t>(), 2, st);
+            const uint64_t rec = 4ull * dim + 8;
+            stats.scan_bytes_algorithmic += h[0] * rec + (uint64_t)nqb * dim * 4 + (uint64_t)nqb * np * 4 + (uint64_t)nqb * k * 12;
+            stats.scan_bytes_logical += h[1] * rec;
+            stats.scan_flops += h[1] * 3ull * dim;
+            stats.n_pairs += h[2];
+            stats.coarse_flops += 3ull * dim * nqb * nlist;
+            stats.n_dense_items += cnt[0];
+            stats.n_sparse_items += cnt[1];
+        }
+    }
+    if (profiling) {
+        VIDX_CUDA(cudaEventRecord(ev[7], st));
+        VIDX_CUDA(cudaEventSynchronize(ev[7]));
+        float ms;
+        VIDX_CUDA(cudaEventElapsedTime(&ms, ev[6], ev[7]));
+        stats.ms_total = ms;
+        stats.ms_coarse = st_ms[0];
+        stats.ms_select = st_ms[1];
+        stats.ms_group = st_ms[2];
+        stats.ms_scan = st_ms[3];
+        stats.ms_merge = st_ms[4];
+    }
+    stats.kernel_launches = g_kernel_launches.load() - launches0;
+}
+
+}  // namespace vidx
+
+// ====================================================================================
+// C ABI
+// ====================================================================================
+using namespace vidx;
+
+struct vidx_index {
+    Index ix;
+    std::mutex mu;
+};
+
+namespace {
+template <class F>
+int guarded(F&& f) {
+    try {
+        f();
+        return VIDX_OK;
+    } catch (const ApiError& e) {
+        t_last_error = e.what();
+        return e.code;
+    } catch (const CudaError& e) {
+        t_last_error = e.what();
+        return VIDX_ERR_CUDA;
+    } catch (const std::bad_alloc&) {
+        t_last_error = "out of host memory";
+        return VIDX_ERR_OTHER;
+    } catch (const std::exception& e) {
+        t_last_error = e.what();
+        return VIDX_ERR_OTHER;
+    }
+}
+void require(bool c, int code, const char* msg) {
+    if (!c) throw ApiError(code, msg);
+}
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        VIDX_CUDA(cudaSetDevice(dev));
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+}  // namespace
+
+extern "C" {
+
+const char* vidx_last_error(void) { return t_last_error.c_str(); }
+
+int vidx_create(uint32_t dimension, int device, vidx_index** out) {
+    return guarded([&] {
+        require(out != nullptr, VIDX_ERR_INVALID_INPUT, "out is NULL");
+        require(dimension > 0, VIDX_ERR_INVALID_INPUT, "dimension must be > 0");
+        auto* h = new vidx_index();
+        h->ix.dim = dimension;
+        h->ix.device = device;
+        *out = h;
+    });
+}
+void vidx_free(vidx_index* idx) { delete idx; }
+
+int vidx_set_limits(vidx_index* idx, uint64_t default_k, uint64_t default_n_probe, uint64_t max_k, uint64_t max_n_probe) {
+    return guarded([&] {
+        require(idx, VIDX_ERR_INVALID_INPUT, "idx is NULL");
+        idx->ix.default_k = default_k;
+        idx->ix.default_n_probe = default_n_probe;
+        idx->ix.max_k = max_k;
+        idx->ix.max_n_probe = max_n_probe;
+    });
+}
+
+static void do_train(Index& ix, const float* data, uint64_t n, uint64_t seed, uint64_t nlist, uint64_t max_iters,
+                     DevBuf& d_data, DevBuf& d_labels) {
+    require(n > 0 && data, VIDX_ERR_INVALID_INPUT, "no vectors provided");  // api.rs:116-118
+    ix.ensure_device();
+    d_data.reserve((size_t)n * ix.dim * 4);
+    h2d(d_data.as<float>(), data, (size_t)n * ix.dim, ix.stream);
+    ix.train_on_device(d_data.as<float>(), n, seed, nlist, max_iters, d_labels);
+}
+
+int vidx_build(vidx_index* idx, const float* data, const uint64_t* ext_ids, const uint64_t* timestamps, uint64_t n,
+               uint64_t seed, uint64_t nlist, uint64_t max_iters) {
+    return guarded([&] {
+        require(idx, VIDX_ERR_INVALID_INPUT, "idx is NULL");
+        std::lock_guard<std::mutex> lk(idx->mu);
+        Index& ix = idx->ix;
+        DevBuf d_data, d_labels;
+        do_train(ix, data, n, seed, nlist, max_iters, d_data, d_labels);
+        std::vector<uint32_t> labels(n);
+        d2h_sync(labels.data(), d_labels.as<uint32_t>(), n, ix.stream);
+        ix.build_lists(d_data.as<float>(), n, labels.data(), ext_ids, timestamps, ix.train_centroids.data(), ix.k_trained,
+                       ix.super_labels.data());
+    });
+}
+
+int vidx_train(vidx_index* idx, const float* data, uint64_t n, uint64_t seed, uint64_t nlist, uint64_t max_iters) {
+    return guarded([&] {
+        require(idx, VIDX_ERR_INVALID_INPUT, "idx is NULL");
+        std::lock_guard<std::mutex> lk(idx->mu);
+        DevBuf d_data, d_labels;
+        do_train(idx->ix, data, n, seed, nlist, max_iters, d_data, d_labels);
+    });
+}
+
+int vidx_add(vidx_index* idx, const float* data, const uint64_t* ext_ids, const uint64_t* timestamps, uint64_t n) {
+    return guarded([&] {
+        require(idx, VIDX_ERR_INVALID_INPUT, "idx is NULL");
+        std::lock_guard<std::mutex> lk(idx->mu);
+        Index& ix = idx->ix;
+        require(ix.trained, VIDX_ERR_INVALID_INPUT, "vidx_add before vidx_train");
+        require(n > 0 && data, VIDX_ERR_INVALID_INPUT, "no vectors provided");
+        ix.ensure_device();
+        DevBuf d_data, d_cents, d_labels;
+        d_data.reserve((size_t)n * ix.dim * 4);
+        h2d(d_data.as<float>(), data, (size_t)n * ix.dim, ix.stream);
+        d_cents.reserve(ix.train_centroids.size() * 4);
+        h2d(d_cents.as<float>(), ix.train_centroids.data(), ix.train_centroids.size(), ix.stream);
+        d_labels.reserve((size_t)n * 4);
+        {
+            DeviceKMeans km(d_data.as<float>(), n, (int)ix.dim, ix.stream);
+            km.assign(d_cents.as<float>(), (uint32_t)ix.k_trained, ix.seed, d_labels.as<uint32_t>());
+        }
+        std::vector<uint32_t> labels(n);
+        d2h_sync(labels.data(), d_labels.as<uint32_t>(), n, ix.stream);
+        ix.build_lists(d_data.as<float>(), n, labels.data(), ext_ids, timestamps, ix.train_centroids.data(), ix.k_trained,
+                       ix.super_labels.data());
+    });
+}
+
+int vidx_build_from_labels(vidx_index* idx, const float* data, const uint64_t* ext_ids, uint64_t n, const float* centroids,
+                           uint64_t k, const uint64_t* labels, const uint64_t* centroid_shard) {
+    return guarded([&] {
+        require(idx, VIDX_ERR_INVALID_INPUT, "idx is NULL");
+        require(n > 0 && data && centroids && labels && k > 0, VIDX_ERR_INVALID_INPUT, "no vectors provided");
+        std::lock_guard<std::mutex> lk(idx->mu);
+        Index& ix = idx->ix;
+        ix.ensure_device();
+        DevBuf d_data;
+        d_data.reserve((size_t)n * ix.dim * 4);
+        h2d(d_data.as<float>(), data, (size_t)n * ix.dim, ix.stream);
+        std::vector<uint32_t> l32(n), sh(k, 0);
+        for (uint64_t i = 0; i < n; i++) {
+            require(labels[i] < k, VIDX_ERR_INVALID_INPUT, "label out of range");
+            l32[i] = (uint32_t)labels[i];
+        }
+        uint64_t ns = 1;
+        if (centroid_shard)
+            for (uint64_t c = 0; c < k; c++) {
+                sh[c] = (uint32_t)centroid_shard[c];
+                ns = std::max<uint64_t>(ns, centroid_shard[c] + 1);
+            }
+        ix.k_trained = k;
+        ix.num_shards = ns;
+        ix.train_centroids.assign(centroids, centroids + k * ix.dim);
+        ix.super_labels = sh;
+        ix.trained = true;
+        ix.build_lists(d_data.as<float>(), n, l32.data(), ext_ids, nullptr, centroids, k, sh.data());
+    });
+}
+
+static void search_host(vidx_index* idx, const float* xq, uint64_t nq, uint64_t k, uint64_t n_probe, float* D, int64_t* I,
+                        float* V) {
+    require(idx, VIDX_ERR_INVALID_INPUT, "idx is NULL");
+    require(k != 0 && n_probe != 0, VIDX_ERR_INVALID_INPUT, "k and n_probe must be greater than 0");
+    if (nq == 0) return;
+    require(xq && D && I, VIDX_ERR_INVALID_INPUT, "NULL buffer");
+    std::lock_guard<std::mutex> lk(idx->mu);
+    Index& ix = idx->ix;
+    require(ix.built, VIDX_ERR_OTHER, "index has not been built or loaded");
+    ix.ensure_device();
+    const size_t nres = (size_t)nq * k;
+    ix.io_xq.reserve((size_t)nq * ix.dim * 4);
+    ix.io_D.reserve(nres * 4);
+    ix.io_I.reserve(nres * 8);
+    ix.io_rows.reserve(nres * 4);
+    h2d(ix.io_xq.as<float>(), xq, (size_t)nq * ix.dim, ix.stream);
+    ix.search_device(ix.io_xq.as<float>(), nq, k, n_probe, ix.io_D.as<float>(), ix.io_I.as<int64_t>(),
+                     V ? ix.io_rows.as<uint32_t>() : nullptr, ix.stream, nullptr, nullptr);
+    VIDX_CUDA(cudaMemcpyAsync(D, ix.io_D.p, nres * 4, cudaMemcpyDeviceToHost, ix.stream));
+    VIDX_CUDA(cudaMemcpyAsync(I, ix.io_I.p, nres * 8, cudaMemcpyDeviceToHost, ix.stream));
+    if (V) {
+        ix.io_V.reserve(nres * ix.dim * 4);
+        launch_gather_vectors(ix.d_vecs.as<float>(), ix.dq(), (int)ix.dim, ix.io_rows.as<uint32_t>(), nres, ix.io_V.as<float>(),
+                              ix.stream);
+        VIDX_CUDA(cudaMemcpyAsync(V, ix.io_V.p, nres * ix.dim * 4, cudaMemcpyDeviceToHost, ix.stream));
+    }
+    VIDX_CUDA(cudaStreamSynchronize(ix.stream));
+}
+
+int vidx_search(vidx_index* idx, const float* xq, uint64_t nq, uint64_t k, uint64_t n_probe, float* D, int64_t* I) {
+    return guarded([&] { search_host(idx, xq, nq, k, n_probe, D, I, nullptr); });
+}
+int vidx_search_with_vectors(vidx_index* idx, const float* xq, uint64_t nq, uint64_t k, uint64_t n_probe, float* D, int64_t* I,
+                             float* V) {
+    return guarded([&] {
+        require(V != nullptr, VIDX_ERR_INVALID_INPUT, "V is NULL");
+        search_host(idx, xq, nq, k, n_probe, D, I, V);
+    });
+}
+int vidx_search_device(vidx_index* idx, const float* d_xq, uint64_t nq, uint64_t k, uint64_t n_probe, float* d_D, int64_t* d_I,
+                       void* stream) {
+    return guarded([&] {
+        require(idx, VIDX_ERR_INVALID_INPUT, "idx is NULL");
+        std::lock_guard<std::mutex> lk(idx->mu);
+        Index& ix = idx->ix;
+        ix.ensure_device();
+        ix.search_device(d_xq, nq, k, n_probe, d_D, d_I, nullptr, stream ? (cudaStream_t)stream : ix.stream, nullptr, nullptr);
+    });
+}
+int vidx_coarse_probes(vidx_index* idx, const float* xq, uint64_t nq, uint64_t n_probe, uint32_t* lists, float* dists) {
+    return guarded([&] {
+        require(idx, VIDX_ERR_INVALID_INPUT, "idx is NULL");
+        require(n_probe != 0, VIDX_ERR_INVALID_INPUT, "k and n_probe must be greater than 0");
+        if (nq == 0) return;
+        std::lock_guard<std::mutex> lk(idx->mu);
+        Index& ix = idx->ix;
+        require(ix.built, VIDX_ERR_OTHER, "index has not been built or loaded");
+        ix.ensure_device();
+        DevBuf d_xq, d_l, d_d;
+        d_xq.reserve((size_t)nq * ix.dim * 4);
+        d_l.reserve((size_t)nq * n_probe * 4);
+        d_d.reserve((size_t)nq * n_probe * 4);
+        h2d(d_xq.as<float>(), xq, (size_t)nq * ix.dim, ix.stream);
+        ix.search_device(d_xq.as<float>(), nq, 1, n_probe, nullptr, nullptr, nullptr, ix.stream, d_l.as<uint32_t>(),
+                         dists ? d_d.as<float>() : nullptr);
+        d2h_sync(lists, d_l.as<uint32_t>(), (size_t)nq * n_probe, ix.stream);
+        if (dists) d2h_sync(dists, d_d.as<float>(), (size_t)nq * n_probe, ix.stream);
+    });
+}
+
+uint32_t vidx_dimension(const vidx_index* idx) { return idx ? idx->ix.dim : 0; }
+uint64_t vidx_ntotal(const vidx_index* idx) { return idx ? idx->ix.ntotal : 0; }
+uint64_t vidx_nlist(const vidx_index* idx) { return idx ? idx->ix.nlist : 0; }
+uint64_t vidx_num_shards(const vidx_index* idx) { return idx ? idx->ix.num_shards : 0; }
+uint64_t vidx_k_trained(const vidx_index* idx) { return idx ? idx->ix.k_trained : 0; }
+
+int vidx_get_centroids(const vidx_index* idx, float* out) {
+    return guarded([&] {
+        require(idx && out, VIDX_ERR_INVALID_INPUT, "NULL argument");
+        std::memcpy(out, idx->ix.centroids.data(), idx->ix.centroids.size() * 4);
+    });
+}
+int vidx_get_centroids_to_shard(const vidx_index* idx, uint64_t* out) {
+    return guarded([&] {
+        require(idx && out, VIDX_ERR_INVALID_INPUT, "NULL argument");
+        for (size_t i = 0; i < idx->ix.c2shard.size(); i++) out[i] = idx->ix.c2shard[i];
+    });
+}
+int vidx_get_list_sizes(const vidx_index* idx, uint64_t* out) {
+    return guarded([&] {
+        require(idx && out, VIDX_ERR_INVALID_INPUT, "NULL argument");
+        for (size_t i = 0; i < idx->ix.list_len.size(); i++) out[i] = idx->ix.list_len[i];
+    });
+}
+int vidx_get_list_members(const vidx_index* idx, uint64_t list, uint64_t* out) {
+    return guarded([&] {
+        require(idx && out, VIDX_ERR_INVALID_INPUT, "NULL argument");
+        const Index& ix = idx->ix;
+        require(list < ix.nlist, VIDX_ERR_NOT_FOUND, "list id out of range");
+        uint64_t r0 = ix.list_goff[list] * kGroup;
+        for (uint32_t j = 0; j < ix.list_len[list]; j++) {
+            uint32_t src = ix.row_src[r0 + j];
+            out[j] = ix.internal_ids.empty() ? (uint64_t)src : ix.internal_ids[src];
+        }
+    });
+}
+int vidx_get_train_labels(const vidx_index* idx, uint64_t* out) {
+    return guarded([&] {
+        require(idx && out, VIDX_ERR_INVALID_INPUT, "NULL argument");
+        for (size_t i = 0; i < idx->ix.train_labels.size(); i++) out[i] = idx->ix.train_labels[i];
+    });
+}
+int vidx_get_train_centroids(const vidx_index* idx, float* out) {
+    return guarded([&] {
+        require(idx && out, VIDX_ERR_INVALID_INPUT, "NULL argument");
+        std::memcpy(out, idx->ix.train_centroids.data(), idx->ix.train_centroids.size() * 4);
+    });
+}
+
+// ---- k-means entry points -----------------------------------------------------------
+namespace {
+struct KmCall {
+    cudaStream_t st = nullptr;
+    DevBuf d_data, d_cents, d_labels;
+    ~KmCall() { if (st) cudaStreamDestroy(st); }
+    void setup(int device, const float* data, uint64_t n, uint64_t dim, uint64_t k) {
+        require(n > 0 && dim > 0 && data, VIDX_ERR_INVALID_INPUT, "Input vectors cannot be empty");  // kmeans.rs:23-28
+        require(k > 0, VIDX_ERR_INVALID_INPUT, "k must be > 0");
+        require(n < 0xffffffffull && k < 0x7fffffffull, VIDX_ERR_UNSUPPORTED, "problem too large");
+        int count = 0;
+        if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) {
+            (void)cudaGetLastError();
+            throw CudaError("no CUDA device available (libvidx_b200 has no CPU fallback)");
+        }
+        VIDX_CUDA(cudaSetDevice(device));
+        VIDX_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        d_data.reserve((size_t)n * dim * 4);
+        d_cents.reserve((size_t)k * dim * 4);
+        d_labels.reserve((size_t)n * 4);
+        h2d(d_data.as<float>(), data, (size_t)n * dim, st);
+    }
+    void labels_out(uint64_t n, uint64_t* out) {
+        if (!out) return;
+        std::vector<uint32_t> l(n);
+        d2h_sync(l.data(), d_labels.as<uint32_t>(), n, st);
+        for (uint64_t i = 0; i < n; i++) out[i] = l[i];
+    }
+};
+}  // namespace
+
+int vidx_kmeans_mini_batch(int device, const float* data, uint64_t n, uint64_t dim, uint64_t k, uint64_t max_iters, float tol,
+                           uint64_t seed, float* out_centroids, uint64_t* out_labels, uint64_t* iters_run) {
+    return guarded([&] {
+        KmCall c;
+        c.setup(device, data, n, dim, k);
+        DeviceKMeans km(c.d_data.as<float>(), n, (int)dim, c.st);
+        uint64_t it = km.mini_batch((uint32_t)k, max_iters, tol, seed, c.d_cents.as<float>(), c.d_labels.as<uint32_t>());
+        if (iters_run) *iters_run = it;
+        if (out_centroids) d2h_sync(out_centroids, c.d_cents.as<float>(), (size_t)k * dim, c.st);
+        c.labels_out(n, out_labels);
+    });
+}
+int vidx_kmeans_parallel(int device, const float* data, uint64_t n, uint64_t dim, uint64_t k, uint64_t max_iters, float tol,
+                         uint64_t seed, float* out_centroids, uint64_t* out_labels, uint64_t* iters_run) {
+    return guarded([&] {
+        KmCall c;
+        c.setup(device, data, n, dim, k);
+        DeviceKMeans km(c.d_data.as<float>(), n, (int)dim, c.st);
+        uint64_t it = km.lloyd((uint32_t)k, max_iters, tol, seed, c.d_cents.as<float>(), c.d_labels.as<uint32_t>());
+        if (iters_run) *iters_run = it;
+        if (out_centroids) d2h_sync(out_centroids, c.d_cents.as<float>(), (size_t)k * dim, c.st);
+        c.labels_out(n, out_labels);
+    });
+}
+int vidx_assign_points(int device, const float* data, uint64_t n, uint64_t dim, const float* centroids, uint64_t k,
+                       uint64_t seed, uint64_t* out_labels) {
+    return guarded([&] {
+        require(centroids != nullptr, VIDX_ERR_INVALID_INPUT, "centroids is NULL");
+        KmCall c;
+        c.setup(device, data, n, dim, k);
+        h2d(c.d_cents.as<float>(), centroids, (size_t)k * dim, c.st);
+        DeviceKMeans km(c.d_data.as<float>(), n, (int)dim, c.st);
+        km.assign(c.d_cents.as<float>(), (uint32_t)k, seed, c.d_labels.as<uint32_t>());
+        c.labels_out(n, out_labels);
+    });
+}
+int vidx_kmeans_pp_init(int device, const float* data, uint64_t n, uint64_t dim, uint64_t k, uint64_t seed,
+                        float* out_centroids) {
+    return guarded([&] {
+        require(out_centroids != nullptr, VIDX_ERR_INVALID_INPUT, "out_centroids is NULL");
+        KmCall c;
+        c.setup(device, data, n, dim, k);
+        DeviceKMeans km(c.d_data.as<float>(), n, (int)dim, c.st);
+        km.pp_init((uint32_t)k, seed, c.d_cents.as<float>());
+        d2h_sync(out_centroids, c.d_cents.as<float>(), (size_t)k * dim, c.st);
+    });
+}
+
+// utils.rs:9-16
+uint64_t vidx_calculate_num_clusters(uint64_t n) {
+    if (n < 10000) return (uint64_t)std::sqrt((double)n);
+    if (n < 100000) return 2 * (uint64_t)std::ceil(std::sqrt((double)n));
+    return 4 * (uint64_t)std::ceil(std::sqrt((double)n));
+}
+// utils.rs:18-26
+uint64_t vidx_calculate_max_iterations(uint64_t n) {
+    if (n < 10000) return 300;
+    if (n < 100000) return 100;
+    if (n < 1000000) return 50;
+    return 20;
+}
+
+// ---- persistence ---------------------------------------------------------------------
+int vidx_save(const vidx_index* cidx, const char* index_dir, const char* shards_dir) {
+    return guarded([&] {
+        vidx_index* idx = const_cast<vidx_index*>(cidx);
+        require(idx && index_dir && shards_dir, VIDX_ERR_INVALID_INPUT, "NULL argument");
+        std::lock_guard<std::mutex> lk(idx->mu);
+        Index& ix = idx->ix;
+        require(ix.built, VIDX_ERR_OTHER, "index has not been built or loaded");
+        ix.ensure_device();
+        // vectors back to the host in internal-id order, gathered from the interleaved store
+        const uint64_t n = ix.ntotal;
+        std::vector<uint32_t> row_of(n, kNoRow);
+        for (size_t r = 0; r < ix.row_src.size(); r++)
+            if (ix.row_src[r] != kNoRow) row_of[ix.row_src[r]] = (uint32_t)r;
+        std::vector<float> host((size_t)n * ix.dim);
+        const uint64_t chunk = 1ull << 20;
+        DevBuf d_rows, d_out;
+        d_rows.reserve(chunk * 4);
+        d_out.reserve(chunk * ix.dim * 4);
+        for (uint64_t i0 = 0; i0 < n; i0 += chunk) {
+            uint64_t m = std::min(chunk, n - i0);
+            h2d(d_rows.as<uint32_t>(), row_of.data() + i0, m, ix.stream);
+            launch_gather_vectors(ix.d_vecs.as<float>(), ix.dq(), (int)ix.dim, d_rows.as<uint32_t>(), m, d_out.as<float>(), ix.stream);
+            d2h_sync(host.data() + i0 * ix.dim, d_out.as<float>(), m * ix.dim, ix.stream);
+        }
+        save_index(ix, host, index_dir, shards_dir);
+    });
+}
+int vidx_load(vidx_index* idx, const char* index_dir, const char* shards_dir) {
+    return guarded([&] {
+        require(idx && index_dir && shards_dir, VIDX_ERR_INVALID_INPUT, "NULL argument");
+        std::lock_guard<std::mutex> lk(idx->mu);
+        Index& ix = idx->ix;
+        LoadedIndex L;
+        load_index_files(index_dir, shards_dir, ix.dim, L);
+        ix.ensure_device();
+        ix.dim = L.dim;  // IvfIndex.dimension from the file (ivf_index.rs:36-41)
+        uint64_t n = 0;
+        for (auto& m : L.list_meta) n += m.size() / 3;
+        std::vector<float> data((size_t)std::max<uint64_t>(n, 1) * L.dim);
+        std::vector<uint32_t> labels(n);
+        std::vector<uint64_t> ext(n), ts(n), internal(n);
+        uint64_t at = 0;
+        for (uint64_t l = 0; l < L.nlist; l++) {
+            uint64_t len = L.list_meta[l].size() / 3;
+            if (len) std::memcpy(&data[at * L.dim], L.list_vectors[l].data(), len * L.dim * 4);
+            for (uint64_t j = 0; j < len; j++, at++) {
+                labels[at] = (uint32_t)l;
+                internal[at] = L.list_meta[l][3 * j];
+                ext[at] = L.list_meta[l][3 * j + 1];
+                ts[at] = L.list_meta[l][3 * j + 2];
+            }
+        }
+        DevBuf d_data;
+        d_data.reserve(data.size() * 4);
+        h2d(d_data.as<float>(), data.data(), data.size(), ix.stream);
+        ix.k_trained = L.nlist;
+        ix.num_shards = L.num_shards;
+        ix.train_centroids = L.centroids;
+        ix.super_labels = L.c2shard;
+        ix.trained = true;
+        ix.build_lists(d_data.as<float>(), n, labels.data(), ext.data(), ts.data(), L.centroids.data(), L.nlist, L.c2shard.data(),
+                       /*keep_empty=*/true);
+        ix.internal_ids = internal;
+        ix.load_warnings = L.skipped_shards;
+    });
+}
+
+// ---- multi-GPU ----------------------------------------------------------------------
+int vidx_set_partition(vidx_index* idx, int rank, int world) {
+    return guarded([&] {
+        require(idx, VIDX_ERR_INVALID_INPUT, "idx is NULL");
+        require(world >= 1 && rank >= 0 && rank < world, VIDX_ERR_INVALID_INPUT, "bad rank/world");
+        std::lock_guard<std::mutex> lk(idx->mu);
+        Index& ix = idx->ix;
+        require(ix.built, VIDX_ERR_OTHER, "index has not been built or loaded");
+        ix.ensure_device();
+        ix.part_rank = rank;
+        ix.part_world = world;
+        ix.apply_partition();
+    });
+}
+int vidx_get_shard_owner(const vidx_index* idx, int world, int32_t* out) {
+    return guarded([&] {
+        require(idx && out && world >= 1, VIDX_ERR_INVALID_INPUT, "bad argument");
+        std::vector<int32_t> o = idx->ix.shard_owners(world);
+        for (size_t i = 0; i < o.size() && i < idx->ix.num_shards; i++) out[i] = o[i];
+    });
+}
+int vidx_merge_topk_device(int device, const float* d_D_runs, const int64_t* d_I_runs, uint32_t nruns, uint64_t nq, uint64_t k,
+                           float* d_D, int64_t* d_I, void* stream) {
+    return guarded([&] {
+        require(k > 0 && nruns > 0, VIDX_ERR_INVALID_INPUT, "k and nruns must be > 0");
+        require(k <= 32, VIDX_ERR_UNSUPPORTED, "vidx_merge_topk_device supports k <= 32");
+        DeviceGuard g(device);
+        launch_merge_runs(d_D_runs, d_I_runs, nruns, nq, (uint32_t)k, d_D, d_I, (cudaStream_t)stream);
+    });
+}
+
+// ---- measurement ---------------------------------------------------------------------
+int vidx_set_profiling(vidx_index* idx, int enabled) {
+    return guarded([&] {
+        require(idx, VIDX_ERR_INVALID_INPUT, "idx is NULL");
+        idx->ix.profiling = enabled != 0;
+    });
+}
+int vidx_get_search_stats(vidx_index* idx, vidx_search_stats* out) {
+    return guarded([&] {
+        require(idx && out, VIDX_ERR_INVALID_INPUT, "NULL argument");
+        *out = idx->ix.stats;
+    });
+}
+uint64_t vidx_kernel_launch_count(void) { return g_kernel_launches.load(); }
+
+}  // extern "C"

@@ -1,0 +1,260 @@
+// persist.cu -- cold-start path: the reference's on-disk formats.
+//   shards/shard_{id}.bin   Shard::save_to / get_centroid_vectors_from  (src/shards.rs:22-51, :68-177, :188-349)
+//   index/index.bin         IvfIndex::save_to / load_index_from         (src/ivf_index.rs:274-316)
+// Files written here are meant to be readable by the reference and vice versa.  The
+// shard layout is fully specified by the reference's #[repr(C)] structs.  index.bin is
+// bincode 2.0.1 `standard()` (little endian, varint integers) over serde; the ndarray
+// 0.15.6 serde wrapper {v: u8 = 1, dim, data} is restated from the published crate
+// (sources are not on disk) and is flagged "unverified" in DESIGN.md.
+#include <cerrno>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <sys/stat.h>
+
+#include "../../include/vidx_b200.h"
+#include "index.h"
+
+namespace vidx {
+
+namespace {
+
+#pragma pack(push, 1)
+struct ShardHeader {  // shards.rs:22-31 (40 bytes; the source comment says 48)
+    uint64_t shard_id, version;
+    uint32_t dimensions, num_centroids;
+    uint64_t index_offset, data_offset;
+};
+struct CentroidIndexEntry {  // shards.rs:34-42
+    uint64_t centroid_id;
+    uint32_t num_vectors, padding;
+    uint64_t data_offset, data_size;
+};
+struct VectorMetaRec {  // shards.rs:45-51
+    uint64_t id, external_id, timestamp;
+};
+#pragma pack(pop)
+static_assert(sizeof(ShardHeader) == 40 && sizeof(CentroidIndexEntry) == 32 && sizeof(VectorMetaRec) == 24, "layout");
+
+void mkdirs(const std::string& path) {
+    std::string cur;
+    for (size_t i = 0; i <= path.size(); i++) {
+        if (i == path.size() || path[i] == '/') {
+            if (!cur.empty()) mkdir(cur.c_str(), 0755);
+        }
+        if (i < path.size()) cur.push_back(path[i]);
+    }
+}
+
+// ---- bincode 2 varint ------------------------------------------------------------------
+void put_varint(std::vector<uint8_t>& o, uint64_t v) {
+    if (v < 251) {
+        o.push_back((uint8_t)v);
+    } else if (v < (1ull << 16)) {
+        o.push_back(251);
+        for (int i = 0; i < 2; i++) o.push_back((uint8_t)(v >> (8 * i)));
+    } else if (v < (1ull << 32)) {
+        o.push_back(252);
+        for (int i = 0; i < 4; i++) o.push_back((uint8_t)(v >> (8 * i)));
+    } else {
+        o.push_back(253);
+        for (int i = 0; i < 8; i++) o.push_back((uint8_t)(v >> (8 * i)));
+    }
+}
+struct Reader {
+    const uint8_t* p;
+    size_t n, pos = 0;
+    void need(size_t k) {
+        if (pos + k > n) throw ApiError(VIDX_ERR_OTHER, "Bincode decoding error: unexpected end of index.bin");
+    }
+    uint8_t u8() { need(1); return p[pos++]; }
+    uint64_t le(int bytes) {
+        need(bytes);
+        uint64_t v = 0;
+        for (int i = 0; i < bytes; i++) v |= (uint64_t)p[pos + i] << (8 * i);
+        pos += bytes;
+        return v;
+    }
+    uint64_t varint() {
+        uint8_t b = u8();
+        if (b < 251) return b;
+        if (b == 251) return le(2);
+        if (b == 252) return le(4);
+        if (b == 253) return le(8);
+        throw ApiError(VIDX_ERR_OTHER, "Bincode decoding error: unsupported integer width");
+    }
+    float f32() {
+        uint32_t v = (uint32_t)le(4);
+        float f;
+        std::memcpy(&f, &v, 4);
+        return f;
+    }
+};
+
+}  // namespace
+
+// ---- save --------------------------------------------------------------------------------
+void save_index(const Index& ix, const std::vector<float>& host_vectors /* ntotal x dim, by internal id */,
+                const std::string& index_dir, const std::string& shards_dir) {
+    const uint32_t D = ix.dim;
+    mkdirs(shards_dir);
+    const size_t vsz = (size_t)D * 4, pad = (8 - vsz % 8) % 8;
+    // shard files: lists in ascending list id (ivf_index.rs:152-164)
+    std::vector<std::vector<uint32_t>> shard_lists(ix.num_shards);
+    for (uint64_t l = 0; l < ix.nlist; l++) {
+        if (ix.c2shard[l] >= shard_lists.size()) shard_lists.resize(ix.c2shard[l] + 1);
+        shard_lists[ix.c2shard[l]].push_back((uint32_t)l);
+    }
+    const char zeros[8] = {0};
+    for (size_t s = 0; s < shard_lists.size(); s++) {
+        std::string path = shards_dir + "/shard_" + std::to_string(s) + ".bin";
+        remove(path.c_str());
+        FILE* f = fopen(path.c_str(), "wb");
+        if (!f) throw ApiError(VIDX_ERR_OTHER, "cannot create " + path + ": " + strerror(errno));
+        const auto& ls = shard_lists[s];
+        ShardHeader hd{(uint64_t)s, 1, D, (uint32_t)ls.size(), 40, 40 + 32ull * ls.size()};
+        fwrite(&hd, sizeof hd, 1, f);
+        uint64_t off = hd.data_offset;
+        for (uint32_t l : ls) {
+            uint64_t size = vsz + pad + (uint64_t)ix.list_len[l] * (24 + vsz + pad);
+            CentroidIndexEntry e{l, ix.list_len[l], 0, off, size};
+            fwrite(&e, sizeof e, 1, f);
+            off += size;
+        }
+        for (uint32_t l : ls) {
+            fwrite(&ix.centroids[(size_t)l * D], 4, D, f);
+            fwrite(zeros, 1, pad, f);
+            uint64_t r0 = ix.list_goff[l] * kGroup;
+            for (uint32_t j = 0; j < ix.list_len[l]; j++) {
+                uint32_t src = ix.row_src[r0 + j];
+                VectorMetaRec m{ix.internal_ids.empty() ? (uint64_t)src : ix.internal_ids[src], ix.ext_ids[src], ix.timestamps[src]};
+                fwrite(&m, sizeof m, 1, f);
+                fwrite(&host_vectors[(size_t)src * D], 4, D, f);
+                fwrite(zeros, 1, pad, f);
+            }
+        }
+        if (fclose(f) != 0) throw ApiError(VIDX_ERR_OTHER, "write failed: " + path);
+    }
+    // index.bin
+    std::vector<uint8_t> o;
+    o.push_back(1);  // ndarray ARRAY_FORMAT_VERSION
+    put_varint(o, ix.nlist);  // dim: [usize; 1]
+    put_varint(o, ix.nlist);  // data: seq length
+    for (uint64_t l = 0; l < ix.nlist; l++) {
+        put_varint(o, l);  // Centroid.id
+        put_varint(o, D);  // Vec<f32> length
+        const uint8_t* b = reinterpret_cast<const uint8_t*>(&ix.centroids[(size_t)l * D]);
+        o.insert(o.end(), b, b + vsz);
+    }
+    o.push_back(1);
+    put_varint(o, ix.nlist);
+    put_varint(o, ix.nlist);
+    for (uint64_t l = 0; l < ix.nlist; l++) put_varint(o, ix.c2shard[l]);
+    put_varint(o, D);  // dimension: u32
+    mkdirs(index_dir);
+    std::string ipath = index_dir + "/index.bin";
+    FILE* f = fopen(ipath.c_str(), "wb");
+    if (!f) throw ApiError(VIDX_ERR_OTHER, "cannot create " + ipath + ": " + strerror(errno));
+    fwrite(o.data(), 1, o.size(), f);
+    if (fclose(f) != 0) throw ApiError(VIDX_ERR_OTHER, "write failed: " + ipath);
+}
+
+// ---- load --------------------------------------------------------------------------------
+void load_index_files(const std::string& index_dir, const std::string& shards_dir, uint32_t expect_dim, LoadedIndex& out) {
+    std::string ipath = index_dir + "/index.bin";
+    FILE* f = fopen(ipath.c_str(), "rb");
+    if (!f) throw ApiError(errno == ENOENT ? VIDX_ERR_NOT_FOUND : VIDX_ERR_OTHER, "cannot open " + ipath + ": " + strerror(errno));
+    std::vector<uint8_t> buf;
+    {
+        uint8_t tmp[1 << 16];
+        size_t g;
+        while ((g = fread(tmp, 1, sizeof tmp, f)) > 0) buf.insert(buf.end(), tmp, tmp + g);
+        fclose(f);
+    }
+    Reader r{buf.data(), buf.size()};
+    if (r.u8() != 1) throw ApiError(VIDX_ERR_OTHER, "Bincode decoding error: unknown array version");
+    uint64_t n1 = r.varint(), n2 = r.varint();
+    if (n1 != n2) throw ApiError(VIDX_ERR_OTHER, "Bincode decoding error: array shape mismatch");
+    out.nlist = n1;
+    out.centroids.clear();
+    std::vector<uint64_t> cid(n1);
+    uint64_t D = 0;
+    for (uint64_t l = 0; l < n1; l++) {
+        cid[l] = r.varint();
+        uint64_t len = r.varint();
+        if (l == 0) D = len;
+        if (len != D) throw ApiError(VIDX_ERR_OTHER, "Bincode decoding error: ragged centroid vectors");
+        for (uint64_t d = 0; d < len; d++) out.centroids.push_back(r.f32());
+    }
+    if (r.u8() != 1) throw ApiError(VIDX_ERR_OTHER, "Bincode decoding error: unknown array version");
+    uint64_t m1 = r.varint(), m2 = r.varint();
+    if (m1 != m2 || m1 != n1) throw ApiError(VIDX_ERR_OTHER, "Bincode decoding error: centroids_to_shard shape mismatch");
+    out.c2shard.resize(n1);
+    uint64_t max_shard = 0;
+    for (uint64_t l = 0; l < n1; l++) {
+        out.c2shard[l] = (uint32_t)r.varint();
+        max_shard = std::max<uint64_t>(max_shard, out.c2shard[l]);
+    }
+    out.dim = (uint32_t)r.varint();
+    if (n1 && D != out.dim) throw ApiError(VIDX_ERR_INVALID_DATA, "index.bin: centroid length differs from dimension");
+    (void)expect_dim;  // the reference does not check cfg.dimension against the file (api.rs:109-112)
+    out.num_shards = n1 ? max_shard + 1 : 0;
+
+    // whole-shard loads (shards.rs:352-425).  A shard that cannot be opened or parsed is
+    // skipped, as search_with_paths drops failed shard reads (ivf_index.rs:254).
+    const size_t vsz = (size_t)out.dim * 4, pad = (8 - vsz % 8) % 8;
+    out.list_vectors.assign(n1, {});
+    out.list_meta.assign(n1, {});
+    out.skipped_shards.clear();
+    for (uint64_t s = 0; s < out.num_shards; s++) {
+        std::string path = shards_dir + "/shard_" + std::to_string(s) + ".bin";
+        FILE* sf = fopen(path.c_str(), "rb");
+        auto skip = [&](const char* why) {
+            out.skipped_shards.push_back(path + ": " + why);
+            if (sf) fclose(sf);
+        };
+        if (!sf) { skip("cannot open"); continue; }
+        ShardHeader hd;
+        if (fread(&hd, sizeof hd, 1, sf) != 1) { skip("invalid shard header"); continue; }
+        if (hd.shard_id != s) { skip("shard id mismatch"); continue; }
+        if (hd.dimensions != out.dim) { skip("dimension mismatch"); continue; }
+        std::vector<CentroidIndexEntry> ents(hd.num_centroids);
+        if (fseek(sf, (long)hd.index_offset, SEEK_SET) != 0 ||
+            (hd.num_centroids && fread(ents.data(), sizeof(CentroidIndexEntry), hd.num_centroids, sf) != hd.num_centroids)) {
+            skip("invalid index");
+            continue;
+        }
+        bool bad = false;
+        std::vector<uint8_t> blk;
+        for (const auto& e : ents) {
+            if (e.centroid_id >= n1) { bad = true; break; }
+            blk.resize(e.data_size);
+            if (fseek(sf, (long)e.data_offset, SEEK_SET) != 0 || (e.data_size && fread(blk.data(), 1, blk.size(), sf) != blk.size())) {
+                bad = true;
+                break;
+            }
+            size_t off = vsz + pad;
+            auto& lv = out.list_vectors[e.centroid_id];
+            auto& lm = out.list_meta[e.centroid_id];
+            for (uint32_t j = 0; j < e.num_vectors; j++) {
+                if (off + 24 + vsz > blk.size()) { bad = true; break; }
+                VectorMetaRec m;
+                std::memcpy(&m, blk.data() + off, 24);
+                lm.push_back(m.id);
+                lm.push_back(m.external_id);
+                lm.push_back(m.timestamp);
+                size_t at = lv.size();
+                lv.resize(at + out.dim);
+                std::memcpy(&lv[at], blk.data() + off + 24, vsz);
+                off += 24 + vsz + pad;
+            }
+            if (bad) break;
+        }
+        if (bad) { skip("invalid cluster block"); continue; }
+        fclose(sf);
+    }
+}
+
+}  // namespace vidx
