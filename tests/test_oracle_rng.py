@@ -1,0 +1,114 @@
+"""Pins the oracle's restated rand 0.8.5 StdRng (ChaCha12) where something independent
+exists to pin it against, and checks the structural properties of everything else."""
+import struct
+
+import numpy as np
+import pytest
+
+
+def test_chacha_block_matches_openssl(oracle):
+    """The ChaCha block function at 20 rounds against OpenSSL's ChaCha20 (cryptography pkg);
+    StdRng runs the same code at 12 rounds (rand_chacha 0.3.1 ChaCha12Core)."""
+    algorithms = pytest.importorskip("cryptography.hazmat.primitives.ciphers.algorithms")
+    from cryptography.hazmat.primitives.ciphers import Cipher
+    rng = np.random.default_rng(0)
+    for _ in range(8):
+        key = rng.integers(0, 2 ** 32, 8, dtype=np.uint64).astype(np.uint32)
+        ctr = int(rng.integers(0, 2 ** 31))
+        nonce = struct.pack("<Q", ctr) + b"\0" * 8  # 64-bit counter (words 12-13), stream id 0
+        ks = np.frombuffer(Cipher(algorithms.ChaCha20(key.tobytes(), nonce), mode=None).encryptor().update(b"\0" * 256),
+                           dtype=np.uint32)
+        mine = np.concatenate([oracle.chacha_block(key, ctr + i, 0, 20) for i in range(4)])
+        assert np.array_equal(ks, mine)
+
+
+def test_chacha_rfc7539_quarter_round_vector(oracle):
+    """RFC 7539 section 2.3.2 block test vector, mapped onto the 64-bit-counter layout:
+    counter word 12 = 1, words 13..15 = nonce (09 00 00 00 | 4a 00 00 00 | 00 00 00 00)."""
+    key = np.frombuffer(bytes(range(32)), dtype=np.uint32)
+    counter = 1 | (0x09000000 << 32)
+    stream = 0x4a000000
+    out = oracle.chacha_block(key, counter, stream, 20)
+    expect = [0xe4e7f110, 0x15593bd1, 0x1fdd0f50, 0xc47120a3, 0xc7f4d1c7, 0x0368c033, 0x9aaa2204, 0x4e6cd4c3,
+              0x466482d2, 0x09aa9f07, 0x05d7c214, 0xa2028bd9, 0xd19c12b5, 0xb94e16de, 0xe883d0cb, 0x4e3c50a2]
+    assert out.tolist() == expect
+
+
+def test_seed_from_u64_pcg_expansion(oracle):
+    """rand_core 0.6.4 seed_from_u64: eight PCG32 (XSH-RR) outputs, recomputed here in Python."""
+    def pcg(seed):
+        s, words = seed, []
+        for _ in range(8):
+            s = (s * 6364136223846793005 + 11634580027462260723) & (2 ** 64 - 1)
+            x = (((s >> 18) ^ s) >> 27) & 0xffffffff
+            rot = s >> 59
+            words.append(((x >> rot) | (x << ((32 - rot) & 31))) & 0xffffffff)
+        return words
+    for seed in (0, 1, 42, 756, 1309, 2 ** 63 + 5):
+        assert oracle.Rng(seed).key().tolist() == pcg(seed)
+
+
+def test_block_rng_word_order_and_u64_straddle(oracle):
+    a, b = oracle.Rng(42), oracle.Rng(42)
+    key = a.key()
+    words = np.concatenate([oracle.chacha_block(key, i, 0, 12) for i in range(8)])
+    assert [a.next_u32() for _ in range(70)] == words[:70].tolist()
+    # next_u64 = (hi << 32) | lo from consecutive words; with one word left it straddles the refill
+    for _ in range(63):
+        b.next_u32()
+    v = b.next_u64()
+    assert v == (int(words[64]) << 32) | int(words[63])
+    assert b.next_u32() == words[65]
+
+
+def test_gen_range_is_unbiased_widening_multiply(oracle):
+    r, r2 = oracle.Rng(7), oracle.Rng(7)
+    for n in (1, 2, 3, 10, 1000, 50000, 10 ** 6, 2 ** 40 + 17):
+        zone = ((n << (64 - n.bit_length())) - 1) & (2 ** 64 - 1)
+        while True:
+            v = r2.next_u64()
+            m = v * n
+            if (m & (2 ** 64 - 1)) <= zone:
+                break
+        assert r.gen_range(n) == m >> 64
+    vals = [oracle.Rng(s).gen_range(10) for s in range(400)]
+    assert set(vals) == set(range(10))
+
+
+def test_shuffle_is_a_permutation_and_deterministic(oracle):
+    p = oracle.Rng(42).shuffle(1000)
+    assert sorted(p.tolist()) == list(range(1000))
+    assert np.array_equal(p, oracle.Rng(42).shuffle(1000))
+    assert not np.array_equal(p, oracle.Rng(43).shuffle(1000))
+    # descending Fisher-Yates with u32 index draws: replay by hand
+    r = oracle.Rng(5)
+    a = list(range(20))
+    for i in range(19, 0, -1):
+        j = r.gen_index(i + 1)
+        a[i], a[j] = a[j], a[i]
+    assert oracle.Rng(5).shuffle(20).tolist() == a
+
+
+def test_choose_multiple_reservoir(oracle):
+    c = oracle.Rng(756).choose_multiple(4096, 64)
+    assert len(c) == 64 and len(set(c.tolist())) == 64 and c.max() < 4096
+    assert oracle.Rng(1).choose_multiple(5, 5).tolist() == [0, 1, 2, 3, 4]
+    assert oracle.Rng(1).choose_multiple(3, 5).tolist() == [0, 1, 2]
+
+
+def test_weighted_index_semantics(oracle):
+    # a single positive weight is always chosen; zero-weight items never are
+    w = np.zeros(100, np.float32)
+    w[37] = 2.5
+    assert all(oracle.Rng(s).weighted_index(w) == 37 for s in range(50))
+    w = np.array([1, 0, 0, 3], np.float32)
+    picks = [oracle.Rng(s).weighted_index(w) for s in range(400)]
+    assert set(picks) == {0, 3} and 0.6 < np.mean(np.array(picks) == 3) < 0.9
+
+
+def test_deterministic_vectors_fixture(oracle):
+    # tests/test_utils/mod.rs:245-252: gen_range(-10.0..10.0)
+    v = oracle.create_deterministic_vectors(100, 8, 42)
+    assert v.shape == (100, 8) and v.min() >= -10 and v.max() < 10
+    assert np.array_equal(v, oracle.create_deterministic_vectors(100, 8, 42))
+    assert abs(v.mean()) < 1.5
