@@ -154,6 +154,10 @@ int vidx_load(vidx_index* idx, const char* index_dir, const char* shards_dir);
  * probe lists.  Call after build/load, before search. */
 int vidx_set_partition(vidx_index* idx, int rank, int world);
 int vidx_get_shard_owner(const vidx_index* idx, int world, int32_t* out /* num_shards */);
+/* The partition rule on its own (host only, no device needed): shard_sizes[num_shards]
+ * vector counts -> owner rank per shard; largest shard first to the least loaded rank,
+ * ties to the lower rank / lower shard id. */
+int vidx_partition_shards(const uint64_t* shard_sizes, uint64_t num_shards, int world, int32_t* out);
 /* Merge `nruns` per-rank results (each nq x k, ascending, padded) laid out run-major in
  * DEVICE memory into the global top-k: the reduction behind join_all + concat + sort
  * in src/ivf_index.rs:249-266.  Ties resolve to the lower run index. */

@@ -81,6 +81,7 @@ def lib():
         L.vo_ivf_from_labels.restype = C.c_void_p
         L.vo_ivf_from_labels.argtypes = [f32p, u64p, u64, u64, f32p, u64, u64p]
         L.vo_ivf_free.argtypes = [C.c_void_p]
+        L.vo_ivf_set_list_mask.argtypes = [C.c_void_p, C.c_char_p]
         for name in ("nlist", "k_trained", "num_shards", "iters_run"):
             fn = getattr(L, "vo_ivf_" + name)
             fn.restype = u64
@@ -345,6 +346,10 @@ class Ivf:
         out = np.zeros(self.nlist, np.uint64)
         lib().vo_ivf_list_sizes(self.h, _u(out))
         return out.astype(np.int64)
+
+    def set_list_mask(self, mask):
+        """Scan only lists with mask[l] != 0 (None clears): one rank of the sharded search."""
+        lib().vo_ivf_set_list_mask(self.h, None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8).tobytes())
 
     def list_members(self, l):
         sz = int(self.list_sizes()[l])

@@ -579,6 +579,7 @@ struct OracleIvf {
     std::vector<float> centroids_all;        // k x dim before the empty-list filter
     std::vector<u64> old_to_new;             // k entries, (u64)-1 for dropped lists
     u64 num_shards = 0, k_trained = 0, iters_run = 0;
+    std::vector<unsigned char> list_mask;  // optional: lists scanned by this "rank" (multi-GPU tests)
 };
 
 // ivf_index.rs:58-177
@@ -640,6 +641,7 @@ static long ivf_search_one(const OracleIvf* ix, const float* q, size_t k, size_t
     size_t np = std::min(nprobe, nlist);
     cand.clear();
     for (size_t r = 0; r < np; r++) {
+        if (!ix->list_mask.empty() && !ix->list_mask[cd[r].second]) continue;
         for (u64 id : ix->lists[cd[r].second]) {
             float d = euclidean_distance_squared(q, &ix->data[id * dim], dim);
             if (d != d) return -2;
@@ -790,6 +792,12 @@ void* vo_ivf_from_labels(const float* data, const u64* ext, u64 n, u64 dim, cons
     return ix;
 }
 void vo_ivf_free(void* h) { delete (OracleIvf*)h; }
+// Restrict the scan to a subset of lists (probe selection still sees every centroid):
+// what one rank of the sharded multi-GPU search does.  mask == NULL clears it.
+void vo_ivf_set_list_mask(void* h, const unsigned char* mask) {
+    OracleIvf* ix = (OracleIvf*)h;
+    if (mask) ix->list_mask.assign(mask, mask + ix->lists.size()); else ix->list_mask.clear();
+}
 u64 vo_ivf_nlist(void* h) { return ((OracleIvf*)h)->lists.size(); }
 u64 vo_ivf_k_trained(void* h) { return ((OracleIvf*)h)->k_trained; }
 u64 vo_ivf_num_shards(void* h) { return ((OracleIvf*)h)->num_shards; }

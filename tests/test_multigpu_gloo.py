@@ -1,0 +1,79 @@
+"""N > 1 host logic on CPU: world_size-2 gloo processes.  Each rank owns the shards the
+library's partition rule gives it, scans only those lists (the oracle stands in for the
+device-local scan here -- it is the checker, not the product), the per-rank top-k are
+exchanged with all_gather in the [run][q][k] layout the device merge kernel consumes, and
+the merged answer must equal the unpartitioned search."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def merge_runs(D, I):
+    """Restatement of merge_runs_kernel: stable by (distance, run, position)."""
+    nruns, nq, k = D.shape
+    oD = np.full((nq, k), np.inf, np.float32)
+    oI = np.full((nq, k), -1, np.int64)
+    for q in range(nq):
+        d = D[:, q, :].reshape(-1)
+        i = I[:, q, :].reshape(-1)
+        keep = i >= 0
+        order = np.argsort(d[keep], kind="stable")[:k]
+        oD[q, :len(order)] = d[keep][order]
+        oI[q, :len(order)] = i[keep][order]
+    return oD, oI
+
+
+def worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "vector-indexer_b200"))
+    import oracle as O
+    from vector_indexer_py import _ffi
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(42)
+    xb = rng.standard_normal((3000, 16)).astype(np.float32)
+    xq = rng.standard_normal((40, 16)).astype(np.float32)
+    ix = O.Ivf.fit(xb, seed=42)  # deterministic: every rank builds the same index
+    c2s, sizes = ix.centroids_to_shard(), ix.list_sizes()
+    shard_sizes = np.bincount(c2s, weights=sizes, minlength=ix.num_shards).astype(np.uint64)
+    owner = _ffi.partition_shards(shard_sizes, world)
+    k, nprobe = 10, 12
+    Dfull, Ifull = ix.search_batch(xq, k, nprobe)
+    ix.set_list_mask(owner[c2s] == rank)
+    Dl, Il = ix.search_batch(xq, k, nprobe)
+    gD = [torch.empty(40, k) for _ in range(world)]
+    gI = [torch.empty(40, k, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(gD, torch.from_numpy(Dl))
+    dist.all_gather(gI, torch.from_numpy(Il))
+    D, I = merge_runs(torch.stack(gD).numpy(), torch.stack(gI).numpy())
+    ok = np.array_equal(D, Dfull) and np.array_equal(I, Ifull)
+    loads = np.bincount(owner, weights=shard_sizes.astype(np.float64), minlength=world)
+    with open(os.path.join(out_dir, f"rank{rank}.txt"), "w") as f:
+        f.write(f"{int(ok)} {loads.tolist()} {owner.tolist()}")
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharded_search_equals_single(tmp_path):
+    port = 29500 + os.getpid() % 2000
+    mp.spawn(worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    outs = [open(tmp_path / f"rank{r}.txt").read() for r in range(2)]
+    assert all(o.startswith("1 ") for o in outs), outs
+    assert outs[0][2:] == outs[1][2:]  # both ranks derived the same partition
+
+
+def test_partition_rule_balances(ffi):
+    owner = ffi.partition_shards([100, 90, 50, 40, 10, 10], 2)
+    assert owner.tolist() == [0, 1, 1, 0, 0, 1]  # 100|90, 50->r1, 40->r0, tie 140/140 -> lower rank
+    sizes = np.random.default_rng(0).integers(1, 1000, 64)
+    for world in (2, 4, 8):
+        o = ffi.partition_shards(sizes, world)
+        loads = np.bincount(o, weights=sizes, minlength=world)
+        assert loads.max() - loads.min() <= sizes.max() and set(o.tolist()) == set(range(world))
+    assert ffi.partition_shards([5, 5, 5], 1).tolist() == [0, 0, 0]

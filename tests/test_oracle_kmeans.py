@@ -18,7 +18,6 @@ def test_ramp_fixture(oracle):
     # tests/test_utils/mod.rs:10-16: (x as f32 * 0.1) % 50.0
     v = oracle.create_test_vectors(5, 4)
     assert v.dtype == np.float32 and v.shape == (5, 4)
-    assert np.array_equal(v.ravel()[:4], np.array([0.0, 0.1, 0.2, 0.3], np.float32) * 1) or True
     x = np.float32(7) * np.float32(0.1)
     assert v.ravel()[7] == np.fmod(x, np.float32(50.0))
     assert oracle.create_test_vectors(1000, 32).max() < 50.0
@@ -75,8 +74,7 @@ def test_full_batch_labels_are_optimal(oracle):
     # tests/kmeans_tests.rs:38-49
     data = oracle.create_test_vectors(500, 8)
     c, l, _ = oracle.kmeans_parallel(data, 4, 100)
-    assert verify_optimal_assignment(data, c, l) or True  # Lloyd returns labels of the pre-update centroids
-    assert np.array_equal(l, oracle.assign_points(data, c)) or True
+    assert verify_optimal_assignment(data, c, l)
 
 
 def test_single_cluster_is_the_mean(oracle):
@@ -143,7 +141,7 @@ def test_mini_batch_inertia_within_factor_of_full_batch(oracle):
     cf, lf, _ = oracle.kmeans_parallel(data, 8, 100)
     cm, lm, _ = oracle.kmeans_mini_batch(data, 8, 100)
     lf = oracle.assign_brute_force(data, cf)
-    assert inertia(data, cm, lm) < 1.5 * inertia(data, cf, lf) * 1.0 + 1e-3 or inertia(data, cm, lm) < 2.0 * inertia(data, cf, lf)
+    assert inertia(data, cm, lm) < 1.5 * inertia(data, cf, lf)
 
 
 def test_deterministic_runs(oracle):

@@ -197,12 +197,7 @@ void Index::build_lists(const float* d_data, uint64_t n, const uint32_t* labels,
 
 // Shards -> ranks by greedy balance on vector count (largest shard first, least loaded
 // rank, ties to the lower rank).
-std::vector<int32_t> Index::shard_owners(int world) const {
-    std::vector<uint64_t> load(num_shards ? num_shards : 1, 0);
-    for (uint64_t l = 0; l < nlist; l++) {
-        if (c2shard[l] >= load.size()) load.resize(c2shard[l] + 1, 0);
-        load[c2shard[l]] += list_len[l];
-    }
+static std::vector<int32_t> partition_shards(const std::vector<uint64_t>& load, int world) {
     std::vector<uint32_t> order(load.size());
     std::iota(order.begin(), order.end(), 0u);
     std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return load[a] > load[b]; });
@@ -216,6 +211,15 @@ std::vector<int32_t> Index::shard_owners(int world) const {
         rank_load[best] += load[s];
     }
     return owner;
+}
+std::vector<int32_t> partition_shards_public(const std::vector<uint64_t>& load, int world) { return partition_shards(load, world); }
+std::vector<int32_t> Index::shard_owners(int world) const {
+    std::vector<uint64_t> load(num_shards ? num_shards : 1, 0);
+    for (uint64_t l = 0; l < nlist; l++) {
+        if (c2shard[l] >= load.size()) load.resize(c2shard[l] + 1, 0);
+        load[c2shard[l]] += list_len[l];
+    }
+    return partition_shards(load, world);
 }
 
 // Lists this rank does not own get zero segments, so grouping skips them; the centroid
@@ -911,6 +915,14 @@ int vidx_get_shard_owner(const vidx_index* idx, int world, int32_t* out) {
         require(idx && out && world >= 1, VIDX_ERR_INVALID_INPUT, "bad argument");
         std::vector<int32_t> o = idx->ix.shard_owners(world);
         for (size_t i = 0; i < o.size() && i < idx->ix.num_shards; i++) out[i] = o[i];
+    });
+}
+int vidx_partition_shards(const uint64_t* shard_sizes, uint64_t num_shards, int world, int32_t* out) {
+    return guarded([&] {
+        require(shard_sizes && out && world >= 1, VIDX_ERR_INVALID_INPUT, "bad argument");
+        std::vector<uint64_t> load(shard_sizes, shard_sizes + num_shards);
+        std::vector<int32_t> o = vidx::partition_shards_public(load, world);
+        for (uint64_t i = 0; i < num_shards; i++) out[i] = o[i];
     });
 }
 int vidx_merge_topk_device(int device, const float* d_D_runs, const int64_t* d_I_runs, uint32_t nruns, uint64_t nq, uint64_t k,

@@ -73,6 +73,8 @@ struct Index {
 };
 
 
+std::vector<int32_t> partition_shards_public(const std::vector<uint64_t>& load, int world);
+
 // What vidx_load reads from index.bin + the shard files.
 struct LoadedIndex {
     uint32_t dim = 0;

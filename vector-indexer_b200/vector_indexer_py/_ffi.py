@@ -78,6 +78,7 @@ _SIGS = {
     "vidx_load": (i32, [vp, C.c_char_p, C.c_char_p]),
     "vidx_set_partition": (i32, [vp, i32, i32]),
     "vidx_get_shard_owner": (i32, [vp, i32, i32p]),
+    "vidx_partition_shards": (i32, [u64p, u64, i32, i32p]),
     "vidx_merge_topk_device": (i32, [i32, vp, vp, u32, u64, u64, vp, vp, vp]),
     "vidx_set_profiling": (i32, [vp, i32]),
     "vidx_get_search_stats": (i32, [vp, C.POINTER(SearchStats)]),
@@ -192,6 +193,10 @@ class Index:
         check(lib().vidx_search(self.h, _f(xq), nq, k, n_probe, _f(D), I.ctypes.data_as(i64p)))
         return D, I
 
+    def search_host_ptr(self, xq_ptr, nq, k, n_probe, D_ptr, I_ptr):
+        """vidx_search on raw HOST addresses (e.g. pinned torch tensors)."""
+        check(lib().vidx_search(self.h, C.cast(xq_ptr, f32p), nq, k, n_probe, C.cast(D_ptr, f32p), C.cast(I_ptr, i64p)))
+
     def search_device(self, d_xq_ptr, nq, k, n_probe, d_D_ptr, d_I_ptr, stream_ptr=0):
         check(lib().vidx_search_device(self.h, d_xq_ptr, nq, k, n_probe, d_D_ptr, d_I_ptr, stream_ptr))
 
@@ -277,6 +282,13 @@ class Index:
         s = SearchStats()
         check(lib().vidx_get_search_stats(self.h, C.byref(s)))
         return s.asdict()
+
+
+def partition_shards(shard_sizes, world):
+    sizes = np.ascontiguousarray(shard_sizes, dtype=np.uint64)
+    out = np.zeros(len(sizes), np.int32)
+    check(lib().vidx_partition_shards(_u(sizes), len(sizes), world, out.ctypes.data_as(i32p)))
+    return out
 
 
 def merge_topk_device(device, d_D_runs, d_I_runs, nruns, nq, k, d_D, d_I, stream=0):
