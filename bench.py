@@ -203,7 +203,13 @@ def run_ours(args):
     t0 = time.perf_counter()
     ix = _ffi.Index(d, local).build(xb, seed=42, nlist=w["nlist"])
     build_s = time.perf_counter() - t0
-    stream = torch.cuda.current_stream().cuda_stream
+    # The library launches on the stream it is given; torch's legacy default stream has handle 0,
+    # which the ABI reads as "use the handle's own stream", so run everything on an explicit
+    # torch stream: torch.cuda.Event then brackets exactly the kernels being timed.
+    tstream = torch.cuda.Stream()
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
     d_xq = torch.from_numpy(xq).cuda()
     d_D = torch.empty((nq, k), dtype=torch.float32, device="cuda")
     d_I = torch.empty((nq, k), dtype=torch.int64, device="cuda")
