@@ -175,10 +175,17 @@ typedef struct vidx_search_stats {
     uint64_t n_pairs;                /* (query, segment) pairs scanned */
     uint64_t n_dense_items, n_sparse_items;
     uint64_t kernel_launches;        /* kernels launched by the last search */
+    double ms_scan_tc;               /* the tensor-core scan kernel alone (part of ms_scan) */
+    uint64_t n_tc_items, n_tc_survivors, n_tc_overflow; /* work items, candidates re-checked exactly, queries redone exactly */
+    uint64_t tc_mma_flops;           /* 2*D per (query, vector) pair issued to the tensor cores (TF32) */
 } vidx_search_stats;
 /* Enable per-stage CUDA-event timing (adds stream synchronisation at the end of a
  * search); stats describe the last completed search on this handle. */
 int vidx_set_profiling(vidx_index* idx, int enabled);
+/* Scan algorithm: 0 (default) = tcgen05 TF32 pre-filter + exact re-check whenever the shape allows
+ * (D padded to a multiple of 8 floats, D <= 128, k <= 32), 1 = exact FP32 kernels only.  Results are
+ * bit-identical either way. */
+int vidx_set_scan_mode(vidx_index* idx, int mode);
 int vidx_get_search_stats(vidx_index* idx, vidx_search_stats* out);
 /* Total kernels launched by this library in this process (bench.py's gpu_launches). */
 uint64_t vidx_kernel_launch_count(void);

@@ -152,3 +152,47 @@ def test_search_stats_and_launch_counter(oracle, ffi):
     assert st["n_pairs"] >= 500 * 4
     assert st["scan_bytes_logical"] >= st["scan_bytes_algorithmic"] > 0
     assert st["ms_scan"] > 0 and st["ms_total"] >= st["ms_scan"]
+
+
+# ---- tensor-core pre-filter path (tcgen05 TF32 + exact re-check) ------------------------------
+@pytest.mark.parametrize("d,nlist,nq,nprobe,k", [(64, 8, 700, 3, 10), (128, 20, 300, 20, 10), (32, 4, 150, 4, 32),
+                                                  (8, 6, 90, 2, 1), (96, 50, 1000, 7, 5)])
+def test_tensor_core_scan_equals_exact_scan_and_oracle(oracle, ffi, d, nlist, nq, nprobe, k):
+    xb, xq = bench_data(40000, d, nq, seed=d + nq)
+    oix, gix = make_pair(oracle, ffi, xb, nlist)
+    gix.set_profiling(True)
+    gix.set_scan_mode(0)
+    Dt, It = check_search(oix, gix, xq, k, nprobe)
+    st = gix.stats()
+    assert st["n_tc_items"] > 0 and st["n_tc_survivors"] >= nq * min(k, 1) and st["n_tc_overflow"] == 0, st
+    assert st["n_dense_items"] == 0 and st["n_sparse_items"] == 0, st
+    gix.set_scan_mode(1)
+    De, Ie = gix.search(xq, k, nprobe)
+    st = gix.stats()
+    assert st["n_tc_items"] == 0 and st["n_dense_items"] + st["n_sparse_items"] > 0
+    assert np.array_equal(Dt.view(np.uint32), De.view(np.uint32)) and np.array_equal(It, Ie)
+
+
+def test_tensor_core_survivor_overflow_is_redone_exactly(oracle, ffi):
+    # thousands of identical vectors: every one ties with the k-th best, the survivor buffer of
+    # those queries overflows and the exact kernels redo them -- results still match the oracle
+    rng = np.random.default_rng(5)
+    base = rng.standard_normal((3000, 16)).astype(np.float32)
+    dup = np.tile(base[:1], (6000, 1))
+    xb = np.concatenate([dup, base])
+    xq = np.concatenate([base[:1] + 0.01, base[5:40]])
+    oix, gix = make_pair(oracle, ffi, xb, 4)
+    gix.set_profiling(True)
+    check_search(oix, gix, xq, 10, 4)
+    st = gix.stats()
+    assert st["n_tc_overflow"] >= 1 and st["n_dense_items"] + st["n_sparse_items"] > 0, st
+
+
+def test_tensor_core_filter_never_drops_a_true_neighbour_on_hard_data(oracle, ffi):
+    # large norms + tiny distances: the regime where |q|^2+|v|^2-2q.v cancels catastrophically
+    rng = np.random.default_rng(11)
+    centers = rng.standard_normal((50, 64)).astype(np.float32) * 100
+    xb = (centers[rng.integers(0, 50, 30000)] + rng.standard_normal((30000, 64)).astype(np.float32) * 0.01).astype(np.float32)
+    xq = (xb[rng.choice(30000, 400, replace=False)] + rng.standard_normal((400, 64)).astype(np.float32) * 0.001).astype(np.float32)
+    oix, gix = make_pair(oracle, ffi, xb, 16)
+    check_search(oix, gix, xq, 10, 8)

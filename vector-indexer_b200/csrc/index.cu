@@ -13,6 +13,7 @@
 #include "../../include/vidx_b200.h"
 #include "index.h"
 #include "kmeans_host.h"
+#include "scan_tc.h"
 #include "search.h"
 
 namespace vidx {
@@ -188,6 +189,29 @@ void Index::build_lists(const float* d_data, uint64_t n, const uint32_t* labels,
     }
     d_segs.reserve(std::max<size_t>(segs.size(), 1) * sizeof(SegDesc));
     h2d(d_segs.as<SegDesc>(), segs.data(), segs.size(), stream);
+    // per-list layout + row norms for the tensor-core scan
+    {
+        std::vector<uint32_t> g0(nlist + 1), ng(nlist + 1);
+        for (uint64_t l = 0; l < nlist; l++) {
+            g0[l] = (uint32_t)list_goff[l];
+            ng[l] = (uint32_t)(list_goff[l + 1] - list_goff[l]);
+        }
+        d_list_g0.reserve(g0.size() * 4);
+        d_list_ng.reserve(ng.size() * 4);
+        d_list_len.reserve((nlist + 1) * 4);
+        h2d(d_list_g0.as<uint32_t>(), g0.data(), g0.size(), stream);
+        h2d(d_list_ng.as<uint32_t>(), ng.data(), ng.size(), stream);
+        h2d(d_list_len.as<uint32_t>(), list_len.data(), list_len.size(), stream);
+        d_vnorm.reserve(std::max<uint64_t>(nrows, 1) * 4);
+        DevBuf d_vntrue;
+        d_vntrue.reserve(std::max<uint64_t>(nrows, 1) * 4);
+        launch_row_norms(d_vecs.as<float4>(), Dq, d_row_src.as<uint32_t>(), nrows, d_vnorm.as<float>(), d_vntrue.as<float>(), stream);
+        std::vector<float> vt(nrows);
+        d2h_sync(vt.data(), d_vntrue.as<float>(), nrows, stream);
+        vn_max = 0.0f;
+        for (float v : vt)
+            if (v > vn_max) vn_max = v;
+    }
     part_rank = 0;
     part_world = 1;
     apply_partition();
@@ -254,24 +278,26 @@ void Index::apply_partition() {
 // ------------------------------------------------------------------------------------
 struct Index::Workspace {
     DevBuf xq_pad, dist, probes, pair_ns, slot_off, seg_cnt, seg_qoff, seg_cur, seg_qlist, slot_seg, dense, sparse, counters,
-        scan_tmp, cand_d, cand_r, alld, row_off, row_len, sel_pos, sel_val, rows, stats;
+        scan_tmp, cand_d, cand_r, alld, row_off, row_len, sel_pos, sel_val, rows, stats, slot_rank, list_cnt, list_cur, list_qoff,
+        list_qlist, items_per_list, item_off, qnorm, gthr, cand_cnt, overflow, cand;
 };
 void Index::delete_workspace() {
     delete ws;
     ws = nullptr;
 }
 
-// stats: distinct probed segments -> algorithmic bytes; pairs -> logical bytes / flops
-__global__ void scan_stats_kernel(const uint32_t* __restrict__ seg_cnt, const SegDesc* __restrict__ segs, uint32_t nseg,
+// stats: distinct probed lists -> algorithmic bytes; (query, list) pairs -> logical bytes / flops
+__global__ void list_stats_kernel(const uint32_t* __restrict__ list_cnt, const uint32_t* __restrict__ list_len, uint32_t nlist,
                                   unsigned long long* __restrict__ out /*[0]=distinct vectors,[1]=pair vectors,[2]=pairs*/) {
-    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= nseg) return;
-    uint32_t c = seg_cnt[s];
+    uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= nlist) return;
+    uint32_t c = list_cnt[l];
     if (!c) return;
-    atomicAdd(&out[0], (unsigned long long)segs[s].nvalid);
-    atomicAdd(&out[1], (unsigned long long)segs[s].nvalid * c);
+    atomicAdd(&out[0], (unsigned long long)list_len[l]);
+    atomicAdd(&out[1], (unsigned long long)list_len[l] * c);
     atomicAdd(&out[2], (unsigned long long)c);
 }
+
 void Index::search_device(const float* d_xq, uint64_t nq, uint64_t k_req, uint64_t nprobe_req, float* d_D, int64_t* d_I,
                           uint32_t* d_rows_out, cudaStream_t st, uint32_t* d_probe_out, float* d_probe_dist_out) {
     if (k_req == 0 || nprobe_req == 0)
@@ -288,6 +314,9 @@ void Index::search_device(const float* d_xq, uint64_t nq, uint64_t k_req, uint64
     const int Dq = dq(), Dp = Dq * 4;
     const bool coarse_only = d_probe_out != nullptr;
     const bool fused = k <= 32;
+    // tensor-core pre-filter + exact finalize whenever the shape allows; the exact kernels then
+    // only see the queries it hands back (survivor buffer overflow)
+    const bool tc = fused && scan_mode != 1 && tc_supported(Dq, (uint32_t)k) && !coarse_only;
     const uint32_t nseg = (uint32_t)segs.size();
     const uint32_t ldc = ncgroups * kGroup;
     // pairs bound per query: the np largest per-list segment counts
@@ -303,10 +332,16 @@ void Index::search_device(const float* d_xq, uint64_t nq, uint64_t k_req, uint64
     shrink((double)pairs_per_q * (fused ? (double)k * 8 : (double)kSegVecs * 4), 6e9);
     shrink((double)std::max<uint64_t>(pairs_per_q, np), 1.5e9 / 1.0);  // 32-bit pair / slot indices
     qb = std::min<uint64_t>(qb, 65535ull * 64);
+    uint32_t capq = 0;
+    if (tc) {
+        // survivors per query: a few hundred in practice; a query that overflows is redone exactly
+        capq = (uint32_t)std::min<uint64_t>(4096, std::max<uint64_t>(256, (uint64_t)(2e9 / (8.0 * (double)qb))));
+        capq = (uint32_t)std::min<uint64_t>(capq, std::max<uint64_t>(owned_vectors, 32));
+    }
 
     cudaEvent_t* ev = events;
     if (profiling) {
-        st_ms[0] = st_ms[1] = st_ms[2] = st_ms[3] = st_ms[4] = 0;
+        for (double& m : st_ms) m = 0;
         stats = vidx_search_stats{};
     }
     uint64_t launches0 = g_kernel_launches.load();
@@ -351,8 +386,75 @@ void Index::search_device(const float* d_xq, uint64_t nq, uint64_t k_req, uint64
             }
             continue;
         }
-        // K3: group (query, probed list) by segment
         const size_t npairs = (size_t)nqb * np;
+        w.scan_tmp.reserve(exclusive_scan_tmp_entries(std::max<size_t>(std::max<size_t>(npairs, nseg), nlist) + 1) * 4);
+        w.counters.reserve(16 * 4);
+        VIDX_CUDA(cudaMemsetAsync(w.counters.p, 0, 16 * 4, st));
+        uint32_t* counters = w.counters.as<uint32_t>();  // [0]=#dense [1]=#sparse [4],[5]=their work counters [8]=tc work counter
+
+        // ---- tensor-core path: group by list, TF32 pre-filter, survivors per query ---------------
+        const bool want_list_cnt = tc || profiling;
+        if (want_list_cnt) {
+            w.list_cnt.reserve(((size_t)nlist + 1) * 4);
+            VIDX_CUDA(cudaMemsetAsync(w.list_cnt.p, 0, ((size_t)nlist + 1) * 4, st));
+            launch_tc_count(w.probes.as<uint32_t>(), npairs, d_list_seg.as<uint2>(), w.list_cnt.as<uint32_t>(), st);
+        }
+        if (profiling) {
+            w.stats.reserve(64);
+            VIDX_CUDA(cudaMemsetAsync(w.stats.p, 0, 64, st));
+            list_stats_kernel<<<(unsigned)ceil_div(std::max<uint64_t>(nlist, 1), 256), 256, 0, st>>>(
+                w.list_cnt.as<uint32_t>(), d_list_len.as<uint32_t>(), (uint32_t)nlist, w.stats.as<unsigned long long>());
+            VIDX_LAUNCHED();
+        }
+        if (tc) {
+            w.qnorm.reserve((size_t)nqb * 4);
+            w.gthr.reserve((size_t)nqb * 4);
+            w.cand_cnt.reserve((size_t)nqb * 4);
+            w.overflow.reserve((size_t)nqb * 4);
+            w.cand.reserve((size_t)nqb * capq * 8);
+            w.list_cur.reserve(((size_t)nlist + 1) * 4);
+            w.list_qoff.reserve(((size_t)nlist + 1) * 4);
+            w.list_qlist.reserve(std::max<size_t>(npairs, 1) * 8);
+            w.items_per_list.reserve(((size_t)nlist + 1) * 4);
+            w.item_off.reserve(((size_t)nlist + 1) * 4);
+            launch_query_norms(xq4, Dq, nqb, w.qnorm.as<float>(), w.gthr.as<uint32_t>(), w.cand_cnt.as<uint32_t>(),
+                               w.overflow.as<uint32_t>(), st);
+            VIDX_CUDA(cudaMemsetAsync(w.list_cur.p, 0, ((size_t)nlist + 1) * 4, st));
+            exclusive_scan_u32(w.list_cnt.as<uint32_t>(), w.list_qoff.as<uint32_t>(), nlist, w.scan_tmp.as<uint32_t>(), st);
+            launch_tc_fill(w.probes.as<uint32_t>(), npairs, np, d_list_seg.as<uint2>(), w.list_qoff.as<uint32_t>(),
+                           w.list_cur.as<uint32_t>(), w.list_qlist.as<uint2>(), st);
+            launch_tc_items(w.list_cnt.as<uint32_t>(), d_list_ng.as<uint32_t>(), (uint32_t)nlist, w.items_per_list.as<uint32_t>(), st);
+            exclusive_scan_u32(w.items_per_list.as<uint32_t>(), w.item_off.as<uint32_t>(), nlist, w.scan_tmp.as<uint32_t>(), st);
+        }
+        if (profiling) VIDX_CUDA(cudaEventRecord(ev[3], st));
+        if (tc) {
+            TcParams tp{};
+            tp.vecs = d_vecs.as<float4>();
+            tp.vnorm = d_vnorm.as<float>();
+            tp.Dq = Dq;
+            tp.xq4 = xq4;
+            tp.qnorm = w.qnorm.as<float>();
+            tp.list_g0 = d_list_g0.as<uint32_t>();
+            tp.list_ngroups = d_list_ng.as<uint32_t>();
+            tp.list_cnt = w.list_cnt.as<uint32_t>();
+            tp.list_qoff = w.list_qoff.as<uint32_t>();
+            tp.list_qlist = w.list_qlist.as<uint2>();
+            tp.item_off = w.item_off.as<uint32_t>();
+            tp.nlist = (uint32_t)nlist;
+            tp.work_counter = counters + 8;
+            tp.gthr_bits = w.gthr.as<uint32_t>();
+            tp.cand = w.cand.as<unsigned long long>();
+            tp.cand_cnt = w.cand_cnt.as<uint32_t>();
+            tp.overflow = w.overflow.as<uint32_t>();
+            tp.capq = capq;
+            tp.k = (uint32_t)k;
+            tp.vn_max = vn_max;
+            launch_scan_tc(tp, st);
+        }
+        if (profiling) VIDX_CUDA(cudaEventRecord(ev[8], st));
+
+        // ---- exact path: all pairs, or only the queries the tensor-core path handed back ---------
+        const uint32_t* only_flag = tc ? w.overflow.as<uint32_t>() : nullptr;
         const uint64_t pair_cap = std::max<uint64_t>(1, (uint64_t)nqb * pairs_per_q);
         w.pair_ns.reserve((npairs + 1) * 4);
         w.slot_off.reserve((npairs + 1) * 4);
@@ -361,51 +463,61 @@ void Index::search_device(const float* d_xq, uint64_t nq, uint64_t k_req, uint64
         w.seg_cur.reserve(((size_t)nseg + 1) * 4);
         w.seg_qlist.reserve(pair_cap * 8);
         w.slot_seg.reserve(pair_cap * 4);
+        w.slot_rank.reserve(pair_cap * 4);
         const uint32_t sparse_max = sparse_supported(Dq) ? 16u : 0u;
         const size_t dense_cap = pair_cap / 64 + nseg + 1, sparse_cap = (size_t)nseg * 2 + 1;
         w.dense.reserve(dense_cap * sizeof(ScanItem));
         w.sparse.reserve(sparse_cap * sizeof(ScanItem));
-        w.counters.reserve(16 * 4);
-        w.scan_tmp.reserve(exclusive_scan_tmp_entries(std::max<size_t>(npairs, nseg) + 1) * 4);
         VIDX_CUDA(cudaMemsetAsync(w.seg_cnt.p, 0, ((size_t)nseg + 1) * 4, st));
         VIDX_CUDA(cudaMemsetAsync(w.seg_cur.p, 0, ((size_t)nseg + 1) * 4, st));
-        VIDX_CUDA(cudaMemsetAsync(w.counters.p, 0, 16 * 4, st));
-        launch_group_count(w.probes.as<uint32_t>(), npairs, d_list_seg.as<uint2>(), w.pair_ns.as<uint32_t>(),
+        launch_group_count(w.probes.as<uint32_t>(), npairs, np, d_list_seg.as<uint2>(), only_flag, w.pair_ns.as<uint32_t>(),
                            w.seg_cnt.as<uint32_t>(), st);
         exclusive_scan_u32(w.pair_ns.as<uint32_t>(), w.slot_off.as<uint32_t>(), npairs, w.scan_tmp.as<uint32_t>(), st);
         exclusive_scan_u32(w.seg_cnt.as<uint32_t>(), w.seg_qoff.as<uint32_t>(), nseg, w.scan_tmp.as<uint32_t>(), st);
         launch_group_fill(w.probes.as<uint32_t>(), npairs, np, d_list_seg.as<uint2>(), w.slot_off.as<uint32_t>(),
                           w.seg_qoff.as<uint32_t>(), w.seg_cur.as<uint32_t>(), w.seg_qlist.as<uint2>(), w.slot_seg.as<uint32_t>(),
-                          st);
-        launch_group_items(w.seg_cnt.as<uint32_t>(), nseg, sparse_max, w.dense.as<ScanItem>(), w.sparse.as<ScanItem>(),
-                           w.counters.as<uint32_t>(), st);
-        if (profiling) {
-            w.stats.reserve(64);
-            VIDX_CUDA(cudaMemsetAsync(w.stats.p, 0, 64, st));
-            scan_stats_kernel<<<(unsigned)ceil_div(std::max<uint32_t>(nseg, 1), 256), 256, 0, st>>>(
-                w.seg_cnt.as<uint32_t>(), d_segs.as<SegDesc>(), nseg, w.stats.as<unsigned long long>());
-            VIDX_LAUNCHED();
-        }
-        if (profiling) VIDX_CUDA(cudaEventRecord(ev[3], st));
-        // K4+K5: scan
+                          only_flag, w.slot_rank.as<uint32_t>(), st);
+        launch_group_items(w.seg_cnt.as<uint32_t>(), nseg, sparse_max, w.dense.as<ScanItem>(), w.sparse.as<ScanItem>(), counters,
+                           st);
         w.rows.reserve((size_t)nqb * kout * 4);
         uint32_t* rows_out = d_rows_out ? d_rows_out + q0 * kout : nullptr;
         if (fused) {
             w.cand_d.reserve(pair_cap * k * 4);
             w.cand_r.reserve(pair_cap * k * 4);
             launch_scan(false, d_vecs.as<float4>(), Dq, xq4, d_segs.as<SegDesc>(), w.seg_qoff.as<uint32_t>(),
-                        w.seg_qlist.as<uint2>(), w.dense.as<ScanItem>(), w.sparse.as<ScanItem>(), w.counters.as<uint32_t>(),
-                        w.counters.as<uint32_t>() + 4, (uint32_t)k, w.cand_d.as<float>(), w.cand_r.as<uint32_t>(), nullptr,
-                        sparse_max > 0, st);
+                        w.seg_qlist.as<uint2>(), w.dense.as<ScanItem>(), w.sparse.as<ScanItem>(), counters, counters + 4, (uint32_t)k,
+                        w.cand_d.as<float>(), w.cand_r.as<uint32_t>(), nullptr, sparse_max > 0, st);
             if (profiling) VIDX_CUDA(cudaEventRecord(ev[4], st));
-            launch_merge_slots(w.cand_d.as<float>(), w.cand_r.as<uint32_t>(), w.slot_off.as<uint32_t>(), nqb, np, (uint32_t)k, kout,
-                               d_row_ext.as<uint64_t>(), d_D + q0 * kout, d_I + q0 * kout, rows_out, st);
+            // K5: exact distances of the survivors + merge with the exact slots
+            FinalizeParams fp{};
+            fp.nq = nqb;
+            fp.nprobe = np;
+            fp.k = (uint32_t)k;
+            fp.kout = kout;
+            fp.Dq = Dq;
+            fp.vecs = d_vecs.as<float4>();
+            fp.xq4 = xq4;
+            if (tc) {
+                fp.cand = w.cand.as<unsigned long long>();
+                fp.cand_cnt = w.cand_cnt.as<uint32_t>();
+                fp.overflow = w.overflow.as<uint32_t>();
+                fp.capq = capq;
+            }
+            fp.slot_off = w.slot_off.as<uint32_t>();
+            fp.slot_d = w.cand_d.as<float>();
+            fp.slot_r = w.cand_r.as<uint32_t>();
+            fp.slot_rank = w.slot_rank.as<uint32_t>();
+            fp.row_ext = d_row_ext.as<uint64_t>();
+            fp.D = d_D + q0 * kout;
+            fp.I = d_I + q0 * kout;
+            fp.out_rows = rows_out;
+            launch_finalize(fp, st);
         } else {
             // large k: every (query, segment) distance row, then an exact radix select per query
             w.alld.reserve(pair_cap * kSegVecs * 4);
             launch_scan(true, d_vecs.as<float4>(), Dq, xq4, d_segs.as<SegDesc>(), w.seg_qoff.as<uint32_t>(),
-                        w.seg_qlist.as<uint2>(), w.dense.as<ScanItem>(), w.sparse.as<ScanItem>(), w.counters.as<uint32_t>(),
-                        w.counters.as<uint32_t>() + 4, (uint32_t)k, nullptr, nullptr, w.alld.as<float>(), sparse_max > 0, st);
+                        w.seg_qlist.as<uint2>(), w.dense.as<ScanItem>(), w.sparse.as<ScanItem>(), counters, counters + 4, (uint32_t)k,
+                        nullptr, nullptr, w.alld.as<float>(), sparse_max > 0, st);
             if (profiling) VIDX_CUDA(cudaEventRecord(ev[4], st));
             w.row_off.reserve((size_t)nqb * 8);
             w.row_len.reserve((size_t)nqb * 4);
@@ -427,10 +539,12 @@ void Index::search_device(const float* d_xq, uint64_t nq, uint64_t k_req, uint64
                 VIDX_CUDA(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
                 st_ms[i] += ms;
             }
+            VIDX_CUDA(cudaEventElapsedTime(&ms, ev[3], ev[8]));
+            st_ms[5] += ms;
             unsigned long long h[3];
-            uint32_t cnt[2];
+            uint32_t cnt[12];
             d2h_sync(h, w.stats.as<unsigned long long>(), 3, st);
-            d2h_sync(cnt, w.counters.as<uint32_t>(), 2, st);
+            d2h_sync(cnt, counters, 12, st);
             const uint64_t rec = 4ull * dim + 8;
             stats.scan_bytes_algorithmic += h[0] * rec + (uint64_t)nqb * dim * 4 + (uint64_t)nqb * np * 4 + (uint64_t)nqb * k * 12;
             stats.scan_bytes_logical += h[1] * rec;
@@ -439,6 +553,19 @@ void Index::search_device(const float* d_xq, uint64_t nq, uint64_t k_req, uint64
             stats.coarse_flops += 3ull * dim * nqb * nlist;
             stats.n_dense_items += cnt[0];
             stats.n_sparse_items += cnt[1];
+            if (tc) {
+                std::vector<uint32_t> cc(nqb), of(nqb);
+                d2h_sync(cc.data(), w.cand_cnt.as<uint32_t>(), nqb, st);
+                d2h_sync(of.data(), w.overflow.as<uint32_t>(), nqb, st);
+                uint32_t tot_items = 0;
+                d2h_sync(&tot_items, w.item_off.as<uint32_t>() + nlist, 1, st);
+                stats.n_tc_items += tot_items;
+                for (uint32_t i = 0; i < nqb; i++) {
+                    stats.n_tc_survivors += cc[i];
+                    stats.n_tc_overflow += of[i] ? 1 : 0;
+                }
+                stats.tc_mma_flops += h[1] * 2ull * Dp;
+            }
         }
     }
     if (profiling) {
@@ -452,6 +579,7 @@ void Index::search_device(const float* d_xq, uint64_t nq, uint64_t k_req, uint64
         stats.ms_group = st_ms[2];
         stats.ms_scan = st_ms[3];
         stats.ms_merge = st_ms[4];
+        stats.ms_scan_tc = st_ms[5];
     }
     stats.kernel_launches = g_kernel_launches.load() - launches0;
 }
@@ -940,6 +1068,13 @@ int vidx_set_profiling(vidx_index* idx, int enabled) {
     return guarded([&] {
         require(idx, VIDX_ERR_INVALID_INPUT, "idx is NULL");
         idx->ix.profiling = enabled != 0;
+    });
+}
+int vidx_set_scan_mode(vidx_index* idx, int mode) {
+    return guarded([&] {
+        require(idx, VIDX_ERR_INVALID_INPUT, "idx is NULL");
+        require(mode == 0 || mode == 1, VIDX_ERR_INVALID_INPUT, "mode must be 0 or 1");
+        idx->ix.scan_mode = mode;
     });
 }
 int vidx_get_search_stats(vidx_index* idx, vidx_search_stats* out) {

@@ -46,16 +46,18 @@ struct Index {
 
     // device store
     cudaStream_t stream = nullptr;
-    cudaEvent_t events[8] = {};
+    cudaEvent_t events[10] = {};
     uint32_t ncgroups = 0;
-    DevBuf d_vecs, d_cents, d_row_ext, d_segs, d_list_seg;
+    DevBuf d_vecs, d_cents, d_row_ext, d_segs, d_list_seg, d_list_g0, d_list_ng, d_list_len, d_vnorm;
+    float vn_max = 0.0f;   // max |v|^2 over the stored rows (bound for the tensor-core filter)
+    int scan_mode = 0;     // 0 = tensor-core pre-filter when the shape allows, 1 = exact kernels only
     DevBuf io_xq, io_D, io_I, io_rows, io_V;
     struct Workspace;
     Workspace* ws = nullptr;
 
     // measurement
     bool profiling = false;
-    double st_ms[5] = {};
+    double st_ms[6] = {};
     vidx_search_stats stats{};
 
     int dq() const { return (int)((dim + 3) / 4); }

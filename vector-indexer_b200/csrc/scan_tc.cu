@@ -1,0 +1,580 @@
+// scan_tc.cu -- tensor-core list scan for sm_100a: tcgen05 TF32 pre-filter + exact re-check.
+//
+// The inverted-list scan (src/ivf_index.rs:252-266) is, for a batch of queries grouped by
+// probed list, the contraction  dot[q][v] = sum_d q[d]*v[d]  followed by a top-k.  The
+// reference's distance is fp32 and results must be bit-exact, so the tensor cores are used
+// as a FILTER only:
+//
+//   L(q,v) = (1-eps)*(|q|^2 + |v|^2) - 2*dot_tf32(q,v)      is a guaranteed LOWER bound of
+//   the reference distance (eps covers TF32 operand truncation, 2^-9*|q||v| <=
+//   2^-10(|q|^2+|v|^2), plus every fp32 rounding involved).
+//
+//   A candidate survives iff L <= U, where U is an UPPER bound of the query's exact k-th best
+//   distance: the k-th smallest L seen so far plus 2*eps*(|q|^2 + max|v|^2), or a bound
+//   published by another CTA for the same query.  Every true top-k member survives.
+//
+//   Survivors (a few hundred per query) get the reference's exact sequential fp32 distance in
+//   finalize_kernel, which then selects the top-k by (distance, probe rank, row) -- the same
+//   keys the exact scan kernels order by.  The final answer is bit-identical to the exact path.
+//
+// Kernel anatomy (one CTA per SM, persistent, 6 warps):
+//   warp 0  producer : cp.async.bulk (1-D TMA) of 4 groups (128 vectors, full D) + their scaled
+//                      norms per stage, completion on an mbarrier (complete_tx::bytes)
+//   warp 1  MMA      : one elected thread issues tcgen05.mma.cta_group::1.kind::tf32, M=128
+//                      queries x N=32 vectors x K=8 per instruction; operands are read from shared
+//                      memory through no-swizzle K-major descriptors -- the interleaved group
+//                      layout [Dq][32 vectors][16 B] IS the UMMA core-matrix layout (8 rows x 16 B
+//                      contiguous, SBO = 128 B, LBO = 512 B), so list data needs no reshaping
+//   warps 2-5 epilogue: tcgen05.ld the 128x128 fp32 accumulator tile from TMEM (double buffered,
+//                      256 columns), one thread per query row, 1 FFMA + 1 compare per element
+// Accumulators never leave the SM; HBM sees each list tile once per 128-query tile.
+#include "scan_tc.h"
+
+namespace vidx {
+
+constexpr int kTcThreads = 192;
+constexpr int kTcM = 128;            // queries per tile (UMMA M)
+constexpr int kTcTileGroups = 4;     // 4 groups = 128 vectors per stage
+constexpr int kTcChunkTiles = 64;    // tiles per work item (8192 vectors)
+constexpr int kTcTmemCols = 256;     // 2 accumulator stages x 128 columns
+constexpr float kTcEps = 2.5e-3f;    // see header comment; needed: ~1.99e-3
+
+// ---- PTX wrappers ------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// try_wait suspends the thread for a hardware time slice per attempt; a wait that is still
+// pending after ~2^24 attempts is a protocol bug, so trap instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    for (uint32_t spins = 0; !mbar_try_wait(bar, parity); spins++)
+        if (spins > (1u << 24)) __trap();
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, TF32 inputs, FP32 accumulate.
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// 32 lanes x 32 columns of fp32: thread t of the warp gets lane (quarter*32 + t), 32 consecutive columns.
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
+}
+// Shared-memory matrix descriptor, no swizzle, K-major: 8-row x 16-byte core matrices;
+// LBO = byte distance between the two 16-byte K chunks of one instruction, SBO = byte distance
+// between consecutive 8-row groups; version 1 (Blackwell).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32) | (1ull << 46);
+}
+// Instruction descriptor: D = F32 (bits 4-5 = 1), A = B = TF32 (2 at bits 7-9 / 10-12), both K-major,
+// N >> 3 at bits 17-22, M >> 4 at bits 24-28.
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------
+// norms
+// ------------------------------------------------------------------------------------------
+// Per stored row: (1-eps)*|v|^2, NaN for padding rows (NaN never passes a '<=' test).
+__global__ void row_norm_kernel(const float4* __restrict__ vecs, int Dq, const uint32_t* __restrict__ row_src, size_t nrows,
+                                float* __restrict__ vn_scaled, float* __restrict__ vn_true) {
+    size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= nrows) return;
+    if (row_src[row] == kNoRow) {
+        vn_scaled[row] = __int_as_float(0x7fc00000);
+        vn_true[row] = 0.0f;
+        return;
+    }
+    const float4* p = vecs + (row >> 5) * (size_t)Dq * 32 + (row & 31);
+    float s = 0.0f;
+    for (int c = 0; c < Dq; c++) {
+        float4 v = p[(size_t)c * 32];
+        s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+    vn_true[row] = s;
+    vn_scaled[row] = (1.0f - kTcEps) * s;
+}
+__global__ void query_norm_kernel(const float4* __restrict__ xq4, int Dq, uint32_t nq, float* __restrict__ qn,
+                                  uint32_t* __restrict__ gthr_bits, uint32_t* __restrict__ cand_cnt, uint32_t* __restrict__ overflow) {
+    uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    float s = 0.0f;
+    for (int c = 0; c < Dq; c++) {
+        float4 v = xq4[(size_t)q * Dq + c];
+        s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+    qn[q] = s;
+    gthr_bits[q] = 0x7f800000u;  // +inf
+    cand_cnt[q] = 0;
+    overflow[q] = 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// grouping by list
+// ------------------------------------------------------------------------------------------
+__global__ void tc_count_kernel(const uint32_t* __restrict__ probes, size_t npairs, const uint2* __restrict__ list_seg,
+                                uint32_t* __restrict__ list_cnt) {
+    size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npairs) return;
+    uint32_t l = probes[p];
+    if (l == kNoRow) return;
+    uint2 sr = list_seg[l];
+    if (sr.y > sr.x) atomicAdd(&list_cnt[l], 1u);  // owned, non-empty list
+}
+__global__ void tc_fill_kernel(const uint32_t* __restrict__ probes, size_t npairs, uint32_t nprobe,
+                               const uint2* __restrict__ list_seg, const uint32_t* __restrict__ list_qoff,
+                               uint32_t* __restrict__ list_cur, uint2* __restrict__ list_qlist) {
+    size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npairs) return;
+    uint32_t l = probes[p];
+    if (l == kNoRow) return;
+    uint2 sr = list_seg[l];
+    if (sr.y <= sr.x) return;
+    uint32_t i = atomicAdd(&list_cur[l], 1u);
+    list_qlist[list_qoff[l] + i] = make_uint2((uint32_t)(p / nprobe), (uint32_t)(p % nprobe));
+}
+// items of list l = (#query tiles) x (#vector chunks); enumerated chunk-major so that CTAs running
+// at the same time share a vector chunk (L2 reuse) and a query's later chunks start with a warm bound.
+__global__ void tc_items_kernel(const uint32_t* __restrict__ list_cnt, const uint32_t* __restrict__ list_ngroups, uint32_t nlist,
+                                uint32_t* __restrict__ items_per_list) {
+    uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= nlist) return;
+    uint32_t c = list_cnt[l];
+    uint32_t ntiles = (list_ngroups[l] + kTcTileGroups - 1) / kTcTileGroups;
+    uint32_t nch = (ntiles + kTcChunkTiles - 1) / kTcChunkTiles;
+    items_per_list[l] = c ? ((c + kTcM - 1) / kTcM) * nch : 0u;
+}
+
+// ------------------------------------------------------------------------------------------
+// the tensor-core scan
+// ------------------------------------------------------------------------------------------
+struct TcSmemLayout {
+    uint32_t a_bytes, b_bytes, off_b, off_vn, off_tk, off_q, off_bar, off_misc, total;
+};
+__host__ __device__ inline TcSmemLayout tc_smem_layout(int Dq, int k) {
+    TcSmemLayout L;
+    L.a_bytes = (uint32_t)Dq * kTcM * 16;
+    L.b_bytes = (uint32_t)Dq * kTcTileGroups * 512;
+    L.off_b = L.a_bytes;
+    L.off_vn = L.off_b + 2 * L.b_bytes;
+    L.off_tk = L.off_vn + 2 * 128 * 4;
+    L.off_q = L.off_tk + (uint32_t)k * 128 * 4;
+    L.off_bar = L.off_q + 128 * 8;
+    L.off_misc = L.off_bar + 8 * 8;
+    L.total = L.off_misc + 64;
+    return L;
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const TcSmemLayout L = tc_smem_layout(p.Dq, (int)p.k);
+    unsigned char* sA = smem;
+    unsigned char* sB = smem + L.off_b;
+    float* s_vn = reinterpret_cast<float*>(smem + L.off_vn);
+    float* s_tk = reinterpret_cast<float*>(smem + L.off_tk);
+    uint2* s_q = reinterpret_cast<uint2*>(smem + L.off_q);
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + L.off_bar);
+    uint64_t* bar_empty = bar_full + 2;
+    uint64_t* bar_tfull = bar_full + 4;
+    uint64_t* bar_tempty = bar_full + 6;
+    uint32_t* s_misc = reinterpret_cast<uint32_t*>(smem + L.off_misc);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int Dq = p.Dq;
+    if (tid == 0) {
+        for (int i = 0; i < 2; i++) {
+            mbar_init(&bar_full[i], 1);
+            mbar_init(&bar_empty[i], 1);
+            mbar_init(&bar_tfull[i], 1);
+            mbar_init(&bar_tempty[i], 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_misc[0])), "r"(kTcTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = s_misc[0];
+    const uint32_t total_items = p.item_off[p.nlist];
+    const uint32_t idesc = make_idesc_tf32(kTcM, 32);
+    uint32_t it = 0;  // tiles processed so far by this CTA (stage = it & 1, phase = (it >> 1) & 1)
+
+    for (;;) {
+        if (tid == 0) s_misc[1] = atomicAdd(p.work_counter, 1u);
+        __syncthreads();
+        const uint32_t item = s_misc[1];
+        if (item >= total_items) break;
+        // decode item -> (list, chunk, query tile)
+        uint32_t lo = 0, hi = p.nlist;
+        while (hi - lo > 1) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (p.item_off[mid] <= item) lo = mid; else hi = mid;
+        }
+        const uint32_t l = lo;
+        const uint32_t cnt = p.list_cnt[l];
+        const uint32_t nqt = (cnt + kTcM - 1) / kTcM;
+        const uint32_t local = item - p.item_off[l];
+        const uint32_t chunk = local / nqt, qt = local - chunk * nqt;
+        const uint32_t ngl = p.list_ngroups[l];
+        const uint32_t g_list = p.list_g0[l];
+        const uint32_t ntiles = (ngl + kTcTileGroups - 1) / kTcTileGroups;
+        const uint32_t t0 = chunk * kTcChunkTiles, t1 = min(ntiles, t0 + kTcChunkTiles);
+        const uint32_t nq_tile = min((uint32_t)kTcM, cnt - qt * kTcM);
+
+        if (tid < kTcM) s_q[tid] = tid < (int)nq_tile ? p.list_qlist[p.list_qoff[l] + qt * kTcM + tid] : make_uint2(kNoRow, 0);
+        __syncthreads();
+        // A tile: [c][128 rows][16 B] (core matrices of 8 rows x 16 B, SBO 128 B, LBO 2048 B)
+        for (int idx = tid; idx < Dq * kTcM; idx += kTcThreads) {
+            int c = idx >> 7, r = idx & 127;
+            uint32_t q = s_q[r].x;
+            float4 v = make_float4(0, 0, 0, 0);
+            if (q != kNoRow) v = p.xq4[(size_t)q * Dq + c];
+            reinterpret_cast<float4*>(sA)[idx] = v;
+        }
+        if (warp >= 2) {
+            int row = (warp & 3) * 32 + lane;
+            for (uint32_t i = 0; i < p.k; i++) s_tk[i * 128 + row] = __int_as_float(0x7f800000);
+        }
+        fence_proxy_async();
+        __syncthreads();
+
+        if (warp == 0) {
+            // ===== producer =====
+            if (lane == 0) {
+                for (uint32_t t = t0; t < t1; t++, it++) {
+                    const uint32_t s = it & 1, ph = (it >> 1) & 1;
+                    mbar_wait(&bar_empty[s], ph ^ 1);
+                    mbar_wait(&bar_tempty[s], ph ^ 1);  // norms buffer of this stage is read by the epilogue
+                    const uint32_t ng = min((uint32_t)kTcTileGroups, ngl - t * kTcTileGroups);
+                    const uint32_t gbytes = (uint32_t)Dq * 512;
+                    mbar_expect_tx(&bar_full[s], ng * gbytes + ng * 128);
+                    const size_t g0 = (size_t)g_list + (size_t)t * kTcTileGroups;
+                    for (uint32_t g = 0; g < ng; g++)
+                        bulk_g2s(sB + s * L.b_bytes + g * gbytes, p.vecs + (g0 + g) * (size_t)Dq * 32, gbytes, &bar_full[s]);
+                    bulk_g2s(s_vn + s * 128, p.vnorm + g0 * 32, ng * 128, &bar_full[s]);
+                }
+            } else {
+                it += t1 - t0;
+            }
+            it = __shfl_sync(kFull, it, 0);
+        } else if (warp == 1) {
+            // ===== MMA issuer =====
+            if (lane == 0) {
+                const uint32_t a_addr = smem_u32(sA);
+                for (uint32_t t = t0; t < t1; t++, it++) {
+                    const uint32_t s = it & 1, ph = (it >> 1) & 1;
+                    mbar_wait(&bar_full[s], ph);
+                    mbar_wait(&bar_tempty[s], ph ^ 1);
+                    tc_fence_after();
+                    const uint32_t ng = min((uint32_t)kTcTileGroups, ngl - t * kTcTileGroups);
+                    const uint32_t b_addr = smem_u32(sB + s * L.b_bytes);
+                    for (uint32_t g = 0; g < ng; g++) {
+                        const uint32_t d_tmem = tmem_base + s * 128 + g * 32;
+                        for (int ks = 0; ks < (Dq >> 1); ks++) {
+                            uint64_t da = make_smem_desc(a_addr + ks * 4096, 2048, 128);
+                            uint64_t db = make_smem_desc(b_addr + g * Dq * 512 + ks * 1024, 512, 128);
+                            tc_mma_tf32(d_tmem, da, db, idesc, ks > 0 ? 1u : 0u);
+                        }
+                    }
+                    tc_commit(&bar_empty[s]);   // smem stage free once these MMAs have read it
+                    tc_commit(&bar_tfull[s]);   // accumulator stage ready for the epilogue
+                }
+            } else {
+                it += t1 - t0;
+            }
+            it = __shfl_sync(kFull, it, 0);
+        } else {
+            // ===== epilogue: one thread per query row =====
+            const int quarter = warp & 3;
+            const int row = quarter * 32 + lane;
+            const uint2 qi = s_q[row];
+            const bool valid = qi.x != kNoRow;
+            const uint32_t q = qi.x, rank = qi.y;
+            float base_t = 0.0f, delta = 0.0f, tau_g = __int_as_float(0x7f800000);
+            if (valid) {
+                float qn = p.qnorm[q];
+                base_t = (1.0f - kTcEps) * qn;
+                delta = 2.0f * kTcEps * (qn + p.vn_max);
+                float g = __uint_as_float(p.gthr_bits[q]);
+                tau_g = (g - base_t) + 1e-5f * (g + base_t);
+            }
+            float t_k = __int_as_float(0x7f800000);
+            uint32_t pos_max = 0;
+            float P = tau_g;
+            for (uint32_t t = t0; t < t1; t++, it++) {
+                const uint32_t s = it & 1, ph = (it >> 1) & 1;
+                mbar_wait(&bar_tfull[s], ph);
+                tc_fence_after();
+                const uint32_t ng = min((uint32_t)kTcTileGroups, ngl - t * kTcTileGroups);
+                const uint32_t row0 = (g_list + t * kTcTileGroups) * 32u;
+                for (uint32_t cb = 0; cb < ng; cb++) {
+                    float acc[32];
+                    tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + s * 128 + cb * 32, acc);
+                    if (valid) {
+                        const float4* vn4 = reinterpret_cast<const float4*>(s_vn + s * 128 + cb * 32);
+#pragma unroll
+                        for (int j4 = 0; j4 < 8; j4++) {
+                            float4 n4 = vn4[j4];
+                            float tv[4];
+                            tv[0] = __fmaf_rn(acc[4 * j4 + 0], -2.0f, n4.x);
+                            tv[1] = __fmaf_rn(acc[4 * j4 + 1], -2.0f, n4.y);
+                            tv[2] = __fmaf_rn(acc[4 * j4 + 2], -2.0f, n4.z);
+                            tv[3] = __fmaf_rn(acc[4 * j4 + 3], -2.0f, n4.w);
+#pragma unroll
+                            for (int u = 0; u < 4; u++) {
+                                if (tv[u] <= P) {
+                                    // survivor: record it, tighten the local bound
+                                    uint32_t idx = atomicAdd(&p.cand_cnt[q], 1u);
+                                    if (idx < p.capq)
+                                        p.cand[(size_t)q * p.capq + idx] = ((unsigned long long)rank << 32) | (row0 + cb * 32 + 4 * j4 + u);
+                                    else
+                                        p.overflow[q] = 1u;
+                                    if (tv[u] < t_k) {
+                                        s_tk[pos_max * 128 + row] = tv[u];
+                                        float m = -__int_as_float(0x7f800000);
+                                        uint32_t pm = 0;
+                                        for (uint32_t i = 0; i < p.k; i++) {
+                                            float v = s_tk[i * 128 + row];
+                                            if (v > m) { m = v; pm = i; }
+                                        }
+                                        t_k = m;
+                                        pos_max = pm;
+                                        P = fminf(tau_g, t_k + delta);
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_tempty[s]);
+            }
+            // publish an upper bound of this query's exact k-th best distance
+            if (valid && t_k < __int_as_float(0x7f800000)) {
+                float U = fmaxf(t_k + base_t + delta, 0.0f);
+                U = U + 1e-5f * U;
+                atomicMin(&p.gthr_bits[q], __float_as_uint(U));
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTcTmemCols) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// finalize: exact distances of the survivors + merge with the exact-path slots -> top-k
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool lex_less(float d, unsigned long long key, float d2, unsigned long long key2) {
+    return d < d2 || (d == d2 && key < key2);
+}
+__device__ __forceinline__ void warp_insert_lex64(float cd, unsigned long long ck, float& my_d, unsigned long long& my_k, int lane) {
+    unsigned m = __ballot_sync(kFull, lex_less(my_d, my_k, cd, ck));
+    int pos = __popc(m);
+    float up_d = __shfl_up_sync(kFull, my_d, 1);
+    unsigned long long up_k = __shfl_up_sync(kFull, my_k, 1);
+    if (lane == pos) { my_d = cd; my_k = ck; }
+    else if (lane > pos) { my_d = up_d; my_k = up_k; }
+}
+// The reference's exact distance of one stored row (utils.rs:28-30), from the interleaved store.
+__device__ __forceinline__ float exact_row_distance(const float4* __restrict__ vecs, int Dq, uint32_t row,
+                                                    const float4* __restrict__ q4) {
+    const float4* pv = vecs + (size_t)(row >> 5) * Dq * 32 + (row & 31);
+    float a = 0.0f;
+#pragma unroll 4
+    for (int c = 0; c < Dq; c++) {
+        float4 v = __ldg(pv + (size_t)c * 32);
+        float4 q = __ldg(q4 + c);
+        a = sqdiff_acc(a, q.x, v.x);
+        a = sqdiff_acc(a, q.y, v.y);
+        a = sqdiff_acc(a, q.z, v.z);
+        a = sqdiff_acc(a, q.w, v.w);
+    }
+    return a;
+}
+
+__global__ void finalize_kernel(FinalizeParams p) {
+    uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (q >= p.nq) return;
+    const uint32_t k = p.k;
+    float fd = __int_as_float(0x7f800000);
+    unsigned long long fk = ~0ull;
+    // (1) tensor-core survivors of this query (skipped when its buffer overflowed: the exact path redid it)
+    if (p.cand) {
+        uint32_t n = p.cand_cnt[q];
+        bool ovf = p.overflow[q] != 0 || n > p.capq;
+        if (!ovf) {
+            const float4* q4 = p.xq4 + (size_t)q * p.Dq;
+            for (uint32_t base = 0; base < n; base += 32) {
+                uint32_t i = base + lane;
+                bool have = i < n;
+                unsigned long long key = have ? p.cand[(size_t)q * p.capq + i] : ~0ull;
+                float d = have ? exact_row_distance(p.vecs, p.Dq, (uint32_t)key, q4) : __int_as_float(0x7f800000);
+                float td = __shfl_sync(kFull, fd, k - 1);
+                unsigned long long tk = __shfl_sync(kFull, fk, k - 1);
+                unsigned m = __ballot_sync(kFull, have && lex_less(d, key, td, tk));
+                while (m) {
+                    int src = __ffs(m) - 1;
+                    m &= m - 1;
+                    float cd = __shfl_sync(kFull, d, src);
+                    unsigned long long ck = __shfl_sync(kFull, key, src);
+                    td = __shfl_sync(kFull, fd, k - 1);
+                    tk = __shfl_sync(kFull, fk, k - 1);
+                    if (lex_less(cd, ck, td, tk)) warp_insert_lex64(cd, ck, fd, fk, lane);
+                }
+            }
+        }
+    }
+    // (2) slots of the exact scan kernels (sorted by (distance, row); slot order = (probe rank, segment))
+    if (p.slot_off) {
+        uint32_t s0 = p.slot_off[(size_t)q * p.nprobe], s1 = p.slot_off[(size_t)(q + 1) * p.nprobe];
+        for (uint32_t s = s0; s < s1; s++) {
+            float d = __int_as_float(0x7f800000);
+            uint32_t r = kNoRow;
+            if (lane < (int)k) {
+                d = p.slot_d[(size_t)s * k + lane];
+                r = p.slot_r[(size_t)s * k + lane];
+            }
+            unsigned long long key = ((unsigned long long)p.slot_rank[s] << 32) | r;
+            float td = __shfl_sync(kFull, fd, k - 1);
+            unsigned long long tk = __shfl_sync(kFull, fk, k - 1);
+            unsigned m = __ballot_sync(kFull, r != kNoRow && lex_less(d, key, td, tk));
+            while (m) {
+                int src = __ffs(m) - 1;
+                m &= m - 1;
+                float cd = __shfl_sync(kFull, d, src);
+                unsigned long long ck = __shfl_sync(kFull, key, src);
+                td = __shfl_sync(kFull, fd, k - 1);
+                tk = __shfl_sync(kFull, fk, k - 1);
+                if (lex_less(cd, ck, td, tk)) warp_insert_lex64(cd, ck, fd, fk, lane);
+            }
+        }
+    }
+    if (lane < (int)k) {
+        size_t o = (size_t)q * p.kout + lane;
+        bool ok = fk != ~0ull;
+        uint32_t row = (uint32_t)fk;
+        p.D[o] = ok ? fd : __int_as_float(0x7f800000);
+        p.I[o] = ok ? (int64_t)p.row_ext[row] : -1;
+        if (p.out_rows) p.out_rows[o] = ok ? row : kNoRow;
+    }
+}
+
+// ====================================================================================
+// launchers
+// ====================================================================================
+bool tc_supported(int Dq, uint32_t k) {
+    if (k == 0 || k > 32) return false;
+    if (Dq < 2 || (Dq & 1)) return false;  // K = 8 floats per MMA = two 16-byte chunks
+    return tc_smem_layout(Dq, (int)k).total <= 227 * 1024;
+}
+void launch_row_norms(const float4* vecs, int Dq, const uint32_t* row_src, size_t nrows, float* vn_scaled, float* vn_true,
+                      cudaStream_t st) {
+    if (!nrows) return;
+    row_norm_kernel<<<(unsigned)ceil_div(nrows, 256), 256, 0, st>>>(vecs, Dq, row_src, nrows, vn_scaled, vn_true);
+    VIDX_LAUNCHED();
+}
+void launch_query_norms(const float4* xq4, int Dq, uint32_t nq, float* qn, uint32_t* gthr_bits, uint32_t* cand_cnt,
+                        uint32_t* overflow, cudaStream_t st) {
+    if (!nq) return;
+    query_norm_kernel<<<(unsigned)ceil_div(nq, 128), 128, 0, st>>>(xq4, Dq, nq, qn, gthr_bits, cand_cnt, overflow);
+    VIDX_LAUNCHED();
+}
+void launch_tc_count(const uint32_t* probes, size_t npairs, const uint2* list_seg, uint32_t* list_cnt, cudaStream_t st) {
+    if (!npairs) return;
+    tc_count_kernel<<<(unsigned)ceil_div(npairs, 256), 256, 0, st>>>(probes, npairs, list_seg, list_cnt);
+    VIDX_LAUNCHED();
+}
+void launch_tc_fill(const uint32_t* probes, size_t npairs, uint32_t nprobe, const uint2* list_seg, const uint32_t* list_qoff,
+                    uint32_t* list_cur, uint2* list_qlist, cudaStream_t st) {
+    if (!npairs) return;
+    tc_fill_kernel<<<(unsigned)ceil_div(npairs, 256), 256, 0, st>>>(probes, npairs, nprobe, list_seg, list_qoff, list_cur, list_qlist);
+    VIDX_LAUNCHED();
+}
+void launch_tc_items(const uint32_t* list_cnt, const uint32_t* list_ngroups, uint32_t nlist, uint32_t* items_per_list,
+                     cudaStream_t st) {
+    if (!nlist) return;
+    tc_items_kernel<<<(unsigned)ceil_div(nlist, 256), 256, 0, st>>>(list_cnt, list_ngroups, nlist, items_per_list);
+    VIDX_LAUNCHED();
+}
+void launch_scan_tc(const TcParams& p, cudaStream_t st) {
+    static int sms = 0;
+    static size_t attr = 0;
+    if (!sms) {
+        int dev;
+        VIDX_CUDA(cudaGetDevice(&dev));
+        VIDX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    size_t smem = tc_smem_layout(p.Dq, (int)p.k).total;
+    if (smem > attr) {
+        VIDX_CUDA(cudaFuncSetAttribute(scan_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = smem;
+    }
+    scan_tc_kernel<<<sms, kTcThreads, smem, st>>>(p);
+    VIDX_LAUNCHED();
+}
+void launch_finalize(const FinalizeParams& p, cudaStream_t st) {
+    if (!p.nq) return;
+    finalize_kernel<<<(unsigned)ceil_div((size_t)p.nq * 32, 128), 128, 0, st>>>(p);
+    VIDX_LAUNCHED();
+}
+
+}  // namespace vidx

@@ -1,0 +1,64 @@
+// scan_tc.h -- tensor-core list scan (tcgen05 TF32 pre-filter + exact finalize).
+#pragma once
+#include "common.cuh"
+
+namespace vidx {
+
+struct TcParams {
+    const float4* vecs;            // interleaved groups
+    const float* vnorm;            // per row: (1-eps)*|v|^2, NaN for padding rows
+    int Dq;
+    const float4* xq4;             // queries, row-major, Dq float4 per row
+    const float* qnorm;            // per query |q|^2
+    const uint32_t* list_g0;       // first group of each list
+    const uint32_t* list_ngroups;  // groups of each list
+    const uint32_t* list_cnt;      // queries probing each list (this batch)
+    const uint32_t* list_qoff;     // CSR offsets into list_qlist
+    const uint2* list_qlist;       // (query, probe rank)
+    const uint32_t* item_off;      // nlist+1: prefix of work items per list
+    uint32_t nlist;
+    uint32_t* work_counter;
+    uint32_t* gthr_bits;           // per query: upper bound of the exact k-th best distance (float bits)
+    unsigned long long* cand;      // per query capq survivors: (rank << 32 | row)
+    uint32_t* cand_cnt;
+    uint32_t* overflow;
+    uint32_t capq;
+    uint32_t k;
+    float vn_max;                  // max |v|^2 over the stored rows
+};
+
+struct FinalizeParams {
+    uint32_t nq, nprobe, k, kout;
+    int Dq;
+    const float4* vecs;
+    const float4* xq4;
+    // tensor-core survivors (cand == nullptr: none)
+    const unsigned long long* cand;
+    const uint32_t* cand_cnt;
+    const uint32_t* overflow;
+    uint32_t capq;
+    // exact-path slots (slot_off == nullptr: none)
+    const uint32_t* slot_off;
+    const float* slot_d;
+    const uint32_t* slot_r;
+    const uint32_t* slot_rank;
+    const uint64_t* row_ext;
+    float* D;
+    int64_t* I;
+    uint32_t* out_rows;
+};
+
+bool tc_supported(int Dq, uint32_t k);
+void launch_row_norms(const float4* vecs, int Dq, const uint32_t* row_src, size_t nrows, float* vn_scaled, float* vn_true,
+                      cudaStream_t st);
+void launch_query_norms(const float4* xq4, int Dq, uint32_t nq, float* qn, uint32_t* gthr_bits, uint32_t* cand_cnt,
+                        uint32_t* overflow, cudaStream_t st);
+void launch_tc_count(const uint32_t* probes, size_t npairs, const uint2* list_seg, uint32_t* list_cnt, cudaStream_t st);
+void launch_tc_fill(const uint32_t* probes, size_t npairs, uint32_t nprobe, const uint2* list_seg, const uint32_t* list_qoff,
+                    uint32_t* list_cur, uint2* list_qlist, cudaStream_t st);
+void launch_tc_items(const uint32_t* list_cnt, const uint32_t* list_ngroups, uint32_t nlist, uint32_t* items_per_list,
+                     cudaStream_t st);
+void launch_scan_tc(const TcParams& p, cudaStream_t st);
+void launch_finalize(const FinalizeParams& p, cudaStream_t st);
+
+}  // namespace vidx

@@ -23,11 +23,11 @@ void launch_coarse_dist(const float4* cents, int ngroups, int Dq, const float4* 
 uint32_t select_kcap(uint32_t k);
 void launch_select_topk(const float* vals, const uint64_t* row_off, const uint32_t* row_len, uint64_t ld, uint32_t n_fixed,
                         uint64_t nrows, uint32_t k, uint32_t* out_pos, float* out_val, cudaStream_t st);
-void launch_group_count(const uint32_t* probes, size_t npairs, const uint2* list_seg, uint32_t* pair_ns,
-                        uint32_t* seg_cnt, cudaStream_t st);
+void launch_group_count(const uint32_t* probes, size_t npairs, uint32_t nprobe, const uint2* list_seg,
+                        const uint32_t* only_flag, uint32_t* pair_ns, uint32_t* seg_cnt, cudaStream_t st);
 void launch_group_fill(const uint32_t* probes, size_t npairs, uint32_t nprobe, const uint2* list_seg,
                        const uint32_t* slot_off, const uint32_t* seg_qoff, uint32_t* seg_cur, uint2* seg_qlist,
-                       uint32_t* slot_seg, cudaStream_t st);
+                       uint32_t* slot_seg, const uint32_t* only_flag, uint32_t* slot_rank, cudaStream_t st);
 void launch_group_items(const uint32_t* seg_cnt, uint32_t nseg, uint32_t sparse_max, ScanItem* dense, ScanItem* sparse,
                         uint32_t* counters, cudaStream_t st);
 bool sparse_supported(int Dq);

@@ -392,14 +392,16 @@ select_topk_kernel(const float* __restrict__ vals, const uint64_t* __restrict__ 
 // ------------------------------------------------------------------------------------
 // pair p = q*nprobe + r.  pair_ns[p] = segments of the probed list (0 for padding / lists
 // this rank does not own).  seg_cnt[s] += 1 for each of them.
-__global__ void group_count_kernel(const uint32_t* __restrict__ probes, size_t npairs,
-                                   const uint2* __restrict__ list_seg, uint32_t* __restrict__ pair_ns,
-                                   uint32_t* __restrict__ seg_cnt) {
+// only_flag (optional): per-query flag; when given, only queries whose flag is set take part
+// (the queries the tensor-core path handed back to the exact kernels).
+__global__ void group_count_kernel(const uint32_t* __restrict__ probes, size_t npairs, uint32_t nprobe,
+                                   const uint2* __restrict__ list_seg, const uint32_t* __restrict__ only_flag,
+                                   uint32_t* __restrict__ pair_ns, uint32_t* __restrict__ seg_cnt) {
     size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= npairs) return;
     uint32_t l = probes[p];
     uint32_t ns = 0;
-    if (l != kNoRow) {
+    if (l != kNoRow && (!only_flag || only_flag[p / nprobe])) {
         uint2 sr = list_seg[l];
         uint32_t s0 = sr.x, s1 = sr.y;
         ns = s1 - s0;
@@ -411,12 +413,14 @@ __global__ void group_count_kernel(const uint32_t* __restrict__ probes, size_t n
 __global__ void group_fill_kernel(const uint32_t* __restrict__ probes, size_t npairs, uint32_t nprobe,
                                   const uint2* __restrict__ list_seg, const uint32_t* __restrict__ slot_off,
                                   const uint32_t* __restrict__ seg_qoff, uint32_t* __restrict__ seg_cur,
-                                  uint2* __restrict__ seg_qlist, uint32_t* __restrict__ slot_seg) {
+                                  uint2* __restrict__ seg_qlist, uint32_t* __restrict__ slot_seg,
+                                  const uint32_t* __restrict__ only_flag, uint32_t* __restrict__ slot_rank) {
     size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= npairs) return;
     uint32_t l = probes[p];
     if (l == kNoRow) return;
     uint32_t q = (uint32_t)(p / nprobe);
+    if (only_flag && !only_flag[q]) return;
     uint2 sr = list_seg[l];
     uint32_t s0 = sr.x, s1 = sr.y;
     uint32_t slot = slot_off[p];
@@ -424,6 +428,7 @@ __global__ void group_fill_kernel(const uint32_t* __restrict__ probes, size_t np
         uint32_t i = atomicAdd(&seg_cur[s], 1u);
         seg_qlist[seg_qoff[s] + i] = make_uint2(q, slot);
         slot_seg[slot] = s;
+        slot_rank[slot] = (uint32_t)(p - (size_t)q * nprobe);
     }
 }
 // One thread per segment: split its query list into dense items (tiles of <= 64 queries
@@ -1036,18 +1041,19 @@ void launch_select_topk(const float* vals, const uint64_t* row_off, const uint32
                                                                     out_val);
     VIDX_LAUNCHED();
 }
-void launch_group_count(const uint32_t* probes, size_t npairs, const uint2* list_seg, uint32_t* pair_ns,
-                        uint32_t* seg_cnt, cudaStream_t st) {
+void launch_group_count(const uint32_t* probes, size_t npairs, uint32_t nprobe, const uint2* list_seg,
+                        const uint32_t* only_flag, uint32_t* pair_ns, uint32_t* seg_cnt, cudaStream_t st) {
     if (!npairs) return;
-    group_count_kernel<<<(unsigned)ceil_div(npairs, 256), 256, 0, st>>>(probes, npairs, list_seg, pair_ns, seg_cnt);
+    group_count_kernel<<<(unsigned)ceil_div(npairs, 256), 256, 0, st>>>(probes, npairs, nprobe, list_seg, only_flag, pair_ns,
+                                                                         seg_cnt);
     VIDX_LAUNCHED();
 }
 void launch_group_fill(const uint32_t* probes, size_t npairs, uint32_t nprobe, const uint2* list_seg,
                        const uint32_t* slot_off, const uint32_t* seg_qoff, uint32_t* seg_cur, uint2* seg_qlist,
-                       uint32_t* slot_seg, cudaStream_t st) {
+                       uint32_t* slot_seg, const uint32_t* only_flag, uint32_t* slot_rank, cudaStream_t st) {
     if (!npairs) return;
-    group_fill_kernel<<<(unsigned)ceil_div(npairs, 256), 256, 0, st>>>(probes, npairs, nprobe, list_seg, slot_off,
-                                                                        seg_qoff, seg_cur, seg_qlist, slot_seg);
+    group_fill_kernel<<<(unsigned)ceil_div(npairs, 256), 256, 0, st>>>(probes, npairs, nprobe, list_seg, slot_off, seg_qoff,
+                                                                        seg_cur, seg_qlist, slot_seg, only_flag, slot_rank);
     VIDX_LAUNCHED();
 }
 void launch_group_items(const uint32_t* seg_cnt, uint32_t nseg, uint32_t sparse_max, ScanItem* dense, ScanItem* sparse,

@@ -26,7 +26,8 @@ vp = C.c_void_p
 class SearchStats(C.Structure):
     _fields_ = [(n, C.c_double) for n in ("ms_coarse", "ms_select", "ms_group", "ms_scan", "ms_merge", "ms_total")] + [
         (n, u64) for n in ("scan_bytes_algorithmic", "scan_bytes_logical", "scan_flops", "coarse_flops", "n_pairs",
-                           "n_dense_items", "n_sparse_items", "kernel_launches")]
+                           "n_dense_items", "n_sparse_items", "kernel_launches")] + [("ms_scan_tc", C.c_double)] + [
+        (n, u64) for n in ("n_tc_items", "n_tc_survivors", "n_tc_overflow", "tc_mma_flops")]
 
     def asdict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -81,6 +82,7 @@ _SIGS = {
     "vidx_partition_shards": (i32, [u64p, u64, i32, i32p]),
     "vidx_merge_topk_device": (i32, [i32, vp, vp, u32, u64, u64, vp, vp, vp]),
     "vidx_set_profiling": (i32, [vp, i32]),
+    "vidx_set_scan_mode": (i32, [vp, i32]),
     "vidx_get_search_stats": (i32, [vp, C.POINTER(SearchStats)]),
     "vidx_kernel_launch_count": (u64, []),
 }
@@ -277,6 +279,10 @@ class Index:
 
     def set_profiling(self, on=True):
         check(lib().vidx_set_profiling(self.h, 1 if on else 0))
+
+    def set_scan_mode(self, mode):
+        """0 = tensor-core pre-filter + exact re-check (default), 1 = exact kernels only."""
+        check(lib().vidx_set_scan_mode(self.h, mode))
 
     def stats(self):
         s = SearchStats()
