@@ -423,7 +423,8 @@ void Index::search_device(const float* d_xq, uint64_t nq, uint64_t k_req, uint64
             exclusive_scan_u32(w.list_cnt.as<uint32_t>(), w.list_qoff.as<uint32_t>(), nlist, w.scan_tmp.as<uint32_t>(), st);
             launch_tc_fill(w.probes.as<uint32_t>(), npairs, np, d_list_seg.as<uint2>(), w.list_qoff.as<uint32_t>(),
                            w.list_cur.as<uint32_t>(), w.list_qlist.as<uint2>(), st);
-            launch_tc_items(w.list_cnt.as<uint32_t>(), d_list_ng.as<uint32_t>(), (uint32_t)nlist, w.items_per_list.as<uint32_t>(), st);
+            launch_tc_items(w.list_cnt.as<uint32_t>(), d_list_ng.as<uint32_t>(), (uint32_t)nlist,
+                            reinterpret_cast<unsigned long long*>(counters + 12), counters + 10, w.items_per_list.as<uint32_t>(), st);
             exclusive_scan_u32(w.items_per_list.as<uint32_t>(), w.item_off.as<uint32_t>(), nlist, w.scan_tmp.as<uint32_t>(), st);
         }
         if (profiling) VIDX_CUDA(cudaEventRecord(ev[3], st));
@@ -442,6 +443,7 @@ void Index::search_device(const float* d_xq, uint64_t nq, uint64_t k_req, uint64
             tp.item_off = w.item_off.as<uint32_t>();
             tp.nlist = (uint32_t)nlist;
             tp.work_counter = counters + 8;
+            tp.chunk_tiles = counters + 10;
             tp.gthr_bits = w.gthr.as<uint32_t>();
             tp.cand = w.cand.as<unsigned long long>();
             tp.cand_cnt = w.cand_cnt.as<uint32_t>();

@@ -35,7 +35,8 @@ namespace vidx {
 constexpr int kTcThreads = 192;
 constexpr int kTcM = 128;            // queries per tile (UMMA M)
 constexpr int kTcTileGroups = 4;     // 4 groups = 128 vectors per stage
-constexpr int kTcChunkTiles = 64;    // tiles per work item (8192 vectors)
+constexpr int kTcMaxChunkTiles = 64; // tiles per work item: chosen on the device, 4..64 (512..8192 vectors)
+constexpr int kTcStageCap = 512;     // survivors staged in shared memory per epilogue warp before a flush
 constexpr int kTcTmemCols = 256;     // 2 accumulator stages x 128 columns
 constexpr float kTcEps = 2.5e-3f;    // see header comment; needed: ~1.99e-3
 
@@ -183,15 +184,30 @@ __global__ void tc_fill_kernel(const uint32_t* __restrict__ probes, size_t npair
     uint32_t i = atomicAdd(&list_cur[l], 1u);
     list_qlist[list_qoff[l] + i] = make_uint2((uint32_t)(p / nprobe), (uint32_t)(p % nprobe));
 }
-// items of list l = (#query tiles) x (#vector chunks); enumerated chunk-major so that CTAs running
-// at the same time share a vector chunk (L2 reuse) and a query's later chunks start with a warm bound.
-__global__ void tc_items_kernel(const uint32_t* __restrict__ list_cnt, const uint32_t* __restrict__ list_ngroups, uint32_t nlist,
-                                uint32_t* __restrict__ items_per_list) {
+// Work items of list l = (#query tiles) x (#vector chunks), enumerated chunk-major so that CTAs
+// running at the same time share a vector chunk (L2 reuse) and a query's later chunks start with a
+// warm bound.  The chunk length is chosen on the device from the total tile count so that a batch
+// yields several items per SM: ctl[0] = total (query tile x vector tile) count, ctl[1] = chunk tiles.
+__global__ void tc_work_kernel(const uint32_t* __restrict__ list_cnt, const uint32_t* __restrict__ list_ngroups, uint32_t nlist,
+                               unsigned long long* __restrict__ total) {
     uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= nlist) return;
     uint32_t c = list_cnt[l];
+    if (!c) return;
     uint32_t ntiles = (list_ngroups[l] + kTcTileGroups - 1) / kTcTileGroups;
-    uint32_t nch = (ntiles + kTcChunkTiles - 1) / kTcChunkTiles;
+    atomicAdd(total, (unsigned long long)((c + kTcM - 1) / kTcM) * ntiles);
+}
+__global__ void tc_items_kernel(const uint32_t* __restrict__ list_cnt, const uint32_t* __restrict__ list_ngroups, uint32_t nlist,
+                                const unsigned long long* __restrict__ total, uint32_t num_sms, uint32_t* __restrict__ chunk_out,
+                                uint32_t* __restrict__ items_per_list) {
+    uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long per = *total / (8ull * num_sms);
+    uint32_t chunk = (uint32_t)min((unsigned long long)kTcMaxChunkTiles, max(4ull, per));
+    if (l == 0) *chunk_out = chunk;
+    if (l >= nlist) return;
+    uint32_t c = list_cnt[l];
+    uint32_t ntiles = (list_ngroups[l] + kTcTileGroups - 1) / kTcTileGroups;
+    uint32_t nch = (ntiles + chunk - 1) / chunk;
     items_per_list[l] = c ? ((c + kTcM - 1) / kTcM) * nch : 0u;
 }
 
@@ -207,21 +223,24 @@ __host__ __device__ inline TcSmemLayout tc_smem_layout(int Dq, int k) {
     L.b_bytes = (uint32_t)Dq * kTcTileGroups * 512;
     L.off_b = L.a_bytes;
     L.off_vn = L.off_b + 2 * L.b_bytes;
-    L.off_tk = L.off_vn + 2 * 128 * 4;
-    L.off_q = L.off_tk + (uint32_t)k * 128 * 4;
+    L.off_tk = L.off_vn + 2 * 128 * 4;                  // survivor staging: [4 warps][cap] row ids + lanes
+    L.off_q = L.off_tk + 4u * kTcStageCap * 8;
+    (void)k;
     L.off_bar = L.off_q + 128 * 8;
     L.off_misc = L.off_bar + 8 * 8;
     L.total = L.off_misc + 64;
     return L;
 }
 
+template <int KR>
 __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const TcSmemLayout L = tc_smem_layout(p.Dq, (int)p.k);
     unsigned char* sA = smem;
     unsigned char* sB = smem + L.off_b;
     float* s_vn = reinterpret_cast<float*>(smem + L.off_vn);
-    float* s_tk = reinterpret_cast<float*>(smem + L.off_tk);
+    uint32_t* s_crow = reinterpret_cast<uint32_t*>(smem + L.off_tk);            // [4][cap] survivor row ids
+    uint32_t* s_clane = s_crow + 4 * kTcStageCap;                               // [4][cap] owning lane (query row)
     uint2* s_q = reinterpret_cast<uint2*>(smem + L.off_q);
     uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + L.off_bar);
     uint64_t* bar_empty = bar_full + 2;
@@ -251,6 +270,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
     const uint32_t tmem_base = s_misc[0];
     const uint32_t total_items = p.item_off[p.nlist];
     const uint32_t idesc = make_idesc_tf32(kTcM, 32);
+    const uint32_t chunk_tiles = *p.chunk_tiles;
     uint32_t it = 0;  // tiles processed so far by this CTA (stage = it & 1, phase = (it >> 1) & 1)
 
     for (;;) {
@@ -272,7 +292,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
         const uint32_t ngl = p.list_ngroups[l];
         const uint32_t g_list = p.list_g0[l];
         const uint32_t ntiles = (ngl + kTcTileGroups - 1) / kTcTileGroups;
-        const uint32_t t0 = chunk * kTcChunkTiles, t1 = min(ntiles, t0 + kTcChunkTiles);
+        const uint32_t t0 = chunk * chunk_tiles, t1 = min(ntiles, t0 + chunk_tiles);
         const uint32_t nq_tile = min((uint32_t)kTcM, cnt - qt * kTcM);
 
         if (tid < kTcM) s_q[tid] = tid < (int)nq_tile ? p.list_qlist[p.list_qoff[l] + qt * kTcM + tid] : make_uint2(kNoRow, 0);
@@ -285,10 +305,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
             if (q != kNoRow) v = p.xq4[(size_t)q * Dq + c];
             reinterpret_cast<float4*>(sA)[idx] = v;
         }
-        if (warp >= 2) {
-            int row = (warp & 3) * 32 + lane;
-            for (uint32_t i = 0; i < p.k; i++) s_tk[i * 128 + row] = __int_as_float(0x7f800000);
-        }
+        if (warp >= 2 && lane == 0) s_misc[4 + (warp & 3)] = 0;  // survivor staging counters
         fence_proxy_async();
         __syncthreads();
 
@@ -343,7 +360,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
             const int row = quarter * 32 + lane;
             const uint2 qi = s_q[row];
             const bool valid = qi.x != kNoRow;
-            const uint32_t q = qi.x, rank = qi.y;
+            const uint32_t q = qi.x;
+            uint32_t* s_cnt = &s_misc[4 + quarter];
+            uint32_t* crow = s_crow + quarter * kTcStageCap;
+            uint32_t* clane = s_clane + quarter * kTcStageCap;
             float base_t = 0.0f, delta = 0.0f, tau_g = __int_as_float(0x7f800000);
             if (valid) {
                 float qn = p.qnorm[q];
@@ -352,9 +372,27 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
                 float g = __uint_as_float(p.gthr_bits[q]);
                 tau_g = (g - base_t) + 1e-5f * (g + base_t);
             }
-            float t_k = __int_as_float(0x7f800000);
-            uint32_t pos_max = 0;
+            // the k smallest filter values seen so far in this item, DESCENDING: r[0] is the k-th smallest
+            // (+inf until k values were seen); slots >= k are pinned at -inf and never take part
+            float r[KR];
+#pragma unroll
+            for (int i = 0; i < KR; i++) r[i] = i < (int)p.k ? __int_as_float(0x7f800000) : -__int_as_float(0x7f800000);
             float P = tau_g;
+            // survivors are staged in shared memory per warp and flushed cooperatively, so the hot loop
+            // never waits on a global atomic
+            auto flush = [&]() {
+                __syncwarp();
+                uint32_t n = min(*s_cnt, (uint32_t)kTcStageCap);
+                for (uint32_t i = lane; i < n; i += 32) {
+                    uint2 e = s_q[quarter * 32 + clane[i]];
+                    uint32_t idx = atomicAdd(&p.cand_cnt[e.x], 1u);
+                    if (idx < p.capq) p.cand[(size_t)e.x * p.capq + idx] = ((unsigned long long)e.y << 32) | crow[i];
+                    else p.overflow[e.x] = 1u;
+                }
+                __syncwarp();
+                if (lane == 0) *s_cnt = 0;
+                __syncwarp();
+            };
             for (uint32_t t = t0; t < t1; t++, it++) {
                 const uint32_t s = it & 1, ph = (it >> 1) & 1;
                 mbar_wait(&bar_tfull[s], ph);
@@ -374,39 +412,47 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
                             tv[1] = __fmaf_rn(acc[4 * j4 + 1], -2.0f, n4.y);
                             tv[2] = __fmaf_rn(acc[4 * j4 + 2], -2.0f, n4.z);
                             tv[3] = __fmaf_rn(acc[4 * j4 + 3], -2.0f, n4.w);
+                            // (NaN norms of padding rows fail every comparison)
+                            if (fminf(fminf(tv[0], tv[1]), fminf(tv[2], tv[3])) <= P) {
 #pragma unroll
-                            for (int u = 0; u < 4; u++) {
-                                if (tv[u] <= P) {
-                                    // survivor: record it, tighten the local bound
-                                    uint32_t idx = atomicAdd(&p.cand_cnt[q], 1u);
-                                    if (idx < p.capq)
-                                        p.cand[(size_t)q * p.capq + idx] = ((unsigned long long)rank << 32) | (row0 + cb * 32 + 4 * j4 + u);
-                                    else
-                                        p.overflow[q] = 1u;
-                                    if (tv[u] < t_k) {
-                                        s_tk[pos_max * 128 + row] = tv[u];
-                                        float m = -__int_as_float(0x7f800000);
-                                        uint32_t pm = 0;
-                                        for (uint32_t i = 0; i < p.k; i++) {
-                                            float v = s_tk[i * 128 + row];
-                                            if (v > m) { m = v; pm = i; }
+                                for (int u = 0; u < 4; u++) {
+                                    if (tv[u] <= P) {
+                                        const uint32_t rowid = row0 + cb * 32 + 4 * j4 + u;
+                                        uint32_t idx = atomicAdd(s_cnt, 1u);
+                                        if (idx < (uint32_t)kTcStageCap) {
+                                            crow[idx] = rowid;
+                                            clane[idx] = (uint32_t)lane;
+                                        } else {  // staging full (pathological tie storms): append directly
+                                            uint32_t gi = atomicAdd(&p.cand_cnt[q], 1u);
+                                            if (gi < p.capq) p.cand[(size_t)q * p.capq + gi] = ((unsigned long long)qi.y << 32) | rowid;
+                                            else p.overflow[q] = 1u;
                                         }
-                                        t_k = m;
-                                        pos_max = pm;
-                                        P = fminf(tau_g, t_k + delta);
+                                        if (tv[u] < r[0]) {
+                                            r[0] = tv[u];
+#pragma unroll
+                                            for (int i = 0; i + 1 < KR; i++) {
+                                                float hi = fmaxf(r[i], r[i + 1]), lo = fminf(r[i], r[i + 1]);
+                                                r[i] = hi;
+                                                r[i + 1] = lo;
+                                            }
+                                            P = fminf(tau_g, r[0] + delta);
+                                        }
                                     }
                                 }
                             }
                         }
                     }
+                    __syncwarp();
+                    if (*s_cnt >= (uint32_t)(kTcStageCap / 2)) flush();
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bar_tempty[s]);
             }
+            flush();
             // publish an upper bound of this query's exact k-th best distance
-            if (valid && t_k < __int_as_float(0x7f800000)) {
-                float U = fmaxf(t_k + base_t + delta, 0.0f);
+            if (valid && r[0] < __int_as_float(0x7f800000)) {
+                float U = fmaxf(r[0] + base_t + delta, 0.0f);
                 U = U + 1e-5f * U;
                 atomicMin(&p.gthr_bits[q], __float_as_uint(U));
             }
@@ -549,27 +595,39 @@ void launch_tc_fill(const uint32_t* probes, size_t npairs, uint32_t nprobe, cons
     tc_fill_kernel<<<(unsigned)ceil_div(npairs, 256), 256, 0, st>>>(probes, npairs, nprobe, list_seg, list_qoff, list_cur, list_qlist);
     VIDX_LAUNCHED();
 }
-void launch_tc_items(const uint32_t* list_cnt, const uint32_t* list_ngroups, uint32_t nlist, uint32_t* items_per_list,
-                     cudaStream_t st) {
-    if (!nlist) return;
-    tc_items_kernel<<<(unsigned)ceil_div(nlist, 256), 256, 0, st>>>(list_cnt, list_ngroups, nlist, items_per_list);
-    VIDX_LAUNCHED();
-}
-void launch_scan_tc(const TcParams& p, cudaStream_t st) {
+static int tc_num_sms() {
     static int sms = 0;
-    static size_t attr = 0;
     if (!sms) {
         int dev;
         VIDX_CUDA(cudaGetDevice(&dev));
         VIDX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     }
-    size_t smem = tc_smem_layout(p.Dq, (int)p.k).total;
+    return sms;
+}
+void launch_tc_items(const uint32_t* list_cnt, const uint32_t* list_ngroups, uint32_t nlist, unsigned long long* total,
+                     uint32_t* chunk_out, uint32_t* items_per_list, cudaStream_t st) {
+    if (!nlist) return;
+    tc_work_kernel<<<(unsigned)ceil_div(nlist, 256), 256, 0, st>>>(list_cnt, list_ngroups, nlist, total);
+    VIDX_LAUNCHED();
+    tc_items_kernel<<<(unsigned)ceil_div(nlist, 256), 256, 0, st>>>(list_cnt, list_ngroups, nlist, total, (uint32_t)tc_num_sms(),
+                                                                   chunk_out, items_per_list);
+    VIDX_LAUNCHED();
+}
+template <int KR>
+static void launch_scan_tc_kr(const TcParams& p, size_t smem, cudaStream_t st) {
+    static size_t attr = 0;
     if (smem > attr) {
-        VIDX_CUDA(cudaFuncSetAttribute(scan_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        VIDX_CUDA(cudaFuncSetAttribute(scan_tc_kernel<KR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = smem;
     }
-    scan_tc_kernel<<<sms, kTcThreads, smem, st>>>(p);
+    scan_tc_kernel<KR><<<tc_num_sms(), kTcThreads, smem, st>>>(p);
     VIDX_LAUNCHED();
+}
+void launch_scan_tc(const TcParams& p, cudaStream_t st) {
+    size_t smem = tc_smem_layout(p.Dq, (int)p.k).total;
+    if (p.k <= 8) launch_scan_tc_kr<8>(p, smem, st);
+    else if (p.k <= 16) launch_scan_tc_kr<16>(p, smem, st);
+    else launch_scan_tc_kr<32>(p, smem, st);
 }
 void launch_finalize(const FinalizeParams& p, cudaStream_t st) {
     if (!p.nq) return;

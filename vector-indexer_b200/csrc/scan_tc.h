@@ -18,6 +18,7 @@ struct TcParams {
     const uint32_t* item_off;      // nlist+1: prefix of work items per list
     uint32_t nlist;
     uint32_t* work_counter;
+    const uint32_t* chunk_tiles;   // tiles per work item, chosen by tc_items_kernel
     uint32_t* gthr_bits;           // per query: upper bound of the exact k-th best distance (float bits)
     unsigned long long* cand;      // per query capq survivors: (rank << 32 | row)
     uint32_t* cand_cnt;
@@ -56,8 +57,8 @@ void launch_query_norms(const float4* xq4, int Dq, uint32_t nq, float* qn, uint3
 void launch_tc_count(const uint32_t* probes, size_t npairs, const uint2* list_seg, uint32_t* list_cnt, cudaStream_t st);
 void launch_tc_fill(const uint32_t* probes, size_t npairs, uint32_t nprobe, const uint2* list_seg, const uint32_t* list_qoff,
                     uint32_t* list_cur, uint2* list_qlist, cudaStream_t st);
-void launch_tc_items(const uint32_t* list_cnt, const uint32_t* list_ngroups, uint32_t nlist, uint32_t* items_per_list,
-                     cudaStream_t st);
+void launch_tc_items(const uint32_t* list_cnt, const uint32_t* list_ngroups, uint32_t nlist, unsigned long long* total,
+                     uint32_t* chunk_out, uint32_t* items_per_list, cudaStream_t st);
 void launch_scan_tc(const TcParams& p, cudaStream_t st);
 void launch_finalize(const FinalizeParams& p, cudaStream_t st);
 
