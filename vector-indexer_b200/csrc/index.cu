@@ -279,12 +279,15 @@ void Index::apply_partition() {
 struct Index::Workspace {
     DevBuf xq_pad, dist, probes, pair_ns, slot_off, seg_cnt, seg_qoff, seg_cur, seg_qlist, slot_seg, dense, sparse, counters,
         scan_tmp, cand_d, cand_r, alld, row_off, row_len, sel_pos, sel_val, rows, stats, slot_rank, list_cnt, list_cur, list_qoff,
-        list_qlist, items_per_list, item_off, qnorm, gthr, cand_cnt, overflow, cand;
+        list_qlist, items_per_list, item_off, qnorm, gthr, cand_cnt, overflow, cand, list_cnt0, list_cur0, list_qoff0, list_qlist0,
+        items_per_list0, item_off0;
 };
 void Index::delete_workspace() {
     delete ws;
     ws = nullptr;
 }
+
+constexpr uint32_t kSeedTiles = 16;  // seeding pass: first 2048 vectors of each query's nearest list
 
 // stats: distinct probed lists -> algorithmic bytes; (query, list) pairs -> logical bytes / flops
 __global__ void list_stats_kernel(const uint32_t* __restrict__ list_cnt, const uint32_t* __restrict__ list_len, uint32_t nlist,
@@ -397,7 +400,7 @@ void Index::search_device(const float* d_xq, uint64_t nq, uint64_t k_req, uint64
         if (want_list_cnt) {
             w.list_cnt.reserve(((size_t)nlist + 1) * 4);
             VIDX_CUDA(cudaMemsetAsync(w.list_cnt.p, 0, ((size_t)nlist + 1) * 4, st));
-            launch_tc_count(w.probes.as<uint32_t>(), npairs, d_list_seg.as<uint2>(), w.list_cnt.as<uint32_t>(), st);
+            launch_tc_count(w.probes.as<uint32_t>(), npairs, np, false, d_list_seg.as<uint2>(), w.list_cnt.as<uint32_t>(), st);
         }
         if (profiling) {
             w.stats.reserve(64);
@@ -421,11 +424,27 @@ void Index::search_device(const float* d_xq, uint64_t nq, uint64_t k_req, uint64
                                w.overflow.as<uint32_t>(), st);
             VIDX_CUDA(cudaMemsetAsync(w.list_cur.p, 0, ((size_t)nlist + 1) * 4, st));
             exclusive_scan_u32(w.list_cnt.as<uint32_t>(), w.list_qoff.as<uint32_t>(), nlist, w.scan_tmp.as<uint32_t>(), st);
-            launch_tc_fill(w.probes.as<uint32_t>(), npairs, np, d_list_seg.as<uint2>(), w.list_qoff.as<uint32_t>(),
+            launch_tc_fill(w.probes.as<uint32_t>(), npairs, np, false, d_list_seg.as<uint2>(), w.list_qoff.as<uint32_t>(),
                            w.list_cur.as<uint32_t>(), w.list_qlist.as<uint2>(), st);
             launch_tc_items(w.list_cnt.as<uint32_t>(), d_list_ng.as<uint32_t>(), (uint32_t)nlist,
-                            reinterpret_cast<unsigned long long*>(counters + 12), counters + 10, w.items_per_list.as<uint32_t>(), st);
+                            reinterpret_cast<unsigned long long*>(counters + 12), 0, counters + 10, w.items_per_list.as<uint32_t>(), st);
             exclusive_scan_u32(w.items_per_list.as<uint32_t>(), w.item_off.as<uint32_t>(), nlist, w.scan_tmp.as<uint32_t>(), st);
+            // seeding pass: the same grouping restricted to each query's nearest list
+            w.list_cnt0.reserve(((size_t)nlist + 1) * 4);
+            w.list_cur0.reserve(((size_t)nlist + 1) * 4);
+            w.list_qoff0.reserve(((size_t)nlist + 1) * 4);
+            w.list_qlist0.reserve(std::max<size_t>(nqb, 1) * 8);
+            w.items_per_list0.reserve(((size_t)nlist + 1) * 4);
+            w.item_off0.reserve(((size_t)nlist + 1) * 4);
+            VIDX_CUDA(cudaMemsetAsync(w.list_cnt0.p, 0, ((size_t)nlist + 1) * 4, st));
+            VIDX_CUDA(cudaMemsetAsync(w.list_cur0.p, 0, ((size_t)nlist + 1) * 4, st));
+            launch_tc_count(w.probes.as<uint32_t>(), npairs, np, true, d_list_seg.as<uint2>(), w.list_cnt0.as<uint32_t>(), st);
+            exclusive_scan_u32(w.list_cnt0.as<uint32_t>(), w.list_qoff0.as<uint32_t>(), nlist, w.scan_tmp.as<uint32_t>(), st);
+            launch_tc_fill(w.probes.as<uint32_t>(), npairs, np, true, d_list_seg.as<uint2>(), w.list_qoff0.as<uint32_t>(),
+                           w.list_cur0.as<uint32_t>(), w.list_qlist0.as<uint2>(), st);
+            launch_tc_items(w.list_cnt0.as<uint32_t>(), d_list_ng.as<uint32_t>(), (uint32_t)nlist, nullptr, kSeedTiles, counters + 11,
+                            w.items_per_list0.as<uint32_t>(), st);
+            exclusive_scan_u32(w.items_per_list0.as<uint32_t>(), w.item_off0.as<uint32_t>(), nlist, w.scan_tmp.as<uint32_t>(), st);
         }
         if (profiling) VIDX_CUDA(cudaEventRecord(ev[3], st));
         if (tc) {
@@ -437,13 +456,7 @@ void Index::search_device(const float* d_xq, uint64_t nq, uint64_t k_req, uint64
             tp.qnorm = w.qnorm.as<float>();
             tp.list_g0 = d_list_g0.as<uint32_t>();
             tp.list_ngroups = d_list_ng.as<uint32_t>();
-            tp.list_cnt = w.list_cnt.as<uint32_t>();
-            tp.list_qoff = w.list_qoff.as<uint32_t>();
-            tp.list_qlist = w.list_qlist.as<uint2>();
-            tp.item_off = w.item_off.as<uint32_t>();
             tp.nlist = (uint32_t)nlist;
-            tp.work_counter = counters + 8;
-            tp.chunk_tiles = counters + 10;
             tp.gthr_bits = w.gthr.as<uint32_t>();
             tp.cand = w.cand.as<unsigned long long>();
             tp.cand_cnt = w.cand_cnt.as<uint32_t>();
@@ -451,6 +464,24 @@ void Index::search_device(const float* d_xq, uint64_t nq, uint64_t k_req, uint64
             tp.capq = capq;
             tp.k = (uint32_t)k;
             tp.vn_max = vn_max;
+            tp.seed_tiles = kSeedTiles;
+            // pass 1: seed every query's bound from the head of its nearest list
+            tp.mode = 1;
+            tp.list_cnt = w.list_cnt0.as<uint32_t>();
+            tp.list_qoff = w.list_qoff0.as<uint32_t>();
+            tp.list_qlist = w.list_qlist0.as<uint2>();
+            tp.item_off = w.item_off0.as<uint32_t>();
+            tp.work_counter = counters + 9;
+            tp.chunk_tiles = counters + 11;
+            launch_scan_tc(tp, st);
+            // pass 2: everything else, starting from warm bounds
+            tp.mode = 0;
+            tp.list_cnt = w.list_cnt.as<uint32_t>();
+            tp.list_qoff = w.list_qoff.as<uint32_t>();
+            tp.list_qlist = w.list_qlist.as<uint2>();
+            tp.item_off = w.item_off.as<uint32_t>();
+            tp.work_counter = counters + 8;
+            tp.chunk_tiles = counters + 10;
             launch_scan_tc(tp, st);
         }
         if (profiling) VIDX_CUDA(cudaEventRecord(ev[8], st));

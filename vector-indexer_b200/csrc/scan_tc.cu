@@ -163,20 +163,23 @@ __global__ void query_norm_kernel(const float4* __restrict__ xq4, int Dq, uint32
 // ------------------------------------------------------------------------------------------
 // grouping by list
 // ------------------------------------------------------------------------------------------
-__global__ void tc_count_kernel(const uint32_t* __restrict__ probes, size_t npairs, const uint2* __restrict__ list_seg,
-                                uint32_t* __restrict__ list_cnt) {
+// rank0_only: only each query's nearest list (the seeding pass).
+__global__ void tc_count_kernel(const uint32_t* __restrict__ probes, size_t npairs, uint32_t nprobe, int rank0_only,
+                                const uint2* __restrict__ list_seg, uint32_t* __restrict__ list_cnt) {
     size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= npairs) return;
+    if (rank0_only && (p % nprobe) != 0) return;
     uint32_t l = probes[p];
     if (l == kNoRow) return;
     uint2 sr = list_seg[l];
     if (sr.y > sr.x) atomicAdd(&list_cnt[l], 1u);  // owned, non-empty list
 }
-__global__ void tc_fill_kernel(const uint32_t* __restrict__ probes, size_t npairs, uint32_t nprobe,
+__global__ void tc_fill_kernel(const uint32_t* __restrict__ probes, size_t npairs, uint32_t nprobe, int rank0_only,
                                const uint2* __restrict__ list_seg, const uint32_t* __restrict__ list_qoff,
                                uint32_t* __restrict__ list_cur, uint2* __restrict__ list_qlist) {
     size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= npairs) return;
+    if (rank0_only && (p % nprobe) != 0) return;
     uint32_t l = probes[p];
     if (l == kNoRow) return;
     uint2 sr = list_seg[l];
@@ -190,6 +193,7 @@ __global__ void tc_fill_kernel(const uint32_t* __restrict__ probes, size_t npair
 // yields several items per SM: ctl[0] = total (query tile x vector tile) count, ctl[1] = chunk tiles.
 __global__ void tc_work_kernel(const uint32_t* __restrict__ list_cnt, const uint32_t* __restrict__ list_ngroups, uint32_t nlist,
                                unsigned long long* __restrict__ total) {
+    // (main pass only; the seeding pass has one fixed-size chunk per list)
     uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= nlist) return;
     uint32_t c = list_cnt[l];
@@ -198,15 +202,21 @@ __global__ void tc_work_kernel(const uint32_t* __restrict__ list_cnt, const uint
     atomicAdd(total, (unsigned long long)((c + kTcM - 1) / kTcM) * ntiles);
 }
 __global__ void tc_items_kernel(const uint32_t* __restrict__ list_cnt, const uint32_t* __restrict__ list_ngroups, uint32_t nlist,
-                                const unsigned long long* __restrict__ total, uint32_t num_sms, uint32_t* __restrict__ chunk_out,
-                                uint32_t* __restrict__ items_per_list) {
+                                const unsigned long long* __restrict__ total, uint32_t num_sms, uint32_t seed_tiles,
+                                uint32_t* __restrict__ chunk_out, uint32_t* __restrict__ items_per_list) {
     uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned long long per = *total / (8ull * num_sms);
-    uint32_t chunk = (uint32_t)min((unsigned long long)kTcMaxChunkTiles, max(4ull, per));
+    uint32_t chunk;
+    if (seed_tiles) {
+        chunk = seed_tiles;
+    } else {
+        unsigned long long per = *total / (8ull * num_sms);
+        chunk = (uint32_t)min((unsigned long long)kTcMaxChunkTiles, max(8ull, per));
+    }
     if (l == 0) *chunk_out = chunk;
     if (l >= nlist) return;
     uint32_t c = list_cnt[l];
     uint32_t ntiles = (list_ngroups[l] + kTcTileGroups - 1) / kTcTileGroups;
+    if (seed_tiles) ntiles = min(ntiles, seed_tiles);
     uint32_t nch = (ntiles + chunk - 1) / chunk;
     items_per_list[l] = c ? ((c + kTcM - 1) / kTcM) * nch : 0u;
 }
@@ -291,7 +301,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
         const uint32_t chunk = local / nqt, qt = local - chunk * nqt;
         const uint32_t ngl = p.list_ngroups[l];
         const uint32_t g_list = p.list_g0[l];
-        const uint32_t ntiles = (ngl + kTcTileGroups - 1) / kTcTileGroups;
+        uint32_t ntiles = (ngl + kTcTileGroups - 1) / kTcTileGroups;
+        if (p.mode == 1) ntiles = min(ntiles, p.seed_tiles);  // seeding pass: the head of each query's nearest list
         const uint32_t t0 = chunk * chunk_tiles, t1 = min(ntiles, t0 + chunk_tiles);
         const uint32_t nq_tile = min((uint32_t)kTcM, cnt - qt * kTcM);
 
@@ -378,6 +389,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
 #pragma unroll
             for (int i = 0; i < KR; i++) r[i] = i < (int)p.k ? __int_as_float(0x7f800000) : -__int_as_float(0x7f800000);
             float P = tau_g;
+            // rows whose nearest list this is already scanned its first seed_tiles tiles in the seeding pass
+            const bool skip_seeded = p.mode == 0 && qi.y == 0;
+            float published = __int_as_float(0x7f800000);
             // survivors are staged in shared memory per warp and flushed cooperatively, so the hot loop
             // never waits on a global atomic
             auto flush = [&]() {
@@ -399,10 +413,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
                 tc_fence_after();
                 const uint32_t ng = min((uint32_t)kTcTileGroups, ngl - t * kTcTileGroups);
                 const uint32_t row0 = (g_list + t * kTcTileGroups) * 32u;
+                const bool active = valid && !(skip_seeded && t < p.seed_tiles);
+                // bounds other CTAs published for this query meanwhile (latency hidden behind the tile)
+                uint32_t g_bits = valid ? __ldcg(&p.gthr_bits[q]) : 0x7f800000u;
                 for (uint32_t cb = 0; cb < ng; cb++) {
                     float acc[32];
                     tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + s * 128 + cb * 32, acc);
-                    if (valid) {
+                    if (active) {
                         const float4* vn4 = reinterpret_cast<const float4*>(s_vn + s * 128 + cb * 32);
 #pragma unroll
                         for (int j4 = 0; j4 < 8; j4++) {
@@ -448,14 +465,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bar_tempty[s]);
+                if (valid) {
+                    // publish / adopt upper bounds of this query's exact k-th best distance
+                    if (r[0] < published) {
+                        published = r[0];
+                        float U = fmaxf(r[0] + base_t + delta, 0.0f);
+                        U = U + 1e-5f * U;
+                        atomicMin(&p.gthr_bits[q], __float_as_uint(U));
+                    }
+                    float g = __uint_as_float(g_bits);
+                    tau_g = fminf(tau_g, (g - base_t) + 1e-5f * (g + base_t));
+                    P = fminf(P, tau_g);
+                }
             }
             flush();
-            // publish an upper bound of this query's exact k-th best distance
-            if (valid && r[0] < __int_as_float(0x7f800000)) {
-                float U = fmaxf(r[0] + base_t + delta, 0.0f);
-                U = U + 1e-5f * U;
-                atomicMin(&p.gthr_bits[q], __float_as_uint(U));
-            }
         }
     }
     tc_fence_before();
@@ -584,15 +607,17 @@ void launch_query_norms(const float4* xq4, int Dq, uint32_t nq, float* qn, uint3
     query_norm_kernel<<<(unsigned)ceil_div(nq, 128), 128, 0, st>>>(xq4, Dq, nq, qn, gthr_bits, cand_cnt, overflow);
     VIDX_LAUNCHED();
 }
-void launch_tc_count(const uint32_t* probes, size_t npairs, const uint2* list_seg, uint32_t* list_cnt, cudaStream_t st) {
+void launch_tc_count(const uint32_t* probes, size_t npairs, uint32_t nprobe, bool rank0_only, const uint2* list_seg,
+                     uint32_t* list_cnt, cudaStream_t st) {
     if (!npairs) return;
-    tc_count_kernel<<<(unsigned)ceil_div(npairs, 256), 256, 0, st>>>(probes, npairs, list_seg, list_cnt);
+    tc_count_kernel<<<(unsigned)ceil_div(npairs, 256), 256, 0, st>>>(probes, npairs, nprobe, rank0_only ? 1 : 0, list_seg, list_cnt);
     VIDX_LAUNCHED();
 }
-void launch_tc_fill(const uint32_t* probes, size_t npairs, uint32_t nprobe, const uint2* list_seg, const uint32_t* list_qoff,
-                    uint32_t* list_cur, uint2* list_qlist, cudaStream_t st) {
+void launch_tc_fill(const uint32_t* probes, size_t npairs, uint32_t nprobe, bool rank0_only, const uint2* list_seg,
+                    const uint32_t* list_qoff, uint32_t* list_cur, uint2* list_qlist, cudaStream_t st) {
     if (!npairs) return;
-    tc_fill_kernel<<<(unsigned)ceil_div(npairs, 256), 256, 0, st>>>(probes, npairs, nprobe, list_seg, list_qoff, list_cur, list_qlist);
+    tc_fill_kernel<<<(unsigned)ceil_div(npairs, 256), 256, 0, st>>>(probes, npairs, nprobe, rank0_only ? 1 : 0, list_seg, list_qoff,
+                                                                     list_cur, list_qlist);
     VIDX_LAUNCHED();
 }
 static int tc_num_sms() {
@@ -605,12 +630,14 @@ static int tc_num_sms() {
     return sms;
 }
 void launch_tc_items(const uint32_t* list_cnt, const uint32_t* list_ngroups, uint32_t nlist, unsigned long long* total,
-                     uint32_t* chunk_out, uint32_t* items_per_list, cudaStream_t st) {
+                     uint32_t seed_tiles, uint32_t* chunk_out, uint32_t* items_per_list, cudaStream_t st) {
     if (!nlist) return;
-    tc_work_kernel<<<(unsigned)ceil_div(nlist, 256), 256, 0, st>>>(list_cnt, list_ngroups, nlist, total);
-    VIDX_LAUNCHED();
+    if (!seed_tiles) {
+        tc_work_kernel<<<(unsigned)ceil_div(nlist, 256), 256, 0, st>>>(list_cnt, list_ngroups, nlist, total);
+        VIDX_LAUNCHED();
+    }
     tc_items_kernel<<<(unsigned)ceil_div(nlist, 256), 256, 0, st>>>(list_cnt, list_ngroups, nlist, total, (uint32_t)tc_num_sms(),
-                                                                   chunk_out, items_per_list);
+                                                                   seed_tiles, chunk_out, items_per_list);
     VIDX_LAUNCHED();
 }
 template <int KR>

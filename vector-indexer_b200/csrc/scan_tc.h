@@ -26,6 +26,8 @@ struct TcParams {
     uint32_t capq;
     uint32_t k;
     float vn_max;                  // max |v|^2 over the stored rows
+    uint32_t mode;                 // 0 = main pass, 1 = seeding pass (head of each query's nearest list only)
+    uint32_t seed_tiles;           // tiles per list covered by the seeding pass (0 = no seeding pass was run)
 };
 
 struct FinalizeParams {
@@ -54,11 +56,12 @@ void launch_row_norms(const float4* vecs, int Dq, const uint32_t* row_src, size_
                       cudaStream_t st);
 void launch_query_norms(const float4* xq4, int Dq, uint32_t nq, float* qn, uint32_t* gthr_bits, uint32_t* cand_cnt,
                         uint32_t* overflow, cudaStream_t st);
-void launch_tc_count(const uint32_t* probes, size_t npairs, const uint2* list_seg, uint32_t* list_cnt, cudaStream_t st);
-void launch_tc_fill(const uint32_t* probes, size_t npairs, uint32_t nprobe, const uint2* list_seg, const uint32_t* list_qoff,
-                    uint32_t* list_cur, uint2* list_qlist, cudaStream_t st);
+void launch_tc_count(const uint32_t* probes, size_t npairs, uint32_t nprobe, bool rank0_only, const uint2* list_seg,
+                     uint32_t* list_cnt, cudaStream_t st);
+void launch_tc_fill(const uint32_t* probes, size_t npairs, uint32_t nprobe, bool rank0_only, const uint2* list_seg,
+                    const uint32_t* list_qoff, uint32_t* list_cur, uint2* list_qlist, cudaStream_t st);
 void launch_tc_items(const uint32_t* list_cnt, const uint32_t* list_ngroups, uint32_t nlist, unsigned long long* total,
-                     uint32_t* chunk_out, uint32_t* items_per_list, cudaStream_t st);
+                     uint32_t seed_tiles, uint32_t* chunk_out, uint32_t* items_per_list, cudaStream_t st);
 void launch_scan_tc(const TcParams& p, cudaStream_t st);
 void launch_finalize(const FinalizeParams& p, cudaStream_t st);
 
