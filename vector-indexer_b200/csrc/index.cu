@@ -202,7 +202,9 @@ void Index::build_lists(const float* d_data, uint64_t n, const uint32_t* labels,
         h2d(d_list_g0.as<uint32_t>(), g0.data(), g0.size(), stream);
         h2d(d_list_ng.as<uint32_t>(), ng.data(), ng.size(), stream);
         h2d(d_list_len.as<uint32_t>(), list_len.data(), list_len.size(), stream);
-        d_vnorm.reserve(std::max<uint64_t>(nrows, 1) * 4);
+        d_vnorm.reserve((std::max<uint64_t>(nrows, 1) + 256) * 4);  // + slack: the tile copy always reads 128 norms
+        VIDX_CUDA(cudaMemsetAsync(d_vnorm.p, 0xff, (std::max<uint64_t>(nrows, 1) + 256) * 4, stream));
+        if (tc_supported(Dq, 1)) make_tc_tensor_map(tc_tmap, d_vecs.p, ngroups, Dq);
         DevBuf d_vntrue;
         d_vntrue.reserve(std::max<uint64_t>(nrows, 1) * 4);
         launch_row_norms(d_vecs.as<float4>(), Dq, d_row_src.as<uint32_t>(), nrows, d_vnorm.as<float>(), d_vntrue.as<float>(), stream);
@@ -473,7 +475,7 @@ void Index::search_device(const float* d_xq, uint64_t nq, uint64_t k_req, uint64
             tp.item_off = w.item_off0.as<uint32_t>();
             tp.work_counter = counters + 9;
             tp.chunk_tiles = counters + 11;
-            launch_scan_tc(tp, st);
+            launch_scan_tc(tc_tmap, tp, st);
             // pass 2: everything else, starting from warm bounds
             tp.mode = 0;
             tp.list_cnt = w.list_cnt.as<uint32_t>();
@@ -482,7 +484,7 @@ void Index::search_device(const float* d_xq, uint64_t nq, uint64_t k_req, uint64
             tp.item_off = w.item_off.as<uint32_t>();
             tp.work_counter = counters + 8;
             tp.chunk_tiles = counters + 10;
-            launch_scan_tc(tp, st);
+            launch_scan_tc(tc_tmap, tp, st);
         }
         if (profiling) VIDX_CUDA(cudaEventRecord(ev[8], st));
 

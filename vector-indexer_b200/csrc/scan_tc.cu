@@ -18,17 +18,22 @@
 //   keys the exact scan kernels order by.  The final answer is bit-identical to the exact path.
 //
 // Kernel anatomy (one CTA per SM, persistent, 6 warps):
-//   warp 0  producer : cp.async.bulk (1-D TMA) of 4 groups (128 vectors, full D) + their scaled
-//                      norms per stage, completion on an mbarrier (complete_tx::bytes)
+//   warp 0  producer : ONE 3-D TMA tensor copy (cp.async.bulk.tensor) per stage brings 4 groups
+//                      (128 vectors, full D, 64 KB) and permutes them on the fly -- the tensor map
+//                      lists the dims as (16B x 32 lanes, group, chunk), so the box lands in shared
+//                      memory chunk-major: [Dq][128 vectors][16 B]; plus a 1-D bulk copy of the 128
+//                      scaled norms; completion on an mbarrier (complete_tx::bytes)
 //   warp 1  MMA      : one elected thread issues tcgen05.mma.cta_group::1.kind::tf32, M=128
-//                      queries x N=32 vectors x K=8 per instruction; operands are read from shared
-//                      memory through no-swizzle K-major descriptors -- the interleaved group
-//                      layout [Dq][32 vectors][16 B] IS the UMMA core-matrix layout (8 rows x 16 B
-//                      contiguous, SBO = 128 B, LBO = 512 B), so list data needs no reshaping
+//                      queries x N=128 vectors x K=8 per instruction; operands are read from shared
+//                      memory through no-swizzle K-major descriptors: that chunk-major layout IS
+//                      the UMMA core-matrix layout (8 rows x 16 B contiguous, SBO = 128 B,
+//                      LBO = 2048 B), for the query tile and the list tile alike
 //   warps 2-5 epilogue: tcgen05.ld the 128x128 fp32 accumulator tile from TMEM (double buffered,
 //                      256 columns), one thread per query row, 1 FFMA + 1 compare per element
 // Accumulators never leave the SM; HBM sees each list tile once per 128-query tile.
 #include "scan_tc.h"
+
+#include <cudaTypedefs.h>
 
 namespace vidx {
 
@@ -74,6 +79,12 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                      smem_u32(smem_dst)),
                  "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* tmap, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
                  : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -243,7 +254,7 @@ __host__ __device__ inline TcSmemLayout tc_smem_layout(int Dq, int k) {
 }
 
 template <int KR>
-__global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
+__global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const TcSmemLayout L = tc_smem_layout(p.Dq, (int)p.k);
     unsigned char* sA = smem;
@@ -261,6 +272,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int Dq = p.Dq;
     if (tid == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap)) : "memory");
         for (int i = 0; i < 2; i++) {
             mbar_init(&bar_full[i], 1);
             mbar_init(&bar_empty[i], 1);
@@ -279,7 +291,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
     tc_fence_after();
     const uint32_t tmem_base = s_misc[0];
     const uint32_t total_items = p.item_off[p.nlist];
-    const uint32_t idesc = make_idesc_tf32(kTcM, 32);
+    const uint32_t idesc = make_idesc_tf32(kTcM, kTcTileGroups * 32);
     const uint32_t chunk_tiles = *p.chunk_tiles;
     uint32_t it = 0;  // tiles processed so far by this CTA (stage = it & 1, phase = (it >> 1) & 1)
 
@@ -327,13 +339,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
                     const uint32_t s = it & 1, ph = (it >> 1) & 1;
                     mbar_wait(&bar_empty[s], ph ^ 1);
                     mbar_wait(&bar_tempty[s], ph ^ 1);  // norms buffer of this stage is read by the epilogue
-                    const uint32_t ng = min((uint32_t)kTcTileGroups, ngl - t * kTcTileGroups);
-                    const uint32_t gbytes = (uint32_t)Dq * 512;
-                    mbar_expect_tx(&bar_full[s], ng * gbytes + ng * 128);
+                    // the box always covers 4 groups: groups past the end of this list belong to the next
+                    // list (or are zero-filled past the end of the store) and are ignored by the epilogue
+                    mbar_expect_tx(&bar_full[s], L.b_bytes + 512);
                     const size_t g0 = (size_t)g_list + (size_t)t * kTcTileGroups;
-                    for (uint32_t g = 0; g < ng; g++)
-                        bulk_g2s(sB + s * L.b_bytes + g * gbytes, p.vecs + (g0 + g) * (size_t)Dq * 32, gbytes, &bar_full[s]);
-                    bulk_g2s(s_vn + s * 128, p.vnorm + g0 * 32, ng * 128, &bar_full[s]);
+                    tma_load_3d(sB + s * L.b_bytes, &tmap, 0, (int)g0, 0, &bar_full[s]);
+                    bulk_g2s(s_vn + s * 128, p.vnorm + g0 * 32, 512, &bar_full[s]);
                 }
             } else {
                 it += t1 - t0;
@@ -348,15 +359,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
                     mbar_wait(&bar_full[s], ph);
                     mbar_wait(&bar_tempty[s], ph ^ 1);
                     tc_fence_after();
-                    const uint32_t ng = min((uint32_t)kTcTileGroups, ngl - t * kTcTileGroups);
                     const uint32_t b_addr = smem_u32(sB + s * L.b_bytes);
-                    for (uint32_t g = 0; g < ng; g++) {
-                        const uint32_t d_tmem = tmem_base + s * 128 + g * 32;
-                        for (int ks = 0; ks < (Dq >> 1); ks++) {
-                            uint64_t da = make_smem_desc(a_addr + ks * 4096, 2048, 128);
-                            uint64_t db = make_smem_desc(b_addr + g * Dq * 512 + ks * 1024, 512, 128);
-                            tc_mma_tf32(d_tmem, da, db, idesc, ks > 0 ? 1u : 0u);
-                        }
+                    const uint32_t d_tmem = tmem_base + s * 128;
+                    for (int ks = 0; ks < (Dq >> 1); ks++) {
+                        uint64_t da = make_smem_desc(a_addr + ks * 4096, 2048, 128);
+                        uint64_t db = make_smem_desc(b_addr + ks * 4096, 2048, 128);
+                        tc_mma_tf32(d_tmem, da, db, idesc, ks > 0 ? 1u : 0u);
                     }
                     tc_commit(&bar_empty[s]);   // smem stage free once these MMAs have read it
                     tc_commit(&bar_tfull[s]);   // accumulator stage ready for the epilogue
@@ -641,20 +649,43 @@ void launch_tc_items(const uint32_t* list_cnt, const uint32_t* list_ngroups, uin
     VIDX_LAUNCHED();
 }
 template <int KR>
-static void launch_scan_tc_kr(const TcParams& p, size_t smem, cudaStream_t st) {
+static void launch_scan_tc_kr(const CUtensorMap& tmap, const TcParams& p, size_t smem, cudaStream_t st) {
     static size_t attr = 0;
     if (smem > attr) {
         VIDX_CUDA(cudaFuncSetAttribute(scan_tc_kernel<KR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = smem;
     }
-    scan_tc_kernel<KR><<<tc_num_sms(), kTcThreads, smem, st>>>(p);
+    scan_tc_kernel<KR><<<tc_num_sms(), kTcThreads, smem, st>>>(tmap, p);
     VIDX_LAUNCHED();
 }
-void launch_scan_tc(const TcParams& p, cudaStream_t st) {
+void launch_scan_tc(const TcTensorMap& tm, const TcParams& p, cudaStream_t st) {
+    const CUtensorMap& tmap = *reinterpret_cast<const CUtensorMap*>(tm.bytes);
     size_t smem = tc_smem_layout(p.Dq, (int)p.k).total;
-    if (p.k <= 8) launch_scan_tc_kr<8>(p, smem, st);
-    else if (p.k <= 16) launch_scan_tc_kr<16>(p, smem, st);
-    else launch_scan_tc_kr<32>(p, smem, st);
+    if (p.k <= 8) launch_scan_tc_kr<8>(tmap, p, smem, st);
+    else if (p.k <= 16) launch_scan_tc_kr<16>(tmap, p, smem, st);
+    else launch_scan_tc_kr<32>(tmap, p, smem, st);
+}
+// 3-D view of the interleaved store for the list-tile copy: dim0 = the 128 floats (32 lanes x 16 B)
+// of one (group, chunk) row, dim1 = group (stride Dq*512 B), dim2 = chunk (stride 512 B).  A box of
+// (128, 4, Dq) therefore arrives in shared memory as [chunk][4 groups x 32 vectors][16 B].
+void make_tc_tensor_map(TcTensorMap& out, const void* vecs, uint64_t ngroups, int Dq) {
+    static_assert(sizeof(CUtensorMap) <= sizeof(out.bytes), "tensor map storage");
+    static PFN_cuTensorMapEncodeTiled encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        VIDX_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) throw CudaError("cuTensorMapEncodeTiled is not available in this driver");
+        encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(fn);
+    }
+    cuuint64_t dims[3] = {128, std::max<uint64_t>(ngroups, 1), (cuuint64_t)Dq};
+    cuuint64_t strides[2] = {(cuuint64_t)Dq * 512, 512};
+    cuuint32_t box[3] = {128, (cuuint32_t)kTcTileGroups, (cuuint32_t)Dq};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = encode(reinterpret_cast<CUtensorMap*>(out.bytes), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(vecs), dims,
+                        strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw CudaError("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
 }
 void launch_finalize(const FinalizeParams& p, cudaStream_t st) {
     if (!p.nq) return;
