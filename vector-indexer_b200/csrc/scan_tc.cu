@@ -43,6 +43,9 @@ constexpr int kTcTileGroups = 4;     // 4 groups = 128 vectors per stage
 constexpr int kTcMaxChunkTiles = 64; // tiles per work item: chosen on the device, 4..64 (512..8192 vectors)
 constexpr int kTcStageCap = 512;     // survivors staged in shared memory per epilogue warp before a flush
 constexpr int kTcTmemCols = 256;     // 2 accumulator stages x 128 columns
+constexpr int kTcStages = 8;         // shared-memory ring: stages of 128 vectors x 32 dims (16 KB)
+constexpr int kTcStageChunks = 8;    // 16-byte chunks (4 floats) of every vector per stage
+constexpr uint32_t kTcStageBytes = kTcStageChunks * kTcTileGroups * 512;
 constexpr float kTcEps = 2.5e-3f;    // see header comment; needed: ~1.99e-3
 
 // ---- PTX wrappers ------------------------------------------------------------------------
@@ -236,19 +239,18 @@ __global__ void tc_items_kernel(const uint32_t* __restrict__ list_cnt, const uin
 // the tensor-core scan
 // ------------------------------------------------------------------------------------------
 struct TcSmemLayout {
-    uint32_t a_bytes, b_bytes, off_b, off_vn, off_tk, off_q, off_bar, off_misc, total;
+    uint32_t a_bytes, off_b, off_vn, off_stage, off_q, off_bar, off_misc, total;
 };
 __host__ __device__ inline TcSmemLayout tc_smem_layout(int Dq, int k) {
-    TcSmemLayout L;
-    L.a_bytes = (uint32_t)Dq * kTcM * 16;
-    L.b_bytes = (uint32_t)Dq * kTcTileGroups * 512;
-    L.off_b = L.a_bytes;
-    L.off_vn = L.off_b + 2 * L.b_bytes;
-    L.off_tk = L.off_vn + 2 * 128 * 4;                  // survivor staging: [4 warps][cap] row ids + lanes
-    L.off_q = L.off_tk + 4u * kTcStageCap * 8;
     (void)k;
+    TcSmemLayout L;
+    L.a_bytes = (uint32_t)Dq * kTcM * 16;                  // query tile, [chunk][128 rows][16 B]
+    L.off_b = L.a_bytes;                                   // ring of kTcStages list-tile K-slices
+    L.off_vn = L.off_b + kTcStages * kTcStageBytes;        // scaled norms of the tile, per accumulator stage
+    L.off_stage = L.off_vn + 2 * 128 * 4;                  // survivor staging: [4 warps][cap] row ids + lanes
+    L.off_q = L.off_stage + 4u * kTcStageCap * 8;
     L.off_bar = L.off_q + 128 * 8;
-    L.off_misc = L.off_bar + 8 * 8;
+    L.off_misc = L.off_bar + (2 * kTcStages + 4) * 8;
     L.total = L.off_misc + 64;
     return L;
 }
@@ -260,22 +262,24 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(const __grid_con
     unsigned char* sA = smem;
     unsigned char* sB = smem + L.off_b;
     float* s_vn = reinterpret_cast<float*>(smem + L.off_vn);
-    uint32_t* s_crow = reinterpret_cast<uint32_t*>(smem + L.off_tk);            // [4][cap] survivor row ids
+    uint32_t* s_crow = reinterpret_cast<uint32_t*>(smem + L.off_stage);         // [4][cap] survivor row ids
     uint32_t* s_clane = s_crow + 4 * kTcStageCap;                               // [4][cap] owning lane (query row)
     uint2* s_q = reinterpret_cast<uint2*>(smem + L.off_q);
-    uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + L.off_bar);
-    uint64_t* bar_empty = bar_full + 2;
-    uint64_t* bar_tfull = bar_full + 4;
-    uint64_t* bar_tempty = bar_full + 6;
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + L.off_bar);  // [kTcStages] K-slice landed
+    uint64_t* bar_empty = bar_full + kTcStages;                          // [kTcStages] K-slice consumed by the MMAs
+    uint64_t* bar_tfull = bar_empty + kTcStages;                         // [2] accumulator tile complete
+    uint64_t* bar_tempty = bar_tfull + 2;                                // [2] accumulator tile (and its norms) drained
     uint32_t* s_misc = reinterpret_cast<uint32_t*>(smem + L.off_misc);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int Dq = p.Dq;
     if (tid == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap)) : "memory");
-        for (int i = 0; i < 2; i++) {
+        for (int i = 0; i < kTcStages; i++) {
             mbar_init(&bar_full[i], 1);
             mbar_init(&bar_empty[i], 1);
+        }
+        for (int i = 0; i < 2; i++) {
             mbar_init(&bar_tfull[i], 1);
             mbar_init(&bar_tempty[i], 4);
         }
@@ -293,7 +297,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(const __grid_con
     const uint32_t total_items = p.item_off[p.nlist];
     const uint32_t idesc = make_idesc_tf32(kTcM, kTcTileGroups * 32);
     const uint32_t chunk_tiles = *p.chunk_tiles;
-    uint32_t it = 0;  // tiles processed so far by this CTA (stage = it & 1, phase = (it >> 1) & 1)
+    const int nkc = (Dq + kTcStageChunks - 1) / kTcStageChunks;  // K-slices per tile
+    uint32_t it = 0;  // tiles processed so far by this CTA (accumulator stage = it & 1, phase = (it >> 1) & 1)
+    uint32_t ks_it = 0;  // K-slices processed so far (ring stage = ks_it % kTcStages, phase = (ks_it / kTcStages) & 1)
 
     for (;;) {
         if (tid == 0) s_misc[1] = atomicAdd(p.work_counter, 1u);
@@ -321,12 +327,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(const __grid_con
         if (tid < kTcM) s_q[tid] = tid < (int)nq_tile ? p.list_qlist[p.list_qoff[l] + qt * kTcM + tid] : make_uint2(kNoRow, 0);
         __syncthreads();
         // A tile: [c][128 rows][16 B] (core matrices of 8 rows x 16 B, SBO 128 B, LBO 2048 B)
-        for (int idx = tid; idx < Dq * kTcM; idx += kTcThreads) {
-            int c = idx >> 7, r = idx & 127;
-            uint32_t q = s_q[r].x;
-            float4 v = make_float4(0, 0, 0, 0);
-            if (q != kNoRow) v = p.xq4[(size_t)q * Dq + c];
-            reinterpret_cast<float4*>(sA)[idx] = v;
+        for (int base = 0; base < Dq * kTcM; base += kTcThreads * 8) {
+            float4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {  // issue the gathers first, then store: 8 loads in flight per thread
+                int idx = base + u * kTcThreads + tid;
+                v[u] = make_float4(0, 0, 0, 0);
+                if (idx < Dq * kTcM) {
+                    uint32_t q = s_q[idx & 127].x;
+                    if (q != kNoRow) v[u] = __ldg(&p.xq4[(size_t)q * Dq + (idx >> 7)]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                int idx = base + u * kTcThreads + tid;
+                if (idx < Dq * kTcM) reinterpret_cast<float4*>(sA)[idx] = v[u];
+            }
         }
         if (warp >= 2 && lane == 0) s_misc[4 + (warp & 3)] = 0;  // survivor staging counters
         fence_proxy_async();
@@ -336,43 +352,56 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(const __grid_con
             // ===== producer =====
             if (lane == 0) {
                 for (uint32_t t = t0; t < t1; t++, it++) {
-                    const uint32_t s = it & 1, ph = (it >> 1) & 1;
-                    mbar_wait(&bar_empty[s], ph ^ 1);
-                    mbar_wait(&bar_tempty[s], ph ^ 1);  // norms buffer of this stage is read by the epilogue
-                    // the box always covers 4 groups: groups past the end of this list belong to the next
-                    // list (or are zero-filled past the end of the store) and are ignored by the epilogue
-                    mbar_expect_tx(&bar_full[s], L.b_bytes + 512);
+                    const uint32_t a = it & 1, aph = (it >> 1) & 1;
                     const size_t g0 = (size_t)g_list + (size_t)t * kTcTileGroups;
-                    tma_load_3d(sB + s * L.b_bytes, &tmap, 0, (int)g0, 0, &bar_full[s]);
-                    bulk_g2s(s_vn + s * 128, p.vnorm + g0 * 32, 512, &bar_full[s]);
+                    for (int kc = 0; kc < nkc; kc++, ks_it++) {
+                        const uint32_t s = ks_it % kTcStages, ph = (ks_it / kTcStages) & 1;
+                        mbar_wait(&bar_empty[s], ph ^ 1);
+                        // The box always covers 4 groups x 8 chunks: groups past the end of this list belong to
+                        // the next list, chunks past Dq are zero-filled; neither is used.
+                        const bool last = kc == nkc - 1;
+                        if (last) mbar_wait(&bar_tempty[a], aph ^ 1);  // norms slot of this accumulator stage is free
+                        mbar_expect_tx(&bar_full[s], kTcStageBytes + (last ? 512u : 0u));
+                        tma_load_3d(sB + s * kTcStageBytes, &tmap, 0, (int)g0, kc * kTcStageChunks, &bar_full[s]);
+                        if (last) bulk_g2s(s_vn + a * 128, p.vnorm + g0 * 32, 512, &bar_full[s]);
+                    }
                 }
             } else {
                 it += t1 - t0;
+                ks_it += (t1 - t0) * nkc;
             }
             it = __shfl_sync(kFull, it, 0);
+            ks_it = __shfl_sync(kFull, ks_it, 0);
         } else if (warp == 1) {
             // ===== MMA issuer =====
             if (lane == 0) {
                 const uint32_t a_addr = smem_u32(sA);
                 for (uint32_t t = t0; t < t1; t++, it++) {
-                    const uint32_t s = it & 1, ph = (it >> 1) & 1;
-                    mbar_wait(&bar_full[s], ph);
-                    mbar_wait(&bar_tempty[s], ph ^ 1);
-                    tc_fence_after();
-                    const uint32_t b_addr = smem_u32(sB + s * L.b_bytes);
-                    const uint32_t d_tmem = tmem_base + s * 128;
-                    for (int ks = 0; ks < (Dq >> 1); ks++) {
-                        uint64_t da = make_smem_desc(a_addr + ks * 4096, 2048, 128);
-                        uint64_t db = make_smem_desc(b_addr + ks * 4096, 2048, 128);
-                        tc_mma_tf32(d_tmem, da, db, idesc, ks > 0 ? 1u : 0u);
+                    const uint32_t a = it & 1, aph = (it >> 1) & 1;
+                    mbar_wait(&bar_tempty[a], aph ^ 1);
+                    const uint32_t d_tmem = tmem_base + a * 128;
+                    for (int kc = 0; kc < nkc; kc++, ks_it++) {
+                        const uint32_t s = ks_it % kTcStages, ph = (ks_it / kTcStages) & 1;
+                        mbar_wait(&bar_full[s], ph);
+                        tc_fence_after();
+                        const uint32_t b_addr = smem_u32(sB + s * kTcStageBytes);
+                        const int nks = min(kTcStageChunks / 2, (Dq >> 1) - kc * (kTcStageChunks / 2));
+                        for (int ks = 0; ks < nks; ks++) {
+                            // 16-byte chunk c of all 128 rows is one 2 KB block in both tiles
+                            uint64_t da = make_smem_desc(a_addr + (kc * kTcStageChunks + 2 * ks) * 2048, 2048, 128);
+                            uint64_t db = make_smem_desc(b_addr + 2 * ks * 2048, 2048, 128);
+                            tc_mma_tf32(d_tmem, da, db, idesc, (kc | ks) ? 1u : 0u);
+                        }
+                        tc_commit(&bar_empty[s]);  // K-slice free once these MMAs have read it
                     }
-                    tc_commit(&bar_empty[s]);   // smem stage free once these MMAs have read it
-                    tc_commit(&bar_tfull[s]);   // accumulator stage ready for the epilogue
+                    tc_commit(&bar_tfull[a]);      // accumulator tile ready for the epilogue
                 }
             } else {
                 it += t1 - t0;
+                ks_it += (t1 - t0) * nkc;
             }
             it = __shfl_sync(kFull, it, 0);
+            ks_it = __shfl_sync(kFull, ks_it, 0);
         } else {
             // ===== epilogue: one thread per query row =====
             const int quarter = warp & 3;
@@ -667,7 +696,8 @@ void launch_scan_tc(const TcTensorMap& tm, const TcParams& p, cudaStream_t st) {
 }
 // 3-D view of the interleaved store for the list-tile copy: dim0 = the 128 floats (32 lanes x 16 B)
 // of one (group, chunk) row, dim1 = group (stride Dq*512 B), dim2 = chunk (stride 512 B).  A box of
-// (128, 4, Dq) therefore arrives in shared memory as [chunk][4 groups x 32 vectors][16 B].
+// (128, 4, 8) -- one K-slice of a list tile -- therefore arrives in shared memory as
+// [chunk][4 groups x 32 vectors][16 B].
 void make_tc_tensor_map(TcTensorMap& out, const void* vecs, uint64_t ngroups, int Dq) {
     static_assert(sizeof(CUtensorMap) <= sizeof(out.bytes), "tensor map storage");
     static PFN_cuTensorMapEncodeTiled encode = nullptr;
@@ -680,7 +710,7 @@ void make_tc_tensor_map(TcTensorMap& out, const void* vecs, uint64_t ngroups, in
     }
     cuuint64_t dims[3] = {128, std::max<uint64_t>(ngroups, 1), (cuuint64_t)Dq};
     cuuint64_t strides[2] = {(cuuint64_t)Dq * 512, 512};
-    cuuint32_t box[3] = {128, (cuuint32_t)kTcTileGroups, (cuuint32_t)Dq};
+    cuuint32_t box[3] = {128, (cuuint32_t)kTcTileGroups, (cuuint32_t)kTcStageChunks};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = encode(reinterpret_cast<CUtensorMap*>(out.bytes), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(vecs), dims,
                         strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
