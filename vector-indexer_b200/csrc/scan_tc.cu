@@ -28,8 +28,9 @@
 //                      memory through no-swizzle K-major descriptors: that chunk-major layout IS
 //                      the UMMA core-matrix layout (8 rows x 16 B contiguous, SBO = 128 B,
 //                      LBO = 2048 B), for the query tile and the list tile alike
-//   warps 2-5 epilogue: tcgen05.ld the 128x128 fp32 accumulator tile from TMEM (double buffered,
-//                      256 columns), one thread per query row, 1 FFMA + 1 compare per element
+//   warps 2-9 epilogue: tcgen05.ld the 128x128 fp32 accumulator tile from TMEM (double buffered,
+//                      256 columns); two warps per TMEM lane quarter, each thread owns one query row
+//                      and 64 of the 128 columns: 1 FFMA + 1 min per element, one branch per 32
 // Accumulators never leave the SM; HBM sees each list tile once per 128-query tile.
 #include "scan_tc.h"
 
@@ -37,11 +38,12 @@
 
 namespace vidx {
 
-constexpr int kTcThreads = 192;
+constexpr int kTcThreads = 320;       // warp 0 producer, warp 1 MMA, warps 2-9 epilogue
+constexpr int kTcEpiWarps = 8;
 constexpr int kTcM = 128;            // queries per tile (UMMA M)
 constexpr int kTcTileGroups = 4;     // 4 groups = 128 vectors per stage
 constexpr int kTcMaxChunkTiles = 64; // tiles per work item: chosen on the device, 4..64 (512..8192 vectors)
-constexpr int kTcStageCap = 512;     // survivors staged in shared memory per epilogue warp before a flush
+constexpr int kTcStageCap = 256;     // survivors staged in shared memory per epilogue warp before a flush
 constexpr int kTcTmemCols = 256;     // 2 accumulator stages x 128 columns
 constexpr int kTcStages = 8;         // shared-memory ring: stages of 128 vectors x 32 dims (16 KB)
 constexpr int kTcStageChunks = 8;    // 16-byte chunks (4 floats) of every vector per stage
@@ -123,6 +125,30 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
     for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
+}
+// Two 32-column loads in flight, one wait.
+__device__ __forceinline__ void tc_ld32x2(uint32_t taddr0, uint32_t taddr1, float (&v)[64]) {
+    uint32_t r[64];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%64];\n\t"
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
+        "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%65];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]), "=r"(r[32]),
+          "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]), "=r"(r[40]),
+          "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]), "=r"(r[48]),
+          "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]), "=r"(r[56]),
+          "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
+        : "r"(taddr0), "r"(taddr1)
+        : "memory");
+#pragma unroll
+    for (int i = 0; i < 64; i++) v[i] = __uint_as_float(r[i]);
 }
 // Shared-memory matrix descriptor, no swizzle, K-major: 8-row x 16-byte core matrices;
 // LBO = byte distance between the two 16-byte K chunks of one instruction, SBO = byte distance
@@ -247,8 +273,8 @@ __host__ __device__ inline TcSmemLayout tc_smem_layout(int Dq, int k) {
     L.a_bytes = (uint32_t)Dq * kTcM * 16;                  // query tile, [chunk][128 rows][16 B]
     L.off_b = L.a_bytes;                                   // ring of kTcStages list-tile K-slices
     L.off_vn = L.off_b + kTcStages * kTcStageBytes;        // scaled norms of the tile, per accumulator stage
-    L.off_stage = L.off_vn + 2 * 128 * 4;                  // survivor staging: [4 warps][cap] row ids + lanes
-    L.off_q = L.off_stage + 4u * kTcStageCap * 8;
+    L.off_stage = L.off_vn + 2 * 128 * 4;                  // survivor staging: [8 warps][cap] row ids + lanes
+    L.off_q = L.off_stage + (uint32_t)kTcEpiWarps * kTcStageCap * 8;
     L.off_bar = L.off_q + 128 * 8;
     L.off_misc = L.off_bar + (2 * kTcStages + 4) * 8;
     L.total = L.off_misc + 64;
@@ -262,8 +288,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(const __grid_con
     unsigned char* sA = smem;
     unsigned char* sB = smem + L.off_b;
     float* s_vn = reinterpret_cast<float*>(smem + L.off_vn);
-    uint32_t* s_crow = reinterpret_cast<uint32_t*>(smem + L.off_stage);         // [4][cap] survivor row ids
-    uint32_t* s_clane = s_crow + 4 * kTcStageCap;                               // [4][cap] owning lane (query row)
+    uint32_t* s_crow = reinterpret_cast<uint32_t*>(smem + L.off_stage);         // [8][cap] survivor row ids
+    uint32_t* s_clane = s_crow + kTcEpiWarps * kTcStageCap;                     // [8][cap] owning lane (query row)
     uint2* s_q = reinterpret_cast<uint2*>(smem + L.off_q);
     uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + L.off_bar);  // [kTcStages] K-slice landed
     uint64_t* bar_empty = bar_full + kTcStages;                          // [kTcStages] K-slice consumed by the MMAs
@@ -281,7 +307,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(const __grid_con
         }
         for (int i = 0; i < 2; i++) {
             mbar_init(&bar_tfull[i], 1);
-            mbar_init(&bar_tempty[i], 4);
+            mbar_init(&bar_tempty[i], kTcEpiWarps);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -344,7 +370,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(const __grid_con
                 if (idx < Dq * kTcM) reinterpret_cast<float4*>(sA)[idx] = v[u];
             }
         }
-        if (warp >= 2 && lane == 0) s_misc[4 + (warp & 3)] = 0;  // survivor staging counters
+        if (warp >= 2 && lane == 0) s_misc[4 + (warp - 2)] = 0;  // survivor staging counters
         fence_proxy_async();
         __syncthreads();
 
@@ -403,15 +429,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(const __grid_con
             it = __shfl_sync(kFull, it, 0);
             ks_it = __shfl_sync(kFull, ks_it, 0);
         } else {
-            // ===== epilogue: one thread per query row =====
-            const int quarter = warp & 3;
+            // ===== epilogue: one thread per (query row, column half) =====
+            const int quarter = warp & 3;        // TMEM lanes this warp may read: 32*quarter .. +31
+            const int half = (warp - 2) >> 2;    // column blocks 2*half, 2*half+1 of every tile
+            const int ew = warp - 2;
             const int row = quarter * 32 + lane;
             const uint2 qi = s_q[row];
             const bool valid = qi.x != kNoRow;
             const uint32_t q = qi.x;
-            uint32_t* s_cnt = &s_misc[4 + quarter];
-            uint32_t* crow = s_crow + quarter * kTcStageCap;
-            uint32_t* clane = s_clane + quarter * kTcStageCap;
+            uint32_t* s_cnt = &s_misc[4 + ew];
+            uint32_t* crow = s_crow + ew * kTcStageCap;
+            uint32_t* clane = s_clane + ew * kTcStageCap;
             float base_t = 0.0f, delta = 0.0f, tau_g = __int_as_float(0x7f800000);
             if (valid) {
                 float qn = p.qnorm[q];
@@ -453,52 +481,60 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(const __grid_con
                 const bool active = valid && !(skip_seeded && t < p.seed_tiles);
                 // bounds other CTAs published for this query meanwhile (latency hidden behind the tile)
                 uint32_t g_bits = valid ? __ldcg(&p.gthr_bits[q]) : 0x7f800000u;
-                for (uint32_t cb = 0; cb < ng; cb++) {
-                    float acc[32];
-                    tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + s * 128 + cb * 32, acc);
-                    if (active) {
+                float acc[64];
+                const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + s * 128 + half * 64;
+                tc_ld32x2(tbase, tbase + 32, acc);
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const uint32_t cb = 2 * half + h;
+                    if (active && cb < ng) {
                         const float4* vn4 = reinterpret_cast<const float4*>(s_vn + s * 128 + cb * 32);
+                        float tv[32];
 #pragma unroll
                         for (int j4 = 0; j4 < 8; j4++) {
                             float4 n4 = vn4[j4];
-                            float tv[4];
-                            tv[0] = __fmaf_rn(acc[4 * j4 + 0], -2.0f, n4.x);
-                            tv[1] = __fmaf_rn(acc[4 * j4 + 1], -2.0f, n4.y);
-                            tv[2] = __fmaf_rn(acc[4 * j4 + 2], -2.0f, n4.z);
-                            tv[3] = __fmaf_rn(acc[4 * j4 + 3], -2.0f, n4.w);
-                            // (NaN norms of padding rows fail every comparison)
-                            if (fminf(fminf(tv[0], tv[1]), fminf(tv[2], tv[3])) <= P) {
+                            tv[4 * j4 + 0] = __fmaf_rn(acc[32 * h + 4 * j4 + 0], -2.0f, n4.x);
+                            tv[4 * j4 + 1] = __fmaf_rn(acc[32 * h + 4 * j4 + 1], -2.0f, n4.y);
+                            tv[4 * j4 + 2] = __fmaf_rn(acc[32 * h + 4 * j4 + 2], -2.0f, n4.z);
+                            tv[4 * j4 + 3] = __fmaf_rn(acc[32 * h + 4 * j4 + 3], -2.0f, n4.w);
+                        }
+                        // one test per 32 columns (NaN norms of padding rows drop out of fminf)
+                        float m8[8];
 #pragma unroll
-                                for (int u = 0; u < 4; u++) {
-                                    if (tv[u] <= P) {
-                                        const uint32_t rowid = row0 + cb * 32 + 4 * j4 + u;
-                                        uint32_t idx = atomicAdd(s_cnt, 1u);
-                                        if (idx < (uint32_t)kTcStageCap) {
-                                            crow[idx] = rowid;
-                                            clane[idx] = (uint32_t)lane;
-                                        } else {  // staging full (pathological tie storms): append directly
-                                            uint32_t gi = atomicAdd(&p.cand_cnt[q], 1u);
-                                            if (gi < p.capq) p.cand[(size_t)q * p.capq + gi] = ((unsigned long long)qi.y << 32) | rowid;
-                                            else p.overflow[q] = 1u;
-                                        }
-                                        if (tv[u] < r[0]) {
-                                            r[0] = tv[u];
+                        for (int j4 = 0; j4 < 8; j4++)
+                            m8[j4] = fminf(fminf(tv[4 * j4], tv[4 * j4 + 1]), fminf(tv[4 * j4 + 2], tv[4 * j4 + 3]));
+                        float mall = fminf(fminf(fminf(m8[0], m8[1]), fminf(m8[2], m8[3])), fminf(fminf(m8[4], m8[5]), fminf(m8[6], m8[7])));
+                        if (mall <= P) {
 #pragma unroll
-                                            for (int i = 0; i + 1 < KR; i++) {
-                                                float hi = fmaxf(r[i], r[i + 1]), lo = fminf(r[i], r[i + 1]);
-                                                r[i] = hi;
-                                                r[i + 1] = lo;
-                                            }
-                                            P = fminf(tau_g, r[0] + delta);
+                            for (int j = 0; j < 32; j++) {
+                                if (tv[j] <= P) {
+                                    const uint32_t rowid = row0 + cb * 32 + j;
+                                    uint32_t idx = atomicAdd(s_cnt, 1u);
+                                    if (idx < (uint32_t)kTcStageCap) {
+                                        crow[idx] = rowid;
+                                        clane[idx] = (uint32_t)lane;
+                                    } else {  // staging full (pathological tie storms): append directly
+                                        uint32_t gi = atomicAdd(&p.cand_cnt[q], 1u);
+                                        if (gi < p.capq) p.cand[(size_t)q * p.capq + gi] = ((unsigned long long)qi.y << 32) | rowid;
+                                        else p.overflow[q] = 1u;
+                                    }
+                                    if (tv[j] < r[0]) {
+                                        r[0] = tv[j];
+#pragma unroll
+                                        for (int i = 0; i + 1 < KR; i++) {
+                                            float hi = fmaxf(r[i], r[i + 1]), lo = fminf(r[i], r[i + 1]);
+                                            r[i] = hi;
+                                            r[i + 1] = lo;
                                         }
+                                        P = fminf(tau_g, r[0] + delta);
                                     }
                                 }
                             }
                         }
                     }
-                    __syncwarp();
-                    if (*s_cnt >= (uint32_t)(kTcStageCap / 2)) flush();
                 }
+                __syncwarp();
+                if (*s_cnt >= (uint32_t)(kTcStageCap / 2)) flush();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bar_tempty[s]);
