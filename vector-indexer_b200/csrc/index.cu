@@ -282,7 +282,7 @@ struct Index::Workspace {
     DevBuf xq_pad, dist, probes, pair_ns, slot_off, seg_cnt, seg_qoff, seg_cur, seg_qlist, slot_seg, dense, sparse, counters,
         scan_tmp, cand_d, cand_r, alld, row_off, row_len, sel_pos, sel_val, rows, stats, slot_rank, list_cnt, list_cur, list_qoff,
         list_qlist, items_per_list, item_off, qnorm, gthr, cand_cnt, overflow, cand, list_cnt0, list_cur0, list_qoff0, list_qlist0,
-        items_per_list0, item_off0;
+        items_per_list0, item_off0, gtop, glock;
 };
 void Index::delete_workspace() {
     delete ws;
@@ -422,8 +422,10 @@ void Index::search_device(const float* d_xq, uint64_t nq, uint64_t k_req, uint64
             w.list_qlist.reserve(std::max<size_t>(npairs, 1) * 8);
             w.items_per_list.reserve(((size_t)nlist + 1) * 4);
             w.item_off.reserve(((size_t)nlist + 1) * 4);
-            launch_query_norms(xq4, Dq, nqb, w.qnorm.as<float>(), w.gthr.as<uint32_t>(), w.cand_cnt.as<uint32_t>(),
-                               w.overflow.as<uint32_t>(), st);
+            w.gtop.reserve((size_t)nqb * k * 4);
+            w.glock.reserve((size_t)nqb * 4);
+            launch_query_norms(xq4, Dq, nqb, (uint32_t)k, w.qnorm.as<float>(), w.gthr.as<uint32_t>(), w.cand_cnt.as<uint32_t>(),
+                               w.overflow.as<uint32_t>(), w.gtop.as<float>(), w.glock.as<uint32_t>(), st);
             VIDX_CUDA(cudaMemsetAsync(w.list_cur.p, 0, ((size_t)nlist + 1) * 4, st));
             exclusive_scan_u32(w.list_cnt.as<uint32_t>(), w.list_qoff.as<uint32_t>(), nlist, w.scan_tmp.as<uint32_t>(), st);
             launch_tc_fill(w.probes.as<uint32_t>(), npairs, np, false, d_list_seg.as<uint2>(), w.list_qoff.as<uint32_t>(),
@@ -460,6 +462,8 @@ void Index::search_device(const float* d_xq, uint64_t nq, uint64_t k_req, uint64
             tp.list_ngroups = d_list_ng.as<uint32_t>();
             tp.nlist = (uint32_t)nlist;
             tp.gthr_bits = w.gthr.as<uint32_t>();
+            tp.gtop = w.gtop.as<float>();
+            tp.glock = w.glock.as<uint32_t>();
             tp.cand = w.cand.as<unsigned long long>();
             tp.cand_cnt = w.cand_cnt.as<uint32_t>();
             tp.overflow = w.overflow.as<uint32_t>();

@@ -185,8 +185,9 @@ __global__ void row_norm_kernel(const float4* __restrict__ vecs, int Dq, const u
     vn_true[row] = s;
     vn_scaled[row] = (1.0f - kTcEps) * s;
 }
-__global__ void query_norm_kernel(const float4* __restrict__ xq4, int Dq, uint32_t nq, float* __restrict__ qn,
-                                  uint32_t* __restrict__ gthr_bits, uint32_t* __restrict__ cand_cnt, uint32_t* __restrict__ overflow) {
+__global__ void query_norm_kernel(const float4* __restrict__ xq4, int Dq, uint32_t nq, uint32_t k, float* __restrict__ qn,
+                                  uint32_t* __restrict__ gthr_bits, uint32_t* __restrict__ cand_cnt, uint32_t* __restrict__ overflow,
+                                  float* __restrict__ gtop, uint32_t* __restrict__ glock) {
     uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= nq) return;
     float s = 0.0f;
@@ -198,6 +199,8 @@ __global__ void query_norm_kernel(const float4* __restrict__ xq4, int Dq, uint32
     gthr_bits[q] = 0x7f800000u;  // +inf
     cand_cnt[q] = 0;
     overflow[q] = 0;
+    glock[q] = 0;
+    for (uint32_t i = 0; i < k; i++) gtop[(size_t)q * k + i] = __int_as_float(0x7f800000);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -448,15 +451,47 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(const __grid_con
                 float g = __uint_as_float(p.gthr_bits[q]);
                 tau_g = (g - base_t) + 1e-5f * (g + base_t);
             }
-            // the k smallest filter values seen so far in this item, DESCENDING: r[0] is the k-th smallest
-            // (+inf until k values were seen); slots >= k are pinned at -inf and never take part
+            // r[]: the k smallest filter values known for this query, DESCENDING (r[0] = k-th smallest, +inf until
+            // k values exist); slots >= k are pinned at -inf and never take part.  It starts from the set all
+            // CTAs share in global memory (gtop) and is merged back at the end of the item, so every item starts
+            // warm and the bound converges to the k-th best over EVERYTHING scanned so far for the query.
+            const float kInf = __int_as_float(0x7f800000);
             float r[KR];
 #pragma unroll
-            for (int i = 0; i < KR; i++) r[i] = i < (int)p.k ? __int_as_float(0x7f800000) : -__int_as_float(0x7f800000);
-            float P = tau_g;
+            for (int i = 0; i < KR; i++) r[i] = i < (int)p.k ? kInf : -kInf;
+            // Critical sections run INSIDE the retry loop: a lane that holds a lock always finishes and
+            // releases it before it waits for the other lanes of its warp (the paired epilogue warp
+            // contends for the same locks lane by lane).
+            // insert v into the descending array g (drops the current largest)
+            auto insert_desc = [&](float (&g)[KR], float v) {
+                g[0] = v;
+#pragma unroll
+                for (int i = 0; i + 1 < KR; i++) {
+                    float hi = fmaxf(g[i], g[i + 1]), lo = fminf(g[i], g[i + 1]);
+                    g[i] = hi;
+                    g[i + 1] = lo;
+                }
+            };
+            if (valid) {
+                bool done = false;
+                while (!done) {
+                    if (atomicCAS(&p.glock[q], 0u, 1u) == 0u) {
+                        __threadfence();
+#pragma unroll
+                        for (int i = 0; i < KR; i++)
+                            if (i < (int)p.k) r[i] = __ldcg(&p.gtop[(size_t)q * p.k + i]);
+                        __threadfence();
+                        atomicExch(&p.glock[q], 0u);
+                        done = true;
+                    } else {
+                        __nanosleep(64);
+                    }
+                }
+            }
+            float P = fminf(tau_g, r[0] + delta);
             // rows whose nearest list this is already scanned its first seed_tiles tiles in the seeding pass
             const bool skip_seeded = p.mode == 0 && qi.y == 0;
-            float published = __int_as_float(0x7f800000);
+            float published = r[0];
             // survivors are staged in shared memory per warp and flushed cooperatively, so the hot loop
             // never waits on a global atomic
             auto flush = [&]() {
@@ -505,31 +540,41 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(const __grid_con
                             m8[j4] = fminf(fminf(tv[4 * j4], tv[4 * j4 + 1]), fminf(tv[4 * j4 + 2], tv[4 * j4 + 3]));
                         float mall = fminf(fminf(fminf(m8[0], m8[1]), fminf(m8[2], m8[3])), fminf(fminf(m8[4], m8[5]), fminf(m8[6], m8[7])));
                         if (mall <= P) {
+                            // rare path, kept compact: (1) survivors = columns passing the bound AS OF block entry
+                            uint32_t mask = 0;
 #pragma unroll
-                            for (int j = 0; j < 32; j++) {
-                                if (tv[j] <= P) {
-                                    const uint32_t rowid = row0 + cb * 32 + j;
-                                    uint32_t idx = atomicAdd(s_cnt, 1u);
-                                    if (idx < (uint32_t)kTcStageCap) {
-                                        crow[idx] = rowid;
-                                        clane[idx] = (uint32_t)lane;
-                                    } else {  // staging full (pathological tie storms): append directly
-                                        uint32_t gi = atomicAdd(&p.cand_cnt[q], 1u);
-                                        if (gi < p.capq) p.cand[(size_t)q * p.capq + gi] = ((unsigned long long)qi.y << 32) | rowid;
-                                        else p.overflow[q] = 1u;
-                                    }
-                                    if (tv[j] < r[0]) {
-                                        r[0] = tv[j];
-#pragma unroll
-                                        for (int i = 0; i + 1 < KR; i++) {
-                                            float hi = fmaxf(r[i], r[i + 1]), lo = fminf(r[i], r[i + 1]);
-                                            r[i] = hi;
-                                            r[i + 1] = lo;
-                                        }
-                                        P = fminf(tau_g, r[0] + delta);
-                                    }
+                            for (int j = 0; j < 32; j++) mask |= (tv[j] <= P) ? (1u << j) : 0u;
+                            while (mask) {
+                                const int j = __ffs(mask) - 1;
+                                mask &= mask - 1;
+                                const uint32_t rowid = row0 + cb * 32 + j;
+                                uint32_t idx = atomicAdd(s_cnt, 1u);
+                                if (idx < (uint32_t)kTcStageCap) {
+                                    crow[idx] = rowid;
+                                    clane[idx] = (uint32_t)lane;
+                                } else {  // staging full (pathological tie storms): append directly
+                                    uint32_t gi = atomicAdd(&p.cand_cnt[q], 1u);
+                                    if (gi < p.capq) p.cand[(size_t)q * p.capq + gi] = ((unsigned long long)qi.y << 32) | rowid;
+                                    else p.overflow[q] = 1u;
                                 }
                             }
+                            // (2) tighten: fold every value below the current k-th smallest into r[], smallest first
+                            for (;;) {
+#pragma unroll
+                                for (int j4 = 0; j4 < 8; j4++)
+                                    m8[j4] = fminf(fminf(tv[4 * j4], tv[4 * j4 + 1]), fminf(tv[4 * j4 + 2], tv[4 * j4 + 3]));
+                                mall = fminf(fminf(fminf(m8[0], m8[1]), fminf(m8[2], m8[3])), fminf(fminf(m8[4], m8[5]), fminf(m8[6], m8[7])));
+                                if (!(mall < r[0])) break;
+                                insert_desc(r, mall);
+                                bool taken = false;  // consume exactly one occurrence
+#pragma unroll
+                                for (int j = 0; j < 32; j++) {
+                                    bool hit = !taken && tv[j] == mall;
+                                    tv[j] = hit ? kInf : tv[j];
+                                    taken = taken || hit;
+                                }
+                            }
+                            P = fminf(tau_g, r[0] + delta);
                         }
                     }
                 }
@@ -552,6 +597,48 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(const __grid_con
                 }
             }
             flush();
+            // merge this item's k smallest into the shared set (distinct values only: a value both sides
+            // already hold must not be counted twice; dropping a legitimately equal value only loosens the bound)
+            if (valid) {
+              bool done = false;
+              while (!done) {
+                if (atomicCAS(&p.glock[q], 0u, 1u) != 0u) {
+                    __nanosleep(64);
+                    continue;
+                }
+                __threadfence();
+                float g[KR];
+#pragma unroll
+                for (int i = 0; i < KR; i++) g[i] = i < (int)p.k ? __ldcg(&p.gtop[(size_t)q * p.k + i]) : -kInf;
+                bool changed = false;
+#pragma unroll
+                for (int i = KR - 1; i >= 0; i--) {
+                    const float v = r[i];
+                    if (v > -kInf && v < g[0]) {
+                        bool dup = false;
+#pragma unroll
+                        for (int j = 0; j < KR; j++) dup = dup || (g[j] == v);
+                        if (!dup) {
+                            insert_desc(g, v);
+                            changed = true;
+                        }
+                    }
+                }
+                if (changed) {
+#pragma unroll
+                    for (int i = 0; i < KR; i++)
+                        if (i < (int)p.k) __stcg(&p.gtop[(size_t)q * p.k + i], g[i]);
+                    if (g[0] < kInf) {
+                        float U = fmaxf(g[0] + base_t + delta, 0.0f);
+                        U = U + 1e-5f * U;
+                        atomicMin(&p.gthr_bits[q], __float_as_uint(U));
+                    }
+                }
+                __threadfence();
+                atomicExch(&p.glock[q], 0u);
+                done = true;
+              }
+            }
         }
     }
     tc_fence_before();
@@ -674,10 +761,10 @@ void launch_row_norms(const float4* vecs, int Dq, const uint32_t* row_src, size_
     row_norm_kernel<<<(unsigned)ceil_div(nrows, 256), 256, 0, st>>>(vecs, Dq, row_src, nrows, vn_scaled, vn_true);
     VIDX_LAUNCHED();
 }
-void launch_query_norms(const float4* xq4, int Dq, uint32_t nq, float* qn, uint32_t* gthr_bits, uint32_t* cand_cnt,
-                        uint32_t* overflow, cudaStream_t st) {
+void launch_query_norms(const float4* xq4, int Dq, uint32_t nq, uint32_t k, float* qn, uint32_t* gthr_bits, uint32_t* cand_cnt,
+                        uint32_t* overflow, float* gtop, uint32_t* glock, cudaStream_t st) {
     if (!nq) return;
-    query_norm_kernel<<<(unsigned)ceil_div(nq, 128), 128, 0, st>>>(xq4, Dq, nq, qn, gthr_bits, cand_cnt, overflow);
+    query_norm_kernel<<<(unsigned)ceil_div(nq, 128), 128, 0, st>>>(xq4, Dq, nq, k, qn, gthr_bits, cand_cnt, overflow, gtop, glock);
     VIDX_LAUNCHED();
 }
 void launch_tc_count(const uint32_t* probes, size_t npairs, uint32_t nprobe, bool rank0_only, const uint2* list_seg,

@@ -20,6 +20,8 @@ struct TcParams {
     uint32_t* work_counter;
     const uint32_t* chunk_tiles;   // tiles per work item, chosen by tc_items_kernel
     uint32_t* gthr_bits;           // per query: upper bound of the exact k-th best distance (float bits)
+    float* gtop;                   // per query: the k smallest filter values found so far by any CTA, descending
+    uint32_t* glock;               // per query: spin lock guarding gtop
     unsigned long long* cand;      // per query capq survivors: (rank << 32 | row)
     uint32_t* cand_cnt;
     uint32_t* overflow;
@@ -60,8 +62,8 @@ void make_tc_tensor_map(TcTensorMap& out, const void* vecs, uint64_t ngroups, in
 bool tc_supported(int Dq, uint32_t k);
 void launch_row_norms(const float4* vecs, int Dq, const uint32_t* row_src, size_t nrows, float* vn_scaled, float* vn_true,
                       cudaStream_t st);
-void launch_query_norms(const float4* xq4, int Dq, uint32_t nq, float* qn, uint32_t* gthr_bits, uint32_t* cand_cnt,
-                        uint32_t* overflow, cudaStream_t st);
+void launch_query_norms(const float4* xq4, int Dq, uint32_t nq, uint32_t k, float* qn, uint32_t* gthr_bits, uint32_t* cand_cnt,
+                        uint32_t* overflow, float* gtop, uint32_t* glock, cudaStream_t st);
 void launch_tc_count(const uint32_t* probes, size_t npairs, uint32_t nprobe, bool rank0_only, const uint2* list_seg,
                      uint32_t* list_cnt, cudaStream_t st);
 void launch_tc_fill(const uint32_t* probes, size_t npairs, uint32_t nprobe, bool rank0_only, const uint2* list_seg,
