@@ -423,7 +423,7 @@ void Index::search_device(const float* d_xq, uint64_t nq, uint64_t k_req, uint64
             w.items_per_list.reserve(((size_t)nlist + 1) * 4);
             w.item_off.reserve(((size_t)nlist + 1) * 4);
             w.gtop.reserve((size_t)nqb * k * 4);
-            w.glock.reserve((size_t)nqb * 4);
+            w.glock.reserve((size_t)nqb * 8);  // locks, then seqlock versions
             launch_query_norms(xq4, Dq, nqb, (uint32_t)k, w.qnorm.as<float>(), w.gthr.as<uint32_t>(), w.cand_cnt.as<uint32_t>(),
                                w.overflow.as<uint32_t>(), w.gtop.as<float>(), w.glock.as<uint32_t>(), st);
             VIDX_CUDA(cudaMemsetAsync(w.list_cur.p, 0, ((size_t)nlist + 1) * 4, st));
@@ -464,6 +464,7 @@ void Index::search_device(const float* d_xq, uint64_t nq, uint64_t k_req, uint64
             tp.gthr_bits = w.gthr.as<uint32_t>();
             tp.gtop = w.gtop.as<float>();
             tp.glock = w.glock.as<uint32_t>();
+            tp.gver = w.glock.as<uint32_t>() + nqb;
             tp.cand = w.cand.as<unsigned long long>();
             tp.cand_cnt = w.cand_cnt.as<uint32_t>();
             tp.overflow = w.overflow.as<uint32_t>();

@@ -200,6 +200,7 @@ __global__ void query_norm_kernel(const float4* __restrict__ xq4, int Dq, uint32
     cand_cnt[q] = 0;
     overflow[q] = 0;
     glock[q] = 0;
+    glock[nq + q] = 0;  // seqlock version of gtop
     for (uint32_t i = 0; i < k; i++) gtop[(size_t)q * k + i] = __int_as_float(0x7f800000);
 }
 
@@ -473,21 +474,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(const __grid_con
                 }
             };
             if (valid) {
-                bool done = false;
-                while (!done) {
-                    if (atomicCAS(&p.glock[q], 0u, 1u) == 0u) {
-                        __threadfence();
+                // seqlock read: writers make the version odd while they update the set
+                const volatile uint32_t* ver = p.gver + q;
+                for (;;) {
+                    uint32_t v1 = *ver;
+                    if (v1 & 1u) { __nanosleep(32); continue; }
+                    __threadfence();
 #pragma unroll
-                        for (int i = 0; i < KR; i++)
-                            if (i < (int)p.k) r[i] = __ldcg(&p.gtop[(size_t)q * p.k + i]);
-                        __threadfence();
-                        atomicExch(&p.glock[q], 0u);
-                        done = true;
-                    } else {
-                        __nanosleep(64);
-                    }
+                    for (int i = 0; i < KR; i++)
+                        if (i < (int)p.k) r[i] = __ldcg(&p.gtop[(size_t)q * p.k + i]);
+                    __threadfence();
+                    if (*ver == v1) break;
                 }
             }
+            bool improved = false;
             float P = fminf(tau_g, r[0] + delta);
             // rows whose nearest list this is already scanned its first seed_tiles tiles in the seeding pass
             const bool skip_seeded = p.mode == 0 && qi.y == 0;
@@ -566,6 +566,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(const __grid_con
                                 mall = fminf(fminf(fminf(m8[0], m8[1]), fminf(m8[2], m8[3])), fminf(fminf(m8[4], m8[5]), fminf(m8[6], m8[7])));
                                 if (!(mall < r[0])) break;
                                 insert_desc(r, mall);
+                                improved = true;
                                 bool taken = false;  // consume exactly one occurrence
 #pragma unroll
                                 for (int j = 0; j < 32; j++) {
@@ -599,7 +600,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(const __grid_con
             flush();
             // merge this item's k smallest into the shared set (distinct values only: a value both sides
             // already hold must not be counted twice; dropping a legitimately equal value only loosens the bound)
-            if (valid) {
+            if (valid && improved) {
               bool done = false;
               while (!done) {
                 if (atomicCAS(&p.glock[q], 0u, 1u) != 0u) {
@@ -625,9 +626,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(const __grid_con
                     }
                 }
                 if (changed) {
+                    atomicAdd(p.gver + q, 1u);  // odd: update in progress
+                    __threadfence();
 #pragma unroll
                     for (int i = 0; i < KR; i++)
                         if (i < (int)p.k) __stcg(&p.gtop[(size_t)q * p.k + i], g[i]);
+                    __threadfence();
+                    atomicAdd(p.gver + q, 1u);  // even: consistent again
                     if (g[0] < kInf) {
                         float U = fmaxf(g[0] + base_t + delta, 0.0f);
                         U = U + 1e-5f * U;

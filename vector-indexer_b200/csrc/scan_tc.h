@@ -21,7 +21,8 @@ struct TcParams {
     const uint32_t* chunk_tiles;   // tiles per work item, chosen by tc_items_kernel
     uint32_t* gthr_bits;           // per query: upper bound of the exact k-th best distance (float bits)
     float* gtop;                   // per query: the k smallest filter values found so far by any CTA, descending
-    uint32_t* glock;               // per query: spin lock guarding gtop
+    uint32_t* glock;               // per query: spin lock serialising writers of gtop
+    uint32_t* gver;                // per query: seqlock version of gtop (odd while being written)
     unsigned long long* cand;      // per query capq survivors: (rank << 32 | row)
     uint32_t* cand_cnt;
     uint32_t* overflow;
