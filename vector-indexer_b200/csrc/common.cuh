@@ -10,7 +10,8 @@
 
 namespace vidx {
 
-constexpr int kGroup = 32;          // vectors per interleaved group (one per lane)
+constexpr int kGroup = 32;          // vectors per group (one per lane)
+constexpr int kSuper = 128;         // vectors per supergroup = 4 groups: the unit of the HBM layout and of a tensor-core tile
 constexpr int kSegGroups = 32;      // groups per segment (<= 1024 vectors): the scan work unit
 constexpr int kSegVecs = kGroup * kSegGroups;
 constexpr unsigned kFull = 0xffffffffu;
@@ -90,6 +91,21 @@ struct SegDesc {
     uint32_t nvalid;  // valid vectors in this segment (<= ng*32)
     uint32_t list;    // owning list
 };
+
+// ---- HBM layout of vectors ------------------------------------------------------------
+// A supergroup holds 128 consecutive vectors of one list as float4 [Dq][128]: the 16-byte
+// chunk c (dims 4c..4c+3) of all 128 vectors is one contiguous 2 KB block, and any run of
+// chunks of a supergroup is contiguous too.  That is at once
+//   * coalesced for a warp (lane <-> vector: 512 contiguous bytes per chunk per group), and
+//   * the tcgen05 no-swizzle K-major operand layout (8-row x 16-byte core matrices, SBO 128 B,
+//     LBO 2048 B), so a K-slice of a list tile is ONE contiguous bulk copy into shared memory.
+// Rows are numbered linearly (row = group*32 + lane); lists start on supergroup boundaries.
+__host__ __device__ inline size_t f4_index(size_t group, int Dq, int c, int lane) {
+    return ((group >> 2) * (size_t)Dq + c) * kSuper + (group & 3) * kGroup + lane;
+}
+__host__ __device__ inline size_t f4_row_base(size_t row, int Dq) {  // + c*kSuper per chunk
+    return (row >> 7) * (size_t)Dq * kSuper + (row & 127);
+}
 
 #ifdef __CUDACC__
 // ---- reference arithmetic ---------------------------------------------------------

@@ -138,7 +138,7 @@ void Index::build_lists(const float* d_data, uint64_t n, const uint32_t* labels,
     list_seg_off_all.assign(nlist + 1, 0);
     segs.clear();
     for (uint64_t l = 0; l < nlist; l++) {
-        uint32_t ng = (uint32_t)ceil_div(list_len[l], kGroup);
+        uint32_t ng = 4 * (uint32_t)ceil_div(list_len[l], kSuper);  // whole supergroups
         list_goff[l + 1] = list_goff[l] + ng;
         for (uint32_t g = 0; g < ng; g += kSegGroups) {
             SegDesc s;
@@ -174,7 +174,7 @@ void Index::build_lists(const float* d_data, uint64_t n, const uint32_t* labels,
     d_row_ext.reserve(std::max<uint64_t>(nrows, 1) * 8);
     h2d(d_row_ext.as<uint64_t>(), row_ext.data(), nrows, stream);
     // centroids in the same interleaved layout
-    ncgroups = (uint32_t)ceil_div(nlist, kGroup);
+    ncgroups = 4 * (uint32_t)ceil_div(nlist, kSuper);
     {
         DevBuf d_c, d_map;
         d_c.reserve(std::max<size_t>(centroids.size(), 1) * 4);
@@ -204,7 +204,6 @@ void Index::build_lists(const float* d_data, uint64_t n, const uint32_t* labels,
         h2d(d_list_len.as<uint32_t>(), list_len.data(), list_len.size(), stream);
         d_vnorm.reserve((std::max<uint64_t>(nrows, 1) + 256) * 4);  // + slack: the tile copy always reads 128 norms
         VIDX_CUDA(cudaMemsetAsync(d_vnorm.p, 0xff, (std::max<uint64_t>(nrows, 1) + 256) * 4, stream));
-        if (tc_supported(Dq, 1)) make_tc_tensor_map(tc_tmap, d_vecs.p, ngroups, Dq);
         DevBuf d_vntrue;
         d_vntrue.reserve(std::max<uint64_t>(nrows, 1) * 4);
         launch_row_norms(d_vecs.as<float4>(), Dq, d_row_src.as<uint32_t>(), nrows, d_vnorm.as<float>(), d_vntrue.as<float>(), stream);
@@ -480,7 +479,7 @@ void Index::search_device(const float* d_xq, uint64_t nq, uint64_t k_req, uint64
             tp.item_off = w.item_off0.as<uint32_t>();
             tp.work_counter = counters + 9;
             tp.chunk_tiles = counters + 11;
-            launch_scan_tc(tc_tmap, tp, st);
+            launch_scan_tc(tp, st);
             // pass 2: everything else, starting from warm bounds
             tp.mode = 0;
             tp.list_cnt = w.list_cnt.as<uint32_t>();
@@ -489,7 +488,7 @@ void Index::search_device(const float* d_xq, uint64_t nq, uint64_t k_req, uint64
             tp.item_off = w.item_off.as<uint32_t>();
             tp.work_counter = counters + 8;
             tp.chunk_tiles = counters + 10;
-            launch_scan_tc(tc_tmap, tp, st);
+            launch_scan_tc(tp, st);
         }
         if (profiling) VIDX_CUDA(cudaEventRecord(ev[8], st));
 

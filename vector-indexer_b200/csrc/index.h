@@ -50,7 +50,6 @@ struct Index {
     cudaEvent_t events[10] = {};
     uint32_t ncgroups = 0;
     DevBuf d_vecs, d_cents, d_row_ext, d_segs, d_list_seg, d_list_g0, d_list_ng, d_list_len, d_vnorm;
-    TcTensorMap tc_tmap{};  // TMA view of d_vecs for the tensor-core scan
     float vn_max = 0.0f;   // max |v|^2 over the stored rows (bound for the tensor-core filter)
     int scan_mode = 0;     // 0 = tensor-core pre-filter when the shape allows, 1 = exact kernels only
     DevBuf io_xq, io_D, io_I, io_rows, io_V;

@@ -18,11 +18,10 @@
 //   keys the exact scan kernels order by.  The final answer is bit-identical to the exact path.
 //
 // Kernel anatomy (one CTA per SM, persistent, 6 warps):
-//   warp 0  producer : ONE 3-D TMA tensor copy (cp.async.bulk.tensor) per stage brings 4 groups
-//                      (128 vectors, full D, 64 KB) and permutes them on the fly -- the tensor map
-//                      lists the dims as (16B x 32 lanes, group, chunk), so the box lands in shared
-//                      memory chunk-major: [Dq][128 vectors][16 B]; plus a 1-D bulk copy of the 128
-//                      scaled norms; completion on an mbarrier (complete_tx::bytes)
+//   warp 0  producer : one cp.async.bulk (1-D TMA, 16 KB) per K-slice of a 128-vector tile -- the
+//                      HBM layout keeps chunk c of a supergroup's 128 vectors contiguous, so a
+//                      slice is a single contiguous run -- into an 8-deep shared-memory ring, plus
+//                      the tile's 128 scaled norms; completion on mbarriers (complete_tx::bytes)
 //   warp 1  MMA      : one elected thread issues tcgen05.mma.cta_group::1.kind::tf32, M=128
 //                      queries x N=128 vectors x K=8 per instruction; operands are read from shared
 //                      memory through no-swizzle K-major descriptors: that chunk-major layout IS
@@ -33,8 +32,6 @@
 //                      and 64 of the 128 columns: 1 FFMA + 1 min per element, one branch per 32
 // Accumulators never leave the SM; HBM sees each list tile once per 128-query tile.
 #include "scan_tc.h"
-
-#include <cudaTypedefs.h>
 
 namespace vidx {
 
@@ -84,12 +81,6 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                      smem_u32(smem_dst)),
                  "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* tmap, int c0, int c1, int c2, uint64_t* bar) {
-    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
-                     smem_u32(smem_dst)),
-                 "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
                  : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -176,10 +167,10 @@ __global__ void row_norm_kernel(const float4* __restrict__ vecs, int Dq, const u
         vn_true[row] = 0.0f;
         return;
     }
-    const float4* p = vecs + (row >> 5) * (size_t)Dq * 32 + (row & 31);
+    const float4* p = vecs + f4_row_base(row, Dq);
     float s = 0.0f;
     for (int c = 0; c < Dq; c++) {
-        float4 v = p[(size_t)c * 32];
+        float4 v = p[(size_t)c * kSuper];
         s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
     }
     vn_true[row] = s;
@@ -286,7 +277,7 @@ __host__ __device__ inline TcSmemLayout tc_smem_layout(int Dq, int k) {
 }
 
 template <int KR>
-__global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcParams p) {
+__global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const TcSmemLayout L = tc_smem_layout(p.Dq, (int)p.k);
     unsigned char* sA = smem;
@@ -304,7 +295,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(const __grid_con
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int Dq = p.Dq;
     if (tid == 0) {
-        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap)) : "memory");
         for (int i = 0; i < kTcStages; i++) {
             mbar_init(&bar_full[i], 1);
             mbar_init(&bar_empty[i], 1);
@@ -387,12 +377,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(const __grid_con
                     for (int kc = 0; kc < nkc; kc++, ks_it++) {
                         const uint32_t s = ks_it % kTcStages, ph = (ks_it / kTcStages) & 1;
                         mbar_wait(&bar_empty[s], ph ^ 1);
-                        // The box always covers 4 groups x 8 chunks: groups past the end of this list belong to
-                        // the next list, chunks past Dq are zero-filled; neither is used.
+                        // K-slice = chunks [8kc, 8kc+8) of the tile's supergroup: one contiguous run of HBM
                         const bool last = kc == nkc - 1;
                         if (last) mbar_wait(&bar_tempty[a], aph ^ 1);  // norms slot of this accumulator stage is free
-                        mbar_expect_tx(&bar_full[s], kTcStageBytes + (last ? 512u : 0u));
-                        tma_load_3d(sB + s * kTcStageBytes, &tmap, 0, (int)g0, kc * kTcStageChunks, &bar_full[s]);
+                        const uint32_t nch = (uint32_t)min(kTcStageChunks, Dq - kc * kTcStageChunks);
+                        const uint32_t bytes = nch * kSuper * 16;
+                        mbar_expect_tx(&bar_full[s], bytes + (last ? 512u : 0u));
+                        bulk_g2s(sB + s * kTcStageBytes, p.vecs + f4_index(g0, Dq, kc * kTcStageChunks, 0), bytes, &bar_full[s]);
                         if (last) bulk_g2s(s_vn + a * 128, p.vnorm + g0 * 32, 512, &bar_full[s]);
                     }
                 }
@@ -670,11 +661,11 @@ __device__ __forceinline__ void warp_insert_lex64(float cd, unsigned long long c
 // The reference's exact distance of one stored row (utils.rs:28-30), from the interleaved store.
 __device__ __forceinline__ float exact_row_distance(const float4* __restrict__ vecs, int Dq, uint32_t row,
                                                     const float4* __restrict__ q4) {
-    const float4* pv = vecs + (size_t)(row >> 5) * Dq * 32 + (row & 31);
+    const float4* pv = vecs + f4_row_base(row, Dq);
     float a = 0.0f;
 #pragma unroll 4
     for (int c = 0; c < Dq; c++) {
-        float4 v = __ldg(pv + (size_t)c * 32);
+        float4 v = __ldg(pv + (size_t)c * kSuper);
         float4 q = __ldg(q4 + c);
         a = sqdiff_acc(a, q.x, v.x);
         a = sqdiff_acc(a, q.y, v.y);
@@ -806,44 +797,20 @@ void launch_tc_items(const uint32_t* list_cnt, const uint32_t* list_ngroups, uin
     VIDX_LAUNCHED();
 }
 template <int KR>
-static void launch_scan_tc_kr(const CUtensorMap& tmap, const TcParams& p, size_t smem, cudaStream_t st) {
+static void launch_scan_tc_kr(const TcParams& p, size_t smem, cudaStream_t st) {
     static size_t attr = 0;
     if (smem > attr) {
         VIDX_CUDA(cudaFuncSetAttribute(scan_tc_kernel<KR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = smem;
     }
-    scan_tc_kernel<KR><<<tc_num_sms(), kTcThreads, smem, st>>>(tmap, p);
+    scan_tc_kernel<KR><<<tc_num_sms(), kTcThreads, smem, st>>>(p);
     VIDX_LAUNCHED();
 }
-void launch_scan_tc(const TcTensorMap& tm, const TcParams& p, cudaStream_t st) {
-    const CUtensorMap& tmap = *reinterpret_cast<const CUtensorMap*>(tm.bytes);
+void launch_scan_tc(const TcParams& p, cudaStream_t st) {
     size_t smem = tc_smem_layout(p.Dq, (int)p.k).total;
-    if (p.k <= 8) launch_scan_tc_kr<8>(tmap, p, smem, st);
-    else if (p.k <= 16) launch_scan_tc_kr<16>(tmap, p, smem, st);
-    else launch_scan_tc_kr<32>(tmap, p, smem, st);
-}
-// 3-D view of the interleaved store for the list-tile copy: dim0 = the 128 floats (32 lanes x 16 B)
-// of one (group, chunk) row, dim1 = group (stride Dq*512 B), dim2 = chunk (stride 512 B).  A box of
-// (128, 4, 8) -- one K-slice of a list tile -- therefore arrives in shared memory as
-// [chunk][4 groups x 32 vectors][16 B].
-void make_tc_tensor_map(TcTensorMap& out, const void* vecs, uint64_t ngroups, int Dq) {
-    static_assert(sizeof(CUtensorMap) <= sizeof(out.bytes), "tensor map storage");
-    static PFN_cuTensorMapEncodeTiled encode = nullptr;
-    if (!encode) {
-        void* fn = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        VIDX_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
-        if (!fn || qres != cudaDriverEntryPointSuccess) throw CudaError("cuTensorMapEncodeTiled is not available in this driver");
-        encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(fn);
-    }
-    cuuint64_t dims[3] = {128, std::max<uint64_t>(ngroups, 1), (cuuint64_t)Dq};
-    cuuint64_t strides[2] = {(cuuint64_t)Dq * 512, 512};
-    cuuint32_t box[3] = {128, (cuuint32_t)kTcTileGroups, (cuuint32_t)kTcStageChunks};
-    cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = encode(reinterpret_cast<CUtensorMap*>(out.bytes), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(vecs), dims,
-                        strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) throw CudaError("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+    if (p.k <= 8) launch_scan_tc_kr<8>(p, smem, st);
+    else if (p.k <= 16) launch_scan_tc_kr<16>(p, smem, st);
+    else launch_scan_tc_kr<32>(p, smem, st);
 }
 void launch_finalize(const FinalizeParams& p, cudaStream_t st) {
     if (!p.nq) return;

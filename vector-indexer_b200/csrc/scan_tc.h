@@ -54,12 +54,6 @@ struct FinalizeParams {
     uint32_t* out_rows;
 };
 
-// Opaque storage for the CUtensorMap of the list store (kept out of this header's dependencies).
-struct alignas(64) TcTensorMap {
-    unsigned char bytes[128];
-};
-void make_tc_tensor_map(TcTensorMap& out, const void* vecs, uint64_t ngroups, int Dq);
-
 bool tc_supported(int Dq, uint32_t k);
 void launch_row_norms(const float4* vecs, int Dq, const uint32_t* row_src, size_t nrows, float* vn_scaled, float* vn_true,
                       cudaStream_t st);
@@ -71,7 +65,7 @@ void launch_tc_fill(const uint32_t* probes, size_t npairs, uint32_t nprobe, bool
                     const uint32_t* list_qoff, uint32_t* list_cur, uint2* list_qlist, cudaStream_t st);
 void launch_tc_items(const uint32_t* list_cnt, const uint32_t* list_ngroups, uint32_t nlist, unsigned long long* total,
                      uint32_t seed_tiles, uint32_t* chunk_out, uint32_t* items_per_list, cudaStream_t st);
-void launch_scan_tc(const TcTensorMap& tm, const TcParams& p, cudaStream_t st);
+void launch_scan_tc(const TcParams& p, cudaStream_t st);
 void launch_finalize(const FinalizeParams& p, cudaStream_t st);
 
 }  // namespace vidx

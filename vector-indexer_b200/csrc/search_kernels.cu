@@ -8,13 +8,12 @@
 // in dimension order, so distances are bit-identical to the reference and every
 // ordering decision (probe order, top-k order) is made on identical keys.
 //
-// Data layout (HBM): vectors of one list are stored in consecutive "groups" of 32
-// vectors; group g holds float4 [Dq][32]: element (c, lane) = dims 4c..4c+3 of vector
-// `lane` of the group.  A warp's 16-byte loads for one c are one contiguous 512 B line
-// set, whether they come from HBM directly (sparse kernel) or from the shared-memory
-// stage (dense kernel).  Lists are padded to whole groups (zero rows, masked by
-// position); a "segment" is up to 32 groups (1024 vectors) of one list and is the unit
-// of work and of result slots.
+// Data layout (HBM): see f4_index() in common.cuh.  Vectors of one list are stored in
+// consecutive supergroups of 128 vectors, each float4 [Dq][128]; a "group" is 32 of those
+// vectors (one per lane), so a warp's 16-byte loads for one chunk are 512 contiguous bytes
+// whether they come from HBM directly (sparse kernel) or from the shared-memory stage (dense
+// kernel).  Lists are padded to whole supergroups (zero rows, masked by position); a "segment"
+// is up to 32 groups (1024 vectors) of one list and is the unit of work and of result slots.
 #include "search.h"
 
 namespace vidx {
@@ -162,7 +161,7 @@ __device__ __forceinline__ void stage_issue(float4* stage, const float4* __restr
         int i = idx >> 8;          // group within tile (256 float4 per group per stage)
         int c = (idx >> 5) & 7;    // float4 within chunk
         int l = idx & 31;
-        if (i < ng_tile && c0 + c < Dq) cp_async16(&sv[idx], &vecs[((gbase + i) * (size_t)Dq + c0 + c) * 32 + l]);
+        if (i < ng_tile && c0 + c < Dq) cp_async16(&sv[idx], &vecs[f4_index(gbase + i, Dq, c0 + c, l)]);
     }
 #pragma unroll
     for (int it = 0; it < kQStageF4 / kDenseThreads; it++) {
@@ -625,9 +624,9 @@ __device__ __forceinline__ void sparse_group_pair(const float4* __restrict__ v0,
     for (; c + 4 <= Dq; c += 4) {
         float4 x0[4], x1[4];
 #pragma unroll
-        for (int u = 0; u < 4; u++) x0[u] = ldg_f4(&v0[(size_t)(c + u) * 32 + lane]);
+        for (int u = 0; u < 4; u++) x0[u] = ldg_f4(&v0[(size_t)(c + u) * kSuper + lane]);
 #pragma unroll
-        for (int u = 0; u < 4; u++) x1[u] = has1 ? ldg_f4(&v1[(size_t)(c + u) * 32 + lane]) : make_float4(0, 0, 0, 0);
+        for (int u = 0; u < 4; u++) x1[u] = has1 ? ldg_f4(&v1[(size_t)(c + u) * kSuper + lane]) : make_float4(0, 0, 0, 0);
 #pragma unroll
         for (int u = 0; u < 4; u++) {
 #pragma unroll
@@ -649,8 +648,8 @@ __device__ __forceinline__ void sparse_group_pair(const float4* __restrict__ v0,
         }
     }
     for (; c < Dq; c++) {
-        float4 x0 = ldg_f4(&v0[(size_t)c * 32 + lane]);
-        float4 x1 = has1 ? ldg_f4(&v1[(size_t)c * 32 + lane]) : make_float4(0, 0, 0, 0);
+        float4 x0 = ldg_f4(&v0[(size_t)c * kSuper + lane]);
+        float4 x1 = has1 ? ldg_f4(&v1[(size_t)c * kSuper + lane]) : make_float4(0, 0, 0, 0);
 #pragma unroll
         for (int j = 0; j < QT; j++) {
             float4 q = sq[(size_t)j * Dq + c];
@@ -749,8 +748,8 @@ scan_sparse_kernel(const float4* __restrict__ vecs, int Dq, const float4* __rest
         for (int g = warp; g < (int)sg.ng; g += 16) {
             int g2 = g + 8;
             bool has1 = g2 < (int)sg.ng;
-            const float4* v0 = vecs + (size_t)(sg.g0 + g) * Dq * 32;
-            const float4* v1 = vecs + (size_t)(sg.g0 + (has1 ? g2 : g)) * Dq * 32;
+            const float4* v0 = vecs + f4_index(sg.g0 + g, Dq, 0, 0);  // + c*kSuper + lane
+            const float4* v1 = vecs + f4_index(sg.g0 + (has1 ? g2 : g), Dq, 0, 0);
             float a0[8], a1[8];
             switch (nq) {
                 case 8: sparse_group_pair<8>(v0, v1, has1, Dq, sq, lane, a0, a1); break;
@@ -913,9 +912,7 @@ __global__ void gather_vectors_kernel(const float* __restrict__ vecs, int Dq, in
     uint32_t row = rows[res];
     float v = 0.0f;
     if (row != kNoRow) {
-        size_t g = row >> 5;
-        int l = row & 31;
-        v = vecs[((g * Dq + (d >> 2)) * 32 + l) * 4 + (d & 3)];
+        v = vecs[(f4_row_base(row, Dq) + (size_t)(d >> 2) * kSuper) * 4 + (d & 3)];
     }
     out[i] = v;
 }
@@ -926,10 +923,11 @@ __global__ void interleave_kernel(const float* __restrict__ src, int D, int Dq, 
                                   size_t nrows, float4* __restrict__ dst) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // one float4 of dst
     if (i >= nrows * (size_t)Dq) return;
-    size_t g = i / ((size_t)Dq * 32);
-    size_t rem = i - g * (size_t)Dq * 32;
-    int c = (int)(rem >> 5), l = (int)(rem & 31);
-    uint32_t s = row_src[g * 32 + l];
+    // dst index i = (supergroup * Dq + c) * 128 + r
+    size_t sg = i / ((size_t)Dq * kSuper);
+    size_t rem = i - sg * (size_t)Dq * kSuper;
+    int c = (int)(rem >> 7), r = (int)(rem & 127);
+    uint32_t s = row_src[sg * kSuper + r];
     float4 v = make_float4(0, 0, 0, 0);
     if (s != kNoRow) {
         const float* p = src + (size_t)s * D + 4 * c;
