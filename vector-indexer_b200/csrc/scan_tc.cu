@@ -35,7 +35,7 @@
 
 namespace vidx {
 
-constexpr int kTcThreads = 320;       // warp 0 producer, warp 1 MMA, warps 2-9 epilogue
+constexpr int kTcThreads = 352;       // warp 0 producer, warp 1 MMA (even tiles), warps 2-9 epilogue, warp 10 MMA (odd tiles)
 constexpr int kTcEpiWarps = 8;
 constexpr int kTcM = 128;            // queries per tile (UMMA M)
 constexpr int kTcTileGroups = 4;     // 4 groups = 128 vectors per stage
@@ -98,6 +98,22 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t desc_a, ui
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
         "}" ::"r"(tmem_d),
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// Same, with the two descriptors given as 32-bit halves: only the 14-bit start-address field of the
+// low word differs between the MMAs of a tile, so the issuing thread does one IADD per descriptor.
+template <bool ACC>
+__device__ __forceinline__ void tc_mma_tf32_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "n"(ACC ? 1 : 0)
         : "memory");
 }
 // 32 lanes x 32 columns of fp32: thread t of the warp gets lane (quarter*32 + t), 32 consecutive columns.
@@ -364,7 +380,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
                 if (idx < Dq * kTcM) reinterpret_cast<float4*>(sA)[idx] = v[u];
             }
         }
-        if (warp >= 2 && lane == 0) s_misc[4 + (warp - 2)] = 0;  // survivor staging counters
+        if (warp >= 2 && warp < 10 && lane == 0) s_misc[4 + (warp - 2)] = 0;  // survivor staging counters
         fence_proxy_async();
         __syncthreads();
 
@@ -393,26 +409,36 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
             }
             it = __shfl_sync(kFull, it, 0);
             ks_it = __shfl_sync(kFull, ks_it, 0);
-        } else if (warp == 1) {
-            // ===== MMA issuer =====
+        } else if (warp == 1 || warp == 10) {
+            // ===== MMA issuers: warp 1 takes the even tiles of this CTA's tile sequence, warp 10 the odd ones
+            // (one thread each; the loop is kept to a few dozen instructions per K-slice because a single
+            // thread's issue latency, not the tensor pipe, would otherwise bound the kernel) =====
+            const uint32_t my_par = warp == 1 ? 0u : 1u;
             if (lane == 0) {
-                const uint32_t a_addr = smem_u32(sA);
-                for (uint32_t t = t0; t < t1; t++, it++) {
+                // descriptor = lo | hi << 32; lo = start address >> 4 (14 bits) | LBO >> 4 << 16, hi = SBO >> 4 | version 1 << 14
+                const uint32_t desc_hi = (128u >> 4) | (1u << 14);
+                const uint32_t lbo_bits = (2048u >> 4) << 16;
+                const uint32_t a_lo0 = ((smem_u32(sA) >> 4) & 0x3fffu) | lbo_bits;
+                const uint32_t b_lo0 = ((smem_u32(sB) >> 4) & 0x3fffu) | lbo_bits;
+                for (uint32_t t = t0; t < t1; t++, it++, ks_it += nkc) {
+                    if ((it & 1u) != my_par) continue;
                     const uint32_t a = it & 1, aph = (it >> 1) & 1;
                     mbar_wait(&bar_tempty[a], aph ^ 1);
                     const uint32_t d_tmem = tmem_base + a * 128;
-                    for (int kc = 0; kc < nkc; kc++, ks_it++) {
-                        const uint32_t s = ks_it % kTcStages, ph = (ks_it / kTcStages) & 1;
+                    uint32_t kq = ks_it;
+                    for (int kc = 0; kc < nkc; kc++, kq++) {
+                        const uint32_t s = kq % kTcStages, ph = (kq / kTcStages) & 1;
                         mbar_wait(&bar_full[s], ph);
                         tc_fence_after();
-                        const uint32_t b_addr = smem_u32(sB + s * kTcStageBytes);
+                        // chunk c of all 128 rows is one 2 KB block (128 x 16 B) in both tiles: +128 per chunk in >>4 units
+                        const uint32_t al = a_lo0 + (uint32_t)kc * (kTcStageChunks * 128);
+                        const uint32_t bl = b_lo0 + s * (kTcStageBytes >> 4);
                         const int nks = min(kTcStageChunks / 2, (Dq >> 1) - kc * (kTcStageChunks / 2));
-                        for (int ks = 0; ks < nks; ks++) {
-                            // 16-byte chunk c of all 128 rows is one 2 KB block in both tiles
-                            uint64_t da = make_smem_desc(a_addr + (kc * kTcStageChunks + 2 * ks) * 2048, 2048, 128);
-                            uint64_t db = make_smem_desc(b_addr + 2 * ks * 2048, 2048, 128);
-                            tc_mma_tf32(d_tmem, da, db, idesc, (kc | ks) ? 1u : 0u);
-                        }
+                        if (kc == 0) tc_mma_tf32_lo<false>(d_tmem, al, bl, desc_hi, idesc);
+                        else tc_mma_tf32_lo<true>(d_tmem, al, bl, desc_hi, idesc);
+                        if (nks > 1) tc_mma_tf32_lo<true>(d_tmem, al + 256, bl + 256, desc_hi, idesc);
+                        if (nks > 2) tc_mma_tf32_lo<true>(d_tmem, al + 512, bl + 512, desc_hi, idesc);
+                        if (nks > 3) tc_mma_tf32_lo<true>(d_tmem, al + 768, bl + 768, desc_hi, idesc);
                         tc_commit(&bar_empty[s]);  // K-slice free once these MMAs have read it
                     }
                     tc_commit(&bar_tfull[a]);      // accumulator tile ready for the epilogue
