@@ -293,6 +293,15 @@ def run_ours(args):
             ms = float(t.item())
         return ms, launches
 
+    if args.profile_window:
+        # ncu --profile-from-start off: exactly one warmed-up step between cudaProfilerStart/Stop
+        for _ in range(args.warmup):
+            step_device()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        step_device()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
     sampler = ClockSampler(local)
     sampler.start()
     ms_dev, launches = timed(step_device, args.steps, args.warmup)
@@ -412,6 +421,8 @@ def main():
     ap.add_argument("--nprobe", type=int, default=0, help="0 = smallest power of two with recall@10 >= 0.9")
     ap.add_argument("--full-curve", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-window", action="store_true",
+                    help="bracket one warmed-up step with cudaProfilerStart/Stop (for ncu --profile-from-start off)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
