@@ -202,11 +202,11 @@ void Index::build_lists(const float* d_data, uint64_t n, const uint32_t* labels,
         h2d(d_list_g0.as<uint32_t>(), g0.data(), g0.size(), stream);
         h2d(d_list_ng.as<uint32_t>(), ng.data(), ng.size(), stream);
         h2d(d_list_len.as<uint32_t>(), list_len.data(), list_len.size(), stream);
-        d_vnorm.reserve((std::max<uint64_t>(nrows, 1) + 256) * 4);  // + slack: the tile copy always reads 128 norms
-        VIDX_CUDA(cudaMemsetAsync(d_vnorm.p, 0xff, (std::max<uint64_t>(nrows, 1) + 256) * 4, stream));
+        d_vnorm.reserve((std::max<uint64_t>(nrows, 1) + 128) * 16);  // rows are whole supergroups: a tile copy reads 128 entries
+        VIDX_CUDA(cudaMemsetAsync(d_vnorm.p, 0xff, (std::max<uint64_t>(nrows, 1) + 128) * 16, stream));
         DevBuf d_vntrue;
         d_vntrue.reserve(std::max<uint64_t>(nrows, 1) * 4);
-        launch_row_norms(d_vecs.as<float4>(), Dq, d_row_src.as<uint32_t>(), nrows, d_vnorm.as<float>(), d_vntrue.as<float>(), stream);
+        launch_row_norms(d_vecs.as<float4>(), Dq, d_row_src.as<uint32_t>(), nrows, d_vnorm.as<float4>(), d_vntrue.as<float>(), stream);
         std::vector<float> vt(nrows);
         d2h_sync(vt.data(), d_vntrue.as<float>(), nrows, stream);
         vn_max = 0.0f;
@@ -453,7 +453,7 @@ void Index::search_device(const float* d_xq, uint64_t nq, uint64_t k_req, uint64
         if (tc) {
             TcParams tp{};
             tp.vecs = d_vecs.as<float4>();
-            tp.vnorm = d_vnorm.as<float>();
+            tp.vnorm = d_vnorm.as<float4>();
             tp.Dq = Dq;
             tp.xq4 = xq4;
             tp.qnorm = w.qnorm.as<float>();

@@ -35,13 +35,15 @@
 
 namespace vidx {
 
-constexpr int kTcThreads = 352;       // warp 0 producer, warp 1 MMA (even tiles), warps 2-9 epilogue, warp 10 MMA (odd tiles)
+constexpr int kTcThreads = 384;       // warp 0 producer, warp 1 MMA (even tiles), warps 2-9 epilogue, warp 10 MMA (odd tiles), warp 11 selector
 constexpr int kTcEpiWarps = 8;
 constexpr int kTcM = 128;            // queries per tile (UMMA M)
 constexpr int kTcTileGroups = 4;     // 4 groups = 128 vectors per stage
 constexpr int kTcMaxChunkTiles = 64; // tiles per work item: chosen on the device, 4..64 (512..8192 vectors)
-constexpr int kTcStageCap = 256;     // survivors staged in shared memory per epilogue warp before a flush
-constexpr int kTcTmemCols = 256;     // 2 accumulator stages x 128 columns
+constexpr int kTcQueueCap = 512;     // hit queue entries (power of two)
+constexpr int kTcStageCap = 256;     // survivors staged by the selector before a bulk append
+constexpr int kTcAccStages = 4;      // accumulator tiles in TMEM
+constexpr int kTcTmemCols = 512;     // 4 accumulator stages x 128 columns
 constexpr int kTcStages = 8;         // shared-memory ring: stages of 128 vectors x 32 dims (16 KB)
 constexpr int kTcStageChunks = 8;    // 16-byte chunks (4 floats) of every vector per stage
 constexpr uint32_t kTcStageBytes = kTcStageChunks * kTcTileGroups * 512;
@@ -173,13 +175,15 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
 // ------------------------------------------------------------------------------------------
 // norms
 // ------------------------------------------------------------------------------------------
-// Per stored row: (1-eps)*|v|^2, NaN for padding rows (NaN never passes a '<=' test).
+// Per stored row: n = (1-eps)*|v|^2 split into three TF32-exact terms (n_hi + n_mid + n_lo == n exactly), the
+// B operand of the norm step of the tensor-core scan; NaN for padding rows (NaN never passes a '<=' test).
+__device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 __global__ void row_norm_kernel(const float4* __restrict__ vecs, int Dq, const uint32_t* __restrict__ row_src, size_t nrows,
-                                float* __restrict__ vn_scaled, float* __restrict__ vn_true) {
+                                float4* __restrict__ vn3, float* __restrict__ vn_true) {
     size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= nrows) return;
     if (row_src[row] == kNoRow) {
-        vn_scaled[row] = __int_as_float(0x7fc00000);
+        vn3[row] = make_float4(__int_as_float(0x7fc00000), 0.0f, 0.0f, 0.0f);
         vn_true[row] = 0.0f;
         return;
     }
@@ -190,7 +194,11 @@ __global__ void row_norm_kernel(const float4* __restrict__ vecs, int Dq, const u
         s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
     }
     vn_true[row] = s;
-    vn_scaled[row] = (1.0f - kTcEps) * s;
+    const float n = (1.0f - kTcEps) * s;
+    const float hi = tf32_trunc(n);
+    const float r1 = n - hi;          // exact
+    const float mid = tf32_trunc(r1);
+    vn3[row] = make_float4(hi, mid, r1 - mid, 0.0f);
 }
 __global__ void query_norm_kernel(const float4* __restrict__ xq4, int Dq, uint32_t nq, uint32_t k, float* __restrict__ qn,
                                   uint32_t* __restrict__ gthr_bits, uint32_t* __restrict__ cand_cnt, uint32_t* __restrict__ overflow,
@@ -276,51 +284,103 @@ __global__ void tc_items_kernel(const uint32_t* __restrict__ list_cnt, const uin
 // the tensor-core scan
 // ------------------------------------------------------------------------------------------
 struct TcSmemLayout {
-    uint32_t a_bytes, off_b, off_vn, off_stage, off_q, off_bar, off_misc, total;
+    uint32_t a_bytes, off_b, off_norm, off_ones, off_zero, off_r, off_queue, off_stage, off_q, off_row, off_bar, off_misc, total;
+    uint32_t stages;
 };
-__host__ __device__ inline TcSmemLayout tc_smem_layout(int Dq, int k) {
-    (void)k;
+__host__ __device__ inline TcSmemLayout tc_smem_layout(int Dq, int kr) {
     TcSmemLayout L;
-    L.a_bytes = (uint32_t)Dq * kTcM * 16;                  // query tile, [chunk][128 rows][16 B]
-    L.off_b = L.a_bytes;                                   // ring of kTcStages list-tile K-slices
-    L.off_vn = L.off_b + kTcStages * kTcStageBytes;        // scaled norms of the tile, per accumulator stage
-    L.off_stage = L.off_vn + 2 * 128 * 4;                  // survivor staging: [8 warps][cap] row ids + lanes
-    L.off_q = L.off_stage + (uint32_t)kTcEpiWarps * kTcStageCap * 8;
-    L.off_bar = L.off_q + 128 * 8;
-    L.off_misc = L.off_bar + (2 * kTcStages + 4) * 8;
+    L.stages = kr > 16 ? kTcStages - 1 : kTcStages;         // the 32-entry top-k sets need the room of one ring stage
+    L.a_bytes = (uint32_t)Dq * kTcM * 16;                   // query tile, [chunk][128 rows][16 B]
+    L.off_b = L.a_bytes;                                    // ring of list-tile K-slices
+    L.off_norm = L.off_b + L.stages * kTcStageBytes;        // per accumulator stage: norm chunk [128 rows][16 B]
+    L.off_ones = L.off_norm + kTcAccStages * 2048;          // A-side partner of the norm chunk: (1,1,1,0) per row
+    L.off_zero = L.off_ones + 2048;                         // second K chunk of the norm step, both operands: zeros
+    L.off_r = L.off_zero + 2048;                            // per query row: its k smallest filter values, descending
+    L.off_queue = L.off_r + (uint32_t)kTcM * (kr + 1) * 4;  // (row stride kr+1: lanes on different rows hit different banks)
+    L.off_stage = L.off_queue + kTcQueueCap * 8;            // hit queue: epilogue threads -> selector warp; then survivor staging
+    L.off_q = L.off_stage + kTcStageCap * 12;               // (query, probe rank) of the tile's rows
+    L.off_row = L.off_q + kTcM * 8;                         // per row: bound P, delta, base, improved flag
+    L.off_bar = L.off_row + 4 * kTcM * 4;
+    L.off_misc = L.off_bar + (2 * kTcStages + 2 * kTcAccStages) * 8;
     L.total = L.off_misc + 64;
     return L;
 }
 
+__device__ __forceinline__ uint32_t lds_volatile(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ float lds_volatile_f(const float* p) { return __uint_as_float(lds_volatile(reinterpret_cast<const uint32_t*>(p))); }
+__device__ __forceinline__ void sts_volatile(uint32_t* p, uint32_t v) {
+    asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint2 lds_volatile_v2(const uint2* p) {
+    uint2 v;
+    asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_volatile_v2(uint2* p, uint2 v) {
+    asm volatile("st.volatile.shared.v2.u32 [%0], {%1, %2};" ::"r"(smem_u32(p)), "r"(v.x), "r"(v.y) : "memory");
+}
+// min of 32 registers as a tree of 3-input minima (FMNMX3); NaNs (padding rows) drop out
+__device__ __forceinline__ float min3(float a, float b, float c) { return fminf(fminf(a, b), c); }
+__device__ __forceinline__ float min32(const float* v) {
+    float a0 = min3(v[0], v[1], v[2]), a1 = min3(v[3], v[4], v[5]), a2 = min3(v[6], v[7], v[8]), a3 = min3(v[9], v[10], v[11]);
+    float a4 = min3(v[12], v[13], v[14]), a5 = min3(v[15], v[16], v[17]), a6 = min3(v[18], v[19], v[20]);
+    float a7 = min3(v[21], v[22], v[23]), a8 = min3(v[24], v[25], v[26]), a9 = min3(v[27], v[28], v[29]);
+    float b0 = min3(a0, a1, a2), b1 = min3(a3, a4, a5), b2 = min3(a6, a7, a8), b3 = min3(a9, v[30], v[31]);
+    return fminf(fminf(b0, b1), fminf(b2, b3));
+}
+
+// Queue entry (8 bytes, written with one 64-bit store): x = 0x40000000 | kind << 31 | tile << 14 | column << 7 | row
+// (never zero; zero marks an empty slot), y = float bits of the value.  kind 0 = a filter value that passed
+// the row's bound (a survivor candidate), kind 1 = a tighter bound for the row.
+constexpr uint32_t kEntValid = 0x40000000u;
+
 template <int KR>
 __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    const TcSmemLayout L = tc_smem_layout(p.Dq, (int)p.k);
+    const TcSmemLayout L = tc_smem_layout(p.Dq, KR);
     unsigned char* sA = smem;
     unsigned char* sB = smem + L.off_b;
-    float* s_vn = reinterpret_cast<float*>(smem + L.off_vn);
-    uint32_t* s_crow = reinterpret_cast<uint32_t*>(smem + L.off_stage);         // [8][cap] survivor row ids
-    uint32_t* s_clane = s_crow + kTcEpiWarps * kTcStageCap;                     // [8][cap] owning lane (query row)
+    unsigned char* sNorm = smem + L.off_norm;
+    constexpr int kRS = KR + 1;                                     // row stride of s_r
+    float* s_r = reinterpret_cast<float*>(smem + L.off_r);          // [128][KR+1]
+    uint2* s_stage = reinterpret_cast<uint2*>(smem + L.off_stage);  // [kTcStageCap] (row id, query row)
+    float* s_stage_v = reinterpret_cast<float*>(smem + L.off_stage + kTcStageCap * 8);  // [kTcStageCap] filter value
+    uint2* s_queue = reinterpret_cast<uint2*>(smem + L.off_queue);  // [kTcQueueCap]
     uint2* s_q = reinterpret_cast<uint2*>(smem + L.off_q);
-    uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + L.off_bar);  // [kTcStages] K-slice landed
-    uint64_t* bar_empty = bar_full + kTcStages;                          // [kTcStages] K-slice consumed by the MMAs
-    uint64_t* bar_tfull = bar_empty + kTcStages;                         // [2] accumulator tile complete
-    uint64_t* bar_tempty = bar_tfull + 2;                                // [2] accumulator tile (and its norms) drained
-    uint32_t* s_misc = reinterpret_cast<uint32_t*>(smem + L.off_misc);
+    float* s_P = reinterpret_cast<float*>(smem + L.off_row);        // [128] bound in filter space (written by the selector only)
+    float* s_delta = s_P + kTcM;                                    // [128]
+    float* s_base = s_delta + kTcM;                                 // [128]
+    uint32_t* s_impr = reinterpret_cast<uint32_t*>(s_base + kTcM);  // [128] the row's set changed during this item
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + L.off_bar);  // [stages] K-slice landed
+    uint64_t* bar_empty = bar_full + kTcStages;                          // [stages] K-slice consumed by the MMAs
+    uint64_t* bar_tfull = bar_empty + kTcStages;                         // [4] accumulator tile complete
+    uint64_t* bar_tempty = bar_tfull + kTcAccStages;                     // [4] accumulator tile drained
+    uint32_t* s_misc = reinterpret_cast<uint32_t*>(smem + L.off_misc);   // [0] tmem base [1] item [2] queue tail [3] queue head [4] done
+    const uint32_t nstages = L.stages;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int Dq = p.Dq;
     if (tid == 0) {
-        for (int i = 0; i < kTcStages; i++) {
+        for (uint32_t i = 0; i < nstages; i++) {
             mbar_init(&bar_full[i], 1);
             mbar_init(&bar_empty[i], 1);
         }
-        for (int i = 0; i < 2; i++) {
+        for (int i = 0; i < kTcAccStages; i++) {
             mbar_init(&bar_tfull[i], 1);
             mbar_init(&bar_tempty[i], kTcEpiWarps);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    // constant operands of the norm step and an empty queue
+    for (int i = tid; i < 128; i += kTcThreads) {
+        reinterpret_cast<float4*>(smem + L.off_ones)[i] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+        reinterpret_cast<float4*>(smem + L.off_zero)[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    }
+    for (int i = tid; i < kTcQueueCap; i += kTcThreads) s_queue[i] = make_uint2(0u, 0u);
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_misc[0])), "r"(kTcTmemCols)
                      : "memory");
@@ -334,14 +394,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
     const uint32_t idesc = make_idesc_tf32(kTcM, kTcTileGroups * 32);
     const uint32_t chunk_tiles = *p.chunk_tiles;
     const int nkc = (Dq + kTcStageChunks - 1) / kTcStageChunks;  // K-slices per tile
-    uint32_t it = 0;  // tiles processed so far by this CTA (accumulator stage = it & 1, phase = (it >> 1) & 1)
-    uint32_t ks_it = 0;  // K-slices processed so far (ring stage = ks_it % kTcStages, phase = (ks_it / kTcStages) & 1)
+    const float kInf = __int_as_float(0x7f800000);
+    uint32_t it = 0;     // tiles processed so far by this CTA (accumulator stage = it & 3, phase = (it >> 2) & 1)
+    uint32_t ks_it = 0;  // K-slices processed so far (ring stage = ks_it % nstages, phase = (ks_it / nstages) & 1)
 
     for (;;) {
         if (tid == 0) s_misc[1] = atomicAdd(p.work_counter, 1u);
-        __syncthreads();
+        __syncthreads();  // also: every warp is done with the previous item's queue
         const uint32_t item = s_misc[1];
         if (item >= total_items) break;
+        if (tid == kTcThreads - 1) {  // empty queue for this item (published by the barriers below)
+            s_misc[2] = 0;
+            s_misc[3] = 0;
+            s_misc[4] = 0;
+        }
         // decode item -> (list, chunk, query tile)
         uint32_t lo = 0, hi = p.nlist;
         while (hi - lo > 1) {
@@ -360,9 +426,43 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
         const uint32_t t0 = chunk * chunk_tiles, t1 = min(ntiles, t0 + chunk_tiles);
         const uint32_t nq_tile = min((uint32_t)kTcM, cnt - qt * kTcM);
 
-        if (tid < kTcM) s_q[tid] = tid < (int)nq_tile ? p.list_qlist[p.list_qoff[l] + qt * kTcM + tid] : make_uint2(kNoRow, 0);
+        if (tid < kTcM) {
+            // per-row state of this item: the (query, rank) of the row, its top-k set as known to all CTAs, its bound
+            const uint2 qi = tid < (int)nq_tile ? p.list_qlist[p.list_qoff[l] + qt * kTcM + tid] : make_uint2(kNoRow, 0);
+            s_q[tid] = qi;
+            float P = -kInf, delta = 0.0f, base_t = 0.0f;
+            float* rr = s_r + tid * kRS;
+            if (qi.x != kNoRow) {
+                const uint32_t q = qi.x;
+                const float qn = p.qnorm[q];
+                base_t = (1.0f - kTcEps) * qn;
+                delta = 2.0f * kTcEps * (qn + p.vn_max);
+                const float g = __uint_as_float(__ldcg(&p.gthr_bits[q]));
+                const float tau_g = (g - base_t) + 1e-5f * (g + base_t);
+                // seqlock read: writers make the version odd while they update the set
+                const volatile uint32_t* ver = p.gver + q;
+                float r0 = kInf;
+                for (;;) {
+                    uint32_t v1 = *ver;
+                    if (v1 & 1u) { __nanosleep(32); continue; }
+                    __threadfence();
+                    for (int i = 0; i < KR; i++) {
+                        float v = i < (int)p.k ? __ldcg(&p.gtop[(size_t)q * p.k + i]) : -kInf;
+                        rr[i] = v;
+                        if (i == 0) r0 = v;
+                    }
+                    __threadfence();
+                    if (*ver == v1) break;
+                }
+                P = fminf(tau_g, r0 + delta);
+            }
+            s_P[tid] = P;
+            s_delta[tid] = delta;
+            s_base[tid] = base_t;
+            s_impr[tid] = 0;
+        }
         __syncthreads();
-        // A tile: [c][128 rows][16 B] (core matrices of 8 rows x 16 B, SBO 128 B, LBO 2048 B)
+        // A tile = -2 * queries: [c][128 rows][16 B] (core matrices of 8 rows x 16 B, SBO 128 B, LBO 2048 B)
         for (int base = 0; base < Dq * kTcM; base += kTcThreads * 8) {
             float4 v[8];
 #pragma unroll
@@ -377,10 +477,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
 #pragma unroll
             for (int u = 0; u < 8; u++) {
                 int idx = base + u * kTcThreads + tid;
-                if (idx < Dq * kTcM) reinterpret_cast<float4*>(sA)[idx] = v[u];
+                if (idx < Dq * kTcM)
+                    reinterpret_cast<float4*>(sA)[idx] = make_float4(-2.0f * v[u].x, -2.0f * v[u].y, -2.0f * v[u].z, -2.0f * v[u].w);
             }
         }
-        if (warp >= 2 && warp < 10 && lane == 0) s_misc[4 + (warp - 2)] = 0;  // survivor staging counters
         fence_proxy_async();
         __syncthreads();
 
@@ -388,19 +488,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
             // ===== producer =====
             if (lane == 0) {
                 for (uint32_t t = t0; t < t1; t++, it++) {
-                    const uint32_t a = it & 1, aph = (it >> 1) & 1;
+                    const uint32_t a = it & (kTcAccStages - 1), aph = (it / kTcAccStages) & 1;
                     const size_t g0 = (size_t)g_list + (size_t)t * kTcTileGroups;
                     for (int kc = 0; kc < nkc; kc++, ks_it++) {
-                        const uint32_t s = ks_it % kTcStages, ph = (ks_it / kTcStages) & 1;
+                        const uint32_t s = ks_it % nstages, ph = (ks_it / nstages) & 1;
                         mbar_wait(&bar_empty[s], ph ^ 1);
                         // K-slice = chunks [8kc, 8kc+8) of the tile's supergroup: one contiguous run of HBM
                         const bool last = kc == nkc - 1;
-                        if (last) mbar_wait(&bar_tempty[a], aph ^ 1);  // norms slot of this accumulator stage is free
+                        if (last) mbar_wait(&bar_tempty[a], aph ^ 1);  // norm chunk of this accumulator stage is free
                         const uint32_t nch = (uint32_t)min(kTcStageChunks, Dq - kc * kTcStageChunks);
                         const uint32_t bytes = nch * kSuper * 16;
-                        mbar_expect_tx(&bar_full[s], bytes + (last ? 512u : 0u));
+                        mbar_expect_tx(&bar_full[s], bytes + (last ? 2048u : 0u));
                         bulk_g2s(sB + s * kTcStageBytes, p.vecs + f4_index(g0, Dq, kc * kTcStageChunks, 0), bytes, &bar_full[s]);
-                        if (last) bulk_g2s(s_vn + a * 128, p.vnorm + g0 * 32, 512, &bar_full[s]);
+                        if (last) bulk_g2s(sNorm + a * 2048, p.vnorm + g0 * 32, 2048, &bar_full[s]);
                     }
                 }
             } else {
@@ -420,14 +520,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
                 const uint32_t lbo_bits = (2048u >> 4) << 16;
                 const uint32_t a_lo0 = ((smem_u32(sA) >> 4) & 0x3fffu) | lbo_bits;
                 const uint32_t b_lo0 = ((smem_u32(sB) >> 4) & 0x3fffu) | lbo_bits;
+                // norm step: K chunk 0 = (1,1,1,0) x (n_hi, n_mid, n_lo, 0), K chunk 1 = the shared zero block
+                const uint32_t ones_lo = ((smem_u32(smem + L.off_ones) >> 4) & 0x3fffu) | (((L.off_zero - L.off_ones) >> 4) << 16);
                 for (uint32_t t = t0; t < t1; t++, it++, ks_it += nkc) {
                     if ((it & 1u) != my_par) continue;
-                    const uint32_t a = it & 1, aph = (it >> 1) & 1;
+                    const uint32_t a = it & (kTcAccStages - 1), aph = (it / kTcAccStages) & 1;
                     mbar_wait(&bar_tempty[a], aph ^ 1);
                     const uint32_t d_tmem = tmem_base + a * 128;
                     uint32_t kq = ks_it;
                     for (int kc = 0; kc < nkc; kc++, kq++) {
-                        const uint32_t s = kq % kTcStages, ph = (kq / kTcStages) & 1;
+                        const uint32_t s = kq % nstages, ph = (kq / nstages) & 1;
                         mbar_wait(&bar_full[s], ph);
                         tc_fence_after();
                         // chunk c of all 128 rows is one 2 KB block (128 x 16 B) in both tiles: +128 per chunk in >>4 units
@@ -439,6 +541,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
                         if (nks > 1) tc_mma_tf32_lo<true>(d_tmem, al + 256, bl + 256, desc_hi, idesc);
                         if (nks > 2) tc_mma_tf32_lo<true>(d_tmem, al + 512, bl + 512, desc_hi, idesc);
                         if (nks > 3) tc_mma_tf32_lo<true>(d_tmem, al + 768, bl + 768, desc_hi, idesc);
+                        if (kc == nkc - 1) {
+                            const uint32_t noff = L.off_norm + a * 2048;
+                            const uint32_t norm_lo = ((smem_u32(smem + noff) >> 4) & 0x3fffu) | (((L.off_zero - noff) >> 4) << 16);
+                            tc_mma_tf32_lo<true>(d_tmem, ones_lo, norm_lo, desc_hi, idesc);
+                        }
                         tc_commit(&bar_empty[s]);  // K-slice free once these MMAs have read it
                     }
                     tc_commit(&bar_tfull[a]);      // accumulator tile ready for the epilogue
@@ -449,177 +556,234 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
             }
             it = __shfl_sync(kFull, it, 0);
             ks_it = __shfl_sync(kFull, ks_it, 0);
+        } else if (warp == 11) {
+            // ===== selector: the only writer of the rows' bounds and top-k sets =====
+            const uint32_t row0_item = (g_list + t0 * kTcTileGroups) * 32u;
+            volatile float* vP = s_P;
+            volatile float* vr = s_r;
+            uint32_t head = 0, refresh = 0, idle = 0, nstage = 0;
+            // survivors are staged in shared memory and appended to the per-query lists in bulk: four global
+            // atomics in flight per lane instead of one round trip per batch; entries that fell outside the
+            // row's bound meanwhile are dropped
+            auto flush = [&]() {
+                for (uint32_t base = 0; base < nstage; base += 128) {
+                    uint32_t gi[4], rid[4];
+                    uint2 qq[4];
+                    bool ok[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const uint32_t i = base + u * 32 + lane;
+                        ok[u] = false;
+                        if (i < nstage) {
+                            const uint2 se = s_stage[i];
+                            const uint32_t srow = se.y & 127u;
+                            qq[u] = s_q[srow];
+                            rid[u] = se.x;
+                            ok[u] = s_stage_v[i] <= vP[srow];
+                            if (ok[u]) gi[u] = atomicAdd(&p.cand_cnt[qq[u].x], 1u);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        if (ok[u]) {
+                            if (gi[u] < p.capq) p.cand[(size_t)qq[u].x * p.capq + gi[u]] = ((unsigned long long)qq[u].y << 32) | rid[u];
+                            else p.overflow[qq[u].x] = 1u;
+                        }
+                    }
+                }
+                nstage = 0;
+                __syncwarp();
+            };
+            auto adopt = [&](int rr) {  // bounds other CTAs published for this row's query
+                const uint32_t q = s_q[rr].x;
+                if (q != kNoRow) {
+                    const float g = __uint_as_float(__ldcg(&p.gthr_bits[q]));
+                    const float b = s_base[rr];
+                    const float tau = (g - b) + 1e-5f * (g + b);
+                    if (tau < vP[rr]) vP[rr] = tau;
+                }
+            };
+            for (;;) {
+                const uint2 e = lds_volatile_v2(&s_queue[(head + lane) & (kTcQueueCap - 1)]);
+                const unsigned have = __ballot_sync(kFull, e.x != 0u);
+                const int n = have == kFull ? 32 : __ffs(~have) - 1;  // longest prefix of written slots
+                if (n == 0) {
+                    if (lds_volatile(&s_misc[4]) == (uint32_t)kTcEpiWarps && lds_volatile(&s_misc[2]) == head) break;
+                    if (++idle > (1u << 21)) __trap();  // an item never takes this long
+                    adopt(lane + 32 * (int)(refresh++ & 3u));
+                    continue;
+                }
+                idle = 0;
+                const bool mine = lane < n;
+                if (mine) sts_volatile_v2(&s_queue[(head + lane) & (kTcQueueCap - 1)], make_uint2(0u, 0u));
+                head += (uint32_t)n;
+                if (lane == 0) sts_volatile(&s_misc[3], head);
+                const uint32_t row = e.x & 127u, kind = e.x >> 31;
+                const float val = __uint_as_float(e.y);
+                // (1) survivors: everything still inside the row's bound goes to the exact re-check
+                const bool cand_ok = mine && kind == 0u && val <= vP[row];
+                const unsigned cm = __ballot_sync(kFull, cand_ok);
+                if (cand_ok) {
+                    const uint32_t pos = nstage + __popc(cm & ((1u << lane) - 1u));
+                    s_stage[pos] = make_uint2(row0_item + ((e.x >> 14) & 127u) * 128u + ((e.x >> 7) & 127u), row);
+                    s_stage_v[pos] = val;
+                }
+                nstage += __popc(cm);
+                __syncwarp();
+                if (nstage > (uint32_t)kTcStageCap - 32u) flush();
+                // (2) state changes: one lane per distinct row and round, each lane updating its row's set serially
+                bool todo = mine && (kind == 1u ? val < vP[row] : (cand_ok && val < vr[row * kRS]));
+                for (;;) {
+                    const unsigned tm = __ballot_sync(kFull, todo);
+                    if (!tm) break;
+                    if (todo) {
+                        const unsigned peers = __match_any_sync(tm, row);
+                        if (lane == __ffs(peers) - 1) {
+                            float newP = val;
+                            if (kind == 0u) {
+                                float g[KR];
+#pragma unroll
+                                for (int i = 0; i < KR; i++) g[i] = vr[row * kRS + i];
+                                if (val < g[0]) {
+                                    g[0] = val;  // drop the largest, bubble the new value into place (descending)
+#pragma unroll
+                                    for (int i = 0; i + 1 < KR; i++) {
+                                        const float hi_v = fmaxf(g[i], g[i + 1]), lo_v = fminf(g[i], g[i + 1]);
+                                        g[i] = hi_v;
+                                        g[i + 1] = lo_v;
+                                    }
+#pragma unroll
+                                    for (int i = 0; i < KR; i++) vr[row * kRS + i] = g[i];
+                                    s_impr[row] = 1u;
+                                }
+                                newP = g[0] + s_delta[row];
+                            }
+                            if (newP < vP[row]) {
+                                vP[row] = newP;
+                                s_impr[row] = 1u;
+                                float U = fmaxf(newP + s_base[row], 0.0f);
+                                U = U + 1e-5f * U;
+                                atomicMin(&p.gthr_bits[s_q[row].x], __float_as_uint(U));
+                            }
+                            todo = false;
+                        }
+                    }
+                    __syncwarp();
+                    todo = todo && (kind == 1u ? val < vP[row] : val < vr[row * kRS]);
+                }
+                if ((++refresh & 15u) == 0u) adopt(lane + 32 * (int)((refresh >> 4) & 3u));
+            }
+            flush();
+            it += t1 - t0;
+            ks_it += (t1 - t0) * nkc;
+            asm volatile("bar.sync 1, %0;" ::"n"((kTcEpiWarps + 1) * 32) : "memory");
         } else {
-            // ===== epilogue: one thread per (query row, column half) =====
+            // ===== epilogue: one thread per (query row, column half); the accumulators already hold
+            // (1-eps)|v|^2 - 2 q.v, so a tile costs one 3-input min per three columns and one branch per 32 =====
             const int quarter = warp & 3;        // TMEM lanes this warp may read: 32*quarter .. +31
             const int half = (warp - 2) >> 2;    // column blocks 2*half, 2*half+1 of every tile
-            const int ew = warp - 2;
             const int row = quarter * 32 + lane;
             const uint2 qi = s_q[row];
             const bool valid = qi.x != kNoRow;
-            const uint32_t q = qi.x;
-            uint32_t* s_cnt = &s_misc[4 + ew];
-            uint32_t* crow = s_crow + ew * kTcStageCap;
-            uint32_t* clane = s_clane + ew * kTcStageCap;
-            float base_t = 0.0f, delta = 0.0f, tau_g = __int_as_float(0x7f800000);
-            if (valid) {
-                float qn = p.qnorm[q];
-                base_t = (1.0f - kTcEps) * qn;
-                delta = 2.0f * kTcEps * (qn + p.vn_max);
-                float g = __uint_as_float(p.gthr_bits[q]);
-                tau_g = (g - base_t) + 1e-5f * (g + base_t);
-            }
-            // r[]: the k smallest filter values known for this query, DESCENDING (r[0] = k-th smallest, +inf until
-            // k values exist); slots >= k are pinned at -inf and never take part.  It starts from the set all
-            // CTAs share in global memory (gtop) and is merged back at the end of the item, so every item starts
-            // warm and the bound converges to the k-th best over EVERYTHING scanned so far for the query.
-            const float kInf = __int_as_float(0x7f800000);
-            float r[KR];
-#pragma unroll
-            for (int i = 0; i < KR; i++) r[i] = i < (int)p.k ? kInf : -kInf;
-            // Critical sections run INSIDE the retry loop: a lane that holds a lock always finishes and
-            // releases it before it waits for the other lanes of its warp (the paired epilogue warp
-            // contends for the same locks lane by lane).
-            // insert v into the descending array g (drops the current largest)
-            auto insert_desc = [&](float (&g)[KR], float v) {
-                g[0] = v;
-#pragma unroll
-                for (int i = 0; i + 1 < KR; i++) {
-                    float hi = fmaxf(g[i], g[i + 1]), lo = fminf(g[i], g[i + 1]);
-                    g[i] = hi;
-                    g[i + 1] = lo;
-                }
-            };
-            if (valid) {
-                // seqlock read: writers make the version odd while they update the set
-                const volatile uint32_t* ver = p.gver + q;
-                for (;;) {
-                    uint32_t v1 = *ver;
-                    if (v1 & 1u) { __nanosleep(32); continue; }
-                    __threadfence();
-#pragma unroll
-                    for (int i = 0; i < KR; i++)
-                        if (i < (int)p.k) r[i] = __ldcg(&p.gtop[(size_t)q * p.k + i]);
-                    __threadfence();
-                    if (*ver == v1) break;
-                }
-            }
-            bool improved = false;
-            float P = fminf(tau_g, r[0] + delta);
+            const float delta = s_delta[row];
+            float P = s_P[row];
             // rows whose nearest list this is already scanned its first seed_tiles tiles in the seeding pass
             const bool skip_seeded = p.mode == 0 && qi.y == 0;
-            float published = r[0];
-            // survivors are staged in shared memory per warp and flushed cooperatively, so the hot loop
-            // never waits on a global atomic
-            auto flush = [&]() {
-                __syncwarp();
-                uint32_t n = min(*s_cnt, (uint32_t)kTcStageCap);
-                for (uint32_t i = lane; i < n; i += 32) {
-                    uint2 e = s_q[quarter * 32 + clane[i]];
-                    uint32_t idx = atomicAdd(&p.cand_cnt[e.x], 1u);
-                    if (idx < p.capq) p.cand[(size_t)e.x * p.capq + idx] = ((unsigned long long)e.y << 32) | crow[i];
-                    else p.overflow[e.x] = 1u;
+            auto push = [&](uint32_t info, float v) {
+                const uint32_t idx = atomicAdd(&s_misc[2], 1u);
+                for (uint32_t spins = 0; idx - lds_volatile(&s_misc[3]) >= (uint32_t)kTcQueueCap; spins++) {
+                    __nanosleep(32);
+                    if (spins > (1u << 22)) __trap();  // the selector always drains: a protocol bug, do not hang the GPU
                 }
-                __syncwarp();
-                if (lane == 0) *s_cnt = 0;
-                __syncwarp();
+                sts_volatile_v2(&s_queue[idx & (kTcQueueCap - 1)], make_uint2(info, __float_as_uint(v)));
             };
             for (uint32_t t = t0; t < t1; t++, it++) {
-                const uint32_t s = it & 1, ph = (it >> 1) & 1;
+                const uint32_t s = it & (kTcAccStages - 1), ph = (it / kTcAccStages) & 1;
                 mbar_wait(&bar_tfull[s], ph);
                 tc_fence_after();
                 const uint32_t ng = min((uint32_t)kTcTileGroups, ngl - t * kTcTileGroups);
-                const uint32_t row0 = (g_list + t * kTcTileGroups) * 32u;
                 const bool active = valid && !(skip_seeded && t < p.seed_tiles);
-                // bounds other CTAs published for this query meanwhile (latency hidden behind the tile)
-                uint32_t g_bits = valid ? __ldcg(&p.gthr_bits[q]) : 0x7f800000u;
+                P = fminf(P, lds_volatile_f(&s_P[row]));
                 float acc[64];
                 const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + s * 128 + half * 64;
                 tc_ld32x2(tbase, tbase + 32, acc);
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
                     const uint32_t cb = 2 * half + h;
-                    if (active && cb < ng) {
-                        const float4* vn4 = reinterpret_cast<const float4*>(s_vn + s * 128 + cb * 32);
-                        float tv[32];
+                    const float* tv = acc + 32 * h;
+                    if (active && cb < ng && min32(tv) <= P) {
+                        // rare path: this row has columns inside its bound (as of the latest bound)
+                        P = fminf(P, lds_volatile_f(&s_P[row]));
+                        uint32_t mask = 0;
 #pragma unroll
-                        for (int j4 = 0; j4 < 8; j4++) {
-                            float4 n4 = vn4[j4];
-                            tv[4 * j4 + 0] = __fmaf_rn(acc[32 * h + 4 * j4 + 0], -2.0f, n4.x);
-                            tv[4 * j4 + 1] = __fmaf_rn(acc[32 * h + 4 * j4 + 1], -2.0f, n4.y);
-                            tv[4 * j4 + 2] = __fmaf_rn(acc[32 * h + 4 * j4 + 2], -2.0f, n4.z);
-                            tv[4 * j4 + 3] = __fmaf_rn(acc[32 * h + 4 * j4 + 3], -2.0f, n4.w);
+                        for (int j = 0; j < 32; j++) mask |= (tv[j] <= P) ? (1u << j) : 0u;
+                        if (__popc(mask) >= (int)p.k) {
+                            // flood control (cold or very loose bound): the k-th smallest of these 32 values bounds
+                            // the row's k-th best, so tighten locally before anything is queued
+                            float lo_v = -kInf, kth = kInf;
+                            for (uint32_t i = 0; i < p.k; i++) {
+                                float nxt = kInf;
+#pragma unroll
+                                for (int j = 0; j < 32; j++) nxt = (tv[j] > lo_v) ? fminf(nxt, tv[j]) : nxt;
+                                int c = 0;
+#pragma unroll
+                                for (int j = 0; j < 32; j++) c += (tv[j] <= nxt) ? 1 : 0;
+                                kth = nxt;
+                                if (c >= (int)p.k) break;
+                                lo_v = nxt;
+                            }
+                            const float nP = kth + delta;
+                            if (nP < P) {
+                                P = nP;
+                                push(kEntValid | (1u << 31) | (uint32_t)row, P);
+                                mask = 0;
+#pragma unroll
+                                for (int j = 0; j < 32; j++) mask |= (tv[j] <= P) ? (1u << j) : 0u;
+                            }
                         }
-                        // one test per 32 columns (NaN norms of padding rows drop out of fminf)
-                        float m8[8];
+                        const uint32_t tl = t - t0;
+                        while (mask) {
+                            const int j = __ffs(mask) - 1;
+                            mask &= mask - 1;
+                            float v = tv[0];
 #pragma unroll
-                        for (int j4 = 0; j4 < 8; j4++)
-                            m8[j4] = fminf(fminf(tv[4 * j4], tv[4 * j4 + 1]), fminf(tv[4 * j4 + 2], tv[4 * j4 + 3]));
-                        float mall = fminf(fminf(fminf(m8[0], m8[1]), fminf(m8[2], m8[3])), fminf(fminf(m8[4], m8[5]), fminf(m8[6], m8[7])));
-                        if (mall <= P) {
-                            // rare path, kept compact: (1) survivors = columns passing the bound AS OF block entry
-                            uint32_t mask = 0;
-#pragma unroll
-                            for (int j = 0; j < 32; j++) mask |= (tv[j] <= P) ? (1u << j) : 0u;
-                            while (mask) {
-                                const int j = __ffs(mask) - 1;
-                                mask &= mask - 1;
-                                const uint32_t rowid = row0 + cb * 32 + j;
-                                uint32_t idx = atomicAdd(s_cnt, 1u);
-                                if (idx < (uint32_t)kTcStageCap) {
-                                    crow[idx] = rowid;
-                                    clane[idx] = (uint32_t)lane;
-                                } else {  // staging full (pathological tie storms): append directly
-                                    uint32_t gi = atomicAdd(&p.cand_cnt[q], 1u);
-                                    if (gi < p.capq) p.cand[(size_t)q * p.capq + gi] = ((unsigned long long)qi.y << 32) | rowid;
-                                    else p.overflow[q] = 1u;
-                                }
-                            }
-                            // (2) tighten: fold every value below the current k-th smallest into r[], smallest first
-                            for (;;) {
-#pragma unroll
-                                for (int j4 = 0; j4 < 8; j4++)
-                                    m8[j4] = fminf(fminf(tv[4 * j4], tv[4 * j4 + 1]), fminf(tv[4 * j4 + 2], tv[4 * j4 + 3]));
-                                mall = fminf(fminf(fminf(m8[0], m8[1]), fminf(m8[2], m8[3])), fminf(fminf(m8[4], m8[5]), fminf(m8[6], m8[7])));
-                                if (!(mall < r[0])) break;
-                                insert_desc(r, mall);
-                                improved = true;
-                                bool taken = false;  // consume exactly one occurrence
-#pragma unroll
-                                for (int j = 0; j < 32; j++) {
-                                    bool hit = !taken && tv[j] == mall;
-                                    tv[j] = hit ? kInf : tv[j];
-                                    taken = taken || hit;
-                                }
-                            }
-                            P = fminf(tau_g, r[0] + delta);
+                            for (int jj = 1; jj < 32; jj++) v = (jj == j) ? tv[jj] : v;
+                            push(kEntValid | (tl << 14) | ((cb * 32u + (uint32_t)j) << 7) | (uint32_t)row, v);
                         }
                     }
                 }
-                __syncwarp();
-                if (*s_cnt >= (uint32_t)(kTcStageCap / 2)) flush();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bar_tempty[s]);
-                if (valid) {
-                    // publish / adopt upper bounds of this query's exact k-th best distance
-                    if (r[0] < published) {
-                        published = r[0];
-                        float U = fmaxf(r[0] + base_t + delta, 0.0f);
-                        U = U + 1e-5f * U;
-                        atomicMin(&p.gthr_bits[q], __float_as_uint(U));
-                    }
-                    float g = __uint_as_float(g_bits);
-                    tau_g = fminf(tau_g, (g - base_t) + 1e-5f * (g + base_t));
-                    P = fminf(P, tau_g);
-                }
             }
-            flush();
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence_block();
+                atomicAdd(&s_misc[4], 1u);
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"((kTcEpiWarps + 1) * 32) : "memory");
             // merge this item's k smallest into the shared set (distinct values only: a value both sides
             // already hold must not be counted twice; dropping a legitimately equal value only loosens the bound)
-            if (valid && improved) {
+            if (valid && half == 0 && s_impr[row]) {
+              const uint32_t q = qi.x;
+              const float base_t = s_base[row];
+              float r[KR];
+#pragma unroll
+              for (int i = 0; i < KR; i++) r[i] = s_r[row * kRS + i];
+              // insert v into the descending array g (drops the current largest)
+              auto insert_desc = [&](float (&g)[KR], float v) {
+                  g[0] = v;
+#pragma unroll
+                  for (int i = 0; i + 1 < KR; i++) {
+                      float hi_v = fmaxf(g[i], g[i + 1]), lo_v = fminf(g[i], g[i + 1]);
+                      g[i] = hi_v;
+                      g[i + 1] = lo_v;
+                  }
+              };
               bool done = false;
               while (!done) {
+                // the critical section runs INSIDE the retry loop: a lane that holds a lock always finishes
+                // and releases it before it waits for the other lanes of its warp
                 if (atomicCAS(&p.glock[q], 0u, 1u) != 0u) {
                     __nanosleep(64);
                     continue;
@@ -775,12 +939,12 @@ __global__ void finalize_kernel(FinalizeParams p) {
 bool tc_supported(int Dq, uint32_t k) {
     if (k == 0 || k > 32) return false;
     if (Dq < 2 || (Dq & 1)) return false;  // K = 8 floats per MMA = two 16-byte chunks
-    return tc_smem_layout(Dq, (int)k).total <= 227 * 1024;
+    return tc_smem_layout(Dq, k <= 8 ? 8 : (k <= 16 ? 16 : 32)).total <= 227 * 1024;
 }
-void launch_row_norms(const float4* vecs, int Dq, const uint32_t* row_src, size_t nrows, float* vn_scaled, float* vn_true,
+void launch_row_norms(const float4* vecs, int Dq, const uint32_t* row_src, size_t nrows, float4* vn3, float* vn_true,
                       cudaStream_t st) {
     if (!nrows) return;
-    row_norm_kernel<<<(unsigned)ceil_div(nrows, 256), 256, 0, st>>>(vecs, Dq, row_src, nrows, vn_scaled, vn_true);
+    row_norm_kernel<<<(unsigned)ceil_div(nrows, 256), 256, 0, st>>>(vecs, Dq, row_src, nrows, vn3, vn_true);
     VIDX_LAUNCHED();
 }
 void launch_query_norms(const float4* xq4, int Dq, uint32_t nq, uint32_t k, float* qn, uint32_t* gthr_bits, uint32_t* cand_cnt,
@@ -833,10 +997,9 @@ static void launch_scan_tc_kr(const TcParams& p, size_t smem, cudaStream_t st) {
     VIDX_LAUNCHED();
 }
 void launch_scan_tc(const TcParams& p, cudaStream_t st) {
-    size_t smem = tc_smem_layout(p.Dq, (int)p.k).total;
-    if (p.k <= 8) launch_scan_tc_kr<8>(p, smem, st);
-    else if (p.k <= 16) launch_scan_tc_kr<16>(p, smem, st);
-    else launch_scan_tc_kr<32>(p, smem, st);
+    if (p.k <= 8) launch_scan_tc_kr<8>(p, tc_smem_layout(p.Dq, 8).total, st);
+    else if (p.k <= 16) launch_scan_tc_kr<16>(p, tc_smem_layout(p.Dq, 16).total, st);
+    else launch_scan_tc_kr<32>(p, tc_smem_layout(p.Dq, 32).total, st);
 }
 void launch_finalize(const FinalizeParams& p, cudaStream_t st) {
     if (!p.nq) return;

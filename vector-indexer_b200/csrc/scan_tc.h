@@ -6,7 +6,7 @@ namespace vidx {
 
 struct TcParams {
     const float4* vecs;            // interleaved groups
-    const float* vnorm;            // per row: (1-eps)*|v|^2, NaN for padding rows
+    const float4* vnorm;           // per row: (1-eps)*|v|^2 as three TF32-exact terms (x+y+z), NaN for padding rows
     int Dq;
     const float4* xq4;             // queries, row-major, Dq float4 per row
     const float* qnorm;            // per query |q|^2
@@ -55,7 +55,7 @@ struct FinalizeParams {
 };
 
 bool tc_supported(int Dq, uint32_t k);
-void launch_row_norms(const float4* vecs, int Dq, const uint32_t* row_src, size_t nrows, float* vn_scaled, float* vn_true,
+void launch_row_norms(const float4* vecs, int Dq, const uint32_t* row_src, size_t nrows, float4* vn3, float* vn_true,
                       cudaStream_t st);
 void launch_query_norms(const float4* xq4, int Dq, uint32_t nq, uint32_t k, float* qn, uint32_t* gthr_bits, uint32_t* cand_cnt,
                         uint32_t* overflow, float* gtop, uint32_t* glock, cudaStream_t st);
