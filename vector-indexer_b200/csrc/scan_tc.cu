@@ -85,6 +85,20 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                  "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// One lane of a converged warp (CUTLASS's elect_one_sync): lets the warp run a role's loop with warp-uniform
+// values -- which the compiler keeps in uniform registers -- while a single thread issues.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t"
+        ".reg .b32 rx;\n\t"
+        ".reg .pred px;\n\t"
+        "elect.sync rx|px, 0xffffffff;\n\t"
+        "@px mov.s32 %0, 1;\n\t"
+        "}"
+        : "+r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -362,7 +376,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
     uint32_t* s_misc = reinterpret_cast<uint32_t*>(smem + L.off_misc);   // [0] tmem base [1] item [2] queue tail [3] queue head [4] done
     const uint32_t nstages = L.stages;
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(kFull, tid >> 5, 0);  // warp-uniform for the compiler too
     const int Dq = p.Dq;
     if (tid == 0) {
         for (uint32_t i = 0; i < nstages; i++) {
@@ -401,7 +416,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
     for (;;) {
         if (tid == 0) s_misc[1] = atomicAdd(p.work_counter, 1u);
         __syncthreads();  // also: every warp is done with the previous item's queue
-        const uint32_t item = s_misc[1];
+        const uint32_t item = __shfl_sync(kFull, s_misc[1], 0);
         if (item >= total_items) break;
         if (tid == kTcThreads - 1) {  // empty queue for this item (published by the barriers below)
             s_misc[2] = 0;
@@ -485,36 +500,32 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
         __syncthreads();
 
         if (warp == 0) {
-            // ===== producer =====
-            if (lane == 0) {
-                for (uint32_t t = t0; t < t1; t++, it++) {
-                    const uint32_t a = it & (kTcAccStages - 1), aph = (it / kTcAccStages) & 1;
-                    const size_t g0 = (size_t)g_list + (size_t)t * kTcTileGroups;
-                    for (int kc = 0; kc < nkc; kc++, ks_it++) {
-                        const uint32_t s = ks_it % nstages, ph = (ks_it / nstages) & 1;
-                        mbar_wait(&bar_empty[s], ph ^ 1);
-                        // K-slice = chunks [8kc, 8kc+8) of the tile's supergroup: one contiguous run of HBM
-                        const bool last = kc == nkc - 1;
-                        if (last) mbar_wait(&bar_tempty[a], aph ^ 1);  // norm chunk of this accumulator stage is free
-                        const uint32_t nch = (uint32_t)min(kTcStageChunks, Dq - kc * kTcStageChunks);
-                        const uint32_t bytes = nch * kSuper * 16;
+            // ===== producer: the whole warp runs the loop (warp-uniform values), one elected lane issues =====
+            for (uint32_t t = t0; t < t1; t++, it++) {
+                const uint32_t a = it & (kTcAccStages - 1), aph = (it / kTcAccStages) & 1;
+                const size_t g0 = (size_t)g_list + (size_t)t * kTcTileGroups;
+                for (int kc = 0; kc < nkc; kc++, ks_it++) {
+                    const uint32_t s = ks_it % nstages, ph = (ks_it / nstages) & 1;
+                    mbar_wait(&bar_empty[s], ph ^ 1);
+                    // K-slice = chunks [8kc, 8kc+8) of the tile's supergroup: one contiguous run of HBM
+                    const bool last = kc == nkc - 1;
+                    if (last) mbar_wait(&bar_tempty[a], aph ^ 1);  // norm chunk of this accumulator stage is free
+                    const uint32_t nch = (uint32_t)min(kTcStageChunks, Dq - kc * kTcStageChunks);
+                    const uint32_t bytes = nch * kSuper * 16;
+                    if (elect_one()) {
                         mbar_expect_tx(&bar_full[s], bytes + (last ? 2048u : 0u));
                         bulk_g2s(sB + s * kTcStageBytes, p.vecs + f4_index(g0, Dq, kc * kTcStageChunks, 0), bytes, &bar_full[s]);
                         if (last) bulk_g2s(sNorm + a * 2048, p.vnorm + g0 * 32, 2048, &bar_full[s]);
                     }
+                    __syncwarp();
                 }
-            } else {
-                it += t1 - t0;
-                ks_it += (t1 - t0) * nkc;
             }
-            it = __shfl_sync(kFull, it, 0);
-            ks_it = __shfl_sync(kFull, ks_it, 0);
         } else if (warp == 1 || warp == 10) {
             // ===== MMA issuers: warp 1 takes the even tiles of this CTA's tile sequence, warp 10 the odd ones
             // (one thread each; the loop is kept to a few dozen instructions per K-slice because a single
             // thread's issue latency, not the tensor pipe, would otherwise bound the kernel) =====
             const uint32_t my_par = warp == 1 ? 0u : 1u;
-            if (lane == 0) {
+            {
                 // descriptor = lo | hi << 32; lo = start address >> 4 (14 bits) | LBO >> 4 << 16, hi = SBO >> 4 | version 1 << 14
                 const uint32_t desc_hi = (128u >> 4) | (1u << 14);
                 const uint32_t lbo_bits = (2048u >> 4) << 16;
@@ -536,26 +547,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
                         const uint32_t al = a_lo0 + (uint32_t)kc * (kTcStageChunks * 128);
                         const uint32_t bl = b_lo0 + s * (kTcStageBytes >> 4);
                         const int nks = min(kTcStageChunks / 2, (Dq >> 1) - kc * (kTcStageChunks / 2));
-                        if (kc == 0) tc_mma_tf32_lo<false>(d_tmem, al, bl, desc_hi, idesc);
-                        else tc_mma_tf32_lo<true>(d_tmem, al, bl, desc_hi, idesc);
-                        if (nks > 1) tc_mma_tf32_lo<true>(d_tmem, al + 256, bl + 256, desc_hi, idesc);
-                        if (nks > 2) tc_mma_tf32_lo<true>(d_tmem, al + 512, bl + 512, desc_hi, idesc);
-                        if (nks > 3) tc_mma_tf32_lo<true>(d_tmem, al + 768, bl + 768, desc_hi, idesc);
-                        if (kc == nkc - 1) {
-                            const uint32_t noff = L.off_norm + a * 2048;
-                            const uint32_t norm_lo = ((smem_u32(smem + noff) >> 4) & 0x3fffu) | (((L.off_zero - noff) >> 4) << 16);
-                            tc_mma_tf32_lo<true>(d_tmem, ones_lo, norm_lo, desc_hi, idesc);
+                        const uint32_t noff = L.off_norm + a * 2048;
+                        const uint32_t norm_lo = ((smem_u32(smem + noff) >> 4) & 0x3fffu) | (((L.off_zero - noff) >> 4) << 16);
+                        if (elect_one()) {
+                            if (kc == 0) tc_mma_tf32_lo<false>(d_tmem, al, bl, desc_hi, idesc);
+                            else tc_mma_tf32_lo<true>(d_tmem, al, bl, desc_hi, idesc);
+                            if (nks > 1) tc_mma_tf32_lo<true>(d_tmem, al + 256, bl + 256, desc_hi, idesc);
+                            if (nks > 2) tc_mma_tf32_lo<true>(d_tmem, al + 512, bl + 512, desc_hi, idesc);
+                            if (nks > 3) tc_mma_tf32_lo<true>(d_tmem, al + 768, bl + 768, desc_hi, idesc);
+                            if (kc == nkc - 1) tc_mma_tf32_lo<true>(d_tmem, ones_lo, norm_lo, desc_hi, idesc);
+                            tc_commit(&bar_empty[s]);                       // K-slice free once these MMAs have read it
+                            if (kc == nkc - 1) tc_commit(&bar_tfull[a]);    // accumulator tile ready for the epilogue
                         }
-                        tc_commit(&bar_empty[s]);  // K-slice free once these MMAs have read it
+                        __syncwarp();
                     }
-                    tc_commit(&bar_tfull[a]);      // accumulator tile ready for the epilogue
                 }
-            } else {
-                it += t1 - t0;
-                ks_it += (t1 - t0) * nkc;
             }
-            it = __shfl_sync(kFull, it, 0);
-            ks_it = __shfl_sync(kFull, ks_it, 0);
         } else if (warp == 11) {
             // ===== selector: the only writer of the rows' bounds and top-k sets =====
             const uint32_t row0_item = (g_list + t0 * kTcTileGroups) * 32u;
