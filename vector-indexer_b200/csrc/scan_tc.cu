@@ -35,7 +35,7 @@
 
 namespace vidx {
 
-constexpr int kTcThreads = 384;       // warp 0 producer, warp 1 MMA (even tiles), warps 2-9 epilogue, warp 10 MMA (odd tiles), warp 11 selector
+constexpr int kTcThreads = 416;       // warps 0, 12 producers (even / odd K-slices), warps 1, 10 MMA (even / odd tiles), warps 2-9 epilogue, warp 11 selector
 constexpr int kTcEpiWarps = 8;
 constexpr int kTcM = 128;            // queries per tile (UMMA M)
 constexpr int kTcTileGroups = 4;     // 4 groups = 128 vectors per stage
@@ -499,25 +499,32 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
         fence_proxy_async();
         __syncthreads();
 
-        if (warp == 0) {
-            // ===== producer: the whole warp runs the loop (warp-uniform values), one elected lane issues =====
-            for (uint32_t t = t0; t < t1; t++, it++) {
+        if (warp == 0 || warp == 12) {
+            // ===== producers: warp 0 loads the even K-slices of this CTA's slice sequence, warp 12 the odd ones.
+            // Each warp runs the loop converged (warp-uniform values), one elected lane issues.  A list chunk is
+            // one linear stream in HBM (tiles and their K-slices are consecutive), so the source just advances. =====
+            const uint32_t my_par = warp == 0 ? 0u : 1u;
+            const uint32_t tile_bytes = (uint32_t)Dq * kSuper * 16;
+            const unsigned char* src = reinterpret_cast<const unsigned char*>(p.vecs) + ((size_t)(g_list >> 2) + t0) * tile_bytes;
+            const float4* nsrc = p.vnorm + ((size_t)g_list + (size_t)t0 * kTcTileGroups) * 32;
+            for (uint32_t t = t0; t < t1; t++, it++, nsrc += kSuper) {
                 const uint32_t a = it & (kTcAccStages - 1), aph = (it / kTcAccStages) & 1;
-                const size_t g0 = (size_t)g_list + (size_t)t * kTcTileGroups;
                 for (int kc = 0; kc < nkc; kc++, ks_it++) {
-                    const uint32_t s = ks_it % nstages, ph = (ks_it / nstages) & 1;
-                    mbar_wait(&bar_empty[s], ph ^ 1);
-                    // K-slice = chunks [8kc, 8kc+8) of the tile's supergroup: one contiguous run of HBM
-                    const bool last = kc == nkc - 1;
-                    if (last) mbar_wait(&bar_tempty[a], aph ^ 1);  // norm chunk of this accumulator stage is free
                     const uint32_t nch = (uint32_t)min(kTcStageChunks, Dq - kc * kTcStageChunks);
                     const uint32_t bytes = nch * kSuper * 16;
-                    if (elect_one()) {
-                        mbar_expect_tx(&bar_full[s], bytes + (last ? 2048u : 0u));
-                        bulk_g2s(sB + s * kTcStageBytes, p.vecs + f4_index(g0, Dq, kc * kTcStageChunks, 0), bytes, &bar_full[s]);
-                        if (last) bulk_g2s(sNorm + a * 2048, p.vnorm + g0 * 32, 2048, &bar_full[s]);
+                    if ((ks_it & 1u) == my_par) {
+                        const uint32_t s = ks_it % nstages, ph = (ks_it / nstages) & 1;
+                        mbar_wait(&bar_empty[s], ph ^ 1);
+                        const bool last = kc == nkc - 1;
+                        if (last) mbar_wait(&bar_tempty[a], aph ^ 1);  // norm chunk of this accumulator stage is free
+                        if (elect_one()) {
+                            mbar_expect_tx(&bar_full[s], bytes + (last ? 2048u : 0u));
+                            bulk_g2s(sB + s * kTcStageBytes, src, bytes, &bar_full[s]);
+                            if (last) bulk_g2s(sNorm + a * 2048, nsrc, 2048, &bar_full[s]);
+                        }
+                        __syncwarp();
                     }
-                    __syncwarp();
+                    src += bytes;
                 }
             }
         } else if (warp == 1 || warp == 10) {
