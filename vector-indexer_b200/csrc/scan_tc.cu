@@ -44,8 +44,8 @@ constexpr int kTcQueueCap = 512;     // hit queue entries (power of two)
 constexpr int kTcStageCap = 256;     // survivors staged by the selector before a bulk append
 constexpr int kTcAccStages = 4;      // accumulator tiles in TMEM
 constexpr int kTcTmemCols = 512;     // 4 accumulator stages x 128 columns
-constexpr int kTcStages = 8;         // shared-memory ring: stages of 128 vectors x 32 dims (16 KB)
-constexpr int kTcStageChunks = 8;    // 16-byte chunks (4 floats) of every vector per stage
+constexpr int kTcStages = 4;         // shared-memory ring: stages of 128 vectors x 64 dims (32 KB)
+constexpr int kTcStageChunks = 16;   // 16-byte chunks (4 floats) of every vector per stage
 constexpr uint32_t kTcStageBytes = kTcStageChunks * kTcTileGroups * 512;
 constexpr float kTcEps = 2.5e-3f;    // see header comment; needed: ~1.99e-3
 
@@ -559,9 +559,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
                         if (elect_one()) {
                             if (kc == 0) tc_mma_tf32_lo<false>(d_tmem, al, bl, desc_hi, idesc);
                             else tc_mma_tf32_lo<true>(d_tmem, al, bl, desc_hi, idesc);
-                            if (nks > 1) tc_mma_tf32_lo<true>(d_tmem, al + 256, bl + 256, desc_hi, idesc);
-                            if (nks > 2) tc_mma_tf32_lo<true>(d_tmem, al + 512, bl + 512, desc_hi, idesc);
-                            if (nks > 3) tc_mma_tf32_lo<true>(d_tmem, al + 768, bl + 768, desc_hi, idesc);
+#pragma unroll
+                            for (int ks = 1; ks < kTcStageChunks / 2; ks++)
+                                if (ks < nks) tc_mma_tf32_lo<true>(d_tmem, al + ks * 256, bl + ks * 256, desc_hi, idesc);
                             if (kc == nkc - 1) tc_mma_tf32_lo<true>(d_tmem, ones_lo, norm_lo, desc_hi, idesc);
                             tc_commit(&bar_empty[s]);                       // K-slice free once these MMAs have read it
                             if (kc == nkc - 1) tc_commit(&bar_tfull[a]);    // accumulator tile ready for the epilogue
