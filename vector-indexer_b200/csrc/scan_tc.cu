@@ -40,11 +40,13 @@ constexpr int kTcEpiWarps = 8;
 constexpr int kTcM = 128;            // queries per tile (UMMA M)
 constexpr int kTcTileGroups = 4;     // 4 groups = 128 vectors per stage
 constexpr int kTcMaxChunkTiles = 64; // tiles per work item: chosen on the device, 4..64 (512..8192 vectors)
-constexpr int kTcQueueCap = 512;     // hit queue entries (power of two)
-constexpr int kTcStageCap = 256;     // survivors staged by the selector before a bulk append
+// hit queue entries (power of two) and survivors staged by the selector before a bulk append; the 32-entry
+// top-k sets (k > 16) leave room for smaller ones only
+__host__ __device__ constexpr int tc_queue_cap(int kr) { return kr > 16 ? 128 : 512; }
+__host__ __device__ constexpr int tc_stage_cap(int kr) { return kr > 16 ? 128 : 256; }
 constexpr int kTcAccStages = 4;      // accumulator tiles in TMEM
 constexpr int kTcTmemCols = 512;     // 4 accumulator stages x 128 columns
-constexpr int kTcStages = 4;         // shared-memory ring: stages of 128 vectors x 64 dims (32 KB)
+constexpr int kTcStages = 4;         // shared-memory ring: stages of 128 vectors x 64 dims (32 KB), two per tile pipeline
 constexpr int kTcStageChunks = 16;   // 16-byte chunks (4 floats) of every vector per stage
 constexpr uint32_t kTcStageBytes = kTcStageChunks * kTcTileGroups * 512;
 constexpr float kTcEps = 2.5e-3f;    // see header comment; needed: ~1.99e-3
@@ -303,7 +305,7 @@ struct TcSmemLayout {
 };
 __host__ __device__ inline TcSmemLayout tc_smem_layout(int Dq, int kr) {
     TcSmemLayout L;
-    L.stages = kr > 16 ? kTcStages - 1 : kTcStages;         // the 32-entry top-k sets need the room of one ring stage
+    L.stages = kTcStages;
     L.a_bytes = (uint32_t)Dq * kTcM * 16;                   // query tile, [chunk][128 rows][16 B]
     L.off_b = L.a_bytes;                                    // ring of list-tile K-slices
     L.off_norm = L.off_b + L.stages * kTcStageBytes;        // per accumulator stage: norm chunk [128 rows][16 B]
@@ -311,8 +313,8 @@ __host__ __device__ inline TcSmemLayout tc_smem_layout(int Dq, int kr) {
     L.off_zero = L.off_ones + 2048;                         // second K chunk of the norm step, both operands: zeros
     L.off_r = L.off_zero + 2048;                            // per query row: its k smallest filter values, descending
     L.off_queue = L.off_r + (uint32_t)kTcM * (kr + 1) * 4;  // (row stride kr+1: lanes on different rows hit different banks)
-    L.off_stage = L.off_queue + kTcQueueCap * 8;            // hit queue: epilogue threads -> selector warp; then survivor staging
-    L.off_q = L.off_stage + kTcStageCap * 12;               // (query, probe rank) of the tile's rows
+    L.off_stage = L.off_queue + tc_queue_cap(kr) * 8;            // hit queue: epilogue threads -> selector warp; then survivor staging
+    L.off_q = L.off_stage + tc_stage_cap(kr) * 12;               // (query, probe rank) of the tile's rows
     L.off_row = L.off_q + kTcM * 8;                         // per row: bound P, delta, base, improved flag
     L.off_bar = L.off_row + 4 * kTcM * 4;
     L.off_misc = L.off_bar + (2 * kTcStages + 2 * kTcAccStages) * 8;
@@ -361,6 +363,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
     unsigned char* sNorm = smem + L.off_norm;
     constexpr int kRS = KR + 1;                                     // row stride of s_r
     float* s_r = reinterpret_cast<float*>(smem + L.off_r);          // [128][KR+1]
+    constexpr int kTcQueueCap = tc_queue_cap(KR), kTcStageCap = tc_stage_cap(KR);
     uint2* s_stage = reinterpret_cast<uint2*>(smem + L.off_stage);  // [kTcStageCap] (row id, query row)
     float* s_stage_v = reinterpret_cast<float*>(smem + L.off_stage + kTcStageCap * 8);  // [kTcStageCap] filter value
     uint2* s_queue = reinterpret_cast<uint2*>(smem + L.off_queue);  // [kTcQueueCap]
@@ -374,7 +377,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
     uint64_t* bar_tfull = bar_empty + kTcStages;                         // [4] accumulator tile complete
     uint64_t* bar_tempty = bar_tfull + kTcAccStages;                     // [4] accumulator tile drained
     uint32_t* s_misc = reinterpret_cast<uint32_t*>(smem + L.off_misc);   // [0] tmem base [1] item [2] queue tail [3] queue head [4] done
-    const uint32_t nstages = L.stages;
+    constexpr uint32_t nstages = kTcStages;
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(kFull, tid >> 5, 0);  // warp-uniform for the compiler too
@@ -411,7 +414,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
     const int nkc = (Dq + kTcStageChunks - 1) / kTcStageChunks;  // K-slices per tile
     const float kInf = __int_as_float(0x7f800000);
     uint32_t it = 0;     // tiles processed so far by this CTA (accumulator stage = it & 3, phase = (it >> 2) & 1)
-    uint32_t ks_it = 0;  // K-slices processed so far (ring stage = ks_it % nstages, phase = (ks_it / nstages) & 1)
+    // Two independent tile pipelines, each with its own producer warp, MMA warp and half of the ring: pipeline 0
+    // takes the even tiles of this CTA's tile sequence, pipeline 1 the odd ones.  (One ring shared by two issuers
+    // would let an issuer run a whole ring ahead of the other, where a phase-parity wait reads a stale "ready".)
+    uint32_t ks_it = 0;  // K-slices processed so far by this warp's pipeline (stage = 2*pipe + (ks_it & 1), phase = (ks_it >> 1) & 1)
 
     for (;;) {
         if (tid == 0) s_misc[1] = atomicAdd(p.work_counter, 1u);
@@ -500,38 +506,38 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
         __syncthreads();
 
         if (warp == 0 || warp == 12) {
-            // ===== producers: warp 0 loads the even K-slices of this CTA's slice sequence, warp 12 the odd ones.
-            // Each warp runs the loop converged (warp-uniform values), one elected lane issues.  A list chunk is
-            // one linear stream in HBM (tiles and their K-slices are consecutive), so the source just advances. =====
-            const uint32_t my_par = warp == 0 ? 0u : 1u;
+            // ===== producers (pipeline 0: warp 0, pipeline 1: warp 12).  The warp runs the loop converged
+            // (warp-uniform values), one elected lane issues.  A list chunk is one linear stream in HBM (tiles and
+            // their K-slices are consecutive), so the source just advances. =====
+            const uint32_t pipe = warp == 0 ? 0u : 1u;
             const uint32_t tile_bytes = (uint32_t)Dq * kSuper * 16;
             const unsigned char* src = reinterpret_cast<const unsigned char*>(p.vecs) + ((size_t)(g_list >> 2) + t0) * tile_bytes;
             const float4* nsrc = p.vnorm + ((size_t)g_list + (size_t)t0 * kTcTileGroups) * 32;
-            for (uint32_t t = t0; t < t1; t++, it++, nsrc += kSuper) {
+            for (uint32_t t = t0; t < t1; t++, it++, nsrc += kSuper, src += tile_bytes) {
+                if ((it & 1u) != pipe) continue;
                 const uint32_t a = it & (kTcAccStages - 1), aph = (it / kTcAccStages) & 1;
+                const unsigned char* ssrc = src;
                 for (int kc = 0; kc < nkc; kc++, ks_it++) {
                     const uint32_t nch = (uint32_t)min(kTcStageChunks, Dq - kc * kTcStageChunks);
                     const uint32_t bytes = nch * kSuper * 16;
-                    if ((ks_it & 1u) == my_par) {
-                        const uint32_t s = ks_it % nstages, ph = (ks_it / nstages) & 1;
-                        mbar_wait(&bar_empty[s], ph ^ 1);
-                        const bool last = kc == nkc - 1;
-                        if (last) mbar_wait(&bar_tempty[a], aph ^ 1);  // norm chunk of this accumulator stage is free
-                        if (elect_one()) {
-                            mbar_expect_tx(&bar_full[s], bytes + (last ? 2048u : 0u));
-                            bulk_g2s(sB + s * kTcStageBytes, src, bytes, &bar_full[s]);
-                            if (last) bulk_g2s(sNorm + a * 2048, nsrc, 2048, &bar_full[s]);
-                        }
-                        __syncwarp();
+                    const uint32_t s = 2 * pipe + (ks_it & 1u), ph = (ks_it >> 1) & 1;
+                    mbar_wait(&bar_empty[s], ph ^ 1);
+                    const bool last = kc == nkc - 1;
+                    if (last) mbar_wait(&bar_tempty[a], aph ^ 1);  // norm chunk of this accumulator stage is free
+                    if (elect_one()) {
+                        mbar_expect_tx(&bar_full[s], bytes + (last ? 2048u : 0u));
+                        bulk_g2s(sB + s * kTcStageBytes, ssrc, bytes, &bar_full[s]);
+                        if (last) bulk_g2s(sNorm + a * 2048, nsrc, 2048, &bar_full[s]);
                     }
-                    src += bytes;
+                    __syncwarp();
+                    ssrc += bytes;
                 }
             }
         } else if (warp == 1 || warp == 10) {
             // ===== MMA issuers: warp 1 takes the even tiles of this CTA's tile sequence, warp 10 the odd ones
             // (one thread each; the loop is kept to a few dozen instructions per K-slice because a single
             // thread's issue latency, not the tensor pipe, would otherwise bound the kernel) =====
-            const uint32_t my_par = warp == 1 ? 0u : 1u;
+            const uint32_t pipe = warp == 1 ? 0u : 1u;
             {
                 // descriptor = lo | hi << 32; lo = start address >> 4 (14 bits) | LBO >> 4 << 16, hi = SBO >> 4 | version 1 << 14
                 const uint32_t desc_hi = (128u >> 4) | (1u << 14);
@@ -540,14 +546,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
                 const uint32_t b_lo0 = ((smem_u32(sB) >> 4) & 0x3fffu) | lbo_bits;
                 // norm step: K chunk 0 = (1,1,1,0) x (n_hi, n_mid, n_lo, 0), K chunk 1 = the shared zero block
                 const uint32_t ones_lo = ((smem_u32(smem + L.off_ones) >> 4) & 0x3fffu) | (((L.off_zero - L.off_ones) >> 4) << 16);
-                for (uint32_t t = t0; t < t1; t++, it++, ks_it += nkc) {
-                    if ((it & 1u) != my_par) continue;
+                for (uint32_t t = t0; t < t1; t++, it++) {
+                    if ((it & 1u) != pipe) continue;
                     const uint32_t a = it & (kTcAccStages - 1), aph = (it / kTcAccStages) & 1;
                     mbar_wait(&bar_tempty[a], aph ^ 1);
                     const uint32_t d_tmem = tmem_base + a * 128;
-                    uint32_t kq = ks_it;
-                    for (int kc = 0; kc < nkc; kc++, kq++) {
-                        const uint32_t s = kq % nstages, ph = (kq / nstages) & 1;
+                    for (int kc = 0; kc < nkc; kc++, ks_it++) {
+                        const uint32_t s = 2 * pipe + (ks_it & 1u), ph = (ks_it >> 1) & 1;
                         mbar_wait(&bar_full[s], ph);
                         tc_fence_after();
                         // chunk c of all 128 rows is one 2 KB block (128 x 16 B) in both tiles: +128 per chunk in >>4 units
@@ -689,7 +694,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
             }
             flush();
             it += t1 - t0;
-            ks_it += (t1 - t0) * nkc;
             asm volatile("bar.sync 1, %0;" ::"n"((kTcEpiWarps + 1) * 32) : "memory");
         } else {
             // ===== epilogue: one thread per (query row, column half); the accumulators already hold
