@@ -39,7 +39,7 @@ constexpr int kTcThreads = 416;       // warps 0, 12 producers (even / odd K-sli
 constexpr int kTcEpiWarps = 8;
 constexpr int kTcM = 128;            // queries per tile (UMMA M)
 constexpr int kTcTileGroups = 4;     // 4 groups = 128 vectors per stage
-constexpr int kTcMaxChunkTiles = 64; // tiles per work item: chosen on the device, 4..64 (512..8192 vectors)
+constexpr int kTcMaxChunkTiles = 128; // tiles per work item: chosen on the device, 8..128 (1024..16384 vectors)
 // hit queue entries (power of two) and survivors staged by the selector before a bulk append; the 32-entry
 // top-k sets (k > 16) leave room for smaller ones only
 __host__ __device__ constexpr int tc_queue_cap(int kr) { return kr > 16 ? 128 : 512; }
@@ -349,7 +349,7 @@ __device__ __forceinline__ float min32(const float* v) {
     return fminf(fminf(b0, b1), fminf(b2, b3));
 }
 
-// Queue entry (8 bytes, written with one 64-bit store): x = 0x40000000 | kind << 31 | tile << 14 | column << 7 | row
+// Queue entry (8 bytes, written with one 64-bit store): x = 0x40000000 | kind << 31 | tile (8 bits) << 14 | column << 7 | row
 // (never zero; zero marks an empty slot), y = float bits of the value.  kind 0 = a filter value that passed
 // the row's bound (a survivor candidate), kind 1 = a tighter bound for the row.
 constexpr uint32_t kEntValid = 0x40000000u;
@@ -644,7 +644,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
                 const unsigned cm = __ballot_sync(kFull, cand_ok);
                 if (cand_ok) {
                     const uint32_t pos = nstage + __popc(cm & ((1u << lane) - 1u));
-                    s_stage[pos] = make_uint2(row0_item + ((e.x >> 14) & 127u) * 128u + ((e.x >> 7) & 127u), row);
+                    s_stage[pos] = make_uint2(row0_item + ((e.x >> 14) & 255u) * 128u + ((e.x >> 7) & 127u), row);
                     s_stage_v[pos] = val;
                 }
                 nstage += __popc(cm);
