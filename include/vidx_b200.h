@@ -153,6 +153,12 @@ int vidx_load(vidx_index* idx, const char* index_dir, const char* shards_dir);
  * src/ivf_index.rs:104-164).  Centroids stay replicated so every rank computes the same
  * probe lists.  Call after build/load, before search. */
 int vidx_set_partition(vidx_index* idx, int rank, int world);
+/* How the index is split: 0 = auto (default: shards, unless the most loaded rank would exceed the
+ * mean by more than 15 % -- then ranges), 1 = shards, 2 = ranges (every rank owns the r-th contiguous
+ * range of the segments of every list).  vidx_get_partition_kind: what the last vidx_set_partition
+ * used (1 shards, 2 ranges). */
+int vidx_set_partition_mode(vidx_index* idx, int mode);
+int vidx_get_partition_kind(const vidx_index* idx);
 int vidx_get_shard_owner(const vidx_index* idx, int world, int32_t* out /* num_shards */);
 /* The partition rule on its own (host only, no device needed): shard_sizes[num_shards]
  * vector counts -> owner rank per shard; largest shard first to the least loaded rank,

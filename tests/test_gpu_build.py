@@ -127,9 +127,10 @@ def test_load_with_missing_shard_does_not_fail(ffi, tmp_path):
     assert not (set(I.ravel().tolist()) & gone)
 
 
-def test_partition_and_merge_equal_single_gpu(ffi):
-    """Multi-GPU data flow emulated on one device: each 'rank' scans only the lists of the
-    shards it owns; merging the per-rank top-k reproduces the single-GPU answer."""
+@pytest.mark.parametrize("mode", ["shards", "ranges"])
+def test_partition_and_merge_equal_single_gpu(ffi, mode):
+    """Multi-GPU data flow emulated on one device: each 'rank' scans only what it owns (the lists of
+    its shards, or its range of every list); merging the per-rank top-k reproduces the single-GPU answer."""
     import torch
     xb, xq = bench_data(20000, 32, 256)
     full = ffi.Index(32).build(xb)
@@ -137,9 +138,11 @@ def test_partition_and_merge_equal_single_gpu(ffi):
     world = 4
     owners = full.shard_owner(world)
     assert set(owners.tolist()) == set(range(world))
+    full.set_partition_mode(mode)
     Ds, Is = [], []
     for r in range(world):
         full.set_partition(r, world)
+        assert full.partition_kind == mode
         D, I = full.search(xq, 10, 16)
         Ds.append(D)
         Is.append(I)

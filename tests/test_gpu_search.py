@@ -45,6 +45,14 @@ def test_search_matches_oracle_dense_regime(oracle, ffi):
     check_search(oix, gix, xq, 32, 2)
 
 
+@pytest.mark.parametrize("d,k", [(32, 17), (32, 32), (64, 32), (200, 10), (256, 10)])
+def test_search_tensor_core_pipeline_shapes(oracle, ffi, d, k):
+    # one / two / four K-slices per tile and the 32-entry top-k sets: every ring geometry of scan_tc_kernel
+    xb, xq = bench_data(30000, d, 1500)
+    oix, gix = make_pair(oracle, ffi, xb, 12)
+    check_search(oix, gix, xq, k, 2)
+
+
 @pytest.mark.parametrize("d", [1, 3, 30, 129, 200])
 def test_search_odd_dimensions(oracle, ffi, d):
     xb, xq = bench_data(3000, d, 150, seed=d)

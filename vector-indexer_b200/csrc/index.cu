@@ -191,16 +191,7 @@ void Index::build_lists(const float* d_data, uint64_t n, const uint32_t* labels,
     h2d(d_segs.as<SegDesc>(), segs.data(), segs.size(), stream);
     // per-list layout + row norms for the tensor-core scan
     {
-        std::vector<uint32_t> g0(nlist + 1), ng(nlist + 1);
-        for (uint64_t l = 0; l < nlist; l++) {
-            g0[l] = (uint32_t)list_goff[l];
-            ng[l] = (uint32_t)(list_goff[l + 1] - list_goff[l]);
-        }
-        d_list_g0.reserve(g0.size() * 4);
-        d_list_ng.reserve(ng.size() * 4);
         d_list_len.reserve((nlist + 1) * 4);
-        h2d(d_list_g0.as<uint32_t>(), g0.data(), g0.size(), stream);
-        h2d(d_list_ng.as<uint32_t>(), ng.data(), ng.size(), stream);
         h2d(d_list_len.as<uint32_t>(), list_len.data(), list_len.size(), stream);
         d_vnorm.reserve((std::max<uint64_t>(nrows, 1) + 128) * 16);  // rows are whole supergroups: a tile copy reads 128 entries
         VIDX_CUDA(cudaMemsetAsync(d_vnorm.p, 0xff, (std::max<uint64_t>(nrows, 1) + 128) * 16, stream));
@@ -247,23 +238,58 @@ std::vector<int32_t> Index::shard_owners(int world) const {
     return partition_shards(load, world);
 }
 
-// Lists this rank does not own get zero segments, so grouping skips them; the centroid
-// table stays complete so every rank derives identical probe lists.
+// Two ways to split the index over `world` ranks; the centroid table stays complete either way, so every rank
+// derives identical probe lists with no communication.
+//   shards : the reference's unit (super-centroid groups of lists, ivf_index.rs:104-164) dealt to ranks by greedy
+//            balance; a list a rank does not own gets an empty segment range, so grouping skips it.
+//   ranges : every rank owns one contiguous range of the segments of EVERY list (list l: rank r owns range
+//            (r + l) mod world, so short lists spread over all ranks).  Equal distances that straddle ranks may
+//            come back in a different order than on one GPU -- the reference leaves that order unspecified too
+//            (HashSet iteration, ivf_index.rs:223-229).  Used when the shards cannot be balanced: the reference's barely-trained k-means routinely
+//            puts nearly all vectors into a handful of lists of ONE shard (SIFT-1M shape, nlist = 1024: one shard
+//            holds 999 954 of 1 000 000 vectors).
+// part_mode 0 picks shards unless the most loaded rank would exceed the mean by more than 15 %.
 void Index::apply_partition() {
     std::vector<int32_t> owner;
-    if (part_world > 1) owner = shard_owners(part_world);
-    // segment ids stay global; an unowned list maps to an empty range
+    part_by_ranges = false;
+    if (part_world > 1) {
+        owner = shard_owners(part_world);
+        std::vector<uint64_t> rank_load(part_world, 0);
+        uint64_t total = 0;
+        for (uint64_t l = 0; l < nlist; l++) {
+            rank_load[owner[c2shard[l]]] += list_len[l];
+            total += list_len[l];
+        }
+        uint64_t mx = 0;
+        for (uint64_t v : rank_load) mx = std::max(mx, v);
+        const bool unbalanced = (double)mx * part_world > 1.15 * (double)std::max<uint64_t>(total, 1);
+        part_by_ranges = part_mode == 2 || (part_mode == 0 && unbalanced);
+    }
+    // segment ids stay global; an unowned list (or part of a list) maps to an empty range
     list_seg_part.assign(nlist + 1, make_uint2(0, 0));
+    std::vector<uint32_t> g0(nlist + 1, 0), ng(nlist + 1, 0);
     owned_vectors = 0;
     std::vector<uint32_t> nseg_owned;
     for (uint64_t l = 0; l < nlist; l++) {
-        bool own = part_world <= 1 || owner[c2shard[l]] == part_rank;
-        uint32_t s0 = list_seg_off_all[l], s1 = list_seg_off_all[l + 1];
-        list_seg_part[l] = make_uint2(s0, own ? s1 : s0);
-        if (own) {
-            owned_vectors += list_len[l];
-            nseg_owned.push_back(s1 - s0);
+        const uint32_t s0 = list_seg_off_all[l], s1 = list_seg_off_all[l + 1];
+        uint32_t a = s0, b = s1;
+        if (part_world > 1) {
+            if (part_by_ranges) {
+                // rotate by the list id so that lists with fewer segments than ranks spread over all ranks
+                const uint64_t S = s1 - s0, rr = ((uint64_t)part_rank + l) % (uint64_t)part_world;
+                a = s0 + (uint32_t)(S * rr / (uint64_t)part_world);
+                b = s0 + (uint32_t)(S * (rr + 1) / (uint64_t)part_world);
+            } else if (owner[c2shard[l]] != part_rank) {
+                b = a;
+            }
         }
+        list_seg_part[l] = make_uint2(a, b);
+        g0[l] = b > a ? segs[a].g0 : (uint32_t)list_goff[l];
+        for (uint32_t sidx = a; sidx < b; sidx++) {
+            ng[l] += segs[sidx].ng;
+            owned_vectors += segs[sidx].nvalid;
+        }
+        if (b > a) nseg_owned.push_back(b - a);
     }
     // prefix of the largest per-list segment counts: bounds the (query,segment) pairs
     std::sort(nseg_owned.begin(), nseg_owned.end(), std::greater<uint32_t>());
@@ -271,6 +297,11 @@ void Index::apply_partition() {
     for (size_t i = 0; i < nseg_owned.size(); i++) seg_prefix[i + 1] = seg_prefix[i] + nseg_owned[i];
     d_list_seg.reserve(list_seg_part.size() * sizeof(uint2));
     h2d(d_list_seg.as<uint2>(), list_seg_part.data(), list_seg_part.size(), stream);
+    // geometry of the owned part of each list for the tensor-core scan
+    d_list_g0.reserve(g0.size() * 4);
+    d_list_ng.reserve(ng.size() * 4);
+    h2d(d_list_g0.as<uint32_t>(), g0.data(), g0.size(), stream);
+    h2d(d_list_ng.as<uint32_t>(), ng.data(), ng.size(), stream);
     VIDX_CUDA(cudaStreamSynchronize(stream));
 }
 
@@ -1077,6 +1108,19 @@ int vidx_set_partition(vidx_index* idx, int rank, int world) {
         ix.apply_partition();
     });
 }
+int vidx_set_partition_mode(vidx_index* idx, int mode) {
+    return guarded([&] {
+        require(idx, VIDX_ERR_INVALID_INPUT, "idx is NULL");
+        require(mode >= 0 && mode <= 2, VIDX_ERR_INVALID_INPUT, "partition mode must be 0 (auto), 1 (shards) or 2 (ranges)");
+        std::lock_guard<std::mutex> lk(idx->mu);
+        idx->ix.part_mode = mode;
+        if (idx->ix.built) {
+            idx->ix.ensure_device();
+            idx->ix.apply_partition();
+        }
+    });
+}
+int vidx_get_partition_kind(const vidx_index* idx) { return idx ? (idx->ix.part_by_ranges ? 2 : 1) : 0; }
 int vidx_get_shard_owner(const vidx_index* idx, int world, int32_t* out) {
     return guarded([&] {
         require(idx && out && world >= 1, VIDX_ERR_INVALID_INPUT, "bad argument");

@@ -41,6 +41,8 @@ struct Index {
 
     // partition (multi-GPU): lists owned by this rank keep their segment range
     int part_rank = 0, part_world = 1;
+    int part_mode = 0;                    // 0 auto, 1 shards, 2 segment ranges of every list
+    bool part_by_ranges = false;          // what apply_partition chose
     uint64_t owned_vectors = 0;
     std::vector<uint2> list_seg_part;     // per list (first segment, end segment); empty if not owned
     std::vector<uint64_t> seg_prefix;     // prefix sums of per-list segment counts, largest first

@@ -78,6 +78,8 @@ _SIGS = {
     "vidx_save": (i32, [vp, C.c_char_p, C.c_char_p]),
     "vidx_load": (i32, [vp, C.c_char_p, C.c_char_p]),
     "vidx_set_partition": (i32, [vp, i32, i32]),
+    "vidx_set_partition_mode": (i32, [vp, i32]),
+    "vidx_get_partition_kind": (i32, [vp]),
     "vidx_get_shard_owner": (i32, [vp, i32, i32p]),
     "vidx_partition_shards": (i32, [u64p, u64, i32, i32p]),
     "vidx_merge_topk_device": (i32, [i32, vp, vp, u32, u64, u64, vp, vp, vp]),
@@ -271,6 +273,14 @@ class Index:
 
     def set_partition(self, rank, world):
         check(lib().vidx_set_partition(self.h, rank, world))
+
+    def set_partition_mode(self, mode):
+        """0 auto, 1 the reference's shards, 2 segment ranges of every list."""
+        check(lib().vidx_set_partition_mode(self.h, {"auto": 0, "shards": 1, "ranges": 2}.get(mode, mode)))
+
+    @property
+    def partition_kind(self):
+        return {1: "shards", 2: "ranges"}.get(lib().vidx_get_partition_kind(self.h))
 
     def shard_owner(self, world):
         out = np.zeros(self.num_shards, np.int32)
