@@ -396,7 +396,8 @@ def run_ours(args):
                 "config": {"workload": "configs[1]: 1Mx128 fp32 nlist=1024 nq=10k k=10", **w, "nprobe": nprobe,
                            "recall_at_10": final_recall, "recall_curve": curve, "nlist_nonempty": ix.nlist,
                            "l2": "inputs larger than L2 (index 512 MB)", "index_build_s": build_s,
-                           "parallelism": f"shards over {world} GPU(s), NCCL all-gather + merge" if world > 1 else "1 GPU"},
+                           "parallelism": (f"{ix.partition_kind} over {world} GPUs, queries replicated, NCCL all-gather of per-GPU "
+                                           f"top-k + device merge") if world > 1 else "1 GPU"},
                 "e2e": {"value": nq * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(xq.nbytes),
                         "d2h_bytes_per_step": int(nq * k * 12), "ms_per_step": 1e3 * e2e_s / args.steps},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_hbm": roofline_hbm,

@@ -191,8 +191,7 @@ void Index::build_lists(const float* d_data, uint64_t n, const uint32_t* labels,
     h2d(d_segs.as<SegDesc>(), segs.data(), segs.size(), stream);
     // per-list layout + row norms for the tensor-core scan
     {
-        d_list_len.reserve((nlist + 1) * 4);
-        h2d(d_list_len.as<uint32_t>(), list_len.data(), list_len.size(), stream);
+
         d_vnorm.reserve((std::max<uint64_t>(nrows, 1) + 128) * 16);  // rows are whole supergroups: a tile copy reads 128 entries
         VIDX_CUDA(cudaMemsetAsync(d_vnorm.p, 0xff, (std::max<uint64_t>(nrows, 1) + 128) * 16, stream));
         DevBuf d_vntrue;
@@ -267,7 +266,7 @@ void Index::apply_partition() {
     }
     // segment ids stay global; an unowned list (or part of a list) maps to an empty range
     list_seg_part.assign(nlist + 1, make_uint2(0, 0));
-    std::vector<uint32_t> g0(nlist + 1, 0), ng(nlist + 1, 0);
+    std::vector<uint32_t> g0(nlist + 1, 0), ng(nlist + 1, 0), own_len(nlist + 1, 0);
     owned_vectors = 0;
     std::vector<uint32_t> nseg_owned;
     for (uint64_t l = 0; l < nlist; l++) {
@@ -287,6 +286,7 @@ void Index::apply_partition() {
         g0[l] = b > a ? segs[a].g0 : (uint32_t)list_goff[l];
         for (uint32_t sidx = a; sidx < b; sidx++) {
             ng[l] += segs[sidx].ng;
+            own_len[l] += segs[sidx].nvalid;
             owned_vectors += segs[sidx].nvalid;
         }
         if (b > a) nseg_owned.push_back(b - a);
@@ -302,6 +302,8 @@ void Index::apply_partition() {
     d_list_ng.reserve(ng.size() * 4);
     h2d(d_list_g0.as<uint32_t>(), g0.data(), g0.size(), stream);
     h2d(d_list_ng.as<uint32_t>(), ng.data(), ng.size(), stream);
+    d_list_len.reserve(own_len.size() * 4);  // vectors of each list this rank scans (measurement only)
+    h2d(d_list_len.as<uint32_t>(), own_len.data(), own_len.size(), stream);
     VIDX_CUDA(cudaStreamSynchronize(stream));
 }
 
@@ -319,7 +321,7 @@ void Index::delete_workspace() {
     ws = nullptr;
 }
 
-constexpr uint32_t kSeedTiles = 16;  // seeding pass: first 2048 vectors of each query's nearest list
+constexpr uint32_t kSeedTiles = 4;  // seeding pass: first 512 vectors of each query's nearest list
 
 // stats: distinct probed lists -> algorithmic bytes; (query, list) pairs -> logical bytes / flops
 __global__ void list_stats_kernel(const uint32_t* __restrict__ list_cnt, const uint32_t* __restrict__ list_len, uint32_t nlist,

@@ -38,6 +38,8 @@ namespace vidx {
 constexpr int kTcThreads = 416;       // warps 0, 12 producers (even / odd K-slices), warps 1, 10 MMA (even / odd tiles), warps 2-9 epilogue, warp 11 selector
 constexpr int kTcEpiWarps = 8;
 constexpr int kTcM = 128;            // queries per tile (UMMA M)
+constexpr int kTcSeedRows = 32;      // seeding pass: queries per work item (every row starts cold there and floods the
+                                     // selector, so the items are kept small to spread them over all SMs)
 constexpr int kTcTileGroups = 4;     // 4 groups = 128 vectors per stage
 constexpr int kTcMaxChunkTiles = 128; // tiles per work item: chosen on the device, 8..128 (1024..16384 vectors)
 // hit queue entries (power of two) and survivors staged by the selector before a bulk append; the 32-entry
@@ -293,7 +295,8 @@ __global__ void tc_items_kernel(const uint32_t* __restrict__ list_cnt, const uin
     uint32_t ntiles = (list_ngroups[l] + kTcTileGroups - 1) / kTcTileGroups;
     if (seed_tiles) ntiles = min(ntiles, seed_tiles);
     uint32_t nch = (ntiles + chunk - 1) / chunk;
-    items_per_list[l] = c ? ((c + kTcM - 1) / kTcM) * nch : 0u;
+    const uint32_t qrows = seed_tiles ? (uint32_t)kTcSeedRows : (uint32_t)kTcM;
+    items_per_list[l] = c ? ((c + qrows - 1) / qrows) * nch : 0u;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -318,7 +321,7 @@ __host__ __device__ inline TcSmemLayout tc_smem_layout(int Dq, int kr) {
     L.off_row = L.off_q + kTcM * 8;                         // per row: bound P, delta, base, improved flag
     L.off_bar = L.off_row + 4 * kTcM * 4;
     L.off_misc = L.off_bar + (2 * kTcStages + 2 * kTcAccStages) * 8;
-    L.total = L.off_misc + 64;
+    L.total = L.off_misc + 64 + 128;
     return L;
 }
 
@@ -349,9 +352,9 @@ __device__ __forceinline__ float min32(const float* v) {
     return fminf(fminf(b0, b1), fminf(b2, b3));
 }
 
-// Queue entry (8 bytes, written with one 64-bit store): x = 0x40000000 | kind << 31 | tile (8 bits) << 14 | column << 7 | row
-// (never zero; zero marks an empty slot), y = float bits of the value.  kind 0 = a filter value that passed
-// the row's bound (a survivor candidate), kind 1 = a tighter bound for the row.
+// Queue entry (8 bytes, written with one 64-bit store): x = 0x40000000 | tile (8 bits) << 14 | column << 7 | row
+// (never zero; zero marks an empty slot), y = float bits of the value: a filter value that passed the row's
+// bound (a survivor candidate).
 constexpr uint32_t kEntValid = 0x40000000u;
 
 template <int KR>
@@ -377,6 +380,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
     uint64_t* bar_tfull = bar_empty + kTcStages;                         // [4] accumulator tile complete
     uint64_t* bar_tempty = bar_tfull + kTcAccStages;                     // [4] accumulator tile drained
     uint32_t* s_misc = reinterpret_cast<uint32_t*>(smem + L.off_misc);   // [0] tmem base [1] item [2] queue tail [3] queue head [4] done
+    volatile float* s_tmpv = reinterpret_cast<volatile float*>(s_misc + 16);  // [32] selector scratch
     constexpr uint32_t nstages = kTcStages;
 
     const int tid = threadIdx.x, lane = tid & 31;
@@ -437,7 +441,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
         }
         const uint32_t l = lo;
         const uint32_t cnt = p.list_cnt[l];
-        const uint32_t nqt = (cnt + kTcM - 1) / kTcM;
+        const uint32_t qrows = p.mode == 1 ? (uint32_t)kTcSeedRows : (uint32_t)kTcM;  // query rows per work item
+        const uint32_t nqt = (cnt + qrows - 1) / qrows;
         const uint32_t local = item - p.item_off[l];
         const uint32_t chunk = local / nqt, qt = local - chunk * nqt;
         const uint32_t ngl = p.list_ngroups[l];
@@ -445,11 +450,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
         uint32_t ntiles = (ngl + kTcTileGroups - 1) / kTcTileGroups;
         if (p.mode == 1) ntiles = min(ntiles, p.seed_tiles);  // seeding pass: the head of each query's nearest list
         const uint32_t t0 = chunk * chunk_tiles, t1 = min(ntiles, t0 + chunk_tiles);
-        const uint32_t nq_tile = min((uint32_t)kTcM, cnt - qt * kTcM);
+        const uint32_t nq_tile = min(qrows, cnt - qt * qrows);
 
         if (tid < kTcM) {
             // per-row state of this item: the (query, rank) of the row, its top-k set as known to all CTAs, its bound
-            const uint2 qi = tid < (int)nq_tile ? p.list_qlist[p.list_qoff[l] + qt * kTcM + tid] : make_uint2(kNoRow, 0);
+            const uint2 qi = tid < (int)nq_tile ? p.list_qlist[p.list_qoff[l] + qt * qrows + tid] : make_uint2(kNoRow, 0);
             s_q[tid] = qi;
             float P = -kInf, delta = 0.0f, base_t = 0.0f;
             float* rr = s_r + tid * kRS;
@@ -637,10 +642,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
                 if (mine) sts_volatile_v2(&s_queue[(head + lane) & (kTcQueueCap - 1)], make_uint2(0u, 0u));
                 head += (uint32_t)n;
                 if (lane == 0) sts_volatile(&s_misc[3], head);
-                const uint32_t row = e.x & 127u, kind = e.x >> 31;
+                const uint32_t row = e.x & 127u;
                 const float val = __uint_as_float(e.y);
                 // (1) survivors: everything still inside the row's bound goes to the exact re-check
-                const bool cand_ok = mine && kind == 0u && val <= vP[row];
+                const bool cand_ok = mine && val <= vP[row];
                 const unsigned cm = __ballot_sync(kFull, cand_ok);
                 if (cand_ok) {
                     const uint32_t pos = nstage + __popc(cm & ((1u << lane) - 1u));
@@ -650,45 +655,48 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
                 nstage += __popc(cm);
                 __syncwarp();
                 if (nstage > (uint32_t)kTcStageCap - 32u) flush();
-                // (2) state changes: one lane per distinct row and round, each lane updating its row's set serially
-                bool todo = mine && (kind == 1u ? val < vP[row] : (cand_ok && val < vr[row * kRS]));
-                for (;;) {
-                    const unsigned tm = __ballot_sync(kFull, todo);
-                    if (!tm) break;
+                // (2) state changes: one lane per distinct row folds ALL of that row's values of this batch into the
+                // row's set (threads queue their hits back to back, so a batch usually holds runs of one row)
+                const bool todo = cand_ok && val < vr[row * kRS];
+                const unsigned tm = __ballot_sync(kFull, todo);
+                if (tm) {
+                    s_tmpv[lane] = val;
+                    __syncwarp();
                     if (todo) {
                         const unsigned peers = __match_any_sync(tm, row);
                         if (lane == __ffs(peers) - 1) {
-                            float newP = val;
-                            if (kind == 0u) {
-                                float g[KR];
+                            float g[KR];
 #pragma unroll
-                                for (int i = 0; i < KR; i++) g[i] = vr[row * kRS + i];
-                                if (val < g[0]) {
-                                    g[0] = val;  // drop the largest, bubble the new value into place (descending)
+                            for (int i = 0; i < KR; i++) g[i] = vr[row * kRS + i];
+                            bool ins = false;
+                            for (unsigned pm = peers; pm; pm &= pm - 1) {
+                                const float v = s_tmpv[__ffs(pm) - 1];
+                                if (v < g[0]) {
+                                    g[0] = v;  // drop the largest, bubble the new value into place (descending)
 #pragma unroll
                                     for (int i = 0; i + 1 < KR; i++) {
                                         const float hi_v = fmaxf(g[i], g[i + 1]), lo_v = fminf(g[i], g[i + 1]);
                                         g[i] = hi_v;
                                         g[i + 1] = lo_v;
                                     }
-#pragma unroll
-                                    for (int i = 0; i < KR; i++) vr[row * kRS + i] = g[i];
-                                    s_impr[row] = 1u;
+                                    ins = true;
                                 }
-                                newP = g[0] + s_delta[row];
                             }
-                            if (newP < vP[row]) {
-                                vP[row] = newP;
+                            if (ins) {
+#pragma unroll
+                                for (int i = 0; i < KR; i++) vr[row * kRS + i] = g[i];
                                 s_impr[row] = 1u;
-                                float U = fmaxf(newP + s_base[row], 0.0f);
-                                U = U + 1e-5f * U;
-                                atomicMin(&p.gthr_bits[s_q[row].x], __float_as_uint(U));
+                                const float newP = g[0] + s_delta[row];
+                                if (newP < vP[row]) {
+                                    vP[row] = newP;
+                                    float U = fmaxf(newP + s_base[row], 0.0f);
+                                    U = U + 1e-5f * U;
+                                    atomicMin(&p.gthr_bits[s_q[row].x], __float_as_uint(U));
+                                }
                             }
-                            todo = false;
                         }
                     }
                     __syncwarp();
-                    todo = todo && (kind == 1u ? val < vP[row] : val < vr[row * kRS]);
                 }
                 if ((++refresh & 15u) == 0u) adopt(lane + 32 * (int)((refresh >> 4) & 3u));
             }
@@ -705,6 +713,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
             const bool valid = qi.x != kNoRow;
             const float delta = s_delta[row];
             float P = s_P[row];
+            float lr[KR];  // the k smallest values this thread queued in this item, descending (+inf until k exist)
+#pragma unroll
+            for (int i = 0; i < KR; i++) lr[i] = i < (int)p.k ? kInf : -kInf;
             // rows whose nearest list this is already scanned its first seed_tiles tiles in the seeding pass
             const bool skip_seeded = p.mode == 0 && qi.y == 0;
             auto push = [&](uint32_t info, float v) {
@@ -735,30 +746,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
                         uint32_t mask = 0;
 #pragma unroll
                         for (int j = 0; j < 32; j++) mask |= (tv[j] <= P) ? (1u << j) : 0u;
-                        if (__popc(mask) >= (int)p.k) {
-                            // flood control (cold or very loose bound): the k-th smallest of these 32 values bounds
-                            // the row's k-th best, so tighten locally before anything is queued
-                            float lo_v = -kInf, kth = kInf;
-                            for (uint32_t i = 0; i < p.k; i++) {
-                                float nxt = kInf;
-#pragma unroll
-                                for (int j = 0; j < 32; j++) nxt = (tv[j] > lo_v) ? fminf(nxt, tv[j]) : nxt;
-                                int c = 0;
-#pragma unroll
-                                for (int j = 0; j < 32; j++) c += (tv[j] <= nxt) ? 1 : 0;
-                                kth = nxt;
-                                if (c >= (int)p.k) break;
-                                lo_v = nxt;
-                            }
-                            const float nP = kth + delta;
-                            if (nP < P) {
-                                P = nP;
-                                push(kEntValid | (1u << 31) | (uint32_t)row, P);
-                                mask = 0;
-#pragma unroll
-                                for (int j = 0; j < 32; j++) mask |= (tv[j] <= P) ? (1u << j) : 0u;
-                            }
-                        }
                         const uint32_t tl = t - t0;
                         while (mask) {
                             const int j = __ffs(mask) - 1;
@@ -766,7 +753,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
                             float v = tv[0];
 #pragma unroll
                             for (int jj = 1; jj < 32; jj++) v = (jj == j) ? tv[jj] : v;
-                            push(kEntValid | (tl << 14) | ((cb * 32u + (uint32_t)j) << 7) | (uint32_t)row, v);
+                            if (v <= P) {  // the bound may have shrunk since the mask was built
+                                push(kEntValid | (tl << 14) | ((cb * 32u + (uint32_t)j) << 7) | (uint32_t)row, v);
+                                // flood control (cold or very loose bound): the k-th smallest value this thread queued
+                                // in this item bounds the row's k-th best at once, without the selector's latency
+                                if (v < lr[0]) {
+                                    lr[0] = v;
+#pragma unroll
+                                    for (int i = 0; i + 1 < KR; i++) {
+                                        const float hi_v = fmaxf(lr[i], lr[i + 1]), lo_v = fminf(lr[i], lr[i + 1]);
+                                        lr[i] = hi_v;
+                                        lr[i + 1] = lo_v;
+                                    }
+                                    P = fminf(P, lr[0] + delta);
+                                }
+                            }
                         }
                     }
                 }
