@@ -192,16 +192,34 @@ void Index::build_lists(const float* d_data, uint64_t n, const uint32_t* labels,
     // per-list layout + row norms for the tensor-core scan
     {
 
-        d_vnorm.reserve((std::max<uint64_t>(nrows, 1) + 128) * 16);  // rows are whole supergroups: a tile copy reads 128 entries
-        VIDX_CUDA(cudaMemsetAsync(d_vnorm.p, 0xff, (std::max<uint64_t>(nrows, 1) + 128) * 16, stream));
-        DevBuf d_vntrue;
+        // fp16 shadow store of the tensor-core filter: vectors scaled by 2^sv so that the largest component
+        // lands in [2^6, 2^7); norm terms (1-eps)|v|^2 * 2^(2sv-g), g chosen so that they stay below 2^15
+        const int Dh = tc_dh((int)dim);
+        DevBuf d_vntrue, d_stats;
         d_vntrue.reserve(std::max<uint64_t>(nrows, 1) * 4);
-        launch_row_norms(d_vecs.as<float4>(), Dq, d_row_src.as<uint32_t>(), nrows, d_vnorm.as<float4>(), d_vntrue.as<float>(), stream);
+        d_stats.reserve(16);
+        VIDX_CUDA(cudaMemsetAsync(d_stats.p, 0, 16, stream));
+        launch_row_norms(d_vecs.as<float4>(), Dq, d_row_src.as<uint32_t>(), nrows, d_vntrue.as<float>(), d_stats.as<uint32_t>(), stream);
         std::vector<float> vt(nrows);
         d2h_sync(vt.data(), d_vntrue.as<float>(), nrows, stream);
+        uint32_t vmax_bits = 0;
+        d2h_sync(&vmax_bits, d_stats.as<uint32_t>(), 1, stream);
+        memcpy(&vmax, &vmax_bits, 4);
         vn_max = 0.0f;
         for (float v : vt)
             if (v > vn_max) vn_max = v;
+        int e = 0;
+        if (vmax > 0.0f) frexpf(vmax, &e);
+        tc_sv = vmax > 0.0f ? 7 - e : 0;
+        tc_g = 0;
+        while ((16 * (Dh / 2)) > (2 << tc_g)) tc_g++;  // g = ceil(log2(padded dimension)) - 1
+        tc_ok = std::isfinite(vmax) && std::isfinite(vn_max) && tc_sv > -40 && tc_sv < 40;
+        d_vecs16.reserve(tc_ok ? (std::max<uint64_t>(nrows, 1) * Dh * 16) : 16);
+        d_vnorm.reserve((std::max<uint64_t>(nrows, 1) + 128) * 16);  // rows are whole supergroups: a tile copy reads 128 entries
+        if (tc_ok)
+            launch_convert16(d_vecs.as<float4>(), Dq, Dh, d_row_src.as<uint32_t>(), nrows, d_vntrue.as<float>(), tc_sv, tc_g,
+                             d_vecs16.as<uint4>(), d_vnorm.as<uint4>(), stream);
+        VIDX_CUDA(cudaStreamSynchronize(stream));
     }
     part_rank = 0;
     part_world = 1;
@@ -314,7 +332,7 @@ struct Index::Workspace {
     DevBuf xq_pad, dist, probes, pair_ns, slot_off, seg_cnt, seg_qoff, seg_cur, seg_qlist, slot_seg, dense, sparse, counters,
         scan_tmp, cand_d, cand_r, alld, row_off, row_len, sel_pos, sel_val, rows, stats, slot_rank, list_cnt, list_cur, list_qoff,
         list_qlist, items_per_list, item_off, qnorm, gthr, cand_cnt, overflow, cand, list_cnt0, list_cur0, list_qoff0, list_qlist0,
-        items_per_list0, item_off0, gtop, glock;
+        items_per_list0, item_off0, gtop, glock, tcscale;
 };
 void Index::delete_workspace() {
     delete ws;
@@ -353,7 +371,7 @@ void Index::search_device(const float* d_xq, uint64_t nq, uint64_t k_req, uint64
     const bool fused = k <= 32;
     // tensor-core pre-filter + exact finalize whenever the shape allows; the exact kernels then
     // only see the queries it hands back (survivor buffer overflow)
-    const bool tc = fused && scan_mode != 1 && tc_supported(Dq, (uint32_t)k) && !coarse_only;
+    const bool tc = fused && scan_mode != 1 && tc_ok && tc_supported((int)dim, (uint32_t)k) && !coarse_only;
     const uint32_t nseg = (uint32_t)segs.size();
     const uint32_t ldc = ncgroups * kGroup;
     // pairs bound per query: the np largest per-list segment counts
@@ -456,8 +474,12 @@ void Index::search_device(const float* d_xq, uint64_t nq, uint64_t k_req, uint64
             w.item_off.reserve(((size_t)nlist + 1) * 4);
             w.gtop.reserve((size_t)nqb * k * 4);
             w.glock.reserve((size_t)nqb * 8);  // locks, then seqlock versions
+            w.tcscale.reserve(64);  // [0..15] query stats, [16..] TcScale
+            VIDX_CUDA(cudaMemsetAsync(w.tcscale.p, 0, 64, st));
             launch_query_norms(xq4, Dq, nqb, (uint32_t)k, w.qnorm.as<float>(), w.gthr.as<uint32_t>(), w.cand_cnt.as<uint32_t>(),
-                               w.overflow.as<uint32_t>(), w.gtop.as<float>(), w.glock.as<uint32_t>(), st);
+                               w.overflow.as<uint32_t>(), w.gtop.as<float>(), w.glock.as<uint32_t>(), w.tcscale.as<uint32_t>(), st);
+            launch_tc_scale(w.tcscale.as<uint32_t>(), tc_sv, tc_g, (int)dim, vmax, vn_max,
+                            reinterpret_cast<TcScale*>(w.tcscale.as<unsigned char>() + 16), st);
             VIDX_CUDA(cudaMemsetAsync(w.list_cur.p, 0, ((size_t)nlist + 1) * 4, st));
             exclusive_scan_u32(w.list_cnt.as<uint32_t>(), w.list_qoff.as<uint32_t>(), nlist, w.scan_tmp.as<uint32_t>(), st);
             launch_tc_fill(w.probes.as<uint32_t>(), npairs, np, false, d_list_seg.as<uint2>(), w.list_qoff.as<uint32_t>(),
@@ -485,9 +507,12 @@ void Index::search_device(const float* d_xq, uint64_t nq, uint64_t k_req, uint64
         if (profiling) VIDX_CUDA(cudaEventRecord(ev[3], st));
         if (tc) {
             TcParams tp{};
-            tp.vecs = d_vecs.as<float4>();
-            tp.vnorm = d_vnorm.as<float4>();
+            tp.vecs16 = d_vecs16.as<uint4>();
+            tp.vnorm = d_vnorm.as<uint4>();
+            tp.Dh = tc_dh((int)dim);
             tp.Dq = Dq;
+            tp.scale = reinterpret_cast<const TcScale*>(w.tcscale.as<unsigned char>() + 16);
+            tp.nq = nqb;
             tp.xq4 = xq4;
             tp.qnorm = w.qnorm.as<float>();
             tp.list_g0 = d_list_g0.as<uint32_t>();
@@ -636,7 +661,7 @@ void Index::search_device(const float* d_xq, uint64_t nq, uint64_t k_req, uint64
                     stats.n_tc_survivors += cc[i];
                     stats.n_tc_overflow += of[i] ? 1 : 0;
                 }
-                stats.tc_mma_flops += h[1] * 2ull * Dp;
+                stats.tc_mma_flops += h[1] * 2ull * 8 * tc_dh((int)dim);
             }
         }
     }

@@ -51,8 +51,11 @@ struct Index {
     cudaStream_t stream = nullptr;
     cudaEvent_t events[10] = {};
     uint32_t ncgroups = 0;
-    DevBuf d_vecs, d_cents, d_row_ext, d_segs, d_list_seg, d_list_g0, d_list_ng, d_list_len, d_vnorm;
+    DevBuf d_vecs, d_cents, d_row_ext, d_segs, d_list_seg, d_list_g0, d_list_ng, d_list_len, d_vnorm, d_vecs16;
     float vn_max = 0.0f;   // max |v|^2 over the stored rows (bound for the tensor-core filter)
+    float vmax = 0.0f;     // max |component| over the stored rows
+    int tc_sv = 0, tc_g = 0;  // fp16 shadow store: vectors scaled by 2^sv, norm terms by 2^(2sv-g)
+    bool tc_ok = false;    // the shadow store exists (finite data of sane magnitude)
     int scan_mode = 0;     // 0 = tensor-core pre-filter when the shape allows, 1 = exact kernels only
     DevBuf io_xq, io_D, io_I, io_rows, io_V;
     struct Workspace;

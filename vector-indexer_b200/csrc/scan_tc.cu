@@ -1,36 +1,44 @@
-// scan_tc.cu -- tensor-core list scan for sm_100a: tcgen05 TF32 pre-filter + exact re-check.
+// scan_tc.cu -- tensor-core list scan for sm_100a: tcgen05 FP16 pre-filter + exact re-check.
 //
 // The inverted-list scan (src/ivf_index.rs:252-266) is, for a batch of queries grouped by
 // probed list, the contraction  dot[q][v] = sum_d q[d]*v[d]  followed by a top-k.  The
 // reference's distance is fp32 and results must be bit-exact, so the tensor cores are used
 // as a FILTER only:
 //
-//   L(q,v) = (1-eps)*(|q|^2 + |v|^2) - 2*dot_tf32(q,v)      is a guaranteed LOWER bound of
-//   the reference distance (eps covers TF32 operand truncation, 2^-9*|q||v| <=
-//   2^-10(|q|^2+|v|^2), plus every fp32 rounding involved).
+//   L(q,v) = (1-eps)*(|q|^2 + |v|^2) - c_abs - 2*dot_fp16(q,v)    is a guaranteed LOWER bound of
+//   the reference distance: operands are rounded to fp16 (11 significant bits, |error| <= 2^-11
+//   relative after a power-of-two scaling that keeps every component far inside fp16 range), so
+//   |2 dot - 2 dot_fp16| <= 2^-10 |q||v| <= 2^-11 (|q|^2+|v|^2) plus c_abs for components that fall into the
+//   fp16 subnormal range; eps = 1.5e-3 also covers every fp32 rounding involved.
 //
 //   A candidate survives iff L <= U, where U is an UPPER bound of the query's exact k-th best
-//   distance: the k-th smallest L seen so far plus 2*eps*(|q|^2 + max|v|^2), or a bound
+//   distance: the k-th smallest L seen so far plus 2*eps*(|q|^2 + max|v|^2) + 2*c_abs, or a bound
 //   published by another CTA for the same query.  Every true top-k member survives.
 //
-//   Survivors (a few hundred per query) get the reference's exact sequential fp32 distance in
+//   Survivors (a hundred or two per query) get the reference's exact sequential fp32 distance in
 //   finalize_kernel, which then selects the top-k by (distance, probe rank, row) -- the same
 //   keys the exact scan kernels order by.  The final answer is bit-identical to the exact path.
 //
-// Kernel anatomy (one CTA per SM, persistent, 6 warps):
-//   warp 0  producer : one cp.async.bulk (1-D TMA, 16 KB) per K-slice of a 128-vector tile -- the
-//                      HBM layout keeps chunk c of a supergroup's 128 vectors contiguous, so a
-//                      slice is a single contiguous run -- into an 8-deep shared-memory ring, plus
-//                      the tile's 128 scaled norms; completion on mbarriers (complete_tx::bytes)
-//   warp 1  MMA      : one elected thread issues tcgen05.mma.cta_group::1.kind::tf32, M=128
-//                      queries x N=128 vectors x K=8 per instruction; operands are read from shared
-//                      memory through no-swizzle K-major descriptors: that chunk-major layout IS
-//                      the UMMA core-matrix layout (8 rows x 16 B contiguous, SBO = 128 B,
-//                      LBO = 2048 B), for the query tile and the list tile alike
-//   warps 2-9 epilogue: tcgen05.ld the 128x128 fp32 accumulator tile from TMEM (double buffered,
-//                      256 columns); two warps per TMEM lane quarter, each thread owns one query row
-//                      and 64 of the 128 columns: 1 FFMA + 1 min per element, one branch per 32
+// The index keeps an fp16 SHADOW of the vectors for this filter (same supergroup layout, 8 dims per 16-byte
+// chunk); the fp32 store stays the source of every distance that is returned.
+//
+// Kernel anatomy (one CTA per SM, persistent, 13 warps; a work item = 128 queries x up to 128 list tiles):
+//   warps 0, 12 producers : one cp.async.bulk (1-D TMA) per K-slice of a 128-vector tile -- the HBM layout keeps
+//                      a tile's chunks contiguous, so a list chunk is ONE linear stream -- into a ring of 32 KB
+//                      stages, plus the tile's norm terms; completion on mbarriers (complete_tx::bytes)
+//   warps 1, 10 MMA  : one elected thread issues tcgen05.mma.cta_group::1.kind::f16, M=128 queries x N=128
+//                      vectors x K=16 per instruction; operands are read from shared memory through no-swizzle
+//                      K-major descriptors: the chunk-major layout IS the UMMA core-matrix layout (8 rows x 16 B
+//                      contiguous, SBO = 128 B, LBO = 2048 B).  A last K-step multiplies (a,a,a,0..) by the
+//                      three fp16 terms of the row norm, so the accumulator holds the filter value itself.
+//                      Two independent pipelines (producer + issuer + half of the ring) alternate tiles.
+//   warps 2-9 epilogue: tcgen05.ld the 128x128 fp32 accumulator tile from TMEM (4 stages, 512 columns); two warps
+//                      per TMEM lane quarter, each thread owns one query row and 64 of the 128 columns: one 3-input
+//                      min per three columns, one branch per 32; hits go to a shared-memory queue
+//   warp 11 selector : owns the per-row top-k sets and bounds, appends survivors to the per-query lists
 // Accumulators never leave the SM; HBM sees each list tile once per 128-query tile.
+#include <cuda_fp16.h>
+
 #include "scan_tc.h"
 
 namespace vidx {
@@ -48,10 +56,10 @@ __host__ __device__ constexpr int tc_queue_cap(int kr) { return kr > 16 ? 128 : 
 __host__ __device__ constexpr int tc_stage_cap(int kr) { return kr > 16 ? 128 : 256; }
 constexpr int kTcAccStages = 4;      // accumulator tiles in TMEM
 constexpr int kTcTmemCols = 512;     // 4 accumulator stages x 128 columns
-constexpr int kTcStages = 4;         // shared-memory ring: stages of 128 vectors x 64 dims (32 KB), two per tile pipeline
-constexpr int kTcStageChunks = 16;   // 16-byte chunks (4 floats) of every vector per stage
+constexpr int kTcStages = 4;         // shared-memory ring: stages of 128 vectors x 128 dims of fp16 (32 KB), two per tile pipeline
+constexpr int kTcStageChunks = 16;   // 16-byte chunks (8 halfs) of every vector per stage
 constexpr uint32_t kTcStageBytes = kTcStageChunks * kTcTileGroups * 512;
-constexpr float kTcEps = 2.5e-3f;    // see header comment; needed: ~1.99e-3
+constexpr float kTcEps = 1.5e-3f;    // see header comment; needed: ~1.03e-3
 
 // ---- PTX wrappers ------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -109,21 +117,11 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// D[tmem] (+)= A[smem] * B[smem]^T, TF32 inputs, FP32 accumulate.
-__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(tmem_d),
-        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// Same, with the two descriptors given as 32-bit halves: only the 14-bit start-address field of the
-// low word differs between the MMAs of a tile, so the issuing thread does one IADD per descriptor.
+// D[tmem] (+)= A[smem] * B[smem]^T, FP16 inputs, FP32 accumulate.  The two descriptors are given as 32-bit
+// halves: only the 14-bit start-address field of the low word differs between the MMAs of a tile, so the
+// issuing thread does one add per descriptor.
 template <bool ACC>
-__device__ __forceinline__ void tc_mma_tf32_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc) {
+__device__ __forceinline__ void tc_mma_f16_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc) {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
@@ -131,7 +129,7 @@ __device__ __forceinline__ void tc_mma_tf32_lo(uint32_t tmem_d, uint32_t a_lo, u
         "setp.ne.b32 p, %5, 0;\n\t"
         "mov.b64 da, {%1, %3};\n\t"
         "mov.b64 db, {%2, %3};\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, p;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t"
         "}" ::"r"(tmem_d),
         "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "n"(ACC ? 1 : 0)
         : "memory");
@@ -184,57 +182,132 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
     return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16) |
            ((uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32) | (1ull << 46);
 }
-// Instruction descriptor: D = F32 (bits 4-5 = 1), A = B = TF32 (2 at bits 7-9 / 10-12), both K-major,
+// Instruction descriptor: D = F32 (bits 4-5 = 1), A = B = F16 (0 at bits 7-9 / 10-12), both K-major,
 // N >> 3 at bits 17-22, M >> 4 at bits 24-28.
-__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+    return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 // ------------------------------------------------------------------------------------------
-// norms
+// norms, scales and the fp16 shadow store
 // ------------------------------------------------------------------------------------------
-// Per stored row: n = (1-eps)*|v|^2 split into three TF32-exact terms (n_hi + n_mid + n_lo == n exactly), the
-// B operand of the norm step of the tensor-core scan; NaN for padding rows (NaN never passes a '<=' test).
-__device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+int tc_dh(int D) { return 2 * ((D + 15) / 16); }
+
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+// |v|^2 per stored row and the largest |component| of the store.
 __global__ void row_norm_kernel(const float4* __restrict__ vecs, int Dq, const uint32_t* __restrict__ row_src, size_t nrows,
-                                float4* __restrict__ vn3, float* __restrict__ vn_true) {
+                                float* __restrict__ vn_true, uint32_t* __restrict__ stats) {
     size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= nrows) return;
-    if (row_src[row] == kNoRow) {
-        vn3[row] = make_float4(__int_as_float(0x7fc00000), 0.0f, 0.0f, 0.0f);
-        vn_true[row] = 0.0f;
-        return;
+    float s = 0.0f, m = 0.0f;
+    if (row < nrows && row_src[row] != kNoRow) {
+        const float4* p = vecs + f4_row_base(row, Dq);
+        for (int c = 0; c < Dq; c++) {
+            float4 v = p[(size_t)c * kSuper];
+            s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+            m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+        }
     }
+    if (row < nrows) vn_true[row] = s;
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(kFull, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax(&stats[0], __float_as_uint(m));
+}
+// Shadow store: chunk c of a row = dims 8c..8c+7 as fp16 (round to nearest) of v * 2^sv, zero beyond the dimension.
+// Norm terms: b = (1-eps)|v|^2 * 2^(2sv-g) as three fp16 values rounded DOWN (hi + mid + lo <= b, so the filter
+// value can only get smaller); NaN for padding rows (NaN never passes a '<=' test).
+__global__ void convert16_kernel(const float4* __restrict__ vecs, int Dq, int Dh, const uint32_t* __restrict__ row_src, size_t nrows,
+                                 const float* __restrict__ vn_true, float vscale, float nscale, uint4* __restrict__ vecs16,
+                                 uint4* __restrict__ vnorm) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // (row, chunk), row fastest: coalesced on both sides
+    size_t row = i % nrows;
+    int c = (int)(i / nrows);
+    if (c >= Dh) return;
+    const bool pad = row_src[row] == kNoRow;
     const float4* p = vecs + f4_row_base(row, Dq);
-    float s = 0.0f;
-    for (int c = 0; c < Dq; c++) {
-        float4 v = p[(size_t)c * kSuper];
-        s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    float4 a = make_float4(0, 0, 0, 0), b = a;
+    if (!pad && 2 * c < Dq) a = p[(size_t)(2 * c) * kSuper];
+    if (!pad && 2 * c + 1 < Dq) b = p[(size_t)(2 * c + 1) * kSuper];
+    uint4 o;
+    o.x = pack_h2(a.x * vscale, a.y * vscale);
+    o.y = pack_h2(a.z * vscale, a.w * vscale);
+    o.z = pack_h2(b.x * vscale, b.y * vscale);
+    o.w = pack_h2(b.z * vscale, b.w * vscale);
+    vecs16[((row >> 7) * (size_t)Dh + c) * kSuper + (row & 127)] = o;
+    if (c == 0) {
+        uint4 n = make_uint4(0, 0, 0, 0);
+        if (pad) {
+            n.x = 0x7e00u;  // fp16 NaN in the hi term
+        } else {
+            const float bv = (1.0f - kTcEps) * vn_true[row] * nscale;
+            const __half hi = __float2half_rd(bv);
+            const float r1 = bv - __half2float(hi);
+            const __half mid = __float2half_rd(r1);
+            const float r2 = r1 - __half2float(mid);
+            const __half lo = __float2half_rd(r2);
+            n.x = (uint32_t)__half_as_ushort(hi) | ((uint32_t)__half_as_ushort(mid) << 16);
+            n.y = (uint32_t)__half_as_ushort(lo);
+        }
+        vnorm[row] = n;
     }
-    vn_true[row] = s;
-    const float n = (1.0f - kTcEps) * s;
-    const float hi = tf32_trunc(n);
-    const float r1 = n - hi;          // exact
-    const float mid = tf32_trunc(r1);
-    vn3[row] = make_float4(hi, mid, r1 - mid, 0.0f);
 }
 __global__ void query_norm_kernel(const float4* __restrict__ xq4, int Dq, uint32_t nq, uint32_t k, float* __restrict__ qn,
                                   uint32_t* __restrict__ gthr_bits, uint32_t* __restrict__ cand_cnt, uint32_t* __restrict__ overflow,
-                                  float* __restrict__ gtop, uint32_t* __restrict__ glock) {
+                                  float* __restrict__ gtop, uint32_t* __restrict__ glock, uint32_t* __restrict__ stats) {
     uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= nq) return;
-    float s = 0.0f;
-    for (int c = 0; c < Dq; c++) {
-        float4 v = xq4[(size_t)q * Dq + c];
-        s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    float s = 0.0f, m = 0.0f;
+    if (q < nq) {
+        for (int c = 0; c < Dq; c++) {
+            float4 v = xq4[(size_t)q * Dq + c];
+            s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+            m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+        }
+        qn[q] = s;
+        gthr_bits[q] = 0x7f800000u;  // +inf
+        cand_cnt[q] = 0;
+        overflow[q] = 0;
+        glock[q] = 0;
+        glock[nq + q] = 0;  // seqlock version of gtop
+        for (uint32_t i = 0; i < k; i++) gtop[(size_t)q * k + i] = __int_as_float(0x7f800000);
     }
-    qn[q] = s;
-    gthr_bits[q] = 0x7f800000u;  // +inf
-    cand_cnt[q] = 0;
-    overflow[q] = 0;
-    glock[q] = 0;
-    glock[nq + q] = 0;  // seqlock version of gtop
-    for (uint32_t i = 0; i < k; i++) gtop[(size_t)q * k + i] = __int_as_float(0x7f800000);
+    float sm = s;
+    for (int o = 16; o; o >>= 1) {
+        m = fmaxf(m, __shfl_xor_sync(kFull, m, o));
+        sm = fmaxf(sm, __shfl_xor_sync(kFull, sm, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (m > 0.0f) atomicMax(&stats[0], __float_as_uint(m));
+        if (sm > 0.0f) atomicMax(&stats[1], __float_as_uint(sm));
+    }
+}
+// The batch's query scale: largest |2q component| * 2^sq in [2^6, 2^7), moved if the norm partner a = 2^(sq-sv+g)
+// would leave fp16's normal range.
+__global__ void tc_scale_kernel(const uint32_t* __restrict__ qstats, int sv, int g, int D, float vmax, float vn_max,
+                                TcScale* __restrict__ out) {
+    const float qmax2 = 2.0f * __uint_as_float(qstats[0]);
+    const float qn_max = __uint_as_float(qstats[1]);
+    int e = 0;
+    if (qmax2 > 0.0f) frexpf(qmax2, &e);  // qmax2 = m * 2^e, m in [0.5, 1)
+    int sq = qmax2 > 0.0f ? 7 - e : 0;
+    bool ok = isfinite(qmax2) && isfinite(qn_max);
+    int ea = sq - sv + g;
+    if (ea > 15) { sq -= ea - 15; ea = 15; }            // smaller query scale: always safe (precision only)
+    if (ea < -14) {
+        const int up = -14 - ea;                          // larger query scale: must stay below fp16 overflow
+        if (up <= 8) { sq += up; ea = -14; } else ok = false;
+    }
+    if (sq > 100 || sq < -100) ok = false;
+    TcScale t;
+    t.S = ok ? ldexpf(1.0f, sq + sv) : 1.0f;
+    t.invS = ok ? ldexpf(1.0f, -(sq + sv)) : 1.0f;
+    t.qmul = ok ? -ldexpf(1.0f, sq + 1) : 0.0f;
+    t.a_ones = ok ? ldexpf(1.0f, ea) : 0.0f;
+    // components below fp16's normal range carry an absolute error of at most 2^-25 (scaled); see the header
+    t.c_abs = ok ? sqrtf((float)D) * (ldexpf(1.0f, -25 - sq) * sqrtf(vn_max) * 2.0f + ldexpf(1.0f, -24 - sv) * sqrtf(qn_max)) : 0.0f;
+    t.ok = ok ? 1u : 0u;
+    *out = t;
+    (void)vmax;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -306,10 +379,10 @@ struct TcSmemLayout {
     uint32_t a_bytes, off_b, off_norm, off_ones, off_zero, off_r, off_queue, off_stage, off_q, off_row, off_bar, off_misc, total;
     uint32_t stages;
 };
-__host__ __device__ inline TcSmemLayout tc_smem_layout(int Dq, int kr) {
+__host__ __device__ inline TcSmemLayout tc_smem_layout(int Dh, int kr) {
     TcSmemLayout L;
     L.stages = kTcStages;
-    L.a_bytes = (uint32_t)Dq * kTcM * 16;                   // query tile, [chunk][128 rows][16 B]
+    L.a_bytes = (uint32_t)Dh * kTcM * 16;                   // query tile, [chunk][128 rows][16 B = 8 halfs]
     L.off_b = L.a_bytes;                                    // ring of list-tile K-slices
     L.off_norm = L.off_b + L.stages * kTcStageBytes;        // per accumulator stage: norm chunk [128 rows][16 B]
     L.off_ones = L.off_norm + kTcAccStages * 2048;          // A-side partner of the norm chunk: (1,1,1,0) per row
@@ -360,7 +433,7 @@ constexpr uint32_t kEntValid = 0x40000000u;
 template <int KR>
 __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    const TcSmemLayout L = tc_smem_layout(p.Dq, KR);
+    const TcSmemLayout L = tc_smem_layout(p.Dh, KR);
     unsigned char* sA = smem;
     unsigned char* sB = smem + L.off_b;
     unsigned char* sNorm = smem + L.off_norm;
@@ -385,7 +458,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(kFull, tid >> 5, 0);  // warp-uniform for the compiler too
-    const int Dq = p.Dq;
+    const int Dq = p.Dq, Dh = p.Dh;
+    // the batch's scales (uniform loads); a batch that cannot be scaled into fp16 range goes to the exact kernels
+    const float tS = p.scale->S, tInvS = p.scale->invS, tQmul = p.scale->qmul, tCabs = p.scale->c_abs;
+    if (!p.scale->ok) {
+        for (uint32_t q = blockIdx.x * kTcThreads + tid; q < p.nq; q += gridDim.x * kTcThreads) p.overflow[q] = 1u;
+        return;
+    }
     if (tid == 0) {
         for (uint32_t i = 0; i < nstages; i++) {
             mbar_init(&bar_full[i], 1);
@@ -399,8 +478,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
     }
     // constant operands of the norm step and an empty queue
     for (int i = tid; i < 128; i += kTcThreads) {
-        reinterpret_cast<float4*>(smem + L.off_ones)[i] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
-        reinterpret_cast<float4*>(smem + L.off_zero)[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        const float a = p.scale->a_ones;  // (a, a, a, 0, 0, 0, 0, 0) per row, as fp16
+        reinterpret_cast<uint4*>(smem + L.off_ones)[i] = make_uint4(pack_h2(a, a), pack_h2(a, 0.0f), 0u, 0u);
+        reinterpret_cast<uint4*>(smem + L.off_zero)[i] = make_uint4(0u, 0u, 0u, 0u);
     }
     for (int i = tid; i < kTcQueueCap; i += kTcThreads) s_queue[i] = make_uint2(0u, 0u);
     if (warp == 1) {
@@ -413,9 +493,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
     tc_fence_after();
     const uint32_t tmem_base = s_misc[0];
     const uint32_t total_items = p.item_off[p.nlist];
-    const uint32_t idesc = make_idesc_tf32(kTcM, kTcTileGroups * 32);
+    const uint32_t idesc = make_idesc_f16(kTcM, kTcTileGroups * 32);
     const uint32_t chunk_tiles = *p.chunk_tiles;
-    const int nkc = (Dq + kTcStageChunks - 1) / kTcStageChunks;  // K-slices per tile
+    const int nkc = (Dh + kTcStageChunks - 1) / kTcStageChunks;  // K-slices per tile
     const float kInf = __int_as_float(0x7f800000);
     uint32_t it = 0;     // tiles processed so far by this CTA (accumulator stage = it & 3, phase = (it >> 2) & 1)
     // Two independent tile pipelines, each with its own producer warp, MMA warp and half of the ring: pipeline 0
@@ -461,10 +541,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
             if (qi.x != kNoRow) {
                 const uint32_t q = qi.x;
                 const float qn = p.qnorm[q];
-                base_t = (1.0f - kTcEps) * qn;
-                delta = 2.0f * kTcEps * (qn + p.vn_max);
+                // base_t in real units; delta, the set and P in accumulator units (x S, a power of two)
+                base_t = (1.0f - kTcEps) * qn - tCabs;
+                delta = (2.0f * kTcEps * (qn + p.vn_max) + 2.0f * tCabs) * tS;
                 const float g = __uint_as_float(__ldcg(&p.gthr_bits[q]));
-                const float tau_g = (g - base_t) + 1e-5f * (g + base_t);
+                const float tau_g = ((g - base_t) + 1e-5f * (g + fabsf(base_t))) * tS;
                 // seqlock read: writers make the version odd while they update the set
                 const volatile uint32_t* ver = p.gver + q;
                 float r0 = kInf;
@@ -488,23 +569,31 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
             s_impr[tid] = 0;
         }
         __syncthreads();
-        // A tile = -2 * queries: [c][128 rows][16 B] (core matrices of 8 rows x 16 B, SBO 128 B, LBO 2048 B)
-        for (int base = 0; base < Dq * kTcM; base += kTcThreads * 8) {
-            float4 v[8];
+        // A tile = fp16(-2 * 2^sq * queries): [chunk of 8 dims][128 rows][16 B] (core matrices of 8 rows x 16 B,
+        // SBO 128 B, LBO 2048 B); dimensions beyond the query's are zero
+        for (int base = 0; base < Dh * kTcM; base += kTcThreads * 4) {
+            float4 va[4], vb[4];
 #pragma unroll
-            for (int u = 0; u < 8; u++) {  // issue the gathers first, then store: 8 loads in flight per thread
-                int idx = base + u * kTcThreads + tid;
-                v[u] = make_float4(0, 0, 0, 0);
-                if (idx < Dq * kTcM) {
-                    uint32_t q = s_q[idx & 127].x;
-                    if (q != kNoRow) v[u] = __ldg(&p.xq4[(size_t)q * Dq + (idx >> 7)]);
+            for (int u = 0; u < 4; u++) {  // issue the gathers first, then store: 8 loads in flight per thread
+                const int idx = base + u * kTcThreads + tid;
+                va[u] = make_float4(0, 0, 0, 0);
+                vb[u] = va[u];
+                if (idx < Dh * kTcM) {
+                    const uint32_t q = s_q[idx & 127].x;
+                    const int c = idx >> 7;
+                    if (q != kNoRow) {
+                        if (2 * c < Dq) va[u] = __ldg(&p.xq4[(size_t)q * Dq + 2 * c]);
+                        if (2 * c + 1 < Dq) vb[u] = __ldg(&p.xq4[(size_t)q * Dq + 2 * c + 1]);
+                    }
                 }
             }
 #pragma unroll
-            for (int u = 0; u < 8; u++) {
-                int idx = base + u * kTcThreads + tid;
-                if (idx < Dq * kTcM)
-                    reinterpret_cast<float4*>(sA)[idx] = make_float4(-2.0f * v[u].x, -2.0f * v[u].y, -2.0f * v[u].z, -2.0f * v[u].w);
+            for (int u = 0; u < 4; u++) {
+                const int idx = base + u * kTcThreads + tid;
+                if (idx < Dh * kTcM)
+                    reinterpret_cast<uint4*>(sA)[idx] =
+                        make_uint4(pack_h2(tQmul * va[u].x, tQmul * va[u].y), pack_h2(tQmul * va[u].z, tQmul * va[u].w),
+                                   pack_h2(tQmul * vb[u].x, tQmul * vb[u].y), pack_h2(tQmul * vb[u].z, tQmul * vb[u].w));
             }
         }
         fence_proxy_async();
@@ -515,15 +604,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
             // (warp-uniform values), one elected lane issues.  A list chunk is one linear stream in HBM (tiles and
             // their K-slices are consecutive), so the source just advances. =====
             const uint32_t pipe = warp == 0 ? 0u : 1u;
-            const uint32_t tile_bytes = (uint32_t)Dq * kSuper * 16;
-            const unsigned char* src = reinterpret_cast<const unsigned char*>(p.vecs) + ((size_t)(g_list >> 2) + t0) * tile_bytes;
-            const float4* nsrc = p.vnorm + ((size_t)g_list + (size_t)t0 * kTcTileGroups) * 32;
+            const uint32_t tile_bytes = (uint32_t)Dh * kSuper * 16;
+            const unsigned char* src = reinterpret_cast<const unsigned char*>(p.vecs16) + ((size_t)(g_list >> 2) + t0) * tile_bytes;
+            const uint4* nsrc = p.vnorm + ((size_t)g_list + (size_t)t0 * kTcTileGroups) * 32;
             for (uint32_t t = t0; t < t1; t++, it++, nsrc += kSuper, src += tile_bytes) {
                 if ((it & 1u) != pipe) continue;
                 const uint32_t a = it & (kTcAccStages - 1), aph = (it / kTcAccStages) & 1;
                 const unsigned char* ssrc = src;
                 for (int kc = 0; kc < nkc; kc++, ks_it++) {
-                    const uint32_t nch = (uint32_t)min(kTcStageChunks, Dq - kc * kTcStageChunks);
+                    const uint32_t nch = (uint32_t)min(kTcStageChunks, Dh - kc * kTcStageChunks);
                     const uint32_t bytes = nch * kSuper * 16;
                     const uint32_t s = 2 * pipe + (ks_it & 1u), ph = (ks_it >> 1) & 1;
                     mbar_wait(&bar_empty[s], ph ^ 1);
@@ -563,16 +652,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
                         // chunk c of all 128 rows is one 2 KB block (128 x 16 B) in both tiles: +128 per chunk in >>4 units
                         const uint32_t al = a_lo0 + (uint32_t)kc * (kTcStageChunks * 128);
                         const uint32_t bl = b_lo0 + s * (kTcStageBytes >> 4);
-                        const int nks = min(kTcStageChunks / 2, (Dq >> 1) - kc * (kTcStageChunks / 2));
+                        const int nks = min(kTcStageChunks / 2, (Dh >> 1) - kc * (kTcStageChunks / 2));
                         const uint32_t noff = L.off_norm + a * 2048;
                         const uint32_t norm_lo = ((smem_u32(smem + noff) >> 4) & 0x3fffu) | (((L.off_zero - noff) >> 4) << 16);
                         if (elect_one()) {
-                            if (kc == 0) tc_mma_tf32_lo<false>(d_tmem, al, bl, desc_hi, idesc);
-                            else tc_mma_tf32_lo<true>(d_tmem, al, bl, desc_hi, idesc);
+                            if (kc == 0) tc_mma_f16_lo<false>(d_tmem, al, bl, desc_hi, idesc);
+                            else tc_mma_f16_lo<true>(d_tmem, al, bl, desc_hi, idesc);
 #pragma unroll
                             for (int ks = 1; ks < kTcStageChunks / 2; ks++)
-                                if (ks < nks) tc_mma_tf32_lo<true>(d_tmem, al + ks * 256, bl + ks * 256, desc_hi, idesc);
-                            if (kc == nkc - 1) tc_mma_tf32_lo<true>(d_tmem, ones_lo, norm_lo, desc_hi, idesc);
+                                if (ks < nks) tc_mma_f16_lo<true>(d_tmem, al + ks * 256, bl + ks * 256, desc_hi, idesc);
+                            if (kc == nkc - 1) tc_mma_f16_lo<true>(d_tmem, ones_lo, norm_lo, desc_hi, idesc);
                             tc_commit(&bar_empty[s]);                       // K-slice free once these MMAs have read it
                             if (kc == nkc - 1) tc_commit(&bar_tfull[a]);    // accumulator tile ready for the epilogue
                         }
@@ -623,7 +712,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
                 if (q != kNoRow) {
                     const float g = __uint_as_float(__ldcg(&p.gthr_bits[q]));
                     const float b = s_base[rr];
-                    const float tau = (g - b) + 1e-5f * (g + b);
+                    const float tau = ((g - b) + 1e-5f * (g + fabsf(b))) * tS;
                     if (tau < vP[rr]) vP[rr] = tau;
                 }
             };
@@ -689,7 +778,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
                                 const float newP = g[0] + s_delta[row];
                                 if (newP < vP[row]) {
                                     vP[row] = newP;
-                                    float U = fmaxf(newP + s_base[row], 0.0f);
+                                    float U = fmaxf(newP * tInvS + s_base[row], 0.0f);
                                     U = U + 1e-5f * U;
                                     atomicMin(&p.gthr_bits[s_q[row].x], __float_as_uint(U));
                                 }
@@ -834,7 +923,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
                     __threadfence();
                     atomicAdd(p.gver + q, 1u);  // even: consistent again
                     if (g[0] < kInf) {
-                        float U = fmaxf(g[0] + base_t + delta, 0.0f);
+                        float U = fmaxf((g[0] + delta) * tInvS + base_t, 0.0f);
                         U = U + 1e-5f * U;
                         atomicMin(&p.gthr_bits[q], __float_as_uint(U));
                     }
@@ -955,21 +1044,31 @@ __global__ void finalize_kernel(FinalizeParams p) {
 // ====================================================================================
 // launchers
 // ====================================================================================
-bool tc_supported(int Dq, uint32_t k) {
-    if (k == 0 || k > 32) return false;
-    if (Dq < 2 || (Dq & 1)) return false;  // K = 8 floats per MMA = two 16-byte chunks
-    return tc_smem_layout(Dq, k <= 8 ? 8 : (k <= 16 ? 16 : 32)).total <= 227 * 1024;
+bool tc_supported(int D, uint32_t k) {
+    if (k == 0 || k > 32 || D < 1) return false;
+    return tc_smem_layout(tc_dh(D), k <= 8 ? 8 : (k <= 16 ? 16 : 32)).total <= 227 * 1024;
 }
-void launch_row_norms(const float4* vecs, int Dq, const uint32_t* row_src, size_t nrows, float4* vn3, float* vn_true,
+void launch_row_norms(const float4* vecs, int Dq, const uint32_t* row_src, size_t nrows, float* vn_true, uint32_t* stats,
                       cudaStream_t st) {
     if (!nrows) return;
-    row_norm_kernel<<<(unsigned)ceil_div(nrows, 256), 256, 0, st>>>(vecs, Dq, row_src, nrows, vn3, vn_true);
+    row_norm_kernel<<<(unsigned)ceil_div(nrows, 256), 256, 0, st>>>(vecs, Dq, row_src, nrows, vn_true, stats);
+    VIDX_LAUNCHED();
+}
+void launch_convert16(const float4* vecs, int Dq, int Dh, const uint32_t* row_src, size_t nrows, const float* vn_true, int sv, int g,
+                      uint4* vecs16, uint4* vnorm, cudaStream_t st) {
+    if (!nrows) return;
+    convert16_kernel<<<(unsigned)ceil_div(nrows * (size_t)Dh, 256), 256, 0, st>>>(vecs, Dq, Dh, row_src, nrows, vn_true, ldexpf(1.0f, sv),
+                                                                                ldexpf(1.0f, 2 * sv - g), vecs16, vnorm);
     VIDX_LAUNCHED();
 }
 void launch_query_norms(const float4* xq4, int Dq, uint32_t nq, uint32_t k, float* qn, uint32_t* gthr_bits, uint32_t* cand_cnt,
-                        uint32_t* overflow, float* gtop, uint32_t* glock, cudaStream_t st) {
+                        uint32_t* overflow, float* gtop, uint32_t* glock, uint32_t* stats, cudaStream_t st) {
     if (!nq) return;
-    query_norm_kernel<<<(unsigned)ceil_div(nq, 128), 128, 0, st>>>(xq4, Dq, nq, k, qn, gthr_bits, cand_cnt, overflow, gtop, glock);
+    query_norm_kernel<<<(unsigned)ceil_div(nq, 128), 128, 0, st>>>(xq4, Dq, nq, k, qn, gthr_bits, cand_cnt, overflow, gtop, glock, stats);
+    VIDX_LAUNCHED();
+}
+void launch_tc_scale(const uint32_t* qstats, int sv, int g, int D, float vmax, float vn_max, TcScale* out, cudaStream_t st) {
+    tc_scale_kernel<<<1, 1, 0, st>>>(qstats, sv, g, D, vmax, vn_max, out);
     VIDX_LAUNCHED();
 }
 void launch_tc_count(const uint32_t* probes, size_t npairs, uint32_t nprobe, bool rank0_only, const uint2* list_seg,
@@ -1016,9 +1115,9 @@ static void launch_scan_tc_kr(const TcParams& p, size_t smem, cudaStream_t st) {
     VIDX_LAUNCHED();
 }
 void launch_scan_tc(const TcParams& p, cudaStream_t st) {
-    if (p.k <= 8) launch_scan_tc_kr<8>(p, tc_smem_layout(p.Dq, 8).total, st);
-    else if (p.k <= 16) launch_scan_tc_kr<16>(p, tc_smem_layout(p.Dq, 16).total, st);
-    else launch_scan_tc_kr<32>(p, tc_smem_layout(p.Dq, 32).total, st);
+    if (p.k <= 8) launch_scan_tc_kr<8>(p, tc_smem_layout(p.Dh, 8).total, st);
+    else if (p.k <= 16) launch_scan_tc_kr<16>(p, tc_smem_layout(p.Dh, 16).total, st);
+    else launch_scan_tc_kr<32>(p, tc_smem_layout(p.Dh, 32).total, st);
 }
 void launch_finalize(const FinalizeParams& p, cudaStream_t st) {
     if (!p.nq) return;

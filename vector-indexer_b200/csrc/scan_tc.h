@@ -1,13 +1,27 @@
-// scan_tc.h -- tensor-core list scan (tcgen05 TF32 pre-filter + exact finalize).
+// scan_tc.h -- tensor-core list scan (tcgen05 FP16 pre-filter + exact finalize).
 #pragma once
 #include "common.cuh"
 
 namespace vidx {
 
+// Power-of-two scales of one search batch, written on the device by tc_scale_kernel: stored vectors are scaled by
+// 2^sv when the fp16 shadow store is built (index constant), queries by 2^sq per batch, both to a largest
+// component in [2^6, 2^7), so products and sums stay far inside fp16 / fp32 range.
+struct TcScale {
+    float S;        // 2^(sq+sv): an accumulator holds S * (filter value in real units)
+    float invS;
+    float qmul;     // -2 * 2^sq: query components are multiplied by this before the fp16 conversion
+    float a_ones;   // 2^(sq-sv+g): A-side partner of the three norm terms b = (1-eps)|v|^2 * 2^(2sv-g)
+    float c_abs;    // absolute error of 2*dot from fp16 subnormals, real units (0 for ordinary data)
+    uint32_t ok;    // 0: the batch cannot be scaled into fp16 range; every query is handed to the exact kernels
+};
+
 struct TcParams {
-    const float4* vecs;            // interleaved groups
-    const float4* vnorm;           // per row: (1-eps)*|v|^2 as three TF32-exact terms (x+y+z), NaN for padding rows
-    int Dq;
+    const uint4* vecs16;           // fp16 shadow store: [supergroup][Dh chunks][128 vectors][8 halfs], scaled by 2^sv
+    const uint4* vnorm;            // per row 8 halfs: the three fp16 terms of (1-eps)|v|^2 * 2^(2sv-g), then zeros; NaN for padding rows
+    int Dh;                        // 16-byte chunks (8 halfs) per vector in the shadow store; even
+    int Dq;                        // float4 per query row
+    const TcScale* scale;
     const float4* xq4;             // queries, row-major, Dq float4 per row
     const float* qnorm;            // per query |q|^2
     const uint32_t* list_g0;       // first group of each list
@@ -17,6 +31,7 @@ struct TcParams {
     const uint2* list_qlist;       // (query, probe rank)
     const uint32_t* item_off;      // nlist+1: prefix of work items per list
     uint32_t nlist;
+    uint32_t nq;
     uint32_t* work_counter;
     const uint32_t* chunk_tiles;   // tiles per work item, chosen by tc_items_kernel
     uint32_t* gthr_bits;           // per query: upper bound of the exact k-th best distance (float bits)
@@ -54,11 +69,18 @@ struct FinalizeParams {
     uint32_t* out_rows;
 };
 
-bool tc_supported(int Dq, uint32_t k);
-void launch_row_norms(const float4* vecs, int Dq, const uint32_t* row_src, size_t nrows, float4* vn3, float* vn_true,
+bool tc_supported(int D, uint32_t k);  // D = vector dimension
+int tc_dh(int D);  // chunks per vector of the shadow store (dimension padded to a multiple of 16)
+// |v|^2 per row (0 for padding rows) and, in stats[0], the float bits of the largest |component|.
+void launch_row_norms(const float4* vecs, int Dq, const uint32_t* row_src, size_t nrows, float* vn_true, uint32_t* stats,
                       cudaStream_t st);
+// The fp16 shadow store and the norm terms, given the index scale sv and the norm shift g.
+void launch_convert16(const float4* vecs, int Dq, int Dh, const uint32_t* row_src, size_t nrows, const float* vn_true, int sv, int g,
+                      uint4* vecs16, uint4* vnorm, cudaStream_t st);
+// stats[0..1]: float bits of max |q component| and max |q|^2 over the batch (zeroed by the caller).
 void launch_query_norms(const float4* xq4, int Dq, uint32_t nq, uint32_t k, float* qn, uint32_t* gthr_bits, uint32_t* cand_cnt,
-                        uint32_t* overflow, float* gtop, uint32_t* glock, cudaStream_t st);
+                        uint32_t* overflow, float* gtop, uint32_t* glock, uint32_t* stats, cudaStream_t st);
+void launch_tc_scale(const uint32_t* qstats, int sv, int g, int D, float vmax, float vn_max, TcScale* out, cudaStream_t st);
 void launch_tc_count(const uint32_t* probes, size_t npairs, uint32_t nprobe, bool rank0_only, const uint2* list_seg,
                      uint32_t* list_cnt, cudaStream_t st);
 void launch_tc_fill(const uint32_t* probes, size_t npairs, uint32_t nprobe, bool rank0_only, const uint2* list_seg,
