@@ -546,7 +546,31 @@ void Index::search_device(const float* d_xq, uint64_t nq, uint64_t k_req, uint64
             tp.item_off = w.item_off.as<uint32_t>();
             tp.work_counter = counters + 8;
             tp.chunk_tiles = counters + 10;
+#ifdef VIDX_TC_TIMING
+            static DevBuf d_dbg;
+            d_dbg.reserve(1024 * 16 * 8);
+            VIDX_CUDA(cudaMemsetAsync(d_dbg.p, 0, 1024 * 16 * 8, st));
+            tp.dbg = d_dbg.as<unsigned long long>();
+#endif
             launch_scan_tc(tp, st);
+#ifdef VIDX_TC_TIMING
+            if (profiling) {
+                std::vector<unsigned long long> h(1024 * 16);
+                d2h_sync(h.data(), d_dbg.as<unsigned long long>(), h.size(), st);
+                double acc[16] = {};
+                int nb = 0;
+                for (int b = 0; b < 1024; b++) {
+                    if (!h[16 * b + 13]) continue;
+                    nb++;
+                    for (int i = 0; i < 16; i++) acc[i] += (double)h[16 * b + i];
+                }
+                const char* names[16] = {"prod0 wait empty", "prod1 wait empty", "prod0 wait tempty", "prod1 wait tempty", "mma0 wait tempty",
+                                         "mma1 wait tempty", "mma0 wait full", "mma1 wait full", "epi(w2) wait tfull", "w2 drain wait",
+                                         "w2 item setup", "items", "tiles", "kernel cycles", "w2 LDTM+wait", "w2 after LDTM"};
+                fprintf(stderr, "[tc timing] %d CTAs\n", nb);
+                for (int i = 0; i < 16; i++) fprintf(stderr, "  %-20s %12.0f per CTA  (%.1f%% of kernel)\n", names[i], acc[i] / nb, 100.0 * acc[i] / acc[13]);
+            }
+#endif
         }
         if (profiling) VIDX_CUDA(cudaEventRecord(ev[8], st));
 

@@ -58,7 +58,8 @@ constexpr int kTcAccStages = 4;      // accumulator tiles in TMEM
 constexpr int kTcTmemCols = 512;     // 4 accumulator stages x 128 columns
 constexpr int kTcStages = 4;         // shared-memory ring: stages of 128 vectors x 128 dims of fp16 (32 KB), two per tile pipeline
 constexpr int kTcStageChunks = 16;   // 16-byte chunks (8 halfs) of every vector per stage
-constexpr uint32_t kTcStageBytes = kTcStageChunks * kTcTileGroups * 512;
+constexpr uint32_t kTcStageData = kTcStageChunks * kTcTileGroups * 512;  // 32 KB of vector chunks
+constexpr uint32_t kTcStageBytes = kTcStageData + 2048;                  // + the tile's norm chunk (used by the last K-slice)
 constexpr float kTcEps = 1.5e-3f;    // see header comment; needed: ~1.03e-3
 
 // ---- PTX wrappers ------------------------------------------------------------------------
@@ -384,8 +385,8 @@ __host__ __device__ inline TcSmemLayout tc_smem_layout(int Dh, int kr) {
     L.stages = kTcStages;
     L.a_bytes = (uint32_t)Dh * kTcM * 16;                   // query tile, [chunk][128 rows][16 B = 8 halfs]
     L.off_b = L.a_bytes;                                    // ring of list-tile K-slices
-    L.off_norm = L.off_b + L.stages * kTcStageBytes;        // per accumulator stage: norm chunk [128 rows][16 B]
-    L.off_ones = L.off_norm + kTcAccStages * 2048;          // A-side partner of the norm chunk: (1,1,1,0) per row
+    L.off_norm = L.off_b + L.stages * kTcStageBytes;        // (end of the ring; every stage carries its own norm chunk)
+    L.off_ones = L.off_norm;                                // A-side partner of the norm chunk: (a,a,a,0,..) per row
     L.off_zero = L.off_ones + 2048;                         // second K chunk of the norm step, both operands: zeros
     L.off_r = L.off_zero + 2048;                            // per query row: its k smallest filter values, descending
     L.off_queue = L.off_r + (uint32_t)kTcM * (kr + 1) * 4;  // (row stride kr+1: lanes on different rows hit different banks)
@@ -430,13 +431,20 @@ __device__ __forceinline__ float min32(const float* v) {
 // bound (a survivor candidate).
 constexpr uint32_t kEntValid = 0x40000000u;
 
+// Optional role timers (-DVIDX_TC_TIMING): cycles each role spends in its waits, summed per CTA into p.dbg[16 * blockIdx.x + slot].
+#ifdef VIDX_TC_TIMING
+#define TC_T0() const long long _t0 = clock64()
+#define TC_ACC(slot) do { if (lane == 0 && p.dbg) atomicAdd(&p.dbg[16 * blockIdx.x + (slot)], (unsigned long long)(clock64() - _t0)); } while (0)
+#else
+#define TC_T0() do { } while (0)
+#define TC_ACC(slot) do { } while (0)
+#endif
 template <int KR>
 __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const TcSmemLayout L = tc_smem_layout(p.Dh, KR);
     unsigned char* sA = smem;
     unsigned char* sB = smem + L.off_b;
-    unsigned char* sNorm = smem + L.off_norm;
     constexpr int kRS = KR + 1;                                     // row stride of s_r
     float* s_r = reinterpret_cast<float*>(smem + L.off_r);          // [128][KR+1]
     constexpr int kTcQueueCap = tc_queue_cap(KR), kTcStageCap = tc_stage_cap(KR);
@@ -472,7 +480,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
         }
         for (int i = 0; i < kTcAccStages; i++) {
             mbar_init(&bar_tfull[i], 1);
-            mbar_init(&bar_tempty[i], kTcEpiWarps);
+            mbar_init(&bar_tempty[i], kTcEpiWarps / 2);  // the four warps of the epilogue group that owns the tile
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -503,9 +511,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
     // would let an issuer run a whole ring ahead of the other, where a phase-parity wait reads a stale "ready".)
     uint32_t ks_it = 0;  // K-slices processed so far by this warp's pipeline (stage = 2*pipe + (ks_it & 1), phase = (ks_it >> 1) & 1)
 
+#ifdef VIDX_TC_TIMING
+    const long long _tk0 = clock64();
+#endif
     for (;;) {
+#ifdef VIDX_TC_TIMING
+        const long long _ti0 = clock64();
+#endif
         if (tid == 0) s_misc[1] = atomicAdd(p.work_counter, 1u);
         __syncthreads();  // also: every warp is done with the previous item's queue
+#ifdef VIDX_TC_TIMING
+        if (tid == 64 && p.dbg) atomicAdd(&p.dbg[16 * blockIdx.x + 9], (unsigned long long)(clock64() - _ti0));  // warp 2: drain wait
+#endif
         const uint32_t item = __shfl_sync(kFull, s_misc[1], 0);
         if (item >= total_items) break;
         if (tid == kTcThreads - 1) {  // empty queue for this item (published by the barriers below)
@@ -598,6 +615,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
         }
         fence_proxy_async();
         __syncthreads();
+#ifdef VIDX_TC_TIMING
+        if (tid == 64 && p.dbg) {
+            atomicAdd(&p.dbg[16 * blockIdx.x + 10], (unsigned long long)(clock64() - _ti0));  // loop top -> roles start
+            atomicAdd(&p.dbg[16 * blockIdx.x + 11], 1ull);                                    // items
+            atomicAdd(&p.dbg[16 * blockIdx.x + 12], (unsigned long long)(t1 - t0));           // tiles
+        }
+#endif
 
         if (warp == 0 || warp == 12) {
             // ===== producers (pipeline 0: warp 0, pipeline 1: warp 12).  The warp runs the loop converged
@@ -609,19 +633,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
             const uint4* nsrc = p.vnorm + ((size_t)g_list + (size_t)t0 * kTcTileGroups) * 32;
             for (uint32_t t = t0; t < t1; t++, it++, nsrc += kSuper, src += tile_bytes) {
                 if ((it & 1u) != pipe) continue;
-                const uint32_t a = it & (kTcAccStages - 1), aph = (it / kTcAccStages) & 1;
                 const unsigned char* ssrc = src;
                 for (int kc = 0; kc < nkc; kc++, ks_it++) {
                     const uint32_t nch = (uint32_t)min(kTcStageChunks, Dh - kc * kTcStageChunks);
                     const uint32_t bytes = nch * kSuper * 16;
                     const uint32_t s = 2 * pipe + (ks_it & 1u), ph = (ks_it >> 1) & 1;
-                    mbar_wait(&bar_empty[s], ph ^ 1);
+                    { TC_T0(); mbar_wait(&bar_empty[s], ph ^ 1); TC_ACC(0 + pipe); }
                     const bool last = kc == nkc - 1;
-                    if (last) mbar_wait(&bar_tempty[a], aph ^ 1);  // norm chunk of this accumulator stage is free
                     if (elect_one()) {
                         mbar_expect_tx(&bar_full[s], bytes + (last ? 2048u : 0u));
                         bulk_g2s(sB + s * kTcStageBytes, ssrc, bytes, &bar_full[s]);
-                        if (last) bulk_g2s(sNorm + a * 2048, nsrc, 2048, &bar_full[s]);
+                        if (last) bulk_g2s(sB + s * kTcStageBytes + kTcStageData, nsrc, 2048, &bar_full[s]);
                     }
                     __syncwarp();
                     ssrc += bytes;
@@ -643,17 +665,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
                 for (uint32_t t = t0; t < t1; t++, it++) {
                     if ((it & 1u) != pipe) continue;
                     const uint32_t a = it & (kTcAccStages - 1), aph = (it / kTcAccStages) & 1;
-                    mbar_wait(&bar_tempty[a], aph ^ 1);
+                    { TC_T0(); mbar_wait(&bar_tempty[a], aph ^ 1); TC_ACC(4 + pipe); }
                     const uint32_t d_tmem = tmem_base + a * 128;
                     for (int kc = 0; kc < nkc; kc++, ks_it++) {
                         const uint32_t s = 2 * pipe + (ks_it & 1u), ph = (ks_it >> 1) & 1;
-                        mbar_wait(&bar_full[s], ph);
+                        { TC_T0(); mbar_wait(&bar_full[s], ph); TC_ACC(6 + pipe); }
                         tc_fence_after();
                         // chunk c of all 128 rows is one 2 KB block (128 x 16 B) in both tiles: +128 per chunk in >>4 units
                         const uint32_t al = a_lo0 + (uint32_t)kc * (kTcStageChunks * 128);
                         const uint32_t bl = b_lo0 + s * (kTcStageBytes >> 4);
                         const int nks = min(kTcStageChunks / 2, (Dh >> 1) - kc * (kTcStageChunks / 2));
-                        const uint32_t noff = L.off_norm + a * 2048;
+                        const uint32_t noff = L.off_b + s * kTcStageBytes + kTcStageData;
                         const uint32_t norm_lo = ((smem_u32(smem + noff) >> 4) & 0x3fffu) | (((L.off_zero - noff) >> 4) << 16);
                         if (elect_one()) {
                             if (kc == 0) tc_mma_f16_lo<false>(d_tmem, al, bl, desc_hi, idesc);
@@ -793,18 +815,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
             it += t1 - t0;
             asm volatile("bar.sync 1, %0;" ::"n"((kTcEpiWarps + 1) * 32) : "memory");
         } else {
-            // ===== epilogue: one thread per (query row, column half); the accumulators already hold
-            // (1-eps)|v|^2 - 2 q.v, so a tile costs one 3-input min per three columns and one branch per 32 =====
+            // ===== epilogue: two groups of four warps alternate tiles (group g = pipeline g's tiles); a thread owns one
+            // query row of its group's tiles.  The accumulators already hold (1-eps)|v|^2 - 2 q.v (scaled), so a tile costs
+            // one 3-input min per three columns and one branch per 32 =====
             const int quarter = warp & 3;        // TMEM lanes this warp may read: 32*quarter .. +31
-            const int half = (warp - 2) >> 2;    // column blocks 2*half, 2*half+1 of every tile
+            const uint32_t grp = (uint32_t)(warp - 2) >> 2;
             const int row = quarter * 32 + lane;
             const uint2 qi = s_q[row];
             const bool valid = qi.x != kNoRow;
             const float delta = s_delta[row];
+            const uint32_t seed_tiles = p.seed_tiles, kk = p.k;
             float P = s_P[row];
             float lr[KR];  // the k smallest values this thread queued in this item, descending (+inf until k exist)
 #pragma unroll
-            for (int i = 0; i < KR; i++) lr[i] = i < (int)p.k ? kInf : -kInf;
+            for (int i = 0; i < KR; i++) lr[i] = i < (int)kk ? kInf : -kInf;
             // rows whose nearest list this is already scanned its first seed_tiles tiles in the seeding pass
             const bool skip_seeded = p.mode == 0 && qi.y == 0;
             auto push = [&](uint32_t info, float v) {
@@ -816,45 +840,49 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
                 sts_volatile_v2(&s_queue[idx & (kTcQueueCap - 1)], make_uint2(info, __float_as_uint(v)));
             };
             for (uint32_t t = t0; t < t1; t++, it++) {
+                if ((it & 1u) != grp) continue;
                 const uint32_t s = it & (kTcAccStages - 1), ph = (it / kTcAccStages) & 1;
-                mbar_wait(&bar_tfull[s], ph);
+                { TC_T0(); mbar_wait(&bar_tfull[s], ph); if (warp == 2) TC_ACC(8); }
                 tc_fence_after();
                 const uint32_t ng = min((uint32_t)kTcTileGroups, ngl - t * kTcTileGroups);
-                const bool active = valid && !(skip_seeded && t < p.seed_tiles);
+                const bool active = valid && !(skip_seeded && t < seed_tiles);
                 P = fminf(P, lds_volatile_f(&s_P[row]));
-                float acc[64];
-                const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + s * 128 + half * 64;
-                tc_ld32x2(tbase, tbase + 32, acc);
+                const uint32_t tl = t - t0;
+#pragma unroll 1
+                for (uint32_t half = 0; half < 2; half++) {
+                    float acc[64];
+                    const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + s * 128 + half * 64;
+                    { TC_T0(); tc_ld32x2(tbase, tbase + 32, acc); if (warp == 2) TC_ACC(14); }
 #pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const uint32_t cb = 2 * half + h;
-                    const float* tv = acc + 32 * h;
-                    if (active && cb < ng && min32(tv) <= P) {
-                        // rare path: this row has columns inside its bound (as of the latest bound)
-                        P = fminf(P, lds_volatile_f(&s_P[row]));
-                        uint32_t mask = 0;
+                    for (int h = 0; h < 2; h++) {
+                        const uint32_t cb = 2 * half + h;
+                        const float* tv = acc + 32 * h;
+                        if (active && cb < ng && min32(tv) <= P) {
+                            // rare path: this row has columns inside its bound (as of the latest bound)
+                            P = fminf(P, lds_volatile_f(&s_P[row]));
+                            uint32_t mask = 0;
 #pragma unroll
-                        for (int j = 0; j < 32; j++) mask |= (tv[j] <= P) ? (1u << j) : 0u;
-                        const uint32_t tl = t - t0;
-                        while (mask) {
-                            const int j = __ffs(mask) - 1;
-                            mask &= mask - 1;
-                            float v = tv[0];
+                            for (int j = 0; j < 32; j++) mask |= (tv[j] <= P) ? (1u << j) : 0u;
+                            while (mask) {
+                                const int j = __ffs(mask) - 1;
+                                mask &= mask - 1;
+                                float v = tv[0];
 #pragma unroll
-                            for (int jj = 1; jj < 32; jj++) v = (jj == j) ? tv[jj] : v;
-                            if (v <= P) {  // the bound may have shrunk since the mask was built
-                                push(kEntValid | (tl << 14) | ((cb * 32u + (uint32_t)j) << 7) | (uint32_t)row, v);
-                                // flood control (cold or very loose bound): the k-th smallest value this thread queued
-                                // in this item bounds the row's k-th best at once, without the selector's latency
-                                if (v < lr[0]) {
-                                    lr[0] = v;
+                                for (int jj = 1; jj < 32; jj++) v = (jj == j) ? tv[jj] : v;
+                                if (v <= P) {  // the bound may have shrunk since the mask was built
+                                    push(kEntValid | (tl << 14) | ((cb * 32u + (uint32_t)j) << 7) | (uint32_t)row, v);
+                                    // flood control (cold or very loose bound): the k-th smallest value this thread queued
+                                    // in this item bounds the row's k-th best at once, without the selector's latency
+                                    if (v < lr[0]) {
+                                        lr[0] = v;
 #pragma unroll
-                                    for (int i = 0; i + 1 < KR; i++) {
-                                        const float hi_v = fmaxf(lr[i], lr[i + 1]), lo_v = fminf(lr[i], lr[i + 1]);
-                                        lr[i] = hi_v;
-                                        lr[i + 1] = lo_v;
+                                        for (int i = 0; i + 1 < KR; i++) {
+                                            const float hi_v = fmaxf(lr[i], lr[i + 1]), lo_v = fminf(lr[i], lr[i + 1]);
+                                            lr[i] = hi_v;
+                                            lr[i + 1] = lo_v;
+                                        }
+                                        P = fminf(P, lr[0] + delta);
                                     }
-                                    P = fminf(P, lr[0] + delta);
                                 }
                             }
                         }
@@ -872,7 +900,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
             asm volatile("bar.sync 1, %0;" ::"n"((kTcEpiWarps + 1) * 32) : "memory");
             // merge this item's k smallest into the shared set (distinct values only: a value both sides
             // already hold must not be counted twice; dropping a legitimately equal value only loosens the bound)
-            if (valid && half == 0 && s_impr[row]) {
+            if (valid && grp == 0 && s_impr[row]) {
               const uint32_t q = qi.x;
               const float base_t = s_base[row];
               float r[KR];
@@ -937,6 +965,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
     }
     tc_fence_before();
     __syncthreads();
+#ifdef VIDX_TC_TIMING
+    if (tid == 0 && p.dbg) p.dbg[16 * blockIdx.x + 13] += (unsigned long long)(clock64() - _tk0);
+#endif
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTcTmemCols) : "memory");
     }

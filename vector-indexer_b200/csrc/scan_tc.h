@@ -44,6 +44,7 @@ struct TcParams {
     uint32_t capq;
     uint32_t k;
     float vn_max;                  // max |v|^2 over the stored rows
+    unsigned long long* dbg;       // role timers (builds with -DVIDX_TC_TIMING only), else NULL
     uint32_t mode;                 // 0 = main pass, 1 = seeding pass (head of each query's nearest list only)
     uint32_t seed_tiles;           // tiles per list covered by the seeding pass (0 = no seeding pass was run)
 };
