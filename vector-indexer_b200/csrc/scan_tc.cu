@@ -631,8 +631,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
             const uint32_t tile_bytes = (uint32_t)Dh * kSuper * 16;
             const unsigned char* src = reinterpret_cast<const unsigned char*>(p.vecs16) + ((size_t)(g_list >> 2) + t0) * tile_bytes;
             const uint4* nsrc = p.vnorm + ((size_t)g_list + (size_t)t0 * kTcTileGroups) * 32;
-            for (uint32_t t = t0; t < t1; t++, it++, nsrc += kSuper, src += tile_bytes) {
-                if ((it & 1u) != pipe) continue;
+            const uint32_t skip = (pipe ^ it) & 1u;  // first tile of this item that belongs to this pipeline
+            src += (size_t)skip * tile_bytes;
+            nsrc += skip * kSuper;
+            for (uint32_t t = t0 + skip; t < t1; t += 2, nsrc += 2 * kSuper, src += 2 * (size_t)tile_bytes) {
                 const unsigned char* ssrc = src;
                 for (int kc = 0; kc < nkc; kc++, ks_it++) {
                     const uint32_t nch = (uint32_t)min(kTcStageChunks, Dh - kc * kTcStageChunks);
@@ -649,6 +651,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
                     ssrc += bytes;
                 }
             }
+            it += t1 - t0;
         } else if (warp == 1 || warp == 10) {
             // ===== MMA issuers: warp 1 takes the even tiles of this CTA's tile sequence, warp 10 the odd ones
             // (one thread each; the loop is kept to a few dozen instructions per K-slice because a single
@@ -662,9 +665,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
                 const uint32_t b_lo0 = ((smem_u32(sB) >> 4) & 0x3fffu) | lbo_bits;
                 // norm step: K chunk 0 = (1,1,1,0) x (n_hi, n_mid, n_lo, 0), K chunk 1 = the shared zero block
                 const uint32_t ones_lo = ((smem_u32(smem + L.off_ones) >> 4) & 0x3fffu) | (((L.off_zero - L.off_ones) >> 4) << 16);
-                for (uint32_t t = t0; t < t1; t++, it++) {
-                    if ((it & 1u) != pipe) continue;
-                    const uint32_t a = it & (kTcAccStages - 1), aph = (it / kTcAccStages) & 1;
+                const uint32_t skip = (pipe ^ it) & 1u;  // first tile of this item that belongs to this pipeline
+                for (uint32_t itt = it + skip; itt < it + (t1 - t0); itt += 2) {
+                    const uint32_t a = itt & (kTcAccStages - 1), aph = (itt / kTcAccStages) & 1;
                     { TC_T0(); mbar_wait(&bar_tempty[a], aph ^ 1); TC_ACC(4 + pipe); }
                     const uint32_t d_tmem = tmem_base + a * 128;
                     for (int kc = 0; kc < nkc; kc++, ks_it++) {
@@ -690,6 +693,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
                         __syncwarp();
                     }
                 }
+                it += t1 - t0;
             }
         } else if (warp == 11) {
             // ===== selector: the only writer of the rows' bounds and top-k sets =====
@@ -839,15 +843,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
                 }
                 sts_volatile_v2(&s_queue[idx & (kTcQueueCap - 1)], make_uint2(info, __float_as_uint(v)));
             };
-            for (uint32_t t = t0; t < t1; t++, it++) {
-                if ((it & 1u) != grp) continue;
-                const uint32_t s = it & (kTcAccStages - 1), ph = (it / kTcAccStages) & 1;
+            const uint32_t eskip = (grp ^ it) & 1u;  // first tile of this item that belongs to this group
+            for (uint32_t t = t0 + eskip; t < t1; t += 2) {
+                const uint32_t tl = t - t0, itt = it + tl;
+                const uint32_t s = itt & (kTcAccStages - 1), ph = (itt / kTcAccStages) & 1;
+                const float Pnew = lds_volatile_f(&s_P[row]);  // in flight during the wait
                 { TC_T0(); mbar_wait(&bar_tfull[s], ph); if (warp == 2) TC_ACC(8); }
                 tc_fence_after();
                 const uint32_t ng = min((uint32_t)kTcTileGroups, ngl - t * kTcTileGroups);
                 const bool active = valid && !(skip_seeded && t < seed_tiles);
-                P = fminf(P, lds_volatile_f(&s_P[row]));
-                const uint32_t tl = t - t0;
+                P = fminf(P, Pnew);
 #pragma unroll 1
                 for (uint32_t half = 0; half < 2; half++) {
                     float acc[64];
@@ -892,6 +897,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bar_tempty[s]);
             }
+            it += t1 - t0;
             __syncwarp();
             if (lane == 0) {
                 __threadfence_block();
