@@ -332,7 +332,7 @@ struct Index::Workspace {
     DevBuf xq_pad, dist, probes, pair_ns, slot_off, seg_cnt, seg_qoff, seg_cur, seg_qlist, slot_seg, dense, sparse, counters,
         scan_tmp, cand_d, cand_r, alld, row_off, row_len, sel_pos, sel_val, rows, stats, slot_rank, list_cnt, list_cur, list_qoff,
         list_qlist, items_per_list, item_off, qnorm, gthr, cand_cnt, overflow, cand, list_cnt0, list_cur0, list_qoff0, list_qlist0,
-        items_per_list0, item_off0, gtop, glock, tcscale;
+        items_per_list0, item_off0, gtop, glock, tcscale, items, items0;
 };
 void Index::delete_workspace() {
     delete ws;
@@ -487,6 +487,15 @@ void Index::search_device(const float* d_xq, uint64_t nq, uint64_t k_req, uint64
             launch_tc_items(w.list_cnt.as<uint32_t>(), d_list_ng.as<uint32_t>(), (uint32_t)nlist,
                             reinterpret_cast<unsigned long long*>(counters + 12), 0, counters + 10, w.items_per_list.as<uint32_t>(), st);
             exclusive_scan_u32(w.items_per_list.as<uint32_t>(), w.item_off.as<uint32_t>(), nlist, w.scan_tmp.as<uint32_t>(), st);
+            {
+                // one 32-byte record per work item; items <= total/chunk + sum of query tiles per list, with
+                // total <= (nq/128 + 1) * tiles and chunk >= min(128, total / (8 SMs-worth))
+                const uint64_t tiles = (uint64_t)ceil_div(std::max<uint64_t>(owned_vectors, 1), 128) + nlist;
+                const uint64_t cap_items = (nqb / 128 + 1) * tiles / 128 + 8 * 160 + npairs / 128 + 2 * nlist + 64;
+                w.items.reserve(cap_items * sizeof(TcItem));
+                launch_tc_expand(w.list_cnt.as<uint32_t>(), d_list_ng.as<uint32_t>(), d_list_g0.as<uint32_t>(), w.list_qoff.as<uint32_t>(),
+                                 w.item_off.as<uint32_t>(), counters + 10, (uint32_t)nlist, 0, w.items.as<TcItem>(), st);
+            }
             // seeding pass: the same grouping restricted to each query's nearest list
             w.list_cnt0.reserve(((size_t)nlist + 1) * 4);
             w.list_cur0.reserve(((size_t)nlist + 1) * 4);
@@ -503,6 +512,9 @@ void Index::search_device(const float* d_xq, uint64_t nq, uint64_t k_req, uint64
             launch_tc_items(w.list_cnt0.as<uint32_t>(), d_list_ng.as<uint32_t>(), (uint32_t)nlist, nullptr, kSeedTiles, counters + 11,
                             w.items_per_list0.as<uint32_t>(), st);
             exclusive_scan_u32(w.items_per_list0.as<uint32_t>(), w.item_off0.as<uint32_t>(), nlist, w.scan_tmp.as<uint32_t>(), st);
+            w.items0.reserve(((uint64_t)nqb / 32 + 2 * nlist + 64) * sizeof(TcItem));
+            launch_tc_expand(w.list_cnt0.as<uint32_t>(), d_list_ng.as<uint32_t>(), d_list_g0.as<uint32_t>(), w.list_qoff0.as<uint32_t>(),
+                             w.item_off0.as<uint32_t>(), counters + 11, (uint32_t)nlist, kSeedTiles, w.items0.as<TcItem>(), st);
         }
         if (profiling) VIDX_CUDA(cudaEventRecord(ev[3], st));
         if (tc) {
@@ -535,8 +547,8 @@ void Index::search_device(const float* d_xq, uint64_t nq, uint64_t k_req, uint64
             tp.list_qoff = w.list_qoff0.as<uint32_t>();
             tp.list_qlist = w.list_qlist0.as<uint2>();
             tp.item_off = w.item_off0.as<uint32_t>();
+            tp.items = w.items0.as<TcItem>();
             tp.work_counter = counters + 9;
-            tp.chunk_tiles = counters + 11;
             launch_scan_tc(tp, st);
             // pass 2: everything else, starting from warm bounds
             tp.mode = 0;
@@ -544,8 +556,8 @@ void Index::search_device(const float* d_xq, uint64_t nq, uint64_t k_req, uint64
             tp.list_qoff = w.list_qoff.as<uint32_t>();
             tp.list_qlist = w.list_qlist.as<uint2>();
             tp.item_off = w.item_off.as<uint32_t>();
+            tp.items = w.items.as<TcItem>();
             tp.work_counter = counters + 8;
-            tp.chunk_tiles = counters + 10;
 #ifdef VIDX_TC_TIMING
             static DevBuf d_dbg;
             d_dbg.reserve(1024 * 16 * 8);

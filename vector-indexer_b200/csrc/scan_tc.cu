@@ -373,11 +373,43 @@ __global__ void tc_items_kernel(const uint32_t* __restrict__ list_cnt, const uin
     items_per_list[l] = c ? ((c + qrows - 1) / qrows) * nch : 0u;
 }
 
+// One record per work item, so that a CTA decodes an item with a single 32-byte load (prefetched one item ahead)
+// instead of a binary search and a chain of dependent loads.
+__global__ void tc_expand_kernel(const uint32_t* __restrict__ list_cnt, const uint32_t* __restrict__ list_ngroups,
+                                 const uint32_t* __restrict__ list_g0, const uint32_t* __restrict__ list_qoff,
+                                 const uint32_t* __restrict__ item_off, const uint32_t* __restrict__ chunk_tiles, uint32_t nlist,
+                                 uint32_t seed_tiles, TcItem* __restrict__ items) {
+    const uint32_t l = blockIdx.x;
+    if (l >= nlist) return;
+    const uint32_t i0 = item_off[l], n = item_off[l + 1] - i0;
+    if (!n) return;
+    const uint32_t cnt = list_cnt[l], ngl = list_ngroups[l], g_list = list_g0[l], qoff = list_qoff[l], chunk = *chunk_tiles;
+    const uint32_t qrows = seed_tiles ? (uint32_t)kTcSeedRows : (uint32_t)kTcM;
+    const uint32_t nqt = (cnt + qrows - 1) / qrows;
+    uint32_t ntiles = (ngl + kTcTileGroups - 1) / kTcTileGroups;
+    if (seed_tiles) ntiles = min(ntiles, seed_tiles);
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        // chunk-major: CTAs running at the same time share a vector chunk (L2 reuse), and a query's later chunks
+        // start with a warm bound
+        const uint32_t c = i / nqt, qt = i - c * nqt;
+        TcItem r;
+        r.t0 = c * chunk;
+        r.t1 = min(ntiles, r.t0 + chunk);
+        r.qbase = qoff + qt * qrows;
+        r.nq_tile = min(qrows, cnt - qt * qrows);
+        r.g_list = g_list;
+        r.ngl = ngl;
+        r.valid = 1u;
+        r.pad = 0u;
+        items[i0 + i] = r;
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // the tensor-core scan
 // ------------------------------------------------------------------------------------------
 struct TcSmemLayout {
-    uint32_t a_bytes, off_b, off_norm, off_ones, off_zero, off_r, off_queue, off_stage, off_q, off_row, off_bar, off_misc, total;
+    uint32_t a_bytes, off_b, off_norm, off_ones, off_zero, off_r, off_queue, off_stage, off_q, off_row, off_bar, off_misc, off_item, total;
     uint32_t stages;
 };
 __host__ __device__ inline TcSmemLayout tc_smem_layout(int Dh, int kr) {
@@ -395,7 +427,8 @@ __host__ __device__ inline TcSmemLayout tc_smem_layout(int Dh, int kr) {
     L.off_row = L.off_q + kTcM * 8;                         // per row: bound P, delta, base, improved flag
     L.off_bar = L.off_row + 4 * kTcM * 4;
     L.off_misc = L.off_bar + (2 * kTcStages + 2 * kTcAccStages) * 8;
-    L.total = L.off_misc + 64 + 128;
+    L.off_item = L.off_misc + 64 + 128;                      // two staged work-item records
+    L.total = L.off_item + 2 * 32;
     return L;
 }
 
@@ -502,7 +535,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
     const uint32_t tmem_base = s_misc[0];
     const uint32_t total_items = p.item_off[p.nlist];
     const uint32_t idesc = make_idesc_f16(kTcM, kTcTileGroups * 32);
-    const uint32_t chunk_tiles = *p.chunk_tiles;
     const int nkc = (Dh + kTcStageChunks - 1) / kTcStageChunks;  // K-slices per tile
     const float kInf = __int_as_float(0x7f800000);
     uint32_t it = 0;     // tiles processed so far by this CTA (accumulator stage = it & 3, phase = (it >> 2) & 1)
@@ -511,110 +543,119 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
     // would let an issuer run a whole ring ahead of the other, where a phase-parity wait reads a stale "ready".)
     uint32_t ks_it = 0;  // K-slices processed so far by this warp's pipeline (stage = 2*pipe + (ks_it & 1), phase = (ks_it >> 1) & 1)
 
+    // Work items are claimed one ahead: while item i runs, the selector warp (idle during an item's set-up) claims
+    // item i+1 and stages its record in shared memory.
+    TcItem* s_item = reinterpret_cast<TcItem*>(smem + L.off_item);  // [2]
+    auto claim = [&](int slot) {  // one thread
+        const uint32_t idx = atomicAdd(p.work_counter, 1u);
+        TcItem r;
+        if (idx < total_items) r = p.items[idx];
+        else r.valid = 0u;
+        s_item[slot] = r;
+    };
+    if (tid == 0) claim(0);
+    uint32_t cur = 0;
 #ifdef VIDX_TC_TIMING
     const long long _tk0 = clock64();
 #endif
-    for (;;) {
+    for (;; cur ^= 1u) {
 #ifdef VIDX_TC_TIMING
         const long long _ti0 = clock64();
 #endif
-        if (tid == 0) s_misc[1] = atomicAdd(p.work_counter, 1u);
-        __syncthreads();  // also: every warp is done with the previous item's queue
+        __syncthreads();  // the record of this item is staged; every warp is done with the previous item
 #ifdef VIDX_TC_TIMING
         if (tid == 64 && p.dbg) atomicAdd(&p.dbg[16 * blockIdx.x + 9], (unsigned long long)(clock64() - _ti0));  // warp 2: drain wait
 #endif
-        const uint32_t item = __shfl_sync(kFull, s_misc[1], 0);
-        if (item >= total_items) break;
-        if (tid == kTcThreads - 1) {  // empty queue for this item (published by the barriers below)
-            s_misc[2] = 0;
-            s_misc[3] = 0;
-            s_misc[4] = 0;
-        }
-        // decode item -> (list, chunk, query tile)
-        uint32_t lo = 0, hi = p.nlist;
-        while (hi - lo > 1) {
-            uint32_t mid = (lo + hi) >> 1;
-            if (p.item_off[mid] <= item) lo = mid; else hi = mid;
-        }
-        const uint32_t l = lo;
-        const uint32_t cnt = p.list_cnt[l];
-        const uint32_t qrows = p.mode == 1 ? (uint32_t)kTcSeedRows : (uint32_t)kTcM;  // query rows per work item
-        const uint32_t nqt = (cnt + qrows - 1) / qrows;
-        const uint32_t local = item - p.item_off[l];
-        const uint32_t chunk = local / nqt, qt = local - chunk * nqt;
-        const uint32_t ngl = p.list_ngroups[l];
-        const uint32_t g_list = p.list_g0[l];
-        uint32_t ntiles = (ngl + kTcTileGroups - 1) / kTcTileGroups;
-        if (p.mode == 1) ntiles = min(ntiles, p.seed_tiles);  // seeding pass: the head of each query's nearest list
-        const uint32_t t0 = chunk * chunk_tiles, t1 = min(ntiles, t0 + chunk_tiles);
-        const uint32_t nq_tile = min(qrows, cnt - qt * qrows);
+        const TcItem rec = s_item[cur];
+        if (!__shfl_sync(kFull, rec.valid, 0)) break;
+        const uint32_t t0 = __shfl_sync(kFull, rec.t0, 0), t1 = __shfl_sync(kFull, rec.t1, 0);
+        const uint32_t g_list = __shfl_sync(kFull, rec.g_list, 0), ngl = __shfl_sync(kFull, rec.ngl, 0);
+        const uint32_t nq_tile = __shfl_sync(kFull, rec.nq_tile, 0), qbase = __shfl_sync(kFull, rec.qbase, 0);
 
-        if (tid < kTcM) {
-            // per-row state of this item: the (query, rank) of the row, its top-k set as known to all CTAs, its bound
-            const uint2 qi = tid < (int)nq_tile ? p.list_qlist[p.list_qoff[l] + qt * qrows + tid] : make_uint2(kNoRow, 0);
-            s_q[tid] = qi;
-            float P = -kInf, delta = 0.0f, base_t = 0.0f;
-            float* rr = s_r + tid * kRS;
-            if (qi.x != kNoRow) {
-                const uint32_t q = qi.x;
-                const float qn = p.qnorm[q];
-                // base_t in real units; delta, the set and P in accumulator units (x S, a power of two)
-                base_t = (1.0f - kTcEps) * qn - tCabs;
-                delta = (2.0f * kTcEps * (qn + p.vn_max) + 2.0f * tCabs) * tS;
-                const float g = __uint_as_float(__ldcg(&p.gthr_bits[q]));
-                const float tau_g = ((g - base_t) + 1e-5f * (g + fabsf(base_t))) * tS;
-                // seqlock read: writers make the version odd while they update the set
-                const volatile uint32_t* ver = p.gver + q;
-                float r0 = kInf;
-                for (;;) {
-                    uint32_t v1 = *ver;
-                    if (v1 & 1u) { __nanosleep(32); continue; }
-                    __threadfence();
-                    for (int i = 0; i < KR; i++) {
-                        float v = i < (int)p.k ? __ldcg(&p.gtop[(size_t)q * p.k + i]) : -kInf;
-                        rr[i] = v;
-                        if (i == 0) r0 = v;
+        // The producers start streaming this item's tiles at once (they need nothing but the record); everyone else
+        // sets the item up behind two named barriers the producers do not take part in.
+        if (warp != 0 && warp != 12) {
+            constexpr int kSetupThreads = kTcThreads - 64;
+            if (tid == 352) {  // (selector warp) empty queue for this item
+                s_misc[2] = 0;
+                s_misc[3] = 0;
+                s_misc[4] = 0;
+            }
+            const int row = tid - 32;  // warps 1-4 own the 128 query rows during set-up
+            uint2 qi = make_uint2(kNoRow, 0);
+            if (row >= 0 && row < kTcM) {
+                if (row < (int)nq_tile) qi = p.list_qlist[qbase + row];
+                s_q[row] = qi;
+            }
+            asm volatile("bar.sync 2, %0;" ::"n"(kSetupThreads) : "memory");
+            if (row >= 0 && row < kTcM) {
+                // per-row state of this item: its top-k set as known to all CTAs, its bound
+                float P = -kInf, delta = 0.0f, base_t = 0.0f;
+                float* rr = s_r + row * kRS;
+                if (qi.x != kNoRow) {
+                    const uint32_t q = qi.x;
+                    const float qn = p.qnorm[q];
+                    // base_t in real units; delta, the set and P in accumulator units (x S, a power of two)
+                    base_t = (1.0f - kTcEps) * qn - tCabs;
+                    delta = (2.0f * kTcEps * (qn + p.vn_max) + 2.0f * tCabs) * tS;
+                    const float g = __uint_as_float(__ldcg(&p.gthr_bits[q]));
+                    const float tau_g = ((g - base_t) + 1e-5f * (g + fabsf(base_t))) * tS;
+                    // seqlock read: writers make the version odd while they update the set
+                    const volatile uint32_t* ver = p.gver + q;
+                    float r0 = kInf;
+                    for (;;) {
+                        uint32_t v1 = *ver;
+                        if (v1 & 1u) { __nanosleep(32); continue; }
+                        __threadfence();
+                        for (int i = 0; i < KR; i++) {
+                            float v = i < (int)p.k ? __ldcg(&p.gtop[(size_t)q * p.k + i]) : -kInf;
+                            rr[i] = v;
+                            if (i == 0) r0 = v;
+                        }
+                        __threadfence();
+                        if (*ver == v1) break;
                     }
-                    __threadfence();
-                    if (*ver == v1) break;
+                    P = fminf(tau_g, r0 + delta);
                 }
-                P = fminf(tau_g, r0 + delta);
-            }
-            s_P[tid] = P;
-            s_delta[tid] = delta;
-            s_base[tid] = base_t;
-            s_impr[tid] = 0;
-        }
-        __syncthreads();
-        // A tile = fp16(-2 * 2^sq * queries): [chunk of 8 dims][128 rows][16 B] (core matrices of 8 rows x 16 B,
-        // SBO 128 B, LBO 2048 B); dimensions beyond the query's are zero
-        for (int base = 0; base < Dh * kTcM; base += kTcThreads * 4) {
-            float4 va[4], vb[4];
+                s_P[row] = P;
+                s_delta[row] = delta;
+                s_base[row] = base_t;
+                s_impr[row] = 0;
+            } else if (warp >= 5) {
+                // A tile = fp16(-2 * 2^sq * queries): [chunk of 8 dims][128 rows][16 B] (core matrices of 8 rows x
+                // 16 B, SBO 128 B, LBO 2048 B); dimensions beyond the query's are zero.  Warps 5-11 gather it while
+                // warps 1-4 fetch the row state.
+                constexpr int kGatherThreads = 6 * 32 + 32;  // warps 5-11 except the producer warp 12 (not here)
+                const int gt = tid - 160;
+                for (int base = 0; base < Dh * kTcM; base += kGatherThreads * 4) {
+                    float4 va[4], vb[4];
 #pragma unroll
-            for (int u = 0; u < 4; u++) {  // issue the gathers first, then store: 8 loads in flight per thread
-                const int idx = base + u * kTcThreads + tid;
-                va[u] = make_float4(0, 0, 0, 0);
-                vb[u] = va[u];
-                if (idx < Dh * kTcM) {
-                    const uint32_t q = s_q[idx & 127].x;
-                    const int c = idx >> 7;
-                    if (q != kNoRow) {
-                        if (2 * c < Dq) va[u] = __ldg(&p.xq4[(size_t)q * Dq + 2 * c]);
-                        if (2 * c + 1 < Dq) vb[u] = __ldg(&p.xq4[(size_t)q * Dq + 2 * c + 1]);
+                    for (int u = 0; u < 4; u++) {  // issue the gathers first, then store: 8 loads in flight per thread
+                        const int idx = base + u * kGatherThreads + gt;
+                        va[u] = make_float4(0, 0, 0, 0);
+                        vb[u] = va[u];
+                        if (idx < Dh * kTcM) {
+                            const uint32_t q = s_q[idx & 127].x;
+                            const int c = idx >> 7;
+                            if (q != kNoRow) {
+                                if (2 * c < Dq) va[u] = __ldg(&p.xq4[(size_t)q * Dq + 2 * c]);
+                                if (2 * c + 1 < Dq) vb[u] = __ldg(&p.xq4[(size_t)q * Dq + 2 * c + 1]);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const int idx = base + u * kGatherThreads + gt;
+                        if (idx < Dh * kTcM)
+                            reinterpret_cast<uint4*>(sA)[idx] =
+                                make_uint4(pack_h2(tQmul * va[u].x, tQmul * va[u].y), pack_h2(tQmul * va[u].z, tQmul * va[u].w),
+                                           pack_h2(tQmul * vb[u].x, tQmul * vb[u].y), pack_h2(tQmul * vb[u].z, tQmul * vb[u].w));
                     }
                 }
+                fence_proxy_async();
             }
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int idx = base + u * kTcThreads + tid;
-                if (idx < Dh * kTcM)
-                    reinterpret_cast<uint4*>(sA)[idx] =
-                        make_uint4(pack_h2(tQmul * va[u].x, tQmul * va[u].y), pack_h2(tQmul * va[u].z, tQmul * va[u].w),
-                                   pack_h2(tQmul * vb[u].x, tQmul * vb[u].y), pack_h2(tQmul * vb[u].z, tQmul * vb[u].w));
-            }
+            asm volatile("bar.sync 2, %0;" ::"n"(kSetupThreads) : "memory");
         }
-        fence_proxy_async();
-        __syncthreads();
 #ifdef VIDX_TC_TIMING
         if (tid == 64 && p.dbg) {
             atomicAdd(&p.dbg[16 * blockIdx.x + 10], (unsigned long long)(clock64() - _ti0));  // loop top -> roles start
@@ -697,6 +738,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
             }
         } else if (warp == 11) {
             // ===== selector: the only writer of the rows' bounds and top-k sets =====
+            if (lane == 0) claim((int)(cur ^ 1u));  // the next work item, one ahead
+            __syncwarp();
             const uint32_t row0_item = (g_list + t0 * kTcTileGroups) * 32u;
             volatile float* vP = s_P;
             volatile float* vr = s_r;
@@ -1139,6 +1182,13 @@ void launch_tc_items(const uint32_t* list_cnt, const uint32_t* list_ngroups, uin
     }
     tc_items_kernel<<<(unsigned)ceil_div(nlist, 256), 256, 0, st>>>(list_cnt, list_ngroups, nlist, total, (uint32_t)tc_num_sms(),
                                                                    seed_tiles, chunk_out, items_per_list);
+    VIDX_LAUNCHED();
+}
+void launch_tc_expand(const uint32_t* list_cnt, const uint32_t* list_ngroups, const uint32_t* list_g0, const uint32_t* list_qoff,
+                      const uint32_t* item_off, const uint32_t* chunk_tiles, uint32_t nlist, uint32_t seed_tiles, TcItem* items,
+                      cudaStream_t st) {
+    if (!nlist) return;
+    tc_expand_kernel<<<nlist, 64, 0, st>>>(list_cnt, list_ngroups, list_g0, list_qoff, item_off, chunk_tiles, nlist, seed_tiles, items);
     VIDX_LAUNCHED();
 }
 template <int KR>

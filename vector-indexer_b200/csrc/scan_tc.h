@@ -16,6 +16,15 @@ struct TcScale {
     uint32_t ok;    // 0: the batch cannot be scaled into fp16 range; every query is handed to the exact kernels
 };
 
+struct TcItem {      // one work item: query tile x list chunk (32 bytes)
+    uint32_t t0, t1;     // tile range within the list
+    uint32_t qbase;      // first entry of the item's rows in list_qlist
+    uint32_t nq_tile;    // rows in use
+    uint32_t g_list;     // first group of the list (this rank's part)
+    uint32_t ngl;        // groups of the list (this rank's part)
+    uint32_t valid, pad;
+};
+
 struct TcParams {
     const uint4* vecs16;           // fp16 shadow store: [supergroup][Dh chunks][128 vectors][8 halfs], scaled by 2^sv
     const uint4* vnorm;            // per row 8 halfs: the three fp16 terms of (1-eps)|v|^2 * 2^(2sv-g), then zeros; NaN for padding rows
@@ -30,10 +39,10 @@ struct TcParams {
     const uint32_t* list_qoff;     // CSR offsets into list_qlist
     const uint2* list_qlist;       // (query, probe rank)
     const uint32_t* item_off;      // nlist+1: prefix of work items per list
+    const TcItem* items;           // item_off[nlist] records (tc_expand_kernel)
     uint32_t nlist;
     uint32_t nq;
     uint32_t* work_counter;
-    const uint32_t* chunk_tiles;   // tiles per work item, chosen by tc_items_kernel
     uint32_t* gthr_bits;           // per query: upper bound of the exact k-th best distance (float bits)
     float* gtop;                   // per query: the k smallest filter values found so far by any CTA, descending
     uint32_t* glock;               // per query: spin lock serialising writers of gtop
@@ -88,6 +97,9 @@ void launch_tc_fill(const uint32_t* probes, size_t npairs, uint32_t nprobe, bool
                     const uint32_t* list_qoff, uint32_t* list_cur, uint2* list_qlist, cudaStream_t st);
 void launch_tc_items(const uint32_t* list_cnt, const uint32_t* list_ngroups, uint32_t nlist, unsigned long long* total,
                      uint32_t seed_tiles, uint32_t* chunk_out, uint32_t* items_per_list, cudaStream_t st);
+void launch_tc_expand(const uint32_t* list_cnt, const uint32_t* list_ngroups, const uint32_t* list_g0, const uint32_t* list_qoff,
+                      const uint32_t* item_off, const uint32_t* chunk_tiles, uint32_t nlist, uint32_t seed_tiles, TcItem* items,
+                      cudaStream_t st);
 void launch_scan_tc(const TcParams& p, cudaStream_t st);
 void launch_finalize(const FinalizeParams& p, cudaStream_t st);
 
