@@ -56,6 +56,20 @@ int vidx_set_limits(vidx_index* idx, uint64_t default_k, uint64_t default_n_prob
 int vidx_build(vidx_index* idx, const float* data, const uint64_t* ext_ids, const uint64_t* timestamps, uint64_t n,
                uint64_t seed, uint64_t nlist, uint64_t max_iters);
 
+/* VectorIndexer::build_from_vector_file (src/api.rs:149-186): the file is a concatenation of bincode-2
+ * `standard()` batches of (id u64, values Vec<f32>, metadata u64) (src/utils.rs:34-107); decoding stops
+ * silently at the first batch that does not decode, as read_vectors_from_file does.  An empty file or a
+ * record whose length differs from the index dimension is VIDX_ERR_INVALID_INPUT with the reference's
+ * messages; file id = external id, metadata = timestamp (0 -> now, vector_store.rs:36-40).
+ * vidx_vector_file_read: data == NULL only counts (n_out); otherwise fills data[n][dim], ids[n], meta[n]
+ * (cap = rows the buffers hold).  vidx_vector_file_write writes the same framing (batches of `batch`
+ * records, 0 = 1000; ids == NULL: 0..n-1, meta == NULL: 0). */
+int vidx_build_from_vector_file(vidx_index* idx, const char* vector_file, uint64_t seed, uint64_t nlist, uint64_t max_iters);
+int vidx_vector_file_read(const char* vector_file, uint64_t dim, uint64_t cap, float* data, uint64_t* ids, uint64_t* meta,
+                          uint64_t* n_out);
+int vidx_vector_file_write(const char* vector_file, const float* data, const uint64_t* ids, const uint64_t* meta, uint64_t n,
+                           uint64_t dim, uint64_t batch);
+
 /* The two halves of fit_with_paths, exposed separately (north_star "build/train, add"):
  * train  = mini-batch k-means + super-centroid shard assignment    src/ivf_index.rs:59-77, :103-109
  * add    = list assignment by the trained centroids, list build,

@@ -158,3 +158,27 @@ def test_partition_and_merge_equal_single_gpu(ffi, mode):
     # ids equal except where equal distances straddle ranks
     mism = oI.cpu().numpy() != I0
     assert mism.mean() < 0.01
+
+
+def test_faiss_style_adapter_sweep():
+    """The harness surface of bench/faiss_bench_official/vector_indexer_adapter.py:75-140 (`.d`, `.nprobe`,
+    `.search(xq, k)`) and its R@r (bench_all_ivf.py:336-350): recall is monotone in nprobe and 1.0 at nprobe = nlist."""
+    import vector_indexer_py as vip
+    from vector_indexer_py.faiss_adapter import VectorIndexerFaissAdapter, recall_at_ranks
+    xb, xq = bench_data(20000, 32, 200)
+    index = VectorIndexerFaissAdapter(vip.build(xb), k=10)
+    assert index.d == 32
+    index.nprobe = vip.suggest_nlist(len(xb))
+    _, gt = index.search(xq, 1)          # every list probed = exact nearest neighbour
+    brute = ((xq[:20, None, :].astype(np.float64) - xb[None, :, :].astype(np.float64)) ** 2).sum(-1).argmin(1)
+    assert np.array_equal(gt[:20, 0], brute)
+    prev = 0.0
+    for p in (1, 4, 16, 64):
+        index.nprobe = p
+        D, I = index.search(xq, 10)
+        assert D.shape == (200, 10) and I.dtype == np.int64
+        r = recall_at_ranks(I, gt, ranks=(1, 10))
+        assert r[10] >= prev - 1e-9
+        prev = r[10]
+    index.nprobe = 10 ** 6
+    assert recall_at_ranks(index.search(xq, 10)[1], gt, ranks=(1,))[1] == 1.0

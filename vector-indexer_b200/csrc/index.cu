@@ -812,6 +812,48 @@ int vidx_build(vidx_index* idx, const float* data, const uint64_t* ext_ids, cons
     });
 }
 
+// api.rs:149-186: read the file, reject an empty file and any record whose length differs from the index
+// dimension (InvalidInput, same messages), then build as from records (external id = file id, metadata = timestamp).
+int vidx_build_from_vector_file(vidx_index* idx, const char* vector_file, uint64_t seed, uint64_t nlist, uint64_t max_iters) {
+    return guarded([&] {
+        require(idx && vector_file, VIDX_ERR_INVALID_INPUT, "invalid vector_file path");
+        std::vector<uint64_t> ids, lens, meta;
+        std::vector<float> values;
+        read_vector_file(vector_file, ids, lens, values, meta);
+        require(!ids.empty(), VIDX_ERR_INVALID_INPUT, "no vectors in vector_file");
+        const uint64_t dim = idx->ix.dim;
+        for (size_t i = 0; i < lens.size(); i++)
+            if (lens[i] != dim)
+                throw ApiError(VIDX_ERR_INVALID_INPUT, "vector dimension mismatch at index " + std::to_string(i) + ": expected " +
+                                                           std::to_string(dim) + ", got " + std::to_string(lens[i]));
+        const int rc = vidx_build(idx, values.data(), ids.data(), meta.data(), ids.size(), seed, nlist, max_iters);
+        if (rc != VIDX_OK) throw ApiError(rc, vidx_last_error());
+    });
+}
+int vidx_vector_file_read(const char* vector_file, uint64_t dim, uint64_t cap, float* data, uint64_t* ids, uint64_t* meta, uint64_t* n_out) {
+    return guarded([&] {
+        require(vector_file && n_out, VIDX_ERR_INVALID_INPUT, "bad argument");
+        std::vector<uint64_t> vi, lens, vm;
+        std::vector<float> values;
+        read_vector_file(vector_file, vi, lens, values, vm);
+        *n_out = vi.size();
+        if (!data) return;  // count only
+        require(cap >= vi.size(), VIDX_ERR_INVALID_INPUT, "buffer too small");
+        for (size_t i = 0; i < lens.size(); i++)
+            require(lens[i] == dim, VIDX_ERR_INVALID_INPUT, "vector dimension mismatch in vector_file");
+        std::memcpy(data, values.data(), values.size() * 4);
+        if (ids) std::memcpy(ids, vi.data(), vi.size() * 8);
+        if (meta) std::memcpy(meta, vm.data(), vm.size() * 8);
+    });
+}
+int vidx_vector_file_write(const char* vector_file, const float* data, const uint64_t* ids, const uint64_t* meta, uint64_t n, uint64_t dim,
+                           uint64_t batch) {
+    return guarded([&] {
+        require(vector_file && (data || !n), VIDX_ERR_INVALID_INPUT, "bad argument");
+        write_vector_file(vector_file, data, ids, meta, n, dim, batch);
+    });
+}
+
 int vidx_train(vidx_index* idx, const float* data, uint64_t n, uint64_t seed, uint64_t nlist, uint64_t max_iters) {
     return guarded([&] {
         require(idx, VIDX_ERR_INVALID_INPUT, "idx is NULL");

@@ -96,5 +96,10 @@ struct LoadedIndex {
 void save_index(const Index& ix, const std::vector<float>& host_vectors, const std::string& index_dir,
                 const std::string& shards_dir);
 void load_index_files(const std::string& index_dir, const std::string& shards_dir, uint32_t expect_dim, LoadedIndex& out);
+// vector files (src/utils.rs:34-107): concatenated bincode batches of (id, values, metadata)
+void read_vector_file(const std::string& path, std::vector<uint64_t>& ids, std::vector<uint64_t>& lens, std::vector<float>& values,
+                      std::vector<uint64_t>& meta);
+void write_vector_file(const std::string& path, const float* data, const uint64_t* ids, const uint64_t* meta, uint64_t n, uint64_t dim,
+                       uint64_t batch);
 
 }  // namespace vidx

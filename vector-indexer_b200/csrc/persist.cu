@@ -257,4 +257,66 @@ void load_index_files(const std::string& index_dir, const std::string& shards_di
     }
 }
 
+// ---- vector files (src/utils.rs:34-107) ----------------------------------------------------
+// A vector file is a concatenation of bincode-2 `standard()` encodings of Vec<(u64, Vec<f32>, u64)> (batches of 1000 in
+// generate_test_vectors_parallel, utils.rs:34-79): varint length, then per record varint id, varint vector length, f32 LE
+// values, varint metadata.  read_vectors_from_file (utils.rs:82-107) decodes batch after batch and stops -- silently -- at the
+// first batch that fails to decode.
+void read_vector_file(const std::string& path, std::vector<uint64_t>& ids, std::vector<uint64_t>& lens, std::vector<float>& values,
+                      std::vector<uint64_t>& meta) {
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) throw ApiError(VIDX_ERR_OTHER, "read_vectors_from_file: " + path + ": " + strerror(errno));
+    std::vector<uint8_t> buf;
+    uint8_t tmp[1 << 16];
+    size_t got;
+    while ((got = fread(tmp, 1, sizeof(tmp), f)) > 0) buf.insert(buf.end(), tmp, tmp + got);
+    fclose(f);
+    Reader r{buf.data(), buf.size()};
+    while (r.pos < r.n) {
+        const size_t n_ids = ids.size(), n_vals = values.size();
+        try {
+            const uint64_t cnt = r.varint();
+            for (uint64_t i = 0; i < cnt; i++) {
+                const uint64_t id = r.varint();
+                const uint64_t len = r.varint();
+                r.need(len * 4);
+                for (uint64_t j = 0; j < len; j++) values.push_back(r.f32());
+                const uint64_t m = r.varint();
+                ids.push_back(id);
+                lens.push_back(len);
+                meta.push_back(m);
+            }
+        } catch (const ApiError&) {  // Err(_) => break: drop the partial batch
+            ids.resize(n_ids);
+            lens.resize(n_ids);
+            meta.resize(n_ids);
+            values.resize(n_vals);
+            break;
+        }
+    }
+}
+void write_vector_file(const std::string& path, const float* data, const uint64_t* ids, const uint64_t* meta, uint64_t n, uint64_t dim,
+                       uint64_t batch) {
+    FILE* f = fopen(path.c_str(), "wb");
+    if (!f) throw ApiError(VIDX_ERR_OTHER, "cannot create " + path + ": " + strerror(errno));
+    if (!batch) batch = 1000;
+    for (uint64_t b0 = 0; b0 < n; b0 += batch) {
+        const uint64_t b1 = std::min(n, b0 + batch);
+        std::vector<uint8_t> o;
+        put_varint(o, b1 - b0);
+        for (uint64_t i = b0; i < b1; i++) {
+            put_varint(o, ids ? ids[i] : i);
+            put_varint(o, dim);
+            const uint8_t* pv = reinterpret_cast<const uint8_t*>(data + i * dim);
+            o.insert(o.end(), pv, pv + dim * 4);
+            put_varint(o, meta ? meta[i] : 0);
+        }
+        if (fwrite(o.data(), 1, o.size(), f) != o.size()) {
+            fclose(f);
+            throw ApiError(VIDX_ERR_OTHER, "short write to " + path);
+        }
+    }
+    fclose(f);
+}
+
 }  // namespace vidx

@@ -51,6 +51,9 @@ _SIGS = {
     "vidx_last_error": (C.c_char_p, []),
     "vidx_set_limits": (i32, [vp, u64, u64, u64, u64]),
     "vidx_build": (i32, [vp, f32p, u64p, u64p, u64, u64, u64, u64]),
+    "vidx_build_from_vector_file": (i32, [vp, C.c_char_p, u64, u64, u64]),
+    "vidx_vector_file_read": (i32, [C.c_char_p, u64, u64, f32p, u64p, u64p, u64p]),
+    "vidx_vector_file_write": (i32, [C.c_char_p, f32p, u64p, u64p, u64, u64, u64]),
     "vidx_train": (i32, [vp, f32p, u64, u64, u64, u64]),
     "vidx_add": (i32, [vp, f32p, u64p, u64p, u64]),
     "vidx_build_from_labels": (i32, [vp, f32p, u64p, u64, f32p, u64, u64p, u64p]),
@@ -156,6 +159,11 @@ class Index:
         e = None if ext_ids is None else np.ascontiguousarray(ext_ids, dtype=np.uint64)
         t = None if timestamps is None else np.ascontiguousarray(timestamps, dtype=np.uint64)
         check(lib().vidx_build(self.h, _f(data), _u(e), _u(t), n, seed, nlist, max_iters))
+        return self
+
+    def build_from_vector_file(self, path, seed=42, nlist=0, max_iters=0):
+        """VectorIndexer::build_from_vector_file (src/api.rs:149-186)."""
+        check(lib().vidx_build_from_vector_file(self.h, os.fsencode(path), seed, nlist, max_iters))
         return self
 
     def train(self, data, seed=42, nlist=0, max_iters=0):
@@ -298,6 +306,25 @@ class Index:
         s = SearchStats()
         check(lib().vidx_get_search_stats(self.h, C.byref(s)))
         return s.asdict()
+
+
+def write_vector_file(path, data, ids=None, meta=None, batch=1000):
+    """The framing of generate_test_vectors_parallel (src/utils.rs:34-79) with caller-provided values."""
+    data = _c32(data)
+    i = None if ids is None else np.ascontiguousarray(ids, dtype=np.uint64)
+    m = None if meta is None else np.ascontiguousarray(meta, dtype=np.uint64)
+    check(lib().vidx_vector_file_write(os.fsencode(path), _f(data), _u(i), _u(m), data.shape[0], data.shape[1], batch))
+
+
+def read_vector_file(path, dim):
+    """read_vectors_from_file (src/utils.rs:82-107) -> (ids, data[n, dim], metadata)."""
+    n = C.c_uint64(0)
+    check(lib().vidx_vector_file_read(os.fsencode(path), dim, 0, None, None, None, C.byref(n)))
+    data = np.zeros((n.value, dim), np.float32)
+    ids = np.zeros(n.value, np.uint64)
+    meta = np.zeros(n.value, np.uint64)
+    check(lib().vidx_vector_file_read(os.fsencode(path), dim, n.value, _f(data), _u(ids), _u(meta), C.byref(n)))
+    return ids, data, meta
 
 
 def partition_shards(shard_sizes, world):
