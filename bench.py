@@ -252,14 +252,33 @@ def run_ours(args):
     recall = next((c["recall_at_10"] for c in curve if c["nprobe"] == nprobe), None)
 
     # ---- distributed layout -----------------------------------------------------------------
-    if world > 1:
+    # index (default, north_star 4): every rank owns part of the index, queries are replicated, the per-rank top-k are
+    #   all-gathered and merged.  queries: every rank keeps the whole index (it fits: 0.8 GB) and answers its slice of the
+    #   batch; the slices are all-gathered.  Both are strong scaling: the 10 k-query batch is the fixed total work.
+    split_queries = world > 1 and args.multi == "queries"
+    q_lo, q_hi = 0, nq
+    if world > 1 and not split_queries:
         ix.set_partition(rank, world)
         g_D = torch.empty((world, nq, k), dtype=torch.float32, device="cuda")
         g_I = torch.empty((world, nq, k), dtype=torch.int64, device="cuda")
         m_D = torch.empty((nq, k), dtype=torch.float32, device="cuda")
         m_I = torch.empty((nq, k), dtype=torch.int64, device="cuda")
+    if split_queries:
+        per = (nq + world - 1) // world
+        q_lo, q_hi = min(nq, rank * per), min(nq, (rank + 1) * per)
+        s_D = torch.full((per, k), float("inf"), dtype=torch.float32, device="cuda")
+        s_I = torch.full((per, k), -1, dtype=torch.int64, device="cuda")
+        a_D = torch.empty((world * per, k), dtype=torch.float32, device="cuda")
+        a_I = torch.empty((world * per, k), dtype=torch.int64, device="cuda")
+        m_D, m_I = a_D[:nq], a_I[:nq]
 
     def step_device():
+        if split_queries:
+            if q_hi > q_lo:
+                ix.search_device(d_xq[q_lo:q_hi].data_ptr(), q_hi - q_lo, k, nprobe, s_D.data_ptr(), s_I.data_ptr(), stream)
+            dist.all_gather_into_tensor(a_D, s_D)
+            dist.all_gather_into_tensor(a_I, s_I)
+            return
         search_dev(nprobe)
         if world > 1:
             dist.all_gather_into_tensor(g_D, d_D)
@@ -349,7 +368,7 @@ def run_ours(args):
             acc = s if acc is None else {kk: (acc[kk] + s[kk] if kk.startswith("ms_") else s[kk]) for kk in s}
         return {kk: (acc[kk] / reps if kk.startswith("ms_") else acc[kk]) for kk in acc}
 
-    stage = staged(nq, nprobe)
+    stage = staged(q_hi - q_lo if split_queries else nq, nprobe)
     tc_used = stage["n_tc_items"] > 0
     tc_peak = peaks["bf16_tflops"]  # the filter runs tcgen05 kind::f16 (same rate as bf16): the measured dense peak
     if tc_used:
@@ -412,8 +431,10 @@ def run_ours(args):
                 "config": {"workload": "configs[1]: 1Mx128 fp32 nlist=1024 nq=10k k=10", **w, "nprobe": nprobe,
                            "recall_at_10": final_recall, "recall_curve": curve, "nlist_nonempty": ix.nlist,
                            "l2": "inputs larger than L2 (index 512 MB)", "index_build_s": build_s,
-                           "parallelism": (f"{ix.partition_kind} over {world} GPUs, queries replicated, NCCL all-gather of per-GPU "
-                                           f"top-k + device merge") if world > 1 else "1 GPU"},
+                           "parallelism": ("1 GPU" if world == 1 else
+                                           f"index replicated, batch split over {world} GPUs, NCCL all-gather of the slices" if split_queries
+                                           else f"{ix.partition_kind} over {world} GPUs, queries replicated, NCCL all-gather of per-GPU "
+                                                f"top-k + device merge")},
                 "e2e": {"value": nq * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(xq.nbytes),
                         "d2h_bytes_per_step": int(nq * k * 12), "ms_per_step": 1e3 * e2e_s / args.steps},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_hbm": roofline_hbm,
@@ -438,6 +459,8 @@ def main():
     ap.add_argument("--nprobe", type=int, default=0, help="0 = smallest power of two with recall@10 >= 0.9")
     ap.add_argument("--full-curve", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--multi", default="index", choices=["index", "queries"],
+                    help="N > 1: partition the index over the GPUs (default, north_star) or replicate it and split the batch")
     ap.add_argument("--profile-window", action="store_true",
                     help="bracket one warmed-up step with cudaProfilerStart/Stop (for ncu --profile-from-start off)")
     args = ap.parse_args()
