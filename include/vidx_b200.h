@@ -206,6 +206,10 @@ int vidx_set_profiling(vidx_index* idx, int enabled);
  * (D padded to a multiple of 8 floats, D <= 128, k <= 32), 1 = exact FP32 kernels only.  Results are
  * bit-identical either way. */
 int vidx_set_scan_mode(vidx_index* idx, int mode);
+/* Coarse quantization (ivf_index.rs:205-220): 0 = auto (today: the exact FP32 kernels -- the tensor-core filter measured
+ * no faster up to nlist = 12 639), 1 = exact kernels only, 2 = tensor-core filter + exact re-check whenever
+ * it applies (n_probe <= 32).  Probe lists and distances are identical in every mode. */
+int vidx_set_coarse_mode(vidx_index* idx, int mode);
 int vidx_get_search_stats(vidx_index* idx, vidx_search_stats* out);
 /* Total kernels launched by this library in this process (bench.py's gpu_launches). */
 uint64_t vidx_kernel_launch_count(void);

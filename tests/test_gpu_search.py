@@ -204,3 +204,22 @@ def test_tensor_core_filter_never_drops_a_true_neighbour_on_hard_data(oracle, ff
     xq = (xb[rng.choice(30000, 400, replace=False)] + rng.standard_normal((400, 64)).astype(np.float32) * 0.001).astype(np.float32)
     oix, gix = make_pair(oracle, ffi, xb, 16)
     check_search(oix, gix, xq, 10, 8)
+
+
+@pytest.mark.parametrize("d,nlist,nprobe", [(64, 300, 20), (128, 2500, 32), (30, 700, 1), (200, 4096, 8)])
+def test_coarse_tensor_core_filter_equals_exact_coarse(oracle, ffi, d, nlist, nprobe):
+    # ivf_index.rs:205-220 through the fp16 filter + exact re-check: identical probe lists and bit-identical distances
+    xb, xq = bench_data(20000, d, 600, seed=nlist)
+    oix, gix = make_pair(oracle, ffi, xb, nlist)
+    gix.set_coarse_mode(2)
+    lists, dists = gix.coarse_probes(xq, nprobe)
+    gix.set_coarse_mode(1)
+    lists_e, dists_e = gix.coarse_probes(xq, nprobe)
+    assert np.array_equal(lists, lists_e) and np.array_equal(dists.view(np.uint32), dists_e.view(np.uint32))
+    for i in range(0, len(xq), 37):
+        lo, do = oix.probes(xq[i], nprobe)
+        assert np.array_equal(lists[i], lo) and np.array_equal(dists[i].view(np.uint32), do.view(np.uint32))
+    gix.set_coarse_mode(2)
+    D, I = gix.search(xq, 10, nprobe)
+    Do, Io = oix.search_batch(xq, 10, nprobe, nthreads=0)
+    assert np.array_equal(D.view(np.uint32), Do.view(np.uint32)) and np.array_equal(I, Io)

@@ -185,6 +185,43 @@ void Index::build_lists(const float* d_data, uint64_t n, const uint32_t* labels,
         h2d(d_map.as<uint32_t>(), map.data(), map.size(), stream);
         d_cents.reserve(std::max<size_t>(map.size(), 1) * Dq * 16);
         launch_interleave(d_c.as<float>(), (int)dim, Dq, d_map.as<uint32_t>(), map.size(), d_cents.as<float4>(), stream);
+        // fp16 shadow + norm terms of the centroid table (coarse quantization on tensor cores)
+        const size_t crow = map.size();
+        const int Dh = tc_dh((int)dim);
+        DevBuf d_cn, d_cstats;
+        d_cn.reserve(std::max<size_t>(crow, 1) * 4);
+        d_cstats.reserve(16);
+        VIDX_CUDA(cudaMemsetAsync(d_cstats.p, 0, 16, stream));
+        launch_row_norms(d_cents.as<float4>(), Dq, d_map.as<uint32_t>(), crow, d_cn.as<float>(), d_cstats.as<uint32_t>(), stream);
+        std::vector<float> cn(crow);
+        d2h_sync(cn.data(), d_cn.as<float>(), crow, stream);
+        uint32_t cb = 0;
+        d2h_sync(&cb, d_cstats.as<uint32_t>(), 1, stream);
+        memcpy(&ctab.vmax, &cb, 4);
+        ctab.vn_max = 0.0f;
+        for (float v : cn) ctab.vn_max = std::max(ctab.vn_max, v);
+        int e = 0;
+        if (ctab.vmax > 0.0f) frexpf(ctab.vmax, &e);
+        ctab.sv = ctab.vmax > 0.0f ? 7 - e : 0;
+        ctab.g = 0;
+        while ((16 * (Dh / 2)) > (2 << ctab.g)) ctab.g++;
+        ctab.ok = nlist > 0 && std::isfinite(ctab.vmax) && std::isfinite(ctab.vn_max) && ctab.sv > -40 && ctab.sv < 40;
+        if (ctab.ok) {
+            ctab.vecs16.reserve(std::max<size_t>(crow, 1) * Dh * 16);
+            ctab.vnorm.reserve((std::max<size_t>(crow, 1) + 128) * 16);
+            launch_convert16(d_cents.as<float4>(), Dq, Dh, d_map.as<uint32_t>(), crow, d_cn.as<float>(), ctab.sv, ctab.g,
+                             ctab.vecs16.as<uint4>(), ctab.vnorm.as<uint4>(), stream);
+            const uint32_t g0 = 0, ng = ncgroups, ln = (uint32_t)nlist;
+            const uint2 seg = make_uint2(0, 1);
+            ctab.list_g0.reserve(8);
+            ctab.list_ng.reserve(8);
+            ctab.list_len.reserve(8);
+            ctab.list_seg.reserve(16);
+            h2d(ctab.list_g0.as<uint32_t>(), &g0, 1, stream);
+            h2d(ctab.list_ng.as<uint32_t>(), &ng, 1, stream);
+            h2d(ctab.list_len.as<uint32_t>(), &ln, 1, stream);
+            h2d(ctab.list_seg.as<uint2>(), &seg, 1, stream);
+        }
         VIDX_CUDA(cudaStreamSynchronize(stream));
     }
     d_segs.reserve(std::max<size_t>(segs.size(), 1) * sizeof(SegDesc));
@@ -339,6 +376,7 @@ void Index::delete_workspace() {
     ws = nullptr;
 }
 
+constexpr uint64_t kCoarseTcMinLists = 1ull << 20;  // auto mode: measured slower than the exact FP32 stage up to nlist = 12 639
 constexpr uint32_t kSeedTiles = 4;  // seeding pass: first 512 vectors of each query's nearest list
 
 // stats: distinct probed lists -> algorithmic bytes; (query, list) pairs -> logical bytes / flops
@@ -351,6 +389,118 @@ __global__ void list_stats_kernel(const uint32_t* __restrict__ list_cnt, const u
     atomicAdd(&out[0], (unsigned long long)list_len[l]);
     atomicAdd(&out[1], (unsigned long long)list_len[l] * c);
     atomicAdd(&out[2], (unsigned long long)c);
+}
+
+// Coarse quantization on tensor cores: the centroid table is a one-list index that every query "probes"; the same fp16
+// filter + exact re-check as the list scan yields each query's n_probe nearest centroids in the reference's order
+// (ascending distance, then list id = the stable sort of ivf_index.rs:215-220), with the reference's exact distances.
+struct CoarseWs {
+    DevBuf probes0, list_cnt, list_cur, list_qoff, list_qlist, items_per_list, item_off, items, list_cnt0, list_cur0, list_qoff0, list_qlist0,
+        items_per_list0, item_off0, items0, qnorm, gthr, cand_cnt, overflow, cand, gtop, glock, tcscale, counters, scan_tmp, dist_tmp;
+};
+void Index::coarse_tc(const float4* xq4, uint32_t nqb, uint32_t np, uint32_t* d_probes, float* d_probe_dist, cudaStream_t st) {
+    static thread_local CoarseWs* cws = nullptr;  // per host thread, like the search workspace's use under the handle mutex
+    if (!cws) cws = new CoarseWs();
+    CoarseWs& w = *cws;
+    const int Dq = dq();
+    const uint32_t k = np;
+    const uint32_t capq = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(nlist, 32), 4096);
+    w.probes0.reserve((size_t)nqb * 4);
+    w.counters.reserve(64);
+    w.scan_tmp.reserve(exclusive_scan_tmp_entries(4) * 4 + 64);
+    for (DevBuf* b : {&w.list_cnt, &w.list_cur, &w.list_qoff, &w.items_per_list, &w.item_off, &w.list_cnt0, &w.list_cur0, &w.list_qoff0,
+                      &w.items_per_list0, &w.item_off0})
+        b->reserve(16);
+    w.list_qlist.reserve((size_t)nqb * 8);
+    w.list_qlist0.reserve((size_t)nqb * 8);
+    w.qnorm.reserve((size_t)nqb * 4);
+    w.gthr.reserve((size_t)nqb * 4);
+    w.cand_cnt.reserve((size_t)nqb * 4);
+    w.overflow.reserve((size_t)nqb * 4);
+    w.cand.reserve((size_t)nqb * capq * 8);
+    w.gtop.reserve((size_t)nqb * k * 4);
+    w.glock.reserve((size_t)nqb * 8);
+    w.tcscale.reserve(64);
+    w.dist_tmp.reserve((size_t)nqb * k * 4);
+    const uint64_t tiles = ncgroups / 4 + 1;
+    w.items.reserve(((nqb / 128 + 1) * tiles / 8 + 8 * 160 + nqb / 128 + 64) * sizeof(TcItem));
+    w.items0.reserve(((uint64_t)nqb / 32 + 64) * sizeof(TcItem));
+    uint32_t* counters = w.counters.as<uint32_t>();
+    VIDX_CUDA(cudaMemsetAsync(w.probes0.p, 0, (size_t)nqb * 4, st));
+    VIDX_CUDA(cudaMemsetAsync(w.counters.p, 0, 64, st));
+    VIDX_CUDA(cudaMemsetAsync(w.tcscale.p, 0, 64, st));
+    for (DevBuf* b : {&w.list_cnt, &w.list_cur, &w.list_cnt0, &w.list_cur0}) VIDX_CUDA(cudaMemsetAsync(b->p, 0, 16, st));
+    const uint2* lseg = ctab.list_seg.as<uint2>();
+    launch_query_norms(xq4, Dq, nqb, k, w.qnorm.as<float>(), w.gthr.as<uint32_t>(), w.cand_cnt.as<uint32_t>(), w.overflow.as<uint32_t>(),
+                       w.gtop.as<float>(), w.glock.as<uint32_t>(), w.tcscale.as<uint32_t>(), st);
+    launch_tc_scale(w.tcscale.as<uint32_t>(), ctab.sv, ctab.g, (int)dim, ctab.vmax, ctab.vn_max,
+                    reinterpret_cast<TcScale*>(w.tcscale.as<unsigned char>() + 16), st);
+    // main grouping and the seeding grouping coincide here (one list, every pair has rank 0)
+    launch_tc_count(w.probes0.as<uint32_t>(), nqb, 1, false, lseg, w.list_cnt.as<uint32_t>(), st);
+    exclusive_scan_u32(w.list_cnt.as<uint32_t>(), w.list_qoff.as<uint32_t>(), 1, w.scan_tmp.as<uint32_t>(), st);
+    launch_tc_fill(w.probes0.as<uint32_t>(), nqb, 1, false, lseg, w.list_qoff.as<uint32_t>(), w.list_cur.as<uint32_t>(), w.list_qlist.as<uint2>(), st);
+    launch_tc_items(w.list_cnt.as<uint32_t>(), ctab.list_ng.as<uint32_t>(), 1, reinterpret_cast<unsigned long long*>(counters + 12), 0, counters + 10,
+                    w.items_per_list.as<uint32_t>(), st);
+    exclusive_scan_u32(w.items_per_list.as<uint32_t>(), w.item_off.as<uint32_t>(), 1, w.scan_tmp.as<uint32_t>(), st);
+    launch_tc_expand(w.list_cnt.as<uint32_t>(), ctab.list_ng.as<uint32_t>(), ctab.list_g0.as<uint32_t>(), w.list_qoff.as<uint32_t>(),
+                     w.item_off.as<uint32_t>(), counters + 10, 1, 0, w.items.as<TcItem>(), st);
+    launch_tc_items(w.list_cnt.as<uint32_t>(), ctab.list_ng.as<uint32_t>(), 1, nullptr, kSeedTiles, counters + 11, w.items_per_list0.as<uint32_t>(), st);
+    exclusive_scan_u32(w.items_per_list0.as<uint32_t>(), w.item_off0.as<uint32_t>(), 1, w.scan_tmp.as<uint32_t>(), st);
+    launch_tc_expand(w.list_cnt.as<uint32_t>(), ctab.list_ng.as<uint32_t>(), ctab.list_g0.as<uint32_t>(), w.list_qoff.as<uint32_t>(),
+                     w.item_off0.as<uint32_t>(), counters + 11, 1, kSeedTiles, w.items0.as<TcItem>(), st);
+    TcParams tp{};
+    tp.vecs16 = ctab.vecs16.as<uint4>();
+    tp.vnorm = ctab.vnorm.as<uint4>();
+    tp.Dh = tc_dh((int)dim);
+    tp.Dq = Dq;
+    tp.scale = reinterpret_cast<const TcScale*>(w.tcscale.as<unsigned char>() + 16);
+    tp.nq = nqb;
+    tp.xq4 = xq4;
+    tp.qnorm = w.qnorm.as<float>();
+    tp.list_g0 = ctab.list_g0.as<uint32_t>();
+    tp.list_ngroups = ctab.list_ng.as<uint32_t>();
+    tp.nlist = 1;
+    tp.gthr_bits = w.gthr.as<uint32_t>();
+    tp.gtop = w.gtop.as<float>();
+    tp.glock = w.glock.as<uint32_t>();
+    tp.gver = w.glock.as<uint32_t>() + nqb;
+    tp.cand = w.cand.as<unsigned long long>();
+    tp.cand_cnt = w.cand_cnt.as<uint32_t>();
+    tp.overflow = w.overflow.as<uint32_t>();
+    tp.capq = capq;
+    tp.k = k;
+    tp.vn_max = ctab.vn_max;
+    tp.seed_tiles = kSeedTiles;
+    tp.list_cnt = w.list_cnt.as<uint32_t>();
+    tp.list_qoff = w.list_qoff.as<uint32_t>();
+    tp.list_qlist = w.list_qlist.as<uint2>();
+    tp.mode = 1;
+    tp.item_off = w.item_off0.as<uint32_t>();
+    tp.items = w.items0.as<TcItem>();
+    tp.work_counter = counters + 9;
+    launch_scan_tc(tp, st);
+    tp.mode = 0;
+    tp.item_off = w.item_off.as<uint32_t>();
+    tp.items = w.items.as<TcItem>();
+    tp.work_counter = counters + 8;
+    launch_scan_tc(tp, st);
+    FinalizeParams fp{};
+    fp.nq = nqb;
+    fp.nprobe = 1;
+    fp.k = k;
+    fp.kout = k;
+    fp.Dq = Dq;
+    fp.vecs = d_cents.as<float4>();
+    fp.xq4 = xq4;
+    fp.cand = w.cand.as<unsigned long long>();
+    fp.cand_cnt = w.cand_cnt.as<uint32_t>();
+    fp.overflow = w.overflow.as<uint32_t>();
+    fp.capq = capq;
+    fp.brute_rows = (uint32_t)nlist;
+    fp.D = d_probe_dist ? d_probe_dist : w.dist_tmp.as<float>();
+    fp.I = nullptr;
+    fp.out_rows = d_probes;
+    launch_finalize(fp, st);
 }
 
 void Index::search_device(const float* d_xq, uint64_t nq, uint64_t k_req, uint64_t nprobe_req, float* d_D, int64_t* d_I,
@@ -413,19 +563,28 @@ void Index::search_device(const float* d_xq, uint64_t nq, uint64_t k_req, uint64
         } else {
             xq4 = reinterpret_cast<const float4*>(xq);
         }
-        // K1: coarse distances
+        // K1 + K2: coarse distances and probe selection (stable ascending by (distance, list id)): the tensor-core filter +
+        // exact re-check when the table is large enough to pay for its launches, else exact FP32 distances + radix select.
+        // (A query whose survivor buffer overflows -- more than 4096 centroids inside its bound -- is answered by an exact
+        // check of every centroid inside finalize_kernel.)
         if (profiling) VIDX_CUDA(cudaEventRecord(ev[0], st));
-        w.dist.reserve((size_t)nqb * ldc * 4);
-        launch_coarse_dist(d_cents.as<float4>(), (int)ncgroups, Dq, xq4, nqb, w.dist.as<float>(), ldc, st);
-        if (profiling) VIDX_CUDA(cudaEventRecord(ev[1], st));
-        // K2: probe selection (stable ascending by (distance, list id))
         w.probes.reserve((size_t)nqb * np * 4);
         float* pd = nullptr;
         if (coarse_only && d_probe_dist_out) {
             w.sel_val.reserve((size_t)nqb * np * 4);
             pd = w.sel_val.as<float>();
         }
-        launch_select_topk(w.dist.as<float>(), nullptr, nullptr, ldc, (uint32_t)nlist, nqb, np, w.probes.as<uint32_t>(), pd, st);
+        const bool coarse_filter = coarse_mode != 1 && scan_mode != 1 && ctab.ok && np <= 32 && tc_supported((int)dim, np) &&
+                                   (coarse_mode == 2 || nlist >= kCoarseTcMinLists);
+        if (coarse_filter) {
+            coarse_tc(xq4, nqb, np, w.probes.as<uint32_t>(), pd, st);
+            if (profiling) VIDX_CUDA(cudaEventRecord(ev[1], st));
+        } else {
+            w.dist.reserve((size_t)nqb * ldc * 4);
+            launch_coarse_dist(d_cents.as<float4>(), (int)ncgroups, Dq, xq4, nqb, w.dist.as<float>(), ldc, st);
+            if (profiling) VIDX_CUDA(cudaEventRecord(ev[1], st));
+            launch_select_topk(w.dist.as<float>(), nullptr, nullptr, ldc, (uint32_t)nlist, nqb, np, w.probes.as<uint32_t>(), pd, st);
+        }
         if (profiling) VIDX_CUDA(cudaEventRecord(ev[2], st));
         if (coarse_only) {
             // caller's stride is nprobe_req; columns beyond np are padded
@@ -1256,6 +1415,13 @@ int vidx_set_profiling(vidx_index* idx, int enabled) {
     return guarded([&] {
         require(idx, VIDX_ERR_INVALID_INPUT, "idx is NULL");
         idx->ix.profiling = enabled != 0;
+    });
+}
+int vidx_set_coarse_mode(vidx_index* idx, int mode) {
+    return guarded([&] {
+        require(idx && mode >= 0 && mode <= 2, VIDX_ERR_INVALID_INPUT, "coarse mode must be 0 (auto), 1 (exact) or 2 (filter)");
+        std::lock_guard<std::mutex> lk(idx->mu);
+        idx->ix.coarse_mode = mode;
     });
 }
 int vidx_set_scan_mode(vidx_index* idx, int mode) {

@@ -56,6 +56,16 @@ struct Index {
     float vmax = 0.0f;     // max |component| over the stored rows
     int tc_sv = 0, tc_g = 0;  // fp16 shadow store: vectors scaled by 2^sv, norm terms by 2^(2sv-g)
     bool tc_ok = false;    // the shadow store exists (finite data of sane magnitude)
+    // The centroid table as a one-list index of its own: coarse quantization = the same tensor-core filter + exact
+    // re-check, top-n_probe by (distance, list id).
+    struct CoarseTable {
+        DevBuf vecs16, vnorm, list_g0, list_ng, list_len, list_seg;
+        float vn_max = 0.0f, vmax = 0.0f;
+        int sv = 0, g = 0;
+        bool ok = false;
+    } ctab;
+    int coarse_mode = 0;   // 0 = tensor-core filter when n_probe <= 32 and nlist is large enough, 1 = exact kernels only, 2 = filter whenever possible
+    void coarse_tc(const float4* xq4, uint32_t nqb, uint32_t np, uint32_t* d_probes, float* d_probe_dist, cudaStream_t st);
     int scan_mode = 0;     // 0 = tensor-core pre-filter when the shape allows, 1 = exact kernels only
     DevBuf io_xq, io_D, io_I, io_rows, io_V;
     struct Workspace;

@@ -1064,12 +1064,16 @@ __global__ void finalize_kernel(FinalizeParams p) {
     if (p.cand) {
         uint32_t n = p.cand_cnt[q];
         bool ovf = p.overflow[q] != 0 || n > p.capq;
-        if (!ovf) {
+        // one-list tables (coarse quantization) have no exact kernels behind them: a query the filter handed back
+        // (a batch that cannot be scaled into fp16 range) is answered here by checking every row exactly
+        const bool brute = ovf && p.brute_rows != 0;
+        if (brute) n = p.brute_rows;
+        if (!ovf || brute) {
             const float4* q4 = p.xq4 + (size_t)q * p.Dq;
             for (uint32_t base = 0; base < n; base += 32) {
                 uint32_t i = base + lane;
                 bool have = i < n;
-                unsigned long long key = have ? p.cand[(size_t)q * p.capq + i] : ~0ull;
+                unsigned long long key = have ? (brute ? (unsigned long long)i : p.cand[(size_t)q * p.capq + i]) : ~0ull;
                 float d = have ? exact_row_distance(p.vecs, p.Dq, (uint32_t)key, q4) : __int_as_float(0x7f800000);
                 float td = __shfl_sync(kFull, fd, k - 1);
                 unsigned long long tk = __shfl_sync(kFull, fk, k - 1);
@@ -1116,7 +1120,7 @@ __global__ void finalize_kernel(FinalizeParams p) {
         bool ok = fk != ~0ull;
         uint32_t row = (uint32_t)fk;
         p.D[o] = ok ? fd : __int_as_float(0x7f800000);
-        p.I[o] = ok ? (int64_t)p.row_ext[row] : -1;
+        if (p.I) p.I[o] = ok ? (p.row_ext ? (int64_t)p.row_ext[row] : (int64_t)row) : -1;
         if (p.out_rows) p.out_rows[o] = ok ? row : kNoRow;
     }
 }

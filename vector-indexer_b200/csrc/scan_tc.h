@@ -68,6 +68,7 @@ struct FinalizeParams {
     const uint32_t* cand_cnt;
     const uint32_t* overflow;
     uint32_t capq;
+    uint32_t brute_rows;  // != 0: a query flagged in `overflow` is answered by checking rows 0..brute_rows-1 exactly (one-list tables)
     // exact-path slots (slot_off == nullptr: none)
     const uint32_t* slot_off;
     const float* slot_d;

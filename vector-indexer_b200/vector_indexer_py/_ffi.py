@@ -80,6 +80,7 @@ _SIGS = {
     "vidx_calculate_max_iterations": (u64, [u64]),
     "vidx_save": (i32, [vp, C.c_char_p, C.c_char_p]),
     "vidx_load": (i32, [vp, C.c_char_p, C.c_char_p]),
+    "vidx_set_coarse_mode": (i32, [vp, i32]),
     "vidx_set_partition": (i32, [vp, i32, i32]),
     "vidx_set_partition_mode": (i32, [vp, i32]),
     "vidx_get_partition_kind": (i32, [vp]),
@@ -297,6 +298,10 @@ class Index:
 
     def set_profiling(self, on=True):
         check(lib().vidx_set_profiling(self.h, 1 if on else 0))
+
+    def set_coarse_mode(self, mode):
+        """0 = auto, 1 = exact FP32 coarse stage, 2 = tensor-core filter whenever it applies."""
+        check(lib().vidx_set_coarse_mode(self.h, mode))
 
     def set_scan_mode(self, mode):
         """0 = tensor-core pre-filter + exact re-check (default), 1 = exact kernels only."""
