@@ -22,7 +22,7 @@
 // The index keeps an fp16 SHADOW of the vectors for this filter (same supergroup layout, 8 dims per 16-byte
 // chunk); the fp32 store stays the source of every distance that is returned.
 //
-// Kernel anatomy (one CTA per SM, persistent, 13 warps; a work item = 128 queries x up to 128 list tiles):
+// Kernel anatomy (one CTA per SM, persistent, 14 warps; a work item = 128 queries x up to 128 list tiles):
 //   warps 0, 12 producers : one cp.async.bulk (1-D TMA) per K-slice of a 128-vector tile -- the HBM layout keeps
 //                      a tile's chunks contiguous, so a list chunk is ONE linear stream -- into a ring of 32 KB
 //                      stages, plus the tile's norm terms; completion on mbarriers (complete_tx::bytes)
@@ -35,7 +35,8 @@
 //   warps 2-9 epilogue: tcgen05.ld the 128x128 fp32 accumulator tile from TMEM (4 stages, 512 columns); two warps
 //                      per TMEM lane quarter, each thread owns one query row and 64 of the 128 columns: one 3-input
 //                      min per three columns, one branch per 32; hits go to a shared-memory queue
-//   warp 11 selector : owns the per-row top-k sets and bounds, appends survivors to the per-query lists
+//   warps 11, 13 selectors: each owns half of the query rows: their top-k sets and bounds, the hit queue of those rows,
+//                      staged appends of survivors to the per-query lists
 // Accumulators never leave the SM; HBM sees each list tile once per 128-query tile.
 #include <cuda_fp16.h>
 
@@ -43,8 +44,9 @@
 
 namespace vidx {
 
-constexpr int kTcThreads = 416;       // warps 0, 12 producers (even / odd K-slices), warps 1, 10 MMA (even / odd tiles), warps 2-9 epilogue, warp 11 selector
+constexpr int kTcThreads = 448;       // warps 0, 12 producers; 1, 10 MMA (even / odd tiles); 2-9 epilogue; 11, 13 selectors (query rows 0-63 / 64-127)
 constexpr int kTcEpiWarps = 8;
+constexpr int kTcSelectors = 2;      // selector warps: each owns half of the query rows, with its own hit queue and survivor staging
 constexpr int kTcM = 128;            // queries per tile (UMMA M)
 constexpr int kTcSeedRows = 32;      // seeding pass: queries per work item (every row starts cold there and floods the
                                      // selector, so the items are kept small to spread them over all SMs)
@@ -427,7 +429,7 @@ __host__ __device__ inline TcSmemLayout tc_smem_layout(int Dh, int kr) {
     L.off_row = L.off_q + kTcM * 8;                         // per row: bound P, delta, base, improved flag
     L.off_bar = L.off_row + 4 * kTcM * 4;
     L.off_misc = L.off_bar + (2 * kTcStages + 2 * kTcAccStages) * 8;
-    L.off_item = L.off_misc + 64 + 128;                      // two staged work-item records
+    L.off_item = L.off_misc + 64 + 256;                      // two staged work-item records
     L.total = L.off_item + 2 * 32;
     return L;
 }
@@ -480,10 +482,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
     unsigned char* sB = smem + L.off_b;
     constexpr int kRS = KR + 1;                                     // row stride of s_r
     float* s_r = reinterpret_cast<float*>(smem + L.off_r);          // [128][KR+1]
-    constexpr int kTcQueueCap = tc_queue_cap(KR), kTcStageCap = tc_stage_cap(KR);
-    uint2* s_stage = reinterpret_cast<uint2*>(smem + L.off_stage);  // [kTcStageCap] (row id, query row)
-    float* s_stage_v = reinterpret_cast<float*>(smem + L.off_stage + kTcStageCap * 8);  // [kTcStageCap] filter value
-    uint2* s_queue = reinterpret_cast<uint2*>(smem + L.off_queue);  // [kTcQueueCap]
+    constexpr int kTcQueueCap = tc_queue_cap(KR) / kTcSelectors, kTcStageCap = tc_stage_cap(KR) / kTcSelectors;  // per selector
+    uint2* s_stage_all = reinterpret_cast<uint2*>(smem + L.off_stage);  // [2][kTcStageCap] (row id, query row)
+    float* s_stage_v_all = reinterpret_cast<float*>(smem + L.off_stage + kTcSelectors * kTcStageCap * 8);  // [2][kTcStageCap] filter value
+    uint2* s_queue_all = reinterpret_cast<uint2*>(smem + L.off_queue);  // [2][kTcQueueCap]
     uint2* s_q = reinterpret_cast<uint2*>(smem + L.off_q);
     float* s_P = reinterpret_cast<float*>(smem + L.off_row);        // [128] bound in filter space (written by the selector only)
     float* s_delta = s_P + kTcM;                                    // [128]
@@ -494,7 +496,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
     uint64_t* bar_tfull = bar_empty + kTcStages;                         // [4] accumulator tile complete
     uint64_t* bar_tempty = bar_tfull + kTcAccStages;                     // [4] accumulator tile drained
     uint32_t* s_misc = reinterpret_cast<uint32_t*>(smem + L.off_misc);   // [0] tmem base [1] item [2] queue tail [3] queue head [4] done
-    volatile float* s_tmpv = reinterpret_cast<volatile float*>(s_misc + 16);  // [32] selector scratch
+    volatile float* s_tmpv_all = reinterpret_cast<volatile float*>(s_misc + 16);  // [2][32] selector scratch
+    // s_misc: [0] tmem base, [4] epilogue warps done, [8 + 2*sel] queue tail, [9 + 2*sel] queue head
     constexpr uint32_t nstages = kTcStages;
 
     const int tid = threadIdx.x, lane = tid & 31;
@@ -523,7 +526,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
         reinterpret_cast<uint4*>(smem + L.off_ones)[i] = make_uint4(pack_h2(a, a), pack_h2(a, 0.0f), 0u, 0u);
         reinterpret_cast<uint4*>(smem + L.off_zero)[i] = make_uint4(0u, 0u, 0u, 0u);
     }
-    for (int i = tid; i < kTcQueueCap; i += kTcThreads) s_queue[i] = make_uint2(0u, 0u);
+    for (int i = tid; i < kTcSelectors * kTcQueueCap; i += kTcThreads) s_queue_all[i] = make_uint2(0u, 0u);
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_misc[0])), "r"(kTcTmemCols)
                      : "memory");
@@ -576,10 +579,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
         // sets the item up behind two named barriers the producers do not take part in.
         if (warp != 0 && warp != 12) {
             constexpr int kSetupThreads = kTcThreads - 64;
-            if (tid == 352) {  // (selector warp) empty queue for this item
-                s_misc[2] = 0;
-                s_misc[3] = 0;
+            if (tid == 352) {  // (a selector warp) empty queues for this item
                 s_misc[4] = 0;
+                s_misc[8] = 0;
+                s_misc[9] = 0;
+                s_misc[10] = 0;
+                s_misc[11] = 0;
             }
             const int row = tid - 32;  // warps 1-4 own the 128 query rows during set-up
             uint2 qi = make_uint2(kNoRow, 0);
@@ -625,8 +630,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
                 // A tile = fp16(-2 * 2^sq * queries): [chunk of 8 dims][128 rows][16 B] (core matrices of 8 rows x
                 // 16 B, SBO 128 B, LBO 2048 B); dimensions beyond the query's are zero.  Warps 5-11 gather it while
                 // warps 1-4 fetch the row state.
-                constexpr int kGatherThreads = 6 * 32 + 32;  // warps 5-11 except the producer warp 12 (not here)
-                const int gt = tid - 160;
+                constexpr int kGatherThreads = 8 * 32;  // warps 5-11 and 13 (the producer warp 12 is not here)
+                const int gt = warp == 13 ? 224 + lane : tid - 160;
                 for (int base = 0; base < Dh * kTcM; base += kGatherThreads * 4) {
                     float4 va[4], vb[4];
 #pragma unroll
@@ -736,9 +741,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
                 }
                 it += t1 - t0;
             }
-        } else if (warp == 11) {
+        } else if (warp == 11 || warp == 13) {
+            const uint32_t sel = warp == 11 ? 0u : 1u;
+            uint2* s_queue = s_queue_all + sel * kTcQueueCap;
+            uint2* s_stage = s_stage_all + sel * kTcStageCap;
+            float* s_stage_v = s_stage_v_all + sel * kTcStageCap;
+            volatile float* s_tmpv = s_tmpv_all + sel * 32;
+            uint32_t* q_tail = &s_misc[8 + 2 * sel];
+            uint32_t* q_head = &s_misc[9 + 2 * sel];
             // ===== selector: the only writer of the rows' bounds and top-k sets =====
-            if (lane == 0) claim((int)(cur ^ 1u));  // the next work item, one ahead
+            if (lane == 0 && sel == 0) claim((int)(cur ^ 1u));  // the next work item, one ahead
             __syncwarp();
             const uint32_t row0_item = (g_list + t0 * kTcTileGroups) * 32u;
             volatile float* vP = s_P;
@@ -790,16 +802,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
                 const unsigned have = __ballot_sync(kFull, e.x != 0u);
                 const int n = have == kFull ? 32 : __ffs(~have) - 1;  // longest prefix of written slots
                 if (n == 0) {
-                    if (lds_volatile(&s_misc[4]) == (uint32_t)kTcEpiWarps && lds_volatile(&s_misc[2]) == head) break;
+                    if (lds_volatile(&s_misc[4]) == (uint32_t)kTcEpiWarps && lds_volatile(q_tail) == head) break;
                     if (++idle > (1u << 21)) __trap();  // an item never takes this long
-                    adopt(lane + 32 * (int)(refresh++ & 3u));
+                    adopt((int)sel * 64 + lane + 32 * (int)(refresh++ & 1u));
                     continue;
                 }
                 idle = 0;
                 const bool mine = lane < n;
                 if (mine) sts_volatile_v2(&s_queue[(head + lane) & (kTcQueueCap - 1)], make_uint2(0u, 0u));
                 head += (uint32_t)n;
-                if (lane == 0) sts_volatile(&s_misc[3], head);
+                if (lane == 0) sts_volatile(q_head, head);
                 const uint32_t row = e.x & 127u;
                 const float val = __uint_as_float(e.y);
                 // (1) survivors: everything still inside the row's bound goes to the exact re-check
@@ -856,11 +868,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
                     }
                     __syncwarp();
                 }
-                if ((++refresh & 15u) == 0u) adopt(lane + 32 * (int)((refresh >> 4) & 3u));
+                if ((++refresh & 15u) == 0u) adopt((int)sel * 64 + lane + 32 * (int)((refresh >> 4) & 1u));
             }
             flush();
             it += t1 - t0;
-            asm volatile("bar.sync 1, %0;" ::"n"((kTcEpiWarps + 1) * 32) : "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"((kTcEpiWarps + kTcSelectors) * 32) : "memory");
         } else {
             // ===== epilogue: two groups of four warps alternate tiles (group g = pipeline g's tiles); a thread owns one
             // query row of its group's tiles.  The accumulators already hold (1-eps)|v|^2 - 2 q.v (scaled), so a tile costs
@@ -878,9 +890,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
             for (int i = 0; i < KR; i++) lr[i] = i < (int)kk ? kInf : -kInf;
             // rows whose nearest list this is already scanned its first seed_tiles tiles in the seeding pass
             const bool skip_seeded = p.mode == 0 && qi.y == 0;
+            const uint32_t sel = (uint32_t)row >> 6;  // rows 0-63 -> selector 0, rows 64-127 -> selector 1 (warp-uniform)
+            uint2* s_queue = s_queue_all + sel * kTcQueueCap;
+            uint32_t* q_tail = &s_misc[8 + 2 * sel];
+            uint32_t* q_head = &s_misc[9 + 2 * sel];
             auto push = [&](uint32_t info, float v) {
-                const uint32_t idx = atomicAdd(&s_misc[2], 1u);
-                for (uint32_t spins = 0; idx - lds_volatile(&s_misc[3]) >= (uint32_t)kTcQueueCap; spins++) {
+                const uint32_t idx = atomicAdd(q_tail, 1u);
+                for (uint32_t spins = 0; idx - lds_volatile(q_head) >= (uint32_t)kTcQueueCap; spins++) {
                     __nanosleep(32);
                     if (spins > (1u << 22)) __trap();  // the selector always drains: a protocol bug, do not hang the GPU
                 }
@@ -946,7 +962,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
                 __threadfence_block();
                 atomicAdd(&s_misc[4], 1u);
             }
-            asm volatile("bar.sync 1, %0;" ::"n"((kTcEpiWarps + 1) * 32) : "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"((kTcEpiWarps + kTcSelectors) * 32) : "memory");
             // merge this item's k smallest into the shared set (distinct values only: a value both sides
             // already hold must not be counted twice; dropping a legitimately equal value only loosens the bound)
             if (valid && grp == 0 && s_impr[row]) {
