@@ -22,7 +22,7 @@
 // The index keeps an fp16 SHADOW of the vectors for this filter (same supergroup layout, 8 dims per 16-byte
 // chunk); the fp32 store stays the source of every distance that is returned.
 //
-// Kernel anatomy (one CTA per SM, persistent, 14 warps; a work item = 128 queries x up to 128 list tiles):
+// Kernel anatomy (one CTA per SM, persistent, 16 warps; a work item = 128 queries x up to 128 list tiles):
 //   warps 0, 12 producers : one cp.async.bulk (1-D TMA) per K-slice of a 128-vector tile -- the HBM layout keeps
 //                      a tile's chunks contiguous, so a list chunk is ONE linear stream -- into a ring of 32 KB
 //                      stages, plus the tile's norm terms; completion on mbarriers (complete_tx::bytes)
@@ -35,7 +35,7 @@
 //   warps 2-9 epilogue: tcgen05.ld the 128x128 fp32 accumulator tile from TMEM (4 stages, 512 columns); two warps
 //                      per TMEM lane quarter, each thread owns one query row and 64 of the 128 columns: one 3-input
 //                      min per three columns, one branch per 32; hits go to a shared-memory queue
-//   warps 11, 13 selectors: each owns half of the query rows: their top-k sets and bounds, the hit queue of those rows,
+//   warps 11, 13-15 selectors: each owns 32 query rows: their top-k sets and bounds, the hit queue of those rows,
 //                      staged appends of survivors to the per-query lists
 // Accumulators never leave the SM; HBM sees each list tile once per 128-query tile.
 #include <cuda_fp16.h>
@@ -44,18 +44,17 @@
 
 namespace vidx {
 
-constexpr int kTcThreads = 448;       // warps 0, 12 producers; 1, 10 MMA (even / odd tiles); 2-9 epilogue; 11, 13 selectors (query rows 0-63 / 64-127)
+constexpr int kTcThreads = 512;       // warps 0, 12 producers; 1, 10 MMA (even / odd tiles); 2-9 epilogue; 11, 13, 14, 15 selectors (one per 32 query rows)
 constexpr int kTcEpiWarps = 8;
-constexpr int kTcSelectors = 2;      // selector warps: each owns half of the query rows, with its own hit queue and survivor staging
+constexpr int kTcSelectors = 4;      // selector warps: each owns 32 query rows (one TMEM lane quarter), with its own hit queue and survivor staging
 constexpr int kTcM = 128;            // queries per tile (UMMA M)
-constexpr int kTcSeedRows = 32;      // seeding pass: queries per work item (every row starts cold there and floods the
-                                     // selector, so the items are kept small to spread them over all SMs)
+constexpr int kTcSeedRows = 128;     // seeding pass: queries per work item (every row starts cold there; the four selectors share the flood)
 constexpr int kTcTileGroups = 4;     // 4 groups = 128 vectors per stage
 constexpr int kTcMaxChunkTiles = 128; // tiles per work item: chosen on the device, 8..128 (1024..16384 vectors)
 // hit queue entries (power of two) and survivors staged by the selector before a bulk append; the 32-entry
 // top-k sets (k > 16) leave room for smaller ones only
 __host__ __device__ constexpr int tc_queue_cap(int kr) { return kr > 16 ? 128 : 512; }
-__host__ __device__ constexpr int tc_stage_cap(int kr) { return kr > 16 ? 128 : 256; }
+__host__ __device__ constexpr int tc_stage_cap(int kr) { return kr > 16 ? 144 : 512; }
 constexpr int kTcAccStages = 4;      // accumulator tiles in TMEM
 constexpr int kTcTmemCols = 512;     // 4 accumulator stages x 128 columns
 constexpr int kTcStages = 4;         // shared-memory ring: stages of 128 vectors x 128 dims of fp16 (32 KB), two per tile pipeline
@@ -429,7 +428,7 @@ __host__ __device__ inline TcSmemLayout tc_smem_layout(int Dh, int kr) {
     L.off_row = L.off_q + kTcM * 8;                         // per row: bound P, delta, base, improved flag
     L.off_bar = L.off_row + 4 * kTcM * 4;
     L.off_misc = L.off_bar + (2 * kTcStages + 2 * kTcAccStages) * 8;
-    L.off_item = L.off_misc + 64 + 256;                      // two staged work-item records
+    L.off_item = L.off_misc + 64 + 512;                      // two staged work-item records
     L.total = L.off_item + 2 * 32;
     return L;
 }
@@ -496,8 +495,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
     uint64_t* bar_tfull = bar_empty + kTcStages;                         // [4] accumulator tile complete
     uint64_t* bar_tempty = bar_tfull + kTcAccStages;                     // [4] accumulator tile drained
     uint32_t* s_misc = reinterpret_cast<uint32_t*>(smem + L.off_misc);   // [0] tmem base [1] item [2] queue tail [3] queue head [4] done
-    volatile float* s_tmpv_all = reinterpret_cast<volatile float*>(s_misc + 16);  // [2][32] selector scratch
-    // s_misc: [0] tmem base, [4] epilogue warps done, [8 + 2*sel] queue tail, [9 + 2*sel] queue head
+    volatile float* s_tmpv_all = reinterpret_cast<volatile float*>(s_misc + 16);  // [4][32] selector scratch
+    // s_misc: [0] tmem base, [4] epilogue warps done, [8 + 2*sel] queue tail, [9 + 2*sel] queue head (sel < 4)
     constexpr uint32_t nstages = kTcStages;
 
     const int tid = threadIdx.x, lane = tid & 31;
@@ -583,8 +582,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
                 s_misc[4] = 0;
                 s_misc[8] = 0;
                 s_misc[9] = 0;
-                s_misc[10] = 0;
-                s_misc[11] = 0;
+                for (int i = 10; i < 8 + 2 * kTcSelectors; i++) s_misc[i] = 0;
             }
             const int row = tid - 32;  // warps 1-4 own the 128 query rows during set-up
             uint2 qi = make_uint2(kNoRow, 0);
@@ -630,8 +628,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
                 // A tile = fp16(-2 * 2^sq * queries): [chunk of 8 dims][128 rows][16 B] (core matrices of 8 rows x
                 // 16 B, SBO 128 B, LBO 2048 B); dimensions beyond the query's are zero.  Warps 5-11 gather it while
                 // warps 1-4 fetch the row state.
-                constexpr int kGatherThreads = 8 * 32;  // warps 5-11 and 13 (the producer warp 12 is not here)
-                const int gt = warp == 13 ? 224 + lane : tid - 160;
+                constexpr int kGatherThreads = 10 * 32;  // warps 5-11 and 13-15 (the producer warp 12 is not here)
+                const int gt = warp >= 13 ? 224 + (warp - 13) * 32 + lane : tid - 160;
                 for (int base = 0; base < Dh * kTcM; base += kGatherThreads * 4) {
                     float4 va[4], vb[4];
 #pragma unroll
@@ -741,8 +739,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
                 }
                 it += t1 - t0;
             }
-        } else if (warp == 11 || warp == 13) {
-            const uint32_t sel = warp == 11 ? 0u : 1u;
+        } else if (warp == 11 || warp >= 13) {
+            const uint32_t sel = warp == 11 ? 0u : (uint32_t)(warp - 12);
             uint2* s_queue = s_queue_all + sel * kTcQueueCap;
             uint2* s_stage = s_stage_all + sel * kTcStageCap;
             float* s_stage_v = s_stage_v_all + sel * kTcStageCap;
@@ -804,7 +802,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
                 if (n == 0) {
                     if (lds_volatile(&s_misc[4]) == (uint32_t)kTcEpiWarps && lds_volatile(q_tail) == head) break;
                     if (++idle > (1u << 21)) __trap();  // an item never takes this long
-                    adopt((int)sel * 64 + lane + 32 * (int)(refresh++ & 1u));
+                    adopt((int)sel * 32 + lane);
                     continue;
                 }
                 idle = 0;
@@ -868,7 +866,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
                     }
                     __syncwarp();
                 }
-                if ((++refresh & 15u) == 0u) adopt((int)sel * 64 + lane + 32 * (int)((refresh >> 4) & 1u));
+                if ((++refresh & 15u) == 0u) adopt((int)sel * 32 + lane);
             }
             flush();
             it += t1 - t0;
@@ -890,7 +888,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
             for (int i = 0; i < KR; i++) lr[i] = i < (int)kk ? kInf : -kInf;
             // rows whose nearest list this is already scanned its first seed_tiles tiles in the seeding pass
             const bool skip_seeded = p.mode == 0 && qi.y == 0;
-            const uint32_t sel = (uint32_t)row >> 6;  // rows 0-63 -> selector 0, rows 64-127 -> selector 1 (warp-uniform)
+            const uint32_t sel = (uint32_t)quarter;  // the selector of this warp's 32 rows
             uint2* s_queue = s_queue_all + sel * kTcQueueCap;
             uint32_t* q_tail = &s_misc[8 + 2 * sel];
             uint32_t* q_head = &s_misc[9 + 2 * sel];
