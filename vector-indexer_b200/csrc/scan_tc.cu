@@ -928,9 +928,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
                             while (mask) {
                                 const int j = __ffs(mask) - 1;
                                 mask &= mask - 1;
-                                float v = tv[0];
+                                // tv[j] for a run-time j: a 5-level multiplexer tree (31 selects, depth 5) instead of a chain of 31
+                                float s16[16], s8[8], s4[4];
 #pragma unroll
-                                for (int jj = 1; jj < 32; jj++) v = (jj == j) ? tv[jj] : v;
+                                for (int i = 0; i < 16; i++) s16[i] = (j & 16) ? tv[16 + i] : tv[i];
+#pragma unroll
+                                for (int i = 0; i < 8; i++) s8[i] = (j & 8) ? s16[8 + i] : s16[i];
+#pragma unroll
+                                for (int i = 0; i < 4; i++) s4[i] = (j & 4) ? s8[4 + i] : s8[i];
+                                const float s2a = (j & 2) ? s4[2] : s4[0], s2b = (j & 2) ? s4[3] : s4[1];
+                                const float v = (j & 1) ? s2b : s2a;
                                 if (v <= P) {  // the bound may have shrunk since the mask was built
                                     push(kEntValid | (tl << 14) | ((cb * 32u + (uint32_t)j) << 7) | (uint32_t)row, v);
                                     // flood control (cold or very loose bound): the k-th smallest value this thread queued
