@@ -202,9 +202,11 @@ typedef struct vidx_search_stats {
 /* Enable per-stage CUDA-event timing (adds stream synchronisation at the end of a
  * search); stats describe the last completed search on this handle. */
 int vidx_set_profiling(vidx_index* idx, int enabled);
-/* Scan algorithm: 0 (default) = tcgen05 TF32 pre-filter + exact re-check whenever the shape allows
- * (D padded to a multiple of 8 floats, D <= 128, k <= 32), 1 = exact FP32 kernels only.  Results are
- * bit-identical either way. */
+/* Scan algorithm: 0 (default) = tcgen05 FP16 filter + exact re-check whenever the shape allows (k <= 32, finite data):
+ * with survivor queues for large batches, in dump mode (every filter value written out and selected exactly) when the
+ * batch's dump stays below 512 MB -- the few-queries-per-list, HBM-bound regime; 1 = exact FP32 kernels only;
+ * 2 / 3 = the filter with queues only / in dump mode whenever its dump fits in 8 GB.  Results are bit-identical in
+ * every mode. */
 int vidx_set_scan_mode(vidx_index* idx, int mode);
 /* Coarse quantization (ivf_index.rs:205-220): 0 = auto (today: the exact FP32 kernels -- the tensor-core filter measured
  * no faster up to nlist = 12 639), 1 = exact kernels only, 2 = tensor-core filter + exact re-check whenever

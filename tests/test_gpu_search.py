@@ -7,6 +7,17 @@ from conftest import bench_data
 
 pytestmark = pytest.mark.gpu
 
+# Every test of this module runs with both flavours of the tensor-core filter: survivor queues (scan mode 2, what large
+# batches use) and dump mode (scan mode 3, what small batches use); auto mode would pick dump for all of these sizes.
+_FLAVOUR = {"mode": 0}
+
+
+@pytest.fixture(autouse=True, params=["queues", "dump"])
+def flavour(request):
+    _FLAVOUR["mode"] = {"queues": 2, "dump": 3}[request.param]
+    yield request.param
+    _FLAVOUR["mode"] = 0
+
 
 def make_pair(O, ffi, xb, nlist, seed=7, ext=None):
     """Same lists on both sides: random centroids from the data + oracle brute labels."""
@@ -15,6 +26,7 @@ def make_pair(O, ffi, xb, nlist, seed=7, ext=None):
     labels = O.assign_brute_force(xb, cents)
     oix = O.Ivf.from_labels(xb, cents, labels, ext_ids=ext)
     gix = ffi.Index(xb.shape[1]).build_from_labels(xb, cents, labels, ext_ids=ext)
+    gix.set_scan_mode(_FLAVOUR["mode"])
     return oix, gix
 
 
@@ -169,7 +181,6 @@ def test_tensor_core_scan_equals_exact_scan_and_oracle(oracle, ffi, d, nlist, nq
     xb, xq = bench_data(40000, d, nq, seed=d + nq)
     oix, gix = make_pair(oracle, ffi, xb, nlist)
     gix.set_profiling(True)
-    gix.set_scan_mode(0)
     Dt, It = check_search(oix, gix, xq, k, nprobe)
     st = gix.stats()
     assert st["n_tc_items"] > 0 and st["n_tc_survivors"] >= nq * min(k, 1) and st["n_tc_overflow"] == 0, st

@@ -346,6 +346,15 @@ void Index::apply_partition() {
         }
         if (b > a) nseg_owned.push_back(b - a);
     }
+    // prefix of the largest per-list tile counts: bounds the dump of a query (dump mode of the tensor-core scan)
+    {
+        std::vector<uint32_t> nt;
+        for (uint64_t l = 0; l < nlist; l++)
+            if (ng[l]) nt.push_back((ng[l] + 3) / 4);
+        std::sort(nt.begin(), nt.end(), std::greater<uint32_t>());
+        tile_prefix.assign(nt.size() + 1, 0);
+        for (size_t t = 0; t < nt.size(); t++) tile_prefix[t + 1] = tile_prefix[t] + nt[t];
+    }
     // prefix of the largest per-list segment counts: bounds the (query,segment) pairs
     std::sort(nseg_owned.begin(), nseg_owned.end(), std::greater<uint32_t>());
     seg_prefix.assign(nseg_owned.size() + 1, 0);
@@ -369,7 +378,7 @@ struct Index::Workspace {
     DevBuf xq_pad, dist, probes, pair_ns, slot_off, seg_cnt, seg_qoff, seg_cur, seg_qlist, slot_seg, dense, sparse, counters,
         scan_tmp, cand_d, cand_r, alld, row_off, row_len, sel_pos, sel_val, rows, stats, slot_rank, list_cnt, list_cur, list_qoff,
         list_qlist, items_per_list, item_off, qnorm, gthr, cand_cnt, overflow, cand, list_cnt0, list_cur0, list_qoff0, list_qlist0,
-        items_per_list0, item_off0, gtop, glock, tcscale, items, items0;
+        items_per_list0, item_off0, gtop, glock, tcscale, items, items0, pair_tiles, pair_off, dump;
 };
 void Index::delete_workspace() {
     delete ws;
@@ -377,6 +386,8 @@ void Index::delete_workspace() {
 }
 
 constexpr uint64_t kCoarseTcMinLists = 1ull << 20;  // auto mode: measured slower than the exact FP32 stage up to nlist = 12 639
+constexpr double kDumpAutoBytes = 512e6;  // auto mode: dump the filter values when the batch's dump stays below this ...
+constexpr uint64_t kDumpAutoTilesPerQuery = 512;  // ... and a query probes at most 64 K vectors (its select is one block)
 constexpr uint32_t kSeedTiles = 4;  // seeding pass: first 512 vectors of each query's nearest list
 
 // stats: distinct probed lists -> algorithmic bytes; (query, list) pairs -> logical bytes / flops
@@ -522,6 +533,12 @@ void Index::search_device(const float* d_xq, uint64_t nq, uint64_t k_req, uint64
     // tensor-core pre-filter + exact finalize whenever the shape allows; the exact kernels then
     // only see the queries it hands back (survivor buffer overflow)
     const bool tc = fused && scan_mode != 1 && tc_ok && tc_supported((int)dim, (uint32_t)k) && !coarse_only;
+    // dump mode of the filter (few queries per list: every filter value is written out, 4 bytes per (query, vector) pair,
+    // and selected exactly) when the whole batch's dump is small; scan_mode 2 / 3 force the queue / dump flavour
+    const uint64_t dump_tiles_per_q = tile_prefix[std::min<size_t>(np, tile_prefix.size() - 1)];
+    const double dump_bytes = (double)nq * (double)dump_tiles_per_q * 512.0;
+    const bool tc_dump = tc && scan_mode != 2 &&
+                         (scan_mode == 3 ? dump_bytes <= 8e9 : (dump_bytes <= kDumpAutoBytes && dump_tiles_per_q <= kDumpAutoTilesPerQuery));
     const uint32_t nseg = (uint32_t)segs.size();
     const uint32_t ldc = ncgroups * kGroup;
     // pairs bound per query: the np largest per-list segment counts
@@ -655,7 +672,21 @@ void Index::search_device(const float* d_xq, uint64_t nq, uint64_t k_req, uint64
                 launch_tc_expand(w.list_cnt.as<uint32_t>(), d_list_ng.as<uint32_t>(), d_list_g0.as<uint32_t>(), w.list_qoff.as<uint32_t>(),
                                  w.item_off.as<uint32_t>(), counters + 10, (uint32_t)nlist, 0, w.items.as<TcItem>(), st);
             }
+            if (tc_dump) {
+                // dump mode: first tile of every (query, probe rank) pair in the dump, and each query's row of it
+                w.pair_tiles.reserve((npairs + 1) * 4);
+                w.pair_off.reserve((npairs + 1) * 4);
+                w.dump.reserve(std::max<uint64_t>((uint64_t)nqb * dump_tiles_per_q, 1) * 512);
+                w.row_off.reserve((size_t)nqb * 8);
+                w.row_len.reserve((size_t)nqb * 4);
+                w.sel_pos.reserve((size_t)nqb * k * 4);
+                w.sel_val.reserve((size_t)nqb * k * 4);
+                launch_dump_pairs(w.probes.as<uint32_t>(), npairs, d_list_ng.as<uint32_t>(), w.pair_tiles.as<uint32_t>(), st);
+                exclusive_scan_u32(w.pair_tiles.as<uint32_t>(), w.pair_off.as<uint32_t>(), npairs, w.scan_tmp.as<uint32_t>(), st);
+                launch_dump_rows(w.pair_off.as<uint32_t>(), np, nqb, w.row_off.as<uint64_t>(), w.row_len.as<uint32_t>(), st);
+            }
             // seeding pass: the same grouping restricted to each query's nearest list
+            if (!tc_dump) {
             w.list_cnt0.reserve(((size_t)nlist + 1) * 4);
             w.list_cur0.reserve(((size_t)nlist + 1) * 4);
             w.list_qoff0.reserve(((size_t)nlist + 1) * 4);
@@ -674,6 +705,7 @@ void Index::search_device(const float* d_xq, uint64_t nq, uint64_t k_req, uint64
             w.items0.reserve(((uint64_t)nqb / 32 + 2 * nlist + 64) * sizeof(TcItem));
             launch_tc_expand(w.list_cnt0.as<uint32_t>(), d_list_ng.as<uint32_t>(), d_list_g0.as<uint32_t>(), w.list_qoff0.as<uint32_t>(),
                              w.item_off0.as<uint32_t>(), counters + 11, (uint32_t)nlist, kSeedTiles, w.items0.as<TcItem>(), st);
+            }
         }
         if (profiling) VIDX_CUDA(cudaEventRecord(ev[3], st));
         if (tc) {
@@ -699,18 +731,23 @@ void Index::search_device(const float* d_xq, uint64_t nq, uint64_t k_req, uint64
             tp.capq = capq;
             tp.k = (uint32_t)k;
             tp.vn_max = vn_max;
-            tp.seed_tiles = kSeedTiles;
-            // pass 1: seed every query's bound from the head of its nearest list
-            tp.mode = 1;
-            tp.list_cnt = w.list_cnt0.as<uint32_t>();
-            tp.list_qoff = w.list_qoff0.as<uint32_t>();
-            tp.list_qlist = w.list_qlist0.as<uint2>();
-            tp.item_off = w.item_off0.as<uint32_t>();
-            tp.items = w.items0.as<TcItem>();
-            tp.work_counter = counters + 9;
-            launch_scan_tc(tp, st);
-            // pass 2: everything else, starting from warm bounds
-            tp.mode = 0;
+            tp.seed_tiles = tc_dump ? 0 : kSeedTiles;
+            tp.nprobe = np;
+            tp.dump = tc_dump ? w.dump.as<float>() : nullptr;
+            tp.pair_off = tc_dump ? w.pair_off.as<uint32_t>() : nullptr;
+            if (!tc_dump) {
+                // pass 1: seed every query's bound from the head of its nearest list
+                tp.mode = 1;
+                tp.list_cnt = w.list_cnt0.as<uint32_t>();
+                tp.list_qoff = w.list_qoff0.as<uint32_t>();
+                tp.list_qlist = w.list_qlist0.as<uint2>();
+                tp.item_off = w.item_off0.as<uint32_t>();
+                tp.items = w.items0.as<TcItem>();
+                tp.work_counter = counters + 9;
+                launch_scan_tc(tp, st);
+            }
+            // pass 2: everything else, starting from warm bounds (or, in dump mode, the only pass)
+            tp.mode = tc_dump ? 2 : 0;
             tp.list_cnt = w.list_cnt.as<uint32_t>();
             tp.list_qoff = w.list_qoff.as<uint32_t>();
             tp.list_qlist = w.list_qlist.as<uint2>();
@@ -742,6 +779,14 @@ void Index::search_device(const float* d_xq, uint64_t nq, uint64_t k_req, uint64
                 for (int i = 0; i < 16; i++) fprintf(stderr, "  %-20s %12.0f per CTA  (%.1f%% of kernel)\n", names[i], acc[i] / nb, 100.0 * acc[i] / acc[13]);
             }
 #endif
+            if (tc_dump) {
+                // each query's k-th smallest filter value (exact radix select), then everything within its bound
+                launch_select_topk(w.dump.as<float>(), w.row_off.as<uint64_t>(), w.row_len.as<uint32_t>(), 0, 0, nqb, (uint32_t)k,
+                                   w.sel_pos.as<uint32_t>(), w.sel_val.as<float>(), st);
+                launch_dump_collect(w.dump.as<float>(), w.pair_off.as<uint32_t>(), w.probes.as<uint32_t>(), np, nqb, (uint32_t)k,
+                                    w.sel_val.as<float>(), w.qnorm.as<float>(), vn_max, tp.scale, d_list_g0.as<uint32_t>(),
+                                    w.cand.as<unsigned long long>(), w.cand_cnt.as<uint32_t>(), w.overflow.as<uint32_t>(), capq, st);
+            }
         }
         if (profiling) VIDX_CUDA(cudaEventRecord(ev[8], st));
 
@@ -1427,7 +1472,7 @@ int vidx_set_coarse_mode(vidx_index* idx, int mode) {
 int vidx_set_scan_mode(vidx_index* idx, int mode) {
     return guarded([&] {
         require(idx, VIDX_ERR_INVALID_INPUT, "idx is NULL");
-        require(mode == 0 || mode == 1, VIDX_ERR_INVALID_INPUT, "mode must be 0 or 1");
+        require(mode >= 0 && mode <= 3, VIDX_ERR_INVALID_INPUT, "mode must be 0 (auto), 1 (exact), 2 (filter, queues) or 3 (filter, dump)");
         idx->ix.scan_mode = mode;
     });
 }

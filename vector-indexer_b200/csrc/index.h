@@ -46,6 +46,7 @@ struct Index {
     uint64_t owned_vectors = 0;
     std::vector<uint2> list_seg_part;     // per list (first segment, end segment); empty if not owned
     std::vector<uint64_t> seg_prefix;     // prefix sums of per-list segment counts, largest first
+    std::vector<uint64_t> tile_prefix;    // prefix sums of per-list 128-vector tile counts (owned part), largest first
 
     // device store
     cudaStream_t stream = nullptr;
@@ -66,7 +67,8 @@ struct Index {
     } ctab;
     int coarse_mode = 0;   // 0 = tensor-core filter when n_probe <= 32 and nlist is large enough, 1 = exact kernels only, 2 = filter whenever possible
     void coarse_tc(const float4* xq4, uint32_t nqb, uint32_t np, uint32_t* d_probes, float* d_probe_dist, cudaStream_t st);
-    int scan_mode = 0;     // 0 = tensor-core pre-filter when the shape allows, 1 = exact kernels only
+    int scan_mode = 0;     // 0 = tensor-core filter when the shape allows (dump flavour for small batches), 1 = exact kernels only,
+                           // 2 = filter with survivor queues only, 3 = filter in dump mode whenever its dump fits
     DevBuf io_xq, io_D, io_I, io_rows, io_V;
     struct Workspace;
     Workspace* ws = nullptr;
