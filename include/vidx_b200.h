@@ -197,16 +197,16 @@ typedef struct vidx_search_stats {
     uint64_t kernel_launches;        /* kernels launched by the last search */
     double ms_scan_tc;               /* the tensor-core scan kernel alone (part of ms_scan) */
     uint64_t n_tc_items, n_tc_survivors, n_tc_overflow; /* work items, candidates re-checked exactly, queries redone exactly */
-    uint64_t tc_mma_flops;           /* 2*D per (query, vector) pair issued to the tensor cores (TF32) */
+    uint64_t tc_mma_flops;           /* 2*D per (query, vector) pair issued to the tensor cores */
+    uint64_t n_tc_dump_values;       /* sub-tile minima reserved for the bounds pass (0 = the seeded flavour ran) */
 } vidx_search_stats;
 /* Enable per-stage CUDA-event timing (adds stream synchronisation at the end of a
  * search); stats describe the last completed search on this handle. */
 int vidx_set_profiling(vidx_index* idx, int enabled);
 /* Scan algorithm: 0 (default) = tcgen05 FP16 filter + exact re-check whenever the shape allows (k <= 32, finite data):
- * with survivor queues for large batches, in dump mode (every filter value written out and selected exactly) when the
- * batch's dump stays below 512 MB -- the few-queries-per-list, HBM-bound regime; 1 = exact FP32 kernels only;
- * 2 / 3 = the filter with queues only / in dump mode whenever its dump fits in 8 GB.  Results are bit-identical in
- * every mode. */
+ * seeding pass + main pass when a query visits many 128-vector tiles (tensor-bound), bounds pass + main pass when it
+ * visits at most 2048 (the HBM-bound regime); 1 = exact FP32 kernels only; 2 / 3 = the filter with the
+ * seeding pass only / with the bounds pass whenever its minima fit in 8 GB.  Results are bit-identical in every mode. */
 int vidx_set_scan_mode(vidx_index* idx, int mode);
 /* Coarse quantization (ivf_index.rs:205-220): 0 = auto (today: the exact FP32 kernels -- the tensor-core filter measured
  * no faster up to nlist = 12 639), 1 = exact kernels only, 2 = tensor-core filter + exact re-check whenever

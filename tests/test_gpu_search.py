@@ -7,14 +7,15 @@ from conftest import bench_data
 
 pytestmark = pytest.mark.gpu
 
-# Every test of this module runs with both flavours of the tensor-core filter: survivor queues (scan mode 2, what large
-# batches use) and dump mode (scan mode 3, what small batches use); auto mode would pick dump for all of these sizes.
+# Every test of this module runs with both flavours of the tensor-core filter: seeding pass + main pass (scan mode 2, what
+# indexes with giant lists use) and bounds pass + main pass (scan mode 3, what a query that visits few tiles gets); auto
+# mode would pick the second for all of these sizes.
 _FLAVOUR = {"mode": 0}
 
 
-@pytest.fixture(autouse=True, params=["queues", "dump"])
+@pytest.fixture(autouse=True, params=["seeded", "bounds"])
 def flavour(request):
-    _FLAVOUR["mode"] = {"queues": 2, "dump": 3}[request.param]
+    _FLAVOUR["mode"] = {"seeded": 2, "bounds": 3}[request.param]
     yield request.param
     _FLAVOUR["mode"] = 0
 

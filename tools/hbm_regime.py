@@ -13,12 +13,13 @@ ix = _ffi.Index(d, 0).build_from_labels(xb, cents, labels)
 ts = torch.cuda.Stream(); torch.cuda.set_stream(ts)
 d_xq = torch.from_numpy(xq).cuda(); d_D = torch.empty((nq, k), device='cuda'); d_I = torch.empty((nq, k), dtype=torch.int64, device='cuda')
 ix.set_profiling(True)
-for npb in (1,):
+for mode, npb in ((2, 1), (3, 1), (2, 4), (3, 4), (2, 16), (3, 16), (2, 64), (3, 64)):
+    ix.set_scan_mode(mode)
     for _ in range(3):
         ix.search_device(d_xq.data_ptr(), nq, k, npb, d_D.data_ptr(), d_I.data_ptr(), ts.cuda_stream); torch.cuda.synchronize()
     s = ix.stats()
     t = s['ms_scan_tc'] / 1e3
-    print(npb, {kk: round(s[kk], 4) for kk in s if kk.startswith('ms_')}, 'alg GB', s['scan_bytes_algorithmic'] / 1e9, 'GB/s', s['scan_bytes_algorithmic'] / t / 1e9, 'pairs', s['n_pairs'], 'surv', s['n_tc_survivors'], 'ovf', s['n_tc_overflow'], 'items', s['n_tc_items'])
+    print('mode', mode, 'nprobe', npb, 'submin slots', s['n_tc_dump_values'], {kk: round(s[kk], 4) for kk in s if kk.startswith('ms_')}, 'alg GB', s['scan_bytes_algorithmic'] / 1e9, 'GB/s', s['scan_bytes_algorithmic'] / t / 1e9, 'pairs', s['n_pairs'], 'surv', s['n_tc_survivors'], 'ovf', s['n_tc_overflow'], 'items', s['n_tc_items'])
 ix.set_scan_mode(1)
 for npb in (1,):
     for _ in range(3):

@@ -386,8 +386,7 @@ void Index::delete_workspace() {
 }
 
 constexpr uint64_t kCoarseTcMinLists = 1ull << 20;  // auto mode: measured slower than the exact FP32 stage up to nlist = 12 639
-constexpr double kDumpAutoBytes = 512e6;  // auto mode: dump the filter values when the batch's dump stays below this ...
-constexpr uint64_t kDumpAutoTilesPerQuery = 512;  // ... and a query probes at most 64 K vectors (its select is one block)
+constexpr uint64_t kBoundsPassMaxTiles = 2048;  // auto mode: bounds pass first when a query probes at most this many 128-vector tiles
 constexpr uint32_t kSeedTiles = 4;  // seeding pass: first 512 vectors of each query's nearest list
 
 // stats: distinct probed lists -> algorithmic bytes; (query, list) pairs -> logical bytes / flops
@@ -533,12 +532,13 @@ void Index::search_device(const float* d_xq, uint64_t nq, uint64_t k_req, uint64
     // tensor-core pre-filter + exact finalize whenever the shape allows; the exact kernels then
     // only see the queries it hands back (survivor buffer overflow)
     const bool tc = fused && scan_mode != 1 && tc_ok && tc_supported((int)dim, (uint32_t)k) && !coarse_only;
-    // dump mode of the filter (few queries per list: every filter value is written out, 4 bytes per (query, vector) pair,
-    // and selected exactly) when the whole batch's dump is small; scan_mode 2 / 3 force the queue / dump flavour
+    // two passes of the filter when a query visits few tiles (the HBM-bound regime): a bounds pass that only records
+    // the minimum of every 32 columns, then the main pass with final bounds.  With many tile visits per query (a few
+    // giant lists) the doubled tensor-core work costs more than the survivors it saves: seeding pass + main pass.
+    // scan_mode 2 / 3 force the seeded / the two-pass flavour.
     const uint64_t dump_tiles_per_q = tile_prefix[std::min<size_t>(np, tile_prefix.size() - 1)];
-    const double dump_bytes = (double)nq * (double)dump_tiles_per_q * 512.0;
     const bool tc_dump = tc && scan_mode != 2 &&
-                         (scan_mode == 3 ? dump_bytes <= 8e9 : (dump_bytes <= kDumpAutoBytes && dump_tiles_per_q <= kDumpAutoTilesPerQuery));
+                         (scan_mode == 3 ? (double)nq * (double)dump_tiles_per_q * 16.0 <= 8e9 : dump_tiles_per_q <= kBoundsPassMaxTiles);
     const uint32_t nseg = (uint32_t)segs.size();
     const uint32_t ldc = ncgroups * kGroup;
     // pairs bound per query: the np largest per-list segment counts
@@ -673,17 +673,17 @@ void Index::search_device(const float* d_xq, uint64_t nq, uint64_t k_req, uint64
                                  w.item_off.as<uint32_t>(), counters + 10, (uint32_t)nlist, 0, w.items.as<TcItem>(), st);
             }
             if (tc_dump) {
-                // dump mode: first tile of every (query, probe rank) pair in the dump, and each query's row of it
+                // bounds pass: first tile of every (query, probe rank) pair in submin, and each query's row of it
                 w.pair_tiles.reserve((npairs + 1) * 4);
                 w.pair_off.reserve((npairs + 1) * 4);
-                w.dump.reserve(std::max<uint64_t>((uint64_t)nqb * dump_tiles_per_q, 1) * 512);
+                w.dump.reserve(std::max<uint64_t>((uint64_t)nqb * dump_tiles_per_q, 1) * 16);
                 w.row_off.reserve((size_t)nqb * 8);
                 w.row_len.reserve((size_t)nqb * 4);
                 w.sel_pos.reserve((size_t)nqb * k * 4);
                 w.sel_val.reserve((size_t)nqb * k * 4);
-                launch_dump_pairs(w.probes.as<uint32_t>(), npairs, d_list_ng.as<uint32_t>(), w.pair_tiles.as<uint32_t>(), st);
+                launch_pair_tiles(w.probes.as<uint32_t>(), npairs, d_list_ng.as<uint32_t>(), w.pair_tiles.as<uint32_t>(), st);
                 exclusive_scan_u32(w.pair_tiles.as<uint32_t>(), w.pair_off.as<uint32_t>(), npairs, w.scan_tmp.as<uint32_t>(), st);
-                launch_dump_rows(w.pair_off.as<uint32_t>(), np, nqb, w.row_off.as<uint64_t>(), w.row_len.as<uint32_t>(), st);
+                launch_submin_rows(w.pair_off.as<uint32_t>(), np, nqb, w.row_off.as<uint64_t>(), w.row_len.as<uint32_t>(), st);
             }
             // seeding pass: the same grouping restricted to each query's nearest list
             if (!tc_dump) {
@@ -733,7 +733,7 @@ void Index::search_device(const float* d_xq, uint64_t nq, uint64_t k_req, uint64
             tp.vn_max = vn_max;
             tp.seed_tiles = tc_dump ? 0 : kSeedTiles;
             tp.nprobe = np;
-            tp.dump = tc_dump ? w.dump.as<float>() : nullptr;
+            tp.submin = tc_dump ? w.dump.as<float>() : nullptr;
             tp.pair_off = tc_dump ? w.pair_off.as<uint32_t>() : nullptr;
             if (!tc_dump) {
                 // pass 1: seed every query's bound from the head of its nearest list
@@ -746,13 +746,23 @@ void Index::search_device(const float* d_xq, uint64_t nq, uint64_t k_req, uint64
                 tp.work_counter = counters + 9;
                 launch_scan_tc(tp, st);
             }
-            // pass 2: everything else, starting from warm bounds (or, in dump mode, the only pass)
-            tp.mode = tc_dump ? 2 : 0;
             tp.list_cnt = w.list_cnt.as<uint32_t>();
             tp.list_qoff = w.list_qoff.as<uint32_t>();
             tp.list_qlist = w.list_qlist.as<uint2>();
             tp.item_off = w.item_off.as<uint32_t>();
             tp.items = w.items.as<TcItem>();
+            if (tc_dump) {
+                // pass 1: the minima of every (query, probed tile); their k-th smallest is the query's final bound
+                tp.mode = 2;
+                tp.work_counter = counters + 9;
+                launch_scan_tc(tp, st);
+                launch_select_topk(w.dump.as<float>(), w.row_off.as<uint64_t>(), w.row_len.as<uint32_t>(), 0, 0, nqb, (uint32_t)k,
+                                   w.sel_pos.as<uint32_t>(), w.sel_val.as<float>(), st);
+                launch_bounds_apply(w.sel_val.as<float>(), nqb, (uint32_t)k, w.gtop.as<float>(), st);
+            }
+            // pass 2: everything else, starting from warm bounds (after a bounds pass: from final ones)
+            tp.mode = 0;
+            tp.frozen = tc_dump ? 1 : 0;
             tp.work_counter = counters + 8;
 #ifdef VIDX_TC_TIMING
             static DevBuf d_dbg;
@@ -779,14 +789,6 @@ void Index::search_device(const float* d_xq, uint64_t nq, uint64_t k_req, uint64
                 for (int i = 0; i < 16; i++) fprintf(stderr, "  %-20s %12.0f per CTA  (%.1f%% of kernel)\n", names[i], acc[i] / nb, 100.0 * acc[i] / acc[13]);
             }
 #endif
-            if (tc_dump) {
-                // each query's k-th smallest filter value (exact radix select), then everything within its bound
-                launch_select_topk(w.dump.as<float>(), w.row_off.as<uint64_t>(), w.row_len.as<uint32_t>(), 0, 0, nqb, (uint32_t)k,
-                                   w.sel_pos.as<uint32_t>(), w.sel_val.as<float>(), st);
-                launch_dump_collect(w.dump.as<float>(), w.pair_off.as<uint32_t>(), w.probes.as<uint32_t>(), np, nqb, (uint32_t)k,
-                                    w.sel_val.as<float>(), w.qnorm.as<float>(), vn_max, tp.scale, d_list_g0.as<uint32_t>(),
-                                    w.cand.as<unsigned long long>(), w.cand_cnt.as<uint32_t>(), w.overflow.as<uint32_t>(), capq, st);
-            }
         }
         if (profiling) VIDX_CUDA(cudaEventRecord(ev[8], st));
 
@@ -902,6 +904,7 @@ void Index::search_device(const float* d_xq, uint64_t nq, uint64_t k_req, uint64
                     stats.n_tc_overflow += of[i] ? 1 : 0;
                 }
                 stats.tc_mma_flops += h[1] * 2ull * 8 * tc_dh((int)dim);
+                if (tc_dump) stats.n_tc_dump_values += (uint64_t)nqb * dump_tiles_per_q * 4;
             }
         }
     }
@@ -1472,7 +1475,7 @@ int vidx_set_coarse_mode(vidx_index* idx, int mode) {
 int vidx_set_scan_mode(vidx_index* idx, int mode) {
     return guarded([&] {
         require(idx, VIDX_ERR_INVALID_INPUT, "idx is NULL");
-        require(mode >= 0 && mode <= 3, VIDX_ERR_INVALID_INPUT, "mode must be 0 (auto), 1 (exact), 2 (filter, queues) or 3 (filter, dump)");
+        require(mode >= 0 && mode <= 3, VIDX_ERR_INVALID_INPUT, "mode must be 0 (auto), 1 (exact), 2 (filter, seeded) or 3 (filter, bounds pass first)");
         idx->ix.scan_mode = mode;
     });
 }

@@ -67,8 +67,8 @@ struct Index {
     } ctab;
     int coarse_mode = 0;   // 0 = tensor-core filter when n_probe <= 32 and nlist is large enough, 1 = exact kernels only, 2 = filter whenever possible
     void coarse_tc(const float4* xq4, uint32_t nqb, uint32_t np, uint32_t* d_probes, float* d_probe_dist, cudaStream_t st);
-    int scan_mode = 0;     // 0 = tensor-core filter when the shape allows (dump flavour for small batches), 1 = exact kernels only,
-                           // 2 = filter with survivor queues only, 3 = filter in dump mode whenever its dump fits
+    int scan_mode = 0;     // 0 = tensor-core filter when the shape allows (bounds pass first when a query visits few tiles), 1 = exact kernels
+                           // only, 2 = filter with seeding pass only, 3 = filter with bounds pass whenever its minima fit
     DevBuf io_xq, io_D, io_I, io_rows, io_V;
     struct Workspace;
     Workspace* ws = nullptr;

@@ -597,11 +597,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
                 float* rr = s_r + row * kRS;
                 uint32_t dump_off = 0;
                 if (p.mode == 2) {
-                    // dump mode: no bounds; the row's values go to its (query, probe rank) row of the dump
-                    if (qi.x != kNoRow) {
-                        base_t = (1.0f - kTcEps) * p.qnorm[qi.x] - tCabs;
-                        dump_off = p.pair_off[(size_t)qi.x * p.nprobe + qi.y];
-                    }
+                    // bounds pass: no bounds yet; the row's sub-tile minima go to its (query, probe rank) row of submin
+                    if (qi.x != kNoRow) dump_off = p.pair_off[(size_t)qi.x * p.nprobe + qi.y];
                 } else if (qi.x != kNoRow) {
                     const uint32_t q = qi.x;
                     const float qn = p.qnorm[q];
@@ -630,7 +627,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
                 s_P[row] = P;
                 s_delta[row] = delta;
                 s_base[row] = base_t;
-                s_impr[row] = dump_off;  // (dump mode: first tile of the row's dump; else "set changed" flag = 0)
+                s_impr[row] = dump_off;  // (bounds pass: first tile of the row in submin; else "set changed" flag = 0)
             } else if (warp >= 5) {
                 // A tile = fp16(-2 * 2^sq * queries): [chunk of 8 dims][128 rows][16 B] (core matrices of 8 rows x
                 // 16 B, SBO 128 B, LBO 2048 B); dimensions beyond the query's are zero.  Warps 5-11 gather it while
@@ -761,6 +758,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
             volatile float* vP = s_P;
             volatile float* vr = s_r;
             uint32_t head = 0, refresh = 0, idle = 0, nstage = 0;
+            const bool frozen = p.frozen != 0;
             // survivors are staged in shared memory and appended to the per-query lists in bulk: four global
             // atomics in flight per lane instead of one round trip per batch; entries that fell outside the
             // row's bound meanwhile are dropped
@@ -832,7 +830,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
                 if (nstage > (uint32_t)kTcStageCap - 32u) flush();
                 // (2) state changes: one lane per distinct row folds ALL of that row's values of this batch into the
                 // row's set (threads queue their hits back to back, so a batch usually holds runs of one row)
-                const bool todo = cand_ok && val < vr[row * kRS];
+                const bool todo = cand_ok && !frozen && val < vr[row * kRS];
                 const unsigned tm = __ballot_sync(kFull, todo);
                 if (tm) {
                     s_tmpv[lane] = val;
@@ -889,8 +887,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
             const bool valid = qi.x != kNoRow;
             const float delta = s_delta[row];
             const uint32_t seed_tiles = p.seed_tiles, kk = p.k;
-            const uint32_t dump_row0 = s_impr[row];  // dump mode only
-            const float dump_base = s_base[row];
+            const uint32_t submin_row0 = s_impr[row];  // bounds pass only
             float P = s_P[row];
             float lr[KR];  // the k smallest values this thread queued in this item, descending (+inf until k exist)
 #pragma unroll
@@ -925,22 +922,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
                     const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + s * 128 + half * 64;
                     { TC_T0(); tc_ld32x2(tbase, tbase + 32, acc); if (warp == 2) TC_ACC(14); }
                     if (p.mode == 2) {
-                        // dump mode (few queries per list: HBM-bound): every filter value of the row, in real units and
-                        // clamped to [0, inf] (padding rows / columns past the list: +inf), to the row's dump
-                        if (valid) {
-                            float4* dst = reinterpret_cast<float4*>(p.dump + ((size_t)(dump_row0 + t) * 128 + half * 64));
-#pragma unroll
-                            for (int j4 = 0; j4 < 16; j4++) {
-                                float o[4];
-#pragma unroll
-                                for (int e = 0; e < 4; e++) {
-                                    const int j = 4 * j4 + e;
-                                    const float v = fmaxf(fminf(__fmaf_rn(acc[j], tInvS, dump_base), kInf), 0.0f);
-                                    o[e] = (2 * half + (uint32_t)(j >> 5)) < ng ? v : kInf;
-                                }
-                                dst[j4] = make_float4(o[0], o[1], o[2], o[3]);
-                            }
-                        }
+                        // bounds pass: the minimum of each 32-column group (accumulator units; groups past the list: +inf)
+                        const float m0 = 2 * half < ng ? min32(acc) : kInf, m1 = 2 * half + 1 < ng ? min32(acc + 32) : kInf;
+                        if (valid) *reinterpret_cast<float2*>(p.submin + ((size_t)(submin_row0 + t) * 4 + half * 2)) = make_float2(m0, m1);
                         continue;
                     }
 #pragma unroll
@@ -1072,61 +1056,35 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
 }
 
 // ------------------------------------------------------------------------------------------
-// dump mode: when few queries share a list the scan is HBM-bound and every row of a work item would start cold.  The
-// filter kernel then writes ALL filter values of the (query, probed list) pairs (4 bytes per pair of (query, vector)),
-// an exact radix select finds each query's k-th smallest value, and everything within the bound of that value goes to
-// the exact re-check.  No queues, no bounds, one pass.
+// bounds pass (few tile visits per query: the regime where the scan is HBM-bound and every row of a work item would
+// start cold): a first pass of the filter kernel writes only the minimum of every 32 columns of every (query, probed
+// tile).  The k-th smallest of a query's minima is an upper bound of its k-th smallest filter value (they are values of
+// k distinct vectors), and a tight one; the main pass then runs with final bounds and only collects survivors.
 // ------------------------------------------------------------------------------------------
-__global__ void dump_pairs_kernel(const uint32_t* __restrict__ probes, size_t npairs, const uint32_t* __restrict__ list_ngroups,
+__global__ void pair_tiles_kernel(const uint32_t* __restrict__ probes, size_t npairs, const uint32_t* __restrict__ list_ngroups,
                                   uint32_t* __restrict__ pair_tiles) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= npairs) return;
     const uint32_t l = probes[i];
     pair_tiles[i] = l == kNoRow ? 0u : (list_ngroups[l] + kTcTileGroups - 1) / kTcTileGroups;
 }
-__global__ void dump_rows_kernel(const uint32_t* __restrict__ pair_off, uint32_t nprobe, uint32_t nq, uint64_t* __restrict__ row_off,
-                                 uint32_t* __restrict__ row_len) {
+__global__ void submin_rows_kernel(const uint32_t* __restrict__ pair_off, uint32_t nprobe, uint32_t nq, uint64_t* __restrict__ row_off,
+                                   uint32_t* __restrict__ row_len) {
     uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= nq) return;
     const uint32_t a = pair_off[(size_t)q * nprobe], b = pair_off[(size_t)(q + 1) * nprobe];
-    row_off[q] = (uint64_t)a * 128;
-    row_len[q] = (b - a) * 128;
+    row_off[q] = (uint64_t)a * 4;
+    row_len[q] = (b - a) * 4;
 }
-// One block per query: every dumped value within the bound of the k-th smallest becomes a survivor (rank << 32 | row).
-__global__ void dump_collect_kernel(const float* __restrict__ dump, const uint32_t* __restrict__ pair_off, const uint32_t* __restrict__ probes,
-                                    uint32_t nprobe, uint32_t k, const float* __restrict__ kth_val /* [nq][k] ascending */,
-                                    const float* __restrict__ qnorm, float vn_max, const TcScale* __restrict__ scale,
-                                    const uint32_t* __restrict__ list_g0, unsigned long long* __restrict__ cand, uint32_t* __restrict__ cand_cnt,
-                                    uint32_t* __restrict__ overflow, uint32_t capq) {
-    const uint32_t q = blockIdx.x;
-    __shared__ uint32_t s_off[65];
-    const uint32_t* po = pair_off + (size_t)q * nprobe;
-    const float kth = kth_val[(size_t)q * k + (k - 1)];  // +inf when the query has fewer than k candidates
-    const float thr = kth + (2.0f * kTcEps * (qnorm[q] + vn_max) + 2.0f * scale->c_abs);
-    const uint32_t t0 = po[0];
-    for (uint32_t r0 = 0; r0 < nprobe; r0 += 64) {  // probe ranks in blocks of 64
-        const uint32_t nr = min(64u, nprobe - r0);
-        __syncthreads();
-        for (uint32_t i = threadIdx.x; i <= nr; i += blockDim.x) s_off[i] = po[r0 + i];
-        __syncthreads();
-        const uint32_t a = s_off[0], b = s_off[nr];
-        const float* row = dump + (size_t)a * 128;
-        const uint32_t n = (b - a) * 128;
-        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-            const float v = row[i];
-            if (v <= thr && v < __int_as_float(0x7f800000)) {
-                const uint32_t tile = a + (i >> 7);
-                uint32_t r = 0;
-                while (r + 1 < nr && s_off[r + 1] <= tile) r++;
-                const uint32_t l = probes[(size_t)q * nprobe + r0 + r];
-                const uint32_t rowid = list_g0[l] * 32u + (tile - s_off[r]) * 128u + (i & 127u);
-                const uint32_t idx = atomicAdd(&cand_cnt[q], 1u);
-                if (idx < capq) cand[(size_t)q * capq + idx] = ((unsigned long long)(r0 + r) << 32) | rowid;
-                else overflow[q] = 1u;
-            }
-        }
-    }
-    (void)t0;
+// The k-th smallest minimum (accumulator units) becomes the query's whole top-k set: the main pass reads its bound from
+// the set's largest element.  Queries with fewer than k minima keep the empty set (bound +inf: all of their few
+// candidates are re-checked).
+__global__ void bounds_apply_kernel(const float* __restrict__ sel_val /* [nq][k] ascending */, uint32_t nq, uint32_t k,
+                                    float* __restrict__ gtop) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq * k) return;
+    const float kth = sel_val[(size_t)(i / k) * k + (k - 1)];
+    if (kth < __int_as_float(0x7f800000)) gtop[i] = kth;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1317,22 +1275,19 @@ void launch_scan_tc(const TcParams& p, cudaStream_t st) {
     else if (p.k <= 16) launch_scan_tc_kr<16>(p, tc_smem_layout(p.Dh, 16).total, st);
     else launch_scan_tc_kr<32>(p, tc_smem_layout(p.Dh, 32).total, st);
 }
-void launch_dump_pairs(const uint32_t* probes, size_t npairs, const uint32_t* list_ngroups, uint32_t* pair_tiles, cudaStream_t st) {
+void launch_pair_tiles(const uint32_t* probes, size_t npairs, const uint32_t* list_ngroups, uint32_t* pair_tiles, cudaStream_t st) {
     if (!npairs) return;
-    dump_pairs_kernel<<<(unsigned)ceil_div(npairs, 256), 256, 0, st>>>(probes, npairs, list_ngroups, pair_tiles);
+    pair_tiles_kernel<<<(unsigned)ceil_div(npairs, 256), 256, 0, st>>>(probes, npairs, list_ngroups, pair_tiles);
     VIDX_LAUNCHED();
 }
-void launch_dump_rows(const uint32_t* pair_off, uint32_t nprobe, uint32_t nq, uint64_t* row_off, uint32_t* row_len, cudaStream_t st) {
+void launch_submin_rows(const uint32_t* pair_off, uint32_t nprobe, uint32_t nq, uint64_t* row_off, uint32_t* row_len, cudaStream_t st) {
     if (!nq) return;
-    dump_rows_kernel<<<(unsigned)ceil_div(nq, 256), 256, 0, st>>>(pair_off, nprobe, nq, row_off, row_len);
+    submin_rows_kernel<<<(unsigned)ceil_div(nq, 256), 256, 0, st>>>(pair_off, nprobe, nq, row_off, row_len);
     VIDX_LAUNCHED();
 }
-void launch_dump_collect(const float* dump, const uint32_t* pair_off, const uint32_t* probes, uint32_t nprobe, uint32_t nq, uint32_t k,
-                         const float* kth_val, const float* qnorm, float vn_max, const TcScale* scale, const uint32_t* list_g0,
-                         unsigned long long* cand, uint32_t* cand_cnt, uint32_t* overflow, uint32_t capq, cudaStream_t st) {
+void launch_bounds_apply(const float* sel_val, uint32_t nq, uint32_t k, float* gtop, cudaStream_t st) {
     if (!nq) return;
-    dump_collect_kernel<<<nq, 256, 0, st>>>(dump, pair_off, probes, nprobe, k, kth_val, qnorm, vn_max, scale, list_g0, cand, cand_cnt,
-                                            overflow, capq);
+    bounds_apply_kernel<<<(unsigned)ceil_div((size_t)nq * k, 256), 256, 0, st>>>(sel_val, nq, k, gtop);
     VIDX_LAUNCHED();
 }
 void launch_finalize(const FinalizeParams& p, cudaStream_t st) {

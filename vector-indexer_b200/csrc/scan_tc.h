@@ -54,10 +54,11 @@ struct TcParams {
     uint32_t k;
     float vn_max;                  // max |v|^2 over the stored rows
     unsigned long long* dbg;       // role timers (builds with -DVIDX_TC_TIMING only), else NULL
-    float* dump;                   // dump mode: filter values of every (query, probed list) pair, 128 floats per tile
-    const uint32_t* pair_off;      // dump mode: first tile of pair (query * nprobe + rank) in the dump
+    float* submin;                 // bounds pass: the minimum of every 32 columns of every (query, probed tile): 4 floats per tile
+    const uint32_t* pair_off;      // bounds pass: first tile of pair (query * nprobe + rank) in submin
     uint32_t nprobe;
-    uint32_t mode;                 // 0 = main pass, 1 = seeding pass (head of each query's nearest list only), 2 = dump mode
+    uint32_t mode;                 // 0 = main pass, 1 = seeding pass (head of each query's nearest list only), 2 = bounds pass
+    uint32_t frozen;               // main pass after a bounds pass: the bounds are final, survivors are only collected
     uint32_t seed_tiles;           // tiles per list covered by the seeding pass (0 = no seeding pass was run)
 };
 
@@ -105,11 +106,9 @@ void launch_tc_expand(const uint32_t* list_cnt, const uint32_t* list_ngroups, co
                       const uint32_t* item_off, const uint32_t* chunk_tiles, uint32_t nlist, uint32_t seed_tiles, TcItem* items,
                       cudaStream_t st);
 void launch_scan_tc(const TcParams& p, cudaStream_t st);
-void launch_dump_pairs(const uint32_t* probes, size_t npairs, const uint32_t* list_ngroups, uint32_t* pair_tiles, cudaStream_t st);
-void launch_dump_rows(const uint32_t* pair_off, uint32_t nprobe, uint32_t nq, uint64_t* row_off, uint32_t* row_len, cudaStream_t st);
-void launch_dump_collect(const float* dump, const uint32_t* pair_off, const uint32_t* probes, uint32_t nprobe, uint32_t nq, uint32_t k,
-                         const float* kth_val, const float* qnorm, float vn_max, const TcScale* scale, const uint32_t* list_g0,
-                         unsigned long long* cand, uint32_t* cand_cnt, uint32_t* overflow, uint32_t capq, cudaStream_t st);
+void launch_pair_tiles(const uint32_t* probes, size_t npairs, const uint32_t* list_ngroups, uint32_t* pair_tiles, cudaStream_t st);
+void launch_submin_rows(const uint32_t* pair_off, uint32_t nprobe, uint32_t nq, uint64_t* row_off, uint32_t* row_len, cudaStream_t st);
+void launch_bounds_apply(const float* sel_val, uint32_t nq, uint32_t k, float* gtop, cudaStream_t st);
 void launch_finalize(const FinalizeParams& p, cudaStream_t st);
 
 }  // namespace vidx
