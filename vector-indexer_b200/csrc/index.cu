@@ -387,7 +387,10 @@ void Index::delete_workspace() {
 
 constexpr uint64_t kCoarseTcMinLists = 1ull << 20;  // auto mode: measured slower than the exact FP32 stage up to nlist = 12 639
 constexpr uint64_t kBoundsPassMaxTiles = 2048;  // auto mode: bounds pass first when a query probes at most this many 128-vector tiles
-constexpr uint32_t kSeedTiles = 4;  // seeding pass: first 512 vectors of each query's nearest list
+constexpr uint32_t kSeedTiles = 4;  // coarse table: seeding pass over the first 512 rows
+// list scan, seeded flavour: a bounds pass over the heads of each query's (up to) kSeedRanks nearest lists,
+// kSeedBoundTiles tiles per query in all, gives every query a bound before the main pass starts
+constexpr uint32_t kSeedBoundTiles = 64, kSeedRanks = 4;
 
 // stats: distinct probed lists -> algorithmic bytes; (query, list) pairs -> logical bytes / flops
 __global__ void list_stats_kernel(const uint32_t* __restrict__ list_cnt, const uint32_t* __restrict__ list_len, uint32_t nlist,
@@ -536,6 +539,8 @@ void Index::search_device(const float* d_xq, uint64_t nq, uint64_t k_req, uint64
     // the minimum of every 32 columns, then the main pass with final bounds.  With many tile visits per query (a few
     // giant lists) the doubled tensor-core work costs more than the survivors it saves: seeding pass + main pass.
     // scan_mode 2 / 3 force the seeded / the two-pass flavour.
+    const uint32_t seed_ranks = std::max<uint32_t>(1, std::min<uint32_t>(np, kSeedRanks)), seed_rank_tiles = kSeedBoundTiles / seed_ranks;
+    const uint32_t seed_row = seed_ranks * seed_rank_tiles * 4;  // minima per query of the seeding bounds pass
     const uint64_t dump_tiles_per_q = tile_prefix[std::min<size_t>(np, tile_prefix.size() - 1)];
     const bool tc_dump = tc && scan_mode != 2 &&
                          (scan_mode == 3 ? (double)nq * (double)dump_tiles_per_q * 16.0 <= 8e9 : dump_tiles_per_q <= kBoundsPassMaxTiles);
@@ -685,26 +690,31 @@ void Index::search_device(const float* d_xq, uint64_t nq, uint64_t k_req, uint64
                 exclusive_scan_u32(w.pair_tiles.as<uint32_t>(), w.pair_off.as<uint32_t>(), npairs, w.scan_tmp.as<uint32_t>(), st);
                 launch_submin_rows(w.pair_off.as<uint32_t>(), np, nqb, w.row_off.as<uint64_t>(), w.row_len.as<uint32_t>(), st);
             }
-            // seeding pass: the same grouping restricted to each query's nearest list
+            // seeding pass: the same grouping restricted to the heads of each query's nearest lists
             if (!tc_dump) {
             w.list_cnt0.reserve(((size_t)nlist + 1) * 4);
             w.list_cur0.reserve(((size_t)nlist + 1) * 4);
             w.list_qoff0.reserve(((size_t)nlist + 1) * 4);
-            w.list_qlist0.reserve(std::max<size_t>(nqb, 1) * 8);
+            w.list_qlist0.reserve(std::max<size_t>((size_t)nqb * seed_ranks, 1) * 8);
             w.items_per_list0.reserve(((size_t)nlist + 1) * 4);
             w.item_off0.reserve(((size_t)nlist + 1) * 4);
             VIDX_CUDA(cudaMemsetAsync(w.list_cnt0.p, 0, ((size_t)nlist + 1) * 4, st));
             VIDX_CUDA(cudaMemsetAsync(w.list_cur0.p, 0, ((size_t)nlist + 1) * 4, st));
-            launch_tc_count(w.probes.as<uint32_t>(), npairs, np, true, d_list_seg.as<uint2>(), w.list_cnt0.as<uint32_t>(), st);
+            launch_tc_count(w.probes.as<uint32_t>(), npairs, np, seed_ranks, d_list_seg.as<uint2>(), w.list_cnt0.as<uint32_t>(), st);
             exclusive_scan_u32(w.list_cnt0.as<uint32_t>(), w.list_qoff0.as<uint32_t>(), nlist, w.scan_tmp.as<uint32_t>(), st);
-            launch_tc_fill(w.probes.as<uint32_t>(), npairs, np, true, d_list_seg.as<uint2>(), w.list_qoff0.as<uint32_t>(),
+            launch_tc_fill(w.probes.as<uint32_t>(), npairs, np, seed_ranks, d_list_seg.as<uint2>(), w.list_qoff0.as<uint32_t>(),
                            w.list_cur0.as<uint32_t>(), w.list_qlist0.as<uint2>(), st);
-            launch_tc_items(w.list_cnt0.as<uint32_t>(), d_list_ng.as<uint32_t>(), (uint32_t)nlist, nullptr, kSeedTiles, counters + 11,
+            launch_tc_items(w.list_cnt0.as<uint32_t>(), d_list_ng.as<uint32_t>(), (uint32_t)nlist, nullptr, seed_rank_tiles, counters + 11,
                             w.items_per_list0.as<uint32_t>(), st);
             exclusive_scan_u32(w.items_per_list0.as<uint32_t>(), w.item_off0.as<uint32_t>(), nlist, w.scan_tmp.as<uint32_t>(), st);
-            w.items0.reserve(((uint64_t)nqb / 32 + 2 * nlist + 64) * sizeof(TcItem));
+            w.items0.reserve(((uint64_t)nqb * seed_ranks / 32 + 2 * nlist + 64) * sizeof(TcItem));
             launch_tc_expand(w.list_cnt0.as<uint32_t>(), d_list_ng.as<uint32_t>(), d_list_g0.as<uint32_t>(), w.list_qoff0.as<uint32_t>(),
-                             w.item_off0.as<uint32_t>(), counters + 11, (uint32_t)nlist, kSeedTiles, w.items0.as<TcItem>(), st);
+                             w.item_off0.as<uint32_t>(), counters + 11, (uint32_t)nlist, seed_rank_tiles, w.items0.as<TcItem>(), st);
+            // the seeding pass's minima: one fixed-length row per query, +inf where a list has fewer tiles
+            w.dump.reserve(std::max<uint64_t>((uint64_t)nqb * seed_row, 1) * 4);
+            w.sel_pos.reserve((size_t)nqb * k * 4);
+            w.sel_val.reserve((size_t)nqb * k * 4);
+            launch_fill_u32(w.dump.as<uint32_t>(), 0x7f800000u, (size_t)nqb * seed_row, st);
             }
         }
         if (profiling) VIDX_CUDA(cudaEventRecord(ev[3], st));
@@ -731,13 +741,16 @@ void Index::search_device(const float* d_xq, uint64_t nq, uint64_t k_req, uint64
             tp.capq = capq;
             tp.k = (uint32_t)k;
             tp.vn_max = vn_max;
-            tp.seed_tiles = tc_dump ? 0 : kSeedTiles;
+            tp.seed_tiles = 0;
             tp.nprobe = np;
-            tp.submin = tc_dump ? w.dump.as<float>() : nullptr;
-            tp.pair_off = tc_dump ? w.pair_off.as<uint32_t>() : nullptr;
+            tp.submin = w.dump.as<float>();
+            tp.seed_ranks = seed_ranks;
+            tp.noinsert_tiles = seed_rank_tiles;
+            tp.pair_off = nullptr;
             if (!tc_dump) {
-                // pass 1: seed every query's bound from the head of its nearest list
-                tp.mode = 1;
+                // pass 1: seed every query's bound from the head of its nearest list (minima only, no survivors: the main
+                // pass sees those vectors again)
+                tp.mode = 2;
                 tp.list_cnt = w.list_cnt0.as<uint32_t>();
                 tp.list_qoff = w.list_qoff0.as<uint32_t>();
                 tp.list_qlist = w.list_qlist0.as<uint2>();
@@ -745,7 +758,11 @@ void Index::search_device(const float* d_xq, uint64_t nq, uint64_t k_req, uint64
                 tp.items = w.items0.as<TcItem>();
                 tp.work_counter = counters + 9;
                 launch_scan_tc(tp, st);
+                launch_select_topk(w.dump.as<float>(), nullptr, nullptr, seed_row, seed_row, nqb, (uint32_t)k, w.sel_pos.as<uint32_t>(),
+                                   w.sel_val.as<float>(), st);
+                launch_bounds_apply(w.sel_val.as<float>(), nqb, (uint32_t)k, w.gtop.as<float>(), st);
             }
+            tp.pair_off = tc_dump ? w.pair_off.as<uint32_t>() : nullptr;
             tp.list_cnt = w.list_cnt.as<uint32_t>();
             tp.list_qoff = w.list_qoff.as<uint32_t>();
             tp.list_qlist = w.list_qlist.as<uint2>();
@@ -763,6 +780,7 @@ void Index::search_device(const float* d_xq, uint64_t nq, uint64_t k_req, uint64
             // pass 2: everything else, starting from warm bounds (after a bounds pass: from final ones)
             tp.mode = 0;
             tp.frozen = tc_dump ? 1 : 0;
+            tp.noinsert_tiles = tc_dump ? 0 : seed_rank_tiles;
             tp.work_counter = counters + 8;
 #ifdef VIDX_TC_TIMING
             static DevBuf d_dbg;

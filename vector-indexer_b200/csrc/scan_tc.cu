@@ -315,23 +315,23 @@ __global__ void tc_scale_kernel(const uint32_t* __restrict__ qstats, int sv, int
 // ------------------------------------------------------------------------------------------
 // grouping by list
 // ------------------------------------------------------------------------------------------
-// rank0_only: only each query's nearest list (the seeding pass).
-__global__ void tc_count_kernel(const uint32_t* __restrict__ probes, size_t npairs, uint32_t nprobe, int rank0_only,
+// max_rank != 0: only each query's max_rank nearest lists (the seeding pass).
+__global__ void tc_count_kernel(const uint32_t* __restrict__ probes, size_t npairs, uint32_t nprobe, uint32_t max_rank,
                                 const uint2* __restrict__ list_seg, uint32_t* __restrict__ list_cnt) {
     size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= npairs) return;
-    if (rank0_only && (p % nprobe) != 0) return;
+    if (max_rank && (p % nprobe) >= max_rank) return;
     uint32_t l = probes[p];
     if (l == kNoRow) return;
     uint2 sr = list_seg[l];
     if (sr.y > sr.x) atomicAdd(&list_cnt[l], 1u);  // owned, non-empty list
 }
-__global__ void tc_fill_kernel(const uint32_t* __restrict__ probes, size_t npairs, uint32_t nprobe, int rank0_only,
+__global__ void tc_fill_kernel(const uint32_t* __restrict__ probes, size_t npairs, uint32_t nprobe, uint32_t max_rank,
                                const uint2* __restrict__ list_seg, const uint32_t* __restrict__ list_qoff,
                                uint32_t* __restrict__ list_cur, uint2* __restrict__ list_qlist) {
     size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= npairs) return;
-    if (rank0_only && (p % nprobe) != 0) return;
+    if (max_rank && (p % nprobe) >= max_rank) return;
     uint32_t l = probes[p];
     if (l == kNoRow) return;
     uint2 sr = list_seg[l];
@@ -598,7 +598,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
                 uint32_t dump_off = 0;
                 if (p.mode == 2) {
                     // bounds pass: no bounds yet; the row's sub-tile minima go to its (query, probe rank) row of submin
-                    if (qi.x != kNoRow) dump_off = p.pair_off[(size_t)qi.x * p.nprobe + qi.y];
+                    if (qi.x != kNoRow) dump_off = p.pair_off ? p.pair_off[(size_t)qi.x * p.nprobe + qi.y] : (qi.x * p.seed_ranks + qi.y) * p.noinsert_tiles;
                 } else if (qi.x != kNoRow) {
                     const uint32_t q = qi.x;
                     const float qn = p.qnorm[q];
@@ -759,6 +759,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
             volatile float* vr = s_r;
             uint32_t head = 0, refresh = 0, idle = 0, nstage = 0;
             const bool frozen = p.frozen != 0;
+            const uint32_t noinsert_tiles = p.noinsert_tiles, seed_ranks = p.seed_ranks;
             // survivors are staged in shared memory and appended to the per-query lists in bulk: four global
             // atomics in flight per lane instead of one round trip per batch; entries that fell outside the
             // row's bound meanwhile are dropped
@@ -830,7 +831,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
                 if (nstage > (uint32_t)kTcStageCap - 32u) flush();
                 // (2) state changes: one lane per distinct row folds ALL of that row's values of this batch into the
                 // row's set (threads queue their hits back to back, so a batch usually holds runs of one row)
-                const bool todo = cand_ok && !frozen && val < vr[row * kRS];
+                // (values of the seeded tiles are survivors but never enter the set: the set was initialised from them)
+                const bool seeded = s_q[row].y < seed_ranks && t0 + ((e.x >> 14) & 255u) < noinsert_tiles;
+                const bool todo = cand_ok && !frozen && !seeded && val < vr[row * kRS];
                 const unsigned tm = __ballot_sync(kFull, todo);
                 if (tm) {
                     s_tmpv[lane] = val;
@@ -1076,15 +1079,15 @@ __global__ void submin_rows_kernel(const uint32_t* __restrict__ pair_off, uint32
     row_off[q] = (uint64_t)a * 4;
     row_len[q] = (b - a) * 4;
 }
-// The k-th smallest minimum (accumulator units) becomes the query's whole top-k set: the main pass reads its bound from
-// the set's largest element.  Queries with fewer than k minima keep the empty set (bound +inf: all of their few
-// candidates are re-checked).
+// The k smallest minima (accumulator units; values of k distinct vectors) become the query's top-k set, stored descending:
+// the main pass reads its bound from the set's largest element.  Queries with fewer than k minima keep the empty set
+// (bound +inf).
 __global__ void bounds_apply_kernel(const float* __restrict__ sel_val /* [nq][k] ascending */, uint32_t nq, uint32_t k,
                                     float* __restrict__ gtop) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nq * k) return;
     const float kth = sel_val[(size_t)(i / k) * k + (k - 1)];
-    if (kth < __int_as_float(0x7f800000)) gtop[i] = kth;
+    if (kth < __int_as_float(0x7f800000)) gtop[i] = sel_val[(size_t)(i / k) * k + (k - 1 - i % k)];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1220,16 +1223,16 @@ void launch_tc_scale(const uint32_t* qstats, int sv, int g, int D, float vmax, f
     tc_scale_kernel<<<1, 1, 0, st>>>(qstats, sv, g, D, vmax, vn_max, out);
     VIDX_LAUNCHED();
 }
-void launch_tc_count(const uint32_t* probes, size_t npairs, uint32_t nprobe, bool rank0_only, const uint2* list_seg,
+void launch_tc_count(const uint32_t* probes, size_t npairs, uint32_t nprobe, uint32_t max_rank, const uint2* list_seg,
                      uint32_t* list_cnt, cudaStream_t st) {
     if (!npairs) return;
-    tc_count_kernel<<<(unsigned)ceil_div(npairs, 256), 256, 0, st>>>(probes, npairs, nprobe, rank0_only ? 1 : 0, list_seg, list_cnt);
+    tc_count_kernel<<<(unsigned)ceil_div(npairs, 256), 256, 0, st>>>(probes, npairs, nprobe, max_rank, list_seg, list_cnt);
     VIDX_LAUNCHED();
 }
-void launch_tc_fill(const uint32_t* probes, size_t npairs, uint32_t nprobe, bool rank0_only, const uint2* list_seg,
+void launch_tc_fill(const uint32_t* probes, size_t npairs, uint32_t nprobe, uint32_t max_rank, const uint2* list_seg,
                     const uint32_t* list_qoff, uint32_t* list_cur, uint2* list_qlist, cudaStream_t st) {
     if (!npairs) return;
-    tc_fill_kernel<<<(unsigned)ceil_div(npairs, 256), 256, 0, st>>>(probes, npairs, nprobe, rank0_only ? 1 : 0, list_seg, list_qoff,
+    tc_fill_kernel<<<(unsigned)ceil_div(npairs, 256), 256, 0, st>>>(probes, npairs, nprobe, max_rank, list_seg, list_qoff,
                                                                      list_cur, list_qlist);
     VIDX_LAUNCHED();
 }

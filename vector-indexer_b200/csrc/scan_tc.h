@@ -55,9 +55,12 @@ struct TcParams {
     float vn_max;                  // max |v|^2 over the stored rows
     unsigned long long* dbg;       // role timers (builds with -DVIDX_TC_TIMING only), else NULL
     float* submin;                 // bounds pass: the minimum of every 32 columns of every (query, probed tile): 4 floats per tile
-    const uint32_t* pair_off;      // bounds pass: first tile of pair (query * nprobe + rank) in submin
+    const uint32_t* pair_off;      // bounds pass: first tile of pair (query * nprobe + rank) in submin; null (seeding bounds pass) =
+                                   // (query * seed_ranks + rank) * noinsert_tiles
     uint32_t nprobe;
     uint32_t mode;                 // 0 = main pass, 1 = seeding pass (head of each query's nearest list only), 2 = bounds pass
+    uint32_t seed_ranks, noinsert_tiles;  // seeding bounds pass: the first noinsert_tiles tiles of each query's seed_ranks nearest lists;
+                                   // main pass after it: their values are survivors but never enter the row's set
     uint32_t frozen;               // main pass after a bounds pass: the bounds are final, survivors are only collected
     uint32_t seed_tiles;           // tiles per list covered by the seeding pass (0 = no seeding pass was run)
 };
@@ -96,9 +99,9 @@ void launch_convert16(const float4* vecs, int Dq, int Dh, const uint32_t* row_sr
 void launch_query_norms(const float4* xq4, int Dq, uint32_t nq, uint32_t k, float* qn, uint32_t* gthr_bits, uint32_t* cand_cnt,
                         uint32_t* overflow, float* gtop, uint32_t* glock, uint32_t* stats, cudaStream_t st);
 void launch_tc_scale(const uint32_t* qstats, int sv, int g, int D, float vmax, float vn_max, TcScale* out, cudaStream_t st);
-void launch_tc_count(const uint32_t* probes, size_t npairs, uint32_t nprobe, bool rank0_only, const uint2* list_seg,
+void launch_tc_count(const uint32_t* probes, size_t npairs, uint32_t nprobe, uint32_t max_rank, const uint2* list_seg,
                      uint32_t* list_cnt, cudaStream_t st);
-void launch_tc_fill(const uint32_t* probes, size_t npairs, uint32_t nprobe, bool rank0_only, const uint2* list_seg,
+void launch_tc_fill(const uint32_t* probes, size_t npairs, uint32_t nprobe, uint32_t max_rank, const uint2* list_seg,
                     const uint32_t* list_qoff, uint32_t* list_cur, uint2* list_qlist, cudaStream_t st);
 void launch_tc_items(const uint32_t* list_cnt, const uint32_t* list_ngroups, uint32_t nlist, unsigned long long* total,
                      uint32_t seed_tiles, uint32_t* chunk_out, uint32_t* items_per_list, cudaStream_t st);
