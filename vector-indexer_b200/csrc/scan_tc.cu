@@ -930,10 +930,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
                         if (valid) *reinterpret_cast<float2*>(p.submin + ((size_t)(submin_row0 + t) * 4 + half * 2)) = make_float2(m0, m1);
                         continue;
                     }
+#ifdef VIDX_TC_TIMING
+                    const long long _th0 = clock64();
+#endif
 #pragma unroll
                     for (int h = 0; h < 2; h++) {
                         const uint32_t cb = 2 * half + h;
                         const float* tv = acc + 32 * h;
+#ifdef VIDX_TC_TIMING
+                        {
+                            const unsigned hm = __ballot_sync(kFull, active && cb < ng && min32(tv) <= P);
+                            if (warp == 2 && lane == 0 && p.dbg && hm) {
+                                atomicAdd(&p.dbg[16 * blockIdx.x + 2], 1ull);
+                                atomicAdd(&p.dbg[16 * blockIdx.x + 3], (unsigned long long)__popc(hm));
+                            }
+                        }
+#endif
                         if (active && cb < ng && min32(tv) <= P) {
                             // rare path: this row has columns inside its bound (as of the latest bound)
                             P = fminf(P, lds_volatile_f(&s_P[row]));
@@ -971,6 +983,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
                             }
                         }
                     }
+#ifdef VIDX_TC_TIMING
+                    __syncwarp();
+                    if (warp == 2 && lane == 0 && p.dbg) atomicAdd(&p.dbg[16 * blockIdx.x + 15], (unsigned long long)(clock64() - _th0));
+#endif
                 }
                 tc_fence_before();
                 __syncwarp();
