@@ -605,7 +605,10 @@ void Index::search_device(const float* d_xq, uint64_t nq, uint64_t k_req, uint64
             w.dist.reserve((size_t)nqb * ldc * 4);
             launch_coarse_dist(d_cents.as<float4>(), (int)ncgroups, Dq, xq4, nqb, w.dist.as<float>(), ldc, st);
             if (profiling) VIDX_CUDA(cudaEventRecord(ev[1], st));
-            launch_select_topk(w.dist.as<float>(), nullptr, nullptr, ldc, (uint32_t)nlist, nqb, np, w.probes.as<uint32_t>(), pd, st);
+            if (np <= 32 && nlist <= 16384)
+                launch_select_small(w.dist.as<float>(), nullptr, nullptr, ldc, (uint32_t)nlist, nqb, np, w.probes.as<uint32_t>(), pd, st);
+            else
+                launch_select_topk(w.dist.as<float>(), nullptr, nullptr, ldc, (uint32_t)nlist, nqb, np, w.probes.as<uint32_t>(), pd, st);
         }
         if (profiling) VIDX_CUDA(cudaEventRecord(ev[2], st));
         if (coarse_only) {
@@ -758,7 +761,7 @@ void Index::search_device(const float* d_xq, uint64_t nq, uint64_t k_req, uint64
                 tp.items = w.items0.as<TcItem>();
                 tp.work_counter = counters + 9;
                 launch_scan_tc(tp, st);
-                launch_select_topk(w.dump.as<float>(), nullptr, nullptr, seed_row, seed_row, nqb, (uint32_t)k, w.sel_pos.as<uint32_t>(),
+                launch_select_small(w.dump.as<float>(), nullptr, nullptr, seed_row, seed_row, nqb, (uint32_t)k, w.sel_pos.as<uint32_t>(),
                                    w.sel_val.as<float>(), st);
                 launch_bounds_apply(w.sel_val.as<float>(), nqb, (uint32_t)k, w.gtop.as<float>(), st);
             }
@@ -773,7 +776,7 @@ void Index::search_device(const float* d_xq, uint64_t nq, uint64_t k_req, uint64
                 tp.mode = 2;
                 tp.work_counter = counters + 9;
                 launch_scan_tc(tp, st);
-                launch_select_topk(w.dump.as<float>(), w.row_off.as<uint64_t>(), w.row_len.as<uint32_t>(), 0, 0, nqb, (uint32_t)k,
+                launch_select_small(w.dump.as<float>(), w.row_off.as<uint64_t>(), w.row_len.as<uint32_t>(), 0, 0, nqb, (uint32_t)k,
                                    w.sel_pos.as<uint32_t>(), w.sel_val.as<float>(), st);
                 launch_bounds_apply(w.sel_val.as<float>(), nqb, (uint32_t)k, w.gtop.as<float>(), st);
             }

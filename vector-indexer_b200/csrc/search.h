@@ -23,6 +23,9 @@ void launch_coarse_dist(const float4* cents, int ngroups, int Dq, const float4* 
 uint32_t select_kcap(uint32_t k);
 void launch_select_topk(const float* vals, const uint64_t* row_off, const uint32_t* row_len, uint64_t ld, uint32_t n_fixed,
                         uint64_t nrows, uint32_t k, uint32_t* out_pos, float* out_val, cudaStream_t st);
+// the same for k <= 32 and short rows (one warp per row)
+void launch_select_small(const float* vals, const uint64_t* row_off, const uint32_t* row_len, uint64_t ld, uint32_t n_fixed,
+                        uint64_t nrows, uint32_t k, uint32_t* out_pos, float* out_val, cudaStream_t st);
 void launch_group_count(const uint32_t* probes, size_t npairs, uint32_t nprobe, const uint2* list_seg,
                         const uint32_t* only_flag, uint32_t* pair_ns, uint32_t* seg_cnt, cudaStream_t st);
 void launch_group_fill(const uint32_t* probes, size_t npairs, uint32_t nprobe, const uint2* list_seg,

@@ -385,6 +385,53 @@ select_topk_kernel(const float* __restrict__ vals, const uint64_t* __restrict__ 
     }
 }
 
+// Short rows, k <= 32: one warp per row keeps the 32 smallest (value, position) pairs sorted across its lanes (lane t =
+// t-th smallest) and inserts a candidate with one ballot and one shuffle; no shared memory, no block barriers.  Same
+// contract as select_topk_kernel (ties by position, +inf / NaN never selected, padding kNoRow / +inf); values of either
+// sign.
+__global__ void __launch_bounds__(256)
+select_small_kernel(const float* __restrict__ vals, const uint64_t* __restrict__ row_off, const uint32_t* __restrict__ row_len,
+                    uint64_t ld, uint32_t n_fixed, uint64_t nrows, uint32_t k, uint32_t* __restrict__ out_pos, float* __restrict__ out_val) {
+    const uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (r >= nrows) return;
+    const float* row = vals + (row_off ? row_off[r] : r * ld);
+    const uint32_t n = row_len ? row_len[r] : n_fixed;
+    const float kInf = __int_as_float(0x7f800000);
+    float my_d = kInf;
+    uint32_t my_p = kNoRow;
+    auto less = [](float d, uint32_t p, float d2, uint32_t p2) { return d < d2 || (d == d2 && p < p2); };
+    for (uint32_t base = 0; base < n; base += 32) {
+        const uint32_t i = base + lane;
+        const float v = i < n ? row[i] : kInf;
+        float kd = __shfl_sync(kFull, my_d, (int)k - 1);
+        uint32_t kp = __shfl_sync(kFull, my_p, (int)k - 1);
+        unsigned m = __ballot_sync(kFull, v < kInf && less(v, i, kd, kp));
+        while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            const float cd = __shfl_sync(kFull, v, src);
+            const uint32_t cp = base + (uint32_t)src;
+            const unsigned gm = __ballot_sync(kFull, less(cd, cp, my_d, my_p));  // lanes whose pair is greater: a suffix
+            if (!gm) continue;
+            const int pos = __ffs(gm) - 1;
+            const float up_d = __shfl_up_sync(kFull, my_d, 1);
+            const uint32_t up_p = __shfl_up_sync(kFull, my_p, 1);
+            if (lane == pos) {
+                my_d = cd;
+                my_p = cp;
+            } else if (lane > pos) {
+                my_d = up_d;
+                my_p = up_p;
+            }
+        }
+    }
+    if (lane < (int)k) {
+        if (out_pos) out_pos[r * k + lane] = my_p;
+        if (out_val) out_val[r * k + lane] = my_d;
+    }
+}
+
 // ------------------------------------------------------------------------------------
 // K3: grouping (query, probed list) -> per-segment query lists + result slots
 // (src/ivf_index.rs:223-246 groups probes by shard; here the unit is the segment).
@@ -1037,6 +1084,13 @@ void launch_select_topk(const float* vals, const uint64_t* row_off, const uint32
     }
     select_topk_kernel<<<(unsigned)nrows, kSelThreads, smem, st>>>(vals, row_off, row_len, ld, n_fixed, k, kcap, out_pos,
                                                                     out_val);
+    VIDX_LAUNCHED();
+}
+void launch_select_small(const float* vals, const uint64_t* row_off, const uint32_t* row_len, uint64_t ld, uint32_t n_fixed,
+                         uint64_t nrows, uint32_t k, uint32_t* out_pos, float* out_val, cudaStream_t st) {
+    if (!nrows || !k) return;
+    if (k > 32) throw ApiError(6, "select_small: k > 32");
+    select_small_kernel<<<(unsigned)ceil_div(nrows * 32, 256), 256, 0, st>>>(vals, row_off, row_len, ld, n_fixed, nrows, k, out_pos, out_val);
     VIDX_LAUNCHED();
 }
 void launch_group_count(const uint32_t* probes, size_t npairs, uint32_t nprobe, const uint2* list_seg,
