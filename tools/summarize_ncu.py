@@ -35,7 +35,7 @@ for row in r[2:]:
         if w in hdr: d[w] = {"value": row[hdr.index(w)], "unit": units[hdr.index(w)]}
     caps.append(d)
 json.dump({"command": "ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:scan_tc_kernel -c 2 python bench.py --steps 1 --warmup 3 --no-cpu-baseline --nprobe 8 --profile-window",
-           "launches": ["seeding pass (first 512 vectors of each query's nearest list)", "main pass"], "captures": caps}, open(f'{out}_ncu_scan_tc.json', 'w'), indent=1)
+           "launches": ["seeding bounds pass (minima only, heads of each query's four nearest lists)", "main pass"], "captures": caps}, open(f'{out}_ncu_scan_tc.json', 'w'), indent=1)
 # 3. dram traffic per step for bench.py's roofline.traffic
 def mb(c, k): return float(c[k]["value"].replace(',', '')) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1}[c[k]["unit"]]
 bench = [json.loads(l) for l in open(f'gpurun_out/bench_{tag}.json') if l.startswith('{')][-1]
