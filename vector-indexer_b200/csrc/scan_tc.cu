@@ -15,7 +15,7 @@
 //   distance: the k-th smallest L seen so far plus 2*eps*(|q|^2 + max|v|^2) + 2*c_abs, or a bound
 //   published by another CTA for the same query.  Every true top-k member survives.
 //
-//   Survivors (a hundred or two per query) get the reference's exact sequential fp32 distance in
+//   Survivors (a few dozen per query) get the reference's exact sequential fp32 distance in
 //   finalize_kernel, which then selects the top-k by (distance, probe rank, row) -- the same
 //   keys the exact scan kernels order by.  The final answer is bit-identical to the exact path.
 //
@@ -38,6 +38,11 @@
 //   warps 11, 13-15 selectors: each owns 32 query rows: their top-k sets and bounds, the hit queue of those rows,
 //                      staged appends of survivors to the per-query lists
 // Accumulators never leave the SM; HBM sees each list tile once per 128-query tile.
+//
+// Three launches of the one kernel: mode 2 = bounds pass (the epilogue only records the minimum of every 32 columns; the
+// k smallest minima of a query are its first top-k set), mode 0 = main pass (hit path, queues, selectors; "frozen" after
+// a bounds pass over everything the query probes: bounds are final, survivors are only collected), mode 1 = the older
+// seeding pass with the full hit path (still used by the tensor-core coarse stage).
 #include <cuda_fp16.h>
 
 #include "scan_tc.h"
