@@ -49,9 +49,11 @@
 
 namespace vidx {
 
-constexpr int kTcThreads = 512;       // warps 0, 12 producers; 1, 10 MMA (even / odd tiles); 2-9 epilogue; 11, 13, 14, 15 selectors (one per 32 query rows)
+constexpr int kTcThreads = 384;       // warp 0 producer; 1-8 epilogue; 9, 10 MMA (even / odd tiles); 11 selector.
+                                      // 12 warps, not 16: ptxas sizes registers for whole warpgroups, so 384 threads get 168 registers
+                                      // per thread instead of 128 for the epilogue's per-tile loop
 constexpr int kTcEpiWarps = 8;
-constexpr int kTcSelectors = 4;      // selector warps: each owns 32 query rows (one TMEM lane quarter), with its own hit queue and survivor staging
+constexpr int kTcSelectors = 1;      // selector warps: each owns 32 query rows (one TMEM lane quarter), with its own hit queue and survivor staging
 constexpr int kTcM = 128;            // queries per tile (UMMA M)
 constexpr int kTcSeedRows = 128;     // seeding pass: queries per work item (every row starts cold there; the four selectors share the flood)
 constexpr int kTcTileGroups = 4;     // 4 groups = 128 vectors per stage
@@ -549,6 +551,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
     // takes the even tiles of this CTA's tile sequence, pipeline 1 the odd ones.  (One ring shared by two issuers
     // would let an issuer run a whole ring ahead of the other, where a phase-parity wait reads a stale "ready".)
     uint32_t ks_it = 0;  // K-slices processed so far by this warp's pipeline (stage = 2*pipe + (ks_it & 1), phase = (ks_it >> 1) & 1)
+    uint32_t ks_it1 = 0; // (producer: the same for pipeline 1; ks_it is pipeline 0's)
 
     // Work items are claimed one ahead: while item i runs, the selector warp (idle during an item's set-up) claims
     // item i+1 and stages its record in shared memory.
@@ -581,8 +584,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
 
         // The producers start streaming this item's tiles at once (they need nothing but the record); everyone else
         // sets the item up behind two named barriers the producers do not take part in.
-        if (warp != 0 && warp != 12) {
-            constexpr int kSetupThreads = kTcThreads - 64;
+        if (warp != 0) {
+            constexpr int kSetupThreads = kTcThreads - 32;
             if (tid == 352) {  // (a selector warp) empty queues for this item
                 s_misc[4] = 0;
                 s_misc[8] = 0;
@@ -637,8 +640,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
                 // A tile = fp16(-2 * 2^sq * queries): [chunk of 8 dims][128 rows][16 B] (core matrices of 8 rows x
                 // 16 B, SBO 128 B, LBO 2048 B); dimensions beyond the query's are zero.  Warps 5-11 gather it while
                 // warps 1-4 fetch the row state.
-                constexpr int kGatherThreads = 10 * 32;  // warps 5-11 and 13-15 (the producer warp 12 is not here)
-                const int gt = warp >= 13 ? 224 + (warp - 13) * 32 + lane : tid - 160;
+                constexpr int kGatherThreads = 7 * 32;  // warps 5-11
+                const int gt = tid - 160;
                 for (int base = 0; base < Dh * kTcM; base += kGatherThreads * 4) {
                     float4 va[4], vb[4];
 #pragma unroll
@@ -676,40 +679,37 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
         }
 #endif
 
-        if (warp == 0 || warp == 12) {
-            // ===== producers (pipeline 0: warp 0, pipeline 1: warp 12).  The warp runs the loop converged
+        if (warp == 0) {
+            // ===== producer: feeds both pipelines' halves of the ring in tile order.  The warp runs the loop converged
             // (warp-uniform values), one elected lane issues.  A list chunk is one linear stream in HBM (tiles and
             // their K-slices are consecutive), so the source just advances. =====
-            const uint32_t pipe = warp == 0 ? 0u : 1u;
             const uint32_t tile_bytes = (uint32_t)Dh * kSuper * 16;
             const unsigned char* src = reinterpret_cast<const unsigned char*>(p.vecs16) + ((size_t)(g_list >> 2) + t0) * tile_bytes;
             const uint4* nsrc = p.vnorm + ((size_t)g_list + (size_t)t0 * kTcTileGroups) * 32;
-            const uint32_t skip = (pipe ^ it) & 1u;  // first tile of this item that belongs to this pipeline
-            src += (size_t)skip * tile_bytes;
-            nsrc += skip * kSuper;
-            for (uint32_t t = t0 + skip; t < t1; t += 2, nsrc += 2 * kSuper, src += 2 * (size_t)tile_bytes) {
-                const unsigned char* ssrc = src;
-                for (int kc = 0; kc < nkc; kc++, ks_it++) {
+            for (uint32_t t = t0; t < t1; t++, nsrc += kSuper) {
+                const uint32_t pipe = (it + (t - t0)) & 1u;
+                for (int kc = 0; kc < nkc; kc++) {
+                    const uint32_t cnt = pipe ? ks_it1++ : ks_it++;
                     const uint32_t nch = (uint32_t)min(kTcStageChunks, Dh - kc * kTcStageChunks);
                     const uint32_t bytes = nch * kSuper * 16;
-                    const uint32_t s = 2 * pipe + (ks_it & 1u), ph = (ks_it >> 1) & 1;
+                    const uint32_t s = 2 * pipe + (cnt & 1u), ph = (cnt >> 1) & 1;
                     { TC_T0(); mbar_wait(&bar_empty[s], ph ^ 1); TC_ACC(0 + pipe); }
                     const bool last = kc == nkc - 1;
                     if (elect_one()) {
                         mbar_expect_tx(&bar_full[s], bytes + (last ? 2048u : 0u));
-                        bulk_g2s(sB + s * kTcStageBytes, ssrc, bytes, &bar_full[s]);
+                        bulk_g2s(sB + s * kTcStageBytes, src, bytes, &bar_full[s]);
                         if (last) bulk_g2s(sB + s * kTcStageBytes + kTcStageData, nsrc, 2048, &bar_full[s]);
                     }
                     __syncwarp();
-                    ssrc += bytes;
+                    src += bytes;
                 }
             }
             it += t1 - t0;
-        } else if (warp == 1 || warp == 10) {
+        } else if (warp == 9 || warp == 10) {
             // ===== MMA issuers: warp 1 takes the even tiles of this CTA's tile sequence, warp 10 the odd ones
             // (one thread each; the loop is kept to a few dozen instructions per K-slice because a single
             // thread's issue latency, not the tensor pipe, would otherwise bound the kernel) =====
-            const uint32_t pipe = warp == 1 ? 0u : 1u;
+            const uint32_t pipe = warp == 9 ? 0u : 1u;
             {
                 // descriptor = lo | hi << 32; lo = start address >> 4 (14 bits) | LBO >> 4 << 16, hi = SBO >> 4 | version 1 << 14
                 const uint32_t desc_hi = (128u >> 4) | (1u << 14);
@@ -748,8 +748,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
                 }
                 it += t1 - t0;
             }
-        } else if (warp == 11 || warp >= 13) {
-            const uint32_t sel = warp == 11 ? 0u : (uint32_t)(warp - 12);
+        } else if (warp >= 11) {
+            const uint32_t sel = (uint32_t)(warp - 11);
             uint2* s_queue = s_queue_all + sel * kTcQueueCap;
             uint2* s_stage = s_stage_all + sel * kTcStageCap;
             float* s_stage_v = s_stage_v_all + sel * kTcStageCap;
@@ -813,7 +813,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
                 if (n == 0) {
                     if (lds_volatile(&s_misc[4]) == (uint32_t)kTcEpiWarps && lds_volatile(q_tail) == head) break;
                     if (++idle > (1u << 21)) __trap();  // an item never takes this long
-                    adopt((int)sel * 32 + lane);
+                    for (int a4 = 0; a4 < 4; a4++) adopt(a4 * 32 + lane);
                     continue;
                 }
                 idle = 0;
@@ -879,7 +879,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
                     }
                     __syncwarp();
                 }
-                if ((++refresh & 15u) == 0u) adopt((int)sel * 32 + lane);
+                if ((++refresh & 15u) == 0u)
+                    for (int a4 = 0; a4 < 4; a4++) adopt(a4 * 32 + lane);
             }
             flush();
             it += t1 - t0;
@@ -889,7 +890,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
             // query row of its group's tiles.  The accumulators already hold (1-eps)|v|^2 - 2 q.v (scaled), so a tile costs
             // one 3-input min per three columns and one branch per 32 =====
             const int quarter = warp & 3;        // TMEM lanes this warp may read: 32*quarter .. +31
-            const uint32_t grp = (uint32_t)(warp - 2) >> 2;
+            const uint32_t grp = (uint32_t)(warp - 1) >> 2;
             const int row = quarter * 32 + lane;
             const uint2 qi = s_q[row];
             const bool valid = qi.x != kNoRow;
@@ -902,7 +903,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
             for (int i = 0; i < KR; i++) lr[i] = i < (int)kk ? kInf : -kInf;
             // rows whose nearest list this is already scanned its first seed_tiles tiles in the seeding pass
             const bool skip_seeded = p.mode == 0 && qi.y == 0;
-            const uint32_t sel = (uint32_t)quarter;  // the selector of this warp's 32 rows
+            const uint32_t sel = 0;  // (one selector)
             uint2* s_queue = s_queue_all + sel * kTcQueueCap;
             uint32_t* q_tail = &s_misc[8 + 2 * sel];
             uint32_t* q_head = &s_misc[9 + 2 * sel];
@@ -919,7 +920,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
                 const uint32_t tl = t - t0, itt = it + tl;
                 const uint32_t s = itt & (kTcAccStages - 1), ph = (itt / kTcAccStages) & 1;
                 const float Pnew = lds_volatile_f(&s_P[row]);  // in flight during the wait
-                { TC_T0(); mbar_wait(&bar_tfull[s], ph); if (warp == 2) TC_ACC(8); }
+                { TC_T0(); mbar_wait(&bar_tfull[s], ph); if (warp == 1) TC_ACC(8); }
                 tc_fence_after();
                 const uint32_t ng = min((uint32_t)kTcTileGroups, ngl - t * kTcTileGroups);
                 const bool active = valid && !(skip_seeded && t < seed_tiles);
@@ -928,7 +929,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
                 for (uint32_t half = 0; half < 2; half++) {
                     float acc[64];
                     const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + s * 128 + half * 64;
-                    { TC_T0(); tc_ld32x2(tbase, tbase + 32, acc); if (warp == 2) TC_ACC(14); }
+                    { TC_T0(); tc_ld32x2(tbase, tbase + 32, acc); if (warp == 1) TC_ACC(14); }
                     if (p.mode == 2) {
                         // bounds pass: the minimum of each 32-column group (accumulator units; groups past the list: +inf)
                         const float m0 = 2 * half < ng ? min32(acc) : kInf, m1 = 2 * half + 1 < ng ? min32(acc + 32) : kInf;
@@ -945,7 +946,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
 #ifdef VIDX_TC_TIMING
                         {
                             const unsigned hm = __ballot_sync(kFull, active && cb < ng && min32(tv) <= P);
-                            if (warp == 2 && lane == 0 && p.dbg && hm) {
+                            if (warp == 1 && lane == 0 && p.dbg && hm) {
                                 atomicAdd(&p.dbg[16 * blockIdx.x + 2], 1ull);
                                 atomicAdd(&p.dbg[16 * blockIdx.x + 3], (unsigned long long)__popc(hm));
                             }
@@ -990,7 +991,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
                     }
 #ifdef VIDX_TC_TIMING
                     __syncwarp();
-                    if (warp == 2 && lane == 0 && p.dbg) atomicAdd(&p.dbg[16 * blockIdx.x + 15], (unsigned long long)(clock64() - _th0));
+                    if (warp == 1 && lane == 0 && p.dbg) atomicAdd(&p.dbg[16 * blockIdx.x + 15], (unsigned long long)(clock64() - _th0));
 #endif
                 }
                 tc_fence_before();
