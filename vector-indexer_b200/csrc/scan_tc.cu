@@ -925,7 +925,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
                 const uint32_t ng = min((uint32_t)kTcTileGroups, ngl - t * kTcTileGroups);
                 const bool active = valid && !(skip_seeded && t < seed_tiles);
                 P = fminf(P, Pnew);
-#pragma unroll 1
+#pragma unroll
                 for (uint32_t half = 0; half < 2; half++) {
                     float acc[64];
                     const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + s * 128 + half * 64;
