@@ -22,21 +22,23 @@
 // The index keeps an fp16 SHADOW of the vectors for this filter (same supergroup layout, 8 dims per 16-byte
 // chunk); the fp32 store stays the source of every distance that is returned.
 //
-// Kernel anatomy (one CTA per SM, persistent, 16 warps; a work item = 128 queries x up to 128 list tiles):
-//   warps 0, 12 producers : one cp.async.bulk (1-D TMA) per K-slice of a 128-vector tile -- the HBM layout keeps
+// Kernel anatomy (one CTA per SM, persistent, 12 warps -- ptxas sizes registers for whole warpgroups, so 384 threads get 168
+// registers each and the epilogue's per-tile loop neither spills nor rematerialises; a work item = 128 queries x up to 128
+// list tiles):
+//   warp 0 producer  : one cp.async.bulk (1-D TMA) per K-slice of a 128-vector tile -- the HBM layout keeps
 //                      a tile's chunks contiguous, so a list chunk is ONE linear stream -- into a ring of 32 KB
 //                      stages, plus the tile's norm terms; completion on mbarriers (complete_tx::bytes)
-//   warps 1, 10 MMA  : one elected thread issues tcgen05.mma.cta_group::1.kind::f16, M=128 queries x N=128
+//   warps 9, 10 MMA  : one elected thread issues tcgen05.mma.cta_group::1.kind::f16, M=128 queries x N=128
 //                      vectors x K=16 per instruction; operands are read from shared memory through no-swizzle
 //                      K-major descriptors: the chunk-major layout IS the UMMA core-matrix layout (8 rows x 16 B
 //                      contiguous, SBO = 128 B, LBO = 2048 B).  A last K-step multiplies (a,a,a,0..) by the
 //                      three fp16 terms of the row norm, so the accumulator holds the filter value itself.
-//                      Two independent pipelines (producer + issuer + half of the ring) alternate tiles.
-//   warps 2-9 epilogue: tcgen05.ld the 128x128 fp32 accumulator tile from TMEM (4 stages, 512 columns); two warps
-//                      per TMEM lane quarter, each thread owns one query row and 64 of the 128 columns: one 3-input
+//                      Two independent pipelines (issuer + half of the ring + two accumulator stages) alternate
+//                      tiles: one thread issues an N = 128 MMA only every ~125 cycles (tools/micro/mma_rate.cu).
+//   warps 1-8 epilogue: tcgen05.ld the 128x128 fp32 accumulator tile from TMEM (4 stages, 512 columns); two groups of
+//                      four warps (one per TMEM lane quarter) alternate tiles, each thread owns one query row: one 3-input
 //                      min per three columns, one branch per 32; hits go to a shared-memory queue
-//   warps 11, 13-15 selectors: each owns 32 query rows: their top-k sets and bounds, the hit queue of those rows,
-//                      staged appends of survivors to the per-query lists
+//   warp 11 selector : the rows' top-k sets and bounds, the hit queue, staged appends of survivors to the per-query lists
 // Accumulators never leave the SM; HBM sees each list tile once per 128-query tile.
 //
 // Three launches of the one kernel: mode 2 = bounds pass (the epilogue only records the minimum of every 32 columns; the
