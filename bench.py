@@ -215,6 +215,8 @@ def run_ours(args):
     ix = _ffi.Index(d, local).build(xb, seed=42, nlist=w["nlist"])
     if args.scan_mode:
         ix.set_scan_mode(args.scan_mode)
+    if args.coarse_mode:
+        ix.set_coarse_mode(args.coarse_mode)
     build_s = time.perf_counter() - t0
     # The library launches on the stream it is given; torch's legacy default stream has handle 0,
     # which the ABI reads as "use the handle's own stream", so run everything on an explicit
@@ -464,6 +466,7 @@ def main():
     ap.add_argument("--multi", default="index", choices=["index", "queries"],
                     help="N > 1: partition the index over the GPUs (default, north_star) or replicate it and split the batch")
     ap.add_argument("--scan-mode", type=int, default=0, help="experiments: vidx_set_scan_mode (0 = auto, what the bench line is quoted on)")
+    ap.add_argument("--coarse-mode", type=int, default=0, help="experiments: vidx_set_coarse_mode (0 = auto)")
     ap.add_argument("--profile-window", action="store_true",
                     help="bracket one warmed-up step with cudaProfilerStart/Stop (for ncu --profile-from-start off)")
     args = ap.parse_args()

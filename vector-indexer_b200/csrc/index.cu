@@ -387,7 +387,6 @@ void Index::delete_workspace() {
 
 constexpr uint64_t kCoarseTcMinLists = 1ull << 20;  // auto mode: measured slower than the exact FP32 stage up to nlist = 12 639
 constexpr uint64_t kBoundsPassMaxTiles = 2048;  // auto mode: bounds pass first when a query probes at most this many 128-vector tiles
-constexpr uint32_t kSeedTiles = 4;  // coarse table: seeding pass over the first 512 rows
 // list scan, seeded flavour: a bounds pass over the heads of each query's (up to) kSeedRanks nearest lists,
 // kSeedBoundTiles tiles per query in all, gives every query a bound before the main pass starts
 constexpr uint32_t kSeedBoundTiles = 64, kSeedRanks = 4;
@@ -409,7 +408,8 @@ __global__ void list_stats_kernel(const uint32_t* __restrict__ list_cnt, const u
 // (ascending distance, then list id = the stable sort of ivf_index.rs:215-220), with the reference's exact distances.
 struct CoarseWs {
     DevBuf probes0, list_cnt, list_cur, list_qoff, list_qlist, items_per_list, item_off, items, list_cnt0, list_cur0, list_qoff0, list_qlist0,
-        items_per_list0, item_off0, items0, qnorm, gthr, cand_cnt, overflow, cand, gtop, glock, tcscale, counters, scan_tmp, dist_tmp;
+        items_per_list0, item_off0, items0, qnorm, gthr, cand_cnt, overflow, cand, gtop, glock, tcscale, counters, scan_tmp, dist_tmp,
+        submin, sel_pos, sel_val;
 };
 void Index::coarse_tc(const float4* xq4, uint32_t nqb, uint32_t np, uint32_t* d_probes, float* d_probe_dist, cudaStream_t st) {
     static thread_local CoarseWs* cws = nullptr;  // per host thread, like the search workspace's use under the handle mutex
@@ -457,10 +457,14 @@ void Index::coarse_tc(const float4* xq4, uint32_t nqb, uint32_t np, uint32_t* d_
     exclusive_scan_u32(w.items_per_list.as<uint32_t>(), w.item_off.as<uint32_t>(), 1, w.scan_tmp.as<uint32_t>(), st);
     launch_tc_expand(w.list_cnt.as<uint32_t>(), ctab.list_ng.as<uint32_t>(), ctab.list_g0.as<uint32_t>(), w.list_qoff.as<uint32_t>(),
                      w.item_off.as<uint32_t>(), counters + 10, 1, 0, w.items.as<TcItem>(), st);
-    launch_tc_items(w.list_cnt.as<uint32_t>(), ctab.list_ng.as<uint32_t>(), 1, nullptr, kSeedTiles, counters + 11, w.items_per_list0.as<uint32_t>(), st);
-    exclusive_scan_u32(w.items_per_list0.as<uint32_t>(), w.item_off0.as<uint32_t>(), 1, w.scan_tmp.as<uint32_t>(), st);
-    launch_tc_expand(w.list_cnt.as<uint32_t>(), ctab.list_ng.as<uint32_t>(), ctab.list_g0.as<uint32_t>(), w.list_qoff.as<uint32_t>(),
-                     w.item_off0.as<uint32_t>(), counters + 11, 1, kSeedTiles, w.items0.as<TcItem>(), st);
+    // bounds pass over the whole table (it is short: nlist / 128 tiles per query): minima of every 32 centroids; the n_probe
+    // smallest of a query's minima bound its n_probe-th nearest centroid, and the main pass only collects what is within it
+    const uint32_t ntiles = (ncgroups + kTcTileGroups - 1) / kTcTileGroups;
+    const uint32_t sub_row = ntiles * kTcTileGroups;
+    w.submin.reserve(std::max<size_t>((size_t)nqb * sub_row, 1) * 4);
+    w.sel_pos.reserve((size_t)nqb * k * 4);
+    w.sel_val.reserve((size_t)nqb * k * 4);
+    launch_fill_u32(w.submin.as<uint32_t>(), 0x7f800000u, (size_t)nqb * sub_row, st);
     TcParams tp{};
     tp.vecs16 = ctab.vecs16.as<uint4>();
     tp.vnorm = ctab.vnorm.as<uint4>();
@@ -483,18 +487,24 @@ void Index::coarse_tc(const float4* xq4, uint32_t nqb, uint32_t np, uint32_t* d_
     tp.capq = capq;
     tp.k = k;
     tp.vn_max = ctab.vn_max;
-    tp.seed_tiles = kSeedTiles;
+    tp.seed_tiles = 0;
     tp.list_cnt = w.list_cnt.as<uint32_t>();
     tp.list_qoff = w.list_qoff.as<uint32_t>();
     tp.list_qlist = w.list_qlist.as<uint2>();
-    tp.mode = 1;
-    tp.item_off = w.item_off0.as<uint32_t>();
-    tp.items = w.items0.as<TcItem>();
-    tp.work_counter = counters + 9;
-    launch_scan_tc(tp, st);
-    tp.mode = 0;
     tp.item_off = w.item_off.as<uint32_t>();
     tp.items = w.items.as<TcItem>();
+    tp.nprobe = 1;
+    tp.submin = w.submin.as<float>();
+    tp.pair_off = nullptr;  // row of query q = q * seed_ranks * noinsert_tiles tiles
+    tp.seed_ranks = 1;
+    tp.noinsert_tiles = ntiles;
+    tp.mode = 2;
+    tp.work_counter = counters + 9;
+    launch_scan_tc(tp, st);
+    launch_select_small(w.submin.as<float>(), nullptr, nullptr, sub_row, sub_row, nqb, k, w.sel_pos.as<uint32_t>(), w.sel_val.as<float>(), st);
+    launch_bounds_apply(w.sel_val.as<float>(), nqb, k, w.gtop.as<float>(), st);
+    tp.mode = 0;
+    tp.frozen = 1;
     tp.work_counter = counters + 8;
     launch_scan_tc(tp, st);
     FinalizeParams fp{};

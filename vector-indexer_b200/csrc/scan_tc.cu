@@ -58,7 +58,6 @@ constexpr int kTcEpiWarps = 8;
 constexpr int kTcSelectors = 1;      // selector warps: each owns 32 query rows (one TMEM lane quarter), with its own hit queue and survivor staging
 constexpr int kTcM = 128;            // queries per tile (UMMA M)
 constexpr int kTcSeedRows = 128;     // seeding pass: queries per work item (every row starts cold there; the four selectors share the flood)
-constexpr int kTcTileGroups = 4;     // 4 groups = 128 vectors per stage
 constexpr int kTcMaxChunkTiles = 128; // tiles per work item: chosen on the device, 8..128 (1024..16384 vectors)
 // hit queue entries (power of two) and survivors staged by the selector before a bulk append; the 32-entry
 // top-k sets (k > 16) leave room for smaller ones only

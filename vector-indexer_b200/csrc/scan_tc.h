@@ -7,6 +7,8 @@ namespace vidx {
 // Power-of-two scales of one search batch, written on the device by tc_scale_kernel: stored vectors are scaled by
 // 2^sv when the fp16 shadow store is built (index constant), queries by 2^sq per batch, both to a largest
 // component in [2^6, 2^7), so products and sums stay far inside fp16 / fp32 range.
+constexpr int kTcTileGroups = 4;  // groups of 32 vectors per tile of the tensor-core scan: 128 vectors (UMMA N)
+
 struct TcScale {
     float S;        // 2^(sq+sv): an accumulator holds S * (filter value in real units)
     float invS;

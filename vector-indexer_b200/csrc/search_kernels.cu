@@ -118,7 +118,33 @@ __global__ void scan_apply_kernel(const uint32_t* __restrict__ in, const uint32_
     if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) out[n] = bsum[gridDim.x];
 }
 
+// n <= kScanTile: one block, one launch (the per-list prefix sums of a search are this short)
+__global__ void scan_single_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, size_t n) {
+    __shared__ uint32_t ws[32];
+    size_t base = (size_t)threadIdx.x * kScanItems;
+    uint32_t v[kScanItems];
+    uint32_t s = 0;
+#pragma unroll
+    for (int i = 0; i < kScanItems; i++) {
+        v[i] = (base + i < n) ? in[base + i] : 0;
+        s += v[i];
+    }
+    uint32_t tot;
+    uint32_t e = block_exclusive_scan(s, &tot, ws);
+#pragma unroll
+    for (int i = 0; i < kScanItems; i++) {
+        if (base + i < n) out[base + i] = e;
+        e += v[i];
+    }
+    if (threadIdx.x == 0) out[n] = tot;
+}
+
 void exclusive_scan_u32(const uint32_t* d_in, uint32_t* d_out, size_t n, uint32_t* d_tmp, cudaStream_t st) {
+    if (n <= (size_t)kScanTile) {
+        scan_single_kernel<<<1, kScanThreads, 0, st>>>(d_in, d_out, n);
+        VIDX_LAUNCHED();
+        return;
+    }
     size_t nb = ceil_div(n, kScanTile);
     if (nb == 0) nb = 1;
     scan_block_sums_kernel<<<(unsigned)nb, kScanThreads, 0, st>>>(d_in, d_tmp, n);
