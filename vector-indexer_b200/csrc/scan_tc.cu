@@ -324,27 +324,43 @@ __global__ void tc_scale_kernel(const uint32_t* __restrict__ qstats, int sv, int
 // grouping by list
 // ------------------------------------------------------------------------------------------
 // max_rank != 0: only each query's max_rank nearest lists (the seeding pass).
+// (a few giant lists take most pairs: the lanes of a warp that hit the same list share one atomic)
 __global__ void tc_count_kernel(const uint32_t* __restrict__ probes, size_t npairs, uint32_t nprobe, uint32_t max_rank,
                                 const uint2* __restrict__ list_seg, uint32_t* __restrict__ list_cnt) {
     size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= npairs) return;
-    if (max_rank && (p % nprobe) >= max_rank) return;
-    uint32_t l = probes[p];
-    if (l == kNoRow) return;
-    uint2 sr = list_seg[l];
-    if (sr.y > sr.x) atomicAdd(&list_cnt[l], 1u);  // owned, non-empty list
+    const int lane = threadIdx.x & 31;
+    bool ok = p < npairs && !(max_rank && (p % nprobe) >= max_rank);
+    uint32_t l = ok ? probes[p] : kNoRow;
+    ok = ok && l != kNoRow;
+    if (ok) {
+        uint2 sr = list_seg[l];
+        ok = sr.y > sr.x;  // owned, non-empty list
+    }
+    const unsigned okm = __ballot_sync(kFull, ok);
+    if (!ok) return;
+    const unsigned m = __match_any_sync(okm, l);
+    if (lane == __ffs(m) - 1) atomicAdd(&list_cnt[l], (uint32_t)__popc(m));
 }
 __global__ void tc_fill_kernel(const uint32_t* __restrict__ probes, size_t npairs, uint32_t nprobe, uint32_t max_rank,
                                const uint2* __restrict__ list_seg, const uint32_t* __restrict__ list_qoff,
                                uint32_t* __restrict__ list_cur, uint2* __restrict__ list_qlist) {
     size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= npairs) return;
-    if (max_rank && (p % nprobe) >= max_rank) return;
-    uint32_t l = probes[p];
-    if (l == kNoRow) return;
-    uint2 sr = list_seg[l];
-    if (sr.y <= sr.x) return;
-    uint32_t i = atomicAdd(&list_cur[l], 1u);
+    const int lane = threadIdx.x & 31;
+    bool ok = p < npairs && !(max_rank && (p % nprobe) >= max_rank);
+    uint32_t l = ok ? probes[p] : kNoRow;
+    ok = ok && l != kNoRow;
+    if (ok) {
+        uint2 sr = list_seg[l];
+        ok = sr.y > sr.x;
+    }
+    const unsigned okm = __ballot_sync(kFull, ok);
+    if (!ok) return;
+    const unsigned m = __match_any_sync(okm, l);
+    const int leader = __ffs(m) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(&list_cur[l], (uint32_t)__popc(m));
+    base = __shfl_sync(m, base, leader);
+    const uint32_t i = base + (uint32_t)__popc(m & ((1u << lane) - 1u));
     list_qlist[list_qoff[l] + i] = make_uint2((uint32_t)(p / nprobe), (uint32_t)(p % nprobe));
 }
 // Work items of list l = (#query tiles) x (#vector chunks), enumerated chunk-major so that CTAs
