@@ -378,7 +378,7 @@ struct Index::Workspace {
     DevBuf xq_pad, dist, probes, pair_ns, slot_off, seg_cnt, seg_qoff, seg_cur, seg_qlist, slot_seg, dense, sparse, counters,
         scan_tmp, cand_d, cand_r, alld, row_off, row_len, sel_pos, sel_val, rows, stats, slot_rank, list_cnt, list_cur, list_qoff,
         list_qlist, items_per_list, item_off, qnorm, gthr, cand_cnt, overflow, cand, list_cnt0, list_cur0, list_qoff0, list_qlist0,
-        items_per_list0, item_off0, gtop, glock, tcscale, items, items0, pair_tiles, pair_off, dump;
+        items_per_list0, item_off0, gtop, glock, tcscale, items, items0, pair_tiles, pair_off, dump, cand_val;
 };
 void Index::delete_workspace() {
     delete ws;
@@ -661,6 +661,7 @@ void Index::search_device(const float* d_xq, uint64_t nq, uint64_t k_req, uint64
             w.cand_cnt.reserve((size_t)nqb * 4);
             w.overflow.reserve((size_t)nqb * 4);
             w.cand.reserve((size_t)nqb * capq * 8);
+            w.cand_val.reserve((size_t)nqb * capq * 4);
             w.list_cur.reserve(((size_t)nlist + 1) * 4);
             w.list_qoff.reserve(((size_t)nlist + 1) * 4);
             w.list_qlist.reserve(std::max<size_t>(npairs, 1) * 8);
@@ -749,6 +750,7 @@ void Index::search_device(const float* d_xq, uint64_t nq, uint64_t k_req, uint64
             tp.glock = w.glock.as<uint32_t>();
             tp.gver = w.glock.as<uint32_t>() + nqb;
             tp.cand = w.cand.as<unsigned long long>();
+            tp.cand_val = w.cand_val.as<float>();
             tp.cand_cnt = w.cand_cnt.as<uint32_t>();
             tp.overflow = w.overflow.as<uint32_t>();
             tp.capq = capq;
@@ -869,6 +871,10 @@ void Index::search_device(const float* d_xq, uint64_t nq, uint64_t k_req, uint64
             fp.xq4 = xq4;
             if (tc) {
                 fp.cand = w.cand.as<unsigned long long>();
+                fp.cand_val = w.cand_val.as<float>();
+                fp.gthr_bits = w.gthr.as<uint32_t>();
+                fp.qnorm = w.qnorm.as<float>();
+                fp.scale = reinterpret_cast<const TcScale*>(w.tcscale.as<unsigned char>() + 16);
                 fp.cand_cnt = w.cand_cnt.as<uint32_t>();
                 fp.overflow = w.overflow.as<uint32_t>();
                 fp.capq = capq;

@@ -806,8 +806,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
 #pragma unroll
                     for (int u = 0; u < 4; u++) {
                         if (ok[u]) {
-                            if (gi[u] < p.capq) p.cand[(size_t)qq[u].x * p.capq + gi[u]] = ((unsigned long long)qq[u].y << 32) | rid[u];
-                            else p.overflow[qq[u].x] = 1u;
+                            if (gi[u] < p.capq) {
+                                p.cand[(size_t)qq[u].x * p.capq + gi[u]] = ((unsigned long long)qq[u].y << 32) | rid[u];
+                                if (p.cand_val) p.cand_val[(size_t)qq[u].x * p.capq + gi[u]] = s_stage_v[base + u * 32 + lane];
+                            } else {
+                                p.overflow[qq[u].x] = 1u;
+                            }
                         }
                     }
                 }
@@ -1177,10 +1181,48 @@ __global__ void finalize_kernel(FinalizeParams p) {
         if (brute) n = p.brute_rows;
         if (!ovf || brute) {
             const float4* q4 = p.xq4 + (size_t)q * p.Dq;
-            for (uint32_t base = 0; base < n; base += 32) {
-                uint32_t i = base + lane;
-                bool have = i < n;
-                unsigned long long key = have ? (brute ? (unsigned long long)i : p.cand[(size_t)q * p.capq + i]) : ~0ull;
+            // Survivors were collected under bounds that kept shrinking: most of the early ones lie above the query's final
+            // bound.  Their filter values (lower bounds of the distance) are compared with it first, and the rest is
+            // compacted through shared memory so that the distance gathers run on full batches.
+            __shared__ unsigned long long s_keep[4][64];
+            unsigned long long* keep = s_keep[(threadIdx.x >> 5) & 3];
+            const bool filt = !brute && p.cand_val != nullptr;
+            float U = __int_as_float(0x7f800000), base_t = 0.0f, invS = 0.0f;
+            if (filt) {
+                U = __uint_as_float(p.gthr_bits[q]);
+                base_t = (1.0f - kTcEps) * p.qnorm[q] - p.scale->c_abs;
+                invS = p.scale->invS;
+            }
+            uint32_t pend = 0;
+            for (uint32_t base0 = 0; base0 < n || pend; base0 += 32) {
+                unsigned long long key = ~0ull;
+                bool have = false;
+                if (filt) {
+                    const uint32_t i0 = base0 + lane;
+                    bool kp = false;
+                    unsigned long long kk0 = ~0ull;
+                    if (i0 < n) {
+                        kk0 = p.cand[(size_t)q * p.capq + i0];
+                        kp = __fmaf_rn(p.cand_val[(size_t)q * p.capq + i0], invS, base_t) <= U;
+                    }
+                    const unsigned km = __ballot_sync(kFull, kp);
+                    if (kp) keep[pend + __popc(km & ((1u << lane) - 1u))] = kk0;
+                    pend += __popc(km);
+                    __syncwarp();
+                    if (pend < 32 && base0 + 32 < n) continue;  // gather more before paying for a batch of distances
+                    const uint32_t take = min(pend, 32u);
+                    have = (uint32_t)lane < take;
+                    if (have) key = keep[lane];
+                    __syncwarp();
+                    if (pend > 32 && (uint32_t)lane < pend - 32) keep[lane] = keep[32 + lane];  // (pend <= 63)
+                    pend -= take;
+                    __syncwarp();
+                    if (!take) continue;
+                } else {
+                    const uint32_t i = base0 + lane;
+                    have = i < n;
+                    key = have ? (brute ? (unsigned long long)i : p.cand[(size_t)q * p.capq + i]) : ~0ull;
+                }
                 float d = have ? exact_row_distance(p.vecs, p.Dq, (uint32_t)key, q4) : __int_as_float(0x7f800000);
                 float td = __shfl_sync(kFull, fd, k - 1);
                 unsigned long long tk = __shfl_sync(kFull, fk, k - 1);

@@ -60,6 +60,7 @@ struct TcParams {
     const uint32_t* pair_off;      // bounds pass: first tile of pair (query * nprobe + rank) in submin; null (seeding bounds pass) =
                                    // (query * seed_ranks + rank) * noinsert_tiles
     uint32_t nprobe;
+    float* cand_val;               // optional: filter value (accumulator units) of every survivor, parallel to cand
     uint32_t mode;                 // 0 = main pass, 1 = seeding pass (head of each query's nearest list only), 2 = bounds pass
     uint32_t seed_ranks, noinsert_tiles;  // seeding bounds pass: the first noinsert_tiles tiles of each query's seed_ranks nearest lists;
                                    // main pass after it: their values are survivors but never enter the row's set
@@ -77,6 +78,12 @@ struct FinalizeParams {
     const uint32_t* cand_cnt;
     const uint32_t* overflow;
     uint32_t capq;
+    // optional: the survivors' filter values (accumulator units) and what converts them -- a survivor whose lower bound
+    // exceeds the query's final published bound (gthr) is skipped without a distance computation
+    const float* cand_val;
+    const uint32_t* gthr_bits;
+    const float* qnorm;
+    const TcScale* scale;
     uint32_t brute_rows;  // != 0: a query flagged in `overflow` is answered by checking rows 0..brute_rows-1 exactly (one-list tables)
     // exact-path slots (slot_off == nullptr: none)
     const uint32_t* slot_off;
