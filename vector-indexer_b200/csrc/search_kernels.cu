@@ -427,7 +427,33 @@ select_small_kernel(const float* __restrict__ vals, const uint64_t* __restrict__
     float my_d = kInf;
     uint32_t my_p = kNoRow;
     auto less = [](float d, uint32_t p, float d2, uint32_t p2) { return d < d2 || (d == d2 && p < p2); };
-    for (uint32_t base = 0; base < n; base += 32) {
+    uint32_t first = 0;
+    if (n) {
+        // the first 32 entries: a bitonic sort across the lanes instead of 32 serial insertions
+        const float v = (uint32_t)lane < n ? row[lane] : kInf;
+        if (v < kInf) {
+            my_d = v;
+            my_p = (uint32_t)lane;
+        }
+#pragma unroll
+        for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                const float od = __shfl_xor_sync(kFull, my_d, stride);
+                const uint32_t op = __shfl_xor_sync(kFull, my_p, stride);
+                const bool up = (lane & size) == 0;            // ascending block
+                const bool lower = (lane & stride) == 0;       // this lane keeps the smaller of the pair in an ascending block
+                const bool take_min = up == lower;
+                const bool o_less = less(od, op, my_d, my_p);
+                if (take_min == o_less) {
+                    my_d = od;
+                    my_p = op;
+                }
+            }
+        }
+        first = 32;
+    }
+    for (uint32_t base = first; base < n; base += 32) {
         const uint32_t i = base + lane;
         const float v = i < n ? row[i] : kInf;
         float kd = __shfl_sync(kFull, my_d, (int)k - 1);
