@@ -198,7 +198,7 @@ typedef struct vidx_search_stats {
     double ms_scan_tc;               /* the tensor-core scan kernel alone (part of ms_scan) */
     uint64_t n_tc_items, n_tc_survivors, n_tc_overflow; /* work items, candidates re-checked exactly, queries redone exactly */
     uint64_t tc_mma_flops;           /* 2*D per (query, vector) pair issued to the tensor cores */
-    uint64_t n_tc_dump_values;       /* sub-tile minima reserved for the bounds pass (0 = the seeded flavour ran) */
+    uint64_t n_tc_submin_slots;       /* sub-tile minima reserved for the bounds pass (0 = the seeded flavour ran) */
 } vidx_search_stats;
 /* Enable per-stage CUDA-event timing (adds stream synchronisation at the end of a
  * search); stats describe the last completed search on this handle. */

@@ -19,7 +19,7 @@ for mode, npb in ((2, 1), (3, 1), (2, 4), (3, 4), (2, 16), (3, 16), (2, 64), (3,
         ix.search_device(d_xq.data_ptr(), nq, k, npb, d_D.data_ptr(), d_I.data_ptr(), ts.cuda_stream); torch.cuda.synchronize()
     s = ix.stats()
     t = s['ms_scan_tc'] / 1e3
-    print('mode', mode, 'nprobe', npb, 'submin slots', s['n_tc_dump_values'], {kk: round(s[kk], 4) for kk in s if kk.startswith('ms_')}, 'alg GB', s['scan_bytes_algorithmic'] / 1e9, 'GB/s', s['scan_bytes_algorithmic'] / t / 1e9, 'pairs', s['n_pairs'], 'surv', s['n_tc_survivors'], 'ovf', s['n_tc_overflow'], 'items', s['n_tc_items'])
+    print('mode', mode, 'nprobe', npb, 'submin slots', s['n_tc_submin_slots'], {kk: round(s[kk], 4) for kk in s if kk.startswith('ms_')}, 'alg GB', s['scan_bytes_algorithmic'] / 1e9, 'GB/s', s['scan_bytes_algorithmic'] / t / 1e9, 'pairs', s['n_pairs'], 'surv', s['n_tc_survivors'], 'ovf', s['n_tc_overflow'], 'items', s['n_tc_items'])
 ix.set_scan_mode(1)
 for npb in (1,):
     for _ in range(3):

@@ -941,7 +941,7 @@ void Index::search_device(const float* d_xq, uint64_t nq, uint64_t k_req, uint64
                     stats.n_tc_overflow += of[i] ? 1 : 0;
                 }
                 stats.tc_mma_flops += h[1] * 2ull * 8 * tc_dh((int)dim);
-                if (tc_dump) stats.n_tc_dump_values += (uint64_t)nqb * dump_tiles_per_q * 4;
+                if (tc_dump) stats.n_tc_submin_slots += (uint64_t)nqb * dump_tiles_per_q * 4;
             }
         }
     }

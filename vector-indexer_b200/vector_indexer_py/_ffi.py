@@ -27,7 +27,7 @@ class SearchStats(C.Structure):
     _fields_ = [(n, C.c_double) for n in ("ms_coarse", "ms_select", "ms_group", "ms_scan", "ms_merge", "ms_total")] + [
         (n, u64) for n in ("scan_bytes_algorithmic", "scan_bytes_logical", "scan_flops", "coarse_flops", "n_pairs",
                            "n_dense_items", "n_sparse_items", "kernel_launches")] + [("ms_scan_tc", C.c_double)] + [
-        (n, u64) for n in ("n_tc_items", "n_tc_survivors", "n_tc_overflow", "tc_mma_flops", "n_tc_dump_values")]
+        (n, u64) for n in ("n_tc_items", "n_tc_survivors", "n_tc_overflow", "tc_mma_flops", "n_tc_submin_slots")]
 
     def asdict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
