@@ -389,7 +389,10 @@ constexpr uint64_t kCoarseTcMinLists = 1ull << 20;  // auto mode: measured slowe
 constexpr uint64_t kBoundsPassMaxTiles = 2048;  // auto mode: bounds pass first when a query probes at most this many 128-vector tiles
 // list scan, seeded flavour: a bounds pass over the heads of each query's (up to) kSeedRanks nearest lists,
 // kSeedBoundTiles tiles per query in all, gives every query a bound before the main pass starts
-constexpr uint32_t kSeedBoundTiles = 64, kSeedRanks = 4;
+#ifndef VIDX_SEED_TILES
+#define VIDX_SEED_TILES 64
+#endif
+constexpr uint32_t kSeedBoundTiles = VIDX_SEED_TILES, kSeedRanks = 4;
 
 // stats: distinct probed lists -> algorithmic bytes; (query, list) pairs -> logical bytes / flops
 __global__ void list_stats_kernel(const uint32_t* __restrict__ list_cnt, const uint32_t* __restrict__ list_len, uint32_t nlist,
