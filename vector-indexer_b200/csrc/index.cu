@@ -410,8 +410,7 @@ __global__ void list_stats_kernel(const uint32_t* __restrict__ list_cnt, const u
 // filter + exact re-check as the list scan yields each query's n_probe nearest centroids in the reference's order
 // (ascending distance, then list id = the stable sort of ivf_index.rs:215-220), with the reference's exact distances.
 struct CoarseWs {
-    DevBuf probes0, list_cnt, list_cur, list_qoff, list_qlist, items_per_list, item_off, items, list_cnt0, list_cur0, list_qoff0, list_qlist0,
-        items_per_list0, item_off0, items0, qnorm, gthr, cand_cnt, overflow, cand, gtop, glock, tcscale, counters, scan_tmp, dist_tmp,
+    DevBuf probes0, list_cnt, list_cur, list_qoff, list_qlist, items_per_list, item_off, items, qnorm, gthr, cand_cnt, overflow, cand, gtop, glock, tcscale, counters, scan_tmp, dist_tmp,
         submin, sel_pos, sel_val;
 };
 void Index::coarse_tc(const float4* xq4, uint32_t nqb, uint32_t np, uint32_t* d_probes, float* d_probe_dist, cudaStream_t st) {
@@ -424,11 +423,8 @@ void Index::coarse_tc(const float4* xq4, uint32_t nqb, uint32_t np, uint32_t* d_
     w.probes0.reserve((size_t)nqb * 4);
     w.counters.reserve(64);
     w.scan_tmp.reserve(exclusive_scan_tmp_entries(4) * 4 + 64);
-    for (DevBuf* b : {&w.list_cnt, &w.list_cur, &w.list_qoff, &w.items_per_list, &w.item_off, &w.list_cnt0, &w.list_cur0, &w.list_qoff0,
-                      &w.items_per_list0, &w.item_off0})
-        b->reserve(16);
+    for (DevBuf* b : {&w.list_cnt, &w.list_cur, &w.list_qoff, &w.items_per_list, &w.item_off}) b->reserve(16);
     w.list_qlist.reserve((size_t)nqb * 8);
-    w.list_qlist0.reserve((size_t)nqb * 8);
     w.qnorm.reserve((size_t)nqb * 4);
     w.gthr.reserve((size_t)nqb * 4);
     w.cand_cnt.reserve((size_t)nqb * 4);
@@ -440,18 +436,16 @@ void Index::coarse_tc(const float4* xq4, uint32_t nqb, uint32_t np, uint32_t* d_
     w.dist_tmp.reserve((size_t)nqb * k * 4);
     const uint64_t tiles = ncgroups / 4 + 1;
     w.items.reserve(((nqb / 128 + 1) * tiles / 8 + 8 * 160 + nqb / 128 + 64) * sizeof(TcItem));
-    w.items0.reserve(((uint64_t)nqb / 32 + 64) * sizeof(TcItem));
     uint32_t* counters = w.counters.as<uint32_t>();
     VIDX_CUDA(cudaMemsetAsync(w.probes0.p, 0, (size_t)nqb * 4, st));
     VIDX_CUDA(cudaMemsetAsync(w.counters.p, 0, 64, st));
     VIDX_CUDA(cudaMemsetAsync(w.tcscale.p, 0, 64, st));
-    for (DevBuf* b : {&w.list_cnt, &w.list_cur, &w.list_cnt0, &w.list_cur0}) VIDX_CUDA(cudaMemsetAsync(b->p, 0, 16, st));
+    for (DevBuf* b : {&w.list_cnt, &w.list_cur}) VIDX_CUDA(cudaMemsetAsync(b->p, 0, 16, st));
     const uint2* lseg = ctab.list_seg.as<uint2>();
     launch_query_norms(xq4, Dq, nqb, k, w.qnorm.as<float>(), w.gthr.as<uint32_t>(), w.cand_cnt.as<uint32_t>(), w.overflow.as<uint32_t>(),
                        w.gtop.as<float>(), w.glock.as<uint32_t>(), w.tcscale.as<uint32_t>(), st);
     launch_tc_scale(w.tcscale.as<uint32_t>(), ctab.sv, ctab.g, (int)dim, ctab.vmax, ctab.vn_max,
                     reinterpret_cast<TcScale*>(w.tcscale.as<unsigned char>() + 16), st);
-    // main grouping and the seeding grouping coincide here (one list, every pair has rank 0)
     launch_tc_count(w.probes0.as<uint32_t>(), nqb, 1, false, lseg, w.list_cnt.as<uint32_t>(), st);
     exclusive_scan_u32(w.list_cnt.as<uint32_t>(), w.list_qoff.as<uint32_t>(), 1, w.scan_tmp.as<uint32_t>(), st);
     launch_tc_fill(w.probes0.as<uint32_t>(), nqb, 1, false, lseg, w.list_qoff.as<uint32_t>(), w.list_cur.as<uint32_t>(), w.list_qlist.as<uint2>(), st);
@@ -490,7 +484,6 @@ void Index::coarse_tc(const float4* xq4, uint32_t nqb, uint32_t np, uint32_t* d_
     tp.capq = capq;
     tp.k = k;
     tp.vn_max = ctab.vn_max;
-    tp.seed_tiles = 0;
     tp.list_cnt = w.list_cnt.as<uint32_t>();
     tp.list_qoff = w.list_qoff.as<uint32_t>();
     tp.list_qlist = w.list_qlist.as<uint2>();
@@ -759,7 +752,6 @@ void Index::search_device(const float* d_xq, uint64_t nq, uint64_t k_req, uint64
             tp.capq = capq;
             tp.k = (uint32_t)k;
             tp.vn_max = vn_max;
-            tp.seed_tiles = 0;
             tp.nprobe = np;
             tp.submin = w.dump.as<float>();
             tp.seed_ranks = seed_ranks;

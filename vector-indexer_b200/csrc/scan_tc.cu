@@ -41,10 +41,9 @@
 //   warp 11 selector : the rows' top-k sets and bounds, the hit queue, staged appends of survivors to the per-query lists
 // Accumulators never leave the SM; HBM sees each list tile once per 128-query tile.
 //
-// Three launches of the one kernel: mode 2 = bounds pass (the epilogue only records the minimum of every 32 columns; the
-// k smallest minima of a query are its first top-k set), mode 0 = main pass (hit path, queues, selectors; "frozen" after
-// a bounds pass over everything the query probes: bounds are final, survivors are only collected), mode 1 = the older
-// seeding pass with the full hit path (still used by the tensor-core coarse stage).
+// Two launches of the one kernel: mode 2 = bounds pass (the epilogue only records the minimum of every 32 columns; the
+// k smallest minima of a query are its first top-k set), mode 0 = main pass (hit path, queues, selector; "frozen" after
+// a bounds pass over everything the query probes: bounds are final, survivors are only collected).
 #include <cuda_fp16.h>
 
 #include "scan_tc.h"
@@ -926,14 +925,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
             const uint2 qi = s_q[row];
             const bool valid = qi.x != kNoRow;
             const float delta = s_delta[row];
-            const uint32_t seed_tiles = p.seed_tiles, kk = p.k;
+            const uint32_t kk = p.k;
             const uint32_t submin_row0 = s_impr[row];  // bounds pass only
             float P = s_P[row];
             float lr[KR];  // the k smallest values this thread queued in this item, descending (+inf until k exist)
 #pragma unroll
             for (int i = 0; i < KR; i++) lr[i] = i < (int)kk ? kInf : -kInf;
-            // rows whose nearest list this is already scanned its first seed_tiles tiles in the seeding pass
-            const bool skip_seeded = p.mode == 0 && qi.y == 0;
             const uint32_t sel = 0;  // (one selector)
             uint2* s_queue = s_queue_all + sel * kTcQueueCap;
             uint32_t* q_tail = &s_misc[8 + 2 * sel];
@@ -954,7 +951,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
                 { TC_T0(); mbar_wait(&bar_tfull[s], ph); if (warp == 1) TC_ACC(8); }
                 tc_fence_after();
                 const uint32_t ng = min((uint32_t)kTcTileGroups, ngl - t * kTcTileGroups);
-                const bool active = valid && !(skip_seeded && t < seed_tiles);
+                const bool active = valid;
                 P = fminf(P, Pnew);
 #pragma unroll
                 for (uint32_t half = 0; half < 2; half++) {

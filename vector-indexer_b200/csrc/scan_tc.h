@@ -61,11 +61,10 @@ struct TcParams {
                                    // (query * seed_ranks + rank) * noinsert_tiles
     uint32_t nprobe;
     float* cand_val;               // optional: filter value (accumulator units) of every survivor, parallel to cand
-    uint32_t mode;                 // 0 = main pass, 1 = seeding pass (head of each query's nearest list only), 2 = bounds pass
+    uint32_t mode;                 // 0 = main pass, 2 = bounds pass (minima only)
     uint32_t seed_ranks, noinsert_tiles;  // seeding bounds pass: the first noinsert_tiles tiles of each query's seed_ranks nearest lists;
                                    // main pass after it: their values are survivors but never enter the row's set
     uint32_t frozen;               // main pass after a bounds pass: the bounds are final, survivors are only collected
-    uint32_t seed_tiles;           // tiles per list covered by the seeding pass (0 = no seeding pass was run)
 };
 
 struct FinalizeParams {
