@@ -203,10 +203,12 @@ typedef struct vidx_search_stats {
 /* Enable per-stage CUDA-event timing (adds stream synchronisation at the end of a
  * search); stats describe the last completed search on this handle. */
 int vidx_set_profiling(vidx_index* idx, int enabled);
-/* Scan algorithm: 0 (default) = tcgen05 FP16 filter + exact re-check whenever the shape allows (k <= 32, finite data):
- * seeding pass + main pass when a query visits many 128-vector tiles (tensor-bound), bounds pass + main pass when it
- * visits at most 2048 (the HBM-bound regime); 1 = exact FP32 kernels only; 2 / 3 = the filter with the
- * seeding pass only / with the bounds pass whenever its minima fit in 8 GB.  Results are bit-identical in every mode. */
+/* Scan algorithm: 0 (default) = tcgen05 FP16 filter + exact re-check whenever the shape allows (k <= 32, finite data).
+ * The filter runs a bounds pass (minima only) and a main pass: when a query visits many 128-vector tiles (tensor-bound) the
+ * bounds pass covers the heads of its nearest lists and the main pass keeps tightening the bounds; when it visits at most
+ * 2048 tiles (the HBM-bound regime) the bounds pass covers everything and the main pass only collects.
+ * 1 = exact FP32 kernels only; 2 / 3 = force the first / the second flavour of the filter (the second whenever its minima fit
+ * in 8 GB).  Results are bit-identical in every mode. */
 int vidx_set_scan_mode(vidx_index* idx, int mode);
 /* Coarse quantization (ivf_index.rs:205-220): 0 = auto (today: the exact FP32 kernels -- the tensor-core filter measured
  * no faster up to nlist = 12 639), 1 = exact kernels only, 2 = tensor-core filter + exact re-check whenever
