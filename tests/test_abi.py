@@ -25,6 +25,21 @@ def test_library_exports_every_declared_symbol(ffi):
     assert set(declared) <= exported
 
 
+def test_stats_struct_layout_matches_the_header(ffi, tmp_path):
+    # the ctypes mirror of vidx_search_stats must have the C compiler's layout: field offsets and size
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    fields = [n for n, _ in ffi.SearchStats._fields_]
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "vidx_b200.h"\nint main(void) {\n'
+                   + "".join(f'  printf("{n} %zu\\n", offsetof(vidx_search_stats, {n}));\n' for n in fields)
+                   + '  printf("sizeof %zu\\n", sizeof(vidx_search_stats));\n  return 0;\n}\n')
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)])
+    out = dict(ln.split() for ln in subprocess.check_output([str(exe)]).decode().splitlines())
+    assert int(out.pop("sizeof")) == C.sizeof(ffi.SearchStats)
+    assert {n: int(v) for n, v in out.items()} == {n: getattr(ffi.SearchStats, n).offset for n in fields}
+
+
 def test_library_is_sm100a_cuda_code(ffi):
     out = subprocess.run(["cuobjdump", "-lelf", ffi.LIB_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in out, out[:500]
