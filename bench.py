@@ -6,14 +6,17 @@ Metric (BASELINE.json): search QPS at recall@10 >= 0.9 on synthetic SIFT-1M-shap
 
   python bench.py [--gpus N] [--steps K] [--warmup W]          our CUDA path
   python bench.py --impl reference [...]                        the reference's CPU algorithm (oracle port)
+  python bench.py --config c4 --gpus N                          another BASELINE config as the timed workload
 
 One "step" = one search of the whole nq-query batch at the smallest n_probe of the sweep
-{1,2,4,...} whose recall@10 (set intersection against exact brute force) is >= 0.9.
-`value`  : QPS with queries and index resident in HBM (vidx_search_device), CUDA events.
-`e2e`    : QPS through vidx_search with pinned HOST buffers (H2D + D2H inside the timed region).
-N > 1    : every rank holds the shards it owns (vidx_set_partition), queries are replicated,
-           per-rank top-k are exchanged with one NCCL all-gather and merged on the device;
-           strong scaling (total work fixed), max-over-ranks time.
+{1,2,4,...} whose recall@10 (set intersection against an independent float64 brute force) is >= 0.9.
+`value`  : QPS with queries and index resident in HBM (vidx_search_device / vidx_search_multi_device), CUDA events.
+`e2e`    : QPS through vidx_search / vidx_search_multi with pinned HOST buffers (H2D + D2H inside the timed region).
+N > 1    : one process per GPU.  Every rank declares its partition BEFORE the build (vidx_set_partition), so only the part
+           it owns ever reaches its HBM; queries are replicated; the exchange (probe lists, then ONE packed all-gather of the
+           per-rank top-k + device merge) runs inside the library over its own NCCL communicator (vidx_comm_init).  Strong
+           scaling (the 10 k-query batch is the fixed total work), max-over-ranks time.  The line also carries `c4`: the
+           10M x 128 sharded config (BASELINE configs[3]) measured the same way on the same ranks.
 Inputs are larger than L2 (512 MB index vs 126 MB), so no explicit L2 flush between steps.
 """
 import argparse
@@ -35,6 +38,14 @@ METRIC = "search QPS at recall@10>=0.9 (SIFT-1M shape, nq=10k)"
 UNIT = "queries/s"
 FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12  # 74.4: SMs x lanes x 2 x max SM clock (no FP32 figure in MEASURED_PEAKS)
 
+# BASELINE.json configs: (n, d, nlist (0 = the reference heuristic, utils.rs:9-16), default n_probe (0 = from the recall sweep))
+CONFIGS = {
+    "c1": dict(n=50_000, d=64, nlist=0, nprobe=0, name="configs[0]: 50kx64 fp32 nlist=448 (heuristic) nq=10k k=10"),
+    "c2": dict(n=1_000_000, d=128, nlist=1024, nprobe=0, name="configs[1]: 1Mx128 fp32 nlist=1024 nq=10k k=10"),
+    "c4": dict(n=10_000_000, d=128, nlist=0, nprobe=32, name="configs[3]: 10Mx128 fp32 nlist=12652 (heuristic) n_probe=32 nq=10k k=10"),
+    "c5": dict(n=100_000_000, d=96, nlist=65536, nprobe=32, name="configs[4]: 100Mx96 fp32 nlist=65536 n_probe=32 nq=10k k=10"),
+}
+
 
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -48,10 +59,14 @@ def workload(args):
     return dict(n=args.n, d=args.d, nq=args.nq, k=args.k, nlist=args.nlist, seed=42)
 
 
-def gen_data(w):
-    """bench/faiss_bench_official/bench_all_ivf.py:67-69"""
+def gen_data(w, chunk=1_000_000):
+    """bench/faiss_bench_official/bench_all_ivf.py:67-69: xb then xq from ONE default_rng(seed) stream (drawn in chunks:
+    the stream is the same as one big call)."""
     rng = np.random.default_rng(w["seed"])
-    xb = rng.standard_normal((w["n"], w["d"])).astype(np.float32)
+    xb = np.empty((w["n"], w["d"]), np.float32)
+    for i0 in range(0, w["n"], chunk):
+        i1 = min(w["n"], i0 + chunk)
+        xb[i0:i1] = rng.standard_normal((i1 - i0, w["d"]))
     xq = rng.standard_normal((w["nq"], w["d"])).astype(np.float32)
     return xb, xq
 
@@ -64,14 +79,37 @@ def recall_at_k(I, gt):
     return hit / gt.size
 
 
-def ncu_traffic(w, nprobe):
+def brute_force_topk_f64(xb, xq, k, device="cuda", block=32768):
+    """Independent ground truth (replaces faiss IndexFlatL2 of bench_all_ivf.py:75-78): exact float64 squared L2 by
+    blocks with torch on the GPU -- none of the library's code.  xb may be a host array or a device tensor.
+    Returns (D float64 [nq, k], I int64 [nq, k])."""
+    import torch
+    q = torch.as_tensor(xq, device=device).double()
+    qn = (q * q).sum(1, keepdim=True)
+    best_d = torch.full((len(q), k), float("inf"), dtype=torch.float64, device=device)
+    best_i = torch.full((len(q), k), -1, dtype=torch.int64, device=device)
+    n = len(xb)
+    for b0 in range(0, n, block):
+        b1 = min(n, b0 + block)
+        x = torch.as_tensor(xb[b0:b1], device=device).double()
+        d = qn - 2.0 * (q @ x.T) + (x * x).sum(1)[None, :]
+        kk = min(k, b1 - b0)
+        dv, di = torch.topk(d, kk, dim=1, largest=False)
+        cat_d = torch.cat([best_d, dv], 1)
+        cat_i = torch.cat([best_i, di + b0], 1)
+        o = torch.argsort(cat_d, dim=1, stable=True)[:, :k]
+        best_d, best_i = torch.gather(cat_d, 1, o), torch.gather(cat_i, 1, o)
+    return best_d.cpu().numpy(), best_i.cpu().numpy()
+
+
+def ncu_traffic(w, nprobe, key="dram_bytes"):
     """DRAM bytes of the scan kernel per step from the committed ncu capture of this workload (profiles/ncu_traffic.json)."""
     path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(path):
         with open(path) as f:
             e = json.load(f)
         if all(e["workload"].get(k) == w[k] for k in w) and e["workload"].get("nprobe") == nprobe:
-            return e["dram_bytes"]
+            return e.get(key)
     return None
 
 
@@ -117,7 +155,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.05)
+            time.sleep(0.02)
 
     def result(self):
         self.stop_flag = True
@@ -128,30 +166,69 @@ class ClockSampler(threading.Thread):
 
 
 # ----------------------------------------------------------------------------------------
-def cpu_baseline_sample(O, oix, xq, k, nprobe, seconds=12.0):
-    """The oracle (port of src/ivf_index.rs:190-267) on every host core, on a bounded
-    prefix of the same query batch."""
-    threads = O.num_threads()
+# CPU arm: the oracle port of src/ivf_index.rs:190-267
+# ----------------------------------------------------------------------------------------
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_threads_setup():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm states its own thread count instead of inheriting that."""
+    n = host_cores()
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    import oracle as O
+    O.lib()
+    try:
+        import ctypes
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(n)
+    except Exception:
+        pass
+    return O, n
+
+
+CPU_CHUNK = 64  # queries per oracle call in every CPU measurement (the same in cpu_baseline and --impl reference)
+
+
+def cpu_search_qps(oix, xq, k, nprobe, nthreads, seconds, start=0):
+    """Chunks of CPU_CHUNK queries from `start` until `seconds` have passed.  nthreads = 1 is the reference's own
+    behaviour (one query at a time on one thread, bindings/python/src/lib.rs:74-97); nthreads = all cores is the generous
+    variant (OpenMP over the queries of a chunk)."""
     done, t0 = 0, time.perf_counter()
-    chunk = max(8, 2 * threads)
-    while done < len(xq):
-        oix.search_batch(xq[done:done + chunk], k, nprobe, nthreads=0)
-        done += min(chunk, len(xq) - done)
+    while True:
+        a = (start + done) % max(1, len(xq) - CPU_CHUNK)
+        oix.search_batch(xq[a:a + CPU_CHUNK], k, nprobe, nthreads=nthreads)
+        done += CPU_CHUNK
         if time.perf_counter() - t0 > seconds:
             break
-    dt = time.perf_counter() - t0
-    return {"value": done / dt, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"first {done} of {len(xq)} queries, n_probe={nprobe}, k={k}, oracle with OpenMP over queries "
-                      f"(the reference itself runs queries one at a time on one thread)"}
+    return done / (time.perf_counter() - t0), done
+
+
+def cpu_baseline_block(O, ncores, oix, xq, k, nprobe, seconds_all=10.0, seconds_one=6.0):
+    allc, n_all = cpu_search_qps(oix, xq, k, nprobe, ncores, seconds_all)
+    one, n_one = cpu_search_qps(oix, xq, k, nprobe, 1, seconds_one)
+    return {"value": allc, "unit": UNIT, "cores": ncores, "kind": "port",
+            "sample": f"first {n_all} queries of the batch in chunks of {CPU_CHUNK}, n_probe={nprobe}, k={k}: oracle port with "
+                      f"OpenMP over the queries of a chunk on {ncores} threads",
+            "faithful": {"value": one, "unit": UNIT, "cores": 1,
+                         "sample": f"first {n_one} queries, one query at a time on one thread -- what the reference's Python "
+                                   f"entry point does (bindings/python/src/lib.rs:74-97), minus its per-query shard file reads"}}
+
+
+def config_dict(args, w, nprobe):
+    """The workload, identical in both arms (the driver compares it key by key)."""
+    return {"workload": CONFIGS[args.config]["name"] if args.config in CONFIGS else "custom", **w, "nprobe": nprobe}
 
 
 def run_reference(args):
     """--impl reference: the reference's CPU algorithm.  The Rust crate cannot be compiled in
-    this image (no cargo/rustc), so this is the oracle port on all host threads."""
+    this image (no cargo/rustc), so this is the oracle port on all host threads (stated in `cores`)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import oracle as O
+    O, ncores = cpu_threads_setup()
     w = workload(args)
     xb, xq = gen_data(w)
     t0 = time.perf_counter()
@@ -167,212 +244,203 @@ def run_reference(args):
         gt = O.brute_force_topk(xb, s, w["k"])
         nprobe = 1
         while nprobe < oix.nlist:
-            _, I = oix.search_batch(s, w["k"], nprobe, nthreads=0)
+            _, I = oix.search_batch(s, w["k"], nprobe, nthreads=ncores)
             if recall_at_k(I, gt) >= 0.9:
                 break
             nprobe *= 2
-    threads = O.num_threads()
-    sample = max(threads * 4, 64)
     per_step = []
     for s in range(args.warmup + args.steps):
-        q = xq[(s * sample) % (len(xq) - sample):][:sample]
+        a = (s * CPU_CHUNK) % (len(xq) - CPU_CHUNK)
         t0 = time.perf_counter()
-        oix.search_batch(q, w["k"], nprobe, nthreads=0)
+        oix.search_batch(xq[a:a + CPU_CHUNK], w["k"], nprobe, nthreads=ncores)
         dt = time.perf_counter() - t0
         if s >= args.warmup:
             per_step.append(dt)
     total = float(np.sum(per_step))
-    qps = sample * len(per_step) / total
+    qps = CPU_CHUNK * len(per_step) / total
+    one, n_one = cpu_search_qps(oix, xq, w["k"], nprobe, 1, 6.0)
     line = {"impl": "reference", "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * total / len(per_step), "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "configs[1]: 1Mx128 fp32 nlist=1024 nq=10k k=10", **w, "nprobe": nprobe,
-                       "step": f"{sample}-query sample of the batch per step", "index_build_s": build_s},
-            "cpu_baseline": {"value": qps, "unit": UNIT, "cores": threads, "kind": "port",
-                             "sample": f"{sample} queries per step x {len(per_step)} steps, n_probe={nprobe}"},
+            "config": config_dict(args, w, nprobe),
+            "details": {"step": f"one chunk of {CPU_CHUNK} queries of the batch per step (bounded sample of the workload)",
+                        "index_build_s": build_s, "nlist_nonempty": oix.nlist},
+            "cpu_baseline": {"value": qps, "unit": UNIT, "cores": ncores, "kind": "port",
+                             "sample": f"{CPU_CHUNK} queries per step x {len(per_step)} steps, n_probe={nprobe}, OpenMP over the "
+                                       f"queries of a chunk on {ncores} threads",
+                             "faithful": {"value": one, "unit": UNIT, "cores": 1,
+                                          "sample": f"first {n_one} queries, one at a time on one thread "
+                                                    f"(bindings/python/src/lib.rs:74-97)"}},
             "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
 # ----------------------------------------------------------------------------------------
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
-    from vector_indexer_py import _ffi
+# our arm
+# ----------------------------------------------------------------------------------------
+class Harness:
+    """One process per GPU: device, stream, (optionally) torch.distributed for the host-side plumbing only -- the
+    data-path collectives are the library's own (vidx_comm_init)."""
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    w = workload(args)
-    k = w["k"]
-    xb, xq = gen_data(w)
-    nq, d = xq.shape
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+        # The library launches on the stream it is given; torch's legacy default stream has handle 0,
+        # which the ABI reads as "use a stream of the handle", so run everything on an explicit
+        # torch stream: torch.cuda.Event then brackets exactly the kernels being timed.
+        self.tstream = torch.cuda.Stream()
+        torch.cuda.set_stream(self.tstream)
+        self.stream = self.tstream.cuda_stream
+        assert self.stream != 0
 
-    t0 = time.perf_counter()
-    ix = _ffi.Index(d, local).build(xb, seed=42, nlist=w["nlist"])
-    if args.scan_mode:
-        ix.set_scan_mode(args.scan_mode)
-    if args.coarse_mode:
-        ix.set_coarse_mode(args.coarse_mode)
-    build_s = time.perf_counter() - t0
-    # The library launches on the stream it is given; torch's legacy default stream has handle 0,
-    # which the ABI reads as "use the handle's own stream", so run everything on an explicit
-    # torch stream: torch.cuda.Event then brackets exactly the kernels being timed.
-    tstream = torch.cuda.Stream()
-    torch.cuda.set_stream(tstream)
-    stream = tstream.cuda_stream
-    assert stream != 0
-    d_xq = torch.from_numpy(xq).cuda()
-    d_D = torch.empty((nq, k), dtype=torch.float32, device="cuda")
-    d_I = torch.empty((nq, k), dtype=torch.int64, device="cuda")
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
 
-    def search_dev(nprobe):
-        ix.search_device(d_xq.data_ptr(), nq, k, nprobe, d_D.data_ptr(), d_I.data_ptr(), stream)
+    def max_over_ranks(self, x):
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], device="cuda", dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
 
-    # ---- ground truth + n_probe sweep (untimed; single-GPU view of the whole index) ----------
-    search_dev(ix.nlist)  # probing every list = exact brute force with the same arithmetic
-    torch.cuda.synchronize()
-    gt = d_I.cpu().numpy().copy()
-    curve, nprobe = [], None
-    p = 1
-    while True:
-        p = min(p, ix.nlist)
-        search_dev(p)
-        torch.cuda.synchronize()
-        r = recall_at_k(d_I.cpu().numpy(), gt)
-        curve.append({"nprobe": p, "recall_at_10": r})
-        if nprobe is None and r >= 0.9:
-            nprobe = p
-            if not args.full_curve:
-                break
-        if p >= ix.nlist:
-            break
-        p *= 2
-    if args.nprobe:
-        nprobe = args.nprobe
-    recall = next((c["recall_at_10"] for c in curve if c["nprobe"] == nprobe), None)
+    def comm_for(self, ix):
+        """Rank 0's NCCL id travels over the host-side process group; the communicator itself belongs to the library."""
+        from vector_indexer_py import _ffi
+        obj = [_ffi.comm_unique_id() if self.rank == 0 else None]
+        self.dist.broadcast_object_list(obj, src=0)
+        ix.comm_init(self.rank, self.world, obj[0])
 
-    # ---- distributed layout -----------------------------------------------------------------
-    # index (default, north_star 4): every rank owns part of the index, queries are replicated, the per-rank top-k are
-    #   all-gathered and merged.  queries: every rank keeps the whole index (it fits: 0.8 GB) and answers its slice of the
-    #   batch; the slices are all-gathered.  Both are strong scaling: the 10 k-query batch is the fixed total work.
-    split_queries = world > 1 and args.multi == "queries"
-    q_lo, q_hi = 0, nq
-    if world > 1 and not split_queries:
-        ix.set_partition(rank, world)
-        g_D = torch.empty((world, nq, k), dtype=torch.float32, device="cuda")
-        g_I = torch.empty((world, nq, k), dtype=torch.int64, device="cuda")
-        m_D = torch.empty((nq, k), dtype=torch.float32, device="cuda")
-        m_I = torch.empty((nq, k), dtype=torch.int64, device="cuda")
-    if split_queries:
-        per = (nq + world - 1) // world
-        q_lo, q_hi = min(nq, rank * per), min(nq, (rank + 1) * per)
-        s_D = torch.full((per, k), float("inf"), dtype=torch.float32, device="cuda")
-        s_I = torch.full((per, k), -1, dtype=torch.int64, device="cuda")
-        a_D = torch.empty((world * per, k), dtype=torch.float32, device="cuda")
-        a_I = torch.empty((world * per, k), dtype=torch.int64, device="cuda")
-        m_D, m_I = a_D[:nq], a_I[:nq]
-
-    def step_device():
-        if split_queries:
-            if q_hi > q_lo:
-                ix.search_device(d_xq[q_lo:q_hi].data_ptr(), q_hi - q_lo, k, nprobe, s_D.data_ptr(), s_I.data_ptr(), stream)
-            dist.all_gather_into_tensor(a_D, s_D)
-            dist.all_gather_into_tensor(a_I, s_I)
-            return
-        search_dev(nprobe)
-        if world > 1:
-            dist.all_gather_into_tensor(g_D, d_D)
-            dist.all_gather_into_tensor(g_I, d_I)
-            _ffi.merge_topk_device(local, g_D.data_ptr(), g_I.data_ptr(), world, nq, k, m_D.data_ptr(), m_I.data_ptr(), stream)
-
-    h_xq = torch.from_numpy(xq).pin_memory()
-    h_D = torch.empty((nq, k), dtype=torch.float32).pin_memory()
-    h_I = torch.empty((nq, k), dtype=torch.int64).pin_memory()
-
-    def step_e2e():
-        if world == 1:
-            ix.search_host_ptr(h_xq.data_ptr(), nq, k, nprobe, h_D.data_ptr(), h_I.data_ptr())
-        else:
-            d_xq.copy_(h_xq, non_blocking=True)
-            step_device()
-            h_D.copy_(m_D, non_blocking=True)
-            h_I.copy_(m_I, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps, warmup):
+    def timed(self, fn, steps, warmup):
+        from vector_indexer_py import _ffi
+        torch = self.torch
         for _ in range(warmup):
             fn()
-        barrier()
+        self.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = _ffi.kernel_launch_count()
         e0.record()
         for _ in range(steps):
             fn()
         e1.record()
-        barrier()
-        ms = e0.elapsed_time(e1)
-        launches = _ffi.kernel_launch_count() - l0
-        if world > 1:
-            t = torch.tensor([ms], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms, launches
+        self.barrier()
+        ms = self.max_over_ranks(e0.elapsed_time(e1))
+        return ms, _ffi.kernel_launch_count() - l0
 
-    if args.profile_window:
-        # ncu --profile-from-start off: exactly one warmed-up step between cudaProfilerStart/Stop
-        for _ in range(args.warmup):
-            step_device()
-        torch.cuda.synchronize()
-        torch.cuda.profiler.start()
-        step_device()
-        torch.cuda.synchronize()
-        torch.cuda.profiler.stop()
-    sampler = ClockSampler(local)
-    sampler.start()
-    ms_dev, launches = timed(step_device, args.steps, args.warmup)
-    clocks = sampler.result()
-    # end-to-end: wall clock around host-facing calls (copies included), max over ranks
-    for _ in range(args.warmup):
-        step_e2e()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_e2e()
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
+    def timed_wall(self, fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        self.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        self.barrier()
+        return self.max_over_ranks(time.perf_counter() - t0)
 
-    # ---- correctness of what was timed ------------------------------------------------------
-    final_I = (m_I if world > 1 else d_I).cpu().numpy()
-    final_recall = recall_at_k(final_I, gt)
 
-    # ---- per-stage times + roofline of the scan kernel (instrumented pass, not the timed one) ----
-    peaks, peak_kind = load_peaks()
-    ix.set_profiling(True)
-    reps = 5
+class Searcher:
+    """A built index + device / pinned-host buffers for one batch; search through the same entry points at any N."""
 
-    def staged(nq_used, nprobe_used):
+    def __init__(self, H, w, xb, xq, nlist, scan_mode=0, coarse_mode=0, d_xb=None):
+        from vector_indexer_py import _ffi
+        torch = H.torch
+        self.H, self.k, self.nq, self.d = H, w["k"], len(xq), xq.shape[1]
+        t0 = time.perf_counter()
+        ix = _ffi.Index(self.d, H.local)
+        if H.world > 1:
+            ix.set_partition(H.rank, H.world)   # BEFORE the build: only the owned part reaches HBM
+        if d_xb is not None:
+            ix.build_device(d_xb.data_ptr(), len(d_xb), seed=42, nlist=nlist)
+        else:
+            ix.build(xb, seed=42, nlist=nlist)
+        self.build_s = time.perf_counter() - t0
+        if H.world > 1:
+            H.comm_for(ix)
+        if scan_mode:
+            ix.set_scan_mode(scan_mode)
+        if coarse_mode:
+            ix.set_coarse_mode(coarse_mode)
+        self.ix = ix
+        self.d_xq = torch.from_numpy(xq).cuda()
+        self.d_D = torch.empty((self.nq, self.k), dtype=torch.float32, device="cuda")
+        self.d_I = torch.empty((self.nq, self.k), dtype=torch.int64, device="cuda")
+        self.h_xq = torch.from_numpy(xq).pin_memory()
+        self.h_D = torch.empty((self.nq, self.k), dtype=torch.float32).pin_memory()
+        self.h_I = torch.empty((self.nq, self.k), dtype=torch.int64).pin_memory()
+
+    def search_dev(self, nprobe, nq=None):
+        nq = self.nq if nq is None else nq
+        a = (self.d_xq.data_ptr(), nq, self.k, nprobe, self.d_D.data_ptr(), self.d_I.data_ptr(), self.H.stream)
+        if self.H.world > 1:
+            self.ix.search_multi_device(*a)
+        else:
+            self.ix.search_device(*a)
+
+    def search_e2e(self, nprobe):
+        a = (self.h_xq.data_ptr(), self.nq, self.k, nprobe, self.h_D.data_ptr(), self.h_I.data_ptr())
+        if self.H.world > 1:
+            self.ix.search_multi_host_ptr(*a)
+        else:
+            self.ix.search_host_ptr(*a)
+
+    def result_ids(self):
+        self.H.torch.cuda.synchronize()
+        return self.d_I.cpu().numpy()
+
+    def staged(self, nq_used, nprobe, reps=5):
+        """Per-stage CUDA-event times (instrumented passes, not the timed ones), averaged."""
+        self.ix.set_profiling(True)
         acc = None
         for _ in range(reps):
-            ix.search_device(d_xq.data_ptr(), nq_used, k, nprobe_used, d_D.data_ptr(), d_I.data_ptr(), stream)
-            torch.cuda.synchronize()
-            s = ix.stats()
+            self.search_dev(nprobe, nq_used)
+            self.H.torch.cuda.synchronize()
+            s = self.ix.stats()
             acc = s if acc is None else {kk: (acc[kk] + s[kk] if kk.startswith("ms_") else s[kk]) for kk in s}
+        self.ix.set_profiling(False)
         return {kk: (acc[kk] / reps if kk.startswith("ms_") else acc[kk]) for kk in acc}
 
-    stage = staged(q_hi - q_lo if split_queries else nq, nprobe)
+
+def recall_sweep(S, gt, gt_rows, full_curve, forced):
+    """Smallest n_probe of {1, 2, 4, ...} with recall@10 >= 0.9 against the independent ground truth (rows gt_rows of the batch)."""
+    curve, nprobe, p = [], None, 1
+    while True:
+        p = min(p, S.ix.nlist)
+        S.search_dev(p)
+        r = recall_at_k(S.result_ids()[gt_rows], gt)
+        curve.append({"nprobe": p, "recall_at_10": r})
+        if nprobe is None and r >= 0.9:
+            nprobe = p
+            if not full_curve:
+                break
+        if p >= S.ix.nlist:
+            break
+        p *= 2
+    if forced:
+        nprobe = forced
+    return nprobe or curve[-1]["nprobe"], curve
+
+
+def measure(S, nprobe, steps, warmup):
+    H = S.H
+    sampler = ClockSampler(H.local)
+    sampler.start()
+    ms_dev, launches = H.timed(lambda: S.search_dev(nprobe), steps, warmup)
+    clocks = sampler.result()
+    e2e_s = H.timed_wall(lambda: S.search_e2e(nprobe), steps, warmup)
+    return ms_dev, launches, clocks, e2e_s
+
+
+def scan_rooflines(S, w, nprobe, peaks, peak_kind):
+    H, nq, d = S.H, S.nq, S.d
+    stage = S.staged(nq, nprobe)
     tc_used = stage["n_tc_items"] > 0
     tc_peak = peaks["bf16_tflops"]  # the filter runs tcgen05 kind::f16 (same rate as bf16): the measured dense peak
     if tc_used:
@@ -387,12 +455,11 @@ def run_ours(args):
                     "queries_redone_exactly": stage["n_tc_overflow"],
                     "reference_arithmetic_equivalent_tflops": stage["scan_flops"] / t / 1e12,
                     "hbm_gbs_algorithmic": stage["scan_bytes_algorithmic"] / t / 1e9,
-                    "traffic": ncu_traffic(w, nprobe) if world == 1 else None,
+                    "traffic": ncu_traffic(w, nprobe) if H.world == 1 else None,
                     "traffic_source": "profiles/ncu_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of both launches "
                                       "(ncu --set full); the fp16 shadow store is 256 MB, read once",
                     "note": f"2*D flop per (query, vector) pair, on this rank; at n_probe={nprobe} each probed list is shared by "
-                            f"~{stage['n_pairs'] // max(1, ix.nlist)} queries on average, so the contraction, not HBM, bounds the scan; "
-                            "the tensor pipe is busy 66 % of the main launch (ncu); one thread issues an N=128 tcgen05.mma only every ~125 cycles (two issuers interleave) and the epilogue (min tree + survivor queue) paces the rest"}
+                            f"~{stage['n_pairs'] // max(1, S.ix.nlist)} queries on average, so the contraction, not HBM, bounds the scan"}
     else:
         t = stage["ms_scan"] / 1e3
         ach = stage["scan_flops"] / t / 1e12
@@ -403,50 +470,189 @@ def run_ours(args):
     # the HBM-bound operating point of the same kernel: one 128-query tile, so every probed list is
     # streamed from HBM exactly once (the latency-oriented small-batch case)
     nq_small = min(128, nq)
-    small = staged(nq_small, nprobe)
+    small = S.staged(nq_small, nprobe)
     ts = (small["ms_scan_tc"] if small["n_tc_items"] > 0 else small["ms_scan"]) / 1e3
     roofline_hbm = {"kernel": "scan_tc_kernel" if small["n_tc_items"] > 0 else "scan_dense/sparse_kernel", "bound": "hbm",
                     "achieved": small["scan_bytes_algorithmic"] / ts / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                     "frac": small["scan_bytes_algorithmic"] / ts / 1e9 / peaks["hbm_gbs"], "peak_source": peak_kind,
-                    "bytes_per_launch": small["scan_bytes_algorithmic"], "ms_per_launch": ts * 1e3, "traffic": None,
+                    "bytes_per_launch": small["scan_bytes_algorithmic"], "ms_per_launch": ts * 1e3,
+                    "traffic": ncu_traffic(w, nprobe, "dram_bytes_nq128") if H.world == 1 else None,
                     "workload": f"first {nq_small} queries of the batch, n_probe={nprobe}: distinct probed lists "
                                 f"len*(4D+8) + queries + probe lists + outputs",
                     "qps": nq_small / (small["ms_total"] / 1e3)}
-    ix.set_profiling(False)
+    return stage, roofline, roofline_hbm
 
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+
+def coarse_roofline(S, nprobe, peaks, peak_kind):
+    """Coarse quantization both ways: exact FP32 kernel (default) and tcgen05 filter + exact re-check."""
+    out = {}
+    nq, d = S.nq, S.d
+    for mode, name in ((1, "fp32_exact"), (2, "tensor_core_filter")):
+        S.ix.set_coarse_mode(mode)
+        st = S.staged(nq, nprobe, reps=3)
+        ms = st["ms_coarse"] + st["ms_select"]
+        alg = 2.0 * d * nq * S.ix.nlist  # SURVEY 8d: 2 * nq * nlist * D
+        e = {"ms": ms, "algorithmic_gflop": alg / 1e9, "tflops_algorithmic": alg / (ms / 1e3) / 1e12}
+        if mode == 1:
+            e.update(frac_fp32_peak_3D=(1.5 * alg) / (st["ms_coarse"] / 1e3) / 1e12 / FP32_PEAK_TFLOPS,
+                     kernel="coarse_dist_kernel + select", ms_distances=st["ms_coarse"], ms_select=st["ms_select"])
+        else:
+            # one extra K-step per tile carries the norms: 2 * 8 * Dh halfs per pair are issued, twice (bounds + main pass)
+            dh16 = 16 * ((d + 15) // 16)
+            issued = 2.0 * 2.0 * (dh16 + 16) * nq * (128 * ((S.ix.nlist + 127) // 128))
+            e.update(frac_tensor_peak_issued=issued / (ms / 1e3) / 1e12 / peaks["bf16_tflops"],
+                     kernel="scan_tc_kernel over the centroid table (bounds + frozen pass) + finalize")
+        out[name] = e
+    S.ix.set_coarse_mode(0)
+    st = S.staged(nq, nprobe, reps=3)
+    out["auto"] = {"ms": st["ms_coarse"] + st["ms_select"]}
+    out["peak_source"] = f"{peak_kind} bf16 burst {peaks['bf16_tflops']} TF/s; FP32 {FP32_PEAK_TFLOPS:.1f} TF/s computed"
+    return out
+
+
+def kmeans_block(xb, ncores, with_oracle):
+    """BASELINE configs[2]: mini-batch k-means 1M x 128, k = 4096, 20 iterations, hierarchical final assignment."""
+    from vector_indexer_py import _ffi
+    t0 = time.perf_counter()
+    c, labels, iters = _ffi.kmeans_mini_batch(xb, 4096, 20, seed=42)
+    gpu_s = time.perf_counter() - t0
+    out = {"workload": "configs[2]: mini-batch k-means 1Mx128 k=4096, 20 iterations + hierarchical assignment of all points",
+           "gpu_seconds": gpu_s, "includes": "H2D of the data set (512 MB) and D2H of centroids + labels", "iterations": iters}
+    if with_oracle:
         import oracle as O
-        oix = O.Ivf.from_labels(xb, ix.train_centroids(), ix.train_labels())
-        cpu = cpu_baseline_sample(O, oix, xq, k, nprobe)
+        t0 = time.perf_counter()
+        oc, ol, _ = O.kmeans_mini_batch(xb, 4096, 20, seed=42)
+        out.update(cpu_seconds=time.perf_counter() - t0, cpu_cores=ncores, cpu_kind="port",
+                   centroids_bit_equal=bool(np.array_equal(c.view(np.uint32), oc.view(np.uint32))),
+                   labels_equal=bool(np.array_equal(labels, ol)))
+    return out
+
+
+def run_config(H, args, cfg_name, w, nprobe_forced, steps, warmup, rich):
+    """Build + sweep + timed steps for one workload; `rich` adds rooflines / CPU legs (the headline config)."""
+    torch = H.torch
+    cfg = CONFIGS.get(cfg_name, {})
+    device_gen = cfg_name == "c5"
+    if device_gen:
+        # too large for a host copy per rank: the same counter-based stream on every GPU (torch Philox, seed 42)
+        g = torch.Generator(device="cuda")
+        g.manual_seed(42)
+        d_xb = torch.empty((w["n"], w["d"]), dtype=torch.float32, device="cuda")
+        for i0 in range(0, w["n"], 4_000_000):
+            i1 = min(w["n"], i0 + 4_000_000)
+            d_xb[i0:i1] = torch.randn((i1 - i0, w["d"]), generator=g, device="cuda")
+        xq = torch.randn((w["nq"], w["d"]), generator=g, device="cuda").cpu().numpy()
+        xb = None
+        torch.cuda.synchronize()
+    else:
+        xb, xq = gen_data(w)
+        d_xb = None
+    S = Searcher(H, w, xb, xq, w["nlist"], args.scan_mode, args.coarse_mode, d_xb=d_xb)
+    # ---- independent ground truth (float64 brute force, none of the library's code) on a sample of the batch ----
+    ngt = w["nq"] if w["n"] <= 2_000_000 else 1000
+    gt_rows = np.arange(ngt)
+    src = d_xb if device_gen else xb
+    _, gt = brute_force_topk_f64(src, xq[:ngt], w["k"])
+    del d_xb
+    nprobe, curve = recall_sweep(S, gt, gt_rows, args.full_curve, nprobe_forced)
+    recall = next((c["recall_at_10"] for c in curve if c["nprobe"] == nprobe), None)
+    if args.profile_window and rich:
+        # ncu --profile-from-start off: exactly one warmed-up step between cudaProfilerStart/Stop
+        for _ in range(warmup):
+            S.search_dev(nprobe, args.profile_nq or None)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        S.search_dev(nprobe, args.profile_nq or None)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+    ms_dev, launches, clocks, e2e_s = measure(S, nprobe, steps, warmup)
+    S.search_dev(nprobe)
+    final_recall = recall_at_k(S.result_ids()[gt_rows], gt)
+    if recall is None:
+        recall = final_recall
+    nq, k = w["nq"], w["k"]
+    res = {"S": S, "xb": xb, "xq": xq, "nprobe": nprobe, "curve": curve, "recall": final_recall, "ms_dev": ms_dev,
+           "launches": launches, "clocks": clocks, "e2e_s": e2e_s,
+           "qps": nq * steps / (ms_dev / 1e3), "e2e_qps": nq * steps / e2e_s}
+    ix = S.ix
+    res["residency"] = {"resident_vectors": int(ix.resident_vectors), "ntotal": int(ix.ntotal),
+                        "resident_bytes": int(ix.resident_bytes),
+                        "fraction": ix.resident_vectors / max(1, ix.ntotal)}
+    res["parallelism"] = ("1 GPU" if H.world == 1 else
+                          f"{ix.partition_kind} over {H.world} GPUs: each rank holds {100.0 * ix.resident_vectors / max(1, ix.ntotal):.1f} % "
+                          f"of the vectors in HBM, queries replicated, coarse stage split by query, {ix.comm_version} all-gather of "
+                          f"probe lists and of the packed per-GPU top-k + device merge, all inside the library")
+    return res
+
+
+def run_ours(args):
+    H = Harness()
+    torch = H.torch
+    w = workload(args)
+    peaks, peak_kind = load_peaks()
+    R = run_config(H, args, args.config, w, args.nprobe, args.steps, args.warmup, rich=True)
+    S, xb, xq, nprobe = R["S"], R["xb"], R["xq"], R["nprobe"]
+    nq, k = w["nq"], w["k"]
+    stage, roofline, roofline_hbm = scan_rooflines(S, w, nprobe, peaks, peak_kind)
+    coarse = coarse_roofline(S, nprobe, peaks, peak_kind) if not args.lean else None
+
+    cpu, kmeans, parity = None, None, None
+    if H.rank == 0 and H.world == 1 and not args.no_cpu_baseline and xb is not None:
+        O, ncores = cpu_threads_setup()
+        oix = O.Ivf.from_labels(xb, S.ix.train_centroids(), S.ix.train_labels())
+        cpu = cpu_baseline_block(O, ncores, oix, xq, k, nprobe)
         # the sample doubles as a live parity check of what was timed
         m = 32
-        Do, Io = oix.search_batch(xq[:m], k, nprobe, nthreads=0)
-        search_dev(nprobe)
+        Do, Io = oix.search_batch(xq[:m], k, nprobe, nthreads=ncores)
+        S.search_dev(nprobe)
         torch.cuda.synchronize()
-        assert np.array_equal(d_D[:m].cpu().numpy().view(np.uint32), Do.view(np.uint32)), "GPU distances differ from the oracle"
-        assert np.array_equal(d_I[:m].cpu().numpy(), Io), "GPU ids differ from the oracle"
+        assert np.array_equal(S.d_D[:m].cpu().numpy().view(np.uint32), Do.view(np.uint32)), "GPU distances differ from the oracle"
+        assert np.array_equal(S.d_I[:m].cpu().numpy(), Io), "GPU ids differ from the oracle"
+        parity = f"first {m} queries at n_probe={nprobe}: distances bit-identical, ids identical to the oracle port"
+        del oix
+        if args.config == "c2" and not args.lean:
+            kmeans = kmeans_block(xb, ncores, with_oracle=True)
 
-    if rank == 0:
-        qps = nq * args.steps / (ms_dev / 1e3)
-        line = {"metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+    # ---- the sharded 10M config on the same ranks (N > 1, or on request) -------------------------------------------
+    c4 = None
+    want_c4 = args.extra == "c4" or (args.extra == "auto" and H.world > 1 and args.config == "c2")
+    if want_c4:
+        del S
+        R["S"] = None
+        torch.cuda.empty_cache()
+        try:
+            c = CONFIGS["c4"]
+            w4 = dict(n=c["n"], d=c["d"], nq=args.nq, k=args.k, nlist=c["nlist"], seed=42)
+            t0 = time.perf_counter()
+            R4 = run_config(H, args, "c4", w4, c["nprobe"], max(5, args.steps // 2), 3, rich=False)
+            c4 = {"workload": c["name"], "n_gpus": H.world, "value": R4["qps"], "unit": UNIT,
+                  "ms_per_step": R4["ms_dev"] / max(5, args.steps // 2), "e2e": R4["e2e_qps"], "nprobe": R4["nprobe"],
+                  "recall_at_10": R4["recall"], "recall_sample": "first 1000 queries vs float64 brute force",
+                  "nlist_nonempty": int(R4["S"].ix.nlist), "num_shards": int(R4["S"].ix.num_shards),
+                  "index_build_s": R4["S"].build_s, "residency": R4["residency"], "parallelism": R4["parallelism"],
+                  "gpu_launches": int(R4["launches"]), "seconds_total": time.perf_counter() - t0}
+            R4["S"] = None
+        except Exception as e:  # the headline line must survive a failure of the extra workload
+            c4 = {"error": f"{type(e).__name__}: {e}"}
+
+    if H.rank == 0:
+        line = {"metric": METRIC, "value": R["qps"], "unit": UNIT, "n_gpus": H.world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": R["ms_dev"] / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
-                "config": {"workload": "configs[1]: 1Mx128 fp32 nlist=1024 nq=10k k=10", **w, "nprobe": nprobe,
-                           "recall_at_10": final_recall, "recall_curve": curve, "nlist_nonempty": ix.nlist,
-                           "l2": "inputs larger than L2 (index 512 MB)", "index_build_s": build_s,
-                           "parallelism": ("1 GPU" if world == 1 else
-                                           f"index replicated, batch split over {world} GPUs, NCCL all-gather of the slices" if split_queries
-                                           else f"{ix.partition_kind} over {world} GPUs, queries replicated, NCCL all-gather of per-GPU "
-                                                f"top-k + device merge")},
-                "e2e": {"value": nq * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(xq.nbytes),
-                        "d2h_bytes_per_step": int(nq * k * 12), "ms_per_step": 1e3 * e2e_s / args.steps},
-                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_hbm": roofline_hbm,
+                "config": config_dict(args, w, nprobe),
+                "details": {"recall_at_10": R["recall"], "recall_curve": R["curve"],
+                            "ground_truth": "float64 brute force (torch, blocks of 32768 rows), independent of the library",
+                            "l2": "inputs larger than L2 (index 512 MB)",
+                            "parallelism": R["parallelism"], "residency": R["residency"], "parity": parity},
+                "e2e": {"value": R["e2e_qps"], "unit": UNIT, "h2d_bytes_per_step": int(xq.nbytes),
+                        "d2h_bytes_per_step": int(nq * k * 12), "ms_per_step": 1e3 * R["e2e_s"] / args.steps},
+                "gpu_launches": int(R["launches"]), "clocks": R["clocks"], "roofline": roofline, "roofline_hbm": roofline_hbm,
+                "roofline_coarse": coarse,
                 "stages_ms": {kk: stage[kk] for kk in stage if kk.startswith("ms_")},
-                "cpu_baseline": cpu}
+                "cpu_baseline": cpu, "kmeans": kmeans, "c4": c4}
         print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    if H.world > 1:
+        H.dist.destroy_process_group()
 
 
 def main():
@@ -455,21 +661,29 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=1_000_000)
-    ap.add_argument("--d", type=int, default=128)
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS), help="BASELINE config that is built and timed (default: the headline)")
+    ap.add_argument("--n", type=int, default=0)
+    ap.add_argument("--d", type=int, default=0)
     ap.add_argument("--nq", type=int, default=10_000)
     ap.add_argument("--k", type=int, default=10)
-    ap.add_argument("--nlist", type=int, default=1024)
-    ap.add_argument("--nprobe", type=int, default=0, help="0 = smallest power of two with recall@10 >= 0.9")
+    ap.add_argument("--nlist", type=int, default=-1)
+    ap.add_argument("--nprobe", type=int, default=-1, help="0 = smallest power of two with recall@10 >= 0.9")
     ap.add_argument("--full-curve", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--multi", default="index", choices=["index", "queries"],
-                    help="N > 1: partition the index over the GPUs (default, north_star) or replicate it and split the batch")
+    ap.add_argument("--lean", action="store_true", help="skip the coarse-stage comparison and the k-means block")
+    ap.add_argument("--extra", default="auto", choices=["auto", "c4", "none"],
+                    help="auto: N > 1 also measures the sharded 10M config (BASELINE configs[3]) and reports it under `c4`")
     ap.add_argument("--scan-mode", type=int, default=0, help="experiments: vidx_set_scan_mode (0 = auto, what the bench line is quoted on)")
     ap.add_argument("--coarse-mode", type=int, default=0, help="experiments: vidx_set_coarse_mode (0 = auto)")
     ap.add_argument("--profile-window", action="store_true",
                     help="bracket one warmed-up step with cudaProfilerStart/Stop (for ncu --profile-from-start off)")
+    ap.add_argument("--profile-nq", type=int, default=0, help="queries of the profiled step (0 = the whole batch)")
     args = ap.parse_args()
+    c = CONFIGS[args.config]
+    args.n = args.n or c["n"]
+    args.d = args.d or c["d"]
+    args.nlist = c["nlist"] if args.nlist < 0 else args.nlist
+    args.nprobe = c["nprobe"] if args.nprobe < 0 else args.nprobe
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)

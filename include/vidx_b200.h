@@ -7,8 +7,13 @@
  * VIDX_ERR_* codes, which map 1:1 onto the std::io::ErrorKind values the reference
  * returns for the same condition.  vidx_last_error() gives the message.
  *
- * Threading: a handle may be searched from several threads (calls on one handle
- * are serialised internally); build/load must not race with anything.
+ * Threading: a handle may be searched from several threads at once -- every search
+ * takes its own stream-ordered context (scratch buffers + stream) from a pool in the
+ * handle, as the reference shares one index between OS threads
+ * (tests/ivf_index_tests.rs:768-807).  vidx_search_device calls on different streams
+ * are ordered against each other only through those contexts: results are ready when
+ * the stream given to the call reaches that point.  build / load / set_* are exclusive
+ * (they wait for running searches and block new ones).
  * There is NO CPU fallback: every compute entry point fails with VIDX_ERR_CUDA when
  * no sm_100 device is usable.
  */
@@ -55,6 +60,12 @@ int vidx_set_limits(vidx_index* idx, uint64_t default_k, uint64_t default_n_prob
  * n == 0 => VIDX_ERR_INVALID_INPUT ("no vectors provided", src/api.rs:116-118). */
 int vidx_build(vidx_index* idx, const float* data, const uint64_t* ext_ids, const uint64_t* timestamps, uint64_t n,
                uint64_t seed, uint64_t nlist, uint64_t max_iters);
+
+/* The same with `d_data` already in DEVICE memory of the handle's GPU (n x dimension row-major fp32): no host copy of the
+ * data set is needed, which is what a 100M-vector build on a box with less host RAM than HBM requires.  ext_ids / timestamps
+ * stay host arrays (or NULL). */
+int vidx_build_device(vidx_index* idx, const float* d_data, const uint64_t* ext_ids, const uint64_t* timestamps, uint64_t n,
+                      uint64_t seed, uint64_t nlist, uint64_t max_iters);
 
 /* VectorIndexer::build_from_vector_file (src/api.rs:149-186): the file is a concatenation of bincode-2
  * `standard()` batches of (id u64, values Vec<f32>, metadata u64) (src/utils.rs:34-107); decoding stops
@@ -127,6 +138,10 @@ int vidx_get_list_sizes(const vidx_index* idx, uint64_t* out /* nlist */);
 int vidx_get_list_members(const vidx_index* idx, uint64_t list, uint64_t* out);
 int vidx_get_train_labels(const vidx_index* idx, uint64_t* out /* n, unfiltered numbering */);
 int vidx_get_train_centroids(const vidx_index* idx, float* out /* k_trained x dim */);
+/* What this handle keeps in HBM: vectors, and bytes of the vector store (fp32 rows + fp16 shadow + norm terms + ids).
+ * On a rank of a partitioned index (vidx_set_partition before build / load) both are ~1/world of the whole. */
+uint64_t vidx_resident_vectors(const vidx_index* idx);
+uint64_t vidx_resident_bytes(const vidx_index* idx);
 
 /* ---- k-means (the functions src/kmeans.rs exports) -------------------------------- */
 
@@ -153,19 +168,31 @@ uint64_t vidx_calculate_max_iterations(uint64_t num_vectors);
 
 /* ---- persistence: shard files + index.bin (cold-start path) ----------------------- */
 
-/* IvfIndex::save_to + Shard::save_to for every shard        src/ivf_index.rs:274-294, src/shards.rs:68-177 */
+/* IvfIndex::save_to + Shard::save_to for every shard        src/ivf_index.rs:274-294, src/shards.rs:68-177
+ * A rank of a shard-partitioned index writes the shard files it owns (rank 0 also index.bin): all ranks saving into
+ * the same directories produce the files one GPU would.  Range-partitioned handles cannot save (VIDX_ERR_UNSUPPORTED). */
 int vidx_save(const vidx_index* idx, const char* index_dir, const char* shards_dir);
-/* VectorIndexer::load + whole-shard load into HBM            src/api.rs:109-112, src/shards.rs:352-425
- * Missing index.bin => VIDX_ERR_NOT_FOUND; bad header / shard-id mismatch =>
- * VIDX_ERR_INVALID_DATA; unreadable shard => VIDX_ERR_OTHER. */
+/* VectorIndexer::load + shard load into HBM                  src/api.rs:109-112, src/shards.rs:352-425
+ * Missing index.bin => VIDX_ERR_NOT_FOUND; undecodable index.bin => VIDX_ERR_OTHER / VIDX_ERR_INVALID_DATA.
+ * A shard file that is missing, has a bad header / shard id / dimension, or whose centroid index does not fit the file
+ * is SKIPPED as a whole (its lists stay empty), as search_with_paths drops failed shard reads (src/ivf_index.rs:254);
+ * vidx_load_warning_count / vidx_load_warning list what was skipped.  The dimension stored in index.bin replaces the
+ * handle's (the reference does not compare it with the config, src/api.rs:109-112): re-read vidx_dimension afterwards.
+ * On a partitioned handle (vidx_set_partition before the call) only the owned part is read: the shard files the rank
+ * owns, or -- range split -- its vector range of every list. */
 int vidx_load(vidx_index* idx, const char* index_dir, const char* shards_dir);
+uint64_t vidx_load_warning_count(const vidx_index* idx);
+const char* vidx_load_warning(const vidx_index* idx, uint64_t i);
 
 /* ---- multi-GPU: shard partition + top-k merge -------------------------------------- */
 
-/* Keep only the lists whose shard is owned by `rank` of `world` (shards are dealt to
- * ranks by greedy balance on vector count; the unit is the reference's shard,
- * src/ivf_index.rs:104-164).  Centroids stay replicated so every rank computes the same
- * probe lists.  Call after build/load, before search. */
+/* This handle is rank `rank` of `world`: it scans only the lists (or list ranges) it owns.  Shards are dealt to
+ * ranks by greedy balance on vector count; the unit is the reference's shard, src/ivf_index.rs:104-164.  Centroids
+ * stay replicated so every rank computes the same probe lists.
+ *   BEFORE build / load: only the owned part ever reaches HBM (per-rank residency ~ 1/world; training still sees the
+ *     whole data set, so every rank derives the same centroids and the same partition).  Such a handle cannot be
+ *     re-partitioned afterwards (VIDX_ERR_INVALID_INPUT).
+ *   AFTER build / load of a whole index: a mask only -- everything stays resident, any (rank, world) may follow. */
 int vidx_set_partition(vidx_index* idx, int rank, int world);
 /* How the index is split: 0 = auto (default: shards, unless the most loaded rank would exceed the
  * mean by more than 15 % -- then ranges), 1 = shards, 2 = ranges (every rank owns the r-th contiguous
@@ -178,11 +205,37 @@ int vidx_get_shard_owner(const vidx_index* idx, int world, int32_t* out /* num_s
  * vector counts -> owner rank per shard; largest shard first to the least loaded rank,
  * ties to the lower rank / lower shard id. */
 int vidx_partition_shards(const uint64_t* shard_sizes, uint64_t num_shards, int world, int32_t* out);
-/* Merge `nruns` per-rank results (each nq x k, ascending, padded) laid out run-major in
+/* Merge `nruns` per-rank results (each nq x k, ascending, padded with +inf / -1) laid out run-major in
  * DEVICE memory into the global top-k: the reduction behind join_all + concat + sort
- * in src/ivf_index.rs:249-266.  Ties resolve to the lower run index. */
+ * in src/ivf_index.rs:249-266.  Any k.  Ties resolve to the lower run index. */
 int vidx_merge_topk_device(int device, const float* d_D_runs, const int64_t* d_I_runs, uint32_t nruns, uint64_t nq,
                            uint64_t k, float* d_D, int64_t* d_I, void* stream);
+/* For hosts that run the exchange themselves (MPI, one process driving several GPUs): the local part of a partitioned
+ * search with, per result, the key (probe rank << 32 | global row) -- padded with UINT64_MAX -- and the merge that
+ * orders by (distance, key), i.e. exactly as the reference's stable sort over candidates gathered in probe order does
+ * (src/ivf_index.rs:249-266): the merged answer equals the single-GPU answer bit for bit, ties included.
+ * vidx_search_multi is these two around one NCCL all-gather. */
+int vidx_search_local_device(vidx_index* idx, const float* d_xq, uint64_t nq, uint64_t k, uint64_t n_probe, float* d_D,
+                             int64_t* d_I, uint64_t* d_keys, void* stream);
+int vidx_merge_topk_keyed_device(int device, const float* d_D_runs, const int64_t* d_I_runs, const uint64_t* d_K_runs,
+                                 uint32_t nruns, uint64_t nq, uint64_t k, float* d_D, int64_t* d_I, void* stream);
+
+/* The exchange step inside the library (north_star 4; replaces join_all + concat + sort, src/ivf_index.rs:249-266):
+ * one NCCL communicator per handle, one rank per GPU.  Rank 0 obtains an id (vidx_comm_unique_id), the host program
+ * hands it to every rank (any channel: MPI, a file, torch.distributed), every rank calls vidx_comm_init -- collectively.
+ * rank / world must equal the handle's partition.  NCCL is bound with dlopen("libnccl.so.2") at the first call. */
+#define VIDX_COMM_ID_BYTES 128
+int vidx_comm_unique_id(uint8_t* out /* VIDX_COMM_ID_BYTES */);
+int vidx_comm_init(vidx_index* idx, int rank, int world, const uint8_t* unique_id);
+int vidx_comm_destroy(vidx_index* idx);
+const char* vidx_comm_version(const vidx_index* idx); /* "NCCL x.y.z", "" before vidx_comm_init */
+/* Collective search: every rank passes the SAME queries and gets the FULL answer.  Coarse quantization is split by
+ * query (all-gather of the probe lists), every rank scans what it owns, the per-rank top-k runs are exchanged with ONE
+ * packed all-gather (distance | id | (probe rank, global row) key) and merged on the device by (distance, key) -- the
+ * result is bit-identical to a single-GPU vidx_search, ties included, for any k.  Host buffers / device buffers. */
+int vidx_search_multi(vidx_index* idx, const float* xq, uint64_t nq, uint64_t k, uint64_t n_probe, float* D, int64_t* I);
+int vidx_search_multi_device(vidx_index* idx, const float* d_xq, uint64_t nq, uint64_t k, uint64_t n_probe, float* d_D,
+                             int64_t* d_I, void* stream);
 
 /* ---- measurement ------------------------------------------------------------------- */
 

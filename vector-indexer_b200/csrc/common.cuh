@@ -84,6 +84,34 @@ struct PinnedBuf {
 
 inline size_t ceil_div(size_t a, size_t b) { return (a + b - 1) / b; }
 
+// ---- per-device one-time state ---------------------------------------------------------
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) and the SM count belong to a DEVICE, not to the process: a
+// second handle on another GPU of the same process needs its own opt-ins.  Slots are indexed by the current
+// device ordinal; racing threads at worst set the same attribute twice.
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+    int dev = 0;
+    VIDX_CUDA(cudaGetDevice(&dev));
+    return dev < 0 || dev >= kMaxDevices ? 0 : dev;
+}
+struct PerDeviceSize {
+    std::atomic<size_t> v[kMaxDevices];
+    PerDeviceSize() { for (auto& x : v) x.store(0); }
+    // true when `want` exceeds what this device has been configured for so far (the caller then sets the attribute)
+    bool needs(size_t want) const { return want > v[current_device()].load(std::memory_order_acquire); }
+    void set(size_t want) { v[current_device()].store(want, std::memory_order_release); }
+};
+inline int device_num_sms() {
+    static std::atomic<int> sms[kMaxDevices];
+    const int dev = current_device();
+    int n = sms[dev].load(std::memory_order_acquire);
+    if (!n) {
+        VIDX_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+        sms[dev].store(n, std::memory_order_release);
+    }
+    return n;
+}
+
 // One segment = up to kSegGroups consecutive groups of one list.
 struct SegDesc {
     uint32_t g0;      // first group (global group index into the interleaved store)

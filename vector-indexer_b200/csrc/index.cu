@@ -6,6 +6,7 @@
 #include <cstring>
 #include <ctime>
 #include <mutex>
+#include <shared_mutex>
 #include <numeric>
 #include <string>
 #include <vector>
@@ -47,16 +48,15 @@ void Index::ensure_device() {
         VIDX_CUDA(cudaGetDeviceProperties(&prop, device));
         if (prop.major < 10) throw CudaError("libvidx_b200 is built for sm_100a (Blackwell) only");
         VIDX_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-        for (auto& ev : events) VIDX_CUDA(cudaEventCreate(&ev));
     }
 }
 
 Index::~Index() {
+    if (stream || !pool.empty()) cudaSetDevice(device);
     delete_workspace();
+    comm_destroy(comm);
     if (stream) {
-        cudaSetDevice(device);
         cudaStreamSynchronize(stream);
-        for (auto& ev : events) if (ev) cudaEventDestroy(ev);
         cudaStreamDestroy(stream);
     }
 }
@@ -100,11 +100,69 @@ void Index::train_on_device(const float* d_data, uint64_t n, uint64_t seed_, uin
 // add: lists from labels, empty-list filter + renumbering, shard map, device layout
 // (src/ivf_index.rs:79-164)
 // ------------------------------------------------------------------------------------
+// Global layout: whole supergroups per list, segments of <= kSegGroups groups.
+void Index::layout_lists() {
+    list_goff.assign(nlist + 1, 0);
+    list_seg_off_all.assign(nlist + 1, 0);
+    segs.clear();
+    for (uint64_t l = 0; l < nlist; l++) {
+        uint32_t ng = 4 * (uint32_t)ceil_div(list_len[l], kSuper);  // whole supergroups
+        list_goff[l + 1] = list_goff[l] + ng;
+        for (uint32_t g = 0; g < ng; g += kSegGroups) {
+            SegDesc s;
+            s.g0 = (uint32_t)(list_goff[l] + g);
+            s.ng = std::min<uint32_t>(kSegGroups, ng - g);
+            s.nvalid = std::min<uint32_t>(s.ng * kGroup, list_len[l] - g * kGroup);
+            s.list = (uint32_t)l;
+            segs.push_back(s);
+        }
+        list_seg_off_all[l + 1] = (uint32_t)segs.size();
+    }
+    if (list_goff[nlist] * kGroup >= 0xffffffffull) throw ApiError(VIDX_ERR_UNSUPPORTED, "too many rows for 32-bit row ids");
+}
+
+// What goes to HBM: everything, or -- when the partition was set before build / load -- only the segment ranges this
+// rank owns.  Resident ranges are laid out list by list; rows, groups and d_segs[].g0 on the device are LOCAL.
+void Index::plan_residency() {
+    resident_partial = part_pending && part_world > 1;
+    res_seg.assign(nlist + 1, make_uint2(0, 0));
+    res_g0.assign(nlist + 1, 0);
+    uint64_t g = 0;
+    resident_vectors = 0;
+    for (uint64_t l = 0; l < nlist; l++) {
+        uint2 r = resident_partial ? list_seg_part[l] : make_uint2(list_seg_off_all[l], list_seg_off_all[l + 1]);
+        if (r.y <= r.x) r = make_uint2(list_seg_off_all[l], list_seg_off_all[l]);
+        res_seg[l] = r;
+        res_g0[l] = (uint32_t)g;
+        for (uint32_t s = r.x; s < r.y; s++) {
+            g += segs[s].ng;
+            resident_vectors += segs[s].nvalid;
+        }
+    }
+    res_g0[nlist] = (uint32_t)g;
+    res_groups = g;
+}
+uint32_t Index::local_group_of_seg(uint64_t l, uint32_t s) const {
+    return res_g0[l] + (segs[s].g0 - segs[res_seg[l].x].g0);
+}
+uint32_t Index::local_row(uint64_t l, uint32_t j) const {
+    const uint32_t s = list_seg_off_all[l] + j / kSegVecs;
+    if (s < res_seg[l].x || s >= res_seg[l].y) return kNoRow;
+    return local_group_of_seg(l, s) * kGroup + j % kSegVecs;
+}
+bool Index::list_fully_resident(uint64_t l) const {
+    return res_seg[l].x == list_seg_off_all[l] && res_seg[l].y == list_seg_off_all[l + 1];
+}
+uint64_t Index::resident_bytes() const {
+    return d_vecs.cap + d_vecs16.cap + d_vnorm.cap + d_row_ext.cap;
+}
+
 void Index::build_lists(const float* d_data, uint64_t n, const uint32_t* labels, const uint64_t* ext, const uint64_t* ts,
-                        const float* cents_all, uint64_t k, const uint32_t* shard_of_centroid, bool keep_empty) {
+                        const float* cents_all, uint64_t k, const uint32_t* shard_of_centroid) {
     if (n >= 0xffffffffull) throw ApiError(VIDX_ERR_UNSUPPORTED, "more than 2^32-1 vectors per device");
     ntotal = n;
     internal_ids.clear();
+    load_warnings.clear();
     train_labels.assign(labels, labels + n);
     ext_ids.resize(n);
     timestamps.resize(n);
@@ -126,46 +184,46 @@ void Index::build_lists(const float* d_data, uint64_t n, const uint32_t* labels,
     c2shard.clear();
     list_len.clear();
     for (uint64_t c = 0; c < k; c++) {
-        if (!sz[c] && !keep_empty) continue;
+        if (!sz[c]) continue;
         old_to_new[c] = (uint32_t)list_len.size();
         centroids.insert(centroids.end(), cents_all + c * dim, cents_all + (c + 1) * dim);
         c2shard.push_back(shard_of_centroid ? shard_of_centroid[c] : 0);  // indexed by the OLD id (ivf_index.rs:153-154)
         list_len.push_back(sz[c]);
     }
     nlist = list_len.size();
-    // layout: whole groups per list, segments of <= kSegGroups groups
-    list_goff.assign(nlist + 1, 0);
-    list_seg_off_all.assign(nlist + 1, 0);
-    segs.clear();
-    for (uint64_t l = 0; l < nlist; l++) {
-        uint32_t ng = 4 * (uint32_t)ceil_div(list_len[l], kSuper);  // whole supergroups
-        list_goff[l + 1] = list_goff[l] + ng;
-        for (uint32_t g = 0; g < ng; g += kSegGroups) {
-            SegDesc s;
-            s.g0 = (uint32_t)(list_goff[l] + g);
-            s.ng = std::min<uint32_t>(kSegGroups, ng - g);
-            s.nvalid = std::min<uint32_t>(s.ng * kGroup, list_len[l] - g * kGroup);
-            s.list = (uint32_t)l;
-            segs.push_back(s);
-        }
-        list_seg_off_all[l + 1] = (uint32_t)segs.size();
+    layout_lists();
+    if (!part_pending) {
+        part_rank = 0;
+        part_world = 1;
     }
-    uint64_t ngroups = list_goff[nlist];
-    uint64_t nrows = ngroups * kGroup;
-    if (nrows >= 0xffffffffull) throw ApiError(VIDX_ERR_UNSUPPORTED, "too many rows for 32-bit row ids");
+    plan_partition();
+    plan_residency();
     // stable scatter: vectors keep ascending original index inside a list (ivf_index.rs:94-101)
-    row_src.assign(nrows, kNoRow);
+    row_src.assign(res_groups * kGroup, kNoRow);
     {
-        std::vector<uint64_t> cur(nlist);
-        for (uint64_t l = 0; l < nlist; l++) cur[l] = list_goff[l] * kGroup;
-        for (uint64_t i = 0; i < n; i++) row_src[cur[old_to_new[labels[i]]]++] = (uint32_t)i;
+        std::vector<uint32_t> cur(nlist, 0);
+        for (uint64_t i = 0; i < n; i++) {
+            const uint32_t l = old_to_new[labels[i]];
+            const uint32_t r = local_row(l, cur[l]++);
+            if (r != kNoRow) row_src[r] = (uint32_t)i;
+        }
     }
+    finish_store(d_data);
+}
+
+// row_src (local row -> row of d_data) + the host tables -> everything the search kernels read.
+void Index::finish_store(const float* d_data) {
+    const uint64_t nrows = res_groups * kGroup;
     std::vector<uint64_t> row_ext(nrows, ~0ull);
     for (uint64_t r = 0; r < nrows; r++)
         if (row_src[r] != kNoRow) row_ext[r] = ext_ids[row_src[r]];
 
     // device store
     int Dq = dq();
+    d_vecs.release();
+    d_vecs16.release();
+    d_vnorm.release();
+    d_row_ext.release();
     d_vecs.reserve(std::max<uint64_t>(nrows, 1) * Dq * 16);
     DevBuf d_row_src;
     d_row_src.reserve(std::max<uint64_t>(nrows, 1) * 4);
@@ -224,13 +282,31 @@ void Index::build_lists(const float* d_data, uint64_t n, const uint32_t* labels,
         }
         VIDX_CUDA(cudaStreamSynchronize(stream));
     }
-    d_segs.reserve(std::max<size_t>(segs.size(), 1) * sizeof(SegDesc));
-    h2d(d_segs.as<SegDesc>(), segs.data(), segs.size(), stream);
+    // the segment table the kernels see: local groups for resident segments, empty entries for the rest
+    {
+        std::vector<SegDesc> dsegs(segs.size());
+        for (uint64_t l = 0; l < nlist; l++)
+            for (uint32_t s = list_seg_off_all[l]; s < list_seg_off_all[l + 1]; s++) {
+                SegDesc d = segs[s];
+                if (s >= res_seg[l].x && s < res_seg[l].y) {
+                    d.g0 = local_group_of_seg(l, s);
+                } else {
+                    d.g0 = 0;
+                    d.ng = 0;
+                    d.nvalid = 0;
+                }
+                dsegs[s] = d;
+            }
+        d_segs.reserve(std::max<size_t>(dsegs.size(), 1) * sizeof(SegDesc));
+        h2d(d_segs.as<SegDesc>(), dsegs.data(), dsegs.size(), stream);
+        VIDX_CUDA(cudaStreamSynchronize(stream));
+    }
     // per-list layout + row norms for the tensor-core scan
     {
-
         // fp16 shadow store of the tensor-core filter: vectors scaled by 2^sv so that the largest component
-        // lands in [2^6, 2^7); norm terms (1-eps)|v|^2 * 2^(2sv-g), g chosen so that they stay below 2^15
+        // lands in [2^6, 2^7); norm terms (1-eps)|v|^2 * 2^(2sv-g), g chosen so that they stay below 2^15.
+        // (On a partitioned index vmax / vn_max are those of the resident part: the filter's bounds only need to
+        // hold for the rows this rank scans.)
         const int Dh = tc_dh((int)dim);
         DevBuf d_vntrue, d_stats;
         d_vntrue.reserve(std::max<uint64_t>(nrows, 1) * 4);
@@ -258,9 +334,7 @@ void Index::build_lists(const float* d_data, uint64_t n, const uint32_t* labels,
                              d_vecs16.as<uint4>(), d_vnorm.as<uint4>(), stream);
         VIDX_CUDA(cudaStreamSynchronize(stream));
     }
-    part_rank = 0;
-    part_world = 1;
-    apply_partition();
+    upload_partition();
     VIDX_CUDA(cudaStreamSynchronize(stream));
     built = true;
 }
@@ -297,13 +371,12 @@ std::vector<int32_t> Index::shard_owners(int world) const {
 //   shards : the reference's unit (super-centroid groups of lists, ivf_index.rs:104-164) dealt to ranks by greedy
 //            balance; a list a rank does not own gets an empty segment range, so grouping skips it.
 //   ranges : every rank owns one contiguous range of the segments of EVERY list (list l: rank r owns range
-//            (r + l) mod world, so short lists spread over all ranks).  Equal distances that straddle ranks may
-//            come back in a different order than on one GPU -- the reference leaves that order unspecified too
-//            (HashSet iteration, ivf_index.rs:223-229).  Used when the shards cannot be balanced: the reference's barely-trained k-means routinely
-//            puts nearly all vectors into a handful of lists of ONE shard (SIFT-1M shape, nlist = 1024: one shard
-//            holds 999 954 of 1 000 000 vectors).
+//            (r + l) mod world, so short lists spread over all ranks).  Used when the shards cannot be balanced: the
+//            reference's barely-trained k-means routinely puts nearly all vectors into a handful of lists of ONE shard
+//            (SIFT-1M shape, nlist = 1024: one shard holds 999 954 of 1 000 000 vectors).
 // part_mode 0 picks shards unless the most loaded rank would exceed the mean by more than 15 %.
-void Index::apply_partition() {
+// Host only: the decision depends on list sizes and the shard map alone, so every rank takes the same one.
+void Index::plan_partition() {
     std::vector<int32_t> owner;
     part_by_ranges = false;
     if (part_world > 1) {
@@ -321,9 +394,6 @@ void Index::apply_partition() {
     }
     // segment ids stay global; an unowned list (or part of a list) maps to an empty range
     list_seg_part.assign(nlist + 1, make_uint2(0, 0));
-    std::vector<uint32_t> g0(nlist + 1, 0), ng(nlist + 1, 0), own_len(nlist + 1, 0);
-    owned_vectors = 0;
-    std::vector<uint32_t> nseg_owned;
     for (uint64_t l = 0; l < nlist; l++) {
         const uint32_t s0 = list_seg_off_all[l], s1 = list_seg_off_all[l + 1];
         uint32_t a = s0, b = s1;
@@ -338,13 +408,29 @@ void Index::apply_partition() {
             }
         }
         list_seg_part[l] = make_uint2(a, b);
-        g0[l] = b > a ? segs[a].g0 : (uint32_t)list_goff[l];
+    }
+}
+
+// The owned part of every list in device terms (local groups), and the per-query work bounds derived from it.
+void Index::upload_partition() {
+    std::vector<uint32_t> g0(nlist + 1, 0), ng(nlist + 1, 0), own_len(nlist + 1, 0), rowdelta(nlist + 1, 0);
+    owned_vectors = 0;
+    std::vector<uint32_t> nseg_owned;
+    for (uint64_t l = 0; l < nlist; l++) {
+        const uint32_t a = list_seg_part[l].x, b = list_seg_part[l].y;
+        if (b > a && (a < res_seg[l].x || b > res_seg[l].y))
+            throw ApiError(VIDX_ERR_INVALID_INPUT,
+                           "this handle holds only the part of the index its rank owned at build / load time; a different "
+                           "partition needs a rebuild or reload");
+        g0[l] = b > a ? local_group_of_seg(l, a) : res_g0[l];
         for (uint32_t sidx = a; sidx < b; sidx++) {
             ng[l] += segs[sidx].ng;
             own_len[l] += segs[sidx].nvalid;
             owned_vectors += segs[sidx].nvalid;
         }
         if (b > a) nseg_owned.push_back(b - a);
+        // global row - local row, the same for every resident row of the list
+        if (res_seg[l].y > res_seg[l].x) rowdelta[l] = (segs[res_seg[l].x].g0 - res_g0[l]) * (uint32_t)kGroup;
     }
     // prefix of the largest per-list tile counts: bounds the dump of a query (dump mode of the tensor-core scan)
     {
@@ -368,22 +454,103 @@ void Index::apply_partition() {
     h2d(d_list_ng.as<uint32_t>(), ng.data(), ng.size(), stream);
     d_list_len.reserve(own_len.size() * 4);  // vectors of each list this rank scans (measurement only)
     h2d(d_list_len.as<uint32_t>(), own_len.data(), own_len.size(), stream);
+    d_list_rowdelta.reserve(rowdelta.size() * 4);
+    h2d(d_list_rowdelta.as<uint32_t>(), rowdelta.data(), rowdelta.size(), stream);
     VIDX_CUDA(cudaStreamSynchronize(stream));
+}
+
+void Index::apply_partition() {
+    plan_partition();
+    upload_partition();
 }
 
 // ------------------------------------------------------------------------------------
 // search (src/ivf_index.rs:190-267 for a whole batch)
 // ------------------------------------------------------------------------------------
-struct Index::Workspace {
+struct Workspace {
     DevBuf xq_pad, dist, probes, pair_ns, slot_off, seg_cnt, seg_qoff, seg_cur, seg_qlist, slot_seg, dense, sparse, counters,
         scan_tmp, cand_d, cand_r, alld, row_off, row_len, sel_pos, sel_val, rows, stats, slot_rank, list_cnt, list_cur, list_qoff,
         list_qlist, items_per_list, item_off, qnorm, gthr, cand_cnt, overflow, cand, list_cnt0, list_cur0, list_qoff0, list_qlist0,
-        items_per_list0, item_off0, gtop, glock, tcscale, items, items0, pair_tiles, pair_off, dump, cand_val;
+        items_per_list0, item_off0, gtop, glock, tcscale, items, items0, pair_tiles, pair_off, dump, cand_val, dbg;
 };
-void Index::delete_workspace() {
-    delete ws;
-    ws = nullptr;
+// Coarse quantization on tensor cores has its own scratch (it runs the filter over the centroid table while the list
+// scan's buffers of the same batch are being prepared).
+struct CoarseWs {
+    DevBuf probes0, list_cnt, list_cur, list_qoff, list_qlist, items_per_list, item_off, items, qnorm, gthr, cand_cnt, overflow, cand, gtop, glock, tcscale, counters, scan_tmp, dist_tmp,
+        submin, sel_pos, sel_val;
+};
+// One search in flight.  A call takes a context from the handle's pool, enqueues on its stream (or the caller's) and
+// hands it back; `done` marks the end of that work, and whoever takes the context next makes its stream wait for it,
+// so contexts are reused in stream order without ever being shared by two searches.
+struct SearchCtx {
+    Workspace w;
+    CoarseWs cw;
+    DevBuf io_xq, io_D, io_I, io_rows, io_V;      // vidx_search staging (host-pointer entry points)
+    DevBuf mg_probes_part, mg_probes, mg_pack, mg_all;  // vidx_search_multi: probe slices, packed local / gathered results
+    cudaStream_t stream = nullptr;
+    cudaEvent_t events[10] = {};
+    cudaEvent_t done = nullptr;
+    bool used = false;
+    double st_ms[6] = {};
+    vidx_search_stats stats{};
+    ~SearchCtx() {
+        if (stream) {
+            cudaStreamSynchronize(stream);
+            for (auto& ev : events)
+                if (ev) cudaEventDestroy(ev);
+            if (done) cudaEventDestroy(done);
+            cudaStreamDestroy(stream);
+        }
+    }
+};
+SearchCtx* Index::acquire_ctx() {
+    SearchCtx* c = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(pool_mu);
+        if (!pool.empty()) {
+            c = pool.back();
+            pool.pop_back();
+        }
+    }
+    if (!c) {
+        c = new SearchCtx();
+        try {
+            VIDX_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+            for (auto& ev : c->events) VIDX_CUDA(cudaEventCreate(&ev));
+            VIDX_CUDA(cudaEventCreateWithFlags(&c->done, cudaEventDisableTiming));
+        } catch (...) {
+            delete c;
+            throw;
+        }
+    }
+    return c;
 }
+void Index::release_ctx(SearchCtx* c, cudaStream_t last_stream) {
+    if (last_stream) {
+        cudaEventRecord(c->done, last_stream);
+        c->used = true;
+    }
+    std::lock_guard<std::mutex> lk(pool_mu);
+    stats = c->stats;
+    pool.push_back(c);
+}
+void Index::delete_workspace() {
+    std::lock_guard<std::mutex> lk(pool_mu);
+    for (SearchCtx* c : pool) delete c;
+    pool.clear();
+}
+// RAII: a context for the duration of one enqueue; `st` is the stream the work goes to.
+struct CtxLease {
+    Index& ix;
+    SearchCtx* c;
+    cudaStream_t st = nullptr;
+    explicit CtxLease(Index& i) : ix(i), c(i.acquire_ctx()) {}
+    void use(cudaStream_t s) {
+        st = s;
+        if (c->used) VIDX_CUDA(cudaStreamWaitEvent(st, c->done, 0));  // the context's previous search, whatever stream it ran on
+    }
+    ~CtxLease() { ix.release_ctx(c, st); }
+};
 
 constexpr uint64_t kCoarseTcMinLists = 1ull << 20;  // auto mode: measured slower than the exact FP32 stage up to nlist = 12 639
 constexpr uint64_t kBoundsPassMaxTiles = 2048;  // auto mode: bounds pass first when a query probes at most this many 128-vector tiles
@@ -409,14 +576,9 @@ __global__ void list_stats_kernel(const uint32_t* __restrict__ list_cnt, const u
 // Coarse quantization on tensor cores: the centroid table is a one-list index that every query "probes"; the same fp16
 // filter + exact re-check as the list scan yields each query's n_probe nearest centroids in the reference's order
 // (ascending distance, then list id = the stable sort of ivf_index.rs:215-220), with the reference's exact distances.
-struct CoarseWs {
-    DevBuf probes0, list_cnt, list_cur, list_qoff, list_qlist, items_per_list, item_off, items, qnorm, gthr, cand_cnt, overflow, cand, gtop, glock, tcscale, counters, scan_tmp, dist_tmp,
-        submin, sel_pos, sel_val;
-};
-void Index::coarse_tc(const float4* xq4, uint32_t nqb, uint32_t np, uint32_t* d_probes, float* d_probe_dist, cudaStream_t st) {
-    static thread_local CoarseWs* cws = nullptr;  // per host thread, like the search workspace's use under the handle mutex
-    if (!cws) cws = new CoarseWs();
-    CoarseWs& w = *cws;
+void Index::coarse_tc(SearchCtx& ctx, const float4* xq4, uint32_t nqb, uint32_t np, uint32_t* d_probes, float* d_probe_dist,
+                      cudaStream_t st) {
+    CoarseWs& w = ctx.cw;
     const int Dq = dq();
     const uint32_t k = np;
     const uint32_t capq = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(nlist, 32), 4096);
@@ -522,14 +684,16 @@ void Index::coarse_tc(const float4* xq4, uint32_t nqb, uint32_t np, uint32_t* d_
     launch_finalize(fp, st);
 }
 
-void Index::search_device(const float* d_xq, uint64_t nq, uint64_t k_req, uint64_t nprobe_req, float* d_D, int64_t* d_I,
-                          uint32_t* d_rows_out, cudaStream_t st, uint32_t* d_probe_out, float* d_probe_dist_out) {
+void Index::search_device(SearchCtx& ctx, const float* d_xq, uint64_t nq, uint64_t k_req, uint64_t nprobe_req, float* d_D,
+                          int64_t* d_I, uint32_t* d_rows_out, cudaStream_t st, uint32_t* d_probe_out, float* d_probe_dist_out,
+                          const uint32_t* d_probes_in, unsigned long long* d_keys_out) {
     if (k_req == 0 || nprobe_req == 0)
         throw ApiError(VIDX_ERR_INVALID_INPUT, "k and n_probe must be greater than 0");  // ivf_index.rs:197-202
     if (!built) throw ApiError(VIDX_ERR_OTHER, "index has not been built or loaded");
     if (nq == 0) return;
-    if (!ws) ws = new Workspace();
-    Workspace& w = *ws;
+    Workspace& w = ctx.w;
+    vidx_search_stats& stats = ctx.stats;
+    double (&st_ms)[6] = ctx.st_ms;
     const uint64_t k = std::min<uint64_t>(k_req, max_k);              // api.rs:189
     const uint64_t np_req = std::min<uint64_t>(nprobe_req, max_n_probe);  // api.rs:190
     const uint32_t np = (uint32_t)std::min<uint64_t>(np_req, nlist);
@@ -548,8 +712,7 @@ void Index::search_device(const float* d_xq, uint64_t nq, uint64_t k_req, uint64
     const uint32_t seed_ranks = std::max<uint32_t>(1, std::min<uint32_t>(np, kSeedRanks)), seed_rank_tiles = kSeedBoundTiles / seed_ranks;
     const uint32_t seed_row = seed_ranks * seed_rank_tiles * 4;  // minima per query of the seeding bounds pass
     const uint64_t dump_tiles_per_q = tile_prefix[std::min<size_t>(np, tile_prefix.size() - 1)];
-    const bool tc_dump = tc && scan_mode != 2 &&
-                         (scan_mode == 3 ? (double)nq * (double)dump_tiles_per_q * 16.0 <= 8e9 : dump_tiles_per_q <= kBoundsPassMaxTiles);
+    const bool tc_dump = tc && scan_mode != 2 && dump_tiles_per_q > 0 && (scan_mode == 3 || dump_tiles_per_q <= kBoundsPassMaxTiles);
     const uint32_t nseg = (uint32_t)segs.size();
     const uint32_t ldc = ncgroups * kGroup;
     // pairs bound per query: the np largest per-list segment counts
@@ -564,6 +727,8 @@ void Index::search_device(const float* d_xq, uint64_t nq, uint64_t k_req, uint64
     shrink((double)ldc * 4, 6e9);
     shrink((double)pairs_per_q * (fused ? (double)k * 8 : (double)kSegVecs * 4), 6e9);
     shrink((double)std::max<uint64_t>(pairs_per_q, np), 1.5e9 / 1.0);  // 32-bit pair / slot indices
+    if (tc_dump) shrink((double)dump_tiles_per_q * 16.0, 4e9);           // the bounds pass's minima: 16 B per (query, probed tile)
+    if (tc) shrink(256.0 * 12.0, 4e9);                                    // survivor buffers: at least 256 entries per query
     qb = std::min<uint64_t>(qb, 65535ull * 64);
     uint32_t capq = 0;
     if (tc) {
@@ -572,7 +737,7 @@ void Index::search_device(const float* d_xq, uint64_t nq, uint64_t k_req, uint64
         capq = (uint32_t)std::min<uint64_t>(capq, std::max<uint64_t>(owned_vectors, 32));
     }
 
-    cudaEvent_t* ev = events;
+    cudaEvent_t* ev = ctx.events;
     if (profiling) {
         for (double& m : st_ms) m = 0;
         stats = vidx_search_stats{};
@@ -604,8 +769,13 @@ void Index::search_device(const float* d_xq, uint64_t nq, uint64_t k_req, uint64
         }
         const bool coarse_filter = coarse_mode != 1 && scan_mode != 1 && ctab.ok && np <= 32 && tc_supported((int)dim, np) &&
                                    (coarse_mode == 2 || nlist >= kCoarseTcMinLists);
-        if (coarse_filter) {
-            coarse_tc(xq4, nqb, np, w.probes.as<uint32_t>(), pd, st);
+        if (d_probes_in) {
+            // probe lists computed elsewhere (multi-GPU: every rank ranks the centroids for a slice of the batch and the
+            // slices are all-gathered): row stride np
+            VIDX_CUDA(cudaMemcpyAsync(w.probes.p, d_probes_in + q0 * np, (size_t)nqb * np * 4, cudaMemcpyDeviceToDevice, st));
+            if (profiling) VIDX_CUDA(cudaEventRecord(ev[1], st));
+        } else if (coarse_filter) {
+            coarse_tc(ctx, xq4, nqb, np, w.probes.as<uint32_t>(), pd, st);
             if (profiling) VIDX_CUDA(cudaEventRecord(ev[1], st));
         } else {
             w.dist.reserve((size_t)nqb * ldc * 4);
@@ -628,6 +798,15 @@ void Index::search_device(const float* d_xq, uint64_t nq, uint64_t k_req, uint64
                 h2d(d_probe_dist_out + q0 * npo, inf.data(), inf.size(), st);
                 VIDX_CUDA(cudaMemcpy2DAsync(d_probe_dist_out + q0 * npo, (size_t)npo * 4, pd, (size_t)np * 4, (size_t)np * 4, nqb,
                                             cudaMemcpyDeviceToDevice, st));
+            }
+            if (profiling) {
+                VIDX_CUDA(cudaEventSynchronize(ev[2]));
+                float ms;
+                for (int i = 0; i < 2; i++) {
+                    VIDX_CUDA(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
+                    st_ms[i] += ms;
+                }
+                stats.coarse_flops += 3ull * dim * nqb * nlist;
             }
             continue;
         }
@@ -793,7 +972,7 @@ void Index::search_device(const float* d_xq, uint64_t nq, uint64_t k_req, uint64
             tp.noinsert_tiles = tc_dump ? 0 : seed_rank_tiles;
             tp.work_counter = counters + 8;
 #ifdef VIDX_TC_TIMING
-            static DevBuf d_dbg;
+            DevBuf& d_dbg = w.dbg;
             d_dbg.reserve(1024 * 16 * 8);
             VIDX_CUDA(cudaMemsetAsync(d_dbg.p, 0, 1024 * 16 * 8, st));
             tp.dbg = d_dbg.as<unsigned long long>();
@@ -848,6 +1027,7 @@ void Index::search_device(const float* d_xq, uint64_t nq, uint64_t k_req, uint64
                            st);
         w.rows.reserve((size_t)nqb * kout * 4);
         uint32_t* rows_out = d_rows_out ? d_rows_out + q0 * kout : nullptr;
+        unsigned long long* keys_out = d_keys_out ? d_keys_out + q0 * kout : nullptr;
         if (fused) {
             w.cand_d.reserve(pair_cap * k * 4);
             w.cand_r.reserve(pair_cap * k * 4);
@@ -882,6 +1062,9 @@ void Index::search_device(const float* d_xq, uint64_t nq, uint64_t k_req, uint64
             fp.D = d_D + q0 * kout;
             fp.I = d_I + q0 * kout;
             fp.out_rows = rows_out;
+            fp.out_keys = keys_out;
+            fp.probes = w.probes.as<uint32_t>();
+            fp.list_rowdelta = d_list_rowdelta.as<uint32_t>();
             launch_finalize(fp, st);
         } else {
             // large k: every (query, segment) distance row, then an exact radix select per query
@@ -899,9 +1082,10 @@ void Index::search_device(const float* d_xq, uint64_t nq, uint64_t k_req, uint64
                                w.sel_pos.as<uint32_t>(), w.sel_val.as<float>(), st);
             launch_alldist_finish(w.sel_pos.as<uint32_t>(), w.sel_val.as<float>(), w.slot_off.as<uint32_t>(),
                                   w.slot_seg.as<uint32_t>(), d_segs.as<SegDesc>(), np, nqb, (uint32_t)k, kout,
-                                  d_row_ext.as<uint64_t>(), d_D + q0 * kout, d_I + q0 * kout, rows_out, st);
+                                  d_row_ext.as<uint64_t>(), d_D + q0 * kout, d_I + q0 * kout, rows_out, w.slot_rank.as<uint32_t>(),
+                                  d_list_rowdelta.as<uint32_t>(), keys_out, st);
         }
-        launch_pad_output(d_D + q0 * kout, d_I + q0 * kout, rows_out, nqb, (uint32_t)k, kout, st);
+        launch_pad_output(d_D + q0 * kout, d_I + q0 * kout, rows_out, keys_out, nqb, (uint32_t)k, kout, st);
         if (profiling) {
             VIDX_CUDA(cudaEventRecord(ev[5], st));
             VIDX_CUDA(cudaEventSynchronize(ev[5]));
@@ -956,6 +1140,70 @@ void Index::search_device(const float* d_xq, uint64_t nq, uint64_t k_req, uint64
     stats.kernel_launches = g_kernel_launches.load() - launches0;
 }
 
+// ------------------------------------------------------------------------------------
+// Multi-GPU search: this rank holds part of the index, every rank sees the same query batch.
+//   1. coarse quantization is split by QUERY: rank r ranks the centroids for its slice of the batch (the centroid table
+//      is replicated, the result for a query does not depend on who computes it) and the probe lists are all-gathered --
+//      the stage would otherwise be repeated, whole, on every rank;
+//   2. every rank scans the probed lists (or list ranges) it owns -> its local top-k per query, each result with the
+//      key (probe rank, global row);
+//   3. ONE all-gather of the packed (D | I | key) runs, then a device merge by (distance, key): the order of the
+//      reference's stable sort over candidates gathered in probe order (ivf_index.rs:249-266), so the answer is
+//      bit-identical to the one-GPU answer however the index was split.
+// Every rank ends up with the full answer.  All of it is enqueued on `st`; NCCL orders the collectives with the kernels.
+// ------------------------------------------------------------------------------------
+static void search_multi_device(Index& ix, SearchCtx& c, const float* d_xq, uint64_t nq, uint64_t k_req, uint64_t nprobe_req,
+                                float* d_D, int64_t* d_I, cudaStream_t st) {
+    if (k_req == 0 || nprobe_req == 0) throw ApiError(VIDX_ERR_INVALID_INPUT, "k and n_probe must be greater than 0");
+    if (!ix.built) throw ApiError(VIDX_ERR_OTHER, "index has not been built or loaded");
+    if (!ix.comm) throw ApiError(VIDX_ERR_INVALID_INPUT, "vidx_search_multi before vidx_comm_init");
+    const int world = comm_world(ix.comm), rank = comm_rank(ix.comm);
+    if (world != ix.part_world || rank != ix.part_rank)
+        throw ApiError(VIDX_ERR_INVALID_INPUT, "communicator rank / world differ from the index partition (vidx_set_partition)");
+    if (nq == 0) return;
+    if (k_req > 0xffffffffull) throw ApiError(VIDX_ERR_UNSUPPORTED, "k too large");
+    const uint32_t np = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(nprobe_req, ix.max_n_probe), ix.nlist);
+    const uint64_t per = ceil_div(nq, (size_t)world), lo = std::min<uint64_t>(nq, per * rank), hi = std::min<uint64_t>(nq, lo + per);
+    const bool profiling = ix.profiling;
+    // 1. probe lists of my slice -> all ranks
+    c.mg_probes_part.reserve(per * np * 4);
+    c.mg_probes.reserve(per * world * np * 4);
+    VIDX_CUDA(cudaMemsetAsync(c.mg_probes_part.p, 0xff, per * np * 4, st));
+    if (hi > lo)
+        ix.search_device(c, d_xq + lo * ix.dim, hi - lo, 1, np, nullptr, nullptr, nullptr, st, c.mg_probes_part.as<uint32_t>(), nullptr);
+    vidx_search_stats coarse_stats = c.stats;
+    comm_all_gather(ix.comm, c.mg_probes_part.p, c.mg_probes.p, per * np * 4, st);
+    // 2. local scan of the owned part, results packed for the exchange: D | I | keys
+    const size_t nres = (size_t)nq * k_req;
+    const size_t off_I = (nres * 4 + 15) & ~(size_t)15, off_K = off_I + nres * 8, run_bytes = off_K + nres * 8;
+    c.mg_pack.reserve(run_bytes);
+    c.mg_all.reserve(run_bytes * world);
+    unsigned char* pack = c.mg_pack.as<unsigned char>();
+    ix.search_device(c, d_xq, nq, k_req, np, reinterpret_cast<float*>(pack), reinterpret_cast<int64_t*>(pack + off_I), nullptr, st,
+                     nullptr, nullptr, c.mg_probes.as<uint32_t>(), reinterpret_cast<unsigned long long*>(pack + off_K));
+    // 3. exchange + merge
+    if (profiling) VIDX_CUDA(cudaEventRecord(c.events[9], st));
+    comm_all_gather(ix.comm, pack, c.mg_all.p, run_bytes, st);
+    {
+        const unsigned char* all = c.mg_all.as<unsigned char>();
+        launch_merge_runs(reinterpret_cast<const float*>(all), run_bytes / 4, reinterpret_cast<const int64_t*>(all + off_I), run_bytes / 8,
+                          reinterpret_cast<const unsigned long long*>(all + off_K), run_bytes / 8, (uint32_t)world, nq, (uint32_t)k_req,
+                          d_D, d_I, st);
+    }
+    if (profiling) {
+        VIDX_CUDA(cudaEventRecord(c.events[7], st));
+        VIDX_CUDA(cudaEventSynchronize(c.events[7]));
+        float ms = 0;
+        VIDX_CUDA(cudaEventElapsedTime(&ms, c.events[9], c.events[7]));
+        c.stats.ms_merge += ms;              // all-gather of the runs + merge (the local finalize is already in ms_merge)
+        c.stats.ms_total += ms + coarse_stats.ms_total;
+        c.stats.ms_coarse = coarse_stats.ms_coarse;
+        c.stats.ms_select = coarse_stats.ms_select;
+        c.stats.coarse_flops = coarse_stats.coarse_flops;
+        c.stats.kernel_launches += coarse_stats.kernel_launches;
+    }
+}
+
 }  // namespace vidx
 
 // ====================================================================================
@@ -965,8 +1213,11 @@ using namespace vidx;
 
 struct vidx_index {
     Index ix;
-    std::mutex mu;
+    // build / load / set_* take it exclusively; searches share it (each search has its own context)
+    std::shared_mutex mu;
 };
+using ExclusiveLock = std::unique_lock<std::shared_mutex>;
+using SharedLock = std::shared_lock<std::shared_mutex>;
 
 namespace {
 template <class F>
@@ -1020,6 +1271,7 @@ void vidx_free(vidx_index* idx) { delete idx; }
 int vidx_set_limits(vidx_index* idx, uint64_t default_k, uint64_t default_n_probe, uint64_t max_k, uint64_t max_n_probe) {
     return guarded([&] {
         require(idx, VIDX_ERR_INVALID_INPUT, "idx is NULL");
+        ExclusiveLock lk(idx->mu);
         idx->ix.default_k = default_k;
         idx->ix.default_n_probe = default_n_probe;
         idx->ix.max_k = max_k;
@@ -1035,19 +1287,40 @@ static void do_train(Index& ix, const float* data, uint64_t n, uint64_t seed, ui
     h2d(d_data.as<float>(), data, (size_t)n * ix.dim, ix.stream);
     ix.train_on_device(d_data.as<float>(), n, seed, nlist, max_iters, d_labels);
 }
+static void build_from_device_data(Index& ix, const float* d_data, const uint64_t* ext_ids, const uint64_t* timestamps, uint64_t n,
+                                   uint64_t seed, uint64_t nlist, uint64_t max_iters) {
+    DevBuf d_labels;
+    ix.train_on_device(d_data, n, seed, nlist, max_iters, d_labels);
+    std::vector<uint32_t> labels(n);
+    d2h_sync(labels.data(), d_labels.as<uint32_t>(), n, ix.stream);
+    d_labels.release();
+    ix.build_lists(d_data, n, labels.data(), ext_ids, timestamps, ix.train_centroids.data(), ix.k_trained, ix.super_labels.data());
+}
 
 int vidx_build(vidx_index* idx, const float* data, const uint64_t* ext_ids, const uint64_t* timestamps, uint64_t n,
                uint64_t seed, uint64_t nlist, uint64_t max_iters) {
     return guarded([&] {
         require(idx, VIDX_ERR_INVALID_INPUT, "idx is NULL");
-        std::lock_guard<std::mutex> lk(idx->mu);
+        ExclusiveLock lk(idx->mu);
         Index& ix = idx->ix;
-        DevBuf d_data, d_labels;
-        do_train(ix, data, n, seed, nlist, max_iters, d_data, d_labels);
-        std::vector<uint32_t> labels(n);
-        d2h_sync(labels.data(), d_labels.as<uint32_t>(), n, ix.stream);
-        ix.build_lists(d_data.as<float>(), n, labels.data(), ext_ids, timestamps, ix.train_centroids.data(), ix.k_trained,
-                       ix.super_labels.data());
+        require(n > 0 && data, VIDX_ERR_INVALID_INPUT, "no vectors provided");  // api.rs:116-118
+        ix.ensure_device();
+        DevBuf d_data;
+        d_data.reserve((size_t)n * ix.dim * 4);
+        h2d(d_data.as<float>(), data, (size_t)n * ix.dim, ix.stream);
+        build_from_device_data(ix, d_data.as<float>(), ext_ids, timestamps, n, seed, nlist, max_iters);
+    });
+}
+int vidx_build_device(vidx_index* idx, const float* d_data, const uint64_t* ext_ids, const uint64_t* timestamps, uint64_t n,
+                      uint64_t seed, uint64_t nlist, uint64_t max_iters) {
+    return guarded([&] {
+        require(idx, VIDX_ERR_INVALID_INPUT, "idx is NULL");
+        ExclusiveLock lk(idx->mu);
+        Index& ix = idx->ix;
+        require(n > 0 && d_data, VIDX_ERR_INVALID_INPUT, "no vectors provided");
+        ix.ensure_device();
+        VIDX_CUDA(cudaDeviceSynchronize());  // the caller's writes to d_data, whatever stream they ran on
+        build_from_device_data(ix, d_data, ext_ids, timestamps, n, seed, nlist, max_iters);
     });
 }
 
@@ -1096,7 +1369,7 @@ int vidx_vector_file_write(const char* vector_file, const float* data, const uin
 int vidx_train(vidx_index* idx, const float* data, uint64_t n, uint64_t seed, uint64_t nlist, uint64_t max_iters) {
     return guarded([&] {
         require(idx, VIDX_ERR_INVALID_INPUT, "idx is NULL");
-        std::lock_guard<std::mutex> lk(idx->mu);
+        ExclusiveLock lk(idx->mu);
         DevBuf d_data, d_labels;
         do_train(idx->ix, data, n, seed, nlist, max_iters, d_data, d_labels);
     });
@@ -1105,7 +1378,7 @@ int vidx_train(vidx_index* idx, const float* data, uint64_t n, uint64_t seed, ui
 int vidx_add(vidx_index* idx, const float* data, const uint64_t* ext_ids, const uint64_t* timestamps, uint64_t n) {
     return guarded([&] {
         require(idx, VIDX_ERR_INVALID_INPUT, "idx is NULL");
-        std::lock_guard<std::mutex> lk(idx->mu);
+        ExclusiveLock lk(idx->mu);
         Index& ix = idx->ix;
         require(ix.trained, VIDX_ERR_INVALID_INPUT, "vidx_add before vidx_train");
         require(n > 0 && data, VIDX_ERR_INVALID_INPUT, "no vectors provided");
@@ -1132,7 +1405,7 @@ int vidx_build_from_labels(vidx_index* idx, const float* data, const uint64_t* e
     return guarded([&] {
         require(idx, VIDX_ERR_INVALID_INPUT, "idx is NULL");
         require(n > 0 && data && centroids && labels && k > 0, VIDX_ERR_INVALID_INPUT, "no vectors provided");
-        std::lock_guard<std::mutex> lk(idx->mu);
+        ExclusiveLock lk(idx->mu);
         Index& ix = idx->ix;
         ix.ensure_device();
         DevBuf d_data;
@@ -1159,52 +1432,62 @@ int vidx_build_from_labels(vidx_index* idx, const float* data, const uint64_t* e
 }
 
 static void search_host(vidx_index* idx, const float* xq, uint64_t nq, uint64_t k, uint64_t n_probe, float* D, int64_t* I,
-                        float* V) {
+                        float* V, bool multi) {
     require(idx, VIDX_ERR_INVALID_INPUT, "idx is NULL");
     require(k != 0 && n_probe != 0, VIDX_ERR_INVALID_INPUT, "k and n_probe must be greater than 0");
     if (nq == 0) return;
     require(xq && D && I, VIDX_ERR_INVALID_INPUT, "NULL buffer");
-    std::lock_guard<std::mutex> lk(idx->mu);
+    SharedLock lk(idx->mu);
     Index& ix = idx->ix;
     require(ix.built, VIDX_ERR_OTHER, "index has not been built or loaded");
     ix.ensure_device();
+    CtxLease lease(ix);
+    SearchCtx& c = *lease.c;
+    lease.use(c.stream);
     const size_t nres = (size_t)nq * k;
-    ix.io_xq.reserve((size_t)nq * ix.dim * 4);
-    ix.io_D.reserve(nres * 4);
-    ix.io_I.reserve(nres * 8);
-    ix.io_rows.reserve(nres * 4);
-    h2d(ix.io_xq.as<float>(), xq, (size_t)nq * ix.dim, ix.stream);
-    ix.search_device(ix.io_xq.as<float>(), nq, k, n_probe, ix.io_D.as<float>(), ix.io_I.as<int64_t>(),
-                     V ? ix.io_rows.as<uint32_t>() : nullptr, ix.stream, nullptr, nullptr);
-    VIDX_CUDA(cudaMemcpyAsync(D, ix.io_D.p, nres * 4, cudaMemcpyDeviceToHost, ix.stream));
-    VIDX_CUDA(cudaMemcpyAsync(I, ix.io_I.p, nres * 8, cudaMemcpyDeviceToHost, ix.stream));
+    c.io_xq.reserve((size_t)nq * ix.dim * 4);
+    c.io_D.reserve(nres * 4);
+    c.io_I.reserve(nres * 8);
+    c.io_rows.reserve(nres * 4);
+    h2d(c.io_xq.as<float>(), xq, (size_t)nq * ix.dim, c.stream);
+    if (multi)
+        search_multi_device(ix, c, c.io_xq.as<float>(), nq, k, n_probe, c.io_D.as<float>(), c.io_I.as<int64_t>(), c.stream);
+    else
+        ix.search_device(c, c.io_xq.as<float>(), nq, k, n_probe, c.io_D.as<float>(), c.io_I.as<int64_t>(),
+                         V ? c.io_rows.as<uint32_t>() : nullptr, c.stream, nullptr, nullptr);
+    VIDX_CUDA(cudaMemcpyAsync(D, c.io_D.p, nres * 4, cudaMemcpyDeviceToHost, c.stream));
+    VIDX_CUDA(cudaMemcpyAsync(I, c.io_I.p, nres * 8, cudaMemcpyDeviceToHost, c.stream));
     if (V) {
-        ix.io_V.reserve(nres * ix.dim * 4);
-        launch_gather_vectors(ix.d_vecs.as<float>(), ix.dq(), (int)ix.dim, ix.io_rows.as<uint32_t>(), nres, ix.io_V.as<float>(),
-                              ix.stream);
-        VIDX_CUDA(cudaMemcpyAsync(V, ix.io_V.p, nres * ix.dim * 4, cudaMemcpyDeviceToHost, ix.stream));
+        c.io_V.reserve(nres * ix.dim * 4);
+        launch_gather_vectors(ix.d_vecs.as<float>(), ix.dq(), (int)ix.dim, c.io_rows.as<uint32_t>(), nres, c.io_V.as<float>(),
+                              c.stream);
+        VIDX_CUDA(cudaMemcpyAsync(V, c.io_V.p, nres * ix.dim * 4, cudaMemcpyDeviceToHost, c.stream));
     }
-    VIDX_CUDA(cudaStreamSynchronize(ix.stream));
+    VIDX_CUDA(cudaStreamSynchronize(c.stream));
 }
 
 int vidx_search(vidx_index* idx, const float* xq, uint64_t nq, uint64_t k, uint64_t n_probe, float* D, int64_t* I) {
-    return guarded([&] { search_host(idx, xq, nq, k, n_probe, D, I, nullptr); });
+    return guarded([&] { search_host(idx, xq, nq, k, n_probe, D, I, nullptr, false); });
 }
 int vidx_search_with_vectors(vidx_index* idx, const float* xq, uint64_t nq, uint64_t k, uint64_t n_probe, float* D, int64_t* I,
                              float* V) {
     return guarded([&] {
         require(V != nullptr, VIDX_ERR_INVALID_INPUT, "V is NULL");
-        search_host(idx, xq, nq, k, n_probe, D, I, V);
+        require(!(idx && idx->ix.resident_partial), VIDX_ERR_UNSUPPORTED,
+                "include_vectors on a partitioned index: payloads live on the rank that owns the vector");
+        search_host(idx, xq, nq, k, n_probe, D, I, V, false);
     });
 }
 int vidx_search_device(vidx_index* idx, const float* d_xq, uint64_t nq, uint64_t k, uint64_t n_probe, float* d_D, int64_t* d_I,
                        void* stream) {
     return guarded([&] {
         require(idx, VIDX_ERR_INVALID_INPUT, "idx is NULL");
-        std::lock_guard<std::mutex> lk(idx->mu);
+        SharedLock lk(idx->mu);
         Index& ix = idx->ix;
         ix.ensure_device();
-        ix.search_device(d_xq, nq, k, n_probe, d_D, d_I, nullptr, stream ? (cudaStream_t)stream : ix.stream, nullptr, nullptr);
+        CtxLease lease(ix);
+        lease.use(stream ? (cudaStream_t)stream : lease.c->stream);
+        ix.search_device(*lease.c, d_xq, nq, k, n_probe, d_D, d_I, nullptr, lease.st, nullptr, nullptr);
     });
 }
 int vidx_coarse_probes(vidx_index* idx, const float* xq, uint64_t nq, uint64_t n_probe, uint32_t* lists, float* dists) {
@@ -1212,19 +1495,22 @@ int vidx_coarse_probes(vidx_index* idx, const float* xq, uint64_t nq, uint64_t n
         require(idx, VIDX_ERR_INVALID_INPUT, "idx is NULL");
         require(n_probe != 0, VIDX_ERR_INVALID_INPUT, "k and n_probe must be greater than 0");
         if (nq == 0) return;
-        std::lock_guard<std::mutex> lk(idx->mu);
+        SharedLock lk(idx->mu);
         Index& ix = idx->ix;
         require(ix.built, VIDX_ERR_OTHER, "index has not been built or loaded");
         ix.ensure_device();
+        CtxLease lease(ix);
+        lease.use(lease.c->stream);
+        cudaStream_t st = lease.st;
         DevBuf d_xq, d_l, d_d;
         d_xq.reserve((size_t)nq * ix.dim * 4);
         d_l.reserve((size_t)nq * n_probe * 4);
         d_d.reserve((size_t)nq * n_probe * 4);
-        h2d(d_xq.as<float>(), xq, (size_t)nq * ix.dim, ix.stream);
-        ix.search_device(d_xq.as<float>(), nq, 1, n_probe, nullptr, nullptr, nullptr, ix.stream, d_l.as<uint32_t>(),
+        h2d(d_xq.as<float>(), xq, (size_t)nq * ix.dim, st);
+        ix.search_device(*lease.c, d_xq.as<float>(), nq, 1, n_probe, nullptr, nullptr, nullptr, st, d_l.as<uint32_t>(),
                          dists ? d_d.as<float>() : nullptr);
-        d2h_sync(lists, d_l.as<uint32_t>(), (size_t)nq * n_probe, ix.stream);
-        if (dists) d2h_sync(dists, d_d.as<float>(), (size_t)nq * n_probe, ix.stream);
+        d2h_sync(lists, d_l.as<uint32_t>(), (size_t)nq * n_probe, st);
+        if (dists) d2h_sync(dists, d_d.as<float>(), (size_t)nq * n_probe, st);
     });
 }
 
@@ -1233,6 +1519,8 @@ uint64_t vidx_ntotal(const vidx_index* idx) { return idx ? idx->ix.ntotal : 0; }
 uint64_t vidx_nlist(const vidx_index* idx) { return idx ? idx->ix.nlist : 0; }
 uint64_t vidx_num_shards(const vidx_index* idx) { return idx ? idx->ix.num_shards : 0; }
 uint64_t vidx_k_trained(const vidx_index* idx) { return idx ? idx->ix.k_trained : 0; }
+uint64_t vidx_resident_vectors(const vidx_index* idx) { return idx ? idx->ix.resident_vectors : 0; }
+uint64_t vidx_resident_bytes(const vidx_index* idx) { return idx ? idx->ix.resident_bytes() : 0; }
 
 int vidx_get_centroids(const vidx_index* idx, float* out) {
     return guarded([&] {
@@ -1257,7 +1545,8 @@ int vidx_get_list_members(const vidx_index* idx, uint64_t list, uint64_t* out) {
         require(idx && out, VIDX_ERR_INVALID_INPUT, "NULL argument");
         const Index& ix = idx->ix;
         require(list < ix.nlist, VIDX_ERR_NOT_FOUND, "list id out of range");
-        uint64_t r0 = ix.list_goff[list] * kGroup;
+        require(ix.list_fully_resident(list), VIDX_ERR_NOT_FOUND, "list is not (fully) resident on this rank");
+        uint64_t r0 = (uint64_t)ix.res_g0[list] * kGroup;
         for (uint32_t j = 0; j < ix.list_len[list]; j++) {
             uint32_t src = ix.row_src[r0 + j];
             out[j] = ix.internal_ids.empty() ? (uint64_t)src : ix.internal_ids[src];
@@ -1371,16 +1660,20 @@ uint64_t vidx_calculate_max_iterations(uint64_t n) {
 }
 
 // ---- persistence ---------------------------------------------------------------------
+// A partitioned index saves what it holds: with the shard split every rank writes the shard files it owns and rank 0
+// writes index.bin, so N ranks saving into the same directories produce exactly the files one GPU would.
 int vidx_save(const vidx_index* cidx, const char* index_dir, const char* shards_dir) {
     return guarded([&] {
         vidx_index* idx = const_cast<vidx_index*>(cidx);
         require(idx && index_dir && shards_dir, VIDX_ERR_INVALID_INPUT, "NULL argument");
-        std::lock_guard<std::mutex> lk(idx->mu);
+        ExclusiveLock lk(idx->mu);
         Index& ix = idx->ix;
         require(ix.built, VIDX_ERR_OTHER, "index has not been built or loaded");
+        require(!(ix.resident_partial && ix.part_by_ranges), VIDX_ERR_UNSUPPORTED,
+                "a range-partitioned index holds pieces of every list: save from a shard-partitioned or single-GPU handle");
         ix.ensure_device();
-        // vectors back to the host in internal-id order, gathered from the interleaved store
-        const uint64_t n = ix.ntotal;
+        // vectors back to the host by build position, gathered from the interleaved store
+        const uint64_t n = ix.ext_ids.size();
         std::vector<uint32_t> row_of(n, kNoRow);
         for (size_t r = 0; r < ix.row_src.size(); r++)
             if (ix.row_src[r] != kNoRow) row_of[ix.row_src[r]] = (uint32_t)r;
@@ -1398,44 +1691,78 @@ int vidx_save(const vidx_index* cidx, const char* index_dir, const char* shards_
         save_index(ix, host, index_dir, shards_dir);
     });
 }
+// Two phases: index.bin + the header and centroid index of every shard file (list sizes: the partition is decided on
+// them), then only the vector ranges that become resident on this rank (shards.rs:352-425 reads whole shards; a rank
+// of a shard-partitioned index opens only its own shard files for data, a range-partitioned one seeks to its ranges).
 int vidx_load(vidx_index* idx, const char* index_dir, const char* shards_dir) {
     return guarded([&] {
         require(idx && index_dir && shards_dir, VIDX_ERR_INVALID_INPUT, "NULL argument");
-        std::lock_guard<std::mutex> lk(idx->mu);
+        ExclusiveLock lk(idx->mu);
         Index& ix = idx->ix;
-        LoadedIndex L;
-        load_index_files(index_dir, shards_dir, ix.dim, L);
+        LoadedMeta M;
+        load_index_meta(index_dir, shards_dir, M);
         ix.ensure_device();
-        ix.dim = L.dim;  // IvfIndex.dimension from the file (ivf_index.rs:36-41)
-        uint64_t n = 0;
-        for (auto& m : L.list_meta) n += m.size() / 3;
-        std::vector<float> data((size_t)std::max<uint64_t>(n, 1) * L.dim);
-        std::vector<uint32_t> labels(n);
-        std::vector<uint64_t> ext(n), ts(n), internal(n);
-        uint64_t at = 0;
-        for (uint64_t l = 0; l < L.nlist; l++) {
-            uint64_t len = L.list_meta[l].size() / 3;
-            if (len) std::memcpy(&data[at * L.dim], L.list_vectors[l].data(), len * L.dim * 4);
-            for (uint64_t j = 0; j < len; j++, at++) {
-                labels[at] = (uint32_t)l;
-                internal[at] = L.list_meta[l][3 * j];
-                ext[at] = L.list_meta[l][3 * j + 1];
-                ts[at] = L.list_meta[l][3 * j + 2];
-            }
-        }
-        DevBuf d_data;
-        d_data.reserve(data.size() * 4);
-        h2d(d_data.as<float>(), data.data(), data.size(), ix.stream);
-        ix.k_trained = L.nlist;
-        ix.num_shards = L.num_shards;
-        ix.train_centroids = L.centroids;
-        ix.super_labels = L.c2shard;
+        ix.built = false;
+        ix.dim = M.dim;  // IvfIndex.dimension from the file (ivf_index.rs:36-41)
+        ix.nlist = M.nlist;
+        ix.k_trained = M.nlist;
+        ix.num_shards = M.num_shards;
+        ix.centroids = M.centroids;
+        ix.train_centroids = M.centroids;
+        ix.c2shard = M.c2shard;
+        ix.super_labels = M.c2shard;
+        ix.list_len = M.list_len;
+        ix.old_to_new.resize(M.nlist);
+        std::iota(ix.old_to_new.begin(), ix.old_to_new.end(), 0u);
         ix.trained = true;
-        ix.build_lists(d_data.as<float>(), n, labels.data(), ext.data(), ts.data(), L.centroids.data(), L.nlist, L.c2shard.data(),
-                       /*keep_empty=*/true);
-        ix.internal_ids = internal;
-        ix.load_warnings = L.skipped_shards;
+        ix.ntotal = 0;
+        for (uint32_t len : M.list_len) ix.ntotal += len;
+        require(ix.ntotal < 0xffffffffull, VIDX_ERR_UNSUPPORTED, "more than 2^32-1 vectors per device");
+        ix.layout_lists();
+        if (!ix.part_pending) {
+            ix.part_rank = 0;
+            ix.part_world = 1;
+        }
+        ix.plan_partition();
+        ix.plan_residency();
+        // the resident vector range of every list, in vectors
+        std::vector<uint32_t> v0(M.nlist, 0), v1(M.nlist, 0);
+        uint64_t nres = 0;
+        for (uint64_t l = 0; l < M.nlist; l++) {
+            const uint2 r = ix.res_seg[l];
+            if (r.y <= r.x) continue;
+            v0[l] = (r.x - ix.list_seg_off_all[l]) * (uint32_t)kSegVecs;
+            v1[l] = std::min<uint32_t>(ix.list_len[l], (r.y - ix.list_seg_off_all[l]) * (uint32_t)kSegVecs);
+            nres += v1[l] - v0[l];
+        }
+        std::vector<float> data;
+        std::vector<uint64_t> meta;
+        load_list_ranges(shards_dir, M, v0, v1, data, meta);
+        require(meta.size() == nres * 3, VIDX_ERR_OTHER, "shard files changed while loading");
+        ix.ext_ids.resize(nres);
+        ix.timestamps.resize(nres);
+        ix.internal_ids.resize(nres);
+        ix.train_labels.resize(nres);
+        ix.row_src.assign(ix.res_groups * kGroup, kNoRow);
+        uint64_t at = 0;
+        for (uint64_t l = 0; l < M.nlist; l++)
+            for (uint32_t j = v0[l]; j < v1[l]; j++, at++) {
+                ix.internal_ids[at] = meta[3 * at];
+                ix.ext_ids[at] = meta[3 * at + 1];
+                ix.timestamps[at] = meta[3 * at + 2];
+                ix.train_labels[at] = (uint32_t)l;
+                ix.row_src[ix.local_row(l, j)] = (uint32_t)at;
+            }
+        DevBuf d_data;
+        d_data.reserve(std::max<size_t>(data.size(), 1) * 4);
+        h2d(d_data.as<float>(), data.data(), data.size(), ix.stream);
+        ix.finish_store(d_data.as<float>());
+        ix.load_warnings = M.skipped_shards;
     });
+}
+uint64_t vidx_load_warning_count(const vidx_index* idx) { return idx ? idx->ix.load_warnings.size() : 0; }
+const char* vidx_load_warning(const vidx_index* idx, uint64_t i) {
+    return idx && i < idx->ix.load_warnings.size() ? idx->ix.load_warnings[i].c_str() : "";
 }
 
 // ---- multi-GPU ----------------------------------------------------------------------
@@ -1443,24 +1770,44 @@ int vidx_set_partition(vidx_index* idx, int rank, int world) {
     return guarded([&] {
         require(idx, VIDX_ERR_INVALID_INPUT, "idx is NULL");
         require(world >= 1 && rank >= 0 && rank < world, VIDX_ERR_INVALID_INPUT, "bad rank/world");
-        std::lock_guard<std::mutex> lk(idx->mu);
+        ExclusiveLock lk(idx->mu);
         Index& ix = idx->ix;
-        require(ix.built, VIDX_ERR_OTHER, "index has not been built or loaded");
+        if (!ix.built) {  // before build / load: only the owned part will ever reach HBM
+            ix.part_rank = rank;
+            ix.part_world = world;
+            ix.part_pending = true;
+            return;
+        }
         ix.ensure_device();
+        const int r0 = ix.part_rank, w0 = ix.part_world;
         ix.part_rank = rank;
         ix.part_world = world;
-        ix.apply_partition();
+        try {
+            ix.apply_partition();
+        } catch (...) {
+            ix.part_rank = r0;
+            ix.part_world = w0;
+            ix.apply_partition();
+            throw;
+        }
     });
 }
 int vidx_set_partition_mode(vidx_index* idx, int mode) {
     return guarded([&] {
         require(idx, VIDX_ERR_INVALID_INPUT, "idx is NULL");
         require(mode >= 0 && mode <= 2, VIDX_ERR_INVALID_INPUT, "partition mode must be 0 (auto), 1 (shards) or 2 (ranges)");
-        std::lock_guard<std::mutex> lk(idx->mu);
+        ExclusiveLock lk(idx->mu);
+        const int m0 = idx->ix.part_mode;
         idx->ix.part_mode = mode;
         if (idx->ix.built) {
             idx->ix.ensure_device();
-            idx->ix.apply_partition();
+            try {
+                idx->ix.apply_partition();
+            } catch (...) {
+                idx->ix.part_mode = m0;
+                idx->ix.apply_partition();
+                throw;
+            }
         }
     });
 }
@@ -1480,13 +1827,80 @@ int vidx_partition_shards(const uint64_t* shard_sizes, uint64_t num_shards, int 
         for (uint64_t i = 0; i < num_shards; i++) out[i] = o[i];
     });
 }
+int vidx_merge_topk_keyed_device(int device, const float* d_D_runs, const int64_t* d_I_runs, const uint64_t* d_K_runs0, uint32_t nruns,
+                                 uint64_t nq, uint64_t k, float* d_D, int64_t* d_I, void* stream) {
+    return guarded([&] {
+        const unsigned long long* d_K_runs = reinterpret_cast<const unsigned long long*>(d_K_runs0);
+        require(k > 0 && nruns > 0, VIDX_ERR_INVALID_INPUT, "k and nruns must be > 0");
+        require(k <= 0xffffffffull && d_D_runs && d_I_runs && d_D && d_I, VIDX_ERR_INVALID_INPUT, "bad argument");
+        DeviceGuard g(device);
+        const size_t per = (size_t)nq * k;
+        launch_merge_runs(d_D_runs, per, d_I_runs, per, d_K_runs, per, nruns, nq, (uint32_t)k, d_D, d_I, (cudaStream_t)stream);
+    });
+}
 int vidx_merge_topk_device(int device, const float* d_D_runs, const int64_t* d_I_runs, uint32_t nruns, uint64_t nq, uint64_t k,
                            float* d_D, int64_t* d_I, void* stream) {
+    return vidx_merge_topk_keyed_device(device, d_D_runs, d_I_runs, nullptr, nruns, nq, k, d_D, d_I, stream);
+}
+int vidx_search_local_device(vidx_index* idx, const float* d_xq, uint64_t nq, uint64_t k, uint64_t n_probe, float* d_D, int64_t* d_I,
+                             uint64_t* d_keys, void* stream) {
     return guarded([&] {
-        require(k > 0 && nruns > 0, VIDX_ERR_INVALID_INPUT, "k and nruns must be > 0");
-        require(k <= 32, VIDX_ERR_UNSUPPORTED, "vidx_merge_topk_device supports k <= 32");
-        DeviceGuard g(device);
-        launch_merge_runs(d_D_runs, d_I_runs, nruns, nq, (uint32_t)k, d_D, d_I, (cudaStream_t)stream);
+        require(idx, VIDX_ERR_INVALID_INPUT, "idx is NULL");
+        SharedLock lk(idx->mu);
+        Index& ix = idx->ix;
+        ix.ensure_device();
+        CtxLease lease(ix);
+        lease.use(stream ? (cudaStream_t)stream : lease.c->stream);
+        ix.search_device(*lease.c, d_xq, nq, k, n_probe, d_D, d_I, nullptr, lease.st, nullptr, nullptr, nullptr,
+                         reinterpret_cast<unsigned long long*>(d_keys));
+    });
+}
+
+// The exchange step inside the library (north_star 4): NCCL communicator per handle.
+int vidx_comm_unique_id(uint8_t* out) {
+    return guarded([&] {
+        require(out, VIDX_ERR_INVALID_INPUT, "out is NULL");
+        comm_unique_id(out);
+    });
+}
+int vidx_comm_init(vidx_index* idx, int rank, int world, const uint8_t* unique_id) {
+    return guarded([&] {
+        require(idx && unique_id, VIDX_ERR_INVALID_INPUT, "NULL argument");
+        require(world >= 1 && rank >= 0 && rank < world, VIDX_ERR_INVALID_INPUT, "bad rank/world");
+        ExclusiveLock lk(idx->mu);
+        Index& ix = idx->ix;
+        ix.ensure_device();
+        comm_destroy(ix.comm);
+        ix.comm = nullptr;
+        ix.comm = comm_create(ix.device, rank, world, unique_id);
+    });
+}
+int vidx_comm_destroy(vidx_index* idx) {
+    return guarded([&] {
+        require(idx, VIDX_ERR_INVALID_INPUT, "idx is NULL");
+        ExclusiveLock lk(idx->mu);
+        if (idx->ix.comm) {
+            idx->ix.ensure_device();
+            comm_destroy(idx->ix.comm);
+            idx->ix.comm = nullptr;
+        }
+    });
+}
+const char* vidx_comm_version(const vidx_index* idx) { return idx && idx->ix.comm ? comm_version(idx->ix.comm) : ""; }
+
+int vidx_search_multi(vidx_index* idx, const float* xq, uint64_t nq, uint64_t k, uint64_t n_probe, float* D, int64_t* I) {
+    return guarded([&] { search_host(idx, xq, nq, k, n_probe, D, I, nullptr, true); });
+}
+int vidx_search_multi_device(vidx_index* idx, const float* d_xq, uint64_t nq, uint64_t k, uint64_t n_probe, float* d_D,
+                             int64_t* d_I, void* stream) {
+    return guarded([&] {
+        require(idx, VIDX_ERR_INVALID_INPUT, "idx is NULL");
+        SharedLock lk(idx->mu);
+        Index& ix = idx->ix;
+        ix.ensure_device();
+        CtxLease lease(ix);
+        lease.use(stream ? (cudaStream_t)stream : lease.c->stream);
+        search_multi_device(ix, *lease.c, d_xq, nq, k, n_probe, d_D, d_I, lease.st);
     });
 }
 
@@ -1494,13 +1908,14 @@ int vidx_merge_topk_device(int device, const float* d_D_runs, const int64_t* d_I
 int vidx_set_profiling(vidx_index* idx, int enabled) {
     return guarded([&] {
         require(idx, VIDX_ERR_INVALID_INPUT, "idx is NULL");
+        ExclusiveLock lk(idx->mu);
         idx->ix.profiling = enabled != 0;
     });
 }
 int vidx_set_coarse_mode(vidx_index* idx, int mode) {
     return guarded([&] {
         require(idx && mode >= 0 && mode <= 2, VIDX_ERR_INVALID_INPUT, "coarse mode must be 0 (auto), 1 (exact) or 2 (filter)");
-        std::lock_guard<std::mutex> lk(idx->mu);
+        ExclusiveLock lk(idx->mu);
         idx->ix.coarse_mode = mode;
     });
 }
@@ -1508,12 +1923,14 @@ int vidx_set_scan_mode(vidx_index* idx, int mode) {
     return guarded([&] {
         require(idx, VIDX_ERR_INVALID_INPUT, "idx is NULL");
         require(mode >= 0 && mode <= 3, VIDX_ERR_INVALID_INPUT, "mode must be 0 (auto), 1 (exact), 2 (filter, seeded) or 3 (filter, bounds pass first)");
+        ExclusiveLock lk(idx->mu);
         idx->ix.scan_mode = mode;
     });
 }
 int vidx_get_search_stats(vidx_index* idx, vidx_search_stats* out) {
     return guarded([&] {
         require(idx && out, VIDX_ERR_INVALID_INPUT, "NULL argument");
+        std::lock_guard<std::mutex> lk(idx->ix.pool_mu);
         *out = idx->ix.stats;
     });
 }

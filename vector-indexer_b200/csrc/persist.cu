@@ -96,7 +96,36 @@ struct Reader {
 }  // namespace
 
 // ---- save --------------------------------------------------------------------------------
-void save_index(const Index& ix, const std::vector<float>& host_vectors /* ntotal x dim, by internal id */,
+namespace {
+// fwrite that cannot fail silently (a full disk must not leave a truncated shard behind a success code)
+struct CheckedFile {
+    FILE* f = nullptr;
+    std::string path;
+    CheckedFile(const std::string& p) : path(p) {
+        remove(p.c_str());
+        f = fopen(p.c_str(), "wb");
+        if (!f) throw ApiError(VIDX_ERR_OTHER, "cannot create " + p + ": " + strerror(errno));
+    }
+    void write(const void* src, size_t bytes) {
+        if (bytes && fwrite(src, 1, bytes, f) != bytes) {
+            const std::string why = strerror(errno);
+            fclose(f);
+            f = nullptr;
+            throw ApiError(VIDX_ERR_OTHER, "short write to " + path + ": " + why);
+        }
+    }
+    void close() {
+        FILE* g = f;
+        f = nullptr;
+        if (g && fclose(g) != 0) throw ApiError(VIDX_ERR_OTHER, "write failed: " + path);
+    }
+    ~CheckedFile() { if (f) fclose(f); }
+};
+}  // namespace
+
+// A rank of a shard-partitioned index writes the shard files it owns; index.bin comes from rank 0 (every rank
+// holds the same centroid table).
+void save_index(const Index& ix, const std::vector<float>& host_vectors /* by build position */,
                 const std::string& index_dir, const std::string& shards_dir) {
     const uint32_t D = ix.dim;
     mkdirs(shards_dir);
@@ -109,34 +138,37 @@ void save_index(const Index& ix, const std::vector<float>& host_vectors /* ntota
     }
     const char zeros[8] = {0};
     for (size_t s = 0; s < shard_lists.size(); s++) {
-        std::string path = shards_dir + "/shard_" + std::to_string(s) + ".bin";
-        remove(path.c_str());
-        FILE* f = fopen(path.c_str(), "wb");
-        if (!f) throw ApiError(VIDX_ERR_OTHER, "cannot create " + path + ": " + strerror(errno));
         const auto& ls = shard_lists[s];
+        if (ix.resident_partial) {  // not this rank's shard
+            bool mine = true;
+            for (uint32_t l : ls) mine = mine && ix.list_fully_resident(l);
+            if (!mine) continue;
+        }
+        CheckedFile f(shards_dir + "/shard_" + std::to_string(s) + ".bin");
         ShardHeader hd{(uint64_t)s, 1, D, (uint32_t)ls.size(), 40, 40 + 32ull * ls.size()};
-        fwrite(&hd, sizeof hd, 1, f);
+        f.write(&hd, sizeof hd);
         uint64_t off = hd.data_offset;
         for (uint32_t l : ls) {
             uint64_t size = vsz + pad + (uint64_t)ix.list_len[l] * (24 + vsz + pad);
             CentroidIndexEntry e{l, ix.list_len[l], 0, off, size};
-            fwrite(&e, sizeof e, 1, f);
+            f.write(&e, sizeof e);
             off += size;
         }
         for (uint32_t l : ls) {
-            fwrite(&ix.centroids[(size_t)l * D], 4, D, f);
-            fwrite(zeros, 1, pad, f);
-            uint64_t r0 = ix.list_goff[l] * kGroup;
+            f.write(&ix.centroids[(size_t)l * D], vsz);
+            f.write(zeros, pad);
+            uint64_t r0 = (uint64_t)ix.res_g0[l] * kGroup;
             for (uint32_t j = 0; j < ix.list_len[l]; j++) {
                 uint32_t src = ix.row_src[r0 + j];
                 VectorMetaRec m{ix.internal_ids.empty() ? (uint64_t)src : ix.internal_ids[src], ix.ext_ids[src], ix.timestamps[src]};
-                fwrite(&m, sizeof m, 1, f);
-                fwrite(&host_vectors[(size_t)src * D], 4, D, f);
-                fwrite(zeros, 1, pad, f);
+                f.write(&m, sizeof m);
+                f.write(&host_vectors[(size_t)src * D], vsz);
+                f.write(zeros, pad);
             }
         }
-        if (fclose(f) != 0) throw ApiError(VIDX_ERR_OTHER, "write failed: " + path);
+        f.close();
     }
+    if (ix.resident_partial && ix.part_rank != 0) return;
     // index.bin
     std::vector<uint8_t> o;
     o.push_back(1);  // ndarray ARRAY_FORMAT_VERSION
@@ -154,15 +186,21 @@ void save_index(const Index& ix, const std::vector<float>& host_vectors /* ntota
     for (uint64_t l = 0; l < ix.nlist; l++) put_varint(o, ix.c2shard[l]);
     put_varint(o, D);  // dimension: u32
     mkdirs(index_dir);
-    std::string ipath = index_dir + "/index.bin";
-    FILE* f = fopen(ipath.c_str(), "wb");
-    if (!f) throw ApiError(VIDX_ERR_OTHER, "cannot create " + ipath + ": " + strerror(errno));
-    fwrite(o.data(), 1, o.size(), f);
-    if (fclose(f) != 0) throw ApiError(VIDX_ERR_OTHER, "write failed: " + ipath);
+    CheckedFile f(index_dir + "/index.bin");
+    f.write(o.data(), o.size());
+    f.close();
 }
 
 // ---- load --------------------------------------------------------------------------------
-void load_index_files(const std::string& index_dir, const std::string& shards_dir, uint32_t expect_dim, LoadedIndex& out) {
+static uint64_t file_size(FILE* f) {
+    struct stat st;
+    return fstat(fileno(f), &st) == 0 ? (uint64_t)st.st_size : 0;
+}
+// Phase 1: index.bin, then header + centroid index of every shard file.  Every size read from a file is checked
+// against the file's length before anything is allocated from it.  A shard that cannot be opened or does not parse
+// is skipped as a whole -- search_with_paths drops failed shard reads (ivf_index.rs:254) -- and reported in
+// skipped_shards; its lists stay empty.
+void load_index_meta(const std::string& index_dir, const std::string& shards_dir, LoadedMeta& out) {
     std::string ipath = index_dir + "/index.bin";
     FILE* f = fopen(ipath.c_str(), "rb");
     if (!f) throw ApiError(errno == ENOENT ? VIDX_ERR_NOT_FOUND : VIDX_ERR_OTHER, "cannot open " + ipath + ": " + strerror(errno));
@@ -177,15 +215,16 @@ void load_index_files(const std::string& index_dir, const std::string& shards_di
     if (r.u8() != 1) throw ApiError(VIDX_ERR_OTHER, "Bincode decoding error: unknown array version");
     uint64_t n1 = r.varint(), n2 = r.varint();
     if (n1 != n2) throw ApiError(VIDX_ERR_OTHER, "Bincode decoding error: array shape mismatch");
+    if (n1 > buf.size()) throw ApiError(VIDX_ERR_OTHER, "Bincode decoding error: array longer than the file");
     out.nlist = n1;
     out.centroids.clear();
-    std::vector<uint64_t> cid(n1);
     uint64_t D = 0;
     for (uint64_t l = 0; l < n1; l++) {
-        cid[l] = r.varint();
+        (void)r.varint();  // Centroid.id
         uint64_t len = r.varint();
         if (l == 0) D = len;
         if (len != D) throw ApiError(VIDX_ERR_OTHER, "Bincode decoding error: ragged centroid vectors");
+        r.need(len * 4);
         for (uint64_t d = 0; d < len; d++) out.centroids.push_back(r.f32());
     }
     if (r.u8() != 1) throw ApiError(VIDX_ERR_OTHER, "Bincode decoding error: unknown array version");
@@ -199,14 +238,13 @@ void load_index_files(const std::string& index_dir, const std::string& shards_di
     }
     out.dim = (uint32_t)r.varint();
     if (n1 && D != out.dim) throw ApiError(VIDX_ERR_INVALID_DATA, "index.bin: centroid length differs from dimension");
-    (void)expect_dim;  // the reference does not check cfg.dimension against the file (api.rs:109-112)
+    if (max_shard > n1) throw ApiError(VIDX_ERR_INVALID_DATA, "index.bin: shard id larger than the number of lists");
     out.num_shards = n1 ? max_shard + 1 : 0;
 
-    // whole-shard loads (shards.rs:352-425).  A shard that cannot be opened or parsed is
-    // skipped, as search_with_paths drops failed shard reads (ivf_index.rs:254).
     const size_t vsz = (size_t)out.dim * 4, pad = (8 - vsz % 8) % 8;
-    out.list_vectors.assign(n1, {});
-    out.list_meta.assign(n1, {});
+    out.list_len.assign(n1, 0);
+    out.list_file_shard.assign(n1, 0);
+    out.list_block_off.assign(n1, 0);
     out.skipped_shards.clear();
     for (uint64_t s = 0; s < out.num_shards; s++) {
         std::string path = shards_dir + "/shard_" + std::to_string(s) + ".bin";
@@ -216,45 +254,82 @@ void load_index_files(const std::string& index_dir, const std::string& shards_di
             if (sf) fclose(sf);
         };
         if (!sf) { skip("cannot open"); continue; }
+        const uint64_t fsz = file_size(sf);
         ShardHeader hd;
         if (fread(&hd, sizeof hd, 1, sf) != 1) { skip("invalid shard header"); continue; }
         if (hd.shard_id != s) { skip("shard id mismatch"); continue; }
         if (hd.dimensions != out.dim) { skip("dimension mismatch"); continue; }
+        if (hd.index_offset > fsz || (uint64_t)hd.num_centroids * sizeof(CentroidIndexEntry) > fsz - hd.index_offset) {
+            skip("invalid index");
+            continue;
+        }
         std::vector<CentroidIndexEntry> ents(hd.num_centroids);
         if (fseek(sf, (long)hd.index_offset, SEEK_SET) != 0 ||
             (hd.num_centroids && fread(ents.data(), sizeof(CentroidIndexEntry), hd.num_centroids, sf) != hd.num_centroids)) {
             skip("invalid index");
             continue;
         }
+        // the whole shard is staged and committed only when every entry is sane
         bool bad = false;
-        std::vector<uint8_t> blk;
         for (const auto& e : ents) {
-            if (e.centroid_id >= n1) { bad = true; break; }
-            blk.resize(e.data_size);
-            if (fseek(sf, (long)e.data_offset, SEEK_SET) != 0 || (e.data_size && fread(blk.data(), 1, blk.size(), sf) != blk.size())) {
+            const uint64_t want = vsz + pad + (uint64_t)e.num_vectors * (24 + vsz + pad);
+            if (e.centroid_id >= n1 || e.data_offset > fsz || e.data_size > fsz - e.data_offset || e.data_size < want) {
                 bad = true;
                 break;
             }
-            size_t off = vsz + pad;
-            auto& lv = out.list_vectors[e.centroid_id];
-            auto& lm = out.list_meta[e.centroid_id];
-            for (uint32_t j = 0; j < e.num_vectors; j++) {
-                if (off + 24 + vsz > blk.size()) { bad = true; break; }
-                VectorMetaRec m;
-                std::memcpy(&m, blk.data() + off, 24);
-                lm.push_back(m.id);
-                lm.push_back(m.external_id);
-                lm.push_back(m.timestamp);
-                size_t at = lv.size();
-                lv.resize(at + out.dim);
-                std::memcpy(&lv[at], blk.data() + off + 24, vsz);
-                off += 24 + vsz + pad;
-            }
-            if (bad) break;
         }
         if (bad) { skip("invalid cluster block"); continue; }
+        for (const auto& e : ents) {
+            out.list_len[e.centroid_id] = e.num_vectors;
+            out.list_file_shard[e.centroid_id] = (uint32_t)s;
+            out.list_block_off[e.centroid_id] = e.data_offset;
+        }
         fclose(sf);
     }
+}
+
+// Phase 2: vectors [v0[l], v1[l]) of every list (records are fixed-size, so a range is one seek + one read).
+void load_list_ranges(const std::string& shards_dir, const LoadedMeta& m, const std::vector<uint32_t>& v0,
+                      const std::vector<uint32_t>& v1, std::vector<float>& data, std::vector<uint64_t>& meta) {
+    const size_t vsz = (size_t)m.dim * 4, pad = (8 - vsz % 8) % 8, rec = 24 + vsz + pad;
+    uint64_t total = 0;
+    for (uint64_t l = 0; l < m.nlist; l++) total += v1[l] - v0[l];
+    data.resize((size_t)total * m.dim);
+    meta.resize((size_t)total * 3);
+    uint64_t at = 0;
+    FILE* sf = nullptr;
+    int64_t open_shard = -1;
+    std::vector<uint8_t> blk;
+    // lists grouped by file so that every shard file is opened once
+    std::vector<uint32_t> order(m.nlist);
+    for (uint64_t l = 0; l < m.nlist; l++) order[l] = (uint32_t)l;
+    // (output order is list order; the file of consecutive lists changes rarely, reopen on change)
+    for (uint32_t l : order) {
+        const uint32_t n = v1[l] - v0[l];
+        if (!n) continue;
+        if (open_shard != (int64_t)m.list_file_shard[l]) {
+            if (sf) fclose(sf);
+            const std::string path = shards_dir + "/shard_" + std::to_string(m.list_file_shard[l]) + ".bin";
+            sf = fopen(path.c_str(), "rb");
+            if (!sf) throw ApiError(VIDX_ERR_OTHER, "cannot open " + path + ": " + strerror(errno));
+            open_shard = m.list_file_shard[l];
+        }
+        blk.resize((size_t)n * rec);
+        const uint64_t off = m.list_block_off[l] + vsz + pad + (uint64_t)v0[l] * rec;
+        if (fseek(sf, (long)off, SEEK_SET) != 0 || fread(blk.data(), 1, blk.size(), sf) != blk.size()) {
+            fclose(sf);
+            throw ApiError(VIDX_ERR_OTHER, "short read in shard_" + std::to_string(open_shard) + ".bin");
+        }
+        for (uint32_t j = 0; j < n; j++, at++) {
+            VectorMetaRec mr;
+            std::memcpy(&mr, blk.data() + (size_t)j * rec, 24);
+            meta[3 * at] = mr.id;
+            meta[3 * at + 1] = mr.external_id;
+            meta[3 * at + 2] = mr.timestamp;
+            std::memcpy(&data[(size_t)at * m.dim], blk.data() + (size_t)j * rec + 24, vsz);
+        }
+    }
+    if (sf) fclose(sf);
 }
 
 // ---- vector files (src/utils.rs:34-107) ----------------------------------------------------
@@ -316,7 +391,7 @@ void write_vector_file(const std::string& path, const float* data, const uint64_
             throw ApiError(VIDX_ERR_OTHER, "short write to " + path);
         }
     }
-    fclose(f);
+    if (fclose(f) != 0) throw ApiError(VIDX_ERR_OTHER, "write failed: " + path);
 }
 
 }  // namespace vidx

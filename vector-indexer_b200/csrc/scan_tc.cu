@@ -283,7 +283,9 @@ __global__ void query_norm_kernel(const float4* __restrict__ xq4, int Dq, uint32
         qn[q] = s;
         gthr_bits[q] = 0x7f800000u;  // +inf
         cand_cnt[q] = 0;
-        overflow[q] = 0;
+        // a query with a NaN / infinite component has no usable filter values (fmaxf below drops NaN, so the batch scale
+        // would not notice): the exact kernels answer it, as they do in scan mode 1
+        overflow[q] = (s != s || isinf(s)) ? 1u : 0u;
         glock[q] = 0;
         glock[nq + q] = 0;  // seqlock version of gtop
         for (uint32_t i = 0; i < k; i++) gtop[(size_t)q * k + i] = __int_as_float(0x7f800000);
@@ -1278,6 +1280,11 @@ __global__ void finalize_kernel(FinalizeParams p) {
         p.D[o] = ok ? fd : __int_as_float(0x7f800000);
         if (p.I) p.I[o] = ok ? (p.row_ext ? (int64_t)p.row_ext[row] : (int64_t)row) : -1;
         if (p.out_rows) p.out_rows[o] = ok ? row : kNoRow;
+        if (p.out_keys) {
+            const uint32_t rank = (uint32_t)(fk >> 32);
+            p.out_keys[o] = ok ? ((unsigned long long)rank << 32) | (uint32_t)(row + p.list_rowdelta[p.probes[(size_t)q * p.nprobe + rank]])
+                               : ~0ull;
+        }
     }
 }
 
@@ -1324,15 +1331,7 @@ void launch_tc_fill(const uint32_t* probes, size_t npairs, uint32_t nprobe, uint
                                                                      list_cur, list_qlist);
     VIDX_LAUNCHED();
 }
-static int tc_num_sms() {
-    static int sms = 0;
-    if (!sms) {
-        int dev;
-        VIDX_CUDA(cudaGetDevice(&dev));
-        VIDX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    }
-    return sms;
-}
+static int tc_num_sms() { return device_num_sms(); }
 void launch_tc_items(const uint32_t* list_cnt, const uint32_t* list_ngroups, uint32_t nlist, unsigned long long* total,
                      uint32_t seed_tiles, uint32_t* chunk_out, uint32_t* items_per_list, cudaStream_t st) {
     if (!nlist) return;
@@ -1353,10 +1352,10 @@ void launch_tc_expand(const uint32_t* list_cnt, const uint32_t* list_ngroups, co
 }
 template <int KR>
 static void launch_scan_tc_kr(const TcParams& p, size_t smem, cudaStream_t st) {
-    static size_t attr = 0;
-    if (smem > attr) {
+    static PerDeviceSize attr;  // the opt-in is per device
+    if (attr.needs(smem)) {
         VIDX_CUDA(cudaFuncSetAttribute(scan_tc_kernel<KR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = smem;
+        attr.set(smem);
     }
     scan_tc_kernel<KR><<<tc_num_sms(), kTcThreads, smem, st>>>(p);
     VIDX_LAUNCHED();

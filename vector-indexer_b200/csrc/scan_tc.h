@@ -93,6 +93,11 @@ struct FinalizeParams {
     float* D;
     int64_t* I;
     uint32_t* out_rows;
+    // optional (multi-GPU merge): per result (probe rank << 32 | global row); needs the probe lists and, per list,
+    // (global row - local row) of this rank's resident part
+    unsigned long long* out_keys;
+    const uint32_t* probes;
+    const uint32_t* list_rowdelta;
 };
 
 bool tc_supported(int D, uint32_t k);  // D = vector dimension

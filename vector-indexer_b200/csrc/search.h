@@ -41,14 +41,17 @@ void launch_scan(bool alldist, const float4* vecs, int Dq, const float4* xq4, co
 void launch_merge_slots(const float* cand_d, const uint32_t* cand_r, const uint32_t* slot_off, uint32_t nq, uint32_t nprobe,
                         uint32_t k, uint32_t kout, const uint64_t* row_ext, float* D, int64_t* I, uint32_t* out_rows,
                         cudaStream_t st);
-void launch_pad_output(float* D, int64_t* I, uint32_t* rows, uint64_t nq, uint32_t k, uint32_t kout, cudaStream_t st);
+void launch_pad_output(float* D, int64_t* I, uint32_t* rows, unsigned long long* keys, uint64_t nq, uint32_t k, uint32_t kout,
+                       cudaStream_t st);
 void launch_alldist_rows(const uint32_t* slot_off, uint32_t nprobe, uint64_t nq, uint64_t* row_off, uint32_t* row_len,
                          cudaStream_t st);
 void launch_alldist_finish(const uint32_t* sel_pos, const float* sel_val, const uint32_t* slot_off, const uint32_t* slot_seg,
                            const SegDesc* segs, uint32_t nprobe, uint64_t nq, uint32_t k, uint32_t kout,
-                           const uint64_t* row_ext, float* D, int64_t* I, uint32_t* out_rows, cudaStream_t st);
+                           const uint64_t* row_ext, float* D, int64_t* I, uint32_t* out_rows, const uint32_t* slot_rank,
+                           const uint32_t* list_rowdelta, unsigned long long* out_keys, cudaStream_t st);
 void launch_gather_vectors(const float* vecs, int Dq, int D, const uint32_t* rows, size_t nres, float* out, cudaStream_t st);
-void launch_merge_runs(const float* Dr, const int64_t* Ir, uint32_t nruns, uint64_t nq, uint32_t k, float* D, int64_t* I,
-                       cudaStream_t st);
+// runs: D at Dr + r * sD, I at Ir + r * sI, optional keys at Kr + r * sK (strides in elements); any k; see merge_runs_kernel
+void launch_merge_runs(const float* Dr, size_t sD, const int64_t* Ir, size_t sI, const unsigned long long* Kr, size_t sK,
+                       uint32_t nruns, uint64_t nq, uint32_t k, float* D, int64_t* I, cudaStream_t st);
 
 }  // namespace vidx

@@ -956,7 +956,8 @@ __global__ void merge_slots_kernel(const float* __restrict__ cand_d, const uint3
     }
 }
 // pad columns [k, kout) when the caller's k exceeds the clamped k
-__global__ void pad_output_kernel(float* D, int64_t* I, uint32_t* rows, uint64_t nq, uint32_t k, uint32_t kout) {
+__global__ void pad_output_kernel(float* D, int64_t* I, uint32_t* rows, unsigned long long* keys, uint64_t nq, uint32_t k,
+                                  uint32_t kout) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t w = kout - k;
     if (i >= nq * w) return;
@@ -964,6 +965,7 @@ __global__ void pad_output_kernel(float* D, int64_t* I, uint32_t* rows, uint64_t
     D[q * kout + t] = __int_as_float(0x7f800000);
     I[q * kout + t] = -1;
     if (rows) rows[q * kout + t] = kNoRow;
+    if (keys) keys[q * kout + t] = ~0ull;
 }
 
 // Large-k path: positions selected from the per-query all-distance rows -> ids.
@@ -972,7 +974,9 @@ __global__ void alldist_finish_kernel(const uint32_t* __restrict__ sel_pos, cons
                                       const uint32_t* __restrict__ slot_off, const uint32_t* __restrict__ slot_seg,
                                       const SegDesc* __restrict__ segs, uint32_t nprobe, uint64_t nq, uint32_t k,
                                       uint32_t kout, const uint64_t* __restrict__ row_ext, float* __restrict__ D,
-                                      int64_t* __restrict__ I, uint32_t* __restrict__ out_rows) {
+                                      int64_t* __restrict__ I, uint32_t* __restrict__ out_rows,
+                                      const uint32_t* __restrict__ slot_rank, const uint32_t* __restrict__ list_rowdelta,
+                                      unsigned long long* __restrict__ out_keys) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nq * (size_t)k) return;
     size_t q = i / k;
@@ -983,6 +987,7 @@ __global__ void alldist_finish_kernel(const uint32_t* __restrict__ sel_pos, cons
         D[o] = __int_as_float(0x7f800000);
         I[o] = -1;
         if (out_rows) out_rows[o] = kNoRow;
+        if (out_keys) out_keys[o] = ~0ull;
         return;
     }
     uint32_t slot = slot_off[q * nprobe] + pos / kSegVecs;
@@ -991,6 +996,8 @@ __global__ void alldist_finish_kernel(const uint32_t* __restrict__ sel_pos, cons
     D[o] = sel_val[i];
     I[o] = (int64_t)row_ext[row];
     if (out_rows) out_rows[o] = row;
+    // (probe rank, global row): the order of the reference's stable sort over candidates gathered in probe order
+    if (out_keys) out_keys[o] = ((unsigned long long)slot_rank[slot] << 32) | (uint32_t)(row + list_rowdelta[sg.list]);
 }
 __global__ void alldist_rows_kernel(const uint32_t* __restrict__ slot_off, uint32_t nprobe, uint64_t nq,
                                     uint64_t* __restrict__ row_off, uint32_t* __restrict__ row_len) {
@@ -1039,54 +1046,51 @@ __global__ void interleave_kernel(const float* __restrict__ src, int D, int Dq, 
     dst[i] = v;
 }
 
-// Multi-GPU: merge nruns per-rank (D, I) runs, each [nq][k] ascending and padded, into
-// the global top-k.  One warp per query; ties keep run order (lower rank first).
-__global__ void merge_runs_kernel(const float* __restrict__ Dr, const int64_t* __restrict__ Ir, uint32_t nruns,
-                                  uint64_t nq, uint32_t k, float* __restrict__ D, int64_t* __restrict__ I) {
-    uint64_t q = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    int lane = threadIdx.x & 31;
-    if (q >= nq) return;
-    // k <= 32 fast path: warp list of (dist, encoded source = run*k + t)
-    float fd = __int_as_float(0x7f800000);
-    uint32_t fr = kNoRow;
-    float thr = fd;
-    for (uint32_t r = 0; r < nruns; r++) {
-        float d = __int_as_float(0x7f800000);
-        int64_t id = -1;
-        if (lane < (int)k) {
-            d = Dr[((size_t)r * nq + q) * k + lane];
-            id = Ir[((size_t)r * nq + q) * k + lane];
-        }
-        unsigned m = __ballot_sync(kFull, id >= 0 && d < thr);
-        while (m) {
-            int src = __ffs(m) - 1;
-            m &= m - 1;
-            float cd = __shfl_sync(kFull, d, src);
-            if (cd < thr) {
-                warp_insert_stable(cd, r * k + src, fd, fr, lane);
-                thr = __shfl_sync(kFull, fd, k - 1);
+// Multi-GPU: merge nruns per-rank results -- run r = D[nq][k] f32 at Dr + r * sD, I[nq][k] i64 at Ir + r * sI and,
+// optionally, keys K[nq][k] u64 at Kr + r * sK (strides in elements) -- each sorted ascending by (distance, key) and
+// padded with +inf, into the global top-k.  key = (probe rank << 32 | global row): (distance, key) is the order of the
+// reference's stable sort over candidates gathered in probe order (ivf_index.rs:249-266), so the merged answer is
+// bit-identical to the one-GPU answer however the index was split, ties included.  Without keys ties go to the lower
+// run.  One thread per (query, run, position): its place in the merged order is its position in its own run plus, for
+// every other run, the number of entries that sort before it (binary search).  Any k.
+__global__ void merge_runs_kernel(const float* __restrict__ Dr, size_t sD, const int64_t* __restrict__ Ir, size_t sI,
+                                  const unsigned long long* __restrict__ Kr, size_t sK, uint32_t nruns, uint64_t nq, uint32_t k,
+                                  float* __restrict__ D, int64_t* __restrict__ I) {
+    const size_t per = nq * (size_t)k;
+    const float kInf = __int_as_float(0x7f800000);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < per * nruns; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t r = (uint32_t)(i / per);
+        const size_t e = i - (size_t)r * per, q = e / k;
+        const uint32_t t = (uint32_t)(e - q * k);
+        const float d = Dr[(size_t)r * sD + e];
+        if (!(d < kInf)) continue;  // padding: a returned distance is never +inf
+        const unsigned long long key = Kr ? Kr[(size_t)r * sK + e] : 0ull;
+        uint32_t pos = t;
+        for (uint32_t r2 = 0; r2 < nruns && pos < k; r2++) {
+            if (r2 == r) continue;
+            const float* d2 = Dr + (size_t)r2 * sD + q * k;
+            const unsigned long long* k2 = Kr ? Kr + (size_t)r2 * sK + q * k : nullptr;
+            uint32_t lo = 0, hi = k;  // first entry of run r2 that does NOT sort before (d, key)
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                const float dm = d2[mid];
+                const bool before = dm < d || (dm == d && (k2 ? k2[mid] < key : r2 < r));
+                if (before) lo = mid + 1;
+                else hi = mid;
             }
+            pos += lo;
         }
-    }
-    if (lane < (int)k) {
-        bool ok = fr != kNoRow;
-        D[q * k + lane] = ok ? fd : __int_as_float(0x7f800000);
-        I[q * k + lane] = ok ? Ir[((size_t)(fr / k) * nq + q) * k + (fr % k)] : -1;
+        if (pos < k) {
+            D[q * k + pos] = d;
+            I[q * k + pos] = Ir[(size_t)r * sI + e];
+        }
     }
 }
 
 // ====================================================================================
 // host launchers
 // ====================================================================================
-static int g_num_sms = 0;
-static int num_sms() {
-    if (!g_num_sms) {
-        int dev;
-        VIDX_CUDA(cudaGetDevice(&dev));
-        VIDX_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-    }
-    return g_num_sms;
-}
+static int num_sms() { return device_num_sms(); }
 
 void launch_fill_u32(uint32_t* p, uint32_t v, size_t n, cudaStream_t st) {
     if (!n) return;
@@ -1109,10 +1113,10 @@ void launch_interleave(const float* src, int D, int Dq, const uint32_t* row_src,
 void launch_coarse_dist(const float4* cents, int ngroups, int Dq, const float4* xq4, uint32_t nq, float* out, uint32_t ldo,
                         cudaStream_t st) {
     if (!nq || !ngroups) return;
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceSize attr;  // the opt-in is per device
+    if (attr.needs(kDenseSmemBytes)) {
         VIDX_CUDA(cudaFuncSetAttribute(coarse_dist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDenseSmemBytes));
-        attr = true;
+        attr.set(kDenseSmemBytes);
     }
     dim3 grid((unsigned)ceil_div(ngroups, kTileGroups), (unsigned)ceil_div(nq, kTileQ));
     coarse_dist_kernel<<<grid, kDenseThreads, kDenseSmemBytes, st>>>(cents, ngroups, Dq, xq4, nq, out, ldo);
@@ -1129,10 +1133,10 @@ void launch_select_topk(const float* vals, const uint64_t* row_off, const uint32
     uint32_t kcap = select_kcap(k);
     size_t smem = (size_t)kcap * 8;
     if (smem > 200 * 1024) throw ApiError(6, "select_topk: k too large for this build (max 25600)");
-    static size_t attr_set = 0;
-    if (smem > 48 * 1024 && smem > attr_set) {
+    static PerDeviceSize attr_set;
+    if (smem > 48 * 1024 && attr_set.needs(smem)) {
         VIDX_CUDA(cudaFuncSetAttribute(select_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = smem;
+        attr_set.set(smem);
     }
     select_topk_kernel<<<(unsigned)nrows, kSelThreads, smem, st>>>(vals, row_off, row_len, ld, n_fixed, k, kcap, out_pos,
                                                                     out_val);
@@ -1173,13 +1177,13 @@ void launch_scan(bool alldist, const float4* vecs, int Dq, const float4* xq4, co
                  const uint32_t* seg_qoff, const uint2* seg_qlist, const ScanItem* dense, const ScanItem* sparse,
                  const uint32_t* counters, uint32_t* work_counters, uint32_t k, float* cand_d, uint32_t* cand_r,
                  float* alld, bool use_sparse, cudaStream_t st) {
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceSize attr;
+    if (attr.needs(1)) {
         VIDX_CUDA(cudaFuncSetAttribute(scan_dense_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDenseSmemBytes));
         VIDX_CUDA(cudaFuncSetAttribute(scan_dense_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDenseSmemBytes));
         VIDX_CUDA(cudaFuncSetAttribute(scan_sparse_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         VIDX_CUDA(cudaFuncSetAttribute(scan_sparse_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        attr = true;
+        attr.set(1);
     }
     int grid = num_sms() * 2;
     if (alldist)
@@ -1208,10 +1212,11 @@ void launch_merge_slots(const float* cand_d, const uint32_t* cand_r, const uint3
                                                                                   row_ext, D, I, out_rows);
     VIDX_LAUNCHED();
 }
-void launch_pad_output(float* D, int64_t* I, uint32_t* rows, uint64_t nq, uint32_t k, uint32_t kout, cudaStream_t st) {
+void launch_pad_output(float* D, int64_t* I, uint32_t* rows, unsigned long long* keys, uint64_t nq, uint32_t k, uint32_t kout,
+                       cudaStream_t st) {
     if (kout <= k || !nq) return;
     size_t n = nq * (size_t)(kout - k);
-    pad_output_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(D, I, rows, nq, k, kout);
+    pad_output_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(D, I, rows, keys, nq, k, kout);
     VIDX_LAUNCHED();
 }
 void launch_alldist_rows(const uint32_t* slot_off, uint32_t nprobe, uint64_t nq, uint64_t* row_off, uint32_t* row_len,
@@ -1222,11 +1227,12 @@ void launch_alldist_rows(const uint32_t* slot_off, uint32_t nprobe, uint64_t nq,
 }
 void launch_alldist_finish(const uint32_t* sel_pos, const float* sel_val, const uint32_t* slot_off, const uint32_t* slot_seg,
                            const SegDesc* segs, uint32_t nprobe, uint64_t nq, uint32_t k, uint32_t kout,
-                           const uint64_t* row_ext, float* D, int64_t* I, uint32_t* out_rows, cudaStream_t st) {
+                           const uint64_t* row_ext, float* D, int64_t* I, uint32_t* out_rows, const uint32_t* slot_rank,
+                           const uint32_t* list_rowdelta, unsigned long long* out_keys, cudaStream_t st) {
     size_t n = nq * (size_t)k;
     if (!n) return;
     alldist_finish_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(sel_pos, sel_val, slot_off, slot_seg, segs, nprobe, nq, k,
-                                                                      kout, row_ext, D, I, out_rows);
+                                                                      kout, row_ext, D, I, out_rows, slot_rank, list_rowdelta, out_keys);
     VIDX_LAUNCHED();
 }
 void launch_gather_vectors(const float* vecs, int Dq, int D, const uint32_t* rows, size_t nres, float* out, cudaStream_t st) {
@@ -1235,10 +1241,13 @@ void launch_gather_vectors(const float* vecs, int Dq, int D, const uint32_t* row
     gather_vectors_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(vecs, Dq, D, rows, nres, out);
     VIDX_LAUNCHED();
 }
-void launch_merge_runs(const float* Dr, const int64_t* Ir, uint32_t nruns, uint64_t nq, uint32_t k, float* D, int64_t* I,
-                       cudaStream_t st) {
-    if (!nq) return;
-    merge_runs_kernel<<<(unsigned)ceil_div(nq * 32, 256), 256, 0, st>>>(Dr, Ir, nruns, nq, k, D, I);
+void launch_merge_runs(const float* Dr, size_t sD, const int64_t* Ir, size_t sI, const unsigned long long* Kr, size_t sK,
+                       uint32_t nruns, uint64_t nq, uint32_t k, float* D, int64_t* I, cudaStream_t st) {
+    if (!nq || !k) return;
+    launch_pad_output(D, I, nullptr, nullptr, nq, 0, k, st);  // slots nobody claims: fewer than k candidates in all
+    const size_t n = nq * (size_t)k * nruns;
+    const unsigned grid = (unsigned)std::min<size_t>(ceil_div(n, 256), (size_t)num_sms() * 32);
+    merge_runs_kernel<<<grid, 256, 0, st>>>(Dr, sD, Ir, sI, Kr, sK, nruns, nq, k, D, I);
     VIDX_LAUNCHED();
 }
 

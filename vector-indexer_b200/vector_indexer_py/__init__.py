@@ -56,29 +56,28 @@ class PyVectorIndex:
 
 
 class VectorIndex:
-    """
-    Vector index handle with async search support.
-
-    Use build() or load() to create an instance.
-    """
+    """What build() and load() return: the index resident in HBM, searchable from asyncio code (`await index.search`)
+    or directly (`index.search_sync`).  Mirrors the reference class of the same name
+    (bindings/python/python/vector_indexer_py/__init__.py:26-94)."""
 
     def __init__(self, native_index: PyVectorIndex):
         self._native = native_index
 
     @property
     def dimension(self) -> int:
-        """Get the dimension of vectors in this index."""
+        """Vector dimension the index was built / loaded with."""
         return self._native.dimension
 
     async def search(self, xq: NDArray[np.float32], k: int, n_probe: int) -> Tuple[NDArray[np.float32], NDArray[np.int64]]:
-        """Search for k nearest neighbors of query vectors (runs the blocking call in the default executor)."""
+        """(D, I) for the whole batch: squared L2 distances f32[nq, k] and external ids i64[nq, k]; the blocking GPU
+        call runs in the loop's default executor so the event loop stays free."""
         xq = np.ascontiguousarray(xq, dtype=np.float32)
         loop = asyncio.get_event_loop()
         D, I = await loop.run_in_executor(None, self._native.search_blocking, xq, k, n_probe)
         return D, I
 
     def search_sync(self, xq: NDArray[np.float32], k: int, n_probe: int) -> Tuple[NDArray[np.float32], NDArray[np.int64]]:
-        """Synchronous search for k nearest neighbors."""
+        """The same search without an event loop: blocks until (D, I) are back on the host."""
         xq = np.ascontiguousarray(xq, dtype=np.float32)
         return self._native.search_blocking(xq, k, n_probe)
 
@@ -108,7 +107,9 @@ def load(index_dir: str, shards_dir: str, dimension: int, *, device: int = 0) ->
         ix = _ffi.Index(dimension, device).load(index_dir, shards_dir)
     except VidxError as e:
         raise RuntimeError(f"Failed to load index: {e}") from e
-    return VectorIndex(PyVectorIndex(ix, dimension))
+    # the dimension stored in index.bin wins (the reference never compares it with the argument, src/api.rs:109-112;
+    # validating queries against the caller's number would let a wider file dimension read past the query buffer)
+    return VectorIndex(PyVectorIndex(ix, ix.dimension))
 
 
 def suggest_nlist(n: int) -> int:

@@ -51,6 +51,7 @@ _SIGS = {
     "vidx_last_error": (C.c_char_p, []),
     "vidx_set_limits": (i32, [vp, u64, u64, u64, u64]),
     "vidx_build": (i32, [vp, f32p, u64p, u64p, u64, u64, u64, u64]),
+    "vidx_build_device": (i32, [vp, vp, u64p, u64p, u64, u64, u64, u64]),
     "vidx_build_from_vector_file": (i32, [vp, C.c_char_p, u64, u64, u64]),
     "vidx_vector_file_read": (i32, [C.c_char_p, u64, u64, f32p, u64p, u64p, u64p]),
     "vidx_vector_file_write": (i32, [C.c_char_p, f32p, u64p, u64p, u64, u64, u64]),
@@ -72,6 +73,16 @@ _SIGS = {
     "vidx_get_list_members": (i32, [vp, u64, u64p]),
     "vidx_get_train_labels": (i32, [vp, u64p]),
     "vidx_get_train_centroids": (i32, [vp, f32p]),
+    "vidx_resident_vectors": (u64, [vp]),
+    "vidx_resident_bytes": (u64, [vp]),
+    "vidx_load_warning_count": (u64, [vp]),
+    "vidx_load_warning": (C.c_char_p, [vp, u64]),
+    "vidx_comm_unique_id": (i32, [C.POINTER(C.c_uint8)]),
+    "vidx_comm_init": (i32, [vp, i32, i32, C.POINTER(C.c_uint8)]),
+    "vidx_comm_destroy": (i32, [vp]),
+    "vidx_comm_version": (C.c_char_p, [vp]),
+    "vidx_search_multi": (i32, [vp, f32p, u64, u64, u64, f32p, i64p]),
+    "vidx_search_multi_device": (i32, [vp, vp, u64, u64, u64, vp, vp, vp]),
     "vidx_kmeans_mini_batch": (i32, [i32, f32p, u64, u64, u64, u64, C.c_float, u64, f32p, u64p, u64p]),
     "vidx_kmeans_parallel": (i32, [i32, f32p, u64, u64, u64, u64, C.c_float, u64, f32p, u64p, u64p]),
     "vidx_assign_points": (i32, [i32, f32p, u64, u64, f32p, u64, u64, u64p]),
@@ -87,6 +98,8 @@ _SIGS = {
     "vidx_get_shard_owner": (i32, [vp, i32, i32p]),
     "vidx_partition_shards": (i32, [u64p, u64, i32, i32p]),
     "vidx_merge_topk_device": (i32, [i32, vp, vp, u32, u64, u64, vp, vp, vp]),
+    "vidx_merge_topk_keyed_device": (i32, [i32, vp, vp, vp, u32, u64, u64, vp, vp, vp]),
+    "vidx_search_local_device": (i32, [vp, vp, u64, u64, u64, vp, vp, vp, vp]),
     "vidx_set_profiling": (i32, [vp, i32]),
     "vidx_set_scan_mode": (i32, [vp, i32]),
     "vidx_get_search_stats": (i32, [vp, C.POINTER(SearchStats)]),
@@ -162,6 +175,13 @@ class Index:
         check(lib().vidx_build(self.h, _f(data), _u(e), _u(t), n, seed, nlist, max_iters))
         return self
 
+    def build_device(self, d_data_ptr, n, ext_ids=None, timestamps=None, seed=42, nlist=0, max_iters=0):
+        """vidx_build_device: the data set already sits in this GPU's memory (n x dimension fp32)."""
+        e = None if ext_ids is None else np.ascontiguousarray(ext_ids, dtype=np.uint64)
+        t = None if timestamps is None else np.ascontiguousarray(timestamps, dtype=np.uint64)
+        check(lib().vidx_build_device(self.h, d_data_ptr, _u(e), _u(t), n, seed, nlist, max_iters))
+        return self
+
     def build_from_vector_file(self, path, seed=42, nlist=0, max_iters=0):
         """VectorIndexer::build_from_vector_file (src/api.rs:149-186)."""
         check(lib().vidx_build_from_vector_file(self.h, os.fsencode(path), seed, nlist, max_iters))
@@ -213,6 +233,37 @@ class Index:
     def search_device(self, d_xq_ptr, nq, k, n_probe, d_D_ptr, d_I_ptr, stream_ptr=0):
         check(lib().vidx_search_device(self.h, d_xq_ptr, nq, k, n_probe, d_D_ptr, d_I_ptr, stream_ptr))
 
+    # ---- multi-GPU: NCCL communicator + collective search --------------------------------
+    def comm_init(self, rank, world, unique_id):
+        """unique_id: the 128 bytes rank 0 got from comm_unique_id(), handed to every rank by the host program."""
+        buf = (C.c_uint8 * 128).from_buffer_copy(bytes(unique_id))
+        check(lib().vidx_comm_init(self.h, rank, world, buf))
+
+    def comm_destroy(self):
+        check(lib().vidx_comm_destroy(self.h))
+
+    @property
+    def comm_version(self):
+        return lib().vidx_comm_version(self.h).decode()
+
+    def search_multi(self, xq, k, n_probe):
+        xq = _c32(xq)
+        nq = xq.shape[0]
+        D = np.empty((nq, k), np.float32)
+        I = np.empty((nq, k), np.int64)
+        check(lib().vidx_search_multi(self.h, _f(xq), nq, k, n_probe, _f(D), I.ctypes.data_as(i64p)))
+        return D, I
+
+    def search_multi_host_ptr(self, xq_ptr, nq, k, n_probe, D_ptr, I_ptr):
+        check(lib().vidx_search_multi(self.h, C.cast(xq_ptr, f32p), nq, k, n_probe, C.cast(D_ptr, f32p), C.cast(I_ptr, i64p)))
+
+    def search_multi_device(self, d_xq_ptr, nq, k, n_probe, d_D_ptr, d_I_ptr, stream_ptr=0):
+        check(lib().vidx_search_multi_device(self.h, d_xq_ptr, nq, k, n_probe, d_D_ptr, d_I_ptr, stream_ptr))
+
+    def search_local_device(self, d_xq_ptr, nq, k, n_probe, d_D_ptr, d_I_ptr, d_keys_ptr, stream_ptr=0):
+        """The local part of a partitioned search, with (probe rank << 32 | global row) keys for the merge."""
+        check(lib().vidx_search_local_device(self.h, d_xq_ptr, nq, k, n_probe, d_D_ptr, d_I_ptr, d_keys_ptr, stream_ptr))
+
     def coarse_probes(self, xq, n_probe):
         xq = _c32(xq)
         nq = xq.shape[0]
@@ -241,6 +292,18 @@ class Index:
     @property
     def k_trained(self):
         return lib().vidx_k_trained(self.h)
+
+    @property
+    def resident_vectors(self):
+        return lib().vidx_resident_vectors(self.h)
+
+    @property
+    def resident_bytes(self):
+        return lib().vidx_resident_bytes(self.h)
+
+    def load_warnings(self):
+        n = lib().vidx_load_warning_count(self.h)
+        return [lib().vidx_load_warning(self.h, i).decode(errors="replace") for i in range(n)]
 
     def centroids(self):
         out = np.empty((self.nlist, self.dimension), np.float32)
@@ -332,11 +395,22 @@ def read_vector_file(path, dim):
     return ids, data, meta
 
 
+def comm_unique_id():
+    """ncclGetUniqueId through the library: 128 bytes for rank 0 to hand to the other ranks."""
+    buf = (C.c_uint8 * 128)()
+    check(lib().vidx_comm_unique_id(buf))
+    return bytes(buf)
+
+
 def partition_shards(shard_sizes, world):
     sizes = np.ascontiguousarray(shard_sizes, dtype=np.uint64)
     out = np.zeros(len(sizes), np.int32)
     check(lib().vidx_partition_shards(_u(sizes), len(sizes), world, out.ctypes.data_as(i32p)))
     return out
+
+
+def merge_topk_keyed_device(device, d_D_runs, d_I_runs, d_K_runs, nruns, nq, k, d_D, d_I, stream=0):
+    check(lib().vidx_merge_topk_keyed_device(device, d_D_runs, d_I_runs, d_K_runs, nruns, nq, k, d_D, d_I, stream))
 
 
 def merge_topk_device(device, d_D_runs, d_I_runs, nruns, nq, k, d_D, d_I, stream=0):
