@@ -166,6 +166,14 @@ int vidx_kmeans_pp_init(int device, const float* data, uint64_t n, uint64_t dim,
 uint64_t vidx_calculate_num_clusters(uint64_t num_vectors);
 uint64_t vidx_calculate_max_iterations(uint64_t num_vectors);
 
+/* The random stream every build decision is drawn from (csrc/rng.hpp: rand 0.8.5 StdRng::seed_from_u64 = ChaCha12 behind
+ * rand_core's BlockRng; call sites src/kmeans.rs:31,80,170,240,591), host only, so that it can be pinned against known-answer
+ * vectors without a GPU.  After `skip_u32` next_u32 draws: kind 0 = n x next_u32, 1 = n x next_u64, 2 = n x gen_range(0..arg)
+ * on usize, 3 = (0..arg).shuffle (n == arg), 4 = (0..arg).choose_multiple(n).  vidx_stdrng_weighted: n samples of
+ * WeightedIndex::new(weights) (f32). */
+int vidx_stdrng_draw(uint64_t seed, uint64_t skip_u32, int kind, uint64_t arg, uint64_t n, uint64_t* out);
+int vidx_stdrng_weighted(uint64_t seed, const float* weights, uint64_t nw, uint64_t n, uint64_t* out);
+
 /* ---- persistence: shard files + index.bin (cold-start path) ----------------------- */
 
 /* IvfIndex::save_to + Shard::save_to for every shard        src/ivf_index.rs:274-294, src/shards.rs:68-177
@@ -183,6 +191,14 @@ int vidx_save(const vidx_index* idx, const char* index_dir, const char* shards_d
 int vidx_load(vidx_index* idx, const char* index_dir, const char* shards_dir);
 uint64_t vidx_load_warning_count(const vidx_index* idx);
 const char* vidx_load_warning(const vidx_index* idx, uint64_t i);
+
+/* The index.bin codec on its own, host only (no device needed): the bincode 2.0.1 `standard()` + ndarray-serde framing of
+ * IvfIndex { centroids, centroids_to_shard, dimension } that IvfIndex::save_to / load_index_from use
+ * (src/ivf_index.rs:36-41, :274-316).  Read: centroids == NULL && centroids_to_shard == NULL only reports nlist / dimension. */
+int vidx_index_bin_write(const char* index_dir, const float* centroids /* nlist x dimension */,
+                         const uint64_t* centroids_to_shard /* nlist */, uint64_t nlist, uint32_t dimension);
+int vidx_index_bin_read(const char* index_dir, uint64_t cap_lists, float* centroids, uint64_t* centroids_to_shard,
+                        uint64_t* nlist, uint32_t* dimension);
 
 /* ---- multi-GPU: shard partition + top-k merge -------------------------------------- */
 

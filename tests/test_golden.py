@@ -1,0 +1,130 @@
+"""Pinning parity against the REAL crates.  tools/golden/ is a small Rust program that prints known-answer vectors of
+rand 0.8.5 / rand_chacha 0.3.1 / wide 0.7.33 and of the reference itself (k-means on the ramp fixture, the files of a
+12-vector index).  No Rust toolchain exists in this image, so tests/golden/reference_golden.json cannot be produced here;
+the moment a maintainer drops it in (one cargo command, tools/golden/Cargo.toml), these tests compare
+  * the oracle (oracle/vidx_oracle.cpp)                         -- on the CPU
+  * the product's host codecs (index.bin)                       -- on the CPU
+  * the product's k-means + build + save (csrc/rng.hpp, kmeans_host.cu, persist.cu)  -- on the GPU
+against it.  Until then they skip, loudly, and `test_harness_selfcheck` keeps the comparison code itself honest."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import golden_checks as G
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_golden.json")
+WHY = ("PARITY UNPINNED: tests/golden/reference_golden.json is absent -- generate it with cargo from tools/golden "
+       "(see tools/golden/Cargo.toml); this image has no Rust toolchain")
+
+
+def golden():
+    if not os.path.exists(GOLDEN):
+        pytest.skip(WHY)
+    with open(GOLDEN) as f:
+        return json.load(f)
+
+
+def test_harness_selfcheck(oracle):
+    """The comparison runs end to end on a file made from the oracle itself and flags a planted difference."""
+    mine = G.oracle_side(oracle, with_kmeans=False)
+    fake = json.loads(json.dumps(mine))
+    assert G.compare(fake, mine) == []
+    fake["shuffle_10_seed42"][0] ^= 1
+    fake["wide_f32x8_reduce_add"] += 1
+    assert sorted(k for k, _ in G.compare(fake, mine)) == ["shuffle_10_seed42", "wide_f32x8_reduce_add"]
+    # the lane patterns really separate the candidate reduction trees
+    assert len(set(G.reduce_trees(G.X8).values())) == 4 and len(set(G.reduce_trees(G.X4).values())) == 3
+    assert mine["wide_f32x8_reduce_add"] in G.reduce_trees(G.X8).values()
+
+
+def test_oracle_rng_matches_the_real_rand_crates(oracle):
+    g = golden()
+    mine = G.oracle_side(oracle, with_kmeans=False)
+    keys = [k for k in mine if k.startswith(("rng_", "shuffle_", "gen_range_", "weighted_index_", "choose_multiple_"))]
+    assert G.compare(g, mine, keys) == []
+
+
+def test_product_rng_matches_the_real_rand_crates(ffi):
+    """csrc/rng.hpp, the stream the GPU build actually consumes (host only, no device needed)."""
+    g = golden()
+    assert G.compare(g, G.product_rng_side(ffi)) == []
+
+
+def test_product_rng_equals_oracle_rng(ffi, oracle):
+    """Runs with or without the golden file: the two independently written streams agree on every golden key."""
+    mine, theirs = G.product_rng_side(ffi), G.oracle_side(oracle, with_kmeans=False)
+    assert G.compare(theirs, mine) == [] and len(mine) >= 14
+
+
+def test_oracle_reduce_add_matches_the_real_wide_crate(oracle):
+    g = golden()
+    mine = G.oracle_side(oracle, with_kmeans=False)
+    t8 = {v: k for k, v in G.reduce_trees(G.X8).items()}
+    t4 = {v: k for k, v in G.reduce_trees(G.X4).items()}
+    msg = (f"wide::f32x8::reduce_add is the '{t8.get(g['wide_f32x8_reduce_add'], '?')}' tree, f32x4 the "
+           f"'{t4.get(g['wide_f32x4_reduce_add'], '?')}' one (target features of the golden build: {g.get('wide_target_features')}); "
+           f"the oracle assumes '{t8.get(mine['wide_f32x8_reduce_add'])}' / '{t4.get(mine['wide_f32x4_reduce_add'])}'")
+    assert G.compare(g, mine, ["wide_f32x8_reduce_add", "wide_f32x4_reduce_add"]) == [], msg
+
+
+def test_oracle_matches_the_reference_functions(oracle):
+    g = golden()
+    mine = G.oracle_side(oracle, with_kmeans=True)
+    keys = ["calculate_num_clusters", "euclidean_distance_squared_37"] + [k for k in mine if k.startswith("kmeans_")]
+    assert G.compare(g, mine, keys) == []
+
+
+def test_index_bin_codec_reproduces_the_reference_bytes(ffi, tmp_path):
+    """csrc/persist.cu (host only): decode the reference's index.bin, re-encode it, same bytes."""
+    g = golden()
+    ref = bytes.fromhex(g["index_12x3_seed42_files"]["index.bin"])
+    os.makedirs(tmp_path / "a")
+    (tmp_path / "a" / "index.bin").write_bytes(ref)
+    cents, c2s = ffi.index_bin_read(str(tmp_path / "a"))
+    assert cents.shape[1] == 3
+    ffi.index_bin_write(str(tmp_path / "b"), cents, c2s)
+    assert (tmp_path / "b" / "index.bin").read_bytes() == ref
+
+
+def test_oracle_shard_codec_reproduces_the_reference_bytes(oracle, tmp_path):
+    g = golden()
+    for name, hx in g["index_12x3_seed42_files"].items():
+        if not name.startswith("shard_"):
+            continue
+        ref = bytes.fromhex(hx)
+        sid = int(name[len("shard_"):-len(".bin")])
+        p = tmp_path / name
+        p.write_bytes(ref)
+        r = oracle.shard_read(str(p), sid)
+        q = tmp_path / ("re_" + name)
+        assert oracle.shard_write(str(q), sid, r["dim"], r["centroid_ids"], r["centroid_vecs"], r["lens"], r["meta"], r["vecs"]) == 0
+        assert q.read_bytes() == ref, name
+
+
+@pytest.mark.gpu
+def test_product_kmeans_matches_the_reference(ffi, oracle):
+    g = golden()
+    for n, dim, k, iters in G.KMEANS_CASES:
+        key = f"kmeans_mini_batch_ramp_{n}x{dim}_k{k}_it{iters}"
+        c, l, _ = ffi.kmeans_mini_batch(oracle.create_test_vectors(n, dim), k, iters, seed=42)
+        assert G.bits(c) == g[key]["centroids"] and l.tolist() == g[key]["labels"], key
+    c, l, _ = ffi.kmeans_parallel(oracle.create_test_vectors(600, 8), 5, 10, seed=42)
+    key = "kmeans_parallel_ramp_600x8_k5_it10"
+    assert G.bits(c) == g[key]["centroids"] and l.tolist() == g[key]["labels"]
+
+
+@pytest.mark.gpu
+def test_product_build_and_save_reproduce_the_reference_files(ffi, tmp_path):
+    """vidx_build + vidx_save on the generator's 12 x 3 records: index.bin and every shard file byte for byte."""
+    g = golden()
+    ids, vals, ts = G.tiny_index_records()
+    ix = ffi.Index(3).build(vals, ext_ids=ids, timestamps=ts, seed=42)
+    ix.save(str(tmp_path / "index"), str(tmp_path / "shards"))
+    files = g["index_12x3_seed42_files"]
+    assert (tmp_path / "index" / "index.bin").read_bytes() == bytes.fromhex(files["index.bin"])
+    names = sorted(n for n in files if n.startswith("shard_"))
+    assert sorted(os.listdir(tmp_path / "shards")) == names
+    for n in names:
+        assert (tmp_path / "shards" / n).read_bytes() == bytes.fromhex(files[n]), n

@@ -22,6 +22,24 @@ def test_chacha_block_matches_openssl(oracle):
         assert np.array_equal(ks, mine)
 
 
+def test_chacha12_and_chacha8_published_keystream_vectors(oracle):
+    """Known answers for the REDUCED-round variants (draft-strombergson-chacha-test-vectors-01, 256-bit keys): TC1 = all-zero
+    key and IV at 8 and 12 rounds, TC2 = key 01 00 .. 00 at 12 rounds, first keystream block.  StdRng is ChaCha12, so this
+    pins the 12-round block function itself -- not only the 20-round one checked against OpenSSL -- to a published vector."""
+    z = np.zeros(8, np.uint32)
+    tc1_12 = ("9bf49a6a0755f953811fce125f2683d50429c3bb49e074147e0089a52eae155f"
+              "0564f879d27ae3c02ce82834acfa8c793a629f2ca0de6919610be82f411326be")
+    tc1_8 = ("3e00ef2f895f40d67f5bb8e81f09a5a12c840ec3ce9a7f3b181be188ef711a1e"
+             "984ce172b9216f419f445367456d5619314a42a3da86b001387bfdb80e0cfe42")
+    tc2_12 = ("12056e595d56b0f6eef090f0cd25a20949248c2790525d0f930218ff0b4ddd10"
+              "a6002239d9a454e29e107a7d06fefdfef0210feba044f9f29b1772c960dc29c0")
+    assert oracle.chacha_block(z, 0, 0, 12).tobytes().hex() == tc1_12
+    assert oracle.chacha_block(z, 0, 0, 8).tobytes().hex() == tc1_8
+    k = z.copy()
+    k[0] = 1
+    assert oracle.chacha_block(k, 0, 0, 12).tobytes().hex() == tc2_12
+
+
 def test_chacha_rfc7539_quarter_round_vector(oracle):
     """RFC 7539 section 2.3.2 block test vector, mapped onto the 64-bit-counter layout:
     counter word 12 = 1, words 13..15 = nonce (09 00 00 00 | 4a 00 00 00 | 00 00 00 00)."""

@@ -15,6 +15,7 @@
 #include "index.h"
 #include "kmeans_host.h"
 #include "scan_tc.h"
+#include "rng.hpp"
 #include "search.h"
 
 namespace vidx {
@@ -1659,6 +1660,45 @@ uint64_t vidx_calculate_max_iterations(uint64_t n) {
     return 20;
 }
 
+// The random stream the build draws from (csrc/rng.hpp), host only: lets CPU-side tests pin it against known-answer
+// vectors of the real rand crates (tools/golden) and against the oracle's independent restatement.
+int vidx_stdrng_draw(uint64_t seed, uint64_t skip_u32, int kind, uint64_t arg, uint64_t n, uint64_t* out) {
+    return guarded([&] {
+        require(out || !n, VIDX_ERR_INVALID_INPUT, "out is NULL");
+        ChaCha12Rng r(seed);
+        for (uint64_t i = 0; i < skip_u32; i++) r.next_u32();
+        switch (kind) {
+            case 0: for (uint64_t i = 0; i < n; i++) out[i] = r.next_u32(); break;
+            case 1: for (uint64_t i = 0; i < n; i++) out[i] = r.next_u64(); break;
+            case 2: for (uint64_t i = 0; i < n; i++) out[i] = r.below_u64(arg); break;   // gen_range(0..arg) on usize
+            case 3: {                                                                     // (0..arg).shuffle
+                require(n == arg, VIDX_ERR_INVALID_INPUT, "shuffle: n must equal arg");
+                for (uint64_t i = 0; i < n; i++) out[i] = i;
+                r.shuffle(out, (size_t)n);
+                break;
+            }
+            case 4: {                                                                     // (0..arg).choose_multiple(n)
+                require(arg <= 0xffffffffull && n <= arg, VIDX_ERR_INVALID_INPUT, "choose_multiple: bad sizes");
+                std::vector<uint32_t> c = r.choose_multiple((uint32_t)arg, (uint32_t)n);
+                for (size_t i = 0; i < c.size(); i++) out[i] = c[i];
+                break;
+            }
+            default: throw ApiError(VIDX_ERR_INVALID_INPUT, "kind must be 0..4");
+        }
+    });
+}
+int vidx_stdrng_weighted(uint64_t seed, const float* weights, uint64_t nw, uint64_t n, uint64_t* out) {
+    return guarded([&] {
+        require(weights && nw > 0 && (out || !n), VIDX_ERR_INVALID_INPUT, "bad argument");
+        ChaCha12Rng r(seed);
+        float total = 0.0f;
+        for (uint64_t i = 0; i < nw; i++) total += weights[i];  // sequential f32 sum, as WeightedIndex::new
+        require(total > 0.0f, VIDX_ERR_INVALID_INPUT, "total weight must be positive");
+        std::vector<float> cum;
+        for (uint64_t i = 0; i < n; i++) out[i] = r.weighted_pick(weights, (size_t)nw, total, cum);
+    });
+}
+
 // ---- persistence ---------------------------------------------------------------------
 // A partitioned index saves what it holds: with the shard split every rank writes the shard files it owns and rank 0
 // writes index.bin, so N ranks saving into the same directories produce exactly the files one GPU would.
@@ -1758,6 +1798,31 @@ int vidx_load(vidx_index* idx, const char* index_dir, const char* shards_dir) {
         h2d(d_data.as<float>(), data.data(), data.size(), ix.stream);
         ix.finish_store(d_data.as<float>());
         ix.load_warnings = M.skipped_shards;
+    });
+}
+// The index.bin codec on its own (host only): what IvfIndex::save_to / load_index_from write and read.
+int vidx_index_bin_write(const char* index_dir, const float* centroids, const uint64_t* centroids_to_shard, uint64_t nlist,
+                         uint32_t dimension) {
+    return guarded([&] {
+        require(index_dir && (centroids || !nlist) && (centroids_to_shard || !nlist) && dimension > 0, VIDX_ERR_INVALID_INPUT, "bad argument");
+        std::vector<uint32_t> c2s(nlist);
+        for (uint64_t l = 0; l < nlist; l++) c2s[l] = (uint32_t)centroids_to_shard[l];
+        write_index_bin(index_dir, centroids, c2s.data(), nlist, dimension);
+    });
+}
+int vidx_index_bin_read(const char* index_dir, uint64_t cap_lists, float* centroids, uint64_t* centroids_to_shard, uint64_t* nlist,
+                        uint32_t* dimension) {
+    return guarded([&] {
+        require(index_dir && nlist && dimension, VIDX_ERR_INVALID_INPUT, "bad argument");
+        LoadedMeta M;
+        read_index_bin(index_dir, M);
+        *nlist = M.nlist;
+        *dimension = M.dim;
+        if (!centroids && !centroids_to_shard) return;  // sizes only
+        require(cap_lists >= M.nlist, VIDX_ERR_INVALID_INPUT, "buffer too small");
+        if (centroids) std::memcpy(centroids, M.centroids.data(), M.centroids.size() * 4);
+        if (centroids_to_shard)
+            for (uint64_t l = 0; l < M.nlist; l++) centroids_to_shard[l] = M.c2shard[l];
     });
 }
 uint64_t vidx_load_warning_count(const vidx_index* idx) { return idx ? idx->ix.load_warnings.size() : 0; }

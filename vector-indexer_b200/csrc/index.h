@@ -139,6 +139,9 @@ struct LoadedMeta {
 void save_index(const Index& ix, const std::vector<float>& host_vectors, const std::string& index_dir,
                 const std::string& shards_dir);
 void load_index_meta(const std::string& index_dir, const std::string& shards_dir, LoadedMeta& out);
+// index.bin alone (the bincode / ndarray-serde framing of IvfIndex, ivf_index.rs:36-41, :274-316)
+void write_index_bin(const std::string& index_dir, const float* centroids, const uint32_t* c2shard, uint64_t nlist, uint32_t D);
+void read_index_bin(const std::string& index_dir, LoadedMeta& out);  // fills dim, nlist, num_shards, centroids, c2shard
 // Vectors [v0[l], v1[l]) of every list, appended list by list: data (n x dim) and meta (id, external_id, timestamp per vector).
 void load_list_ranges(const std::string& shards_dir, const LoadedMeta& m, const std::vector<uint32_t>& v0,
                       const std::vector<uint32_t>& v1, std::vector<float>& data, std::vector<uint64_t>& meta);

@@ -169,21 +169,28 @@ void save_index(const Index& ix, const std::vector<float>& host_vectors /* by bu
         f.close();
     }
     if (ix.resident_partial && ix.part_rank != 0) return;
-    // index.bin
+    write_index_bin(index_dir, ix.centroids.data(), ix.c2shard.data(), ix.nlist, D);
+}
+
+// index.bin = bincode 2.0.1 `standard()` (little endian, varint integers) over serde of
+//   IvfIndex { centroids: Array1<Centroid{id: usize, vector: Vec<f32>}>, centroids_to_shard: Array1<usize>, dimension: u32 }
+// (ivf_index.rs:36-41, :274-294); ndarray 0.15.6 serialises an array as {v: u8 = 1, dim, data: seq}.
+void write_index_bin(const std::string& index_dir, const float* centroids, const uint32_t* c2shard, uint64_t nlist, uint32_t D) {
+    const size_t vsz = (size_t)D * 4;
     std::vector<uint8_t> o;
     o.push_back(1);  // ndarray ARRAY_FORMAT_VERSION
-    put_varint(o, ix.nlist);  // dim: [usize; 1]
-    put_varint(o, ix.nlist);  // data: seq length
-    for (uint64_t l = 0; l < ix.nlist; l++) {
+    put_varint(o, nlist);  // dim: [usize; 1]
+    put_varint(o, nlist);  // data: seq length
+    for (uint64_t l = 0; l < nlist; l++) {
         put_varint(o, l);  // Centroid.id
         put_varint(o, D);  // Vec<f32> length
-        const uint8_t* b = reinterpret_cast<const uint8_t*>(&ix.centroids[(size_t)l * D]);
+        const uint8_t* b = reinterpret_cast<const uint8_t*>(centroids + (size_t)l * D);
         o.insert(o.end(), b, b + vsz);
     }
     o.push_back(1);
-    put_varint(o, ix.nlist);
-    put_varint(o, ix.nlist);
-    for (uint64_t l = 0; l < ix.nlist; l++) put_varint(o, ix.c2shard[l]);
+    put_varint(o, nlist);
+    put_varint(o, nlist);
+    for (uint64_t l = 0; l < nlist; l++) put_varint(o, c2shard[l]);
     put_varint(o, D);  // dimension: u32
     mkdirs(index_dir);
     CheckedFile f(index_dir + "/index.bin");
@@ -200,7 +207,7 @@ static uint64_t file_size(FILE* f) {
 // against the file's length before anything is allocated from it.  A shard that cannot be opened or does not parse
 // is skipped as a whole -- search_with_paths drops failed shard reads (ivf_index.rs:254) -- and reported in
 // skipped_shards; its lists stay empty.
-void load_index_meta(const std::string& index_dir, const std::string& shards_dir, LoadedMeta& out) {
+void read_index_bin(const std::string& index_dir, LoadedMeta& out) {
     std::string ipath = index_dir + "/index.bin";
     FILE* f = fopen(ipath.c_str(), "rb");
     if (!f) throw ApiError(errno == ENOENT ? VIDX_ERR_NOT_FOUND : VIDX_ERR_OTHER, "cannot open " + ipath + ": " + strerror(errno));
@@ -240,7 +247,11 @@ void load_index_meta(const std::string& index_dir, const std::string& shards_dir
     if (n1 && D != out.dim) throw ApiError(VIDX_ERR_INVALID_DATA, "index.bin: centroid length differs from dimension");
     if (max_shard > n1) throw ApiError(VIDX_ERR_INVALID_DATA, "index.bin: shard id larger than the number of lists");
     out.num_shards = n1 ? max_shard + 1 : 0;
+}
 
+void load_index_meta(const std::string& index_dir, const std::string& shards_dir, LoadedMeta& out) {
+    read_index_bin(index_dir, out);
+    const uint64_t n1 = out.nlist;
     const size_t vsz = (size_t)out.dim * 4, pad = (8 - vsz % 8) % 8;
     out.list_len.assign(n1, 0);
     out.list_file_shard.assign(n1, 0);

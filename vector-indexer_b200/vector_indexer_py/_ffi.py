@@ -91,6 +91,10 @@ _SIGS = {
     "vidx_calculate_max_iterations": (u64, [u64]),
     "vidx_save": (i32, [vp, C.c_char_p, C.c_char_p]),
     "vidx_load": (i32, [vp, C.c_char_p, C.c_char_p]),
+    "vidx_stdrng_draw": (i32, [u64, u64, i32, u64, u64, u64p]),
+    "vidx_stdrng_weighted": (i32, [u64, f32p, u64, u64, u64p]),
+    "vidx_index_bin_write": (i32, [C.c_char_p, f32p, u64p, u64, u32]),
+    "vidx_index_bin_read": (i32, [C.c_char_p, u64, f32p, u64p, u64p, u32p]),
     "vidx_set_coarse_mode": (i32, [vp, i32]),
     "vidx_set_partition": (i32, [vp, i32, i32]),
     "vidx_set_partition_mode": (i32, [vp, i32]),
@@ -393,6 +397,37 @@ def read_vector_file(path, dim):
     meta = np.zeros(n.value, np.uint64)
     check(lib().vidx_vector_file_read(os.fsencode(path), dim, n.value, _f(data), _u(ids), _u(meta), C.byref(n)))
     return ids, data, meta
+
+
+def stdrng_draw(seed, kind, n, arg=0, skip_u32=0):
+    """The build's random stream (csrc/rng.hpp), host only.  kind: "u32", "u64", "gen_range", "shuffle", "choose_multiple"."""
+    out = np.zeros(max(n, 1), np.uint64)
+    check(lib().vidx_stdrng_draw(seed, skip_u32, ["u32", "u64", "gen_range", "shuffle", "choose_multiple"].index(kind), arg, n, _u(out)))
+    return out[:n]
+
+
+def stdrng_weighted(seed, weights, n):
+    w = _c32(weights)
+    out = np.zeros(max(n, 1), np.uint64)
+    check(lib().vidx_stdrng_weighted(seed, _f(w), len(w), n, _u(out)))
+    return out[:n]
+
+
+def index_bin_write(index_dir, centroids, centroids_to_shard):
+    """index.bin as IvfIndex::save_to writes it (src/ivf_index.rs:274-294); host only."""
+    c = _c32(centroids)
+    s = np.ascontiguousarray(centroids_to_shard, dtype=np.uint64)
+    check(lib().vidx_index_bin_write(os.fsencode(index_dir), _f(c), _u(s), c.shape[0], c.shape[1]))
+
+
+def index_bin_read(index_dir):
+    """-> (centroids f32[nlist, dim], centroids_to_shard i64[nlist]) as load_index_from reads them; host only."""
+    n, d = u64(0), u32(0)
+    check(lib().vidx_index_bin_read(os.fsencode(index_dir), 0, None, None, C.byref(n), C.byref(d)))
+    c = np.zeros((n.value, d.value), np.float32)
+    s = np.zeros(n.value, np.uint64)
+    check(lib().vidx_index_bin_read(os.fsencode(index_dir), n.value, _f(c), _u(s), C.byref(n), C.byref(d)))
+    return c, s.astype(np.int64)
 
 
 def comm_unique_id():
