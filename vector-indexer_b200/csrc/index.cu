@@ -330,9 +330,11 @@ void Index::finish_store(const float* d_data) {
         tc_ok = std::isfinite(vmax) && std::isfinite(vn_max) && tc_sv > -40 && tc_sv < 40;
         d_vecs16.reserve(tc_ok ? (std::max<uint64_t>(nrows, 1) * Dh * 16) : 16);
         d_vnorm.reserve((std::max<uint64_t>(nrows, 1) + 128) * 16);  // rows are whole supergroups: a tile copy reads 128 entries
-        if (tc_ok)
+        if (tc_ok) {
             launch_convert16(d_vecs.as<float4>(), Dq, Dh, d_row_src.as<uint32_t>(), nrows, d_vntrue.as<float>(), tc_sv, tc_g,
                              d_vecs16.as<uint4>(), d_vnorm.as<uint4>(), stream);
+            make_shadow_tensor_map(&shadow_tmap, d_vecs16.p, std::max<uint64_t>(nrows, 1), Dh);
+        }
         VIDX_CUDA(cudaStreamSynchronize(stream));
     }
     upload_partition();
@@ -432,6 +434,14 @@ void Index::upload_partition() {
         if (b > a) nseg_owned.push_back(b - a);
         // global row - local row, the same for every resident row of the list
         if (res_seg[l].y > res_seg[l].x) rowdelta[l] = (segs[res_seg[l].x].g0 - res_g0[l]) * (uint32_t)kGroup;
+    }
+    {
+        double wt = 0.0, wl = 0.0;  // size-biased mean of the owned tiles per list
+        for (uint64_t l = 0; l < nlist; l++) {
+            wt += (double)list_len[l] * (double)((ng[l] + 3) / 4);
+            wl += (double)list_len[l];
+        }
+        mean_probe_tiles = wl > 0 ? wt / wl : 0.0;
     }
     // prefix of the largest per-list tile counts: bounds the dump of a query (dump mode of the tensor-core scan)
     {
@@ -554,6 +564,10 @@ struct CtxLease {
 };
 
 constexpr uint64_t kCoarseTcMinLists = 1ull << 20;  // auto mode: measured slower than the exact FP32 stage up to nlist = 12 639
+constexpr bool kTcPairDefault = false;
+constexpr double kTcPairMinQueriesPerList = 256.0;  // mean queries per list from which the pair kernel is used
+constexpr uint64_t kSmallBatchQueries = 512;
+constexpr double kBoundsPassMaxUnitsPerSm = 256.0;  // ~0.15 ms of tensor work per pass
 constexpr uint64_t kBoundsPassMaxTiles = 2048;  // auto mode: bounds pass first when a query probes at most this many 128-vector tiles
 // list scan, seeded flavour: a bounds pass over the heads of each query's (up to) kSeedRanks nearest lists,
 // kSeedBoundTiles tiles per query in all, gives every query a bound before the main pass starts
@@ -613,10 +627,10 @@ void Index::coarse_tc(SearchCtx& ctx, const float4* xq4, uint32_t nqb, uint32_t 
     exclusive_scan_u32(w.list_cnt.as<uint32_t>(), w.list_qoff.as<uint32_t>(), 1, w.scan_tmp.as<uint32_t>(), st);
     launch_tc_fill(w.probes0.as<uint32_t>(), nqb, 1, false, lseg, w.list_qoff.as<uint32_t>(), w.list_cur.as<uint32_t>(), w.list_qlist.as<uint2>(), st);
     launch_tc_items(w.list_cnt.as<uint32_t>(), ctab.list_ng.as<uint32_t>(), 1, reinterpret_cast<unsigned long long*>(counters + 12), 0, counters + 10,
-                    w.items_per_list.as<uint32_t>(), st);
+                    w.items_per_list.as<uint32_t>(), false, st);
     exclusive_scan_u32(w.items_per_list.as<uint32_t>(), w.item_off.as<uint32_t>(), 1, w.scan_tmp.as<uint32_t>(), st);
     launch_tc_expand(w.list_cnt.as<uint32_t>(), ctab.list_ng.as<uint32_t>(), ctab.list_g0.as<uint32_t>(), w.list_qoff.as<uint32_t>(),
-                     w.item_off.as<uint32_t>(), counters + 10, 1, 0, w.items.as<TcItem>(), st);
+                     w.item_off.as<uint32_t>(), counters + 10, 1, 0, w.items.as<TcItem>(), false, st);
     // bounds pass over the whole table (it is short: nlist / 128 tiles per query): minima of every 32 centroids; the n_probe
     // smallest of a query's minima bound its n_probe-th nearest centroid, and the main pass only collects what is within it
     const uint32_t ntiles = (ncgroups + kTcTileGroups - 1) / kTcTileGroups;
@@ -710,10 +724,33 @@ void Index::search_device(SearchCtx& ctx, const float* d_xq, uint64_t nq, uint64
     // the minimum of every 32 columns, then the main pass with final bounds.  With many tile visits per query (a few
     // giant lists) the doubled tensor-core work costs more than the survivors it saves: seeding pass + main pass.
     // scan_mode 2 / 3 force the seeded / the two-pass flavour.
-    const uint32_t seed_ranks = std::max<uint32_t>(1, std::min<uint32_t>(np, kSeedRanks)), seed_rank_tiles = kSeedBoundTiles / seed_ranks;
+    // Small batches (a handful of 128-query tiles): every CTA works on the same few rows, so (a) the rows' k-smallest sets
+    // stay CTA-local in the main pass -- merging them under the per-query locks at every item end serialised the whole
+    // GPU (0.80 -> 0.13 ms for the 128-query bench batch) -- and (b) the bounds launch looks at 8x more tiles per query,
+    // which costs little with so few rows and keeps the survivor count down without the shared sets.
+    const bool small_batch = nq <= kSmallBatchQueries;
+    const uint32_t seed_ranks = std::max<uint32_t>(1, std::min<uint32_t>(np, kSeedRanks));
+    const uint32_t seed_rank_tiles = (small_batch ? 8u * kSeedBoundTiles : kSeedBoundTiles) / seed_ranks;
     const uint32_t seed_row = seed_ranks * seed_rank_tiles * 4;  // minima per query of the seeding bounds pass
     const uint64_t dump_tiles_per_q = tile_prefix[std::min<size_t>(np, tile_prefix.size() - 1)];
-    const bool tc_dump = tc && scan_mode != 2 && dump_tiles_per_q > 0 && (scan_mode == 3 || dump_tiles_per_q <= kBoundsPassMaxTiles);
+    // tuning knobs for A/B runs on the GPU box (environment, read per search; unset = the defaults the bench is quoted on)
+    const uint32_t tc_flags = [&] { const char* v = getenv("VIDX_TC_FLAGS"); return v && *v ? (uint32_t)strtoul(v, nullptr, 0) : (small_batch ? 1u : 0u); }();
+    const uint64_t bounds_pass_max_tiles = [] { const char* v = getenv("VIDX_BOUNDS_MAX_TILES"); return v && *v ? (uint64_t)strtoull(v, nullptr, 0) : kBoundsPassMaxTiles; }();
+    // The bounds-pass-first flavour runs the tensor work twice: worth it only while one pass is short -- few tiles per
+    // query AND few (query tile x list tile) units per SM.  (A quarter of the bench index is 1560 tiles per query but 800
+    // units per SM: two passes took 1.27 ms where the seeded flavour takes 0.77.)
+    // tiles a query is expected to visit: n_probe lists drawn in proportion to their size (a query falls into a list about
+    // as often as a vector does), never more than the n_probe largest lists
+    const double est_tiles_per_q = std::min((double)dump_tiles_per_q, (double)np * mean_probe_tiles);
+    const double pass_units = (double)std::min<uint64_t>(nq, 65535ull * 64) * est_tiles_per_q / 128.0;
+    const bool tc_dump = tc && scan_mode != 2 && dump_tiles_per_q > 0 &&
+                         (scan_mode == 3 || (dump_tiles_per_q <= bounds_pass_max_tiles && pass_units <= kBoundsPassMaxUnitsPerSm * device_num_sms()));
+    // CTA-pair kernel (cta_group::2) for the main pass: pays when lists are shared by many queries (tensor-bound)
+    const bool tc_pair = [&] {
+        const char* v = getenv("VIDX_TC_PAIR");
+        if (v && *v) return atoi(v) != 0;
+        return kTcPairDefault && !small_batch && (double)nq * (double)np >= kTcPairMinQueriesPerList * (double)std::max<uint64_t>(nlist, 1);
+    }() && tc;
     const uint32_t nseg = (uint32_t)segs.size();
     const uint32_t ldc = ncgroups * kGroup;
     // pairs bound per query: the np largest per-list segment counts
@@ -856,7 +893,7 @@ void Index::search_device(SearchCtx& ctx, const float* d_xq, uint64_t nq, uint64
             launch_tc_fill(w.probes.as<uint32_t>(), npairs, np, false, d_list_seg.as<uint2>(), w.list_qoff.as<uint32_t>(),
                            w.list_cur.as<uint32_t>(), w.list_qlist.as<uint2>(), st);
             launch_tc_items(w.list_cnt.as<uint32_t>(), d_list_ng.as<uint32_t>(), (uint32_t)nlist,
-                            reinterpret_cast<unsigned long long*>(counters + 12), 0, counters + 10, w.items_per_list.as<uint32_t>(), st);
+                            reinterpret_cast<unsigned long long*>(counters + 12), 0, counters + 10, w.items_per_list.as<uint32_t>(), tc_pair, st);
             exclusive_scan_u32(w.items_per_list.as<uint32_t>(), w.item_off.as<uint32_t>(), nlist, w.scan_tmp.as<uint32_t>(), st);
             {
                 // one 32-byte record per work item; items <= total/chunk + sum of query tiles per list, with
@@ -865,7 +902,7 @@ void Index::search_device(SearchCtx& ctx, const float* d_xq, uint64_t nq, uint64
                 const uint64_t cap_items = (nqb / 128 + 1) * tiles / 128 + 8 * 160 + npairs / 128 + 2 * nlist + 64;
                 w.items.reserve(cap_items * sizeof(TcItem));
                 launch_tc_expand(w.list_cnt.as<uint32_t>(), d_list_ng.as<uint32_t>(), d_list_g0.as<uint32_t>(), w.list_qoff.as<uint32_t>(),
-                                 w.item_off.as<uint32_t>(), counters + 10, (uint32_t)nlist, 0, w.items.as<TcItem>(), st);
+                                 w.item_off.as<uint32_t>(), counters + 10, (uint32_t)nlist, 0, w.items.as<TcItem>(), tc_pair, st);
             }
             if (tc_dump) {
                 // bounds pass: first tile of every (query, probe rank) pair in submin, and each query's row of it
@@ -895,11 +932,11 @@ void Index::search_device(SearchCtx& ctx, const float* d_xq, uint64_t nq, uint64
             launch_tc_fill(w.probes.as<uint32_t>(), npairs, np, seed_ranks, d_list_seg.as<uint2>(), w.list_qoff0.as<uint32_t>(),
                            w.list_cur0.as<uint32_t>(), w.list_qlist0.as<uint2>(), st);
             launch_tc_items(w.list_cnt0.as<uint32_t>(), d_list_ng.as<uint32_t>(), (uint32_t)nlist, nullptr, seed_rank_tiles, counters + 11,
-                            w.items_per_list0.as<uint32_t>(), st);
+                            w.items_per_list0.as<uint32_t>(), false, st);
             exclusive_scan_u32(w.items_per_list0.as<uint32_t>(), w.item_off0.as<uint32_t>(), nlist, w.scan_tmp.as<uint32_t>(), st);
-            w.items0.reserve(((uint64_t)nqb * seed_ranks / 32 + 2 * nlist + 64) * sizeof(TcItem));
+            w.items0.reserve((((uint64_t)nqb * seed_ranks / 32 + 2 * nlist) * ceil_div(seed_rank_tiles, 16) + 64) * sizeof(TcItem));
             launch_tc_expand(w.list_cnt0.as<uint32_t>(), d_list_ng.as<uint32_t>(), d_list_g0.as<uint32_t>(), w.list_qoff0.as<uint32_t>(),
-                             w.item_off0.as<uint32_t>(), counters + 11, (uint32_t)nlist, seed_rank_tiles, w.items0.as<TcItem>(), st);
+                             w.item_off0.as<uint32_t>(), counters + 11, (uint32_t)nlist, seed_rank_tiles, w.items0.as<TcItem>(), false, st);
             // the seeding pass's minima: one fixed-length row per query, +inf where a list has fewer tiles
             w.dump.reserve(std::max<uint64_t>((uint64_t)nqb * seed_row, 1) * 4);
             w.sel_pos.reserve((size_t)nqb * k * 4);
@@ -941,6 +978,7 @@ void Index::search_device(SearchCtx& ctx, const float* d_xq, uint64_t nq, uint64
                 // pass 1: seed every query's bound from the head of its nearest list (minima only, no survivors: the main
                 // pass sees those vectors again)
                 tp.mode = 2;
+                tp.pair = 0;  // (its work items are 128-row ones)
                 tp.list_cnt = w.list_cnt0.as<uint32_t>();
                 tp.list_qoff = w.list_qoff0.as<uint32_t>();
                 tp.list_qlist = w.list_qlist0.as<uint2>();
@@ -958,6 +996,8 @@ void Index::search_device(SearchCtx& ctx, const float* d_xq, uint64_t nq, uint64
             tp.list_qlist = w.list_qlist.as<uint2>();
             tp.item_off = w.item_off.as<uint32_t>();
             tp.items = w.items.as<TcItem>();
+            tp.pair = tc_pair ? 1u : 0u;  // both passes of the two-pass flavour run over the same work items
+            if (tc_pair) tp.tmap = shadow_tmap;
             if (tc_dump) {
                 // pass 1: the minima of every (query, probed tile); their k-th smallest is the query's final bound
                 tp.mode = 2;
@@ -970,6 +1010,9 @@ void Index::search_device(SearchCtx& ctx, const float* d_xq, uint64_t nq, uint64
             // pass 2: everything else, starting from warm bounds (after a bounds pass: from final ones)
             tp.mode = 0;
             tp.frozen = tc_dump ? 1 : 0;
+            tp.flags = tc_flags;
+            tp.pair = tc_pair ? 1u : 0u;
+            if (tc_pair) tp.tmap = shadow_tmap;
             tp.noinsert_tiles = tc_dump ? 0 : seed_rank_tiles;
             tp.work_counter = counters + 8;
 #ifdef VIDX_TC_TIMING
@@ -1063,6 +1106,7 @@ void Index::search_device(SearchCtx& ctx, const float* d_xq, uint64_t nq, uint64
             fp.D = d_D + q0 * kout;
             fp.I = d_I + q0 * kout;
             fp.out_rows = rows_out;
+            fp.wpq = small_batch ? 8u : 1u;
             fp.out_keys = keys_out;
             fp.probes = w.probes.as<uint32_t>();
             fp.list_rowdelta = d_list_rowdelta.as<uint32_t>();

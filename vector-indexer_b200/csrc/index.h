@@ -61,6 +61,7 @@ struct Index {
     std::vector<uint2> list_seg_part;     // per list (first segment, end segment), global ids; empty if not owned
     std::vector<uint64_t> seg_prefix;     // prefix sums of per-list segment counts, largest first
     std::vector<uint64_t> tile_prefix;    // prefix sums of per-list 128-vector tile counts (owned part), largest first
+    double mean_probe_tiles = 0.0;        // owned tiles of the list a random vector belongs to (what a probe is expected to cost)
 
     // device store
     cudaStream_t stream = nullptr;        // build / load / save stream
@@ -70,6 +71,7 @@ struct Index {
     float vmax = 0.0f;     // max |component| over the stored rows
     int tc_sv = 0, tc_g = 0;  // fp16 shadow store: vectors scaled by 2^sv, norm terms by 2^(2sv-g)
     bool tc_ok = false;    // the shadow store exists (finite data of sane magnitude)
+    CUtensorMap shadow_tmap{};  // the shadow store as a tiled-TMA tensor (CTA-pair scan kernel)
     // The centroid table as a one-list index of its own: coarse quantization = the same tensor-core filter + exact
     // re-check, top-n_probe by (distance, list id).
     struct CoarseTable {

@@ -61,7 +61,10 @@ constexpr int kTcSeedRows = 128;     // seeding pass: queries per work item (eve
 #define VIDX_CHUNK_TILES 512
 #endif
 #ifndef VIDX_ITEMS_PER_SM
-#define VIDX_ITEMS_PER_SM 8
+#define VIDX_ITEMS_PER_SM 4
+#endif
+#ifndef VIDX_MIN_CHUNK_TILES
+#define VIDX_MIN_CHUNK_TILES 8
 #endif
 constexpr int kTcMaxChunkTiles = VIDX_CHUNK_TILES; // tiles per work item: chosen on the device, 8..512 (1024..65536 vectors); an item
                                       // costs ~8-16 us beyond its tiles (set-up, pipeline fill and drain, merge of the rows' sets):
@@ -133,6 +136,55 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Tiled TMA copy of one box of a 2-D tensor map into shared memory (coordinates innermost first).
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tmap, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+                 : "memory");
+}
+// ---- CTA pair (cluster of two CTAs on one TPC, tcgen05 cta_group::2) ------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {  // every thread of both CTAs
+    asm volatile("barrier.cluster.arrive.release;\n\tbarrier.cluster.wait.acquire;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory location in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void st_cluster_v4(uint32_t cluster_addr, uint4 v) {
+    asm volatile("st.shared::cluster.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(cluster_addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// the commit of a cta_group::2 MMA arrives on the barrier at the same offset in BOTH CTAs
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+// M = 256 (128 rows from each CTA of the pair), N = 128 (64 rows of B from each CTA), issued by one thread of the leader
+template <bool ACC>
+__device__ __forceinline__ void tc_mma_f16_pair(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "n"(ACC ? 1 : 0)
+        : "memory");
 }
 // D[tmem] (+)= A[smem] * B[smem]^T, FP16 inputs, FP32 accumulate.  The two descriptors are given as 32-bit
 // halves: only the 14-bit start-address field of the low word differs between the MMAs of a tile, so the
@@ -377,25 +429,26 @@ __global__ void tc_fill_kernel(const uint32_t* __restrict__ probes, size_t npair
 // warm bound.  The chunk length is chosen on the device from the total tile count so that a batch
 // yields several items per SM: ctl[0] = total (query tile x vector tile) count, ctl[1] = chunk tiles.
 __global__ void tc_work_kernel(const uint32_t* __restrict__ list_cnt, const uint32_t* __restrict__ list_ngroups, uint32_t nlist,
-                               unsigned long long* __restrict__ total) {
+                               uint32_t qrows, unsigned long long* __restrict__ total) {
     // (main pass only; the seeding pass has one fixed-size chunk per list)
     uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= nlist) return;
     uint32_t c = list_cnt[l];
     if (!c) return;
     uint32_t ntiles = (list_ngroups[l] + kTcTileGroups - 1) / kTcTileGroups;
-    atomicAdd(total, (unsigned long long)((c + kTcM - 1) / kTcM) * ntiles);
+    atomicAdd(total, (unsigned long long)((c + qrows - 1) / qrows) * ntiles);
 }
 __global__ void tc_items_kernel(const uint32_t* __restrict__ list_cnt, const uint32_t* __restrict__ list_ngroups, uint32_t nlist,
                                 const unsigned long long* __restrict__ total, uint32_t num_sms, uint32_t seed_tiles,
-                                uint32_t* __restrict__ chunk_out, uint32_t* __restrict__ items_per_list) {
+                                uint32_t items_per_sm, uint32_t min_chunk, uint32_t qrows_main, uint32_t* __restrict__ chunk_out,
+                                uint32_t* __restrict__ items_per_list) {
     uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t chunk;
     if (seed_tiles) {
-        chunk = seed_tiles;
+        chunk = min(seed_tiles, 16u);  // the bounds launch's items are independent: short chunks spread them over the SMs
     } else {
-        unsigned long long per = *total / ((unsigned long long)VIDX_ITEMS_PER_SM * num_sms);
-        chunk = (uint32_t)min((unsigned long long)kTcMaxChunkTiles, max(8ull, per));
+        unsigned long long per = *total / ((unsigned long long)items_per_sm * num_sms);
+        chunk = (uint32_t)min((unsigned long long)kTcMaxChunkTiles, max((unsigned long long)min_chunk, per));
     }
     if (l == 0) *chunk_out = chunk;
     if (l >= nlist) return;
@@ -403,7 +456,7 @@ __global__ void tc_items_kernel(const uint32_t* __restrict__ list_cnt, const uin
     uint32_t ntiles = (list_ngroups[l] + kTcTileGroups - 1) / kTcTileGroups;
     if (seed_tiles) ntiles = min(ntiles, seed_tiles);
     uint32_t nch = (ntiles + chunk - 1) / chunk;
-    const uint32_t qrows = seed_tiles ? (uint32_t)kTcSeedRows : (uint32_t)kTcM;
+    const uint32_t qrows = seed_tiles ? (uint32_t)kTcSeedRows : qrows_main;
     items_per_list[l] = c ? ((c + qrows - 1) / qrows) * nch : 0u;
 }
 
@@ -412,13 +465,13 @@ __global__ void tc_items_kernel(const uint32_t* __restrict__ list_cnt, const uin
 __global__ void tc_expand_kernel(const uint32_t* __restrict__ list_cnt, const uint32_t* __restrict__ list_ngroups,
                                  const uint32_t* __restrict__ list_g0, const uint32_t* __restrict__ list_qoff,
                                  const uint32_t* __restrict__ item_off, const uint32_t* __restrict__ chunk_tiles, uint32_t nlist,
-                                 uint32_t seed_tiles, TcItem* __restrict__ items) {
+                                 uint32_t seed_tiles, uint32_t qrows_main, TcItem* __restrict__ items) {
     const uint32_t l = blockIdx.x;
     if (l >= nlist) return;
     const uint32_t i0 = item_off[l], n = item_off[l + 1] - i0;
     if (!n) return;
     const uint32_t cnt = list_cnt[l], ngl = list_ngroups[l], g_list = list_g0[l], qoff = list_qoff[l], chunk = *chunk_tiles;
-    const uint32_t qrows = seed_tiles ? (uint32_t)kTcSeedRows : (uint32_t)kTcM;
+    const uint32_t qrows = seed_tiles ? (uint32_t)kTcSeedRows : qrows_main;
     const uint32_t nqt = (cnt + qrows - 1) / qrows;
     uint32_t ntiles = (ngl + kTcTileGroups - 1) / kTcTileGroups;
     if (seed_tiles) ntiles = min(ntiles, seed_tiles);
@@ -446,14 +499,17 @@ __global__ void tc_expand_kernel(const uint32_t* __restrict__ list_cnt, const ui
 // ------------------------------------------------------------------------------------------
 struct TcSmemLayout {
     uint32_t a_bytes, off_b, off_norm, off_ones, off_zero, off_r, off_queue, off_stage, off_q, off_row, off_bar, off_misc, off_item, total;
-    uint32_t stages;
+    uint32_t stages, stage_data, stage_bytes;
 };
-__host__ __device__ inline TcSmemLayout tc_smem_layout(int Dh, int kr) {
+// pair = the CTA-pair kernel: a CTA holds 64 of a tile's 128 vectors, so the same ring memory makes 8 stages instead of 4
+__host__ __device__ inline TcSmemLayout tc_smem_layout(int Dh, int kr, bool pair = false) {
     TcSmemLayout L;
-    L.stages = kTcStages;
+    L.stages = pair ? 2 * kTcStages : kTcStages;
+    L.stage_data = pair ? kTcStageData / 2 : kTcStageData;
+    L.stage_bytes = pair ? kTcStageBytes / 2 : kTcStageBytes;
     L.a_bytes = (uint32_t)Dh * kTcM * 16;                   // query tile, [chunk][128 rows][16 B = 8 halfs]
     L.off_b = L.a_bytes;                                    // ring of list-tile K-slices
-    L.off_norm = L.off_b + L.stages * kTcStageBytes;        // (end of the ring; every stage carries its own norm chunk)
+    L.off_norm = L.off_b + L.stages * L.stage_bytes;        // (end of the ring; every stage carries its own norm chunk)
     L.off_ones = L.off_norm;                                // A-side partner of the norm chunk: (a,a,a,0,..) per row
     L.off_zero = L.off_ones + 2048;                         // second K chunk of the norm step, both operands: zeros
     L.off_r = L.off_zero + 2048;                            // per query row: its k smallest filter values, descending
@@ -462,7 +518,7 @@ __host__ __device__ inline TcSmemLayout tc_smem_layout(int Dh, int kr) {
     L.off_q = L.off_stage + tc_stage_cap(kr) * 12;               // (query, probe rank) of the tile's rows
     L.off_row = L.off_q + kTcM * 8;                         // per row: bound P, delta, base, improved flag
     L.off_bar = L.off_row + 4 * kTcM * 4;
-    L.off_misc = L.off_bar + (2 * kTcStages + 2 * kTcAccStages) * 8;
+    L.off_misc = L.off_bar + (2 * 2 * kTcStages + 2 * kTcAccStages) * 8;  // (room for the pair kernel's 8 stages)
     L.off_item = L.off_misc + 64 + 512;                      // two staged work-item records
     L.total = L.off_item + 2 * 32;
     return L;
@@ -508,10 +564,18 @@ constexpr uint32_t kEntValid = 0x40000000u;
 #define TC_T0() do { } while (0)
 #define TC_ACC(slot) do { } while (0)
 #endif
-template <int KR>
-__global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
+// PAIR: two CTAs of a cluster (one TPC) share every tile -- tcgen05 cta_group::2, M = 256: each CTA keeps 128 query rows
+// and their accumulators, loads only HALF of every list tile (64 vectors) and the tensor cores of both SMs read both halves.
+// One issued instruction feeds two tensor pipes (the single-thread issue cadence, ~125 cycles per MMA, no longer bounds a
+// 64-cycle MMA) and the L2 -> SM traffic per flop halves.  Only the leader CTA issues; completion is multicast to the
+// barriers of both CTAs; the peer forwards "my half landed" and "my accumulator stage is drained" to the leader's barriers.
+template <int KR, bool PAIR>
+__global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(const __grid_constant__ TcParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    const TcSmemLayout L = tc_smem_layout(p.Dh, KR);
+    const TcSmemLayout L = tc_smem_layout(p.Dh, KR, PAIR);
+    const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
+    constexpr uint32_t kHalfRows = PAIR ? 64u : 128u;  // vectors of a tile in this CTA's shared memory
+    constexpr uint32_t kStageData = kTcStageChunks * kHalfRows * 16u, kStageBytes = kStageData + kHalfRows * 16u;
     unsigned char* sA = smem;
     unsigned char* sB = smem + L.off_b;
     constexpr int kRS = KR + 1;                                     // row stride of s_r
@@ -526,31 +590,35 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
     float* s_base = s_delta + kTcM;                                 // [128]
     uint32_t* s_impr = reinterpret_cast<uint32_t*>(s_base + kTcM);  // [128] the row's set changed during this item
     uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + L.off_bar);  // [stages] K-slice landed
-    uint64_t* bar_empty = bar_full + kTcStages;                          // [stages] K-slice consumed by the MMAs
-    uint64_t* bar_tfull = bar_empty + kTcStages;                         // [4] accumulator tile complete
+    constexpr uint32_t nstages = PAIR ? 2 * kTcStages : kTcStages, kSP = nstages / 2;  // stages in all / per tile pipeline
+    uint64_t* bar_empty = bar_full + nstages;                            // [stages] K-slice consumed by the MMAs
+    uint64_t* bar_tfull = bar_empty + nstages;                           // [4] accumulator tile complete
     uint64_t* bar_tempty = bar_tfull + kTcAccStages;                     // [4] accumulator tile drained
     uint32_t* s_misc = reinterpret_cast<uint32_t*>(smem + L.off_misc);   // [0] tmem base [1] item [2] queue tail [3] queue head [4] done
     volatile float* s_tmpv_all = reinterpret_cast<volatile float*>(s_misc + 16);  // [4][32] selector scratch
     // s_misc: [0] tmem base, [4] epilogue warps done, [8 + 2*sel] queue tail, [9 + 2*sel] queue head (sel < 4)
-    constexpr uint32_t nstages = kTcStages;
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(kFull, tid >> 5, 0);  // warp-uniform for the compiler too
     const int Dq = p.Dq, Dh = p.Dh;
     // the batch's scales (uniform loads); a batch that cannot be scaled into fp16 range goes to the exact kernels
     const float tS = p.scale->S, tInvS = p.scale->invS, tQmul = p.scale->qmul, tCabs = p.scale->c_abs;
+    // flags bit 0: the rows' k-smallest sets stay CTA-local -- gtop (written by the bounds pass) is read-only in the main
+    // pass, no seqlock / lock traffic at item boundaries; CTAs still share their bounds through gthr (atomicMin)
+    const bool local_sets = (p.flags & 1u) != 0;
     if (!p.scale->ok) {
         for (uint32_t q = blockIdx.x * kTcThreads + tid; q < p.nq; q += gridDim.x * kTcThreads) p.overflow[q] = 1u;
         return;
     }
     if (tid == 0) {
         for (uint32_t i = 0; i < nstages; i++) {
-            mbar_init(&bar_full[i], 1);
+            mbar_init(&bar_full[i], PAIR && cta_rank == 0 ? 2 : 1);  // leader of a pair: its own copies + the peer's "landed"
             mbar_init(&bar_empty[i], 1);
         }
         for (int i = 0; i < kTcAccStages; i++) {
             mbar_init(&bar_tfull[i], 1);
-            mbar_init(&bar_tempty[i], kTcEpiWarps / 2);  // the four warps of the epilogue group that owns the tile
+            // the four warps of the epilogue group that owns the tile (pair: of both CTAs, all on the leader's barrier)
+            mbar_init(&bar_tempty[i], PAIR ? kTcEpiWarps : kTcEpiWarps / 2);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -562,16 +630,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
     }
     for (int i = tid; i < kTcSelectors * kTcQueueCap; i += kTcThreads) s_queue_all[i] = make_uint2(0u, 0u);
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_misc[0])), "r"(kTcTmemCols)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (PAIR) {  // collective over the pair: one warp of each CTA
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_misc[0])), "r"(kTcTmemCols)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_misc[0])), "r"(kTcTmemCols)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all();  // the peer's barriers are initialised before anything arrives on them
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = s_misc[0];
     const uint32_t total_items = p.item_off[p.nlist];
-    const uint32_t idesc = make_idesc_f16(kTcM, kTcTileGroups * 32);
+    const uint32_t idesc = make_idesc_f16(PAIR ? 2 * kTcM : kTcM, kTcTileGroups * 32);
     const int nkc = (Dh + kTcStageChunks - 1) / kTcStageChunks;  // K-slices per tile
     const float kInf = __int_as_float(0x7f800000);
     uint32_t it = 0;     // tiles processed so far by this CTA (accumulator stage = it & 3, phase = (it >> 2) & 1)
@@ -584,14 +659,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
     // Work items are claimed one ahead: while item i runs, the selector warp (idle during an item's set-up) claims
     // item i+1 and stages its record in shared memory.
     TcItem* s_item = reinterpret_cast<TcItem*>(smem + L.off_item);  // [2]
-    auto claim = [&](int slot) {  // one thread
+    auto claim = [&](int slot) {  // one thread (of the leader CTA: both CTAs of a pair work on the same item)
         const uint32_t idx = atomicAdd(p.work_counter, 1u);
         TcItem r;
         if (idx < total_items) r = p.items[idx];
         else r.valid = 0u;
         s_item[slot] = r;
+        if (PAIR) {
+            const uint32_t peer = mapa_u32(smem_u32(&s_item[slot]), 1u);
+            st_cluster_v4(peer, make_uint4(r.t0, r.t1, r.qbase, r.nq_tile));
+            st_cluster_v4(peer + 16u, make_uint4(r.g_list, r.ngl, r.valid, 0u));
+        }
     };
-    if (tid == 0) claim(0);
+    if (tid == 0 && cta_rank == 0) claim(0);
     uint32_t cur = 0;
 #ifdef VIDX_TC_TIMING
     const long long _tk0 = clock64();
@@ -600,7 +680,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
 #ifdef VIDX_TC_TIMING
         const long long _ti0 = clock64();
 #endif
-        __syncthreads();  // the record of this item is staged; every warp is done with the previous item
+        // the record of this item is staged (pair: in both CTAs); every warp is done with the previous item
+        if (PAIR) cluster_sync_all();
+        else __syncthreads();
 #ifdef VIDX_TC_TIMING
         if (tid == 64 && p.dbg) atomicAdd(&p.dbg[16 * blockIdx.x + 9], (unsigned long long)(clock64() - _ti0));  // warp 2: drain wait
 #endif
@@ -623,7 +705,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
             const int row = tid - 32;  // warps 1-4 own the 128 query rows during set-up
             uint2 qi = make_uint2(kNoRow, 0);
             if (row >= 0 && row < kTcM) {
-                if (row < (int)nq_tile) qi = p.list_qlist[qbase + row];
+                const uint32_t irow = cta_rank * kTcM + (uint32_t)row;  // row of the work item (pair: 256 rows, 128 per CTA)
+                if (irow < nq_tile) qi = p.list_qlist[qbase + irow];
                 s_q[row] = qi;
             }
             asm volatile("bar.sync 2, %0;" ::"n"(kSetupThreads) : "memory");
@@ -646,6 +729,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
                     // seqlock read: writers make the version odd while they update the set
                     const volatile uint32_t* ver = p.gver + q;
                     float r0 = kInf;
+                    if (local_sets) {
+                        for (int i = 0; i < KR; i++) {
+                            float v = i < (int)p.k ? __ldcg(&p.gtop[(size_t)q * p.k + i]) : -kInf;
+                            rr[i] = v;
+                            if (i == 0) r0 = v;
+                        }
+                    } else
                     for (;;) {
                         uint32_t v1 = *ver;
                         if (v1 & 1u) { __nanosleep(32); continue; }
@@ -716,17 +806,28 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
             const uint4* nsrc = p.vnorm + ((size_t)g_list + (size_t)t0 * kTcTileGroups) * 32;
             for (uint32_t t = t0; t < t1; t++, nsrc += kSuper) {
                 const uint32_t pipe = (it + (t - t0)) & 1u;
+                const uint32_t blk0 = ((g_list >> 2) + t) * (uint32_t)Dh;  // first 2 KB chunk block of the tile in the shadow store
                 for (int kc = 0; kc < nkc; kc++) {
                     const uint32_t cnt = pipe ? ks_it1++ : ks_it++;
                     const uint32_t nch = (uint32_t)min(kTcStageChunks, Dh - kc * kTcStageChunks);
-                    const uint32_t bytes = nch * kSuper * 16;
-                    const uint32_t s = 2 * pipe + (cnt & 1u), ph = (cnt >> 1) & 1;
+                    const uint32_t bytes = nch * kSuper * 16;  // of the whole 128-vector K-slice in HBM
+                    const uint32_t s = kSP * pipe + (cnt & (kSP - 1u)), ph = (cnt / kSP) & 1;
                     { TC_T0(); mbar_wait(&bar_empty[s], ph ^ 1); TC_ACC(0 + pipe); }
                     const bool last = kc == nkc - 1;
                     if (elect_one()) {
-                        mbar_expect_tx(&bar_full[s], bytes + (last ? 2048u : 0u));
-                        bulk_g2s(sB + s * kTcStageBytes, src, bytes, &bar_full[s]);
-                        if (last) bulk_g2s(sB + s * kTcStageBytes + kTcStageData, nsrc, 2048, &bar_full[s]);
+                        if (PAIR) {
+                            // this CTA's 64 vectors of every 16-byte chunk -- 1 KB out of each 2 KB chunk block -- as ONE tiled
+                            // copy: the shadow store seen as [chunk blocks][2 KB], box = 16 blocks x 1 KB (sixteen 1 KB bulk copies
+                            // per K-slice made the producer the slowest role).  The box always has 16 rows: a short last slice
+                            // pulls in chunks of the next tile, which no MMA reads.
+                            mbar_expect_tx(&bar_full[s], kStageData + (last ? 1024u : 0u));
+                            tma_load_2d(sB + s * kStageBytes, &p.tmap, (int)(cta_rank * 128u), (int)(blk0 + (uint32_t)kc * kTcStageChunks), &bar_full[s]);
+                            if (last) bulk_g2s(sB + s * kStageBytes + kStageData, nsrc + cta_rank * 64u, 1024u, &bar_full[s]);
+                        } else {
+                            mbar_expect_tx(&bar_full[s], bytes + (last ? 2048u : 0u));
+                            bulk_g2s(sB + s * kStageBytes, src, bytes, &bar_full[s]);
+                            if (last) bulk_g2s(sB + s * kStageBytes + kStageData, nsrc, 2048, &bar_full[s]);
+                        }
                     }
                     __syncwarp();
                     src += bytes;
@@ -738,12 +839,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
             // (one thread each; the loop is kept to a few dozen instructions per K-slice because a single
             // thread's issue latency, not the tensor pipe, would otherwise bound the kernel) =====
             const uint32_t pipe = warp == 9 ? 0u : 1u;
-            {
+            if (PAIR && cta_rank != 0) {
+                // the peer CTA issues nothing: this warp tells the leader when this CTA's half of a K-slice has landed
+                const uint32_t skip = (pipe ^ it) & 1u;
+                for (uint32_t itt = it + skip; itt < it + (t1 - t0); itt += 2) {
+                    for (int kc = 0; kc < nkc; kc++, ks_it++) {
+                        const uint32_t s = kSP * pipe + (ks_it & (kSP - 1u)), ph = (ks_it / kSP) & 1;
+                        mbar_wait(&bar_full[s], ph);
+                        if (elect_one()) mbar_arrive_cluster(mapa_u32(smem_u32(&bar_full[s]), 0u));
+                        __syncwarp();
+                    }
+                }
+                it += t1 - t0;
+            } else {
                 // descriptor = lo | hi << 32; lo = start address >> 4 (14 bits) | LBO >> 4 << 16, hi = SBO >> 4 | version 1 << 14
                 const uint32_t desc_hi = (128u >> 4) | (1u << 14);
                 const uint32_t lbo_bits = (2048u >> 4) << 16;
                 const uint32_t a_lo0 = ((smem_u32(sA) >> 4) & 0x3fffu) | lbo_bits;
-                const uint32_t b_lo0 = ((smem_u32(sB) >> 4) & 0x3fffu) | lbo_bits;
+                // B: [chunk][rows in this CTA][16 B] -- consecutive K chunks are kHalfRows * 16 bytes apart
+                const uint32_t b_lo0 = ((smem_u32(sB) >> 4) & 0x3fffu) | (((kHalfRows * 16u) >> 4) << 16);
                 // norm step: K chunk 0 = (1,1,1,0) x (n_hi, n_mid, n_lo, 0), K chunk 1 = the shared zero block
                 const uint32_t ones_lo = ((smem_u32(smem + L.off_ones) >> 4) & 0x3fffu) | (((L.off_zero - L.off_ones) >> 4) << 16);
                 const uint32_t skip = (pipe ^ it) & 1u;  // first tile of this item that belongs to this pipeline
@@ -752,24 +866,37 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
                     { TC_T0(); mbar_wait(&bar_tempty[a], aph ^ 1); TC_ACC(4 + pipe); }
                     const uint32_t d_tmem = tmem_base + a * 128;
                     for (int kc = 0; kc < nkc; kc++, ks_it++) {
-                        const uint32_t s = 2 * pipe + (ks_it & 1u), ph = (ks_it >> 1) & 1;
+                        const uint32_t s = kSP * pipe + (ks_it & (kSP - 1u)), ph = (ks_it / kSP) & 1;
                         { TC_T0(); mbar_wait(&bar_full[s], ph); TC_ACC(6 + pipe); }
                         tc_fence_after();
-                        // chunk c of all 128 rows is one 2 KB block (128 x 16 B) in both tiles: +128 per chunk in >>4 units
+                        // chunk c of all 128 rows is one 2 KB block (128 x 16 B) in the query tile: +128 per chunk in >>4 units;
+                        // a K step (two chunks) of the list tile is 2 * kHalfRows * 16 bytes
                         const uint32_t al = a_lo0 + (uint32_t)kc * (kTcStageChunks * 128);
-                        const uint32_t bl = b_lo0 + s * (kTcStageBytes >> 4);
+                        const uint32_t bl = b_lo0 + s * (kStageBytes >> 4);
+                        constexpr uint32_t kBStep = (2u * kHalfRows * 16u) >> 4;
                         const int nks = min(kTcStageChunks / 2, (Dh >> 1) - kc * (kTcStageChunks / 2));
-                        const uint32_t noff = L.off_b + s * kTcStageBytes + kTcStageData;
+                        const uint32_t noff = L.off_b + s * kStageBytes + kStageData;
                         const uint32_t norm_lo = ((smem_u32(smem + noff) >> 4) & 0x3fffu) | (((L.off_zero - noff) >> 4) << 16);
                         if (elect_one()) {
-                            if (kc == 0) tc_mma_f16_lo<false>(d_tmem, al, bl, desc_hi, idesc);
-                            else tc_mma_f16_lo<true>(d_tmem, al, bl, desc_hi, idesc);
+                            if (PAIR) {
+                                if (kc == 0) tc_mma_f16_pair<false>(d_tmem, al, bl, desc_hi, idesc);
+                                else tc_mma_f16_pair<true>(d_tmem, al, bl, desc_hi, idesc);
 #pragma unroll
-                            for (int ks = 1; ks < kTcStageChunks / 2; ks++)
-                                if (ks < nks) tc_mma_f16_lo<true>(d_tmem, al + ks * 256, bl + ks * 256, desc_hi, idesc);
-                            if (kc == nkc - 1) tc_mma_f16_lo<true>(d_tmem, ones_lo, norm_lo, desc_hi, idesc);
-                            tc_commit(&bar_empty[s]);                       // K-slice free once these MMAs have read it
-                            if (kc == nkc - 1) tc_commit(&bar_tfull[a]);    // accumulator tile ready for the epilogue
+                                for (int ks = 1; ks < kTcStageChunks / 2; ks++)
+                                    if (ks < nks) tc_mma_f16_pair<true>(d_tmem, al + ks * 256, bl + ks * kBStep, desc_hi, idesc);
+                                if (kc == nkc - 1) tc_mma_f16_pair<true>(d_tmem, ones_lo, norm_lo, desc_hi, idesc);
+                                tc_commit_pair(&bar_empty[s]);                       // both CTAs' halves of the K-slice are free
+                                if (kc == nkc - 1) tc_commit_pair(&bar_tfull[a]);    // both CTAs' accumulator tiles are ready
+                            } else {
+                                if (kc == 0) tc_mma_f16_lo<false>(d_tmem, al, bl, desc_hi, idesc);
+                                else tc_mma_f16_lo<true>(d_tmem, al, bl, desc_hi, idesc);
+#pragma unroll
+                                for (int ks = 1; ks < kTcStageChunks / 2; ks++)
+                                    if (ks < nks) tc_mma_f16_lo<true>(d_tmem, al + ks * 256, bl + ks * kBStep, desc_hi, idesc);
+                                if (kc == nkc - 1) tc_mma_f16_lo<true>(d_tmem, ones_lo, norm_lo, desc_hi, idesc);
+                                tc_commit(&bar_empty[s]);                       // K-slice free once these MMAs have read it
+                                if (kc == nkc - 1) tc_commit(&bar_tfull[a]);    // accumulator tile ready for the epilogue
+                            }
                         }
                         __syncwarp();
                     }
@@ -785,7 +912,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
             uint32_t* q_tail = &s_misc[8 + 2 * sel];
             uint32_t* q_head = &s_misc[9 + 2 * sel];
             // ===== selector: the only writer of the rows' bounds and top-k sets =====
-            if (lane == 0 && sel == 0) claim((int)(cur ^ 1u));  // the next work item, one ahead
+            if (lane == 0 && sel == 0 && cta_rank == 0) claim((int)(cur ^ 1u));  // the next work item, one ahead
             __syncwarp();
             const uint32_t row0_item = (g_list + t0 * kTcTileGroups) * 32u;
             volatile float* vP = s_P;
@@ -1026,7 +1153,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&bar_tempty[s]);
+                if (lane == 0) {
+                    if (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(&bar_tempty[s]), 0u));  // the issuer lives in the leader CTA
+                    else mbar_arrive(&bar_tempty[s]);
+                }
             }
             it += t1 - t0;
             __syncwarp();
@@ -1037,7 +1167,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
             asm volatile("bar.sync 1, %0;" ::"n"((kTcEpiWarps + kTcSelectors) * 32) : "memory");
             // merge this item's k smallest into the shared set (distinct values only: a value both sides
             // already hold must not be counted twice; dropping a legitimately equal value only loosens the bound)
-            if (p.mode != 2 && valid && grp == 0 && s_impr[row]) {
+            if (p.mode != 2 && valid && grp == 0 && s_impr[row] && !local_sets) {
               const uint32_t q = qi.x;
               const float base_t = s_base[row];
               float r[KR];
@@ -1101,12 +1231,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(TcParams p) {
         }
     }
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all();  // neither CTA frees tensor memory (or exits) while the other may still use the pair's
+    else __syncthreads();
 #ifdef VIDX_TC_TIMING
     if (tid == 0 && p.dbg) p.dbg[16 * blockIdx.x + 13] += (unsigned long long)(clock64() - _tk0);
 #endif
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTcTmemCols) : "memory");
+        if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTcTmemCols) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTcTmemCols) : "memory");
     }
 }
 
@@ -1173,8 +1305,15 @@ __device__ __forceinline__ float exact_row_distance(const float4* __restrict__ v
     return a;
 }
 
-__global__ void finalize_kernel(FinalizeParams p) {
-    uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+// One warp per query, or -- small batches, where a lone warp's chain of gathers is the run time -- the eight warps of a
+// block share a query: each takes every eighth batch of survivors / slots and keeps its own top-k, warp 0 merges the eight
+// lists.  (distance, key) is a strict total order, so the result does not depend on the split.
+constexpr int kFinWarps = 8;
+__global__ void __launch_bounds__(kFinWarps * 32) finalize_kernel(FinalizeParams p) {
+    const uint32_t wib = threadIdx.x >> 5;  // warp in block
+    const uint32_t wpq = p.wpq;             // warps per query: 1 or kFinWarps
+    const uint32_t q = wpq == 1 ? blockIdx.x * kFinWarps + wib : blockIdx.x;
+    const uint32_t sub = wpq == 1 ? 0u : wib;
     int lane = threadIdx.x & 31;
     if (q >= p.nq) return;
     const uint32_t k = p.k;
@@ -1193,8 +1332,8 @@ __global__ void finalize_kernel(FinalizeParams p) {
             // Survivors were collected under bounds that kept shrinking: most of the early ones lie above the query's final
             // bound.  Their filter values (lower bounds of the distance) are compared with it first, and the rest is
             // compacted through shared memory so that the distance gathers run on full batches.
-            __shared__ unsigned long long s_keep[4][64];
-            unsigned long long* keep = s_keep[(threadIdx.x >> 5) & 3];
+            __shared__ unsigned long long s_keep[kFinWarps][64];
+            unsigned long long* keep = s_keep[wib];
             const bool filt = !brute && p.cand_val != nullptr;
             float U = __int_as_float(0x7f800000), base_t = 0.0f, invS = 0.0f;
             if (filt) {
@@ -1203,7 +1342,8 @@ __global__ void finalize_kernel(FinalizeParams p) {
                 invS = p.scale->invS;
             }
             uint32_t pend = 0;
-            for (uint32_t base0 = 0; base0 < n || pend; base0 += 32) {
+            const uint32_t step = 32u * wpq;
+            for (uint32_t base0 = 32u * sub; base0 < n || pend; base0 += step) {
                 unsigned long long key = ~0ull;
                 bool have = false;
                 if (filt) {
@@ -1218,7 +1358,7 @@ __global__ void finalize_kernel(FinalizeParams p) {
                     if (kp) keep[pend + __popc(km & ((1u << lane) - 1u))] = kk0;
                     pend += __popc(km);
                     __syncwarp();
-                    if (pend < 32 && base0 + 32 < n) continue;  // gather more before paying for a batch of distances
+                    if (pend < 32 && base0 + step < n) continue;  // gather more before paying for a batch of distances
                     const uint32_t take = min(pend, 32u);
                     have = (uint32_t)lane < take;
                     if (have) key = keep[lane];
@@ -1251,7 +1391,7 @@ __global__ void finalize_kernel(FinalizeParams p) {
     // (2) slots of the exact scan kernels (sorted by (distance, row); slot order = (probe rank, segment))
     if (p.slot_off) {
         uint32_t s0 = p.slot_off[(size_t)q * p.nprobe], s1 = p.slot_off[(size_t)(q + 1) * p.nprobe];
-        for (uint32_t s = s0; s < s1; s++) {
+        for (uint32_t s = s0 + sub; s < s1; s += wpq) {
             float d = __int_as_float(0x7f800000);
             uint32_t r = kNoRow;
             if (lane < (int)k) {
@@ -1262,6 +1402,30 @@ __global__ void finalize_kernel(FinalizeParams p) {
             float td = __shfl_sync(kFull, fd, k - 1);
             unsigned long long tk = __shfl_sync(kFull, fk, k - 1);
             unsigned m = __ballot_sync(kFull, r != kNoRow && lex_less(d, key, td, tk));
+            while (m) {
+                int src = __ffs(m) - 1;
+                m &= m - 1;
+                float cd = __shfl_sync(kFull, d, src);
+                unsigned long long ck = __shfl_sync(kFull, key, src);
+                td = __shfl_sync(kFull, fd, k - 1);
+                tk = __shfl_sync(kFull, fk, k - 1);
+                if (lex_less(cd, ck, td, tk)) warp_insert_lex64(cd, ck, fd, fk, lane);
+            }
+        }
+    }
+    if (wpq > 1) {
+        __shared__ float s_md[kFinWarps][32];
+        __shared__ unsigned long long s_mk[kFinWarps][32];
+        s_md[wib][lane] = fd;
+        s_mk[wib][lane] = fk;
+        __syncthreads();  // (all warps of the block belong to query q: nobody returned early)
+        if (wib != 0) return;
+        for (uint32_t w = 1; w < wpq; w++) {
+            const float d = s_md[w][lane];
+            const unsigned long long key = s_mk[w][lane];
+            float td = __shfl_sync(kFull, fd, k - 1);
+            unsigned long long tk = __shfl_sync(kFull, fk, k - 1);
+            unsigned m = __ballot_sync(kFull, lane < (int)k && key != ~0ull && lex_less(d, key, td, tk));
             while (m) {
                 int src = __ffs(m) - 1;
                 m &= m - 1;
@@ -1332,38 +1496,101 @@ void launch_tc_fill(const uint32_t* probes, size_t npairs, uint32_t nprobe, uint
     VIDX_LAUNCHED();
 }
 static int tc_num_sms() { return device_num_sms(); }
+// tuning knobs for A/B runs on the GPU box (environment, read per launch; unset = the defaults the bench line is quoted on)
+static long tc_env(const char* name, long dflt) {
+    const char* v = getenv(name);
+    return v && *v ? strtol(v, nullptr, 0) : dflt;
+}
 void launch_tc_items(const uint32_t* list_cnt, const uint32_t* list_ngroups, uint32_t nlist, unsigned long long* total,
-                     uint32_t seed_tiles, uint32_t* chunk_out, uint32_t* items_per_list, cudaStream_t st) {
+                     uint32_t seed_tiles, uint32_t* chunk_out, uint32_t* items_per_list, bool pair, cudaStream_t st) {
     if (!nlist) return;
+    const uint32_t qrows = pair ? 2u * kTcM : (uint32_t)kTcM;  // rows of a work item of the main pass
     if (!seed_tiles) {
-        tc_work_kernel<<<(unsigned)ceil_div(nlist, 256), 256, 0, st>>>(list_cnt, list_ngroups, nlist, total);
+        tc_work_kernel<<<(unsigned)ceil_div(nlist, 256), 256, 0, st>>>(list_cnt, list_ngroups, nlist, qrows, total);
         VIDX_LAUNCHED();
     }
-    tc_items_kernel<<<(unsigned)ceil_div(nlist, 256), 256, 0, st>>>(list_cnt, list_ngroups, nlist, total, (uint32_t)tc_num_sms(),
-                                                                   seed_tiles, chunk_out, items_per_list);
+    // work-item sizing: an item costs ~6 us of set-up and drain beyond its tiles (0.55 us each), so a batch is cut into
+    // about items_per_sm items per SM but never into chunks of fewer than min_chunk tiles
+    const uint32_t items_per_sm = (uint32_t)tc_env("VIDX_ITEMS_PER_SM", VIDX_ITEMS_PER_SM);
+    const uint32_t min_chunk = (uint32_t)tc_env("VIDX_MIN_CHUNK_TILES", VIDX_MIN_CHUNK_TILES);
+    tc_items_kernel<<<(unsigned)ceil_div(nlist, 256), 256, 0, st>>>(list_cnt, list_ngroups, nlist, total,
+                                                                   (uint32_t)(pair ? tc_num_sms() / 2 : tc_num_sms()), seed_tiles,
+                                                                   std::max(1u, items_per_sm), std::max(1u, min_chunk), qrows, chunk_out,
+                                                                   items_per_list);
     VIDX_LAUNCHED();
 }
 void launch_tc_expand(const uint32_t* list_cnt, const uint32_t* list_ngroups, const uint32_t* list_g0, const uint32_t* list_qoff,
                       const uint32_t* item_off, const uint32_t* chunk_tiles, uint32_t nlist, uint32_t seed_tiles, TcItem* items,
-                      cudaStream_t st) {
+                      bool pair, cudaStream_t st) {
     if (!nlist) return;
-    tc_expand_kernel<<<nlist, 64, 0, st>>>(list_cnt, list_ngroups, list_g0, list_qoff, item_off, chunk_tiles, nlist, seed_tiles, items);
+    tc_expand_kernel<<<nlist, 64, 0, st>>>(list_cnt, list_ngroups, list_g0, list_qoff, item_off, chunk_tiles, nlist, seed_tiles,
+                                           pair ? 2u * kTcM : (uint32_t)kTcM, items);
     VIDX_LAUNCHED();
 }
-template <int KR>
+template <int KR, bool PAIR>
 static void launch_scan_tc_kr(const TcParams& p, size_t smem, cudaStream_t st) {
     static PerDeviceSize attr;  // the opt-in is per device
     if (attr.needs(smem)) {
-        VIDX_CUDA(cudaFuncSetAttribute(scan_tc_kernel<KR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        VIDX_CUDA(cudaFuncSetAttribute(scan_tc_kernel<KR, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr.set(smem);
     }
-    scan_tc_kernel<KR><<<tc_num_sms(), kTcThreads, smem, st>>>(p);
+    if (PAIR) {
+        // clusters of two CTAs: the pair lands on the two SMs of one TPC, which is what tcgen05 cta_group::2 needs
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)(tc_num_sms() / 2) * 2);
+        cfg.blockDim = dim3(kTcThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        VIDX_CUDA(cudaLaunchKernelEx(&cfg, scan_tc_kernel<KR, PAIR>, p));
+    } else {
+        scan_tc_kernel<KR, PAIR><<<tc_num_sms(), kTcThreads, smem, st>>>(p);
+    }
     VIDX_LAUNCHED();
 }
 void launch_scan_tc(const TcParams& p, cudaStream_t st) {
-    if (p.k <= 8) launch_scan_tc_kr<8>(p, tc_smem_layout(p.Dh, 8).total, st);
-    else if (p.k <= 16) launch_scan_tc_kr<16>(p, tc_smem_layout(p.Dh, 16).total, st);
-    else launch_scan_tc_kr<32>(p, tc_smem_layout(p.Dh, 32).total, st);
+    const bool pair = p.pair != 0;
+    const int kr = p.k <= 8 ? 8 : (p.k <= 16 ? 16 : 32);
+    const size_t smem = tc_smem_layout(p.Dh, kr, pair).total;
+    if (pair) {
+        if (kr == 8) launch_scan_tc_kr<8, true>(p, smem, st);
+        else if (kr == 16) launch_scan_tc_kr<16, true>(p, smem, st);
+        else launch_scan_tc_kr<32, true>(p, smem, st);
+    } else {
+        if (kr == 8) launch_scan_tc_kr<8, false>(p, smem, st);
+        else if (kr == 16) launch_scan_tc_kr<16, false>(p, smem, st);
+        else launch_scan_tc_kr<32, false>(p, smem, st);
+    }
+}
+// The fp16 shadow store as a 2-D tensor of 8-byte elements: dim 0 = one 2 KB chunk block (256 elements: one 16-byte chunk of
+// 128 vectors), dim 1 = chunk blocks (Dh per 128-vector tile, tiles consecutive).  Box = 128 elements x 16 blocks: the 64
+// vectors of one CTA of a pair, 16 chunks deep, landing as [chunk][64 vectors][16 B] -- the tcgen05 K-major operand layout.
+void make_shadow_tensor_map(CUtensorMap* out, const void* vecs16, uint64_t nrows, int Dh) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        VIDX_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) throw ApiError(6, "cuTensorMapEncodeTiled is not available in this driver");
+        encode = reinterpret_cast<EncodeFn>(fn);
+    }
+    const uint64_t nblocks = std::max<uint64_t>(1, (nrows + kSuper - 1) / kSuper) * (uint64_t)Dh;
+    const cuuint64_t gdim[2] = {256, nblocks};
+    const cuuint64_t gstride[1] = {(cuuint64_t)kSuper * 16};
+    const cuuint32_t box[2] = {128, (cuuint32_t)kTcStageChunks};
+    const cuuint32_t estride[2] = {1, 1};
+    const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, const_cast<void*>(vecs16), gdim, gstride, box, estride,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw ApiError(6, "cuTensorMapEncodeTiled failed for the fp16 shadow store");
 }
 void launch_pair_tiles(const uint32_t* probes, size_t npairs, const uint32_t* list_ngroups, uint32_t* pair_tiles, cudaStream_t st) {
     if (!npairs) return;
@@ -1382,7 +1609,9 @@ void launch_bounds_apply(const float* sel_val, uint32_t nq, uint32_t k, float* g
 }
 void launch_finalize(const FinalizeParams& p, cudaStream_t st) {
     if (!p.nq) return;
-    finalize_kernel<<<(unsigned)ceil_div((size_t)p.nq * 32, 128), 128, 0, st>>>(p);
+    FinalizeParams q = p;
+    if (q.wpq != (uint32_t)kFinWarps) q.wpq = 1;
+    finalize_kernel<<<q.wpq == 1 ? (unsigned)ceil_div((size_t)q.nq, kFinWarps) : q.nq, kFinWarps * 32, 0, st>>>(q);
     VIDX_LAUNCHED();
 }
 

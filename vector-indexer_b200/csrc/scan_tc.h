@@ -1,5 +1,7 @@
 // scan_tc.h -- tensor-core list scan (tcgen05 FP16 pre-filter + exact finalize).
 #pragma once
+#include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
+
 #include "common.cuh"
 
 namespace vidx {
@@ -21,13 +23,14 @@ struct TcScale {
 struct TcItem {      // one work item: query tile x list chunk (32 bytes)
     uint32_t t0, t1;     // tile range within the list
     uint32_t qbase;      // first entry of the item's rows in list_qlist
-    uint32_t nq_tile;    // rows in use
+    uint32_t nq_tile;    // rows in use (<= 128; <= 256 for the CTA-pair kernel)
     uint32_t g_list;     // first group of the list (this rank's part)
     uint32_t ngl;        // groups of the list (this rank's part)
     uint32_t valid, pad;
 };
 
 struct TcParams {
+    CUtensorMap tmap;              // CTA-pair kernel only: the shadow store as [chunk blocks][2 KB] (make_shadow_tensor_map)
     const uint4* vecs16;           // fp16 shadow store: [supergroup][Dh chunks][128 vectors][8 halfs], scaled by 2^sv
     const uint4* vnorm;            // per row 8 halfs: the three fp16 terms of (1-eps)|v|^2 * 2^(2sv-g), then zeros; NaN for padding rows
     int Dh;                        // 16-byte chunks (8 halfs) per vector in the shadow store; even
@@ -65,6 +68,8 @@ struct TcParams {
     uint32_t seed_ranks, noinsert_tiles;  // seeding bounds pass: the first noinsert_tiles tiles of each query's seed_ranks nearest lists;
                                    // main pass after it: their values are survivors but never enter the row's set
     uint32_t frozen;               // main pass after a bounds pass: the bounds are final, survivors are only collected
+    uint32_t pair;                 // 1 = the CTA-pair kernel (cta_group::2): work items of 256 query rows, clusters of two CTAs
+    uint32_t flags;                // bit 0: keep the rows' sets CTA-local in the main pass (no cross-CTA merge at item ends)
 };
 
 struct FinalizeParams {
@@ -83,6 +88,7 @@ struct FinalizeParams {
     const uint32_t* gthr_bits;
     const float* qnorm;
     const TcScale* scale;
+    uint32_t wpq;         // warps per query: 8 = a block per query (small batches), anything else = one warp per query
     uint32_t brute_rows;  // != 0: a query flagged in `overflow` is answered by checking rows 0..brute_rows-1 exactly (one-list tables)
     // exact-path slots (slot_off == nullptr: none)
     const uint32_t* slot_off;
@@ -117,11 +123,12 @@ void launch_tc_count(const uint32_t* probes, size_t npairs, uint32_t nprobe, uin
 void launch_tc_fill(const uint32_t* probes, size_t npairs, uint32_t nprobe, uint32_t max_rank, const uint2* list_seg,
                     const uint32_t* list_qoff, uint32_t* list_cur, uint2* list_qlist, cudaStream_t st);
 void launch_tc_items(const uint32_t* list_cnt, const uint32_t* list_ngroups, uint32_t nlist, unsigned long long* total,
-                     uint32_t seed_tiles, uint32_t* chunk_out, uint32_t* items_per_list, cudaStream_t st);
+                     uint32_t seed_tiles, uint32_t* chunk_out, uint32_t* items_per_list, bool pair, cudaStream_t st);
 void launch_tc_expand(const uint32_t* list_cnt, const uint32_t* list_ngroups, const uint32_t* list_g0, const uint32_t* list_qoff,
                       const uint32_t* item_off, const uint32_t* chunk_tiles, uint32_t nlist, uint32_t seed_tiles, TcItem* items,
-                      cudaStream_t st);
+                      bool pair, cudaStream_t st);
 void launch_scan_tc(const TcParams& p, cudaStream_t st);
+void make_shadow_tensor_map(CUtensorMap* out, const void* vecs16, uint64_t nrows, int Dh);
 void launch_pair_tiles(const uint32_t* probes, size_t npairs, const uint32_t* list_ngroups, uint32_t* pair_tiles, cudaStream_t st);
 void launch_submin_rows(const uint32_t* pair_off, uint32_t nprobe, uint32_t nq, uint64_t* row_off, uint32_t* row_len, cudaStream_t st);
 void launch_bounds_apply(const float* sel_val, uint32_t nq, uint32_t k, float* gtop, cudaStream_t st);

@@ -453,9 +453,20 @@ select_small_kernel(const float* __restrict__ vals, const uint64_t* __restrict__
         }
         first = 32;
     }
-    for (uint32_t base = first; base < n; base += 32) {
+    // four loads in flight per lane: with few rows (small batches) one warp's chain of dependent loads is the run time
+    for (uint32_t base4 = first; base4 < n; base4 += 128) {
+      float v4[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+          const uint32_t i = base4 + 32u * u + lane;
+          v4[u] = i < n ? row[i] : kInf;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const uint32_t base = base4 + 32u * u;
+        if (base >= n) break;
         const uint32_t i = base + lane;
-        const float v = i < n ? row[i] : kInf;
+        const float v = v4[u];
         float kd = __shfl_sync(kFull, my_d, (int)k - 1);
         uint32_t kp = __shfl_sync(kFull, my_p, (int)k - 1);
         unsigned m = __ballot_sync(kFull, v < kInf && less(v, i, kd, kp));
@@ -477,6 +488,7 @@ select_small_kernel(const float* __restrict__ vals, const uint64_t* __restrict__
                 my_p = up_p;
             }
         }
+      }
     }
     if (lane < (int)k) {
         if (out_pos) out_pos[r * k + lane] = my_p;
