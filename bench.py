@@ -398,6 +398,8 @@ class Searcher:
     def staged(self, nq_used, nprobe, reps=5):
         """Per-stage CUDA-event times (instrumented passes, not the timed ones), averaged."""
         self.ix.set_profiling(True)
+        self.search_dev(nprobe, nq_used)  # untimed: buffers of a stage that has not run yet on this handle get allocated here
+        self.H.torch.cuda.synchronize()
         acc = None
         for _ in range(reps):
             self.search_dev(nprobe, nq_used)

@@ -279,9 +279,10 @@ int vidx_set_profiling(vidx_index* idx, int enabled);
  * 1 = exact FP32 kernels only; 2 / 3 = force the first / the second flavour of the filter (the second whenever its minima fit
  * in 8 GB).  Results are bit-identical in every mode. */
 int vidx_set_scan_mode(vidx_index* idx, int mode);
-/* Coarse quantization (ivf_index.rs:205-220): 0 = auto (today: the exact FP32 kernels -- the tensor-core filter measured
- * no faster up to nlist = 12 639), 1 = exact kernels only, 2 = tensor-core filter + exact re-check whenever
- * it applies (n_probe <= 32).  Probe lists and distances are identical in every mode. */
+/* Coarse quantization (ivf_index.rs:205-220): 0 = auto (the tensor-core filter + exact re-check when n_probe <= 32, the table has
+ * >= 1024 lists and the batch >= 4M (query, centroid) pairs -- measured faster from there, 12x at nlist = 65 536; else the exact
+ * FP32 kernels), 1 = exact kernels only, 2 = the filter whenever it applies (n_probe <= 32).  Probe lists and distances are
+ * identical in every mode. */
 int vidx_set_coarse_mode(vidx_index* idx, int mode);
 int vidx_get_search_stats(vidx_index* idx, vidx_search_stats* out);
 /* Total kernels launched by this library in this process (bench.py's gpu_launches). */

@@ -66,6 +66,29 @@ def test_search_tensor_core_pipeline_shapes(oracle, ffi, d, k):
     check_search(oix, gix, xq, k, 2)
 
 
+@pytest.mark.parametrize("d,k,tc", [(320, 10, True), (384, 32, True), (512, 10, True), (768, 10, False), (1536, 5, False)])
+def test_search_large_dimensions(oracle, ffi, d, k, tc):
+    """The reference's own grids and tests use D = 512, 768, 1536 (bench.yaml:1-15, shards_tests.rs:239-270,
+    ivf_index_tests.rs:661-686).  Up to D = 512 the query tile still fits in shared memory next to a two-stage ring and the
+    scan runs on the tensor cores; beyond that the exact FP32 kernels answer.  Same bits either way."""
+    xb, xq = bench_data(12000, d, 700, seed=d)
+    oix, gix = make_pair(oracle, ffi, xb, 10)
+    gix.set_profiling(True)
+    check_search(oix, gix, xq, k, 3)
+    assert (gix.stats()["n_tc_items"] > 0) == tc
+    gix.set_profiling(False)
+
+
+@pytest.mark.parametrize("flag", ["1"])
+def test_cta_pair_kernel_is_bit_exact(oracle, ffi, flag, monkeypatch):
+    """The experimental CTA-pair scan (tcgen05 cta_group::2, VIDX_TC_PAIR=1): same answers as the oracle."""
+    monkeypatch.setenv("VIDX_TC_PAIR", flag)
+    for d, k, nq in ((64, 10, 900), (128, 17, 1500), (200, 32, 700), (384, 10, 600)):
+        xb, xq = bench_data(20000, d, nq, seed=d + 1)
+        oix, gix = make_pair(oracle, ffi, xb, 12)
+        check_search(oix, gix, xq, k, 3)
+
+
 @pytest.mark.parametrize("d", [1, 3, 30, 129, 200])
 def test_search_odd_dimensions(oracle, ffi, d):
     xb, xq = bench_data(3000, d, 150, seed=d)

@@ -563,7 +563,12 @@ struct CtxLease {
     ~CtxLease() { ix.release_ctx(c, st); }
 };
 
-constexpr uint64_t kCoarseTcMinLists = 1ull << 20;  // auto mode: measured slower than the exact FP32 stage up to nlist = 12 639
+// auto mode: the tensor-core filter when the table has at least kCoarseTcMinLists lists and the batch at least
+// kCoarseTcMinPairs (query, centroid) pairs (below that its ~15 launches cost more than the two of the exact stage).
+// Measured (CUDA events, nq = 10 000, warm): nlist = 1024 (D = 128, n_probe 8) exact 0.19 ms vs filter 0.155;
+// nlist = 12 639 (D = 128, n_probe 32) 2.00 vs 1.94; nlist = 65 280 (D = 96, n_probe 32) 8.71 vs 0.71 ms.
+constexpr uint64_t kCoarseTcMinLists = 1024;
+constexpr double kCoarseTcMinPairs = 4.0e6;
 constexpr bool kTcPairDefault = false;
 constexpr double kTcPairMinQueriesPerList = 256.0;  // mean queries per list from which the pair kernel is used
 constexpr uint64_t kSmallBatchQueries = 512;
@@ -806,7 +811,7 @@ void Index::search_device(SearchCtx& ctx, const float* d_xq, uint64_t nq, uint64
             pd = w.sel_val.as<float>();
         }
         const bool coarse_filter = coarse_mode != 1 && scan_mode != 1 && ctab.ok && np <= 32 && tc_supported((int)dim, np) &&
-                                   (coarse_mode == 2 || nlist >= kCoarseTcMinLists);
+                                   (coarse_mode == 2 || (nlist >= kCoarseTcMinLists && (double)nqb * (double)nlist >= kCoarseTcMinPairs));
         if (d_probes_in) {
             // probe lists computed elsewhere (multi-GPU: every rank ranks the centroids for a slice of the batch and the
             // slices are all-gathered): row stride np

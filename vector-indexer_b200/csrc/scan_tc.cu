@@ -502,9 +502,9 @@ struct TcSmemLayout {
     uint32_t stages, stage_data, stage_bytes;
 };
 // pair = the CTA-pair kernel: a CTA holds 64 of a tile's 128 vectors, so the same ring memory makes 8 stages instead of 4
-__host__ __device__ inline TcSmemLayout tc_smem_layout(int Dh, int kr, bool pair = false) {
+__host__ __device__ inline TcSmemLayout tc_smem_layout_n(int Dh, int kr, bool pair, uint32_t stages) {
     TcSmemLayout L;
-    L.stages = pair ? 2 * kTcStages : kTcStages;
+    L.stages = stages;
     L.stage_data = pair ? kTcStageData / 2 : kTcStageData;
     L.stage_bytes = pair ? kTcStageBytes / 2 : kTcStageBytes;
     L.a_bytes = (uint32_t)Dh * kTcM * 16;                   // query tile, [chunk][128 rows][16 B = 8 halfs]
@@ -521,6 +521,19 @@ __host__ __device__ inline TcSmemLayout tc_smem_layout(int Dh, int kr, bool pair
     L.off_misc = L.off_bar + (2 * 2 * kTcStages + 2 * kTcAccStages) * 8;  // (room for the pair kernel's 8 stages)
     L.off_item = L.off_misc + 64 + 512;                      // two staged work-item records
     L.total = L.off_item + 2 * 32;
+    return L;
+}
+// The whole query tile stays in shared memory for the life of a work item (every list tile is multiplied with it), so the ring
+// gets what is left: four 34 KB stages up to D = 256, two (one per tile pipeline) up to D = 512.  pair = the CTA-pair kernel:
+// a CTA holds 64 of a tile's 128 vectors, so the same ring memory makes twice the stages.
+constexpr uint32_t kTcSmemMax = 227 * 1024;
+__host__ __device__ inline TcSmemLayout tc_smem_layout(int Dh, int kr, bool pair = false) {
+    uint32_t stages = pair ? 2 * kTcStages : kTcStages;
+    TcSmemLayout L = tc_smem_layout_n(Dh, kr, pair, stages);
+    while (L.total > kTcSmemMax && stages > 2) {
+        stages >>= 1;
+        L = tc_smem_layout_n(Dh, kr, pair, stages);
+    }
     return L;
 }
 
@@ -590,9 +603,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(const __grid_con
     float* s_base = s_delta + kTcM;                                 // [128]
     uint32_t* s_impr = reinterpret_cast<uint32_t*>(s_base + kTcM);  // [128] the row's set changed during this item
     uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + L.off_bar);  // [stages] K-slice landed
-    constexpr uint32_t nstages = PAIR ? 2 * kTcStages : kTcStages, kSP = nstages / 2;  // stages in all / per tile pipeline
-    uint64_t* bar_empty = bar_full + nstages;                            // [stages] K-slice consumed by the MMAs
-    uint64_t* bar_tfull = bar_empty + nstages;                           // [4] accumulator tile complete
+    const uint32_t nstages = L.stages, kSP = nstages / 2;                // stages in all / per tile pipeline (1, 2 or 4)
+    const uint32_t kSPs = kSP == 4 ? 2u : (kSP == 2 ? 1u : 0u);          // log2
+    constexpr uint32_t kMaxStages = 2 * kTcStages;
+    uint64_t* bar_empty = bar_full + kMaxStages;                         // [stages] K-slice consumed by the MMAs
+    uint64_t* bar_tfull = bar_empty + kMaxStages;                        // [4] accumulator tile complete
     uint64_t* bar_tempty = bar_tfull + kTcAccStages;                     // [4] accumulator tile drained
     uint32_t* s_misc = reinterpret_cast<uint32_t*>(smem + L.off_misc);   // [0] tmem base [1] item [2] queue tail [3] queue head [4] done
     volatile float* s_tmpv_all = reinterpret_cast<volatile float*>(s_misc + 16);  // [4][32] selector scratch
@@ -811,7 +826,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(const __grid_con
                     const uint32_t cnt = pipe ? ks_it1++ : ks_it++;
                     const uint32_t nch = (uint32_t)min(kTcStageChunks, Dh - kc * kTcStageChunks);
                     const uint32_t bytes = nch * kSuper * 16;  // of the whole 128-vector K-slice in HBM
-                    const uint32_t s = kSP * pipe + (cnt & (kSP - 1u)), ph = (cnt / kSP) & 1;
+                    const uint32_t s = kSP * pipe + (cnt & (kSP - 1u)), ph = (cnt >> kSPs) & 1;
                     { TC_T0(); mbar_wait(&bar_empty[s], ph ^ 1); TC_ACC(0 + pipe); }
                     const bool last = kc == nkc - 1;
                     if (elect_one()) {
@@ -844,7 +859,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(const __grid_con
                 const uint32_t skip = (pipe ^ it) & 1u;
                 for (uint32_t itt = it + skip; itt < it + (t1 - t0); itt += 2) {
                     for (int kc = 0; kc < nkc; kc++, ks_it++) {
-                        const uint32_t s = kSP * pipe + (ks_it & (kSP - 1u)), ph = (ks_it / kSP) & 1;
+                        const uint32_t s = kSP * pipe + (ks_it & (kSP - 1u)), ph = (ks_it >> kSPs) & 1;
                         mbar_wait(&bar_full[s], ph);
                         if (elect_one()) mbar_arrive_cluster(mapa_u32(smem_u32(&bar_full[s]), 0u));
                         __syncwarp();
@@ -866,7 +881,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(const __grid_con
                     { TC_T0(); mbar_wait(&bar_tempty[a], aph ^ 1); TC_ACC(4 + pipe); }
                     const uint32_t d_tmem = tmem_base + a * 128;
                     for (int kc = 0; kc < nkc; kc++, ks_it++) {
-                        const uint32_t s = kSP * pipe + (ks_it & (kSP - 1u)), ph = (ks_it / kSP) & 1;
+                        const uint32_t s = kSP * pipe + (ks_it & (kSP - 1u)), ph = (ks_it >> kSPs) & 1;
                         { TC_T0(); mbar_wait(&bar_full[s], ph); TC_ACC(6 + pipe); }
                         tc_fence_after();
                         // chunk c of all 128 rows is one 2 KB block (128 x 16 B) in the query tile: +128 per chunk in >>4 units;
@@ -1457,7 +1472,7 @@ __global__ void __launch_bounds__(kFinWarps * 32) finalize_kernel(FinalizeParams
 // ====================================================================================
 bool tc_supported(int D, uint32_t k) {
     if (k == 0 || k > 32 || D < 1) return false;
-    return tc_smem_layout(tc_dh(D), k <= 8 ? 8 : (k <= 16 ? 16 : 32)).total <= 227 * 1024;
+    return tc_smem_layout(tc_dh(D), k <= 8 ? 8 : (k <= 16 ? 16 : 32)).total <= kTcSmemMax;
 }
 void launch_row_norms(const float4* vecs, int Dq, const uint32_t* row_src, size_t nrows, float* vn_true, uint32_t* stats,
                       cudaStream_t st) {
