@@ -413,6 +413,9 @@ class Searcher:
 def recall_sweep(S, gt, gt_rows, full_curve, forced):
     """Smallest n_probe of {1, 2, 4, ...} with recall@10 >= 0.9 against the independent ground truth (rows gt_rows of the batch)."""
     curve, nprobe, p = [], None, 1
+    if forced and not full_curve:  # a config that fixes n_probe (BASELINE configs[3], [4]): measure the recall there only
+        S.search_dev(min(forced, S.ix.nlist))
+        return forced, [{"nprobe": forced, "recall_at_10": recall_at_k(S.result_ids()[gt_rows], gt)}]
     while True:
         p = min(p, S.ix.nlist)
         S.search_dev(p)

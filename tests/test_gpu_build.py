@@ -182,3 +182,22 @@ def test_faiss_style_adapter_sweep():
         prev = r[10]
     index.nprobe = 10 ** 6
     assert recall_at_ranks(index.search(xq, 10)[1], gt, ranks=(1,))[1] == 1.0
+
+
+def test_reference_harness_sweep_and_result_files(tmp_path):
+    """bench_all_ivf.py's methodology end to end (eval_setting + n_probe sweep + result files, :283-363, :427-480, :514-533)
+    through vector_indexer_py.bench_harness: keys and table columns of the reference's own result files."""
+    import json
+    from vector_indexer_py import bench_harness as H
+    res = H.main(["--n", "20000", "--d", "32", "--nq", "200", "--k", "100", "--nprobes", "1,4,16,283", "--min_test_duration", "0.05",
+                  "--output-dir", str(tmp_path)])
+    assert res["backend"] == "vector_indexer" and res["nlist"] == 284 and set(res["search_results"]) == {f"nprobe={p}" for p in (1, 4, 16, 283)}
+    rows = [res["search_results"][f"nprobe={p}"] for p in (1, 4, 16, 283)]
+    for r in rows:
+        assert set(r) == {"ms_per_query", "qps", "nrun", "recalls"} and set(r["recalls"]) == {1, 10, 100} and r["nrun"] >= 1
+    r100 = [r["recalls"][100] for r in rows]
+    assert r100 == sorted(r100) and rows[-1]["recalls"][1] == 1.0   # every list probed: the true neighbour is rank 1
+    saved = json.load(open(tmp_path / "faiss_bench_results.json"))
+    assert saved[0]["search_results"]["nprobe=4"]["recalls"]["10"] == rows[1]["recalls"][10]
+    md = open(tmp_path / "faiss_bench_results.md").read()
+    assert "| nprobe | R@1 | R@10 | R@100 | ms/query | QPS |" in md and md.count("\n| ") == 4
