@@ -1,0 +1,23 @@
+"""Timing ablations of scan_tc_kernel on the bench workload (answers are wrong by construction): VIDX_TC_FLAGS bit 1 = the
+epilogue drains nothing, bit 2 = no MMAs are issued.  Tells which role bounds the tile rate."""
+import os, sys
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), '..', 'vector-indexer_b200'))
+import numpy as np, torch
+from vector_indexer_py import _ffi
+n, d, nq, k = 1_000_000, 128, 10_000, 10
+rng = np.random.default_rng(42)
+xb = rng.standard_normal((n, d)).astype(np.float32); xq = rng.standard_normal((nq, d)).astype(np.float32)
+ix = _ffi.Index(d, 0).build(xb, seed=42, nlist=1024)
+ts = torch.cuda.Stream(); torch.cuda.set_stream(ts)
+d_xq = torch.from_numpy(xq).cuda(); d_D = torch.empty((nq, k), device='cuda'); d_I = torch.empty((nq, k), dtype=torch.int64, device='cuda')
+for pair in (0, 1):
+    for fl in (0, 2, 4, 6):
+        os.environ["VIDX_TC_PAIR"] = str(pair); os.environ["VIDX_TC_FLAGS"] = str(fl)
+        ix.set_profiling(True)
+        acc = 0
+        for it in range(5):
+            ix.search_device(d_xq.data_ptr(), nq, k, 8, d_D.data_ptr(), d_I.data_ptr(), ts.cuda_stream); torch.cuda.synchronize()
+            if it >= 2: acc += ix.stats()['ms_scan_tc'] / 3
+        ix.set_profiling(False)
+        print(f"pair={pair} flags={fl} ({'full' if fl == 0 else 'no epilogue' if fl == 2 else 'no MMA' if fl == 4 else 'neither'}): scan_tc {acc:.4f} ms", flush=True)
+os._exit(0)

@@ -893,6 +893,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(const __grid_con
                         const uint32_t noff = L.off_b + s * kStageBytes + kStageData;
                         const uint32_t norm_lo = ((smem_u32(smem + noff) >> 4) & 0x3fffu) | (((L.off_zero - noff) >> 4) << 16);
                         if (elect_one()) {
+                            if (p.flags & 4u) {  // ablation (timing only): no tensor work, the ring just turns over
+                                if (PAIR) { tc_commit_pair(&bar_empty[s]); if (kc == nkc - 1) tc_commit_pair(&bar_tfull[a]); }
+                                else { tc_commit(&bar_empty[s]); if (kc == nkc - 1) tc_commit(&bar_tfull[a]); }
+                            } else
                             if (PAIR) {
                                 if (kc == 0) tc_mma_f16_pair<false>(d_tmem, al, bl, desc_hi, idesc);
                                 else tc_mma_f16_pair<true>(d_tmem, al, bl, desc_hi, idesc);
@@ -1097,6 +1101,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(const __grid_con
                 const uint32_t ng = min((uint32_t)kTcTileGroups, ngl - t * kTcTileGroups);
                 const bool active = valid;
                 P = fminf(P, Pnew);
+                if (p.flags & 2u) {  // ablation (timing only, wrong answers): the epilogue drains nothing
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(&bar_tempty[s]), 0u));
+                        else mbar_arrive(&bar_tempty[s]);
+                    }
+                    continue;
+                }
 #pragma unroll
                 for (uint32_t half = 0; half < 2; half++) {
                     float acc[64];

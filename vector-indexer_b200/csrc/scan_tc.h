@@ -69,7 +69,8 @@ struct TcParams {
                                    // main pass after it: their values are survivors but never enter the row's set
     uint32_t frozen;               // main pass after a bounds pass: the bounds are final, survivors are only collected
     uint32_t pair;                 // 1 = the CTA-pair kernel (cta_group::2): work items of 256 query rows, clusters of two CTAs
-    uint32_t flags;                // bit 0: keep the rows' sets CTA-local in the main pass (no cross-CTA merge at item ends)
+    uint32_t flags;                // bit 0: keep the rows' sets CTA-local in the main pass (no cross-CTA merge at item ends);
+                                   // bits 1, 2: timing ablations (VIDX_TC_FLAGS, wrong answers): epilogue / MMAs do nothing
 };
 
 struct FinalizeParams {
