@@ -161,6 +161,12 @@ int vidx_assign_points(int device, const float* data, uint64_t n, uint64_t dim, 
 int vidx_kmeans_pp_init(int device, const float* data, uint64_t n, uint64_t dim, uint64_t k, uint64_t seed,
                         float* out_centroids);
 
+/* Where the k-means calls of this host thread spent their wall time since the previous call of this function:
+ * out[0] = seconds in the serial random stream the reference's semantics keep on the host (a Fisher-Yates shuffle of all n
+ * indices per mini-batch iteration, src/kmeans.rs:722-726; a sequential prefix sum per k-means++ draw, :285-287),
+ * out[1] = seconds blocked on the device. */
+int vidx_kmeans_last_profile(double* out /* 2 */);
+
 /* calculate_num_clusters / calculate_max_iterations                        src/utils.rs:9-26
  * (= suggest_nlist, bindings/python/src/lib.rs:308-315) */
 uint64_t vidx_calculate_num_clusters(uint64_t num_vectors);

@@ -1695,6 +1695,19 @@ int vidx_kmeans_pp_init(int device, const float* data, uint64_t n, uint64_t dim,
     });
 }
 
+// Wall-time split of the k-means work done by this host thread since the previous call of this function (build, train,
+// the vidx_kmeans_* entry points): out[0] = seconds in the reference's serial random stream on the host (Fisher-Yates over all
+// n indices per mini-batch iteration, kmeans.rs:722-726; one sequential prefix sum per k-means++ draw, :285-287), out[1] =
+// seconds blocked on the device (kernels + copies).  The rest of a call's wall time is host bookkeeping and copies in.
+int vidx_kmeans_last_profile(double* out) {
+    return guarded([&] {
+        require(out != nullptr, VIDX_ERR_INVALID_INPUT, "out is NULL");
+        out[0] = t_km_profile.host_rng_s;
+        out[1] = t_km_profile.device_wait_s;
+        t_km_profile = KmProfile{};
+    });
+}
+
 // utils.rs:9-16
 uint64_t vidx_calculate_num_clusters(uint64_t n) {
     if (n < 10000) return (uint64_t)std::sqrt((double)n);

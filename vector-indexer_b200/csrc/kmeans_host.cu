@@ -1,6 +1,8 @@
 // kmeans_host.cu -- host drivers of k-means (src/kmeans.rs): control flow, the random
 // stream and the small sequential pieces stay on the host; every distance, argmin and
 // centroid update runs on the device.
+#include <chrono>
+
 #include "kmeans_host.h"
 
 #include <algorithm>
@@ -12,16 +14,33 @@
 
 namespace vidx {
 
+thread_local KmProfile t_km_profile;
+
 namespace {
 
 template <class T>
 void h2d(T* dst, const T* src, size_t n, cudaStream_t st) {
     if (n) VIDX_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyHostToDevice, st));
 }
+// Where a k-means call spends its wall time: the serial host parts the reference's semantics force (the rand stream:
+// Fisher-Yates over all n indices per iteration, one sequential 50 000-term prefix sum per k-means++ draw) against
+// waiting for the device.  Per host thread; read through vidx_kmeans_last_profile.
+struct Tick {
+    double& acc;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    explicit Tick(double& a) : acc(a) {}
+    ~Tick() { acc += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
+};
+#define VIDX_SYNC(st)                                  \
+    do {                                               \
+        Tick _t(t_km_profile.device_wait_s);           \
+        VIDX_CUDA(cudaStreamSynchronize(st));          \
+    } while (0)
+
 template <class T>
 void d2h(T* dst, const T* src, size_t n, cudaStream_t st) {
     if (n) VIDX_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyDeviceToHost, st));
-    VIDX_CUDA(cudaStreamSynchronize(st));
+    VIDX_SYNC(st);
 }
 
 // Single-item pair launch (all `npts` points against all `k` centroids).
@@ -99,7 +118,7 @@ void DeviceKMeans::build_hierarchy(const float* d_cents, uint32_t k, uint64_t hs
         h2d(m.members.as<uint32_t>(), mem.data(), mem.size(), st_);
         launch_cluster_mean(d_cents, D_, m.member_off.as<uint32_t>(), m.members.as<uint32_t>(), nullptr, nullptr, meta_k, 1,
                             m.meta.as<float>(), st_);
-        VIDX_CUDA(cudaStreamSynchronize(st_));
+        VIDX_SYNC(st_);
     }
     // meta -> centroid lists, centroids ascending inside each meta (kmeans.rs:518-521);
     // moff/mem of the last iteration are exactly that.
@@ -109,7 +128,7 @@ void DeviceKMeans::build_hierarchy(const float* d_cents, uint32_t k, uint64_t hs
     m.m2c_list.reserve(std::max<size_t>(mem.size(), 1) * 4);
     h2d(m.m2c_off.as<uint32_t>(), moff.data(), moff.size(), st_);
     h2d(m.m2c_list.as<uint32_t>(), mem.data(), mem.size(), st_);
-    VIDX_CUDA(cudaStreamSynchronize(st_));
+    VIDX_SYNC(st_);
 }
 
 // ---- hierarchical assignment (kmeans.rs:474-581) --------------------------------------
@@ -166,7 +185,7 @@ void DeviceKMeans::assign_hierarchical(const float* d_pts, uint64_t npts, const 
         }
         launch_keys_to_labels(m.keys.as<unsigned long long>(), np, m.top3.as<uint32_t>(), m.m2c_off.as<uint32_t>(),
                               m.m2c_list.as<uint32_t>(), d_labels + p0, st_);
-        VIDX_CUDA(cudaStreamSynchronize(st_));  // host vectors reused next chunk
+        VIDX_SYNC(st_);  // host vectors reused next chunk
     }
 }
 
@@ -198,7 +217,10 @@ void DeviceKMeans::pp_init(uint32_t k, uint64_t seed, float* d_cents) {
     if (sampled) {
         sample_idx.resize(n_);
         std::iota(sample_idx.begin(), sample_idx.end(), 0u);
-        rng.shuffle(sample_idx.data(), sample_idx.size());
+        {
+            Tick t(t_km_profile.host_rng_s);
+            rng.shuffle(sample_idx.data(), sample_idx.size());
+        }
         sample_idx.resize(sample_threshold);
         mcount = sample_threshold;
     }
@@ -208,13 +230,14 @@ void DeviceKMeans::pp_init(uint32_t k, uint64_t seed, float* d_cents) {
     {
         std::vector<float> inf(mcount, std::numeric_limits<float>::infinity());
         h2d(m.mind.as<float>(), inf.data(), mcount, st_);
-        VIDX_CUDA(cudaStreamSynchronize(st_));
+        VIDX_SYNC(st_);
     }
     std::vector<float> w(mcount), cum;
     for (uint64_t i = 1; i < actual_k; i++) {
         // NB kmeans.rs:268/:431-436: rows 0..m of the data, also in the sampled variant.
         launch_min_dist(d_data_, D_, (uint32_t)mcount, d_cents + (i - 1) * D_, m.mind.as<float>(), st_);
         d2h(h_min, m.mind.as<float>(), mcount, st_);
+        Tick tk(t_km_profile.host_rng_s);  // the draw: sequential f32 sums over all weights (WeightedIndex, kmeans.rs:285-287)
         float total = 0.0f;
         for (uint64_t t = 0; t < mcount; t++) {
             w[t] = h_min[t] * h_min[t];
@@ -228,7 +251,7 @@ void DeviceKMeans::pp_init(uint32_t k, uint64_t seed, float* d_cents) {
         }
     }
     for (uint64_t i = actual_k; i < k; i++) copy_cent_row((uint32_t)rng.below_u64(actual_k), (uint32_t)i);
-    VIDX_CUDA(cudaStreamSynchronize(st_));
+    VIDX_SYNC(st_);
 }
 
 // kmeans.rs:313-331: clusters with count 0 take a fresh random data row, ascending c.
@@ -246,7 +269,7 @@ static void reseed_empty(DeviceKMeans::Impl& m, const float* d_data, uint64_t n,
     h2d(m.idx_a.as<uint32_t>(), cs.data(), cs.size(), st);
     h2d(m.idx_b.as<uint32_t>(), rs.data(), rs.size(), st);
     launch_copy_rows(d_data, m.idx_b.as<uint32_t>(), d_cents, m.idx_a.as<uint32_t>(), (uint32_t)cs.size(), D, st);
-    VIDX_CUDA(cudaStreamSynchronize(st));
+    VIDX_SYNC(st);
 }
 
 // kmeans.rs:334-351; cross-centroid order fixed to ascending c (the reference's rayon sum
@@ -283,7 +306,10 @@ uint64_t DeviceKMeans::mini_batch(uint32_t k, uint64_t max_iters, float tol, uin
     while (it < max_iters) {
         // sample_batch (kmeans.rs:722-726): shuffle all n indices, take the first b
         std::iota(idx.begin(), idx.end(), 0u);
-        rng.shuffle(idx.data(), idx.size());
+        {
+            Tick t(t_km_profile.host_rng_s);  // sample_batch: Fisher-Yates over ALL n indices (kmeans.rs:722-726)
+            rng.shuffle(idx.data(), idx.size());
+        }
         m.idx_a.reserve((size_t)b * 4);
         h2d(m.idx_a.as<uint32_t>(), idx.data(), b, st_);
         launch_copy_rows(d_data_, m.idx_a.as<uint32_t>(), m.batch.as<float>(), nullptr, b, D_, st_);
@@ -313,7 +339,7 @@ uint64_t DeviceKMeans::mini_batch(uint32_t k, uint64_t max_iters, float tol, uin
         h2d(m.eta.as<float>(), eta.data(), eta.size(), st_);
         launch_cluster_mean(d_data_, D_, m.member_off.as<uint32_t>(), m.members.as<uint32_t>(), m.cluster_ids.as<uint32_t>(),
                             m.eta.as<float>(), (uint32_t)cluster_ids.size(), 2, d_cents, st_);
-        VIDX_CUDA(cudaStreamSynchronize(st_));
+        VIDX_SYNC(st_);
         reseed_empty(m, d_data_, n_, D_, d_cents, counts, rng, st_);
         float delta = centroid_delta(m, d_cents, m.prev.as<float>(), k, D_, st_);
         VIDX_CUDA(cudaMemcpyAsync(m.prev.p, d_cents, (size_t)k * D_ * 4, cudaMemcpyDeviceToDevice, st_));
@@ -321,7 +347,7 @@ uint64_t DeviceKMeans::mini_batch(uint32_t k, uint64_t max_iters, float tol, uin
         if (delta < tol) break;
     }
     assign(d_cents, k, seed, d_labels);
-    VIDX_CUDA(cudaStreamSynchronize(st_));
+    VIDX_SYNC(st_);
     return it;
 }
 
@@ -354,14 +380,14 @@ uint64_t DeviceKMeans::lloyd(uint32_t k, uint64_t max_iters, float tol, uint64_t
         h2d(m.members.as<uint32_t>(), members.data(), members.size(), st_);
         launch_cluster_mean(d_data_, D_, m.member_off.as<uint32_t>(), m.members.as<uint32_t>(), nullptr, nullptr, k, 0,
                             m.newc.as<float>(), st_);
-        VIDX_CUDA(cudaStreamSynchronize(st_));
+        VIDX_SYNC(st_);
         reseed_empty(m, d_data_, n_, D_, m.newc.as<float>(), counts, rng, st_);
         float delta = centroid_delta(m, m.newc.as<float>(), d_cents, k, D_, st_);
         VIDX_CUDA(cudaMemcpyAsync(d_cents, m.newc.p, (size_t)k * D_ * 4, cudaMemcpyDeviceToDevice, st_));
         it++;
         if (delta < tol) break;
     }
-    VIDX_CUDA(cudaStreamSynchronize(st_));
+    VIDX_SYNC(st_);
     return it;
 }
 

@@ -6,6 +6,13 @@
 
 namespace vidx {
 
+// Wall-time split of the k-means calls made on this host thread since the last reset (vidx_kmeans_last_profile).
+struct KmProfile {
+    double host_rng_s = 0.0;     // the reference's serial random stream: shuffles over all n, weighted draws with their prefix sums
+    double device_wait_s = 0.0;  // blocked on the stream (kernels + copies)
+};
+extern thread_local KmProfile t_km_profile;
+
 // Two-level centroid hierarchy (kmeans.rs:584-648).
 struct Hierarchy {
     uint32_t meta_k = 0;

@@ -220,6 +220,29 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
 #pragma unroll
     for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
 }
+// The same in two halves: issue only, and a wait that NAMES the destination registers -- the compiler then cannot move
+// a use of them above the wait (a plain `asm volatile("tcgen05.wait::ld")` orders nothing with respect to registers).
+__device__ __forceinline__ void tc_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld_wait(uint32_t (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
+                   "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+                   "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :
+                 : "memory");
+}
 // Two 32-column loads in flight, one wait.
 __device__ __forceinline__ void tc_ld32x2(uint32_t taddr0, uint32_t taddr1, float (&v)[64]) {
     uint32_t r[64];
@@ -1110,81 +1133,75 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(const __grid_con
                     }
                     continue;
                 }
+                // The tile's 128 columns come out of tensor memory in four loads of 32, double-buffered in registers: while one
+                // chunk goes through the min tree the next load is in flight, so only the first load's latency is exposed
+                // (tcgen05.wait::ld waits for ALL outstanding loads, hence one load ahead, not more).  Once the fourth load has
+                // landed the accumulator stage is handed back to the MMA warp -- before the last chunk is looked at.
+                uint32_t ra[32], rb[32];
+                const uint32_t tb = tmem_base + ((uint32_t)(quarter * 32) << 16) + s * 128;
+                auto chunk = [&](const uint32_t cb, const uint32_t (&r)[32]) -> float {
+                    float tv[32];
 #pragma unroll
-                for (uint32_t half = 0; half < 2; half++) {
-                    float acc[64];
-                    const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + s * 128 + half * 64;
-                    { TC_T0(); tc_ld32x2(tbase, tbase + 32, acc); if (warp == 1) TC_ACC(14); }
-                    if (p.mode == 2) {
-                        // bounds pass: the minimum of each 32-column group (accumulator units; groups past the list: +inf)
-                        const float m0 = 2 * half < ng ? min32(acc) : kInf, m1 = 2 * half + 1 < ng ? min32(acc + 32) : kInf;
-                        if (valid) *reinterpret_cast<float2*>(p.submin + ((size_t)(submin_row0 + t) * 4 + half * 2)) = make_float2(m0, m1);
-                        continue;
-                    }
-#ifdef VIDX_TC_TIMING
-                    const long long _th0 = clock64();
-#endif
+                    for (int j = 0; j < 32; j++) tv[j] = __uint_as_float(r[j]);
+                    const float m = min32(tv);
+                    if (p.mode == 2) return cb < ng ? m : kInf;  // bounds pass: the minimum of the 32-column group (+inf past the list)
+                    if (active && cb < ng && m <= P) {
+                        // rare path: this row has columns inside its bound (as of the latest bound)
+                        P = fminf(P, lds_volatile_f(&s_P[row]));
+                        uint32_t mask = 0;
 #pragma unroll
-                    for (int h = 0; h < 2; h++) {
-                        const uint32_t cb = 2 * half + h;
-                        const float* tv = acc + 32 * h;
-#ifdef VIDX_TC_TIMING
-                        {
-                            const unsigned hm = __ballot_sync(kFull, active && cb < ng && min32(tv) <= P);
-                            if (warp == 1 && lane == 0 && p.dbg && hm) {
-                                atomicAdd(&p.dbg[16 * blockIdx.x + 2], 1ull);
-                                atomicAdd(&p.dbg[16 * blockIdx.x + 3], (unsigned long long)__popc(hm));
-                            }
-                        }
-#endif
-                        if (active && cb < ng && min32(tv) <= P) {
-                            // rare path: this row has columns inside its bound (as of the latest bound)
-                            P = fminf(P, lds_volatile_f(&s_P[row]));
-                            uint32_t mask = 0;
+                        for (int j = 0; j < 32; j++) mask |= (tv[j] <= P) ? (1u << j) : 0u;
+                        while (mask) {
+                            const int j = __ffs(mask) - 1;
+                            mask &= mask - 1;
+                            // tv[j] for a run-time j: a 5-level multiplexer tree (31 selects, depth 5) instead of a chain of 31
+                            float s16[16], s8[8], s4[4];
 #pragma unroll
-                            for (int j = 0; j < 32; j++) mask |= (tv[j] <= P) ? (1u << j) : 0u;
-                            while (mask) {
-                                const int j = __ffs(mask) - 1;
-                                mask &= mask - 1;
-                                // tv[j] for a run-time j: a 5-level multiplexer tree (31 selects, depth 5) instead of a chain of 31
-                                float s16[16], s8[8], s4[4];
+                            for (int i = 0; i < 16; i++) s16[i] = (j & 16) ? tv[16 + i] : tv[i];
 #pragma unroll
-                                for (int i = 0; i < 16; i++) s16[i] = (j & 16) ? tv[16 + i] : tv[i];
+                            for (int i = 0; i < 8; i++) s8[i] = (j & 8) ? s16[8 + i] : s16[i];
 #pragma unroll
-                                for (int i = 0; i < 8; i++) s8[i] = (j & 8) ? s16[8 + i] : s16[i];
+                            for (int i = 0; i < 4; i++) s4[i] = (j & 4) ? s8[4 + i] : s8[i];
+                            const float s2a = (j & 2) ? s4[2] : s4[0], s2b = (j & 2) ? s4[3] : s4[1];
+                            const float v = (j & 1) ? s2b : s2a;
+                            if (v <= P) {  // the bound may have shrunk since the mask was built
+                                push(kEntValid | (tl << 14) | ((cb * 32u + (uint32_t)j) << 7) | (uint32_t)row, v);
+                                // flood control (cold or very loose bound): the k-th smallest value this thread queued
+                                // in this item bounds the row's k-th best at once, without the selector's latency
+                                if (v < lr[0]) {
+                                    lr[0] = v;
 #pragma unroll
-                                for (int i = 0; i < 4; i++) s4[i] = (j & 4) ? s8[4 + i] : s8[i];
-                                const float s2a = (j & 2) ? s4[2] : s4[0], s2b = (j & 2) ? s4[3] : s4[1];
-                                const float v = (j & 1) ? s2b : s2a;
-                                if (v <= P) {  // the bound may have shrunk since the mask was built
-                                    push(kEntValid | (tl << 14) | ((cb * 32u + (uint32_t)j) << 7) | (uint32_t)row, v);
-                                    // flood control (cold or very loose bound): the k-th smallest value this thread queued
-                                    // in this item bounds the row's k-th best at once, without the selector's latency
-                                    if (v < lr[0]) {
-                                        lr[0] = v;
-#pragma unroll
-                                        for (int i = 0; i + 1 < KR; i++) {
-                                            const float hi_v = fmaxf(lr[i], lr[i + 1]), lo_v = fminf(lr[i], lr[i + 1]);
-                                            lr[i] = hi_v;
-                                            lr[i + 1] = lo_v;
-                                        }
-                                        P = fminf(P, lr[0] + delta);
+                                    for (int i = 0; i + 1 < KR; i++) {
+                                        const float hi_v = fmaxf(lr[i], lr[i + 1]), lo_v = fminf(lr[i], lr[i + 1]);
+                                        lr[i] = hi_v;
+                                        lr[i + 1] = lo_v;
                                     }
+                                    P = fminf(P, lr[0] + delta);
                                 }
                             }
                         }
                     }
-#ifdef VIDX_TC_TIMING
-                    __syncwarp();
-                    if (warp == 1 && lane == 0 && p.dbg) atomicAdd(&p.dbg[16 * blockIdx.x + 15], (unsigned long long)(clock64() - _th0));
-#endif
-                }
+                    return m;
+                };
+                tc_ld32_issue(tb, ra);
+                { TC_T0(); tc_ld_wait(ra); if (warp == 1) TC_ACC(14); }
+                tc_ld32_issue(tb + 32, rb);
+                const float m0 = chunk(0, ra);
+                { TC_T0(); tc_ld_wait(rb); if (warp == 1) TC_ACC(14); }
+                tc_ld32_issue(tb + 64, ra);
+                const float m1 = chunk(1, rb);
+                { TC_T0(); tc_ld_wait(ra); if (warp == 1) TC_ACC(14); }
+                tc_ld32_issue(tb + 96, rb);
+                const float m2 = chunk(2, ra);
+                { TC_T0(); tc_ld_wait(rb); if (warp == 1) TC_ACC(14); }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) {
                     if (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(&bar_tempty[s]), 0u));  // the issuer lives in the leader CTA
                     else mbar_arrive(&bar_tempty[s]);
                 }
+                const float m3 = chunk(3, rb);
+                if (p.mode == 2 && valid) *reinterpret_cast<float4*>(p.submin + (size_t)(submin_row0 + t) * 4) = make_float4(m0, m1, m2, m3);
             }
             it += t1 - t0;
             __syncwarp();

@@ -87,6 +87,7 @@ _SIGS = {
     "vidx_kmeans_parallel": (i32, [i32, f32p, u64, u64, u64, u64, C.c_float, u64, f32p, u64p, u64p]),
     "vidx_assign_points": (i32, [i32, f32p, u64, u64, f32p, u64, u64, u64p]),
     "vidx_kmeans_pp_init": (i32, [i32, f32p, u64, u64, u64, u64, f32p]),
+    "vidx_kmeans_last_profile": (i32, [C.POINTER(C.c_double)]),
     "vidx_calculate_num_clusters": (u64, [u64]),
     "vidx_calculate_max_iterations": (u64, [u64]),
     "vidx_save": (i32, [vp, C.c_char_p, C.c_char_p]),
@@ -485,6 +486,13 @@ def kmeans_pp_init(data, k, seed=42, device=0):
     c = np.zeros((k, data.shape[1]), np.float32)
     check(lib().vidx_kmeans_pp_init(device, _f(data), data.shape[0], data.shape[1], k, seed, _f(c)))
     return c
+
+
+def kmeans_last_profile():
+    """(seconds in the host's serial random stream, seconds blocked on the device) of this thread's k-means work since the last call."""
+    out = (C.c_double * 2)()
+    check(lib().vidx_kmeans_last_profile(out))
+    return float(out[0]), float(out[1])
 
 
 def calculate_num_clusters(n):
