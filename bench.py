@@ -455,6 +455,8 @@ def scan_rooflines(S, w, nprobe, peaks, peak_kind):
                               "bounds launch + main launch)",
                     "bound": "tensor", "achieved": ach, "peak": tc_peak, "unit": "TFLOP/s", "frac": ach / tc_peak,
                     "peak_source": f"{peak_kind} bf16 dense GEMM (cuBLAS), burst",
+                    "peak_sustained": peaks.get("bf16_tflops_sustained"),
+                    "frac_of_sustained": (ach / peaks["bf16_tflops_sustained"]) if peaks.get("bf16_tflops_sustained") else None,
                     "flops_per_launch": stage["tc_mma_flops"], "ms_per_launch": stage["ms_scan_tc"],
                     "pairs_per_launch": stage["tc_mma_flops"] // (2 * d), "filter_survivors": stage["n_tc_survivors"],
                     "queries_redone_exactly": stage["n_tc_overflow"],

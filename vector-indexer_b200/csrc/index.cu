@@ -570,6 +570,7 @@ struct CtxLease {
 constexpr uint64_t kCoarseTcMinLists = 1024;
 constexpr double kCoarseTcMinPairs = 4.0e6;
 constexpr bool kTcPairDefault = false;
+constexpr bool kTcTsaDefault = false;
 constexpr double kTcPairMinQueriesPerList = 256.0;  // mean queries per list from which the pair kernel is used
 constexpr uint64_t kSmallBatchQueries = 512;
 constexpr double kBoundsPassMaxUnitsPerSm = 256.0;  // ~0.15 ms of tensor work per pass
@@ -756,6 +757,12 @@ void Index::search_device(SearchCtx& ctx, const float* d_xq, uint64_t nq, uint64
         if (v && *v) return atoi(v) != 0;
         return kTcPairDefault && !small_batch && (double)nq * (double)np >= kTcPairMinQueriesPerList * (double)std::max<uint64_t>(nlist, 1);
     }() && tc;
+    // query tile in tensor memory for the main pass (D <= 240)
+    const bool tc_tsa = [&] {
+        const char* v = getenv("VIDX_TC_TSA");
+        if (v && *v) return atoi(v) != 0;
+        return kTcTsaDefault && !small_batch;
+    }() && tc && !tc_pair;
     const uint32_t nseg = (uint32_t)segs.size();
     const uint32_t ldc = ncgroups * kGroup;
     // pairs bound per query: the np largest per-list segment counts
@@ -1017,6 +1024,7 @@ void Index::search_device(SearchCtx& ctx, const float* d_xq, uint64_t nq, uint64
             tp.frozen = tc_dump ? 1 : 0;
             tp.flags = tc_flags;
             tp.pair = tc_pair ? 1u : 0u;
+            tp.tsa = tc_tsa ? 1u : 0u;
             if (tc_pair) tp.tmap = shadow_tmap;
             tp.noinsert_tiles = tc_dump ? 0 : seed_rank_tiles;
             tp.work_counter = counters + 8;

@@ -74,6 +74,8 @@ constexpr int kTcMaxChunkTiles = VIDX_CHUNK_TILES; // tiles per work item: chose
 __host__ __device__ constexpr int tc_queue_cap(int kr) { return kr > 16 ? 128 : 512; }
 __host__ __device__ constexpr int tc_stage_cap(int kr) { return kr > 16 ? 144 : 512; }
 constexpr int kTcAccStages = 4;      // accumulator tiles in TMEM
+constexpr uint32_t kTcACol = 384;    // A-in-TMEM variant: three accumulator stages, then the query tile (4 columns per 8 dims), then
+                                     // the 8 columns of the norm step's A operand
 constexpr int kTcTmemCols = 512;     // 4 accumulator stages x 128 columns
 constexpr int kTcStages = 4;         // shared-memory ring: stages of 128 vectors x 128 dims of fp16 (32 KB), two per tile pipeline
 constexpr int kTcStageChunks = 16;   // 16-byte chunks (8 halfs) of every vector per stage
@@ -203,6 +205,29 @@ __device__ __forceinline__ void tc_mma_f16_lo(uint32_t tmem_d, uint32_t a_lo, ui
         "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "n"(ACC ? 1 : 0)
         : "memory");
 }
+// The same with the A operand in tensor memory (row i in lane i, the 16 halfs of a K step in 8 consecutive columns): the query
+// tile is then read from TMEM, not from shared memory -- whose bandwidth (128 B/clk) the B operand (4 KB per MMA) and the bulk
+// copies already take most of.
+template <bool ACC>
+__device__ __forceinline__ void tc_mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 db;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "r"(tmem_a), "r"(b_lo), "r"(desc_hi), "r"(idesc), "n"(ACC ? 1 : 0)
+        : "memory");
+}
+// 32 lanes x 8 columns from registers: thread t of the warp writes lane (quarter*32 + t)
+__device__ __forceinline__ void tc_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+                 "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // 32 lanes x 32 columns of fp32: thread t of the warp gets lane (quarter*32 + t), 32 consecutive columns.
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
     uint32_t r[32];
@@ -541,7 +566,7 @@ __host__ __device__ inline TcSmemLayout tc_smem_layout_n(int Dh, int kr, bool pa
     L.off_q = L.off_stage + tc_stage_cap(kr) * 12;               // (query, probe rank) of the tile's rows
     L.off_row = L.off_q + kTcM * 8;                         // per row: bound P, delta, base, improved flag
     L.off_bar = L.off_row + 4 * kTcM * 4;
-    L.off_misc = L.off_bar + (2 * 2 * kTcStages + 2 * kTcAccStages) * 8;  // (room for the pair kernel's 8 stages)
+    L.off_misc = L.off_bar + (2 * 2 * kTcStages + 16) * 8;  // 8 + 8 ring barriers (pair kernel), 16 accumulator barriers (A-in-TMEM)
     L.off_item = L.off_misc + 64 + 512;                      // two staged work-item records
     L.total = L.off_item + 2 * 32;
     return L;
@@ -605,8 +630,14 @@ constexpr uint32_t kEntValid = 0x40000000u;
 // One issued instruction feeds two tensor pipes (the single-thread issue cadence, ~125 cycles per MMA, no longer bounds a
 // 64-cycle MMA) and the L2 -> SM traffic per flop halves.  Only the leader CTA issues; completion is multicast to the
 // barriers of both CTAs; the peer forwards "my half landed" and "my accumulator stage is drained" to the leader's barriers.
-template <int KR, bool PAIR>
+// TSA: the query tile lives in tensor memory (tcgen05.mma with A from TMEM).  The accumulators then have three stages, shared by
+// the two tile pipelines in tile order (stage = tile % 3); the hand-over barriers are per pipeline and four deep (tfull[pipe][j],
+// tdone[pipe][j], j = (tile / 2) % 4), so that every barrier is waited on by exactly one warp role, phase after phase -- a
+// parity wait cannot tell phase n from phase n + 2, and with stage-indexed barriers shared by two issuers a slow issuer would
+// read a stale "drained".
+template <int KR, bool PAIR, bool TSA>
 __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(const __grid_constant__ TcParams p) {
+    static_assert(!(PAIR && TSA), "the A-in-TMEM variant is single-CTA");
     extern __shared__ __align__(1024) unsigned char smem[];
     const TcSmemLayout L = tc_smem_layout(p.Dh, KR, PAIR);
     const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
@@ -630,8 +661,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(const __grid_con
     const uint32_t kSPs = kSP == 4 ? 2u : (kSP == 2 ? 1u : 0u);          // log2
     constexpr uint32_t kMaxStages = 2 * kTcStages;
     uint64_t* bar_empty = bar_full + kMaxStages;                         // [stages] K-slice consumed by the MMAs
-    uint64_t* bar_tfull = bar_empty + kMaxStages;                        // [4] accumulator tile complete
-    uint64_t* bar_tempty = bar_tfull + kTcAccStages;                     // [4] accumulator tile drained
+    uint64_t* bar_tfull = bar_empty + kMaxStages;                        // [4] accumulator tile complete   (TSA: [2][4] per pipeline)
+    uint64_t* bar_tempty = bar_tfull + (TSA ? 8 : kTcAccStages);         // [4] accumulator tile drained    (TSA: [2][4] "group drained its tile")
     uint32_t* s_misc = reinterpret_cast<uint32_t*>(smem + L.off_misc);   // [0] tmem base [1] item [2] queue tail [3] queue head [4] done
     volatile float* s_tmpv_all = reinterpret_cast<volatile float*>(s_misc + 16);  // [4][32] selector scratch
     // s_misc: [0] tmem base, [4] epilogue warps done, [8 + 2*sel] queue tail, [9 + 2*sel] queue head (sel < 4)
@@ -653,7 +684,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(const __grid_con
             mbar_init(&bar_full[i], PAIR && cta_rank == 0 ? 2 : 1);  // leader of a pair: its own copies + the peer's "landed"
             mbar_init(&bar_empty[i], 1);
         }
-        for (int i = 0; i < kTcAccStages; i++) {
+        for (int i = 0; i < (TSA ? 8 : kTcAccStages); i++) {
             mbar_init(&bar_tfull[i], 1);
             // the four warps of the epilogue group that owns the tile (pair: of both CTAs, all on the leader's barrier)
             mbar_init(&bar_tempty[i], PAIR ? kTcEpiWarps : kTcEpiWarps / 2);
@@ -683,6 +714,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(const __grid_con
     else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = s_misc[0];
+    if (TSA && warp >= 5 && warp <= 8) {
+        // the A side of the norm step, (a, a, a, 0, ...) per row as fp16, once: 8 columns behind the query tile
+        const float a = p.scale->a_ones;
+        const uint32_t ones[8] = {pack_h2(a, a), pack_h2(a, 0.0f), 0u, 0u, 0u, 0u, 0u, 0u};
+        tc_st8(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kTcACol + (uint32_t)p.Dh * 4, ones);
+        tc_wait_st();
+        tc_fence_before();
+    }
     const uint32_t total_items = p.item_off[p.nlist];
     const uint32_t idesc = make_idesc_f16(PAIR ? 2 * kTcM : kTcM, kTcTileGroups * 32);
     const int nkc = (Dh + kTcStageChunks - 1) / kTcStageChunks;  // K-slices per tile
@@ -792,6 +831,38 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(const __grid_con
                 s_delta[row] = delta;
                 s_base[row] = base_t;
                 s_impr[row] = dump_off;  // (bounds pass: first tile of the row in submin; else "set changed" flag = 0)
+            } else if (TSA) {
+                // A tile = fp16(-2 * 2^sq * queries) in tensor memory: row r in lane r, 8 dimensions per 4 columns; dimensions
+                // beyond the query's are zero.  A warp reaches the TMEM lanes of its quarter (warp % 4) only: warps 5-8.
+                if (warp >= 5 && warp <= 8) {
+                    const int arow = (warp & 3) * 32 + lane;
+                    const uint32_t q = s_q[arow].x;
+                    const float4* src = p.xq4 + (size_t)(q == kNoRow ? 0u : q) * Dq;
+                    const uint32_t abase = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kTcACol;
+                    for (int ks = 0; ks < Dh / 2; ks += 2) {  // two K steps (32 dimensions, 8 loads) in flight
+                        float4 v[8];
+#pragma unroll
+                        for (int u8 = 0; u8 < 8; u8++) {
+                            const int c4 = ks * 4 + u8;
+                            v[u8] = (q != kNoRow && c4 < Dq) ? __ldg(src + c4) : make_float4(0, 0, 0, 0);
+                        }
+#pragma unroll
+                        for (int h = 0; h < 2; h++) {
+                            if (ks + h < Dh / 2) {
+                                uint32_t r8[8];
+#pragma unroll
+                                for (int u4 = 0; u4 < 4; u4++) {
+                                    const float4 x = v[4 * h + u4];
+                                    r8[2 * u4] = pack_h2(tQmul * x.x, tQmul * x.y);
+                                    r8[2 * u4 + 1] = pack_h2(tQmul * x.z, tQmul * x.w);
+                                }
+                                tc_st8(abase + (uint32_t)(ks + h) * 8, r8);
+                            }
+                        }
+                    }
+                    tc_wait_st();
+                    tc_fence_before();
+                }
             } else if (warp >= 5) {
                 // A tile = fp16(-2 * 2^sq * queries): [chunk of 8 dims][128 rows][16 B] (core matrices of 8 rows x
                 // 16 B, SBO 128 B, LBO 2048 B); dimensions beyond the query's are zero.  Warps 5-11 gather it while
@@ -900,8 +971,28 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(const __grid_con
                 const uint32_t ones_lo = ((smem_u32(smem + L.off_ones) >> 4) & 0x3fffu) | (((L.off_zero - L.off_ones) >> 4) << 16);
                 const uint32_t skip = (pipe ^ it) & 1u;  // first tile of this item that belongs to this pipeline
                 for (uint32_t itt = it + skip; itt < it + (t1 - t0); itt += 2) {
-                    const uint32_t a = itt & (kTcAccStages - 1), aph = (itt / kTcAccStages) & 1;
-                    { TC_T0(); mbar_wait(&bar_tempty[a], aph ^ 1); TC_ACC(4 + pipe); }
+                    uint32_t a, tf;  // accumulator stage of the tile, and the barrier its completion is signalled on
+                    if (TSA) {
+                        a = itt % 3u;
+                        const uint32_t kk = itt >> 1;  // this pipeline's kk-th tile
+                        tf = pipe * 4u + (kk & 3u);
+                        if (itt >= 3) {
+                            // the stage was last used by tile itt - 3, a tile of the OTHER pipeline: wait until its epilogue group
+                            // has drained it (that group's ((itt - 3) / 2)-th tile)
+                            const uint32_t ko = (itt - 3) >> 1;
+                            TC_T0();
+                            mbar_wait(&bar_tempty[(1u - pipe) * 4u + (ko & 3u)], (ko >> 2) & 1);
+                            TC_ACC(4 + pipe);
+                        }
+                    } else {
+                        a = itt & (kTcAccStages - 1);
+                        tf = a;
+                        const uint32_t aph = (itt / kTcAccStages) & 1;
+                        TC_T0();
+                        mbar_wait(&bar_tempty[a], aph ^ 1);
+                        TC_ACC(4 + pipe);
+                    }
+                    tc_fence_after();
                     const uint32_t d_tmem = tmem_base + a * 128;
                     for (int kc = 0; kc < nkc; kc++, ks_it++) {
                         const uint32_t s = kSP * pipe + (ks_it & (kSP - 1u)), ph = (ks_it >> kSPs) & 1;
@@ -917,8 +1008,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(const __grid_con
                         const uint32_t norm_lo = ((smem_u32(smem + noff) >> 4) & 0x3fffu) | (((L.off_zero - noff) >> 4) << 16);
                         if (elect_one()) {
                             if (p.flags & 4u) {  // ablation (timing only): no tensor work, the ring just turns over
-                                if (PAIR) { tc_commit_pair(&bar_empty[s]); if (kc == nkc - 1) tc_commit_pair(&bar_tfull[a]); }
-                                else { tc_commit(&bar_empty[s]); if (kc == nkc - 1) tc_commit(&bar_tfull[a]); }
+                                if (PAIR) { tc_commit_pair(&bar_empty[s]); if (kc == nkc - 1) tc_commit_pair(&bar_tfull[tf]); }
+                                else { tc_commit(&bar_empty[s]); if (kc == nkc - 1) tc_commit(&bar_tfull[tf]); }
                             } else
                             if (PAIR) {
                                 if (kc == 0) tc_mma_f16_pair<false>(d_tmem, al, bl, desc_hi, idesc);
@@ -928,7 +1019,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(const __grid_con
                                     if (ks < nks) tc_mma_f16_pair<true>(d_tmem, al + ks * 256, bl + ks * kBStep, desc_hi, idesc);
                                 if (kc == nkc - 1) tc_mma_f16_pair<true>(d_tmem, ones_lo, norm_lo, desc_hi, idesc);
                                 tc_commit_pair(&bar_empty[s]);                       // both CTAs' halves of the K-slice are free
-                                if (kc == nkc - 1) tc_commit_pair(&bar_tfull[a]);    // both CTAs' accumulator tiles are ready
+                                if (kc == nkc - 1) tc_commit_pair(&bar_tfull[tf]);   // both CTAs' accumulator tiles are ready
+                            } else if (TSA) {
+                                const uint32_t at = tmem_base + kTcACol + (uint32_t)kc * (kTcStageChunks / 2) * 8u;  // 8 columns per K step
+                                if (kc == 0) tc_mma_f16_ts<false>(d_tmem, at, bl, desc_hi, idesc);
+                                else tc_mma_f16_ts<true>(d_tmem, at, bl, desc_hi, idesc);
+#pragma unroll
+                                for (int ks = 1; ks < kTcStageChunks / 2; ks++)
+                                    if (ks < nks) tc_mma_f16_ts<true>(d_tmem, at + ks * 8, bl + ks * kBStep, desc_hi, idesc);
+                                if (kc == nkc - 1) tc_mma_f16_ts<true>(d_tmem, tmem_base + kTcACol + (uint32_t)Dh * 4u, norm_lo, desc_hi, idesc);
+                                tc_commit(&bar_empty[s]);
+                                if (kc == nkc - 1) tc_commit(&bar_tfull[tf]);
                             } else {
                                 if (kc == 0) tc_mma_f16_lo<false>(d_tmem, al, bl, desc_hi, idesc);
                                 else tc_mma_f16_lo<true>(d_tmem, al, bl, desc_hi, idesc);
@@ -937,7 +1038,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(const __grid_con
                                     if (ks < nks) tc_mma_f16_lo<true>(d_tmem, al + ks * 256, bl + ks * kBStep, desc_hi, idesc);
                                 if (kc == nkc - 1) tc_mma_f16_lo<true>(d_tmem, ones_lo, norm_lo, desc_hi, idesc);
                                 tc_commit(&bar_empty[s]);                       // K-slice free once these MMAs have read it
-                                if (kc == nkc - 1) tc_commit(&bar_tfull[a]);    // accumulator tile ready for the epilogue
+                                if (kc == nkc - 1) tc_commit(&bar_tfull[tf]);   // accumulator tile ready for the epilogue
                             }
                         }
                         __syncwarp();
@@ -1117,9 +1218,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(const __grid_con
             const uint32_t eskip = (grp ^ it) & 1u;  // first tile of this item that belongs to this group
             for (uint32_t t = t0 + eskip; t < t1; t += 2) {
                 const uint32_t tl = t - t0, itt = it + tl;
-                const uint32_t s = itt & (kTcAccStages - 1), ph = (itt / kTcAccStages) & 1;
+                // s = accumulator stage; sb = index of the hand-over barriers of this tile (TSA: per pipeline, four deep)
+                const uint32_t s = TSA ? itt % 3u : itt & (kTcAccStages - 1);
+                const uint32_t sb = TSA ? grp * 4u + ((itt >> 1) & 3u) : s;
+                const uint32_t ph = TSA ? (itt >> 3) & 1 : (itt / kTcAccStages) & 1;
                 const float Pnew = lds_volatile_f(&s_P[row]);  // in flight during the wait
-                { TC_T0(); mbar_wait(&bar_tfull[s], ph); if (warp == 1) TC_ACC(8); }
+                { TC_T0(); mbar_wait(&bar_tfull[sb], ph); if (warp == 1) TC_ACC(8); }
                 tc_fence_after();
                 const uint32_t ng = min((uint32_t)kTcTileGroups, ngl - t * kTcTileGroups);
                 const bool active = valid;
@@ -1128,8 +1232,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(const __grid_con
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) {
-                        if (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(&bar_tempty[s]), 0u));
-                        else mbar_arrive(&bar_tempty[s]);
+                        if (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(&bar_tempty[sb]), 0u));
+                        else mbar_arrive(&bar_tempty[sb]);
                     }
                     continue;
                 }
@@ -1197,8 +1301,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(const __grid_con
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) {
-                    if (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(&bar_tempty[s]), 0u));  // the issuer lives in the leader CTA
-                    else mbar_arrive(&bar_tempty[s]);
+                    if (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(&bar_tempty[sb]), 0u));  // the issuer lives in the leader CTA
+                    else mbar_arrive(&bar_tempty[sb]);
                 }
                 const float m3 = chunk(3, rb);
                 if (p.mode == 2 && valid) *reinterpret_cast<float4*>(p.submin + (size_t)(submin_row0 + t) * 4) = make_float4(m0, m1, m2, m3);
@@ -1500,6 +1604,8 @@ __global__ void __launch_bounds__(kFinWarps * 32) finalize_kernel(FinalizeParams
 // ====================================================================================
 // launchers
 // ====================================================================================
+// the query tile (4 columns per chunk) + 8 columns of the norm step fit behind three accumulator stages (D <= 240)
+bool tc_tsa_supported(int Dh) { return (uint32_t)Dh * 4u + 8u <= (uint32_t)kTcTmemCols - kTcACol; }
 bool tc_supported(int D, uint32_t k) {
     if (k == 0 || k > 32 || D < 1) return false;
     return tc_smem_layout(tc_dh(D), k <= 8 ? 8 : (k <= 16 ? 16 : 32)).total <= kTcSmemMax;
@@ -1572,11 +1678,11 @@ void launch_tc_expand(const uint32_t* list_cnt, const uint32_t* list_ngroups, co
                                            pair ? 2u * kTcM : (uint32_t)kTcM, items);
     VIDX_LAUNCHED();
 }
-template <int KR, bool PAIR>
+template <int KR, bool PAIR, bool TSA = false>
 static void launch_scan_tc_kr(const TcParams& p, size_t smem, cudaStream_t st) {
     static PerDeviceSize attr;  // the opt-in is per device
     if (attr.needs(smem)) {
-        VIDX_CUDA(cudaFuncSetAttribute(scan_tc_kernel<KR, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        VIDX_CUDA(cudaFuncSetAttribute(scan_tc_kernel<KR, PAIR, TSA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr.set(smem);
     }
     if (PAIR) {
@@ -1593,9 +1699,9 @@ static void launch_scan_tc_kr(const TcParams& p, size_t smem, cudaStream_t st) {
         at[0].val.clusterDim.z = 1;
         cfg.attrs = at;
         cfg.numAttrs = 1;
-        VIDX_CUDA(cudaLaunchKernelEx(&cfg, scan_tc_kernel<KR, PAIR>, p));
+        VIDX_CUDA(cudaLaunchKernelEx(&cfg, scan_tc_kernel<KR, PAIR, TSA>, p));
     } else {
-        scan_tc_kernel<KR, PAIR><<<tc_num_sms(), kTcThreads, smem, st>>>(p);
+        scan_tc_kernel<KR, PAIR, TSA><<<tc_num_sms(), kTcThreads, smem, st>>>(p);
     }
     VIDX_LAUNCHED();
 }
@@ -1607,6 +1713,10 @@ void launch_scan_tc(const TcParams& p, cudaStream_t st) {
         if (kr == 8) launch_scan_tc_kr<8, true>(p, smem, st);
         else if (kr == 16) launch_scan_tc_kr<16, true>(p, smem, st);
         else launch_scan_tc_kr<32, true>(p, smem, st);
+    } else if (p.tsa && tc_tsa_supported(p.Dh)) {
+        if (kr == 8) launch_scan_tc_kr<8, false, true>(p, smem, st);
+        else if (kr == 16) launch_scan_tc_kr<16, false, true>(p, smem, st);
+        else launch_scan_tc_kr<32, false, true>(p, smem, st);
     } else {
         if (kr == 8) launch_scan_tc_kr<8, false>(p, smem, st);
         else if (kr == 16) launch_scan_tc_kr<16, false>(p, smem, st);

@@ -68,6 +68,7 @@ struct TcParams {
     uint32_t seed_ranks, noinsert_tiles;  // seeding bounds pass: the first noinsert_tiles tiles of each query's seed_ranks nearest lists;
                                    // main pass after it: their values are survivors but never enter the row's set
     uint32_t frozen;               // main pass after a bounds pass: the bounds are final, survivors are only collected
+    uint32_t tsa;                  // 1 = query tile in tensor memory (tcgen05.mma with A from TMEM, three accumulator stages), D <= 240
     uint32_t pair;                 // 1 = the CTA-pair kernel (cta_group::2): work items of 256 query rows, clusters of two CTAs
     uint32_t flags;                // bit 0: keep the rows' sets CTA-local in the main pass (no cross-CTA merge at item ends);
                                    // bits 1, 2: timing ablations (VIDX_TC_FLAGS, wrong answers): epilogue / MMAs do nothing
@@ -108,6 +109,7 @@ struct FinalizeParams {
 };
 
 bool tc_supported(int D, uint32_t k);  // D = vector dimension
+bool tc_tsa_supported(int Dh);
 int tc_dh(int D);  // chunks per vector of the shadow store (dimension padded to a multiple of 16)
 // |v|^2 per row (0 for padding rows) and, in stats[0], the float bits of the largest |component|.
 void launch_row_norms(const float4* vecs, int Dq, const uint32_t* row_src, size_t nrows, float* vn_true, uint32_t* stats,
