@@ -483,6 +483,10 @@ def scan_rooflines(S, w, nprobe, peaks, peak_kind):
                     "achieved": small["scan_bytes_algorithmic"] / ts / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                     "frac": small["scan_bytes_algorithmic"] / ts / 1e9 / peaks["hbm_gbs"], "peak_source": peak_kind,
                     "bytes_per_launch": small["scan_bytes_algorithmic"], "ms_per_launch": ts * 1e3,
+                    # what the filter actually streams: the fp16 shadow store (16 B per 8 dims + 16 B of norm terms per vector)
+                    # instead of the reference's fp32 record -- which is why `achieved` can exceed the copy bandwidth on indexes
+                    # whose probed lists are large
+                    "bytes_streamed_model": int(small["scan_bytes_algorithmic"] / (4 * d + 8) * (32 * ((d + 15) // 16) + 16)),
                     "traffic": ncu_traffic(w, nprobe, "dram_bytes_nq128") if H.world == 1 else None,
                     "workload": f"first {nq_small} queries of the batch, n_probe={nprobe}: distinct probed lists "
                                 f"len*(4D+8) + queries + probe lists + outputs",

@@ -200,4 +200,4 @@ def test_reference_harness_sweep_and_result_files(tmp_path):
     saved = json.load(open(tmp_path / "faiss_bench_results.json"))
     assert saved[0]["search_results"]["nprobe=4"]["recalls"]["10"] == rows[1]["recalls"][10]
     md = open(tmp_path / "faiss_bench_results.md").read()
-    assert "| nprobe | R@1 | R@10 | R@100 | ms/query | QPS |" in md and md.count("\n| ") == 4
+    assert "| nprobe | R@1 | R@10 | R@100 | ms/query | QPS |" in md and md.count("\n| ") == 5  # header + one row per n_probe
