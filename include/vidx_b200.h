@@ -217,7 +217,9 @@ int vidx_index_bin_read(const char* index_dir, uint64_t cap_lists, float* centro
  *   AFTER build / load of a whole index: a mask only -- everything stays resident, any (rank, world) may follow. */
 int vidx_set_partition(vidx_index* idx, int rank, int world);
 /* How the index is split: 0 = auto (default: shards, unless the most loaded rank would exceed the
- * mean by more than 15 % -- then ranges), 1 = shards, 2 = ranges (every rank owns the r-th contiguous
+ * mean by more than 15 % in vectors or 25 % in expected scan work -- the sum of len^2 over its lists:
+ * a query probes a list about as often as a vector falls into it -- then ranges), 1 = shards,
+ * 2 = ranges (every rank owns the r-th contiguous
  * range of the segments of every list).  vidx_get_partition_kind: what the last vidx_set_partition
  * used (1 shards, 2 ranges). */
 int vidx_set_partition_mode(vidx_index* idx, int mode);

@@ -377,22 +377,36 @@ std::vector<int32_t> Index::shard_owners(int world) const {
 //            (r + l) mod world, so short lists spread over all ranks).  Used when the shards cannot be balanced: the
 //            reference's barely-trained k-means routinely puts nearly all vectors into a handful of lists of ONE shard
 //            (SIFT-1M shape, nlist = 1024: one shard holds 999 954 of 1 000 000 vectors).
-// part_mode 0 picks shards unless the most loaded rank would exceed the mean by more than 15 %.
+// part_mode 0 picks shards unless the most loaded rank would exceed the mean by more than 15 % in vectors or 25 % in expected
+// scan work (sum of len^2 over its lists).
 // Host only: the decision depends on list sizes and the shard map alone, so every rank takes the same one.
 void Index::plan_partition() {
     std::vector<int32_t> owner;
     part_by_ranges = false;
     if (part_world > 1) {
         owner = shard_owners(part_world);
+        // Two loads per rank: the vectors it would hold, and the scan work it would get.  A query probes a list about as often
+        // as a vector falls into it, so the expected pairs a list contributes grow with len^2: a rank that owns the few giant
+        // lists the reference's k-means leaves behind holds its fair share of VECTORS and still does most of the scanning
+        // (configs[4], shard split: 12.4 % of the vectors per rank, but the scan stopped shrinking between 4 and 8 GPUs).
         std::vector<uint64_t> rank_load(part_world, 0);
+        std::vector<double> rank_work(part_world, 0.0);
         uint64_t total = 0;
+        double total_work = 0.0;
         for (uint64_t l = 0; l < nlist; l++) {
-            rank_load[owner[c2shard[l]]] += list_len[l];
+            const int o = owner[c2shard[l]];
+            const double w = (double)list_len[l] * (double)list_len[l];
+            rank_load[o] += list_len[l];
+            rank_work[o] += w;
             total += list_len[l];
+            total_work += w;
         }
         uint64_t mx = 0;
+        double mxw = 0.0;
         for (uint64_t v : rank_load) mx = std::max(mx, v);
-        const bool unbalanced = (double)mx * part_world > 1.15 * (double)std::max<uint64_t>(total, 1);
+        for (double v : rank_work) mxw = std::max(mxw, v);
+        const bool unbalanced = (double)mx * part_world > 1.15 * (double)std::max<uint64_t>(total, 1) ||
+                                mxw * part_world > 1.25 * std::max(total_work, 1.0);
         part_by_ranges = part_mode == 2 || (part_mode == 0 && unbalanced);
     }
     // segment ids stay global; an unowned list (or part of a list) maps to an empty range

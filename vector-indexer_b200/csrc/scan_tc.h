@@ -71,7 +71,8 @@ struct TcParams {
     uint32_t tsa;                  // 1 = query tile in tensor memory (tcgen05.mma with A from TMEM, three accumulator stages), D <= 240
     uint32_t pair;                 // 1 = the CTA-pair kernel (cta_group::2): work items of 256 query rows, clusters of two CTAs
     uint32_t flags;                // bit 0: keep the rows' sets CTA-local in the main pass (no cross-CTA merge at item ends);
-                                   // bits 1, 2: timing ablations (VIDX_TC_FLAGS, wrong answers): epilogue / MMAs do nothing
+                                   // bits 1, 2: timing ablations (VIDX_TC_FLAGS, wrong answers): epilogue / MMAs do nothing;
+                                   // bit 3: the producer feeds the two tile pipelines independently instead of in tile order
 };
 
 struct FinalizeParams {
