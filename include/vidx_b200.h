@@ -229,6 +229,10 @@ int vidx_get_shard_owner(const vidx_index* idx, int world, int32_t* out /* num_s
  * vector counts -> owner rank per shard; largest shard first to the least loaded rank,
  * ties to the lower rank / lower shard id. */
 int vidx_partition_shards(const uint64_t* shard_sizes, uint64_t num_shards, int world, int32_t* out);
+/* The whole split decision on its own (host only): list sizes + the list -> shard map -> owner rank per shard and *kind = 1
+ * (shards) or 2 (ranges), by the rule of vidx_set_partition_mode(mode).  Every rank evaluates it on the same numbers. */
+int vidx_partition_plan(const uint64_t* list_sizes, const uint64_t* list_shard, uint64_t nlist, uint64_t num_shards, int world,
+                        int mode, int32_t* shard_owner /* num_shards, may be NULL */, int* kind);
 /* Merge `nruns` per-rank results (each nq x k, ascending, padded with +inf / -1) laid out run-major in
  * DEVICE memory into the global top-k: the reduction behind join_all + concat + sort
  * in src/ivf_index.rs:249-266.  Any k.  Ties resolve to the lower run index. */

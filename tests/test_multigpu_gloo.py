@@ -44,6 +44,8 @@ def worker(rank, world, port, out_dir):
     c2s, sizes = ix.centroids_to_shard(), ix.list_sizes()
     shard_sizes = np.bincount(c2s, weights=sizes, minlength=ix.num_shards).astype(np.uint64)
     owner = _ffi.partition_shards(shard_sizes, world)
+    kind, owner2 = _ffi.partition_plan(sizes, c2s, ix.num_shards, world, mode="shards")
+    assert kind == "shards" and np.array_equal(owner, owner2)
     k, nprobe = 10, 12
     Dfull, Ifull = ix.search_batch(xq, k, nprobe)
     ix.set_list_mask(owner[c2s] == rank)
@@ -66,6 +68,32 @@ def test_two_rank_sharded_search_equals_single(tmp_path):
     outs = [open(tmp_path / f"rank{r}.txt").read() for r in range(2)]
     assert all(o.startswith("1 ") for o in outs), outs
     assert outs[0][2:] == outs[1][2:]  # both ranks derived the same partition
+
+
+def test_split_decision_balances_vectors_and_scan_work(ffi):
+    """vidx_partition_plan: shards when they balance, ranges when one rank would hold too many vectors OR too much expected scan
+    work (sum of len^2: a query probes a list about as often as a vector falls into it)."""
+    rng = np.random.default_rng(1)
+    # 64 lists of similar size in 8 shards: shards balance in both measures
+    sizes = rng.integers(900, 1100, 64)
+    shard = np.arange(64) % 8
+    for world in (2, 4, 8):
+        kind, owner = ffi.partition_plan(sizes, shard, 8, world)
+        assert kind == "shards" and set(owner.tolist()) == set(range(world))
+    # one shard holds nearly everything (the SIFT-1M-shaped bench index): vectors cannot be balanced
+    sizes2 = np.array([100_000] * 10 + [1] * 54)
+    shard2 = np.array([0] * 10 + list(np.arange(54) % 7 + 1))
+    assert ffi.partition_plan(sizes2, shard2, 8, 2)[0] == "ranges"
+    # equal vector counts per shard, but shard 0 is ONE giant list and the others are many small ones (configs[4]-like):
+    # vectors balance, the expected scan work does not
+    sizes3 = np.array([8000] + [100] * 80 * 7)
+    shard3 = np.array([0] + [1 + i // 80 for i in range(560)])
+    loads = np.bincount(shard3, weights=sizes3, minlength=8)
+    assert loads.max() == loads.min() == 8000
+    assert ffi.partition_plan(sizes3, shard3, 8, 8)[0] == "ranges"
+    assert ffi.partition_plan(sizes3, shard3, 8, 8, mode="shards")[0] == "shards"
+    assert ffi.partition_plan(sizes, shard, 8, 4, mode="ranges")[0] == "ranges"
+    assert ffi.partition_plan(sizes3, shard3, 8, 1)[0] == "shards"
 
 
 def test_partition_rule_balances(ffi):

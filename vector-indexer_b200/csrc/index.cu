@@ -380,35 +380,45 @@ std::vector<int32_t> Index::shard_owners(int world) const {
 // part_mode 0 picks shards unless the most loaded rank would exceed the mean by more than 15 % in vectors or 25 % in expected
 // scan work (sum of len^2 over its lists).
 // Host only: the decision depends on list sizes and the shard map alone, so every rank takes the same one.
+// The split decision on its own: list sizes + shard map -> shard owners and "by ranges?" (host only; every rank runs it on
+// the same numbers and so takes the same decision).
+bool choose_partition_split(const uint32_t* list_len, const uint32_t* c2shard, uint64_t nlist, uint64_t num_shards, int world,
+                            int mode, std::vector<int32_t>& owner) {
+    std::vector<uint64_t> load(num_shards ? num_shards : 1, 0);
+    for (uint64_t l = 0; l < nlist; l++) {
+        if (c2shard[l] >= load.size()) load.resize(c2shard[l] + 1, 0);
+        load[c2shard[l]] += list_len[l];
+    }
+    owner = partition_shards(load, world);
+    if (world <= 1) return false;
+    // Two loads per rank: the vectors it would hold, and the scan work it would get.  A query probes a list about as often
+    // as a vector falls into it, so the expected pairs a list contributes grow with len^2: a rank that owns the few giant
+    // lists the reference's k-means leaves behind holds its fair share of VECTORS and still does most of the scanning
+    // (configs[4], shard split: 12.4 % of the vectors per rank, but the scan stopped shrinking between 4 and 8 GPUs).
+    std::vector<uint64_t> rank_load(world, 0);
+    std::vector<double> rank_work(world, 0.0);
+    uint64_t total = 0;
+    double total_work = 0.0;
+    for (uint64_t l = 0; l < nlist; l++) {
+        const int o = owner[c2shard[l]];
+        const double w = (double)list_len[l] * (double)list_len[l];
+        rank_load[o] += list_len[l];
+        rank_work[o] += w;
+        total += list_len[l];
+        total_work += w;
+    }
+    uint64_t mx = 0;
+    double mxw = 0.0;
+    for (uint64_t v : rank_load) mx = std::max(mx, v);
+    for (double v : rank_work) mxw = std::max(mxw, v);
+    const bool unbalanced = (double)mx * world > 1.15 * (double)std::max<uint64_t>(total, 1) ||
+                            mxw * world > 1.25 * std::max(total_work, 1.0);
+    return mode == 2 || (mode == 0 && unbalanced);
+}
+
 void Index::plan_partition() {
     std::vector<int32_t> owner;
-    part_by_ranges = false;
-    if (part_world > 1) {
-        owner = shard_owners(part_world);
-        // Two loads per rank: the vectors it would hold, and the scan work it would get.  A query probes a list about as often
-        // as a vector falls into it, so the expected pairs a list contributes grow with len^2: a rank that owns the few giant
-        // lists the reference's k-means leaves behind holds its fair share of VECTORS and still does most of the scanning
-        // (configs[4], shard split: 12.4 % of the vectors per rank, but the scan stopped shrinking between 4 and 8 GPUs).
-        std::vector<uint64_t> rank_load(part_world, 0);
-        std::vector<double> rank_work(part_world, 0.0);
-        uint64_t total = 0;
-        double total_work = 0.0;
-        for (uint64_t l = 0; l < nlist; l++) {
-            const int o = owner[c2shard[l]];
-            const double w = (double)list_len[l] * (double)list_len[l];
-            rank_load[o] += list_len[l];
-            rank_work[o] += w;
-            total += list_len[l];
-            total_work += w;
-        }
-        uint64_t mx = 0;
-        double mxw = 0.0;
-        for (uint64_t v : rank_load) mx = std::max(mx, v);
-        for (double v : rank_work) mxw = std::max(mxw, v);
-        const bool unbalanced = (double)mx * part_world > 1.15 * (double)std::max<uint64_t>(total, 1) ||
-                                mxw * part_world > 1.25 * std::max(total_work, 1.0);
-        part_by_ranges = part_mode == 2 || (part_mode == 0 && unbalanced);
-    }
+    part_by_ranges = choose_partition_split(list_len.data(), c2shard.data(), nlist, num_shards, part_world, part_mode, owner);
     // segment ids stay global; an unowned list (or part of a list) maps to an empty range
     list_seg_part.assign(nlist + 1, make_uint2(0, 0));
     for (uint64_t l = 0; l < nlist; l++) {
@@ -1974,6 +1984,22 @@ int vidx_partition_shards(const uint64_t* shard_sizes, uint64_t num_shards, int 
         std::vector<uint64_t> load(shard_sizes, shard_sizes + num_shards);
         std::vector<int32_t> o = vidx::partition_shards_public(load, world);
         for (uint64_t i = 0; i < num_shards; i++) out[i] = o[i];
+    });
+}
+int vidx_partition_plan(const uint64_t* list_sizes, const uint64_t* list_shard, uint64_t nlist, uint64_t num_shards, int world, int mode,
+                        int32_t* shard_owner, int* kind) {
+    return guarded([&] {
+        require(list_sizes && list_shard && kind && world >= 1 && mode >= 0 && mode <= 2, VIDX_ERR_INVALID_INPUT, "bad argument");
+        std::vector<uint32_t> len(nlist), sh(nlist);
+        for (uint64_t l = 0; l < nlist; l++) {
+            require(list_sizes[l] <= 0xffffffffull && list_shard[l] < (1ull << 31), VIDX_ERR_INVALID_INPUT, "list size / shard id out of range");
+            len[l] = (uint32_t)list_sizes[l];
+            sh[l] = (uint32_t)list_shard[l];
+        }
+        std::vector<int32_t> owner;
+        *kind = vidx::choose_partition_split(len.data(), sh.data(), nlist, num_shards, world, mode, owner) ? 2 : 1;
+        if (shard_owner)
+            for (uint64_t i = 0; i < num_shards && i < owner.size(); i++) shard_owner[i] = owner[i];
     });
 }
 int vidx_merge_topk_keyed_device(int device, const float* d_D_runs, const int64_t* d_I_runs, const uint64_t* d_K_runs0, uint32_t nruns,

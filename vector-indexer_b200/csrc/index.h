@@ -125,6 +125,8 @@ struct Index {
 };
 
 std::vector<int32_t> partition_shards_public(const std::vector<uint64_t>& load, int world);
+bool choose_partition_split(const uint32_t* list_len, const uint32_t* c2shard, uint64_t nlist, uint64_t num_shards, int world,
+                            int mode, std::vector<int32_t>& owner);
 
 // What vidx_load reads: index.bin and the header + centroid index of every shard file first (list sizes and block
 // positions: the partition is decided on these), then only the vector ranges that become resident on this rank.

@@ -102,6 +102,7 @@ _SIGS = {
     "vidx_get_partition_kind": (i32, [vp]),
     "vidx_get_shard_owner": (i32, [vp, i32, i32p]),
     "vidx_partition_shards": (i32, [u64p, u64, i32, i32p]),
+    "vidx_partition_plan": (i32, [u64p, u64p, u64, u64, i32, i32, i32p, C.POINTER(C.c_int)]),
     "vidx_merge_topk_device": (i32, [i32, vp, vp, u32, u64, u64, vp, vp, vp]),
     "vidx_merge_topk_keyed_device": (i32, [i32, vp, vp, vp, u32, u64, u64, vp, vp, vp]),
     "vidx_search_local_device": (i32, [vp, vp, u64, u64, u64, vp, vp, vp, vp]),
@@ -443,6 +444,17 @@ def partition_shards(shard_sizes, world):
     out = np.zeros(len(sizes), np.int32)
     check(lib().vidx_partition_shards(_u(sizes), len(sizes), world, out.ctypes.data_as(i32p)))
     return out
+
+
+def partition_plan(list_sizes, list_shard, num_shards, world, mode=0):
+    """-> (kind "shards" | "ranges", owner rank per shard): the split vidx_set_partition would choose (host only)."""
+    sizes = np.ascontiguousarray(list_sizes, dtype=np.uint64)
+    shard = np.ascontiguousarray(list_shard, dtype=np.uint64)
+    owner = np.zeros(max(int(num_shards), 1), np.int32)
+    kind = C.c_int(0)
+    check(lib().vidx_partition_plan(_u(sizes), _u(shard), len(sizes), num_shards, world, {"auto": 0, "shards": 1, "ranges": 2}.get(mode, mode),
+                                    owner.ctypes.data_as(i32p), C.byref(kind)))
+    return {1: "shards", 2: "ranges"}[kind.value], owner[:num_shards]
 
 
 def merge_topk_keyed_device(device, d_D_runs, d_I_runs, d_K_runs, nruns, nq, k, d_D, d_I, stream=0):
