@@ -587,11 +587,12 @@ struct CtxLease {
     ~CtxLease() { ix.release_ctx(c, st); }
 };
 
-// auto mode: the tensor-core filter when the table has at least kCoarseTcMinLists lists and the batch at least
+// auto mode: the tensor-core filter when the table has at least kCoarseTcMinLists lists (the bench index keeps 1023 of its 1024)
+// and the batch at least
 // kCoarseTcMinPairs (query, centroid) pairs (below that its ~15 launches cost more than the two of the exact stage).
 // Measured (CUDA events, nq = 10 000, warm): nlist = 1024 (D = 128, n_probe 8) exact 0.19 ms vs filter 0.155;
 // nlist = 12 639 (D = 128, n_probe 32) 2.00 vs 1.94; nlist = 65 280 (D = 96, n_probe 32) 8.71 vs 0.71 ms.
-constexpr uint64_t kCoarseTcMinLists = 1024;
+constexpr uint64_t kCoarseTcMinLists = 512;
 constexpr double kCoarseTcMinPairs = 4.0e6;
 constexpr bool kTcPairDefault = false;
 constexpr bool kTcTsaDefault = false;
