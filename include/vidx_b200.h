@@ -292,7 +292,7 @@ int vidx_set_profiling(vidx_index* idx, int enabled);
  * in 8 GB).  Results are bit-identical in every mode. */
 int vidx_set_scan_mode(vidx_index* idx, int mode);
 /* Coarse quantization (ivf_index.rs:205-220): 0 = auto (the tensor-core filter + exact re-check when n_probe <= 32, the table has
- * >= 512 lists and the batch >= 4M (query, centroid) pairs -- measured faster from there, 12x at nlist = 65 536; else the exact
+ * >= 512 lists and the batch >= 8M (query, centroid) pairs -- measured faster from there, 12x at nlist = 65 536; else the exact
  * FP32 kernels), 1 = exact kernels only, 2 = the filter whenever it applies (n_probe <= 32).  Probe lists and distances are
  * identical in every mode. */
 int vidx_set_coarse_mode(vidx_index* idx, int mode);

@@ -103,9 +103,13 @@ def test_partitioned_load_reads_only_the_owned_part(ffi, tmp_path):
     assert same_bits(D, D0) and np.array_equal(I, I0)
 
 
-def test_collective_path_with_a_one_rank_communicator(ffi):
-    """vidx_comm_init + vidx_search_multi on world = 1: the probe all-gather, the packed all-gather and the keyed merge
-    all run (over one rank) and must return the plain answer; k > 32 takes the large-k path."""
+@pytest.mark.parametrize("exchange", ["", "1"])
+def test_collective_path_with_a_one_rank_communicator(ffi, exchange, monkeypatch):
+    """vidx_comm_init + vidx_search_multi on world = 1: the probe all-gather, the bound exchange (forced on with
+    VIDX_BOUNDS_EXCHANGE: a one-rank world would skip it), the packed all-gather and the keyed merge all run (over one rank)
+    and must return the plain answer; k > 32 takes the large-k path."""
+    if exchange:
+        monkeypatch.setenv("VIDX_BOUNDS_EXCHANGE", exchange)
     xb, xq = bench_data(20000, 32, 333)
     ix = ffi.Index(32).build(xb)
     ix.comm_init(0, 1, ffi.comm_unique_id())

@@ -522,6 +522,7 @@ struct SearchCtx {
     CoarseWs cw;
     DevBuf io_xq, io_D, io_I, io_rows, io_V;      // vidx_search staging (host-pointer entry points)
     DevBuf mg_probes_part, mg_probes, mg_pack, mg_all;  // vidx_search_multi: probe slices, packed local / gathered results
+    DevBuf mg_ub, mg_ub_all;                             // ... and the bound exchange: local / gathered upper bounds [nq][k]
     cudaStream_t stream = nullptr;
     cudaEvent_t events[10] = {};
     cudaEvent_t done = nullptr;
@@ -591,9 +592,10 @@ struct CtxLease {
 // and the batch at least
 // kCoarseTcMinPairs (query, centroid) pairs (below that its ~15 launches cost more than the two of the exact stage).
 // Measured (CUDA events, nq = 10 000, warm): nlist = 1024 (D = 128, n_probe 8) exact 0.19 ms vs filter 0.155;
-// nlist = 12 639 (D = 128, n_probe 32) 2.00 vs 1.94; nlist = 65 280 (D = 96, n_probe 32) 8.71 vs 0.71 ms.
+// nlist = 12 639 (D = 128, n_probe 32) 2.00 vs 1.94; nlist = 65 280 (D = 96, n_probe 32) 8.71 vs 0.71 ms; a 5000-query slice of the
+// first (what a rank of two ranks one): exact 0.113 vs filter 0.138.
 constexpr uint64_t kCoarseTcMinLists = 512;
-constexpr double kCoarseTcMinPairs = 4.0e6;
+constexpr double kCoarseTcMinPairs = 8.0e6;
 constexpr bool kTcPairDefault = false;
 constexpr bool kTcTsaDefault = false;
 constexpr double kTcPairMinQueriesPerList = 256.0;  // mean queries per list from which the pair kernel is used
@@ -732,7 +734,7 @@ void Index::coarse_tc(SearchCtx& ctx, const float4* xq4, uint32_t nqb, uint32_t 
 
 void Index::search_device(SearchCtx& ctx, const float* d_xq, uint64_t nq, uint64_t k_req, uint64_t nprobe_req, float* d_D,
                           int64_t* d_I, uint32_t* d_rows_out, cudaStream_t st, uint32_t* d_probe_out, float* d_probe_dist_out,
-                          const uint32_t* d_probes_in, unsigned long long* d_keys_out) {
+                          const uint32_t* d_probes_in, unsigned long long* d_keys_out, Comm* bounds_comm) {
     if (k_req == 0 || nprobe_req == 0)
         throw ApiError(VIDX_ERR_INVALID_INPUT, "k and n_probe must be greater than 0");  // ivf_index.rs:197-202
     if (!built) throw ApiError(VIDX_ERR_OTHER, "index has not been built or loaded");
@@ -811,6 +813,28 @@ void Index::search_device(SearchCtx& ctx, const float* d_xq, uint64_t nq, uint64
         capq = (uint32_t)std::min<uint64_t>(4096, std::max<uint64_t>(256, (uint64_t)(2e9 / (8.0 * (double)qb))));
         capq = (uint32_t)std::min<uint64_t>(capq, std::max<uint64_t>(owned_vectors, 32));
     }
+
+    // Multi-GPU bound exchange: exactly ONE all-gather of nq x k upper bounds per call on every rank (a collective must be
+    // called by all of them).  A rank that cannot take part -- no tensor-core filter for this shape or index part, or a batch
+    // that it has to cut -- contributes +inf up front and ignores the answer.
+    bool exchange = bounds_comm != nullptr && !coarse_only;
+    const uint32_t xworld = exchange ? (uint32_t)comm_world(bounds_comm) : 1u;
+    if (exchange) {
+        ctx.mg_ub.reserve((size_t)nq * k * 4);
+        ctx.mg_ub_all.reserve((size_t)nq * k * 4 * xworld);
+        if (!(tc && qb == nq)) {
+            launch_fill_u32(ctx.mg_ub.as<uint32_t>(), 0x7f800000u, (size_t)nq * k, st);
+            comm_all_gather(bounds_comm, ctx.mg_ub.p, ctx.mg_ub_all.p, (size_t)nq * k * 4, st);
+            exchange = false;
+        }
+    }
+    auto exchange_bounds = [&](uint32_t nqb) {  // after bounds_apply: sel_val holds each query's k smallest minima, ascending
+        if (!exchange) return;
+        launch_bounds_to_ub(w.sel_val.as<float>(), nqb, (uint32_t)k, w.qnorm.as<float>(),
+                            reinterpret_cast<const TcScale*>(w.tcscale.as<unsigned char>() + 16), vn_max, ctx.mg_ub.as<float>(), st);
+        comm_all_gather(bounds_comm, ctx.mg_ub.p, ctx.mg_ub_all.p, (size_t)nqb * k * 4, st);
+        launch_bounds_merge(ctx.mg_ub_all.as<float>(), xworld, nqb, (uint32_t)k, w.gthr.as<uint32_t>(), st);
+    };
 
     cudaEvent_t* ev = ctx.events;
     if (profiling) {
@@ -1026,6 +1050,7 @@ void Index::search_device(SearchCtx& ctx, const float* d_xq, uint64_t nq, uint64
                 launch_select_small(w.dump.as<float>(), nullptr, nullptr, seed_row, seed_row, nqb, (uint32_t)k, w.sel_pos.as<uint32_t>(),
                                    w.sel_val.as<float>(), st);
                 launch_bounds_apply(w.sel_val.as<float>(), nqb, (uint32_t)k, w.gtop.as<float>(), st);
+                exchange_bounds(nqb);
             }
             tp.pair_off = tc_dump ? w.pair_off.as<uint32_t>() : nullptr;
             tp.list_cnt = w.list_cnt.as<uint32_t>();
@@ -1043,6 +1068,7 @@ void Index::search_device(SearchCtx& ctx, const float* d_xq, uint64_t nq, uint64
                 launch_select_small(w.dump.as<float>(), w.row_off.as<uint64_t>(), w.row_len.as<uint32_t>(), 0, 0, nqb, (uint32_t)k,
                                    w.sel_pos.as<uint32_t>(), w.sel_val.as<float>(), st);
                 launch_bounds_apply(w.sel_val.as<float>(), nqb, (uint32_t)k, w.gtop.as<float>(), st);
+                exchange_bounds(nqb);
             }
             // pass 2: everything else, starting from warm bounds (after a bounds pass: from final ones)
             tp.mode = 0;
@@ -1229,12 +1255,22 @@ void Index::search_device(SearchCtx& ctx, const float* d_xq, uint64_t nq, uint64
 //      is replicated, the result for a query does not depend on who computes it) and the probe lists are all-gathered --
 //      the stage would otherwise be repeated, whole, on every rank;
 //   2. every rank scans the probed lists (or list ranges) it owns -> its local top-k per query, each result with the
-//      key (probe rank, global row);
+//      key (probe rank, global row).  Optionally (VIDX_BOUNDS_EXCHANGE=1) the ranks all-gather each query's k tightest upper
+//      bounds between the scan's bounds launch and its main launch and adopt the k-th smallest of the union;
 //   3. ONE all-gather of the packed (D | I | key) runs, then a device merge by (distance, key): the order of the
 //      reference's stable sort over candidates gathered in probe order (ivf_index.rs:249-266), so the answer is
 //      bit-identical to the one-GPU answer however the index was split.
 // Every rank ends up with the full answer.  All of it is enqueued on `st`; NCCL orders the collectives with the kernels.
 // ------------------------------------------------------------------------------------
+// The bound exchange (see bounds_to_ub_kernel) is off unless VIDX_BOUNDS_EXCHANGE=1: measured neutral on the BASELINE
+// configurations (2 GPUs, configs[1]: 47 instead of 50 survivors per query and rank, 1.68 vs 1.62 ms per step) -- their giant
+// lists run the seeded flavour, whose rows keep tightening their own bounds all through the main launch, so one exchange
+// after the bounds launch buys little and costs a 400 KB all-gather.  It pays where the bounds launch is final (the
+// two-pass flavour: balanced lists), which none of the measured multi-GPU configurations is.  Every rank must agree on it.
+static bool bounds_exchange_enabled() {
+    const char* v = getenv("VIDX_BOUNDS_EXCHANGE");
+    return v && *v && atoi(v) != 0;
+}
 static void search_multi_device(Index& ix, SearchCtx& c, const float* d_xq, uint64_t nq, uint64_t k_req, uint64_t nprobe_req,
                                 float* d_D, int64_t* d_I, cudaStream_t st) {
     if (k_req == 0 || nprobe_req == 0) throw ApiError(VIDX_ERR_INVALID_INPUT, "k and n_probe must be greater than 0");
@@ -1263,7 +1299,8 @@ static void search_multi_device(Index& ix, SearchCtx& c, const float* d_xq, uint
     c.mg_all.reserve(run_bytes * world);
     unsigned char* pack = c.mg_pack.as<unsigned char>();
     ix.search_device(c, d_xq, nq, k_req, np, reinterpret_cast<float*>(pack), reinterpret_cast<int64_t*>(pack + off_I), nullptr, st,
-                     nullptr, nullptr, c.mg_probes.as<uint32_t>(), reinterpret_cast<unsigned long long*>(pack + off_K));
+                     nullptr, nullptr, c.mg_probes.as<uint32_t>(), reinterpret_cast<unsigned long long*>(pack + off_K),
+                     bounds_exchange_enabled() ? ix.comm : nullptr);
     // 3. exchange + merge
     if (profiling) VIDX_CUDA(cudaEventRecord(c.events[9], st));
     comm_all_gather(ix.comm, pack, c.mg_all.p, run_bytes, st);

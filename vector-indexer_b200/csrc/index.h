@@ -118,7 +118,7 @@ struct Index {
     uint64_t resident_bytes() const;
     void search_device(SearchCtx& c, const float* d_xq, uint64_t nq, uint64_t k, uint64_t nprobe, float* d_D, int64_t* d_I,
                        uint32_t* d_rows, cudaStream_t st, uint32_t* d_probe_out, float* d_probe_dist_out,
-                       const uint32_t* d_probes_in = nullptr, unsigned long long* d_keys_out = nullptr);
+                       const uint32_t* d_probes_in = nullptr, unsigned long long* d_keys_out = nullptr, Comm* bounds_comm = nullptr);
     void coarse_tc(SearchCtx& c, const float4* xq4, uint32_t nqb, uint32_t np, uint32_t* d_probes, float* d_probe_dist,
                    cudaStream_t st);
     ~Index();

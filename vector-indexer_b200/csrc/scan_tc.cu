@@ -1459,6 +1459,53 @@ __global__ void bounds_apply_kernel(const float* __restrict__ sel_val /* [nq][k]
     if (kth < __int_as_float(0x7f800000)) gtop[i] = sel_val[(size_t)(i / k) * k + (k - 1 - i % k)];
 }
 
+// Multi-GPU: a rank's bounds are those of its own part of the index -- the k-th best of an eighth of the vectors is about the
+// (8k)-th best of all of them, so every rank would let ~4x more candidates through its filter than one GPU does.  After the bounds
+// launch every rank turns the k smallest minima of each query (sel_val, accumulator units, ascending) into UPPER bounds of the
+// exact distances of k distinct vectors (real units: the scales differ between ranks), the ranks all-gather them, and the k-th
+// smallest of the union -- an upper bound of the global k-th best distance -- becomes the query's published bound on every rank.
+__global__ void bounds_to_ub_kernel(const float* __restrict__ sel_val, uint32_t nq, uint32_t k, const float* __restrict__ qnorm,
+                                    const TcScale* __restrict__ scale, float vn_max, float* __restrict__ ub) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq * k) return;
+    const uint32_t q = i / k;
+    const float v = sel_val[i], kInf = __int_as_float(0x7f800000);
+    float u = kInf;
+    if (scale->ok && v < kInf) {
+        const float qn = qnorm[q], cabs = scale->c_abs;
+        const float base_t = (1.0f - kTcEps) * qn - cabs;
+        const float delta = 2.0f * kTcEps * (qn + vn_max) + 2.0f * cabs;  // real units (scan_tc_kernel keeps it times S)
+        u = fmaxf((v * scale->invS + delta) + base_t, 0.0f);
+        u = u + 1e-5f * u;
+    }
+    ub[i] = u;
+}
+__global__ void bounds_merge_kernel(const float* __restrict__ ub_all /* [world][nq][k] */, uint32_t world, uint32_t nq, uint32_t k,
+                                    uint32_t* __restrict__ gthr_bits) {
+    uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    const float kInf = __int_as_float(0x7f800000);
+    float best[32];  // the k smallest so far, ascending (k <= 32)
+#pragma unroll
+    for (int i = 0; i < 32; i++) best[i] = kInf;
+    for (uint32_t r = 0; r < world; r++) {
+        const float* row = ub_all + ((size_t)r * nq + q) * k;
+        for (uint32_t i = 0; i < k; i++) {
+            float v = row[i];
+            if (!(v < best[k - 1])) break;  // rows ascend: nothing smaller follows
+#pragma unroll
+            for (int j = 0; j < 32; j++) {  // insertion: v bubbles up from its place
+                if ((uint32_t)j < k && v < best[j]) {
+                    const float t = best[j];
+                    best[j] = v;
+                    v = t;
+                }
+            }
+        }
+    }
+    if (best[k - 1] < kInf) atomicMin(&gthr_bits[q], __float_as_uint(best[k - 1]));
+}
+
 // ------------------------------------------------------------------------------------------
 // finalize: exact distances of the survivors + merge with the exact-path slots -> top-k
 // ------------------------------------------------------------------------------------------
@@ -1796,6 +1843,17 @@ void launch_submin_rows(const uint32_t* pair_off, uint32_t nprobe, uint32_t nq, 
 void launch_bounds_apply(const float* sel_val, uint32_t nq, uint32_t k, float* gtop, cudaStream_t st) {
     if (!nq) return;
     bounds_apply_kernel<<<(unsigned)ceil_div((size_t)nq * k, 256), 256, 0, st>>>(sel_val, nq, k, gtop);
+    VIDX_LAUNCHED();
+}
+void launch_bounds_to_ub(const float* sel_val, uint32_t nq, uint32_t k, const float* qnorm, const TcScale* scale, float vn_max, float* ub,
+                         cudaStream_t st) {
+    if (!nq) return;
+    bounds_to_ub_kernel<<<(unsigned)ceil_div((size_t)nq * k, 256), 256, 0, st>>>(sel_val, nq, k, qnorm, scale, vn_max, ub);
+    VIDX_LAUNCHED();
+}
+void launch_bounds_merge(const float* ub_all, uint32_t world, uint32_t nq, uint32_t k, uint32_t* gthr_bits, cudaStream_t st) {
+    if (!nq) return;
+    bounds_merge_kernel<<<(unsigned)ceil_div(nq, 128), 128, 0, st>>>(ub_all, world, nq, k, gthr_bits);
     VIDX_LAUNCHED();
 }
 void launch_finalize(const FinalizeParams& p, cudaStream_t st) {

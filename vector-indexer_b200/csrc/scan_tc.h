@@ -136,6 +136,10 @@ void make_shadow_tensor_map(CUtensorMap* out, const void* vecs16, uint64_t nrows
 void launch_pair_tiles(const uint32_t* probes, size_t npairs, const uint32_t* list_ngroups, uint32_t* pair_tiles, cudaStream_t st);
 void launch_submin_rows(const uint32_t* pair_off, uint32_t nprobe, uint32_t nq, uint64_t* row_off, uint32_t* row_len, cudaStream_t st);
 void launch_bounds_apply(const float* sel_val, uint32_t nq, uint32_t k, float* gtop, cudaStream_t st);
+// multi-GPU bound exchange (see bounds_to_ub_kernel): local k smallest minima -> upper bounds in real units; k-th smallest of all ranks' -> gthr
+void launch_bounds_to_ub(const float* sel_val, uint32_t nq, uint32_t k, const float* qnorm, const TcScale* scale, float vn_max, float* ub,
+                         cudaStream_t st);
+void launch_bounds_merge(const float* ub_all, uint32_t world, uint32_t nq, uint32_t k, uint32_t* gthr_bits, cudaStream_t st);
 void launch_finalize(const FinalizeParams& p, cudaStream_t st);
 
 }  // namespace vidx
