@@ -349,14 +349,17 @@ class Harness:
 class Searcher:
     """A built index + device / pinned-host buffers for one batch; search through the same entry points at any N."""
 
-    def __init__(self, H, w, xb, xq, nlist, scan_mode=0, coarse_mode=0, d_xb=None):
+    def __init__(self, H, w, xb, xq, nlist, scan_mode=0, coarse_mode=0, d_xb=None, parts=0):
         from vector_indexer_py import _ffi
         torch = H.torch
         self.H, self.k, self.nq, self.d = H, w["k"], len(xq), xq.shape[1]
         t0 = time.perf_counter()
         ix = _ffi.Index(self.d, H.local)
-        if H.world > 1:
-            ix.set_partition(H.rank, H.world)   # BEFORE the build: only the owned part reaches HBM
+        # The ranks form a grid of `parts` index parts x world / parts query groups (vidx_search_multi): parts = world is the
+        # plain sharded index, parts = 1 a replica per GPU with the batch split by query.
+        self.parts = parts if parts and H.world % parts == 0 else H.world
+        if self.parts > 1:
+            ix.set_partition(H.rank % self.parts, self.parts)   # BEFORE the build: only the owned part reaches HBM
         if d_xb is not None:
             ix.build_device(d_xb.data_ptr(), len(d_xb), seed=42, nlist=nlist)
         else:
@@ -545,7 +548,7 @@ def kmeans_block(xb, ncores, with_oracle):
     return out
 
 
-def run_config(H, args, cfg_name, w, nprobe_forced, steps, warmup, rich):
+def run_config(H, args, cfg_name, w, nprobe_forced, steps, warmup, rich, parts=0):
     """Build + sweep + timed steps for one workload; `rich` adds rooflines / CPU legs (the headline config)."""
     torch = H.torch
     cfg = CONFIGS.get(cfg_name, {})
@@ -564,7 +567,7 @@ def run_config(H, args, cfg_name, w, nprobe_forced, steps, warmup, rich):
     else:
         xb, xq = gen_data(w)
         d_xb = None
-    S = Searcher(H, w, xb, xq, w["nlist"], args.scan_mode, args.coarse_mode, d_xb=d_xb)
+    S = Searcher(H, w, xb, xq, w["nlist"], args.scan_mode, args.coarse_mode, d_xb=d_xb, parts=parts)
     # ---- independent ground truth (float64 brute force, none of the library's code) on a sample of the batch ----
     ngt = w["nq"] if w["n"] <= 2_000_000 else 1000
     gt_rows = np.arange(ngt)
@@ -595,10 +598,20 @@ def run_config(H, args, cfg_name, w, nprobe_forced, steps, warmup, rich):
     res["residency"] = {"resident_vectors": int(ix.resident_vectors), "ntotal": int(ix.ntotal),
                         "resident_bytes": int(ix.resident_bytes),
                         "fraction": ix.resident_vectors / max(1, ix.ntotal)}
-    res["parallelism"] = ("1 GPU" if H.world == 1 else
-                          f"{ix.partition_kind} over {H.world} GPUs: each rank holds {100.0 * ix.resident_vectors / max(1, ix.ntotal):.1f} % "
-                          f"of the vectors in HBM, queries replicated, coarse stage split by query, {ix.comm_version} all-gather of "
-                          f"probe lists and of the packed per-GPU top-k + device merge, all inside the library")
+    groups = H.world // S.parts
+    held = f"each rank holds {100.0 * ix.resident_vectors / max(1, ix.ntotal):.1f} % of the vectors in HBM"
+    plumbing = (f"coarse stage split by query, {ix.comm_version if H.world > 1 else ''} all-gather of probe lists and of the packed "
+                f"per-GPU top-k + device merge, all inside the library (vidx_search_multi)")
+    if H.world == 1:
+        res["parallelism"] = "1 GPU"
+    elif groups == 1:
+        res["parallelism"] = f"{ix.partition_kind} over {H.world} GPUs: {held}, queries replicated, {plumbing}"
+    elif S.parts == 1:
+        res["parallelism"] = (f"{H.world} replicas ({held}), the batch split by query into {groups} groups, {plumbing}")
+    else:
+        res["parallelism"] = (f"grid of {S.parts} index parts ({ix.partition_kind}) x {groups} query groups over {H.world} GPUs: {held}, "
+                              f"{plumbing}")
+    res["grid"] = {"index_parts": S.parts, "query_groups": groups}
     return res
 
 
@@ -607,7 +620,12 @@ def run_ours(args):
     torch = H.torch
     w = workload(args)
     peaks, peak_kind = load_peaks()
-    R = run_config(H, args, args.config, w, args.nprobe, args.steps, args.warmup, rich=True)
+    # N > 1: the 0.5 GB index of configs[1] is replicated and the batch split by query (a 1 x N grid); the larger
+    # configurations are sharded N ways.  --parts overrides; the fully sharded configs[1] numbers go under `c2_sharded`.
+    parts = args.parts if args.parts > 0 else (1 if args.config == "c2" else H.world)
+    if H.world % parts != 0:
+        parts = H.world
+    R = run_config(H, args, args.config, w, args.nprobe, args.steps, args.warmup, rich=True, parts=parts)
     S, xb, xq, nprobe = R["S"], R["xb"], R["xq"], R["nprobe"]
     nq, k = w["nq"], w["k"]
     stage, roofline, roofline_hbm = scan_rooflines(S, w, nprobe, peaks, peak_kind)
@@ -630,23 +648,41 @@ def run_ours(args):
         if args.config == "c2" and not args.lean:
             kmeans = kmeans_block(xb, ncores, with_oracle=True)
 
+    # ---- configs[1] again, sharded N ways like the reference's own multi-shard search (N > 1) ---------------------------
+    c2_sharded = None
+    if H.world > 1 and parts != H.world and args.extra != "none":
+        del S
+        R["S"] = None
+        S = None
+        torch.cuda.empty_cache()
+        try:
+            n2 = max(5, args.steps // 2)
+            R2 = run_config(H, args, args.config, w, nprobe, n2, 3, rich=False, parts=H.world)
+            c2_sharded = {"value": R2["qps"], "unit": UNIT, "ms_per_step": R2["ms_dev"] / n2, "e2e": R2["e2e_qps"],
+                          "nprobe": R2["nprobe"], "recall_at_10": R2["recall"], "residency": R2["residency"],
+                          "parallelism": R2["parallelism"], "grid": R2["grid"], "gpu_launches": int(R2["launches"])}
+            R2["S"] = None
+            del R2
+        except Exception as e:
+            c2_sharded = {"error": f"{type(e).__name__}: {e}"}
+
     # ---- the sharded 10M config on the same ranks (N > 1, or on request) -------------------------------------------
     c4 = None
     want_c4 = args.extra == "c4" or (args.extra == "auto" and H.world > 1 and args.config == "c2")
     if want_c4:
-        del S
+        S = None
         R["S"] = None
         torch.cuda.empty_cache()
         try:
             c = CONFIGS["c4"]
             w4 = dict(n=c["n"], d=c["d"], nq=args.nq, k=args.k, nlist=c["nlist"], seed=42)
             t0 = time.perf_counter()
-            R4 = run_config(H, args, "c4", w4, c["nprobe"], max(5, args.steps // 2), 3, rich=False)
+            R4 = run_config(H, args, "c4", w4, c["nprobe"], max(5, args.steps // 2), 3, rich=False, parts=H.world)
             c4 = {"workload": c["name"], "n_gpus": H.world, "value": R4["qps"], "unit": UNIT,
                   "ms_per_step": R4["ms_dev"] / max(5, args.steps // 2), "e2e": R4["e2e_qps"], "nprobe": R4["nprobe"],
                   "recall_at_10": R4["recall"], "recall_sample": "first 1000 queries vs float64 brute force",
                   "nlist_nonempty": int(R4["S"].ix.nlist), "num_shards": int(R4["S"].ix.num_shards),
-                  "index_build_s": R4["S"].build_s, "residency": R4["residency"], "parallelism": R4["parallelism"],
+                  "index_build_s": R4["S"].build_s, "residency": R4["residency"], "parallelism": R4["parallelism"], "grid": R4["grid"],
                   "gpu_launches": int(R4["launches"]), "seconds_total": time.perf_counter() - t0}
             R4["S"] = None
         except Exception as e:  # the headline line must survive a failure of the extra workload
@@ -660,13 +696,13 @@ def run_ours(args):
                 "details": {"recall_at_10": R["recall"], "recall_curve": R["curve"],
                             "ground_truth": "float64 brute force (torch, blocks of 32768 rows), independent of the library",
                             "l2": "inputs larger than L2 (index 512 MB)",
-                            "parallelism": R["parallelism"], "residency": R["residency"], "parity": parity},
-                "e2e": {"value": R["e2e_qps"], "unit": UNIT, "h2d_bytes_per_step": int(xq.nbytes),
+                            "parallelism": R["parallelism"], "grid": R["grid"], "residency": R["residency"], "parity": parity},
+                "e2e": {"value": R["e2e_qps"], "unit": UNIT, "h2d_bytes_per_step": int(xq.nbytes // R["grid"]["query_groups"]),
                         "d2h_bytes_per_step": int(nq * k * 12), "ms_per_step": 1e3 * R["e2e_s"] / args.steps},
                 "gpu_launches": int(R["launches"]), "clocks": R["clocks"], "roofline": roofline, "roofline_hbm": roofline_hbm,
                 "roofline_coarse": coarse,
                 "stages_ms": {kk: stage[kk] for kk in stage if kk.startswith("ms_")},
-                "cpu_baseline": cpu, "kmeans": kmeans, "c4": c4}
+                "cpu_baseline": cpu, "kmeans": kmeans, "c2_sharded": c2_sharded, "c4": c4}
         print(json.dumps(line))
     if H.world > 1:
         H.dist.destroy_process_group()
@@ -690,6 +726,8 @@ def main():
     ap.add_argument("--lean", action="store_true", help="skip the coarse-stage comparison and the k-means block")
     ap.add_argument("--extra", default="auto", choices=["auto", "c4", "none"],
                     help="auto: N > 1 also measures the sharded 10M config (BASELINE configs[3]) and reports it under `c4`")
+    ap.add_argument("--parts", type=int, default=0,
+                    help="N > 1: index parts of the rank grid (N / parts query groups); 0 = 1 for configs[1] (replicas), N otherwise")
     ap.add_argument("--scan-mode", type=int, default=0, help="experiments: vidx_set_scan_mode (0 = auto, what the bench line is quoted on)")
     ap.add_argument("--coarse-mode", type=int, default=0, help="experiments: vidx_set_coarse_mode (0 = auto)")
     ap.add_argument("--profile-window", action="store_true",

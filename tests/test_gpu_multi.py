@@ -135,20 +135,39 @@ def _rank_main(rank, world, port, out_dir):
     xb, xq = bench_data(40000, 48, 500)
     xb[7000:7030] = xb[3]
     ok = True
-    for mode in ("shards", "ranges"):
-        ix = _ffi.Index(48, rank)
-        ix.set_partition_mode(mode)
-        ix.set_partition(rank, world)
-        ix.build(xb)
-        obj = [_ffi.comm_unique_id() if rank == 0 else None]       # rank 0's NCCL id, handed round by the host program
-        dist.broadcast_object_list(obj, src=0)
-        ix.comm_init(rank, world, obj[0])
-        D, I = ix.search_multi(xq, 10, 12)
-        if rank == 0:
-            full = _ffi.Index(48, 0).build(xb)
-            D0, I0 = full.search(xq, 10, 12)
-            ok = ok and same_bits(D, D0) and np.array_equal(I, I0) and ix.resident_vectors < 40000
-        ix.comm_destroy()
+    full = _ffi.Index(48, rank).build(xb) if rank == 0 else None
+    # parts x groups grids: parts = world is the plain sharded index, parts = 1 a replica per rank with the batch split
+    # by query, anything between both at once (4 GPUs: 2 parts x 2 query groups)
+    for parts in sorted({p for p in (world, 1, 2) if world % p == 0}, reverse=True):
+        for mode in ("shards", "ranges") if parts > 1 else ("auto",):
+            ix = _ffi.Index(48, rank)
+            ix.set_partition_mode(mode)
+            ix.set_partition(rank % parts, parts)
+            ix.build(xb)
+            obj = [_ffi.comm_unique_id() if rank == 0 else None]   # rank 0's NCCL id, handed round by the host program
+            dist.broadcast_object_list(obj, src=0)
+            ix.comm_init(rank, world, obj[0])
+            for nq, k, nprobe in ((500, 10, 12), (333, 100, 7), (1, 10, 12)):
+                D, I = ix.search_multi(xq[:nq], k, nprobe)
+                if rank == 0:
+                    D0, I0 = full.search(xq[:nq], k, nprobe)
+                    ok = ok and same_bits(D, D0) and np.array_equal(I, I0)
+            if rank == 0:
+                ok = ok and (ix.resident_vectors < 40000 if parts > 1 else ix.resident_vectors == 40000)
+            ix.comm_destroy()
+    # a communicator that does not fit the partition is refused on every rank (no collective is entered)
+    bad = _ffi.Index(48, rank)
+    bad.set_partition(0, 3)
+    bad.build(xb[:5000])
+    obj = [_ffi.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(obj, src=0)
+    bad.comm_init(rank, world, obj[0])
+    try:
+        bad.search_multi(xq[:8], 10, 4)
+        ok = False
+    except _ffi.VidxError:
+        pass
+    bad.comm_destroy()
     with open(os.path.join(out_dir, f"rank{rank}.txt"), "w") as f:
         f.write("1" if ok else "0")
     dist.destroy_process_group()

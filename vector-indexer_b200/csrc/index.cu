@@ -1271,44 +1271,76 @@ static bool bounds_exchange_enabled() {
     const char* v = getenv("VIDX_BOUNDS_EXCHANGE");
     return v && *v && atoi(v) != 0;
 }
+// The ranks of a communicator form a grid: P = the index partition's world (vidx_set_partition) x G = world / P query groups.
+// Rank r holds index part r % P and answers the queries of group r / P; P = world is the plain sharded index (every rank
+// scans its part for every query), P = 1 a replicated index with the batch split by query.
+struct MultiPlan {
+    int world = 1, rank = 0, parts = 1, groups = 1, group = 0;
+    uint64_t per = 0;        // queries whose probe lists one rank computes
+    uint64_t per_group = 0;  // queries of one group = per * parts
+    uint64_t qlo = 0, qhi = 0;  // this rank's group
+};
+static MultiPlan plan_multi(const Index& ix, uint64_t nq) {
+    if (!ix.comm) throw ApiError(VIDX_ERR_INVALID_INPUT, "vidx_search_multi before vidx_comm_init");
+    MultiPlan m;
+    m.world = comm_world(ix.comm);
+    m.rank = comm_rank(ix.comm);
+    m.parts = ix.part_world;
+    if (m.world % m.parts != 0 || m.rank % m.parts != ix.part_rank)
+        throw ApiError(VIDX_ERR_INVALID_INPUT,
+                       "the communicator does not fit the index partition: world must be a multiple of the partition's world and "
+                       "rank % partition world its rank (vidx_set_partition)");
+    m.groups = m.world / m.parts;
+    m.group = m.rank / m.parts;
+    m.per = ceil_div(nq, (size_t)m.world);
+    m.per_group = m.per * m.parts;
+    m.qlo = std::min<uint64_t>(nq, m.per_group * m.group);
+    m.qhi = std::min<uint64_t>(nq, m.qlo + m.per_group);
+    return m;
+}
+
 static void search_multi_device(Index& ix, SearchCtx& c, const float* d_xq, uint64_t nq, uint64_t k_req, uint64_t nprobe_req,
-                                float* d_D, int64_t* d_I, cudaStream_t st) {
+                                float* d_D, int64_t* d_I, cudaStream_t st, bool xq_is_group_slice = false) {
     if (k_req == 0 || nprobe_req == 0) throw ApiError(VIDX_ERR_INVALID_INPUT, "k and n_probe must be greater than 0");
     if (!ix.built) throw ApiError(VIDX_ERR_OTHER, "index has not been built or loaded");
-    if (!ix.comm) throw ApiError(VIDX_ERR_INVALID_INPUT, "vidx_search_multi before vidx_comm_init");
-    const int world = comm_world(ix.comm), rank = comm_rank(ix.comm);
-    if (world != ix.part_world || rank != ix.part_rank)
-        throw ApiError(VIDX_ERR_INVALID_INPUT, "communicator rank / world differ from the index partition (vidx_set_partition)");
+    const MultiPlan m = plan_multi(ix, nq);
     if (nq == 0) return;
     if (k_req > 0xffffffffull) throw ApiError(VIDX_ERR_UNSUPPORTED, "k too large");
     const uint32_t np = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(nprobe_req, ix.max_n_probe), ix.nlist);
-    const uint64_t per = ceil_div(nq, (size_t)world), lo = std::min<uint64_t>(nq, per * rank), hi = std::min<uint64_t>(nq, lo + per);
+    const uint64_t per = m.per, lo = std::min<uint64_t>(nq, per * m.rank), hi = std::min<uint64_t>(nq, lo + per);
+    // d_xq holds the whole batch, or (host entry point) only the rows of this rank's group
+    const float* xq_group = xq_is_group_slice ? d_xq : d_xq + m.qlo * ix.dim;
     const bool profiling = ix.profiling;
-    // 1. probe lists of my slice -> all ranks
+    // 1. probe lists of my slice (a part of my group's queries) -> all ranks
     c.mg_probes_part.reserve(per * np * 4);
-    c.mg_probes.reserve(per * world * np * 4);
+    c.mg_probes.reserve(per * m.world * np * 4);
     VIDX_CUDA(cudaMemsetAsync(c.mg_probes_part.p, 0xff, per * np * 4, st));
     if (hi > lo)
-        ix.search_device(c, d_xq + lo * ix.dim, hi - lo, 1, np, nullptr, nullptr, nullptr, st, c.mg_probes_part.as<uint32_t>(), nullptr);
-    vidx_search_stats coarse_stats = c.stats;
+        ix.search_device(c, xq_group + (lo - m.qlo) * ix.dim, hi - lo, 1, np, nullptr, nullptr, nullptr, st,
+                         c.mg_probes_part.as<uint32_t>(), nullptr);
+    vidx_search_stats coarse_stats = hi > lo ? c.stats : vidx_search_stats{};
     comm_all_gather(ix.comm, c.mg_probes_part.p, c.mg_probes.p, per * np * 4, st);
-    // 2. local scan of the owned part, results packed for the exchange: D | I | keys
-    const size_t nres = (size_t)nq * k_req;
+    // 2. my group's queries against the part I hold, results packed for the exchange: D | I | keys (per_group rows)
+    const size_t nres = (size_t)m.per_group * k_req;
     const size_t off_I = (nres * 4 + 15) & ~(size_t)15, off_K = off_I + nres * 8, run_bytes = off_K + nres * 8;
     c.mg_pack.reserve(run_bytes);
-    c.mg_all.reserve(run_bytes * world);
+    c.mg_all.reserve(run_bytes * m.world);
     unsigned char* pack = c.mg_pack.as<unsigned char>();
-    ix.search_device(c, d_xq, nq, k_req, np, reinterpret_cast<float*>(pack), reinterpret_cast<int64_t*>(pack + off_I), nullptr, st,
-                     nullptr, nullptr, c.mg_probes.as<uint32_t>(), reinterpret_cast<unsigned long long*>(pack + off_K),
-                     bounds_exchange_enabled() ? ix.comm : nullptr);
-    // 3. exchange + merge
+    if (m.qhi > m.qlo)
+        ix.search_device(c, xq_group, m.qhi - m.qlo, k_req, np, reinterpret_cast<float*>(pack), reinterpret_cast<int64_t*>(pack + off_I),
+                         nullptr, st, nullptr, nullptr, c.mg_probes.as<uint32_t>() + m.qlo * np,
+                         reinterpret_cast<unsigned long long*>(pack + off_K),
+                         bounds_exchange_enabled() && m.groups == 1 ? ix.comm : nullptr);
+    else
+        c.stats = vidx_search_stats{};
+    // 3. exchange + merge: every rank ends up with the whole batch's answer
     if (profiling) VIDX_CUDA(cudaEventRecord(c.events[9], st));
     comm_all_gather(ix.comm, pack, c.mg_all.p, run_bytes, st);
     {
         const unsigned char* all = c.mg_all.as<unsigned char>();
         launch_merge_runs(reinterpret_cast<const float*>(all), run_bytes / 4, reinterpret_cast<const int64_t*>(all + off_I), run_bytes / 8,
-                          reinterpret_cast<const unsigned long long*>(all + off_K), run_bytes / 8, (uint32_t)world, nq, (uint32_t)k_req,
-                          d_D, d_I, st);
+                          reinterpret_cast<const unsigned long long*>(all + off_K), run_bytes / 8, (uint32_t)m.parts, nq, (uint32_t)k_req,
+                          d_D, d_I, st, m.per_group);
     }
     if (profiling) {
         VIDX_CUDA(cudaEventRecord(c.events[7], st));
@@ -1569,10 +1601,15 @@ static void search_host(vidx_index* idx, const float* xq, uint64_t nq, uint64_t 
     c.io_D.reserve(nres * 4);
     c.io_I.reserve(nres * 8);
     c.io_rows.reserve(nres * 4);
-    h2d(c.io_xq.as<float>(), xq, (size_t)nq * ix.dim, c.stream);
-    if (multi)
-        search_multi_device(ix, c, c.io_xq.as<float>(), nq, k, n_probe, c.io_D.as<float>(), c.io_I.as<int64_t>(), c.stream);
-    else
+    if (multi) {
+        // only the rows of this rank's query group are needed on this device
+        const MultiPlan m = plan_multi(ix, nq);
+        h2d(c.io_xq.as<float>(), xq + m.qlo * ix.dim, (size_t)(m.qhi - m.qlo) * ix.dim, c.stream);
+        search_multi_device(ix, c, c.io_xq.as<float>(), nq, k, n_probe, c.io_D.as<float>(), c.io_I.as<int64_t>(), c.stream, true);
+    } else {
+        h2d(c.io_xq.as<float>(), xq, (size_t)nq * ix.dim, c.stream);
+    }
+    if (!multi)
         ix.search_device(c, c.io_xq.as<float>(), nq, k, n_probe, c.io_D.as<float>(), c.io_I.as<int64_t>(),
                          V ? c.io_rows.as<uint32_t>() : nullptr, c.stream, nullptr, nullptr);
     VIDX_CUDA(cudaMemcpyAsync(D, c.io_D.p, nres * 4, cudaMemcpyDeviceToHost, c.stream));

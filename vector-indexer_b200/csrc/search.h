@@ -50,8 +50,9 @@ void launch_alldist_finish(const uint32_t* sel_pos, const float* sel_val, const 
                            const uint64_t* row_ext, float* D, int64_t* I, uint32_t* out_rows, const uint32_t* slot_rank,
                            const uint32_t* list_rowdelta, unsigned long long* out_keys, cudaStream_t st);
 void launch_gather_vectors(const float* vecs, int Dq, int D, const uint32_t* rows, size_t nres, float* out, cudaStream_t st);
-// runs: D at Dr + r * sD, I at Ir + r * sI, optional keys at Kr + r * sK (strides in elements); any k; see merge_runs_kernel
+// runs: D at Dr + r * sD, I at Ir + r * sI, optional keys at Kr + r * sK (strides in elements); any k; see merge_runs_kernel.
+// per_group > 0: queries come in groups of per_group, group g's runs are runs g * nruns .. and hold that group's rows only.
 void launch_merge_runs(const float* Dr, size_t sD, const int64_t* Ir, size_t sI, const unsigned long long* Kr, size_t sK,
-                       uint32_t nruns, uint64_t nq, uint32_t k, float* D, int64_t* I, cudaStream_t st);
+                       uint32_t nruns, uint64_t nq, uint32_t k, float* D, int64_t* I, cudaStream_t st, uint64_t per_group = 0);
 
 }  // namespace vidx

@@ -1067,21 +1067,24 @@ __global__ void interleave_kernel(const float* __restrict__ src, int D, int Dq, 
 // every other run, the number of entries that sort before it (binary search).  Any k.
 __global__ void merge_runs_kernel(const float* __restrict__ Dr, size_t sD, const int64_t* __restrict__ Ir, size_t sI,
                                   const unsigned long long* __restrict__ Kr, size_t sK, uint32_t nruns, uint64_t nq, uint32_t k,
-                                  float* __restrict__ D, int64_t* __restrict__ I) {
+                                  uint64_t per_group, float* __restrict__ D, int64_t* __restrict__ I) {
+    // Query q belongs to query group g = q / per_group; its runs are runs g * nruns .. + nruns - 1, which hold the group's
+    // queries only (row q - g * per_group).  One group (per_group >= nq) is the plain case.
     const size_t per = nq * (size_t)k;
     const float kInf = __int_as_float(0x7f800000);
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < per * nruns; i += (size_t)gridDim.x * blockDim.x) {
         const uint32_t r = (uint32_t)(i / per);
         const size_t e = i - (size_t)r * per, q = e / k;
         const uint32_t t = (uint32_t)(e - q * k);
-        const float d = Dr[(size_t)r * sD + e];
+        const size_t g = q / per_group, row = (q - g * per_group) * k, run0 = g * nruns;
+        const float d = Dr[(run0 + r) * sD + row + t];
         if (!(d < kInf)) continue;  // padding: a returned distance is never +inf
-        const unsigned long long key = Kr ? Kr[(size_t)r * sK + e] : 0ull;
+        const unsigned long long key = Kr ? Kr[(run0 + r) * sK + row + t] : 0ull;
         uint32_t pos = t;
         for (uint32_t r2 = 0; r2 < nruns && pos < k; r2++) {
             if (r2 == r) continue;
-            const float* d2 = Dr + (size_t)r2 * sD + q * k;
-            const unsigned long long* k2 = Kr ? Kr + (size_t)r2 * sK + q * k : nullptr;
+            const float* d2 = Dr + (run0 + r2) * sD + row;
+            const unsigned long long* k2 = Kr ? Kr + (run0 + r2) * sK + row : nullptr;
             uint32_t lo = 0, hi = k;  // first entry of run r2 that does NOT sort before (d, key)
             while (lo < hi) {
                 const uint32_t mid = (lo + hi) >> 1;
@@ -1094,7 +1097,7 @@ __global__ void merge_runs_kernel(const float* __restrict__ Dr, size_t sD, const
         }
         if (pos < k) {
             D[q * k + pos] = d;
-            I[q * k + pos] = Ir[(size_t)r * sI + e];
+            I[q * k + pos] = Ir[(run0 + r) * sI + row + t];
         }
     }
 }
@@ -1254,12 +1257,13 @@ void launch_gather_vectors(const float* vecs, int Dq, int D, const uint32_t* row
     VIDX_LAUNCHED();
 }
 void launch_merge_runs(const float* Dr, size_t sD, const int64_t* Ir, size_t sI, const unsigned long long* Kr, size_t sK,
-                       uint32_t nruns, uint64_t nq, uint32_t k, float* D, int64_t* I, cudaStream_t st) {
+                       uint32_t nruns, uint64_t nq, uint32_t k, float* D, int64_t* I, cudaStream_t st, uint64_t per_group) {
     if (!nq || !k) return;
+    if (per_group == 0 || per_group > nq) per_group = nq;
     launch_pad_output(D, I, nullptr, nullptr, nq, 0, k, st);  // slots nobody claims: fewer than k candidates in all
     const size_t n = nq * (size_t)k * nruns;
     const unsigned grid = (unsigned)std::min<size_t>(ceil_div(n, 256), (size_t)num_sms() * 32);
-    merge_runs_kernel<<<grid, 256, 0, st>>>(Dr, sD, Ir, sI, Kr, sK, nruns, nq, k, D, I);
+    merge_runs_kernel<<<grid, 256, 0, st>>>(Dr, sD, Ir, sI, Kr, sK, nruns, nq, k, per_group, D, I);
     VIDX_LAUNCHED();
 }
 
