@@ -527,17 +527,21 @@ def coarse_roofline(S, nprobe, peaks, peak_kind):
 def kmeans_block(xb, ncores, with_oracle):
     """BASELINE configs[2]: mini-batch k-means 1M x 128, k = 4096, 20 iterations, hierarchical final assignment."""
     from vector_indexer_py import _ffi
-    _ffi.kmeans_last_profile()
-    t0 = time.perf_counter()
-    c, labels, iters = _ffi.kmeans_mini_batch(xb, 4096, 20, seed=42)
-    gpu_s = time.perf_counter() - t0
-    host_rng_s, device_wait_s = _ffi.kmeans_last_profile()
+    runs = []
+    for _ in range(3):  # the first run pays the workspace and pinned-buffer allocations: reported, not the headline
+        _ffi.kmeans_last_profile()
+        t0 = time.perf_counter()
+        c, labels, iters = _ffi.kmeans_mini_batch(xb, 4096, 20, seed=42)
+        runs.append((time.perf_counter() - t0,) + tuple(_ffi.kmeans_last_profile()))
+    gpu_s, host_rng_s, device_wait_s = [sum(r[i] for r in runs[1:]) / 2 for i in range(3)]
     out = {"workload": "configs[2]: mini-batch k-means 1Mx128 k=4096, 20 iterations + hierarchical assignment of all points",
-           "gpu_seconds": gpu_s, "includes": "H2D of the data set (512 MB) and D2H of centroids + labels", "iterations": iters,
+           "gpu_seconds": gpu_s, "gpu_seconds_first_call": runs[0][0], "runs": "3 calls; gpu_seconds = mean of calls 2 and 3",
+           "includes": "H2D of the data set (512 MB) and D2H of centroids + labels", "iterations": iters,
            "split_seconds": {"host_serial_random_stream": host_rng_s, "blocked_on_device": device_wait_s,
                              "other_host_and_copies": max(0.0, gpu_s - host_rng_s - device_wait_s)},
-           "split_note": "the reference's semantics keep 20 Fisher-Yates shuffles of 1M indices (kmeans.rs:722-726) and 4095 sequential "
-                         "50 000-term prefix sums (k-means++, :285-287) serial on the host; the device does every distance / argmin / mean"}
+           "split_note": "the reference's semantics keep the draws of 20 Fisher-Yates shuffles of 1M indices (kmeans.rs:722-726) and 4095 "
+                         "sequential 50 000-term prefix sums (k-means++, :270-287) serial on the host; the device does every distance / "
+                         "argmin / mean"}
     if with_oracle:
         import oracle as O
         t0 = time.perf_counter()

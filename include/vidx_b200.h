@@ -175,8 +175,9 @@ uint64_t vidx_calculate_max_iterations(uint64_t num_vectors);
 /* The random stream every build decision is drawn from (csrc/rng.hpp: rand 0.8.5 StdRng::seed_from_u64 = ChaCha12 behind
  * rand_core's BlockRng; call sites src/kmeans.rs:31,80,170,240,591), host only, so that it can be pinned against known-answer
  * vectors without a GPU.  After `skip_u32` next_u32 draws: kind 0 = n x next_u32, 1 = n x next_u64, 2 = n x gen_range(0..arg)
- * on usize, 3 = (0..arg).shuffle (n == arg), 4 = (0..arg).choose_multiple(n).  vidx_stdrng_weighted: n samples of
- * WeightedIndex::new(weights) (f32). */
+ * on usize, 3 = (0..arg).shuffle (n == arg), 4 = (0..arg).choose_multiple(n), 5 = the first n entries of (0..arg).shuffle the
+ * way the mini-batch loop takes them (every draw made, no n-element array permuted) followed by one next_u32 in out[n].
+ * vidx_stdrng_weighted: n samples of WeightedIndex::new(weights) (f32). */
 int vidx_stdrng_draw(uint64_t seed, uint64_t skip_u32, int kind, uint64_t arg, uint64_t n, uint64_t* out);
 int vidx_stdrng_weighted(uint64_t seed, const float* weights, uint64_t nw, uint64_t n, uint64_t* out);
 

@@ -128,3 +128,23 @@ def test_product_build_and_save_reproduce_the_reference_files(ffi, tmp_path):
     assert sorted(os.listdir(tmp_path / "shards")) == names
     for n in names:
         assert (tmp_path / "shards" / n).read_bytes() == bytes.fromhex(files[n]), n
+
+
+@pytest.mark.parametrize("n,head,seed", [(1000, 10, 7), (100000, 256, 42), (4097, 256, 3), (5000, 1, 11), (300, 256, 5), (2, 1, 1),
+                                         (50000, 1024, 9), (1000000, 256, 42)])
+def test_shuffle_head_equals_the_head_of_the_full_shuffle(ffi, n, head, seed):
+    """The mini-batch loop (sample_batch, kmeans.rs:722-726) keeps the first 256 entries of a shuffle of all n indices; the
+    product makes every draw but does not permute an n-element array.  Same head, and the stream ends at the same word."""
+    full = ffi.stdrng_draw(seed, "shuffle", n, arg=n)
+    got = ffi.stdrng_draw(seed, "shuffle_head", head, arg=n)
+    assert got[:head].tolist() == full[:head].tolist()
+    # the word after the shuffle: replay the stream
+    words = ffi.stdrng_draw(seed, "u32", 3 * n + 64)
+    # every accepted or rejected draw is one u32: count them with the reference rule (widening multiply, zone rejection)
+    pos = 0
+    for i in range(n, 1, -1):
+        zone = ((i << (32 - i.bit_length())) - 1) & 0xffffffff
+        while (int(words[pos]) * i) & 0xffffffff > zone:
+            pos += 1
+        pos += 1
+    assert int(got[head]) == int(words[pos])

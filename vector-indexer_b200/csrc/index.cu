@@ -1852,7 +1852,15 @@ int vidx_stdrng_draw(uint64_t seed, uint64_t skip_u32, int kind, uint64_t arg, u
                 for (size_t i = 0; i < c.size(); i++) out[i] = c[i];
                 break;
             }
-            default: throw ApiError(VIDX_ERR_INVALID_INPUT, "kind must be 0..4");
+            case 5: {                                                // first n of (0..arg).shuffle, then one more word
+                require(arg <= 0xffffffffull && n <= arg, VIDX_ERR_INVALID_INPUT, "shuffle head: bad sizes");
+                std::vector<uint32_t> head, scratch;
+                r.shuffle_head((uint32_t)arg, (uint32_t)n, head, scratch);
+                for (size_t i = 0; i < head.size(); i++) out[i] = head[i];
+                out[n] = r.next_u32();                               // where the stream stands afterwards
+                break;
+            }
+            default: throw ApiError(VIDX_ERR_INVALID_INPUT, "kind must be 0..5");
         }
     });
 }

@@ -232,21 +232,17 @@ void DeviceKMeans::pp_init(uint32_t k, uint64_t seed, float* d_cents) {
         h2d(m.mind.as<float>(), inf.data(), mcount, st_);
         VIDX_SYNC(st_);
     }
-    std::vector<float> w(mcount), cum;
+    std::vector<float> cum;
     for (uint64_t i = 1; i < actual_k; i++) {
         // NB kmeans.rs:268/:431-436: rows 0..m of the data, also in the sampled variant.
         launch_min_dist(d_data_, D_, (uint32_t)mcount, d_cents + (i - 1) * D_, m.mind.as<float>(), st_);
         d2h(h_min, m.mind.as<float>(), mcount, st_);
-        Tick tk(t_km_profile.host_rng_s);  // the draw: sequential f32 sums over all weights (WeightedIndex, kmeans.rs:285-287)
-        float total = 0.0f;
-        for (uint64_t t = 0; t < mcount; t++) {
-            w[t] = h_min[t] * h_min[t];
-            total += w[t];
-        }
+        Tick tk(t_km_profile.host_rng_s);  // the draw: one sequential f32 chain over all weights (WeightedIndex, kmeans.rs:270-287)
+        const float total = ChaCha12Rng::square_prefix(h_min, mcount, cum);
         if (total == 0.0f) {
             copy_cent_row((uint32_t)rng.below_u64(i), (uint32_t)i);
         } else {
-            size_t s = rng.weighted_pick(w.data(), mcount, total, cum);
+            size_t s = rng.pick_from_prefix(cum, total);
             copy_data_row(sampled ? sample_idx[s] : s, (uint32_t)i);
         }
     }
@@ -296,7 +292,7 @@ uint64_t DeviceKMeans::mini_batch(uint32_t k, uint64_t max_iters, float tol, uin
     std::vector<uint64_t> counts(k, 0);
     m.prev.reserve((size_t)k * D_ * 4);
     VIDX_CUDA(cudaMemcpyAsync(m.prev.p, d_cents, (size_t)k * D_ * 4, cudaMemcpyDeviceToDevice, st_));
-    std::vector<uint32_t> idx(n_);
+    std::vector<uint32_t> idx, shuffle_scratch;
     const uint32_t b = (uint32_t)std::min<uint64_t>(batch_size, n_);
     m.batch.reserve((size_t)b * D_ * 4);
     m.labels32.reserve((size_t)std::max<uint64_t>(b, 1) * 4);
@@ -305,10 +301,9 @@ uint64_t DeviceKMeans::mini_batch(uint32_t k, uint64_t max_iters, float tol, uin
     uint64_t it = 0;
     while (it < max_iters) {
         // sample_batch (kmeans.rs:722-726): shuffle all n indices, take the first b
-        std::iota(idx.begin(), idx.end(), 0u);
         {
-            Tick t(t_km_profile.host_rng_s);  // sample_batch: Fisher-Yates over ALL n indices (kmeans.rs:722-726)
-            rng.shuffle(idx.data(), idx.size());
+            Tick t(t_km_profile.host_rng_s);  // sample_batch: every draw of a Fisher-Yates over ALL n indices (kmeans.rs:722-726)
+            rng.shuffle_head((uint32_t)n_, b, idx, shuffle_scratch);
         }
         m.idx_a.reserve((size_t)b * 4);
         h2d(m.idx_a.as<uint32_t>(), idx.data(), b, st_);

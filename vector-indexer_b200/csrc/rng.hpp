@@ -6,12 +6,16 @@
 //
 // This is an independent implementation: the test oracle under oracle/ carries its own.
 #pragma once
+#include <algorithm>
 #include <array>
 #include <cstdint>
 #include <cstring>
 #include <vector>
 
 namespace vidx {
+
+// csrc/chacha_blocks.cpp: eight consecutive ChaCha12 blocks (stream id 0), blocks as SIMD lanes
+void chacha12_blocks8(const uint32_t key[8], uint64_t block0, uint32_t* out);
 
 class ChaCha12Rng {
   public:
@@ -92,6 +96,44 @@ class ChaCha12Rng {
         }
     }
 
+    // The first `head` entries of (0..n).shuffle() -- all sample_batch keeps (kmeans.rs:722-726) -- without touching an
+    // n-element array at random.  Every draw is made, in order, so the stream ends where the full shuffle leaves it
+    // (draw i goes to J[i]: sequential writes).  The last `head` swaps only move entries below `head`; what stands there
+    // before them is found by following each of those positions BACK through the earlier swaps: going back, a followed
+    // position p is only ever moved by a swap (i - 1, J[i]) with J[i] == p, to i - 1 -- upward, onto a position no other
+    // swap still to be visited can name as i - 1 -- so one bitmap test per swap finds the few (about head * ln(n / head))
+    // swaps that matter.  The array starts as the identity, so the value is the position the walk ends on.
+    void shuffle_head(uint32_t n, uint32_t head, std::vector<uint32_t>& out, std::vector<uint32_t>& scratch) {
+        out.resize(std::min(n, head));
+        if (n < 2 || head > 1024 || (uint64_t)head * 16 > n) {  // short arrays, long heads (the walk looks a position up linearly)
+            scratch.resize(n);
+            for (uint32_t i = 0; i < n; i++) scratch[i] = i;
+            shuffle(scratch.data(), n);
+            std::copy(scratch.begin(), scratch.begin() + out.size(), out.begin());
+            return;
+        }
+        std::vector<uint32_t>& J = scratch;
+        J.resize((size_t)n + 1);
+        for (uint32_t i = n; i > 1; --i) J[i] = below_u32(i);  // swap (i - 1, J[i]), i = n .. 2
+        std::vector<uint64_t> bits(((size_t)n + 63) / 64, 0);
+        std::vector<uint32_t> pos(head);
+        for (uint32_t t = 0; t < head; t++) {
+            pos[t] = t;
+            bits[t >> 6] |= 1ull << (t & 63);
+        }
+        for (uint32_t i = head + 1; i <= n; ++i) {  // backwards in time over the swaps that precede the last `head`
+            const uint32_t j = J[i];
+            if (!((bits[j >> 6] >> (j & 63)) & 1ull) || j == i - 1) continue;
+            uint32_t t = 0;
+            while (pos[t] != j) ++t;
+            pos[t] = i - 1;
+            bits[j >> 6] &= ~(1ull << (j & 63));
+            bits[(i - 1) >> 6] |= 1ull << ((i - 1) & 63);
+        }
+        for (uint32_t i = head; i > 1; --i) std::swap(pos[i - 1], pos[J[i]]);  // the last swaps, forward in time
+        std::copy(pos.begin(), pos.end(), out.begin());
+    }
+
     // IteratorRandom::choose_multiple over 0..n
     std::vector<uint32_t> choose_multiple(uint32_t n, uint32_t amount) {
         std::vector<uint32_t> r;
@@ -117,6 +159,22 @@ class ChaCha12Rng {
             cum[i - 1] = run;
             run += w[i];
         }
+        return pick_from_prefix(cum, total);
+    }
+    // The k-means++ draw (kmeans.rs:270-287) squares the distances, sums the weights (`weights.iter().sum()`, the zero
+    // test) and lets WeightedIndex::new sum them again for its prefix table.  Both sums are the same sequential chain
+    // (0 + w0 = w0 for w0 >= 0), so ONE pass yields the prefix sums and the total: the chain of n dependent f32 adds is the
+    // floor of this step and is walked once instead of twice.  Returns the total; n >= 1.
+    static float square_prefix(const float* d, size_t n, std::vector<float>& cum) {
+        cum.resize(n - 1);
+        float run = d[0] * d[0];
+        for (size_t i = 1; i < n; ++i) {
+            cum[i - 1] = run;
+            run += d[i] * d[i];
+        }
+        return run;
+    }
+    size_t pick_from_prefix(const std::vector<float>& cum, float total) {
         // Uniform::new(0, total): shrink scale until the largest sample stays below total
         float scale = total;
         const float max_unit = 0.99999988079071044921875f;  // 1 - 2^-23
@@ -139,31 +197,13 @@ class ChaCha12Rng {
   private:
     static constexpr uint64_t kPcgMul = 6364136223846793005ull;
     static constexpr uint64_t kPcgInc = 11634580027462260723ull;
-    static constexpr int kBufWords = 64;  // four 16-word blocks per refill
+    static constexpr int kBufWords = 128;  // eight 16-word blocks per refill (rand_chacha buffers four: the word order is the same)
 
     static uint32_t rotr(uint32_t v, unsigned r) { r &= 31; return r ? (v >> r) | (v << (32 - r)) : v; }
-    static uint32_t rotl(uint32_t v, unsigned r) { return (v << r) | (v >> (32 - r)); }
-
-    static void quarter(std::array<uint32_t, 16>& s, int a, int b, int c, int d) {
-        s[a] += s[b]; s[d] = rotl(s[d] ^ s[a], 16);
-        s[c] += s[d]; s[b] = rotl(s[b] ^ s[c], 12);
-        s[a] += s[b]; s[d] = rotl(s[d] ^ s[a], 8);
-        s[c] += s[d]; s[b] = rotl(s[b] ^ s[c], 7);
-    }
 
     void refill() {
-        for (int blk = 0; blk < 4; ++blk) {
-            std::array<uint32_t, 16> init = {0x61707865u, 0x3320646eu, 0x79622d32u, 0x6b206574u,
-                                             key_[0], key_[1], key_[2], key_[3], key_[4], key_[5], key_[6], key_[7],
-                                             static_cast<uint32_t>(block_), static_cast<uint32_t>(block_ >> 32), 0u, 0u};
-            std::array<uint32_t, 16> s = init;
-            for (int dr = 0; dr < 6; ++dr) {  // 12 rounds = 6 column+diagonal double rounds
-                quarter(s, 0, 4, 8, 12); quarter(s, 1, 5, 9, 13); quarter(s, 2, 6, 10, 14); quarter(s, 3, 7, 11, 15);
-                quarter(s, 0, 5, 10, 15); quarter(s, 1, 6, 11, 12); quarter(s, 2, 7, 8, 13); quarter(s, 3, 4, 9, 14);
-            }
-            for (int i = 0; i < 16; ++i) buf_[blk * 16 + i] = s[i] + init[i];
-            ++block_;
-        }
+        chacha12_blocks8(key_.data(), block_, buf_);
+        block_ += 8;
     }
 
     std::array<uint32_t, 8> key_{};

@@ -402,10 +402,13 @@ def read_vector_file(path, dim):
 
 
 def stdrng_draw(seed, kind, n, arg=0, skip_u32=0):
-    """The build's random stream (csrc/rng.hpp), host only.  kind: "u32", "u64", "gen_range", "shuffle", "choose_multiple"."""
-    out = np.zeros(max(n, 1), np.uint64)
-    check(lib().vidx_stdrng_draw(seed, skip_u32, ["u32", "u64", "gen_range", "shuffle", "choose_multiple"].index(kind), arg, n, _u(out)))
-    return out[:n]
+    """The build's random stream (csrc/rng.hpp), host only.  kind: "u32", "u64", "gen_range", "shuffle", "choose_multiple",
+    "shuffle_head" (first n of a shuffle of 0..arg as the mini-batch loop takes them, plus the next u32 of the stream)."""
+    kinds = ["u32", "u64", "gen_range", "shuffle", "choose_multiple", "shuffle_head"]
+    extra = 1 if kind == "shuffle_head" else 0
+    out = np.zeros(max(n + extra, 1), np.uint64)
+    check(lib().vidx_stdrng_draw(seed, skip_u32, kinds.index(kind), arg, n, _u(out)))
+    return out[:n + extra]
 
 
 def stdrng_weighted(seed, weights, n):
