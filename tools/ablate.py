@@ -4,13 +4,14 @@ import os, sys
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), '..', 'vector-indexer_b200'))
 import numpy as np, torch
 from vector_indexer_py import _ffi
-n, d, nq, k = 1_000_000, 128, 10_000, 10
+n, d, nq, k = 1_000_000, 128, int(os.environ.get('NQ', 10_000)), 10
+variants = [int(v) for v in os.environ.get('VARIANTS', '0,1,2').split(',')]
 rng = np.random.default_rng(42)
 xb = rng.standard_normal((n, d)).astype(np.float32); xq = rng.standard_normal((nq, d)).astype(np.float32)
 ix = _ffi.Index(d, 0).build(xb, seed=42, nlist=1024)
 ts = torch.cuda.Stream(); torch.cuda.set_stream(ts)
 d_xq = torch.from_numpy(xq).cuda(); d_D = torch.empty((nq, k), device='cuda'); d_I = torch.empty((nq, k), dtype=torch.int64, device='cuda')
-for pair in (0, 1, 2):   # 0 = default kernel, 1 = CTA pair, 2 = query tile in tensor memory
+for pair in variants:   # 0 = default kernel, 1 = CTA pair, 2 = query tile in tensor memory
     for fl in (0, 8, 2, 6):
         os.environ["VIDX_TC_PAIR"] = str(int(pair == 1)); os.environ["VIDX_TC_TSA"] = str(int(pair == 2)); os.environ["VIDX_TC_FLAGS"] = str(fl)
         ix.set_profiling(True)

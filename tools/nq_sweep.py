@@ -13,9 +13,9 @@ ix = _ffi.Index(d, 0).build(xb, seed=42, nlist=1024)
 ts = torch.cuda.Stream(); torch.cuda.set_stream(ts)
 d_xq = torch.from_numpy(xq).cuda()
 d_D = torch.empty((10_000, k), device='cuda'); d_I = torch.empty((10_000, k), dtype=torch.int64, device='cuda')
-for nq in (10_000, 5_000, 2_500, 1_250, 625):
+for nq in [int(v) for v in os.environ.get('NQS', '10000,5000,2500,1250,625').split(',')]:
     base = None
-    for sm in (0, 2, 3):
+    for sm in [int(v) for v in os.environ.get('SCAN_MODES', '0,2,3').split(',')]:
         ix.set_scan_mode(sm)
         run = lambda: ix.search_device(d_xq.data_ptr(), nq, k, npb, d_D.data_ptr(), d_I.data_ptr(), ts.cuda_stream)
         for _ in range(3): run()

@@ -600,6 +600,8 @@ constexpr bool kTcPairDefault = false;
 constexpr bool kTcTsaDefault = false;
 constexpr double kTcPairMinQueriesPerList = 256.0;  // mean queries per list from which the pair kernel is used
 constexpr uint64_t kSmallBatchQueries = 512;
+constexpr uint64_t kLocalSetsQueries = 512;
+constexpr uint64_t kWideSeedQueries = 2048;
 constexpr double kBoundsPassMaxUnitsPerSm = 256.0;  // ~0.15 ms of tensor work per pass
 constexpr uint64_t kBoundsPassMaxTiles = 2048;  // auto mode: bounds pass first when a query probes at most this many 128-vector tiles
 // list scan, seeded flavour: a bounds pass over the heads of each query's (up to) kSeedRanks nearest lists,
@@ -761,13 +763,16 @@ void Index::search_device(SearchCtx& ctx, const float* d_xq, uint64_t nq, uint64
     // stay CTA-local in the main pass -- merging them under the per-query locks at every item end serialised the whole
     // GPU (0.80 -> 0.13 ms for the 128-query bench batch) -- and (b) the bounds launch looks at 8x more tiles per query,
     // which costs little with so few rows and keeps the survivor count down without the shared sets.
-    const bool small_batch = nq <= kSmallBatchQueries;
+    auto env_u64 = [](const char* name, uint64_t dflt) { const char* v = getenv(name); return v && *v ? (uint64_t)strtoull(v, nullptr, 0) : dflt; };
+    const bool small_batch = nq <= env_u64("VIDX_SMALL_BATCH", kSmallBatchQueries);          // block-per-query finalize
+    const bool local_sets = nq <= env_u64("VIDX_LOCAL_SETS_MAX", kLocalSetsQueries);         // (a)
+    const bool wide_seed = nq <= env_u64("VIDX_WIDE_SEED_MAX", kWideSeedQueries);            // (b)
     const uint32_t seed_ranks = std::max<uint32_t>(1, std::min<uint32_t>(np, kSeedRanks));
-    const uint32_t seed_rank_tiles = (small_batch ? 8u * kSeedBoundTiles : kSeedBoundTiles) / seed_ranks;
+    const uint32_t seed_rank_tiles = (wide_seed ? 8u * kSeedBoundTiles : kSeedBoundTiles) / seed_ranks;
     const uint32_t seed_row = seed_ranks * seed_rank_tiles * 4;  // minima per query of the seeding bounds pass
     const uint64_t dump_tiles_per_q = tile_prefix[std::min<size_t>(np, tile_prefix.size() - 1)];
     // tuning knobs for A/B runs on the GPU box (environment, read per search; unset = the defaults the bench is quoted on)
-    const uint32_t tc_flags = [&] { const char* v = getenv("VIDX_TC_FLAGS"); return v && *v ? (uint32_t)strtoul(v, nullptr, 0) : (small_batch ? 1u : 0u); }();
+    const uint32_t tc_flags = [&] { const char* v = getenv("VIDX_TC_FLAGS"); return v && *v ? (uint32_t)strtoul(v, nullptr, 0) : (local_sets ? 1u : 0u); }();
     const uint64_t bounds_pass_max_tiles = [] { const char* v = getenv("VIDX_BOUNDS_MAX_TILES"); return v && *v ? (uint64_t)strtoull(v, nullptr, 0) : kBoundsPassMaxTiles; }();
     // The bounds-pass-first flavour runs the tensor work twice: worth it only while one pass is short -- few tiles per
     // query AND few (query tile x list tile) units per SM.  (A quarter of the bench index is 1560 tiles per query but 800

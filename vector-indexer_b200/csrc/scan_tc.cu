@@ -74,6 +74,7 @@ constexpr int kTcMaxChunkTiles = VIDX_CHUNK_TILES; // tiles per work item: chose
 __host__ __device__ constexpr int tc_queue_cap(int kr) { return kr > 16 ? 128 : 512; }
 __host__ __device__ constexpr int tc_stage_cap(int kr) { return kr > 16 ? 144 : 512; }
 constexpr int kTcAccStages = 4;      // accumulator tiles in TMEM
+constexpr int kTcMergeTries = 4;     // end-of-item merge of a row's set into the shared one: attempts at the row's lock
 constexpr uint32_t kTcACol = 384;    // A-in-TMEM variant: three accumulator stages, then the query tile (4 columns per 8 dims), then
                                      // the 8 columns of the norm step's A operand
 constexpr int kTcTmemCols = 512;     // 4 accumulator stages x 128 columns
@@ -1368,8 +1369,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(const __grid_con
                       g[i + 1] = lo_v;
                   }
               };
+              // The row's own set (what it read at set-up plus this item's finds) already bounds its k-th best: publish that
+              // without the lock.  The union with the other CTAs' sets is tighter still, but it is only worth a short wait:
+              // with few query tiles a dozen CTAs finish items of the SAME rows at the same moment, and queueing on the rows'
+              // locks (and the set-up's seqlock reads behind them) cost more than the survivors a merge saves -- a row
+              // whose lock stays taken skips the merge; its values are not lost to the bound, only to the union.
+              if (r[0] < kInf) {
+                  float U = fmaxf((r[0] + delta) * tInvS + base_t, 0.0f);
+                  U = U + 1e-5f * U;
+                  atomicMin(&p.gthr_bits[q], __float_as_uint(U));
+              }
+              const int merge_tries = (p.flags >> 4) ? (int)(p.flags >> 4) : kTcMergeTries;  // (flags bits 4+: A/B override)
               bool done = false;
-              while (!done) {
+              for (int tries = 0; !done && tries < merge_tries; tries++) {
                 // the critical section runs INSIDE the retry loop: a lane that holds a lock always finishes
                 // and releases it before it waits for the other lanes of its warp
                 if (atomicCAS(&p.glock[q], 0u, 1u) != 0u) {

@@ -12,7 +12,8 @@ import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
-LIB_PATH = os.path.join(_ROOT, "lib", "libvidx_b200.so")
+# VIDX_B200_LIB: another build of the same library (the role-timer build of tools/README.md), experiments only
+LIB_PATH = os.environ.get("VIDX_B200_LIB") or os.path.join(_ROOT, "lib", "libvidx_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_ROOT), "include", "vidx_b200.h")
 
 VIDX_OK, INVALID_INPUT, NOT_FOUND, INVALID_DATA, OTHER, CUDA, UNSUPPORTED = range(7)
