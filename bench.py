@@ -79,6 +79,17 @@ def recall_at_k(I, gt):
     return hit / gt.size
 
 
+def faiss_recalls(I, gt):
+    """bench_all_ivf.py:283-363 (the Faiss convention): R@r = share of queries whose TRUE nearest neighbour is among the
+    first r results."""
+    nn = gt[:, :1]
+    return {f"R@{r}": float((I[:, :r] == nn).any(axis=1).mean()) for r in (1, 10) if r <= I.shape[1]}
+
+
+def curve_point(p, I, gt):
+    return {"nprobe": p, "recall_at_10": recall_at_k(I, gt), **faiss_recalls(I, gt)}
+
+
 def brute_force_topk_f64(xb, xq, k, device="cuda", block=32768):
     """Independent ground truth (replaces faiss IndexFlatL2 of bench_all_ivf.py:75-78): exact float64 squared L2 by
     blocks with torch on the GPU -- none of the library's code.  xb may be a host array or a device tensor.
@@ -418,12 +429,12 @@ def recall_sweep(S, gt, gt_rows, full_curve, forced):
     curve, nprobe, p = [], None, 1
     if forced and not full_curve:  # a config that fixes n_probe (BASELINE configs[3], [4]): measure the recall there only
         S.search_dev(min(forced, S.ix.nlist))
-        return forced, [{"nprobe": forced, "recall_at_10": recall_at_k(S.result_ids()[gt_rows], gt)}]
+        return forced, [curve_point(forced, S.result_ids()[gt_rows], gt)]
     while True:
         p = min(p, S.ix.nlist)
         S.search_dev(p)
-        r = recall_at_k(S.result_ids()[gt_rows], gt)
-        curve.append({"nprobe": p, "recall_at_10": r})
+        curve.append(curve_point(p, S.result_ids()[gt_rows], gt))
+        r = curve[-1]["recall_at_10"]
         if nprobe is None and r >= 0.9:
             nprobe = p
             if not full_curve:

@@ -252,7 +252,9 @@ int vidx_merge_topk_keyed_device(int device, const float* d_D_runs, const int64_
 /* The exchange step inside the library (north_star 4; replaces join_all + concat + sort, src/ivf_index.rs:249-266):
  * one NCCL communicator per handle, one rank per GPU.  Rank 0 obtains an id (vidx_comm_unique_id), the host program
  * hands it to every rank (any channel: MPI, a file, torch.distributed), every rank calls vidx_comm_init -- collectively.
- * rank / world must equal the handle's partition.  NCCL is bound with dlopen("libnccl.so.2") at the first call. */
+ * The communicator's world must be a multiple of the handle's partition world P (vidx_set_partition) and rank % P the
+ * partition rank: the ranks then form a grid of P index parts x world / P query groups (below).  NCCL is bound with
+ * dlopen("libnccl.so.2") at the first call. */
 #define VIDX_COMM_ID_BYTES 128
 int vidx_comm_unique_id(uint8_t* out /* VIDX_COMM_ID_BYTES */);
 int vidx_comm_init(vidx_index* idx, int rank, int world, const uint8_t* unique_id);
@@ -261,7 +263,11 @@ const char* vidx_comm_version(const vidx_index* idx); /* "NCCL x.y.z", "" before
 /* Collective search: every rank passes the SAME queries and gets the FULL answer.  Coarse quantization is split by
  * query (all-gather of the probe lists), every rank scans what it owns, the per-rank top-k runs are exchanged with ONE
  * packed all-gather (distance | id | (probe rank, global row) key) and merged on the device by (distance, key) -- the
- * result is bit-identical to a single-GPU vidx_search, ties included, for any k.  Host buffers / device buffers. */
+ * result is bit-identical to a single-GPU vidx_search, ties included, for any k.  Host buffers / device buffers.
+ * Grid: with a communicator of world = P x G ranks over a P-way partition, rank r holds index part r % P and answers only
+ * the queries of group r / P (a contiguous slice of the batch; the host entry point uploads only that slice); P = world
+ * is the plain sharded index, P = 1 (an unpartitioned handle on every rank) a replicated index with the batch split by
+ * query -- what a small index on many GPUs wants. */
 int vidx_search_multi(vidx_index* idx, const float* xq, uint64_t nq, uint64_t k, uint64_t n_probe, float* D, int64_t* I);
 int vidx_search_multi_device(vidx_index* idx, const float* d_xq, uint64_t nq, uint64_t k, uint64_t n_probe, float* d_D,
                              int64_t* d_I, void* stream);
