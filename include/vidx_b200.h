@@ -248,6 +248,14 @@ int vidx_search_local_device(vidx_index* idx, const float* d_xq, uint64_t nq, ui
                              int64_t* d_I, uint64_t* d_keys, void* stream);
 int vidx_merge_topk_keyed_device(int device, const float* d_D_runs, const int64_t* d_I_runs, const uint64_t* d_K_runs,
                                  uint32_t nruns, uint64_t nq, uint64_t k, float* d_D, int64_t* d_I, void* stream);
+/* The rank grid of vidx_search_multi on its own (host only): which queries rank `rank` of `world` answers when the index is
+ * cut into `parts` parts (world % parts == 0).  out[0] = query group (rank / parts), out[1], out[2] = the group's query
+ * range [lo, hi), out[3] = queries per group (the row count of a packed run), out[4], out[5] = the range whose probe lists
+ * this rank computes.  vidx_merge_topk_grid_device: the merge behind it -- run g * parts + p (per_group x k entries each,
+ * run-major) holds part p's results for the queries of group g; output = the whole batch. */
+int vidx_grid_plan(uint64_t nq, int world, int parts, int rank, uint64_t* out /* 6 */);
+int vidx_merge_topk_grid_device(int device, const float* d_D_runs, const int64_t* d_I_runs, const uint64_t* d_K_runs, uint32_t parts,
+                                uint64_t per_group, uint64_t nq, uint64_t k, float* d_D, int64_t* d_I, void* stream);
 
 /* The exchange step inside the library (north_star 4; replaces join_all + concat + sort, src/ivf_index.rs:249-266):
  * one NCCL communicator per handle, one rank per GPU.  Rank 0 obtains an id (vidx_comm_unique_id), the host program

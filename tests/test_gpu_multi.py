@@ -103,6 +103,51 @@ def test_partitioned_load_reads_only_the_owned_part(ffi, tmp_path):
     assert same_bits(D, D0) and np.array_equal(I, I0)
 
 
+@pytest.mark.parametrize("world,nparts", [(4, 2), (4, 1), (6, 3), (8, 2)])
+@pytest.mark.parametrize("nq,k", [(301, 10), (7, 100), (1, 10)])
+def test_rank_grid_emulated_on_one_gpu(ffi, world, nparts, nq, k):
+    """vidx_search_multi's grid of index parts x query groups, with this process playing every rank: rank r searches part
+    r % P for the queries vidx_grid_plan gives group r / P, the packed runs are laid out as the all-gather would leave them,
+    and the grouped merge must return the single-GPU answer for the whole batch (ragged last group, groups without queries)."""
+    import torch
+    xb, xq = bench_data(30000, 32, 301)
+    xq = xq[:nq]
+    xb[5000:5040] = xb[100]
+    full = ffi.Index(32).build(xb)
+    D0, I0 = full.search(xq, k, 16)
+    parts = []
+    for p in range(nparts):
+        ix = ffi.Index(32)
+        if nparts > 1:
+            ix.set_partition(p, nparts)
+        parts.append(ix.build(xb))
+    plans = [ffi.grid_plan(nq, world, nparts, r) for r in range(world)]
+    per_group = plans[0]["per_group"]
+    # the groups tile the batch, and the ranks of a group tile its coarse work
+    covered = np.zeros(nq, np.int32)
+    for r, pl in enumerate(plans):
+        assert pl["group"] == r // nparts and pl["per_group"] == per_group
+        assert pl["q_lo"] <= pl["coarse_lo"] <= pl["coarse_hi"] <= pl["q_hi"] or pl["coarse_lo"] == pl["coarse_hi"]
+        covered[pl["coarse_lo"]:pl["coarse_hi"]] += 1
+    assert (covered == 1).all()
+    d_xq = torch.from_numpy(xq).cuda()
+    D = torch.full((world, per_group, k), float("inf"), dtype=torch.float32, device="cuda")
+    I = torch.full((world, per_group, k), -1, dtype=torch.int64, device="cuda")
+    K = torch.full((world, per_group, k), -1, dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+    for r, pl in enumerate(plans):
+        n = pl["q_hi"] - pl["q_lo"]
+        if n:
+            parts[r % nparts].search_local_device(d_xq[pl["q_lo"]:].data_ptr(), n, k, 16, D[r].data_ptr(), I[r].data_ptr(),
+                                                  K[r].data_ptr(), 0)
+    oD = torch.empty((nq, k), dtype=torch.float32, device="cuda")
+    oI = torch.empty((nq, k), dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+    ffi.merge_topk_grid_device(0, D.data_ptr(), I.data_ptr(), K.data_ptr(), nparts, per_group, nq, k, oD.data_ptr(), oI.data_ptr(), 0)
+    torch.cuda.synchronize()
+    assert same_bits(oD.cpu().numpy(), D0) and np.array_equal(oI.cpu().numpy(), I0)
+
+
 @pytest.mark.parametrize("exchange", ["", "1"])
 def test_collective_path_with_a_one_rank_communicator(ffi, exchange, monkeypatch):
     """vidx_comm_init + vidx_search_multi on world = 1: the probe all-gather, the bound exchange (forced on with

@@ -105,3 +105,29 @@ def test_partition_rule_balances(ffi):
         loads = np.bincount(o, weights=sizes, minlength=world)
         assert loads.max() - loads.min() <= sizes.max() and set(o.tolist()) == set(range(world))
     assert ffi.partition_shards([5, 5, 5], 1).tolist() == [0, 0, 0]
+
+
+@pytest.mark.parametrize("nq", [0, 1, 7, 10000, 10007])
+@pytest.mark.parametrize("world,parts", [(1, 1), (2, 1), (2, 2), (4, 2), (8, 1), (8, 4), (8, 8), (6, 3)])
+def test_grid_plan_tiles_the_batch(nq, world, parts):
+    """vidx_grid_plan (host only): world = parts x groups.  The groups' query ranges tile [0, nq) in rank order, every rank of a
+    group reports the same range, the coarse slices of all ranks tile the batch once, and a rank's slice lies in its group."""
+    sys.path.insert(0, os.path.join(ROOT, "vector-indexer_b200"))
+    from vector_indexer_py import _ffi
+    plans = [_ffi.grid_plan(nq, world, parts, r) for r in range(world)]
+    per_group = plans[0]["per_group"]
+    seen = np.zeros(nq, np.int32)
+    coarse = np.zeros(nq, np.int32)
+    for r, p in enumerate(plans):
+        g = r // parts
+        assert p["group"] == g and p["per_group"] == per_group
+        assert p["q_lo"] == min(nq, g * per_group) and p["q_hi"] == min(nq, (g + 1) * per_group)
+        assert p["q_hi"] - p["q_lo"] <= per_group
+        if r % parts == 0:
+            seen[p["q_lo"]:p["q_hi"]] += 1
+        coarse[p["coarse_lo"]:p["coarse_hi"]] += 1
+        if p["coarse_hi"] > p["coarse_lo"]:
+            assert p["q_lo"] <= p["coarse_lo"] and p["coarse_hi"] <= p["q_hi"]
+    assert (seen == 1).all() and (coarse == 1).all()
+    with pytest.raises(_ffi.VidxError):
+        _ffi.grid_plan(nq, 4, 3, 0)

@@ -1285,23 +1285,27 @@ struct MultiPlan {
     uint64_t per_group = 0;  // queries of one group = per * parts
     uint64_t qlo = 0, qhi = 0;  // this rank's group
 };
-static MultiPlan plan_multi(const Index& ix, uint64_t nq) {
-    if (!ix.comm) throw ApiError(VIDX_ERR_INVALID_INPUT, "vidx_search_multi before vidx_comm_init");
+static MultiPlan grid_plan(uint64_t nq, int world, int parts, int rank) {
     MultiPlan m;
-    m.world = comm_world(ix.comm);
-    m.rank = comm_rank(ix.comm);
-    m.parts = ix.part_world;
-    if (m.world % m.parts != 0 || m.rank % m.parts != ix.part_rank)
-        throw ApiError(VIDX_ERR_INVALID_INPUT,
-                       "the communicator does not fit the index partition: world must be a multiple of the partition's world and "
-                       "rank % partition world its rank (vidx_set_partition)");
-    m.groups = m.world / m.parts;
-    m.group = m.rank / m.parts;
-    m.per = ceil_div(nq, (size_t)m.world);
-    m.per_group = m.per * m.parts;
+    m.world = world;
+    m.rank = rank;
+    m.parts = parts;
+    m.groups = world / parts;
+    m.group = rank / parts;
+    m.per = ceil_div(nq, (size_t)world);
+    m.per_group = m.per * parts;
     m.qlo = std::min<uint64_t>(nq, m.per_group * m.group);
     m.qhi = std::min<uint64_t>(nq, m.qlo + m.per_group);
     return m;
+}
+static MultiPlan plan_multi(const Index& ix, uint64_t nq) {
+    if (!ix.comm) throw ApiError(VIDX_ERR_INVALID_INPUT, "vidx_search_multi before vidx_comm_init");
+    const int world = comm_world(ix.comm), rank = comm_rank(ix.comm), parts = ix.part_world;
+    if (world % parts != 0 || rank % parts != ix.part_rank)
+        throw ApiError(VIDX_ERR_INVALID_INPUT,
+                       "the communicator does not fit the index partition: world must be a multiple of the partition's world and "
+                       "rank % partition world its rank (vidx_set_partition)");
+    return grid_plan(nq, world, parts, rank);
 }
 
 static void search_multi_device(Index& ix, SearchCtx& c, const float* d_xq, uint64_t nq, uint64_t k_req, uint64_t nprobe_req,
@@ -2099,6 +2103,31 @@ int vidx_merge_topk_keyed_device(int device, const float* d_D_runs, const int64_
         DeviceGuard g(device);
         const size_t per = (size_t)nq * k;
         launch_merge_runs(d_D_runs, per, d_I_runs, per, d_K_runs, per, nruns, nq, (uint32_t)k, d_D, d_I, (cudaStream_t)stream);
+    });
+}
+int vidx_grid_plan(uint64_t nq, int world, int parts, int rank, uint64_t* out) {
+    return guarded([&] {
+        require(out && world >= 1 && parts >= 1 && world % parts == 0 && rank >= 0 && rank < world, VIDX_ERR_INVALID_INPUT,
+                "world must be a multiple of parts, 0 <= rank < world");
+        const MultiPlan m = grid_plan(nq, world, parts, rank);
+        const uint64_t lo = std::min<uint64_t>(nq, m.per * (uint64_t)rank);
+        out[0] = (uint64_t)m.group;
+        out[1] = m.qlo;
+        out[2] = m.qhi;
+        out[3] = m.per_group;
+        out[4] = lo;
+        out[5] = std::min<uint64_t>(nq, lo + m.per);
+    });
+}
+int vidx_merge_topk_grid_device(int device, const float* d_D_runs, const int64_t* d_I_runs, const uint64_t* d_K_runs0, uint32_t parts,
+                                uint64_t per_group, uint64_t nq, uint64_t k, float* d_D, int64_t* d_I, void* stream) {
+    return guarded([&] {
+        const unsigned long long* d_K_runs = reinterpret_cast<const unsigned long long*>(d_K_runs0);
+        require(k > 0 && parts > 0 && per_group > 0, VIDX_ERR_INVALID_INPUT, "k, parts and per_group must be > 0");
+        require(k <= 0xffffffffull && d_D_runs && d_I_runs && d_D && d_I, VIDX_ERR_INVALID_INPUT, "bad argument");
+        DeviceGuard g(device);
+        const size_t per = (size_t)per_group * k;
+        launch_merge_runs(d_D_runs, per, d_I_runs, per, d_K_runs, per, parts, nq, (uint32_t)k, d_D, d_I, (cudaStream_t)stream, per_group);
     });
 }
 int vidx_merge_topk_device(int device, const float* d_D_runs, const int64_t* d_I_runs, uint32_t nruns, uint64_t nq, uint64_t k,

@@ -106,6 +106,8 @@ _SIGS = {
     "vidx_partition_plan": (i32, [u64p, u64p, u64, u64, i32, i32, i32p, C.POINTER(C.c_int)]),
     "vidx_merge_topk_device": (i32, [i32, vp, vp, u32, u64, u64, vp, vp, vp]),
     "vidx_merge_topk_keyed_device": (i32, [i32, vp, vp, vp, u32, u64, u64, vp, vp, vp]),
+    "vidx_grid_plan": (i32, [u64, i32, i32, i32, u64p]),
+    "vidx_merge_topk_grid_device": (i32, [i32, vp, vp, vp, u32, u64, u64, u64, vp, vp, vp]),
     "vidx_search_local_device": (i32, [vp, vp, u64, u64, u64, vp, vp, vp, vp]),
     "vidx_set_profiling": (i32, [vp, i32]),
     "vidx_set_scan_mode": (i32, [vp, i32]),
@@ -459,6 +461,17 @@ def partition_plan(list_sizes, list_shard, num_shards, world, mode=0):
     check(lib().vidx_partition_plan(_u(sizes), _u(shard), len(sizes), num_shards, world, {"auto": 0, "shards": 1, "ranges": 2}.get(mode, mode),
                                     owner.ctypes.data_as(i32p), C.byref(kind)))
     return {1: "shards", 2: "ranges"}[kind.value], owner[:num_shards]
+
+
+def grid_plan(nq, world, parts, rank):
+    """vidx_search_multi's rank grid: dict(group, q_lo, q_hi, per_group, coarse_lo, coarse_hi) of one rank (host only)."""
+    out = np.zeros(6, np.uint64)
+    check(lib().vidx_grid_plan(nq, world, parts, rank, _u(out)))
+    return dict(zip(("group", "q_lo", "q_hi", "per_group", "coarse_lo", "coarse_hi"), (int(v) for v in out)))
+
+
+def merge_topk_grid_device(device, d_D_runs, d_I_runs, d_K_runs, parts, per_group, nq, k, d_D, d_I, stream=0):
+    check(lib().vidx_merge_topk_grid_device(device, d_D_runs, d_I_runs, d_K_runs, parts, per_group, nq, k, d_D, d_I, stream))
 
 
 def merge_topk_keyed_device(device, d_D_runs, d_I_runs, d_K_runs, nruns, nq, k, d_D, d_I, stream=0):
