@@ -12,7 +12,7 @@ ix = _ffi.Index(d, 0).build(xb, seed=42, nlist=1024)
 ts = torch.cuda.Stream(); torch.cuda.set_stream(ts)
 d_xq = torch.from_numpy(xq).cuda(); d_D = torch.empty((nq, k), device='cuda'); d_I = torch.empty((nq, k), dtype=torch.int64, device='cuda')
 for pair in variants:   # 0 = default kernel, 1 = CTA pair, 2 = query tile in tensor memory
-    for fl in (0, 8, 2, 6):
+    for fl in [int(v) for v in os.environ.get('FLAGS', '0,8,2,6').split(',')]:
         os.environ["VIDX_TC_PAIR"] = str(int(pair == 1)); os.environ["VIDX_TC_TSA"] = str(int(pair == 2)); os.environ["VIDX_TC_FLAGS"] = str(fl)
         ix.set_profiling(True)
         acc = 0
@@ -20,5 +20,5 @@ for pair in variants:   # 0 = default kernel, 1 = CTA pair, 2 = query tile in te
             ix.search_device(d_xq.data_ptr(), nq, k, 8, d_D.data_ptr(), d_I.data_ptr(), ts.cuda_stream); torch.cuda.synchronize()
             if it >= 2: acc += ix.stats()['ms_scan_tc'] / 3
         ix.set_profiling(False)
-        print(f"variant={('default', 'cta pair', 'A in TMEM')[pair]} flags={fl} ({'full' if fl == 0 else 'no epilogue' if fl == 2 else "independent producer" if fl == 8 else "neither"}): scan_tc {acc:.4f} ms", flush=True)
+        print(f"variant={('default', 'cta pair', 'A in TMEM')[pair]} flags={fl} ({ {0: 'full', 2: 'no epilogue', 4: 'no MMA', 6: 'neither', 8: 'independent producer'}.get(fl, '?') }): scan_tc {acc:.4f} ms", flush=True)
 os._exit(0)

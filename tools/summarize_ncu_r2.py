@@ -56,7 +56,9 @@ full = "ncu --profile-from-start off --set full --clock-control none --import-so
 c10 = captures(f'gpurun_out/prof_{tag}.ncu-rep', 'profiles/r2_ncu_scan_tc.json', full + base, ["bounds launch (minima of the heads of each query's four nearest lists)", "main launch"])
 c128 = captures(f'gpurun_out/prof128_{tag}.ncu-rep', 'profiles/r2_ncu_scan_tc_nq128.json', full + base + " --profile-nq 128",
                 ["bounds launch (128 queries: 512 tiles per query)", "main launch (CTA-local top-k sets)"])
-captures(f'gpurun_out/profc_{tag}.ncu-rep', 'profiles/r2_ncu_coarse_c5shape.json',
+import os
+if os.path.exists(f'gpurun_out/profc_{tag}.ncu-rep'):  # (the closing visit, tools/gpu_final2.sh, does not repeat the coarse capture)
+  captures(f'gpurun_out/profc_{tag}.ncu-rep', 'profiles/r2_ncu_coarse_c5shape.json',
          "ncu --profile-from-start off --set full --clock-control none -k regex:coarse_dist_kernel|scan_tc_kernel|select_topk_kernel|select_small_kernel|finalize_kernel -c 8 python tools/coarse_ncu.py",
          ["exact: coarse_dist_kernel", "exact: select_topk_kernel", "filter: scan_tc_kernel bounds pass over the centroid table", "filter: select_small_kernel",
           "filter: scan_tc_kernel frozen pass", "filter: finalize_kernel (exact re-check + probe order)"])
