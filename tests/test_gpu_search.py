@@ -66,17 +66,35 @@ def test_search_tensor_core_pipeline_shapes(oracle, ffi, d, k):
     check_search(oix, gix, xq, k, 2)
 
 
-@pytest.mark.parametrize("d,k,tc", [(320, 10, True), (384, 32, True), (512, 10, True), (768, 10, False), (1536, 5, False)])
+@pytest.mark.parametrize("d,k,tc", [(320, 10, True), (384, 32, True), (512, 10, True), (520, 10, True), (768, 10, True),
+                                    (1000, 32, True), (1536, 5, True), (2064, 5, False)])
 def test_search_large_dimensions(oracle, ffi, d, k, tc):
     """The reference's own grids and tests use D = 512, 768, 1536 (bench.yaml:1-15, shards_tests.rs:239-270,
-    ivf_index_tests.rs:661-686).  Up to D = 512 the query tile still fits in shared memory next to a two-stage ring and the
-    scan runs on the tensor cores; beyond that the exact FP32 kernels answer.  Same bits either way."""
-    xb, xq = bench_data(12000, d, 700, seed=d)
+    ivf_index_tests.rs:661-686).  Up to D = 512 the query tile stays in shared memory next to a two-stage ring; from there to
+    D = 2048 it is streamed through the ring with the list tiles (scan_tc_kernel<.., SA>, query tiles prepared by
+    tc_atile_kernel); beyond that the exact FP32 kernels answer.  Same bits every way."""
+    xb, xq = bench_data(12000 if d <= 1536 else 4000, d, 700, seed=d)
     oix, gix = make_pair(oracle, ffi, xb, 10)
     gix.set_profiling(True)
     check_search(oix, gix, xq, k, 3)
     assert (gix.stats()["n_tc_items"] > 0) == tc
     gix.set_profiling(False)
+
+
+@pytest.mark.parametrize("d,nq,nlist,nprobe", [(768, 1, 6, 6), (768, 130, 3, 2), (640, 1031, 40, 7), (1536, 257, 1, 1)])
+def test_streamed_query_tiles_ragged(oracle, ffi, d, nq, nlist, nprobe):
+    """Streamed query tiles (D > 512) whose row counts are not multiples of 8, one-row tiles, lists with several tiles and a
+    short last one, a one-list index."""
+    xb, xq = bench_data(6000, d, nq, seed=d + nq)
+    oix, gix = make_pair(oracle, ffi, xb, nlist)
+    gix.set_profiling(True)
+    check_search(oix, gix, xq, 10, nprobe)
+    assert gix.stats()["n_tc_items"] > 0
+    gix.set_profiling(False)
+    Dg, Ig = gix.search(xq, 10, nprobe)  # a second call reuses every buffer
+    gix.set_scan_mode(1)
+    De, Ie = gix.search(xq, 10, nprobe)
+    assert np.array_equal(Dg.view(np.uint32), De.view(np.uint32)) and np.array_equal(Ig, Ie)
 
 
 @pytest.mark.parametrize("flag", ["1"])
@@ -241,7 +259,7 @@ def test_tensor_core_filter_never_drops_a_true_neighbour_on_hard_data(oracle, ff
     check_search(oix, gix, xq, 10, 8)
 
 
-@pytest.mark.parametrize("d,nlist,nprobe", [(64, 300, 20), (128, 2500, 32), (30, 700, 1), (200, 4096, 8)])
+@pytest.mark.parametrize("d,nlist,nprobe", [(64, 300, 20), (128, 2500, 32), (30, 700, 1), (200, 4096, 8), (768, 900, 16)])
 def test_coarse_tensor_core_filter_equals_exact_coarse(oracle, ffi, d, nlist, nprobe):
     # ivf_index.rs:205-220 through the fp16 filter + exact re-check: identical probe lists and bit-identical distances
     xb, xq = bench_data(20000, d, 600, seed=nlist)

@@ -506,13 +506,14 @@ struct Workspace {
     DevBuf xq_pad, dist, probes, pair_ns, slot_off, seg_cnt, seg_qoff, seg_cur, seg_qlist, slot_seg, dense, sparse, counters,
         scan_tmp, cand_d, cand_r, alld, row_off, row_len, sel_pos, sel_val, rows, stats, slot_rank, list_cnt, list_cur, list_qoff,
         list_qlist, items_per_list, item_off, qnorm, gthr, cand_cnt, overflow, cand, list_cnt0, list_cur0, list_qoff0, list_qlist0,
-        items_per_list0, item_off0, gtop, glock, tcscale, items, items0, pair_tiles, pair_off, dump, cand_val, dbg;
+        items_per_list0, item_off0, gtop, glock, tcscale, items, items0, pair_tiles, pair_off, dump, cand_val, dbg,
+        a_rows8, a_rowoff, a_tiles, a_rowoff0, a_tiles0;  // streamed query tiles (D > 512): main grouping / seeding grouping
 };
 // Coarse quantization on tensor cores has its own scratch (it runs the filter over the centroid table while the list
 // scan's buffers of the same batch are being prepared).
 struct CoarseWs {
     DevBuf probes0, list_cnt, list_cur, list_qoff, list_qlist, items_per_list, item_off, items, qnorm, gthr, cand_cnt, overflow, cand, gtop, glock, tcscale, counters, scan_tmp, dist_tmp,
-        submin, sel_pos, sel_val;
+        submin, sel_pos, sel_val, a_rows8, a_rowoff, a_tiles;
 };
 // One search in flight.  A call takes a context from the handle's pool, enqueues on its stream (or the caller's) and
 // hands it back; `done` marks the end of that work, and whoever takes the context next makes its stream wait for it,
@@ -664,8 +665,18 @@ void Index::coarse_tc(SearchCtx& ctx, const float4* xq4, uint32_t nqb, uint32_t 
     launch_tc_items(w.list_cnt.as<uint32_t>(), ctab.list_ng.as<uint32_t>(), 1, reinterpret_cast<unsigned long long*>(counters + 12), 0, counters + 10,
                     w.items_per_list.as<uint32_t>(), false, st);
     exclusive_scan_u32(w.items_per_list.as<uint32_t>(), w.item_off.as<uint32_t>(), 1, w.scan_tmp.as<uint32_t>(), st);
+    const bool stream_a = tc_streams_a((int)dim, k);  // D > 512: the query tiles are prepared in global memory
+    if (stream_a) {
+        w.a_rows8.reserve(16);
+        w.a_rowoff.reserve(16);
+        w.a_tiles.reserve(tc_atile_rows_cap(nqb, 1) * (size_t)tc_dh((int)dim) * 16);
+        launch_tc_atiles(w.list_cnt.as<uint32_t>(), w.list_qoff.as<uint32_t>(), w.list_qlist.as<uint2>(), 1, nqb, xq4, Dq, tc_dh((int)dim),
+                         reinterpret_cast<const TcScale*>(w.tcscale.as<unsigned char>() + 16), w.a_rows8.as<uint32_t>(),
+                         w.a_rowoff.as<uint32_t>(), w.scan_tmp.as<uint32_t>(), w.a_tiles.as<uint4>(), st);
+    }
     launch_tc_expand(w.list_cnt.as<uint32_t>(), ctab.list_ng.as<uint32_t>(), ctab.list_g0.as<uint32_t>(), w.list_qoff.as<uint32_t>(),
-                     w.item_off.as<uint32_t>(), counters + 10, 1, 0, w.items.as<TcItem>(), false, st);
+                     w.item_off.as<uint32_t>(), counters + 10, 1, 0, w.items.as<TcItem>(), false,
+                     stream_a ? w.a_rowoff.as<uint32_t>() : nullptr, st);
     // bounds pass over the whole table (it is short: nlist / 128 tiles per query): minima of every 32 centroids; the n_probe
     // smallest of a query's minima bound its n_probe-th nearest centroid, and the main pass only collects what is within it
     const uint32_t ntiles = (ncgroups + kTcTileGroups - 1) / kTcTileGroups;
@@ -682,6 +693,7 @@ void Index::coarse_tc(SearchCtx& ctx, const float4* xq4, uint32_t nqb, uint32_t 
     tp.scale = reinterpret_cast<const TcScale*>(w.tcscale.as<unsigned char>() + 16);
     tp.nq = nqb;
     tp.xq4 = xq4;
+    tp.a_tiles = stream_a ? w.a_tiles.as<uint4>() : nullptr;
     tp.qnorm = w.qnorm.as<float>();
     tp.list_g0 = ctab.list_g0.as<uint32_t>();
     tp.list_ngroups = ctab.list_ng.as<uint32_t>();
@@ -755,6 +767,8 @@ void Index::search_device(SearchCtx& ctx, const float* d_xq, uint64_t nq, uint64
     // tensor-core pre-filter + exact finalize whenever the shape allows; the exact kernels then
     // only see the queries it hands back (survivor buffer overflow)
     const bool tc = fused && scan_mode != 1 && tc_ok && tc_supported((int)dim, (uint32_t)k) && !coarse_only;
+    const bool tc_sa = tc && tc_streams_a((int)dim, (uint32_t)k);  // D > 512: query tiles streamed through the ring (scan_tc.cu)
+    const int Dh16 = tc_dh((int)dim);
     // two passes of the filter when a query visits few tiles (the HBM-bound regime): a bounds pass that only records
     // the minimum of every 32 columns, then the main pass with final bounds.  With many tile visits per query (a few
     // giant lists) the doubled tensor-core work costs more than the survivors it saves: seeding pass + main pass.
@@ -788,13 +802,13 @@ void Index::search_device(SearchCtx& ctx, const float* d_xq, uint64_t nq, uint64
         const char* v = getenv("VIDX_TC_PAIR");
         if (v && *v) return atoi(v) != 0;
         return kTcPairDefault && !small_batch && (double)nq * (double)np >= kTcPairMinQueriesPerList * (double)std::max<uint64_t>(nlist, 1);
-    }() && tc;
+    }() && tc && !tc_sa;
     // query tile in tensor memory for the main pass (D <= 240)
     const bool tc_tsa = [&] {
         const char* v = getenv("VIDX_TC_TSA");
         if (v && *v) return atoi(v) != 0;
         return kTcTsaDefault && !small_batch;
-    }() && tc && !tc_pair;
+    }() && tc && !tc_pair && !tc_sa;
     const uint32_t nseg = (uint32_t)segs.size();
     const uint32_t ldc = ncgroups * kGroup;
     // pairs bound per query: the np largest per-list segment counts
@@ -811,6 +825,7 @@ void Index::search_device(SearchCtx& ctx, const float* d_xq, uint64_t nq, uint64
     shrink((double)std::max<uint64_t>(pairs_per_q, np), 1.5e9 / 1.0);  // 32-bit pair / slot indices
     if (tc_dump) shrink((double)dump_tiles_per_q * 16.0, 4e9);           // the bounds pass's minima: 16 B per (query, probed tile)
     if (tc) shrink(256.0 * 12.0, 4e9);                                    // survivor buffers: at least 256 entries per query
+    if (tc_sa) shrink((double)np * Dh16 * 16.0 * 2.0, 6e9);               // streamed query tiles: one fp16 row per (query, probed list)
     qb = std::min<uint64_t>(qb, 65535ull * 64);
     uint32_t capq = 0;
     if (tc) {
@@ -961,6 +976,14 @@ void Index::search_device(SearchCtx& ctx, const float* d_xq, uint64_t nq, uint64
             launch_tc_items(w.list_cnt.as<uint32_t>(), d_list_ng.as<uint32_t>(), (uint32_t)nlist,
                             reinterpret_cast<unsigned long long*>(counters + 12), 0, counters + 10, w.items_per_list.as<uint32_t>(), tc_pair, st);
             exclusive_scan_u32(w.items_per_list.as<uint32_t>(), w.item_off.as<uint32_t>(), nlist, w.scan_tmp.as<uint32_t>(), st);
+            if (tc_sa) {
+                w.a_rows8.reserve(((size_t)nlist + 1) * 4);
+                w.a_rowoff.reserve(((size_t)nlist + 1) * 4);
+                w.a_tiles.reserve(tc_atile_rows_cap(npairs, nlist) * (size_t)Dh16 * 16);
+                launch_tc_atiles(w.list_cnt.as<uint32_t>(), w.list_qoff.as<uint32_t>(), w.list_qlist.as<uint2>(), (uint32_t)nlist, npairs, xq4,
+                                 Dq, Dh16, reinterpret_cast<const TcScale*>(w.tcscale.as<unsigned char>() + 16), w.a_rows8.as<uint32_t>(),
+                                 w.a_rowoff.as<uint32_t>(), w.scan_tmp.as<uint32_t>(), w.a_tiles.as<uint4>(), st);
+            }
             {
                 // one 32-byte record per work item; items <= total/chunk + sum of query tiles per list, with
                 // total <= (nq/128 + 1) * tiles and chunk >= min(128, total / (8 SMs-worth))
@@ -968,7 +991,8 @@ void Index::search_device(SearchCtx& ctx, const float* d_xq, uint64_t nq, uint64
                 const uint64_t cap_items = (nqb / 128 + 1) * tiles / 128 + 8 * 160 + npairs / 128 + 2 * nlist + 64;
                 w.items.reserve(cap_items * sizeof(TcItem));
                 launch_tc_expand(w.list_cnt.as<uint32_t>(), d_list_ng.as<uint32_t>(), d_list_g0.as<uint32_t>(), w.list_qoff.as<uint32_t>(),
-                                 w.item_off.as<uint32_t>(), counters + 10, (uint32_t)nlist, 0, w.items.as<TcItem>(), tc_pair, st);
+                                 w.item_off.as<uint32_t>(), counters + 10, (uint32_t)nlist, 0, w.items.as<TcItem>(), tc_pair,
+                                 tc_sa ? w.a_rowoff.as<uint32_t>() : nullptr, st);
             }
             if (tc_dump) {
                 // bounds pass: first tile of every (query, probe rank) pair in submin, and each query's row of it
@@ -1001,8 +1025,18 @@ void Index::search_device(SearchCtx& ctx, const float* d_xq, uint64_t nq, uint64
                             w.items_per_list0.as<uint32_t>(), false, st);
             exclusive_scan_u32(w.items_per_list0.as<uint32_t>(), w.item_off0.as<uint32_t>(), nlist, w.scan_tmp.as<uint32_t>(), st);
             w.items0.reserve((((uint64_t)nqb * seed_ranks / 32 + 2 * nlist) * ceil_div(seed_rank_tiles, 16) + 64) * sizeof(TcItem));
+            if (tc_sa) {
+                const size_t npairs0 = (size_t)nqb * seed_ranks;
+                w.a_rows8.reserve(((size_t)nlist + 1) * 4);
+                w.a_rowoff0.reserve(((size_t)nlist + 1) * 4);
+                w.a_tiles0.reserve(tc_atile_rows_cap(npairs0, nlist) * (size_t)Dh16 * 16);
+                launch_tc_atiles(w.list_cnt0.as<uint32_t>(), w.list_qoff0.as<uint32_t>(), w.list_qlist0.as<uint2>(), (uint32_t)nlist, npairs0,
+                                 xq4, Dq, Dh16, reinterpret_cast<const TcScale*>(w.tcscale.as<unsigned char>() + 16),
+                                 w.a_rows8.as<uint32_t>(), w.a_rowoff0.as<uint32_t>(), w.scan_tmp.as<uint32_t>(), w.a_tiles0.as<uint4>(), st);
+            }
             launch_tc_expand(w.list_cnt0.as<uint32_t>(), d_list_ng.as<uint32_t>(), d_list_g0.as<uint32_t>(), w.list_qoff0.as<uint32_t>(),
-                             w.item_off0.as<uint32_t>(), counters + 11, (uint32_t)nlist, seed_rank_tiles, w.items0.as<TcItem>(), false, st);
+                             w.item_off0.as<uint32_t>(), counters + 11, (uint32_t)nlist, seed_rank_tiles, w.items0.as<TcItem>(), false,
+                             tc_sa ? w.a_rowoff0.as<uint32_t>() : nullptr, st);
             // the seeding pass's minima: one fixed-length row per query, +inf where a list has fewer tiles
             w.dump.reserve(std::max<uint64_t>((uint64_t)nqb * seed_row, 1) * 4);
             w.sel_pos.reserve((size_t)nqb * k * 4);
@@ -1050,6 +1084,7 @@ void Index::search_device(SearchCtx& ctx, const float* d_xq, uint64_t nq, uint64
                 tp.list_qlist = w.list_qlist0.as<uint2>();
                 tp.item_off = w.item_off0.as<uint32_t>();
                 tp.items = w.items0.as<TcItem>();
+                tp.a_tiles = tc_sa ? w.a_tiles0.as<uint4>() : nullptr;
                 tp.work_counter = counters + 9;
                 launch_scan_tc(tp, st);
                 launch_select_small(w.dump.as<float>(), nullptr, nullptr, seed_row, seed_row, nqb, (uint32_t)k, w.sel_pos.as<uint32_t>(),
@@ -1063,6 +1098,7 @@ void Index::search_device(SearchCtx& ctx, const float* d_xq, uint64_t nq, uint64
             tp.list_qlist = w.list_qlist.as<uint2>();
             tp.item_off = w.item_off.as<uint32_t>();
             tp.items = w.items.as<TcItem>();
+            tp.a_tiles = tc_sa ? w.a_tiles.as<uint4>() : nullptr;
             tp.pair = tc_pair ? 1u : 0u;  // both passes of the two-pass flavour run over the same work items
             if (tc_pair) tp.tmap = shadow_tmap;
             if (tc_dump) {

@@ -46,7 +46,10 @@
 // a bounds pass over everything the query probes: bounds are final, survivors are only collected).
 #include <cuda_fp16.h>
 
+#include <algorithm>
+
 #include "scan_tc.h"
+#include "search.h"
 
 namespace vidx {
 
@@ -80,6 +83,8 @@ constexpr uint32_t kTcACol = 384;    // A-in-TMEM variant: three accumulator sta
 constexpr int kTcTmemCols = 512;     // 4 accumulator stages x 128 columns
 constexpr int kTcStages = 4;         // shared-memory ring: stages of 128 vectors x 128 dims of fp16 (32 KB), two per tile pipeline
 constexpr int kTcStageChunks = 16;   // 16-byte chunks (8 halfs) of every vector per stage
+constexpr int kTcStreamChunks = 8;   // ... when the query tile is streamed through the ring too (large D): a stage then holds
+                                     // 16 KB of list chunks, the norm chunk and 16 KB of query chunks -- the same 34 KB
 constexpr uint32_t kTcStageData = kTcStageChunks * kTcTileGroups * 512;  // 32 KB of vector chunks
 constexpr uint32_t kTcStageBytes = kTcStageData + 2048;                  // + the tile's norm chunk (used by the last K-slice)
 constexpr float kTcEps = 1.5e-3f;    // see header comment; needed: ~1.03e-3
@@ -514,7 +519,8 @@ __global__ void tc_items_kernel(const uint32_t* __restrict__ list_cnt, const uin
 __global__ void tc_expand_kernel(const uint32_t* __restrict__ list_cnt, const uint32_t* __restrict__ list_ngroups,
                                  const uint32_t* __restrict__ list_g0, const uint32_t* __restrict__ list_qoff,
                                  const uint32_t* __restrict__ item_off, const uint32_t* __restrict__ chunk_tiles, uint32_t nlist,
-                                 uint32_t seed_tiles, uint32_t qrows_main, TcItem* __restrict__ items) {
+                                 uint32_t seed_tiles, uint32_t qrows_main, const uint32_t* __restrict__ a_rowoff,
+                                 TcItem* __restrict__ items) {
     const uint32_t l = blockIdx.x;
     if (l >= nlist) return;
     const uint32_t i0 = item_off[l], n = item_off[l + 1] - i0;
@@ -524,6 +530,7 @@ __global__ void tc_expand_kernel(const uint32_t* __restrict__ list_cnt, const ui
     const uint32_t nqt = (cnt + qrows - 1) / qrows;
     uint32_t ntiles = (ngl + kTcTileGroups - 1) / kTcTileGroups;
     if (seed_tiles) ntiles = min(ntiles, seed_tiles);
+    const uint32_t arow0 = a_rowoff ? a_rowoff[l] : 0u;  // streamed query tiles (D > 512): first row of the list's tiles
     for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
         // chunk-major: CTAs running at the same time share a vector chunk (L2 reuse), and a query's later chunks
         // start with a warm bound
@@ -538,8 +545,66 @@ __global__ void tc_expand_kernel(const uint32_t* __restrict__ list_cnt, const ui
         r.g_list = g_list;
         r.ngl = ngl;
         r.valid = 1u;
-        r.pad = 0u;
+        r.pad = a_rowoff ? arow0 + qt * qrows : 0u;  // all tiles of a list but the last have qrows rows
         items[i0 + i] = r;
+    }
+}
+
+// Streamed query tiles (D > 512).  The rows of list l's work items are list_qlist[list_qoff[l] ..+ list_cnt[l]), cut into
+// tiles of 128; tile (l, qt) is stored as [chunk of 8 dims][r8 rows][16 B] with r8 = its row count rounded up to 8 -- the
+// tcgen05 K-major operand layout with LBO = r8 * 16 -- starting at row a_rowoff[l] + 128 * qt of a_tiles (a "row" = Dh chunks).
+__global__ void tc_arows_kernel(const uint32_t* __restrict__ list_cnt, uint32_t nlist, uint32_t* __restrict__ rows8) {
+    uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l < nlist) rows8[l] = (list_cnt[l] + 7u) & ~7u;
+}
+// 32 consecutive entries of list_qlist per block (one per lane), the eight warps take every eighth chunk: a warp's stores are
+// 512 contiguous bytes, its loads one full 32-byte sector per lane.
+__global__ void __launch_bounds__(256) tc_atile_kernel(const uint32_t* __restrict__ list_cnt, const uint32_t* __restrict__ list_qoff,
+                                                       const uint2* __restrict__ list_qlist, const uint32_t* __restrict__ a_rowoff,
+                                                       uint32_t nlist, const float4* __restrict__ xq4, int Dq, int Dh,
+                                                       const TcScale* __restrict__ scale, uint4* __restrict__ a_tiles) {
+    __shared__ uint32_t s_query[32], s_tile0[32], s_row[32], s_r8[32], s_fill[32];
+    const uint32_t total = list_qoff[nlist];
+    if (threadIdx.x < 32) {
+        const uint32_t pos = blockIdx.x * 32u + threadIdx.x;
+        uint32_t q = kNoRow, tile0 = 0, row = 0, r8 = 8, fill = 0;
+        if (pos < total) {
+            uint32_t lo = 0, hi = nlist;  // the list with list_qoff[l] <= pos < list_qoff[l + 1] (empty lists share an offset)
+            while (hi - lo > 1) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (list_qoff[mid] <= pos) lo = mid;
+                else hi = mid;
+            }
+            const uint32_t i = pos - list_qoff[lo], cnt = list_cnt[lo], qt = i >> 7;
+            const uint32_t rows = min(128u, cnt - qt * 128u);
+            q = list_qlist[pos].x;
+            row = i & 127u;
+            r8 = (rows + 7u) & ~7u;
+            tile0 = a_rowoff[lo] + qt * 128u;
+            fill = i == cnt - 1 ? r8 - rows : 0u;  // the list's last row also zeroes the padding rows behind it
+        }
+        s_query[threadIdx.x] = q;
+        s_tile0[threadIdx.x] = tile0;
+        s_row[threadIdx.x] = row;
+        s_r8[threadIdx.x] = r8;
+        s_fill[threadIdx.x] = fill;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint32_t q = s_query[lane];
+    if (q == kNoRow) return;
+    const uint32_t r8 = s_r8[lane], fill = s_fill[lane];
+    const float qmul = scale->qmul;
+    uint4* tile = a_tiles + (size_t)s_tile0[lane] * (size_t)Dh + s_row[lane];
+    const float4* src = xq4 + (size_t)q * Dq;
+    for (int c = w; c < Dh; c += 8) {
+        float4 a = make_float4(0, 0, 0, 0), b = a;
+        if (2 * c < Dq) a = __ldg(src + 2 * c);
+        if (2 * c + 1 < Dq) b = __ldg(src + 2 * c + 1);
+        uint4* dst = tile + (size_t)c * r8;
+        *dst = make_uint4(pack_h2(qmul * a.x, qmul * a.y), pack_h2(qmul * a.z, qmul * a.w), pack_h2(qmul * b.x, qmul * b.y),
+                          pack_h2(qmul * b.z, qmul * b.w));
+        for (uint32_t z = 1; z <= fill; z++) dst[z] = make_uint4(0u, 0u, 0u, 0u);
     }
 }
 
@@ -549,11 +614,13 @@ __global__ void tc_expand_kernel(const uint32_t* __restrict__ list_cnt, const ui
 struct TcSmemLayout {
     uint32_t a_bytes, off_b, off_norm, off_ones, off_zero, off_r, off_queue, off_stage, off_q, off_row, off_bar, off_misc, off_item, total;
     uint32_t stages, stage_data, stage_bytes;
+    uint32_t stream_a;  // 1: the query tile does not stay in shared memory -- its K-slices travel through the ring with the list's
 };
 // pair = the CTA-pair kernel: a CTA holds 64 of a tile's 128 vectors, so the same ring memory makes 8 stages instead of 4
 __host__ __device__ inline TcSmemLayout tc_smem_layout_n(int Dh, int kr, bool pair, uint32_t stages) {
     TcSmemLayout L;
     L.stages = stages;
+    L.stream_a = 0;
     L.stage_data = pair ? kTcStageData / 2 : kTcStageData;
     L.stage_bytes = pair ? kTcStageBytes / 2 : kTcStageBytes;
     L.a_bytes = (uint32_t)Dh * kTcM * 16;                   // query tile, [chunk][128 rows][16 B = 8 halfs]
@@ -575,8 +642,12 @@ __host__ __device__ inline TcSmemLayout tc_smem_layout_n(int Dh, int kr, bool pa
 // The whole query tile stays in shared memory for the life of a work item (every list tile is multiplied with it), so the ring
 // gets what is left: four 34 KB stages up to D = 256, two (one per tile pipeline) up to D = 512.  pair = the CTA-pair kernel:
 // a CTA holds 64 of a tile's 128 vectors, so the same ring memory makes twice the stages.
+// Beyond D = 512 (the reference's own grids use 768 and 1536: bench.yaml:1-15, tests/ivf_index_tests.rs:661-686) the query tile is
+// STREAMED: a pre-pass writes every work item's query tile as fp16 in operand layout to global memory (tc_atile_kernel), and a
+// ring stage carries 64 dimensions of the list tile AND of the query tile (stream_a).  The tile then comes from L2 once per list
+// tile instead of once per work item -- half the tensor rate, but ~10 x the exact FP32 kernels these shapes used to fall back to.
 constexpr uint32_t kTcSmemMax = 227 * 1024;
-__host__ __device__ inline TcSmemLayout tc_smem_layout(int Dh, int kr, bool pair = false) {
+__host__ __device__ inline TcSmemLayout tc_smem_layout_resident(int Dh, int kr, bool pair) {
     uint32_t stages = pair ? 2 * kTcStages : kTcStages;
     TcSmemLayout L = tc_smem_layout_n(Dh, kr, pair, stages);
     while (L.total > kTcSmemMax && stages > 2) {
@@ -584,6 +655,16 @@ __host__ __device__ inline TcSmemLayout tc_smem_layout(int Dh, int kr, bool pair
         L = tc_smem_layout_n(Dh, kr, pair, stages);
     }
     return L;
+}
+__host__ __device__ inline TcSmemLayout tc_smem_layout_streamed(int kr) {
+    TcSmemLayout L = tc_smem_layout_n(0, kr, false, kTcStages);
+    L.stream_a = 1;
+    L.stage_data = kTcStreamChunks * kTcTileGroups * 512;
+    return L;
+}
+inline TcSmemLayout tc_smem_layout(int Dh, int kr, bool pair = false) {  // host: which of the two a shape gets
+    const TcSmemLayout L = tc_smem_layout_resident(Dh, kr, pair);
+    return L.total > kTcSmemMax && !pair ? tc_smem_layout_streamed(kr) : L;
 }
 
 __device__ __forceinline__ uint32_t lds_volatile(const uint32_t* p) {
@@ -636,14 +717,21 @@ constexpr uint32_t kEntValid = 0x40000000u;
 // tdone[pipe][j], j = (tile / 2) % 4), so that every barrier is waited on by exactly one warp role, phase after phase -- a
 // parity wait cannot tell phase n from phase n + 2, and with stage-indexed barriers shared by two issuers a slow issuer would
 // read a stale "drained".
-template <int KR, bool PAIR, bool TSA>
+// SA: the query tile is streamed through the ring (D > 512, see tc_smem_layout): K-slices of 8 chunks, a stage = list chunks +
+// norm chunk + the query tile's chunks.  A streamed tile has only as many rows as the item has queries (rounded up to 8): the
+// MMA still reads 128 rows, the rows beyond are whatever the stage holds -- rows of the accumulator nobody looks at.
+template <int KR, bool PAIR, bool TSA, bool SA>
 __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(const __grid_constant__ TcParams p) {
     static_assert(!(PAIR && TSA), "the A-in-TMEM variant is single-CTA");
+    static_assert(!(SA && (PAIR || TSA)), "the streamed query tile is a variant of the default kernel only");
     extern __shared__ __align__(1024) unsigned char smem[];
-    const TcSmemLayout L = tc_smem_layout(p.Dh, KR, PAIR);
+    const TcSmemLayout L = SA ? tc_smem_layout_streamed(KR) : tc_smem_layout_resident(p.Dh, KR, PAIR);
     const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
     constexpr uint32_t kHalfRows = PAIR ? 64u : 128u;  // vectors of a tile in this CTA's shared memory
-    constexpr uint32_t kStageData = kTcStageChunks * kHalfRows * 16u, kStageBytes = kStageData + kHalfRows * 16u;
+    constexpr int kSC = SA ? kTcStreamChunks : kTcStageChunks;  // 16-byte chunks per K-slice
+    constexpr uint32_t kStageData = (uint32_t)kSC * kHalfRows * 16u;  // list chunks of a stage; then the tile's norm chunk
+    constexpr uint32_t kStageA = kStageData + kHalfRows * 16u;        // SA: then the query tile's chunks
+    constexpr uint32_t kStageBytes = (uint32_t)kTcStageChunks * kHalfRows * 16u + kHalfRows * 16u;
     unsigned char* sA = smem;
     unsigned char* sB = smem + L.off_b;
     constexpr int kRS = KR + 1;                                     // row stride of s_r
@@ -725,7 +813,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(const __grid_con
     }
     const uint32_t total_items = p.item_off[p.nlist];
     const uint32_t idesc = make_idesc_f16(PAIR ? 2 * kTcM : kTcM, kTcTileGroups * 32);
-    const int nkc = (Dh + kTcStageChunks - 1) / kTcStageChunks;  // K-slices per tile
+    const int nkc = (Dh + kSC - 1) / kSC;  // K-slices per tile
     const float kInf = __int_as_float(0x7f800000);
     uint32_t it = 0;     // tiles processed so far by this CTA (accumulator stage = it & 3, phase = (it >> 2) & 1)
     // Two independent tile pipelines, each with its own producer warp, MMA warp and half of the ring: pipeline 0
@@ -769,6 +857,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(const __grid_con
         const uint32_t t0 = __shfl_sync(kFull, rec.t0, 0), t1 = __shfl_sync(kFull, rec.t1, 0);
         const uint32_t g_list = __shfl_sync(kFull, rec.g_list, 0), ngl = __shfl_sync(kFull, rec.ngl, 0);
         const uint32_t nq_tile = __shfl_sync(kFull, rec.nq_tile, 0), qbase = __shfl_sync(kFull, rec.qbase, 0);
+        // SA: the item's query tile in p.a_tiles: first row, and its row count (a multiple of 8: whole core matrices)
+        const uint32_t a_row0 = SA ? __shfl_sync(kFull, rec.pad, 0) : 0u;
+        const uint32_t a_r8 = SA ? ((min(nq_tile, (uint32_t)kTcM) + 7u) & ~7u) : (uint32_t)kTcM;
 
         // The producers start streaming this item's tiles at once (they need nothing but the record); everyone else
         // sets the item up behind two named barriers the producers do not take part in.
@@ -864,7 +955,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(const __grid_con
                     tc_wait_st();
                     tc_fence_before();
                 }
-            } else if (warp >= 5) {
+            } else if (!SA && warp >= 5) {
                 // A tile = fp16(-2 * 2^sq * queries): [chunk of 8 dims][128 rows][16 B] (core matrices of 8 rows x
                 // 16 B, SBO 128 B, LBO 2048 B); dimensions beyond the query's are zero.  Warps 5-11 gather it while
                 // warps 1-4 fetch the row state.
@@ -914,11 +1005,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(const __grid_con
             const uint32_t tile_bytes = (uint32_t)Dh * kSuper * 16;
             const unsigned char* src0 = reinterpret_cast<const unsigned char*>(p.vecs16) + ((size_t)(g_list >> 2) + t0) * tile_bytes;
             const uint4* nsrc0 = p.vnorm + ((size_t)g_list + (size_t)t0 * kTcTileGroups) * 32;
+            const unsigned char* asrc0 = SA ? reinterpret_cast<const unsigned char*>(p.a_tiles) + (size_t)a_row0 * (size_t)Dh * 16 : nullptr;
             // One K-slice of tile t into ring stage s.
             auto load_slice = [&](uint32_t t, int kc, uint32_t s) {
-                const uint32_t nch = (uint32_t)min(kTcStageChunks, Dh - kc * kTcStageChunks);
+                const uint32_t nch = (uint32_t)min(kSC, Dh - kc * kSC);
                 const uint32_t bytes = nch * kSuper * 16;  // of the whole 128-vector K-slice in HBM
-                const unsigned char* src = src0 + (size_t)(t - t0) * tile_bytes + (size_t)kc * (kTcStageChunks * kSuper * 16);
+                const unsigned char* src = src0 + (size_t)(t - t0) * tile_bytes + (size_t)kc * (kSC * kSuper * 16);
                 const uint4* nsrc = nsrc0 + (size_t)(t - t0) * kSuper;
                 const bool last = kc == nkc - 1;
                 if (elect_one()) {
@@ -932,9 +1024,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(const __grid_con
                         tma_load_2d(sB + s * kStageBytes, &p.tmap, (int)(cta_rank * 128u), (int)(blk0 + (uint32_t)kc * kTcStageChunks), &bar_full[s]);
                         if (last) bulk_g2s(sB + s * kStageBytes + kStageData, nsrc + cta_rank * 64u, 1024u, &bar_full[s]);
                     } else {
-                        mbar_expect_tx(&bar_full[s], bytes + (last ? 2048u : 0u));
+                        const uint32_t abytes = SA ? nch * a_r8 * 16u : 0u;  // the same K-slice of the query tile: [chunk][a_r8 rows][16 B]
+                        mbar_expect_tx(&bar_full[s], bytes + (last ? 2048u : 0u) + abytes);
                         bulk_g2s(sB + s * kStageBytes, src, bytes, &bar_full[s]);
                         if (last) bulk_g2s(sB + s * kStageBytes + kStageData, nsrc, 2048, &bar_full[s]);
+                        if (SA) bulk_g2s(sB + s * kStageBytes + kStageA, asrc0 + (size_t)kc * ((size_t)kSC * a_r8 * 16u), abytes, &bar_full[s]);
                     }
                 }
                 __syncwarp();
@@ -1037,10 +1131,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(const __grid_con
                         tc_fence_after();
                         // chunk c of all 128 rows is one 2 KB block (128 x 16 B) in the query tile: +128 per chunk in >>4 units;
                         // a K step (two chunks) of the list tile is 2 * kHalfRows * 16 bytes
-                        const uint32_t al = a_lo0 + (uint32_t)kc * (kTcStageChunks * 128);
+                        // (SA: the query tile's K-slice sits in the stage, consecutive chunks a_r8 * 16 bytes apart)
+                        const uint32_t al = SA ? ((((smem_u32(sB) + s * kStageBytes + kStageA) >> 4) & 0x3fffu) | (((a_r8 * 16u) >> 4) << 16))
+                                               : a_lo0 + (uint32_t)kc * (kSC * 128);
+                        const uint32_t a_kstep = SA ? 2u * a_r8 : 256u;  // one K step = two chunks, in 16-byte units
                         const uint32_t bl = b_lo0 + s * (kStageBytes >> 4);
                         constexpr uint32_t kBStep = (2u * kHalfRows * 16u) >> 4;
-                        const int nks = min(kTcStageChunks / 2, (Dh >> 1) - kc * (kTcStageChunks / 2));
+                        const int nks = min(kSC / 2, (Dh >> 1) - kc * (kSC / 2));
                         const uint32_t noff = L.off_b + s * kStageBytes + kStageData;
                         const uint32_t norm_lo = ((smem_u32(smem + noff) >> 4) & 0x3fffu) | (((L.off_zero - noff) >> 4) << 16);
                         if (elect_one()) {
@@ -1052,17 +1149,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(const __grid_con
                                 if (kc == 0) tc_mma_f16_pair<false>(d_tmem, al, bl, desc_hi, idesc);
                                 else tc_mma_f16_pair<true>(d_tmem, al, bl, desc_hi, idesc);
 #pragma unroll
-                                for (int ks = 1; ks < kTcStageChunks / 2; ks++)
+                                for (int ks = 1; ks < kSC / 2; ks++)
                                     if (ks < nks) tc_mma_f16_pair<true>(d_tmem, al + ks * 256, bl + ks * kBStep, desc_hi, idesc);
                                 if (kc == nkc - 1) tc_mma_f16_pair<true>(d_tmem, ones_lo, norm_lo, desc_hi, idesc);
                                 tc_commit_pair(&bar_empty[s]);                       // both CTAs' halves of the K-slice are free
                                 if (kc == nkc - 1) tc_commit_pair(&bar_tfull[tf]);   // both CTAs' accumulator tiles are ready
                             } else if (TSA) {
-                                const uint32_t at = tmem_base + kTcACol + (uint32_t)kc * (kTcStageChunks / 2) * 8u;  // 8 columns per K step
+                                const uint32_t at = tmem_base + kTcACol + (uint32_t)kc * (kSC / 2) * 8u;  // 8 columns per K step
                                 if (kc == 0) tc_mma_f16_ts<false>(d_tmem, at, bl, desc_hi, idesc);
                                 else tc_mma_f16_ts<true>(d_tmem, at, bl, desc_hi, idesc);
 #pragma unroll
-                                for (int ks = 1; ks < kTcStageChunks / 2; ks++)
+                                for (int ks = 1; ks < kSC / 2; ks++)
                                     if (ks < nks) tc_mma_f16_ts<true>(d_tmem, at + ks * 8, bl + ks * kBStep, desc_hi, idesc);
                                 if (kc == nkc - 1) tc_mma_f16_ts<true>(d_tmem, tmem_base + kTcACol + (uint32_t)Dh * 4u, norm_lo, desc_hi, idesc);
                                 tc_commit(&bar_empty[s]);
@@ -1071,8 +1168,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(const __grid_con
                                 if (kc == 0) tc_mma_f16_lo<false>(d_tmem, al, bl, desc_hi, idesc);
                                 else tc_mma_f16_lo<true>(d_tmem, al, bl, desc_hi, idesc);
 #pragma unroll
-                                for (int ks = 1; ks < kTcStageChunks / 2; ks++)
-                                    if (ks < nks) tc_mma_f16_lo<true>(d_tmem, al + ks * 256, bl + ks * kBStep, desc_hi, idesc);
+                                for (int ks = 1; ks < kSC / 2; ks++)
+                                    if (ks < nks) tc_mma_f16_lo<true>(d_tmem, al + ks * a_kstep, bl + ks * kBStep, desc_hi, idesc);
                                 if (kc == nkc - 1) tc_mma_f16_lo<true>(d_tmem, ones_lo, norm_lo, desc_hi, idesc);
                                 tc_commit(&bar_empty[s]);                       // K-slice free once these MMAs have read it
                                 if (kc == nkc - 1) tc_commit(&bar_tfull[tf]);   // accumulator tile ready for the epilogue
@@ -1701,9 +1798,28 @@ __global__ void __launch_bounds__(kFinWarps * 32) finalize_kernel(FinalizeParams
 // ====================================================================================
 // the query tile (4 columns per chunk) + 8 columns of the norm step fit behind three accumulator stages (D <= 240)
 bool tc_tsa_supported(int Dh) { return (uint32_t)Dh * 4u + 8u <= (uint32_t)kTcTmemCols - kTcACol; }
+// (D <= 2048: the filter's error budget covers the fp32 accumulation of that many products, see the header comment)
 bool tc_supported(int D, uint32_t k) {
-    if (k == 0 || k > 32 || D < 1) return false;
+    if (k == 0 || k > 32 || D < 1 || D > 2048) return false;
     return tc_smem_layout(tc_dh(D), k <= 8 ? 8 : (k <= 16 ? 16 : 32)).total <= kTcSmemMax;
+}
+bool tc_streams_a(int D, uint32_t k) {
+    return tc_supported(D, k) && tc_smem_layout(tc_dh(D), k <= 8 ? 8 : (k <= 16 ? 16 : 32)).stream_a != 0;
+}
+size_t tc_atile_rows_cap(size_t npairs, size_t nlist) {
+    // sum over the probed lists of their query count rounded up to 8
+    return std::min(8 * npairs, npairs + 7 * std::min(nlist, npairs)) + 8;
+}
+void launch_tc_atiles(const uint32_t* list_cnt, const uint32_t* list_qoff, const uint2* list_qlist, uint32_t nlist, size_t npairs_cap,
+                      const float4* xq4, int Dq, int Dh, const TcScale* scale, uint32_t* rows8, uint32_t* a_rowoff, uint32_t* scan_tmp,
+                      uint4* a_tiles, cudaStream_t st) {
+    if (!nlist || !npairs_cap) return;
+    tc_arows_kernel<<<(unsigned)ceil_div(nlist, 256), 256, 0, st>>>(list_cnt, nlist, rows8);
+    VIDX_LAUNCHED();
+    exclusive_scan_u32(rows8, a_rowoff, nlist, scan_tmp, st);
+    tc_atile_kernel<<<(unsigned)ceil_div(npairs_cap, 32), 256, 0, st>>>(list_cnt, list_qoff, list_qlist, a_rowoff, nlist, xq4, Dq, Dh, scale,
+                                                                        a_tiles);
+    VIDX_LAUNCHED();
 }
 void launch_row_norms(const float4* vecs, int Dq, const uint32_t* row_src, size_t nrows, float* vn_true, uint32_t* stats,
                       cudaStream_t st) {
@@ -1767,17 +1883,17 @@ void launch_tc_items(const uint32_t* list_cnt, const uint32_t* list_ngroups, uin
 }
 void launch_tc_expand(const uint32_t* list_cnt, const uint32_t* list_ngroups, const uint32_t* list_g0, const uint32_t* list_qoff,
                       const uint32_t* item_off, const uint32_t* chunk_tiles, uint32_t nlist, uint32_t seed_tiles, TcItem* items,
-                      bool pair, cudaStream_t st) {
+                      bool pair, const uint32_t* a_rowoff, cudaStream_t st) {
     if (!nlist) return;
     tc_expand_kernel<<<nlist, 64, 0, st>>>(list_cnt, list_ngroups, list_g0, list_qoff, item_off, chunk_tiles, nlist, seed_tiles,
-                                           pair ? 2u * kTcM : (uint32_t)kTcM, items);
+                                           pair ? 2u * kTcM : (uint32_t)kTcM, a_rowoff, items);
     VIDX_LAUNCHED();
 }
-template <int KR, bool PAIR, bool TSA = false>
+template <int KR, bool PAIR, bool TSA = false, bool SA = false>
 static void launch_scan_tc_kr(const TcParams& p, size_t smem, cudaStream_t st) {
     static PerDeviceSize attr;  // the opt-in is per device
     if (attr.needs(smem)) {
-        VIDX_CUDA(cudaFuncSetAttribute(scan_tc_kernel<KR, PAIR, TSA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        VIDX_CUDA(cudaFuncSetAttribute(scan_tc_kernel<KR, PAIR, TSA, SA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr.set(smem);
     }
     if (PAIR) {
@@ -1794,17 +1910,23 @@ static void launch_scan_tc_kr(const TcParams& p, size_t smem, cudaStream_t st) {
         at[0].val.clusterDim.z = 1;
         cfg.attrs = at;
         cfg.numAttrs = 1;
-        VIDX_CUDA(cudaLaunchKernelEx(&cfg, scan_tc_kernel<KR, PAIR, TSA>, p));
+        VIDX_CUDA(cudaLaunchKernelEx(&cfg, scan_tc_kernel<KR, PAIR, TSA, SA>, p));
     } else {
-        scan_tc_kernel<KR, PAIR, TSA><<<tc_num_sms(), kTcThreads, smem, st>>>(p);
+        scan_tc_kernel<KR, PAIR, TSA, SA><<<tc_num_sms(), kTcThreads, smem, st>>>(p);
     }
     VIDX_LAUNCHED();
 }
 void launch_scan_tc(const TcParams& p, cudaStream_t st) {
     const bool pair = p.pair != 0;
     const int kr = p.k <= 8 ? 8 : (p.k <= 16 ? 16 : 32);
-    const size_t smem = tc_smem_layout(p.Dh, kr, pair).total;
-    if (pair) {
+    const TcSmemLayout L = tc_smem_layout(p.Dh, kr, pair);
+    const size_t smem = L.total;
+    if (L.stream_a) {
+        if (!p.a_tiles) throw ApiError(6, "tensor-core scan: streamed query tiles were not prepared");
+        if (kr == 8) launch_scan_tc_kr<8, false, false, true>(p, smem, st);
+        else if (kr == 16) launch_scan_tc_kr<16, false, false, true>(p, smem, st);
+        else launch_scan_tc_kr<32, false, false, true>(p, smem, st);
+    } else if (pair) {
         if (kr == 8) launch_scan_tc_kr<8, true>(p, smem, st);
         else if (kr == 16) launch_scan_tc_kr<16, true>(p, smem, st);
         else launch_scan_tc_kr<32, true>(p, smem, st);

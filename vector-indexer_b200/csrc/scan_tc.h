@@ -26,7 +26,7 @@ struct TcItem {      // one work item: query tile x list chunk (32 bytes)
     uint32_t nq_tile;    // rows in use (<= 128; <= 256 for the CTA-pair kernel)
     uint32_t g_list;     // first group of the list (this rank's part)
     uint32_t ngl;        // groups of the list (this rank's part)
-    uint32_t valid, pad;
+    uint32_t valid, pad;  // pad: streamed query tiles (D > 512) -- first row of the item's tile in TcParams::a_tiles
 };
 
 struct TcParams {
@@ -73,6 +73,7 @@ struct TcParams {
     uint32_t flags;                // bit 0: keep the rows' sets CTA-local in the main pass (no cross-CTA merge at item ends);
                                    // bits 1, 2: timing ablations (VIDX_TC_FLAGS, wrong answers): epilogue / MMAs do nothing;
                                    // bit 3: the producer feeds the two tile pipelines independently instead of in tile order
+    const uint4* a_tiles;          // D > 512 only (tc_streams_a): every work item's query tile as fp16 in operand layout (launch_tc_atiles)
 };
 
 struct FinalizeParams {
@@ -111,6 +112,13 @@ struct FinalizeParams {
 
 bool tc_supported(int D, uint32_t k);  // D = vector dimension
 bool tc_tsa_supported(int Dh);
+// D > 512: the query tile does not fit in shared memory next to the ring and is streamed through it (TcParams::a_tiles)
+bool tc_streams_a(int D, uint32_t k);
+size_t tc_atile_rows_cap(size_t npairs, size_t nlist);  // rows (of Dh 16-byte chunks) a_tiles needs for a grouping of npairs (query, list) pairs
+// rows8, a_rowoff: nlist + 1 entries each; a_tiles: tc_atile_rows_cap(...) * Dh * 16 bytes.  Needs the TcScale of the batch.
+void launch_tc_atiles(const uint32_t* list_cnt, const uint32_t* list_qoff, const uint2* list_qlist, uint32_t nlist, size_t npairs_cap,
+                      const float4* xq4, int Dq, int Dh, const TcScale* scale, uint32_t* rows8, uint32_t* a_rowoff, uint32_t* scan_tmp,
+                      uint4* a_tiles, cudaStream_t st);
 int tc_dh(int D);  // chunks per vector of the shadow store (dimension padded to a multiple of 16)
 // |v|^2 per row (0 for padding rows) and, in stats[0], the float bits of the largest |component|.
 void launch_row_norms(const float4* vecs, int Dq, const uint32_t* row_src, size_t nrows, float* vn_true, uint32_t* stats,
@@ -130,7 +138,7 @@ void launch_tc_items(const uint32_t* list_cnt, const uint32_t* list_ngroups, uin
                      uint32_t seed_tiles, uint32_t* chunk_out, uint32_t* items_per_list, bool pair, cudaStream_t st);
 void launch_tc_expand(const uint32_t* list_cnt, const uint32_t* list_ngroups, const uint32_t* list_g0, const uint32_t* list_qoff,
                       const uint32_t* item_off, const uint32_t* chunk_tiles, uint32_t nlist, uint32_t seed_tiles, TcItem* items,
-                      bool pair, cudaStream_t st);
+                      bool pair, const uint32_t* a_rowoff, cudaStream_t st);
 void launch_scan_tc(const TcParams& p, cudaStream_t st);
 void make_shadow_tensor_map(CUtensorMap* out, const void* vecs16, uint64_t nrows, int Dh);
 void launch_pair_tiles(const uint32_t* probes, size_t npairs, const uint32_t* list_ngroups, uint32_t* pair_tiles, cudaStream_t st);
