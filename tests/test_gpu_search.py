@@ -203,6 +203,30 @@ def test_repeated_search_identical(oracle, ffi):
         assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
 
 
+def test_repeated_searches_are_replayed_as_graphs(oracle, ffi):
+    """The second search with the same arguments is captured into a CUDA graph, later ones replay it (index.cu, run_cached).
+    Interleaved shapes on one handle: a larger batch moves the context's buffers, which must drop the captured graph;
+    changing the scan mode (handle epoch) must do the same.  Every answer is compared with the oracle's."""
+    xb, xq = bench_data(20000, 64, 900)
+    oix, gix = make_pair(oracle, ffi, xb, 30)
+    before = ffi.kernel_launch_count()
+    small = [check_search(oix, gix, xq[:100], 10, 4) for _ in range(4)]
+    per_call = (ffi.kernel_launch_count() - before) // 4
+    assert per_call > 5 and ffi.kernel_launch_count() - before == 4 * per_call  # replays count their kernels too
+    big = [check_search(oix, gix, xq, 10, 6) for _ in range(3)]      # grows the buffers
+    again = [check_search(oix, gix, xq[:100], 10, 4) for _ in range(3)]
+    for D, I in small[1:] + again:
+        assert np.array_equal(D.view(np.uint32), small[0][0].view(np.uint32)) and np.array_equal(I, small[0][1])
+    for D, I in big[1:]:
+        assert np.array_equal(D.view(np.uint32), big[0][0].view(np.uint32)) and np.array_equal(I, big[0][1])
+    gix.set_scan_mode(1)  # exact kernels: same answer, other launches
+    for _ in range(3):
+        check_search(oix, gix, xq[:100], 10, 4)
+    xq2 = xq[100:200].copy()  # same shape, other queries, same staging buffers: the replay reads the new contents
+    for _ in range(2):
+        check_search(oix, gix, xq2, 10, 4)
+
+
 def test_search_stats_and_launch_counter(oracle, ffi):
     xb, xq = bench_data(20000, 64, 500)
     _, gix = make_pair(oracle, ffi, xb, 100)

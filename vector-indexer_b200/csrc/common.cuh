@@ -43,6 +43,13 @@ extern std::atomic<uint64_t> g_kernel_launches;
         VIDX_CUDA(cudaGetLastError());             \
     } while (0)
 
+// Allocations made by this thread's DevBufs so far: a cached CUDA graph of a search holds the addresses of its context's
+// buffers, so a lease that saw one of them move drops the graph (index.cu, CtxLease).
+inline uint64_t& devbuf_allocs() {
+    static thread_local uint64_t n = 0;
+    return n;
+}
+
 // Grow-only device buffer.
 struct DevBuf {
     void* p = nullptr;
@@ -60,6 +67,7 @@ struct DevBuf {
         if (bytes <= cap) return;
         release();
         size_t want = bytes + bytes / 8 + 256;
+        devbuf_allocs()++;
         VIDX_CUDA(cudaMalloc(&p, want));
         cap = want;
     }

@@ -515,6 +515,12 @@ struct CoarseWs {
     DevBuf probes0, list_cnt, list_cur, list_qoff, list_qlist, items_per_list, item_off, items, qnorm, gthr, cand_cnt, overflow, cand, gtop, glock, tcscale, counters, scan_tmp, dist_tmp,
         submin, sel_pos, sel_val, a_rows8, a_rowoff, a_tiles;
 };
+// What a captured search depends on besides the device-side contents of its buffers: the call's arguments, the handle's
+// state (epoch) and the tuning environment.
+struct GraphKey {
+    uint64_t v[12] = {};
+    bool operator==(const GraphKey& o) const { return memcmp(v, o.v, sizeof(v)) == 0; }
+};
 // One search in flight.  A call takes a context from the handle's pool, enqueues on its stream (or the caller's) and
 // hands it back; `done` marks the end of that work, and whoever takes the context next makes its stream wait for it,
 // so contexts are reused in stream order without ever being shared by two searches.
@@ -530,9 +536,20 @@ struct SearchCtx {
     bool used = false;
     double st_ms[6] = {};
     vidx_search_stats stats{};
+    // A search repeated with the same arguments is replayed as a CUDA graph (run_cached below): `seen` = the key of the last
+    // call that ran launch by launch, `gkey` = the key `gexec` was captured for.
+    GraphKey seen{}, gkey{};
+    cudaGraphExec_t gexec = nullptr;
+    uint64_t g_launches = 0;
+    void drop_graph() {
+        if (gexec) cudaGraphExecDestroy(gexec);
+        gexec = nullptr;
+        seen = GraphKey{};
+    }
     ~SearchCtx() {
         if (stream) {
             cudaStreamSynchronize(stream);
+            drop_graph();
             for (auto& ev : events)
                 if (ev) cudaEventDestroy(ev);
             if (done) cudaEventDestroy(done);
@@ -581,13 +598,105 @@ struct CtxLease {
     Index& ix;
     SearchCtx* c;
     cudaStream_t st = nullptr;
+    const uint64_t allocs0 = devbuf_allocs();
     explicit CtxLease(Index& i) : ix(i), c(i.acquire_ctx()) {}
     void use(cudaStream_t s) {
         st = s;
         if (c->used) VIDX_CUDA(cudaStreamWaitEvent(st, c->done, 0));  // the context's previous search, whatever stream it ran on
     }
-    ~CtxLease() { ix.release_ctx(c, st); }
+    ~CtxLease() {
+        if (devbuf_allocs() != allocs0) c->drop_graph();  // a buffer of the context may have moved: its graph holds the old address
+        ix.release_ctx(c, st);
+    }
 };
+
+// ------------------------------------------------------------------------------------
+// Replay of repeated searches.  A search is ~45 launches of which ~35 run for a few microseconds; for small batches (and
+// for every rank of a multi-GPU grid) the step is bound by launching them.  The sequence has no host synchronisation and
+// depends on the host only through the call's arguments, so the SECOND call with the same arguments on a context is
+// captured into a CUDA graph and every later one is a single cudaGraphLaunch.  The first call runs launch by launch: it
+// sizes every buffer, so that nothing is allocated during capture.  Anything that could change what the launches look
+// like is part of the key (arguments, handle epoch, VIDX_* environment); a buffer of the context that moves drops the
+// graph (CtxLease).  VIDX_GRAPH=0 switches the replay off.
+// ------------------------------------------------------------------------------------
+extern "C" char** environ;
+static uint64_t tuning_env_hash() {
+    uint64_t h = 1469598103934665603ull;
+    for (char** e = environ; e && *e; e++) {
+        if (strncmp(*e, "VIDX_", 5) != 0) continue;
+        for (const char* c = *e; *c; c++) h = (h ^ (unsigned char)*c) * 1099511628211ull;
+        h = (h ^ 0xffu) * 1099511628211ull;
+    }
+    return h;
+}
+static bool graph_replay_enabled() {
+    const char* v = getenv("VIDX_GRAPH");
+    return !(v && *v && atoi(v) == 0);
+}
+template <class F>
+static void run_cached(Index& ix, SearchCtx& c, GraphKey key, cudaStream_t st, F&& enqueue) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (ix.profiling || !graph_replay_enabled() || cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
+        cudaGetLastError();
+        enqueue();
+        return;
+    }
+    key.v[10] = ix.epoch;
+    key.v[11] = tuning_env_hash();
+    if (c.gexec && c.gkey == key) {
+        VIDX_CUDA(cudaGraphLaunch(c.gexec, st));
+        g_kernel_launches.fetch_add(c.g_launches);
+        c.stats.kernel_launches = c.g_launches;
+        return;
+    }
+    if (!(c.seen == key)) {  // first call with these arguments: launch by launch (allocates what the batch needs)
+        c.seen = key;
+        enqueue();
+        return;
+    }
+    if (c.gexec) cudaGraphExecDestroy(c.gexec);
+    c.gexec = nullptr;
+    const uint64_t allocs0 = devbuf_allocs(), launches0 = g_kernel_launches.load();
+    VIDX_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+    cudaGraph_t graph = nullptr;
+    try {
+        enqueue();
+    } catch (...) {
+        cudaStreamEndCapture(st, &graph);
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        c.seen = GraphKey{};
+        throw;
+    }
+    VIDX_CUDA(cudaStreamEndCapture(st, &graph));
+    const uint64_t nl = g_kernel_launches.load() - launches0;
+    cudaGraphExec_t exec = nullptr;
+    const bool moved = devbuf_allocs() != allocs0;  // (cannot happen after an identical call; the captured addresses would be stale)
+    if (moved || cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
+        cudaGetLastError();
+        cudaGraphDestroy(graph);
+        c.seen = GraphKey{};
+        g_kernel_launches.fetch_sub(nl);
+        enqueue();
+        return;
+    }
+    cudaGraphDestroy(graph);
+    c.gexec = exec;
+    c.gkey = key;
+    c.g_launches = nl;
+    VIDX_CUDA(cudaGraphLaunch(exec, st));
+}
+// The collective search: its two all-gathers are captured with the kernels (NCCL supports stream capture; every rank runs
+// the same call sequence, so all of them capture on the same call).  VIDX_GRAPH_MULTI=0 keeps the multi-GPU path launch by launch.
+template <class F>
+static void run_cached_multi(Index& ix, SearchCtx& c, const GraphKey& key, cudaStream_t st, F&& enqueue) {
+    const char* v = getenv("VIDX_GRAPH_MULTI");
+    if (v && *v && atoi(v) == 0) {
+        enqueue();
+        return;
+    }
+    run_cached(ix, c, key, st, enqueue);
+}
 
 // auto mode: the tensor-core filter when the table has at least kCoarseTcMinLists lists (the bench index keeps 1023 of its 1024)
 // and the batch at least
@@ -1469,6 +1578,7 @@ int vidx_set_limits(vidx_index* idx, uint64_t default_k, uint64_t default_n_prob
     return guarded([&] {
         require(idx, VIDX_ERR_INVALID_INPUT, "idx is NULL");
         ExclusiveLock lk(idx->mu);
+        idx->ix.epoch++;
         idx->ix.default_k = default_k;
         idx->ix.default_n_probe = default_n_probe;
         idx->ix.max_k = max_k;
@@ -1499,6 +1609,7 @@ int vidx_build(vidx_index* idx, const float* data, const uint64_t* ext_ids, cons
     return guarded([&] {
         require(idx, VIDX_ERR_INVALID_INPUT, "idx is NULL");
         ExclusiveLock lk(idx->mu);
+        idx->ix.epoch++;
         Index& ix = idx->ix;
         require(n > 0 && data, VIDX_ERR_INVALID_INPUT, "no vectors provided");  // api.rs:116-118
         ix.ensure_device();
@@ -1513,6 +1624,7 @@ int vidx_build_device(vidx_index* idx, const float* d_data, const uint64_t* ext_
     return guarded([&] {
         require(idx, VIDX_ERR_INVALID_INPUT, "idx is NULL");
         ExclusiveLock lk(idx->mu);
+        idx->ix.epoch++;
         Index& ix = idx->ix;
         require(n > 0 && d_data, VIDX_ERR_INVALID_INPUT, "no vectors provided");
         ix.ensure_device();
@@ -1567,6 +1679,7 @@ int vidx_train(vidx_index* idx, const float* data, uint64_t n, uint64_t seed, ui
     return guarded([&] {
         require(idx, VIDX_ERR_INVALID_INPUT, "idx is NULL");
         ExclusiveLock lk(idx->mu);
+        idx->ix.epoch++;
         DevBuf d_data, d_labels;
         do_train(idx->ix, data, n, seed, nlist, max_iters, d_data, d_labels);
     });
@@ -1576,6 +1689,7 @@ int vidx_add(vidx_index* idx, const float* data, const uint64_t* ext_ids, const 
     return guarded([&] {
         require(idx, VIDX_ERR_INVALID_INPUT, "idx is NULL");
         ExclusiveLock lk(idx->mu);
+        idx->ix.epoch++;
         Index& ix = idx->ix;
         require(ix.trained, VIDX_ERR_INVALID_INPUT, "vidx_add before vidx_train");
         require(n > 0 && data, VIDX_ERR_INVALID_INPUT, "no vectors provided");
@@ -1603,6 +1717,7 @@ int vidx_build_from_labels(vidx_index* idx, const float* data, const uint64_t* e
         require(idx, VIDX_ERR_INVALID_INPUT, "idx is NULL");
         require(n > 0 && data && centroids && labels && k > 0, VIDX_ERR_INVALID_INPUT, "no vectors provided");
         ExclusiveLock lk(idx->mu);
+        idx->ix.epoch++;
         Index& ix = idx->ix;
         ix.ensure_device();
         DevBuf d_data;
@@ -1650,13 +1765,26 @@ static void search_host(vidx_index* idx, const float* xq, uint64_t nq, uint64_t 
         // only the rows of this rank's query group are needed on this device
         const MultiPlan m = plan_multi(ix, nq);
         h2d(c.io_xq.as<float>(), xq + m.qlo * ix.dim, (size_t)(m.qhi - m.qlo) * ix.dim, c.stream);
-        search_multi_device(ix, c, c.io_xq.as<float>(), nq, k, n_probe, c.io_D.as<float>(), c.io_I.as<int64_t>(), c.stream, true);
+        GraphKey key;
+        key.v[0] = 2;
+        key.v[1] = (uint64_t)(uintptr_t)c.io_xq.p; key.v[2] = nq; key.v[3] = k; key.v[4] = n_probe;
+        key.v[5] = (uint64_t)(uintptr_t)c.io_D.p; key.v[6] = (uint64_t)(uintptr_t)c.io_I.p; key.v[7] = 1;
+        run_cached_multi(ix, c, key, c.stream, [&] {
+            search_multi_device(ix, c, c.io_xq.as<float>(), nq, k, n_probe, c.io_D.as<float>(), c.io_I.as<int64_t>(), c.stream, true);
+        });
     } else {
         h2d(c.io_xq.as<float>(), xq, (size_t)nq * ix.dim, c.stream);
     }
-    if (!multi)
-        ix.search_device(c, c.io_xq.as<float>(), nq, k, n_probe, c.io_D.as<float>(), c.io_I.as<int64_t>(),
-                         V ? c.io_rows.as<uint32_t>() : nullptr, c.stream, nullptr, nullptr);
+    if (!multi) {
+        GraphKey key;
+        key.v[0] = 1;
+        key.v[1] = (uint64_t)(uintptr_t)c.io_xq.p; key.v[2] = nq; key.v[3] = k; key.v[4] = n_probe;
+        key.v[5] = (uint64_t)(uintptr_t)c.io_D.p; key.v[6] = (uint64_t)(uintptr_t)c.io_I.p; key.v[7] = V ? (uint64_t)(uintptr_t)c.io_rows.p : 0;
+        run_cached(ix, c, key, c.stream, [&] {
+            ix.search_device(c, c.io_xq.as<float>(), nq, k, n_probe, c.io_D.as<float>(), c.io_I.as<int64_t>(),
+                             V ? c.io_rows.as<uint32_t>() : nullptr, c.stream, nullptr, nullptr);
+        });
+    }
     VIDX_CUDA(cudaMemcpyAsync(D, c.io_D.p, nres * 4, cudaMemcpyDeviceToHost, c.stream));
     VIDX_CUDA(cudaMemcpyAsync(I, c.io_I.p, nres * 8, cudaMemcpyDeviceToHost, c.stream));
     if (V) {
@@ -1689,7 +1817,13 @@ int vidx_search_device(vidx_index* idx, const float* d_xq, uint64_t nq, uint64_t
         ix.ensure_device();
         CtxLease lease(ix);
         lease.use(stream ? (cudaStream_t)stream : lease.c->stream);
-        ix.search_device(*lease.c, d_xq, nq, k, n_probe, d_D, d_I, nullptr, lease.st, nullptr, nullptr);
+        GraphKey key;
+        key.v[0] = 1;
+        key.v[1] = (uint64_t)(uintptr_t)d_xq; key.v[2] = nq; key.v[3] = k; key.v[4] = n_probe;
+        key.v[5] = (uint64_t)(uintptr_t)d_D; key.v[6] = (uint64_t)(uintptr_t)d_I;
+        run_cached(ix, *lease.c, key, lease.st, [&] {
+            ix.search_device(*lease.c, d_xq, nq, k, n_probe, d_D, d_I, nullptr, lease.st, nullptr, nullptr);
+        });
     });
 }
 int vidx_coarse_probes(vidx_index* idx, const float* xq, uint64_t nq, uint64_t n_probe, uint32_t* lists, float* dists) {
@@ -1929,6 +2063,7 @@ int vidx_save(const vidx_index* cidx, const char* index_dir, const char* shards_
         vidx_index* idx = const_cast<vidx_index*>(cidx);
         require(idx && index_dir && shards_dir, VIDX_ERR_INVALID_INPUT, "NULL argument");
         ExclusiveLock lk(idx->mu);
+        idx->ix.epoch++;
         Index& ix = idx->ix;
         require(ix.built, VIDX_ERR_OTHER, "index has not been built or loaded");
         require(!(ix.resident_partial && ix.part_by_ranges), VIDX_ERR_UNSUPPORTED,
@@ -1960,6 +2095,7 @@ int vidx_load(vidx_index* idx, const char* index_dir, const char* shards_dir) {
     return guarded([&] {
         require(idx && index_dir && shards_dir, VIDX_ERR_INVALID_INPUT, "NULL argument");
         ExclusiveLock lk(idx->mu);
+        idx->ix.epoch++;
         Index& ix = idx->ix;
         LoadedMeta M;
         load_index_meta(index_dir, shards_dir, M);
@@ -2058,6 +2194,7 @@ int vidx_set_partition(vidx_index* idx, int rank, int world) {
         require(idx, VIDX_ERR_INVALID_INPUT, "idx is NULL");
         require(world >= 1 && rank >= 0 && rank < world, VIDX_ERR_INVALID_INPUT, "bad rank/world");
         ExclusiveLock lk(idx->mu);
+        idx->ix.epoch++;
         Index& ix = idx->ix;
         if (!ix.built) {  // before build / load: only the owned part will ever reach HBM
             ix.part_rank = rank;
@@ -2084,6 +2221,7 @@ int vidx_set_partition_mode(vidx_index* idx, int mode) {
         require(idx, VIDX_ERR_INVALID_INPUT, "idx is NULL");
         require(mode >= 0 && mode <= 2, VIDX_ERR_INVALID_INPUT, "partition mode must be 0 (auto), 1 (shards) or 2 (ranges)");
         ExclusiveLock lk(idx->mu);
+        idx->ix.epoch++;
         const int m0 = idx->ix.part_mode;
         idx->ix.part_mode = mode;
         if (idx->ix.built) {
@@ -2196,6 +2334,7 @@ int vidx_comm_init(vidx_index* idx, int rank, int world, const uint8_t* unique_i
         require(idx && unique_id, VIDX_ERR_INVALID_INPUT, "NULL argument");
         require(world >= 1 && rank >= 0 && rank < world, VIDX_ERR_INVALID_INPUT, "bad rank/world");
         ExclusiveLock lk(idx->mu);
+        idx->ix.epoch++;
         Index& ix = idx->ix;
         ix.ensure_device();
         comm_destroy(ix.comm);
@@ -2207,6 +2346,7 @@ int vidx_comm_destroy(vidx_index* idx) {
     return guarded([&] {
         require(idx, VIDX_ERR_INVALID_INPUT, "idx is NULL");
         ExclusiveLock lk(idx->mu);
+        idx->ix.epoch++;
         if (idx->ix.comm) {
             idx->ix.ensure_device();
             comm_destroy(idx->ix.comm);
@@ -2228,7 +2368,13 @@ int vidx_search_multi_device(vidx_index* idx, const float* d_xq, uint64_t nq, ui
         ix.ensure_device();
         CtxLease lease(ix);
         lease.use(stream ? (cudaStream_t)stream : lease.c->stream);
-        search_multi_device(ix, *lease.c, d_xq, nq, k, n_probe, d_D, d_I, lease.st);
+        GraphKey key;
+        key.v[0] = 2;
+        key.v[1] = (uint64_t)(uintptr_t)d_xq; key.v[2] = nq; key.v[3] = k; key.v[4] = n_probe;
+        key.v[5] = (uint64_t)(uintptr_t)d_D; key.v[6] = (uint64_t)(uintptr_t)d_I;
+        run_cached_multi(ix, *lease.c, key, lease.st, [&] {
+            search_multi_device(ix, *lease.c, d_xq, nq, k, n_probe, d_D, d_I, lease.st);
+        });
     });
 }
 
@@ -2237,6 +2383,7 @@ int vidx_set_profiling(vidx_index* idx, int enabled) {
     return guarded([&] {
         require(idx, VIDX_ERR_INVALID_INPUT, "idx is NULL");
         ExclusiveLock lk(idx->mu);
+        idx->ix.epoch++;
         idx->ix.profiling = enabled != 0;
     });
 }
@@ -2244,6 +2391,7 @@ int vidx_set_coarse_mode(vidx_index* idx, int mode) {
     return guarded([&] {
         require(idx && mode >= 0 && mode <= 2, VIDX_ERR_INVALID_INPUT, "coarse mode must be 0 (auto), 1 (exact) or 2 (filter)");
         ExclusiveLock lk(idx->mu);
+        idx->ix.epoch++;
         idx->ix.coarse_mode = mode;
     });
 }
@@ -2252,6 +2400,7 @@ int vidx_set_scan_mode(vidx_index* idx, int mode) {
         require(idx, VIDX_ERR_INVALID_INPUT, "idx is NULL");
         require(mode >= 0 && mode <= 3, VIDX_ERR_INVALID_INPUT, "mode must be 0 (auto), 1 (exact), 2 (filter, seeded) or 3 (filter, bounds pass first)");
         ExclusiveLock lk(idx->mu);
+        idx->ix.epoch++;
         idx->ix.scan_mode = mode;
     });
 }

@@ -92,6 +92,8 @@ struct Index {
     void release_ctx(SearchCtx* c, cudaStream_t last_stream);
 
     Comm* comm = nullptr;  // vidx_comm_init
+    uint64_t epoch = 0;    // bumped by every call that takes the handle exclusively (build, load, set_*): cached search graphs of an
+                           // older epoch are never replayed
 
     // measurement
     bool profiling = false;
