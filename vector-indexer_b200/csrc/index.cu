@@ -9,6 +9,7 @@
 #include <shared_mutex>
 #include <numeric>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/vidx_b200.h"
@@ -155,7 +156,7 @@ bool Index::list_fully_resident(uint64_t l) const {
     return res_seg[l].x == list_seg_off_all[l] && res_seg[l].y == list_seg_off_all[l + 1];
 }
 uint64_t Index::resident_bytes() const {
-    return d_vecs.cap + d_vecs16.cap + d_vnorm.cap + d_row_ext.cap;
+    return d_vecs.cap + d_vecs16.cap + d_vnorm.cap + d_row_ext.cap + d_shadow_perm.cap + d_vnorm32.cap + d_gmin.cap;
 }
 
 void Index::build_lists(const float* d_data, uint64_t n, const uint32_t* labels, const uint64_t* ext, const uint64_t* ts,
@@ -224,6 +225,9 @@ void Index::finish_store(const float* d_data) {
     d_vecs.release();
     d_vecs16.release();
     d_vnorm.release();
+    d_shadow_perm.release();
+    d_vnorm32.release();
+    d_gmin.release();
     d_row_ext.release();
     d_vecs.reserve(std::max<uint64_t>(nrows, 1) * Dq * 16);
     DevBuf d_row_src;
@@ -331,8 +335,47 @@ void Index::finish_store(const float* d_data) {
         d_vecs16.reserve(tc_ok ? (std::max<uint64_t>(nrows, 1) * Dh * 16) : 16);
         d_vnorm.reserve((std::max<uint64_t>(nrows, 1) + 128) * 16);  // rows are whole supergroups: a tile copy reads 128 entries
         if (tc_ok) {
+            // The shadow rows of every 1024-vector segment are SORTED BY NORM (stable; padding rows last): the 32 rows of a group
+            // then have nearly the same norm term, which is what lets the main pass add the norm in its epilogue instead of by
+            // a ninth MMA per tile (scan_tc_kernel<.., NB>).  The segment is the unit every partition is made of, so the
+            // shadow rows a rank scans are always the same vectors as the fp32 rows of its segments.  Survivors are mapped
+            // back through d_shadow_perm, so row order -- the reference's tie-break -- is that of the fp32 store.
+            std::vector<uint32_t> perm(nrows);
+            std::iota(perm.begin(), perm.end(), 0u);
+            {
+                const uint64_t nsegs = nrows / kSegVecs + 1;
+                std::vector<std::pair<uint32_t, uint32_t>> ranges;  // [first row, end row) of every resident segment
+                ranges.reserve(nsegs);
+                for (uint64_t l = 0; l < nlist; l++)
+                    for (uint32_t sidx = res_seg[l].x; sidx < res_seg[l].y; sidx++) {
+                        const uint32_t r0 = local_group_of_seg(l, sidx) * kGroup;
+                        ranges.emplace_back(r0, r0 + segs[sidx].ng * kGroup);
+                    }
+                auto sort_ranges = [&](size_t a, size_t b) {
+                    for (size_t i = a; i < b; i++)
+                        std::stable_sort(perm.begin() + ranges[i].first, perm.begin() + ranges[i].second, [&](uint32_t x, uint32_t y) {
+                            const float nx = row_src[x] == kNoRow ? INFINITY : vt[x], ny = row_src[y] == kNoRow ? INFINITY : vt[y];
+                            return nx < ny;
+                        });
+                };
+                const size_t nthr = std::min<size_t>(16, std::max<size_t>(1, ranges.size() / 64));
+                if (nthr <= 1) {
+                    sort_ranges(0, ranges.size());
+                } else {
+                    std::vector<std::thread> th;
+                    for (size_t t = 0; t < nthr; t++)
+                        th.emplace_back(sort_ranges, ranges.size() * t / nthr, ranges.size() * (t + 1) / nthr);
+                    for (auto& x : th) x.join();
+                }
+            }
+            d_shadow_perm.reserve(std::max<uint64_t>(nrows, 1) * 4);
+            d_vnorm32.reserve(std::max<uint64_t>(nrows, 1) * 4);
+            d_gmin.reserve((std::max<uint64_t>(nrows, 1) / kGroup + 4) * 4);
+            h2d(d_shadow_perm.as<uint32_t>(), perm.data(), nrows, stream);
             launch_convert16(d_vecs.as<float4>(), Dq, Dh, d_row_src.as<uint32_t>(), nrows, d_vntrue.as<float>(), tc_sv, tc_g,
-                             d_vecs16.as<uint4>(), d_vnorm.as<uint4>(), stream);
+                             d_vecs16.as<uint4>(), d_vnorm.as<uint4>(), stream, d_shadow_perm.as<uint32_t>(), d_vnorm32.as<float>(),
+                             d_gmin.as<float>());
+            VIDX_CUDA(cudaStreamSynchronize(stream));  // (perm is a local)
             make_shadow_tensor_map(&shadow_tmap, d_vecs16.p, std::max<uint64_t>(nrows, 1), Dh);
         }
         VIDX_CUDA(cudaStreamSynchronize(stream));
@@ -876,6 +919,9 @@ void Index::search_device(SearchCtx& ctx, const float* d_xq, uint64_t nq, uint64
     // tensor-core pre-filter + exact finalize whenever the shape allows; the exact kernels then
     // only see the queries it hands back (survivor buffer overflow)
     const bool tc = fused && scan_mode != 1 && tc_ok && tc_supported((int)dim, (uint32_t)k) && !coarse_only;
+    // main pass with the norm added in the epilogue (eight MMAs per 128-d tile instead of nine): VIDX_TC_NB=1.  Bit-exact and
+    // measured SLOWER on the bench workload (2.23 vs 2.10 ms): the scan is bound by its epilogue, not by the tensor pipe.
+    const bool tc_nb = [&] { const char* v = getenv("VIDX_TC_NB"); return v && *v && atoi(v) != 0; }();
     const bool tc_sa = tc && tc_streams_a((int)dim, (uint32_t)k);  // D > 512: query tiles streamed through the ring (scan_tc.cu)
     const int Dh16 = tc_dh((int)dim);
     // two passes of the filter when a query visits few tiles (the HBM-bound regime): a bounds pass that only records
@@ -1158,6 +1204,9 @@ void Index::search_device(SearchCtx& ctx, const float* d_xq, uint64_t nq, uint64
             TcParams tp{};
             tp.vecs16 = d_vecs16.as<uint4>();
             tp.vnorm = d_vnorm.as<uint4>();
+            tp.perm = d_shadow_perm.as<uint32_t>();
+            tp.gmin = d_gmin.as<float>();
+            tp.vnorm32 = d_vnorm32.as<float>();
             tp.Dh = tc_dh((int)dim);
             tp.Dq = Dq;
             tp.scale = reinterpret_cast<const TcScale*>(w.tcscale.as<unsigned char>() + 16);
@@ -1224,6 +1273,7 @@ void Index::search_device(SearchCtx& ctx, const float* d_xq, uint64_t nq, uint64
             tp.mode = 0;
             tp.frozen = tc_dump ? 1 : 0;
             tp.flags = tc_flags;
+            tp.nb = tc_nb ? 1u : 0u;
             tp.pair = tc_pair ? 1u : 0u;
             tp.tsa = tc_tsa ? 1u : 0u;
             if (tc_pair) tp.tmap = shadow_tmap;

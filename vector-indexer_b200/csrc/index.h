@@ -66,7 +66,8 @@ struct Index {
     // device store
     cudaStream_t stream = nullptr;        // build / load / save stream
     uint32_t ncgroups = 0;
-    DevBuf d_vecs, d_cents, d_row_ext, d_segs, d_list_seg, d_list_g0, d_list_ng, d_list_len, d_vnorm, d_vecs16, d_list_rowdelta;
+    DevBuf d_vecs, d_cents, d_row_ext, d_segs, d_list_seg, d_list_g0, d_list_ng, d_list_len, d_vnorm, d_vecs16, d_list_rowdelta,
+        d_shadow_perm, d_vnorm32, d_gmin;  // shadow row -> store row (norm-sorted segments), fp32 norm terms, their group minima
     float vn_max = 0.0f;   // max |v|^2 over the stored rows (bound for the tensor-core filter)
     float vmax = 0.0f;     // max |component| over the stored rows
     int tc_sv = 0, tc_g = 0;  // fp16 shadow store: vectors scaled by 2^sv, norm terms by 2^(2sv-g)

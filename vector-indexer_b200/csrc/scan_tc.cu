@@ -77,6 +77,10 @@ constexpr int kTcMaxChunkTiles = VIDX_CHUNK_TILES; // tiles per work item: chose
 __host__ __device__ constexpr int tc_queue_cap(int kr) { return kr > 16 ? 128 : 512; }
 __host__ __device__ constexpr int tc_stage_cap(int kr) { return kr > 16 ? 144 : 512; }
 constexpr int kTcAccStages = 4;      // accumulator tiles in TMEM
+#ifndef VIDX_FLOOD_AFTER
+#define VIDX_FLOOD_AFTER 2
+#endif
+constexpr uint32_t kTcFloodAfter = VIDX_FLOOD_AFTER;  // values a thread queues per item before it starts tracking its own k smallest
 constexpr int kTcMergeTries = 4;     // end-of-item merge of a row's set into the shared one: attempts at the row's lock
 constexpr uint32_t kTcACol = 384;    // A-in-TMEM variant: three accumulator stages, then the query tile (4 columns per 8 dims), then
                                      // the 8 columns of the norm step's A operand
@@ -340,15 +344,18 @@ __global__ void row_norm_kernel(const float4* __restrict__ vecs, int Dq, const u
 // Shadow store: chunk c of a row = dims 8c..8c+7 as fp16 (round to nearest) of v * 2^sv, zero beyond the dimension.
 // Norm terms: b = (1-eps)|v|^2 * 2^(2sv-g) as three fp16 values rounded DOWN (hi + mid + lo <= b, so the filter
 // value can only get smaller); NaN for padding rows (NaN never passes a '<=' test).
+// perm != nullptr: shadow row `row` holds the vector of store row perm[row] (rows sorted by norm inside every 1024-vector segment,
+// see Index::finish_store); vnorm32[row] = the same norm term as ONE fp32 value rounded down (epilogue-side norms, scan_tc_kernel<.., NB>).
 __global__ void convert16_kernel(const float4* __restrict__ vecs, int Dq, int Dh, const uint32_t* __restrict__ row_src, size_t nrows,
-                                 const float* __restrict__ vn_true, float vscale, float nscale, uint4* __restrict__ vecs16,
-                                 uint4* __restrict__ vnorm) {
+                                 const float* __restrict__ vn_true, float vscale, float nscale, const uint32_t* __restrict__ perm,
+                                 uint4* __restrict__ vecs16, uint4* __restrict__ vnorm, float* __restrict__ vnorm32) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // (row, chunk), row fastest: coalesced on both sides
     size_t row = i % nrows;
     int c = (int)(i / nrows);
     if (c >= Dh) return;
-    const bool pad = row_src[row] == kNoRow;
-    const float4* p = vecs + f4_row_base(row, Dq);
+    const size_t srow = perm ? perm[row] : row;  // row of the fp32 store
+    const bool pad = row_src[srow] == kNoRow;
+    const float4* p = vecs + f4_row_base(srow, Dq);
     float4 a = make_float4(0, 0, 0, 0), b = a;
     if (!pad && 2 * c < Dq) a = p[(size_t)(2 * c) * kSuper];
     if (!pad && 2 * c + 1 < Dq) b = p[(size_t)(2 * c + 1) * kSuper];
@@ -363,7 +370,7 @@ __global__ void convert16_kernel(const float4* __restrict__ vecs, int Dq, int Dh
         if (pad) {
             n.x = 0x7e00u;  // fp16 NaN in the hi term
         } else {
-            const float bv = (1.0f - kTcEps) * vn_true[row] * nscale;
+            const float bv = (1.0f - kTcEps) * vn_true[srow] * nscale;
             const __half hi = __float2half_rd(bv);
             const float r1 = bv - __half2float(hi);
             const __half mid = __float2half_rd(r1);
@@ -373,7 +380,18 @@ __global__ void convert16_kernel(const float4* __restrict__ vecs, int Dq, int Dh
             n.y = (uint32_t)__half_as_ushort(lo);
         }
         vnorm[row] = n;
+        // (NaN for padding rows: their accumulator is 0, and NaN never passes a '<=' test -- not even against a cold row's +inf bound)
+        if (vnorm32) vnorm32[row] = pad ? __int_as_float(0x7fc00000) : __fmul_rd(__fmul_rd(1.0f - kTcEps, vn_true[srow]), nscale);
     }
+}
+// The smallest norm term of every group of 32 shadow rows (fminf drops the NaNs of padding rows; NaN for a group of padding only): scan_tc_kernel<.., NB> compares a
+// row's minimum over the group's 32 accumulator columns with its bound minus this.
+__global__ void group_min_norm_kernel(const float* __restrict__ vnorm32, size_t ngroups, float* __restrict__ gmin) {
+    const size_t g = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (g >= ngroups) return;
+    float m = vnorm32[g * 32 + (threadIdx.x & 31)];
+    for (int o = 16; o; o >>= 1) m = fminf(m, __shfl_xor_sync(kFull, m, o));
+    if ((threadIdx.x & 31) == 0) gmin[g] = m;
 }
 __global__ void query_norm_kernel(const float4* __restrict__ xq4, int Dq, uint32_t nq, uint32_t k, float* __restrict__ qn,
                                   uint32_t* __restrict__ gthr_bits, uint32_t* __restrict__ cand_cnt, uint32_t* __restrict__ overflow,
@@ -720,10 +738,17 @@ constexpr uint32_t kEntValid = 0x40000000u;
 // SA: the query tile is streamed through the ring (D > 512, see tc_smem_layout): K-slices of 8 chunks, a stage = list chunks +
 // norm chunk + the query tile's chunks.  A streamed tile has only as many rows as the item has queries (rounded up to 8): the
 // MMA still reads 128 rows, the rows beyond are whatever the stage holds -- rows of the accumulator nobody looks at.
-template <int KR, bool PAIR, bool TSA, bool SA>
+// NB: the norm term is added in the epilogue instead of by a ninth MMA per tile (main pass of the list scan only).  The shadow
+// rows are sorted by norm inside every 1024-vector segment, so the 32 columns of a group have nearly the same norm term: a row's
+// minimum over the group plus the group's SMALLEST norm term (p.gmin, one float4 per tile, fetched while the thread waits for
+// the accumulator) is a lower bound of every filter value of the group, and only when that passes the row's bound -- the rare
+// path, which already costs a branch -- are the columns' own norm terms (p.vnorm32) looked at.  Saves 1/9 of the tensor work
+// at D = 128 and the 2 KB norm chunk per tile.
+template <int KR, bool PAIR, bool TSA, bool SA, bool NB>
 __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(const __grid_constant__ TcParams p) {
     static_assert(!(PAIR && TSA), "the A-in-TMEM variant is single-CTA");
     static_assert(!(SA && (PAIR || TSA)), "the streamed query tile is a variant of the default kernel only");
+    static_assert(!(NB && (PAIR || TSA || SA)), "epilogue-side norms are a variant of the default kernel only");
     extern __shared__ __align__(1024) unsigned char smem[];
     const TcSmemLayout L = SA ? tc_smem_layout_streamed(KR) : tc_smem_layout_resident(p.Dh, KR, PAIR);
     const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
@@ -761,6 +786,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(const __grid_con
     const int Dq = p.Dq, Dh = p.Dh;
     // the batch's scales (uniform loads); a batch that cannot be scaled into fp16 range goes to the exact kernels
     const float tS = p.scale->S, tInvS = p.scale->invS, tQmul = p.scale->qmul, tCabs = p.scale->c_abs;
+    const float tAones = NB ? p.scale->a_ones : 0.0f;  // 2^(sq-sv+g): the stored norm terms times this are in accumulator units
     // flags bit 0: the rows' k-smallest sets stay CTA-local -- gtop (written by the bounds pass) is read-only in the main
     // pass, no seqlock / lock traffic at item boundaries; CTAs still share their bounds through gthr (atomicMin)
     const bool local_sets = (p.flags & 1u) != 0;
@@ -1025,9 +1051,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(const __grid_con
                         if (last) bulk_g2s(sB + s * kStageBytes + kStageData, nsrc + cta_rank * 64u, 1024u, &bar_full[s]);
                     } else {
                         const uint32_t abytes = SA ? nch * a_r8 * 16u : 0u;  // the same K-slice of the query tile: [chunk][a_r8 rows][16 B]
-                        mbar_expect_tx(&bar_full[s], bytes + (last ? 2048u : 0u) + abytes);
+                        const bool nchunk = last && !NB;                     // the tile's norm chunk rides with its last K-slice
+                        mbar_expect_tx(&bar_full[s], bytes + (nchunk ? 2048u : 0u) + abytes);
                         bulk_g2s(sB + s * kStageBytes, src, bytes, &bar_full[s]);
-                        if (last) bulk_g2s(sB + s * kStageBytes + kStageData, nsrc, 2048, &bar_full[s]);
+                        if (nchunk) bulk_g2s(sB + s * kStageBytes + kStageData, nsrc, 2048, &bar_full[s]);
                         if (SA) bulk_g2s(sB + s * kStageBytes + kStageA, asrc0 + (size_t)kc * ((size_t)kSC * a_r8 * 16u), abytes, &bar_full[s]);
                     }
                 }
@@ -1170,7 +1197,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(const __grid_con
 #pragma unroll
                                 for (int ks = 1; ks < kSC / 2; ks++)
                                     if (ks < nks) tc_mma_f16_lo<true>(d_tmem, al + ks * a_kstep, bl + ks * kBStep, desc_hi, idesc);
-                                if (kc == nkc - 1) tc_mma_f16_lo<true>(d_tmem, ones_lo, norm_lo, desc_hi, idesc);
+                                if (kc == nkc - 1 && !NB) tc_mma_f16_lo<true>(d_tmem, ones_lo, norm_lo, desc_hi, idesc);
                                 tc_commit(&bar_empty[s]);                       // K-slice free once these MMAs have read it
                                 if (kc == nkc - 1) tc_commit(&bar_tfull[tf]);   // accumulator tile ready for the epilogue
                             }
@@ -1215,6 +1242,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(const __grid_con
                             qq[u] = s_q[srow];
                             rid[u] = se.x;
                             ok[u] = s_stage_v[i] <= vP[srow];
+                            if (ok[u] && p.perm) rid[u] = __ldg(&p.perm[se.x]);  // shadow row -> row of the fp32 store
                             if (ok[u]) gi[u] = atomicAdd(&p.cand_cnt[qq[u].x], 1u);
                         }
                     }
@@ -1259,6 +1287,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(const __grid_con
                 if (lane == 0) sts_volatile(q_head, head);
                 const uint32_t row = e.x & 127u;
                 const float val = __uint_as_float(e.y);
+#ifdef VIDX_TC_ABLATE
+                if (p.flags & 0x8000u) continue;  // timing only: the selector drains the queue and drops everything
+#endif
                 // (1) survivors: everything still inside the row's bound goes to the exact re-check
                 const bool cand_ok = mine && val <= vP[row];
                 const unsigned cm = __ballot_sync(kFull, cand_ok);
@@ -1334,7 +1365,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(const __grid_con
             const uint32_t kk = p.k;
             const uint32_t submin_row0 = s_impr[row];  // bounds pass only
             float P = s_P[row];
-            float lr[KR];  // the k smallest values this thread queued in this item, descending (+inf until k exist)
+            uint32_t nhit = 0;  // values this thread queued in this item
+            float lr[KR];  // the k smallest values this thread queued in this item (from the third on), descending (+inf until k exist)
 #pragma unroll
             for (int i = 0; i < KR; i++) lr[i] = i < (int)kk ? kInf : -kInf;
             const uint32_t sel = 0;  // (one selector)
@@ -1342,6 +1374,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(const __grid_con
             uint32_t* q_tail = &s_misc[8 + 2 * sel];
             uint32_t* q_head = &s_misc[9 + 2 * sel];
             auto push = [&](uint32_t info, float v) {
+#ifdef VIDX_TC_ABLATE
+                if (p.flags & 0x4000u) return;  // timing only: the hit path runs, nothing is queued
+#endif
                 const uint32_t idx = atomicAdd(q_tail, 1u);
                 for (uint32_t spins = 0; idx - lds_volatile(q_head) >= (uint32_t)kTcQueueCap; spins++) {
                     __nanosleep(32);
@@ -1357,6 +1392,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(const __grid_con
                 const uint32_t sb = TSA ? grp * 4u + ((itt >> 1) & 3u) : s;
                 const uint32_t ph = TSA ? (itt >> 3) & 1 : (itt / kTcAccStages) & 1;
                 const float Pnew = lds_volatile_f(&s_P[row]);  // in flight during the wait
+                // NB: the smallest norm term of each of the tile's four groups (uniform load, in flight during the wait too)
+                float gsc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                if (NB) {
+                    const float4 gm = __ldg(reinterpret_cast<const float4*>(p.gmin + g_list + t * kTcTileGroups));
+                    gsc[0] = gm.x * tAones; gsc[1] = gm.y * tAones; gsc[2] = gm.z * tAones; gsc[3] = gm.w * tAones;
+                }
                 { TC_T0(); mbar_wait(&bar_tfull[sb], ph); if (warp == 1) TC_ACC(8); }
                 tc_fence_after();
                 const uint32_t ng = min((uint32_t)kTcTileGroups, ngl - t * kTcTileGroups);
@@ -1382,13 +1423,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(const __grid_con
 #pragma unroll
                     for (int j = 0; j < 32; j++) tv[j] = __uint_as_float(r[j]);
                     const float m = min32(tv);
-                    if (p.mode == 2) return cb < ng ? m : kInf;  // bounds pass: the minimum of the 32-column group (+inf past the list)
-                    if (active && cb < ng && m <= P) {
+                    if (!NB && p.mode == 2) return cb < ng ? m : kInf;  // bounds pass: the minimum of the 32-column group (+inf past the list)
+                    // (NB: m + gmin <= every accumulator of the group + its own norm term, and rounding is monotonic)
+                    const float gmn = NB ? gsc[cb & 3u] : 0.0f;
+#ifdef VIDX_TC_ABLATE
+                    if (p.flags & 0x2000u) return r[0] == 0x12345678u ? 1.0f : 0.0f;  // timing only: loads, no min tree, no hits
+                    if ((p.flags & 0x1000u) && m > -1e38f) return m;                    // timing only: min tree, never the hit path
+#endif
+                    if (active && cb < ng && (NB ? m + gmn : m) <= P) {
                         // rare path: this row has columns inside its bound (as of the latest bound)
                         P = fminf(P, lds_volatile_f(&s_P[row]));
                         uint32_t mask = 0;
 #pragma unroll
-                        for (int j = 0; j < 32; j++) mask |= (tv[j] <= P) ? (1u << j) : 0u;
+                        for (int j = 0; j < 32; j++) mask |= ((NB ? tv[j] + gmn : tv[j]) <= P) ? (1u << j) : 0u;
                         while (mask) {
                             const int j = __ffs(mask) - 1;
                             mask &= mask - 1;
@@ -1401,12 +1448,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(const __grid_con
 #pragma unroll
                             for (int i = 0; i < 4; i++) s4[i] = (j & 4) ? s8[4 + i] : s8[i];
                             const float s2a = (j & 2) ? s4[2] : s4[0], s2b = (j & 2) ? s4[3] : s4[1];
-                            const float v = (j & 1) ? s2b : s2a;
+                            float v = (j & 1) ? s2b : s2a;
+                            // NB: the column's own norm term makes it the filter value the ninth MMA would have produced
+                            if (NB) v += __ldg(&p.vnorm32[(size_t)(g_list + t * kTcTileGroups + cb) * 32u + (uint32_t)j]) * tAones;
                             if (v <= P) {  // the bound may have shrunk since the mask was built
                                 push(kEntValid | (tl << 14) | ((cb * 32u + (uint32_t)j) << 7) | (uint32_t)row, v);
                                 // flood control (cold or very loose bound): the k-th smallest value this thread queued
-                                // in this item bounds the row's k-th best at once, without the selector's latency
-                                if (v < lr[0]) {
+                                // in this item bounds the row's k-th best at once, without the selector's latency.  A warm row
+                                // queues a value or two per item and needs none of it: the insertion (a dependent chain of KR
+                                // min / max pairs that the other 31 lanes of the warp wait for) starts with the third value --
+                                // the k smallest of a subset of the queued values still bound the row's k-th best.
+                                if (++nhit > kTcFloodAfter && v < lr[0]) {
                                     lr[0] = v;
 #pragma unroll
                                     for (int i = 0; i + 1 < KR; i++) {
@@ -1476,7 +1528,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(const __grid_con
                   U = U + 1e-5f * U;
                   atomicMin(&p.gthr_bits[q], __float_as_uint(U));
               }
-              const int merge_tries = (p.flags >> 4) ? (int)(p.flags >> 4) : kTcMergeTries;  // (flags bits 4+: A/B override)
+              const int merge_tries = ((p.flags >> 4) & 0xffu) ? (int)((p.flags >> 4) & 0xffu) : kTcMergeTries;  // (flags bits 4-11: A/B override)
               bool done = false;
               for (int tries = 0; !done && tries < merge_tries; tries++) {
                 // the critical section runs INSIDE the retry loop: a lane that holds a lock always finishes
@@ -1828,11 +1880,15 @@ void launch_row_norms(const float4* vecs, int Dq, const uint32_t* row_src, size_
     VIDX_LAUNCHED();
 }
 void launch_convert16(const float4* vecs, int Dq, int Dh, const uint32_t* row_src, size_t nrows, const float* vn_true, int sv, int g,
-                      uint4* vecs16, uint4* vnorm, cudaStream_t st) {
+                      uint4* vecs16, uint4* vnorm, cudaStream_t st, const uint32_t* perm, float* vnorm32, float* gmin) {
     if (!nrows) return;
     convert16_kernel<<<(unsigned)ceil_div(nrows * (size_t)Dh, 256), 256, 0, st>>>(vecs, Dq, Dh, row_src, nrows, vn_true, ldexpf(1.0f, sv),
-                                                                                ldexpf(1.0f, 2 * sv - g), vecs16, vnorm);
+                                                                                ldexpf(1.0f, 2 * sv - g), perm, vecs16, vnorm, vnorm32);
     VIDX_LAUNCHED();
+    if (vnorm32 && gmin) {
+        group_min_norm_kernel<<<(unsigned)ceil_div(nrows, 256), 256, 0, st>>>(vnorm32, nrows / 32, gmin);
+        VIDX_LAUNCHED();
+    }
 }
 void launch_query_norms(const float4* xq4, int Dq, uint32_t nq, uint32_t k, float* qn, uint32_t* gthr_bits, uint32_t* cand_cnt,
                         uint32_t* overflow, float* gtop, uint32_t* glock, uint32_t* stats, cudaStream_t st) {
@@ -1889,11 +1945,11 @@ void launch_tc_expand(const uint32_t* list_cnt, const uint32_t* list_ngroups, co
                                            pair ? 2u * kTcM : (uint32_t)kTcM, a_rowoff, items);
     VIDX_LAUNCHED();
 }
-template <int KR, bool PAIR, bool TSA = false, bool SA = false>
+template <int KR, bool PAIR, bool TSA = false, bool SA = false, bool NB = false>
 static void launch_scan_tc_kr(const TcParams& p, size_t smem, cudaStream_t st) {
     static PerDeviceSize attr;  // the opt-in is per device
     if (attr.needs(smem)) {
-        VIDX_CUDA(cudaFuncSetAttribute(scan_tc_kernel<KR, PAIR, TSA, SA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        VIDX_CUDA(cudaFuncSetAttribute(scan_tc_kernel<KR, PAIR, TSA, SA, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr.set(smem);
     }
     if (PAIR) {
@@ -1910,9 +1966,9 @@ static void launch_scan_tc_kr(const TcParams& p, size_t smem, cudaStream_t st) {
         at[0].val.clusterDim.z = 1;
         cfg.attrs = at;
         cfg.numAttrs = 1;
-        VIDX_CUDA(cudaLaunchKernelEx(&cfg, scan_tc_kernel<KR, PAIR, TSA, SA>, p));
+        VIDX_CUDA(cudaLaunchKernelEx(&cfg, scan_tc_kernel<KR, PAIR, TSA, SA, NB>, p));
     } else {
-        scan_tc_kernel<KR, PAIR, TSA, SA><<<tc_num_sms(), kTcThreads, smem, st>>>(p);
+        scan_tc_kernel<KR, PAIR, TSA, SA, NB><<<tc_num_sms(), kTcThreads, smem, st>>>(p);
     }
     VIDX_LAUNCHED();
 }
@@ -1934,6 +1990,10 @@ void launch_scan_tc(const TcParams& p, cudaStream_t st) {
         if (kr == 8) launch_scan_tc_kr<8, false, true>(p, smem, st);
         else if (kr == 16) launch_scan_tc_kr<16, false, true>(p, smem, st);
         else launch_scan_tc_kr<32, false, true>(p, smem, st);
+    } else if (p.nb && p.mode == 0 && p.gmin && p.vnorm32) {
+        if (kr == 8) launch_scan_tc_kr<8, false, false, false, true>(p, smem, st);
+        else if (kr == 16) launch_scan_tc_kr<16, false, false, false, true>(p, smem, st);
+        else launch_scan_tc_kr<32, false, false, false, true>(p, smem, st);
     } else {
         if (kr == 8) launch_scan_tc_kr<8, false>(p, smem, st);
         else if (kr == 16) launch_scan_tc_kr<16, false>(p, smem, st);

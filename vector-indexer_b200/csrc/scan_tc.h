@@ -73,6 +73,10 @@ struct TcParams {
     uint32_t flags;                // bit 0: keep the rows' sets CTA-local in the main pass (no cross-CTA merge at item ends);
                                    // bits 1, 2: timing ablations (VIDX_TC_FLAGS, wrong answers): epilogue / MMAs do nothing;
                                    // bit 3: the producer feeds the two tile pipelines independently instead of in tile order
+    const uint32_t* perm;          // shadow row -> row of the fp32 store (rows are sorted by norm inside every segment); NULL = identity
+    const float* gmin;             // per group of 32 shadow rows: the smallest norm term (fp32, same scale as vnorm); NaN for groups of padding rows
+    const float* vnorm32;          // per shadow row: the norm term as one fp32 value, rounded down; NaN for padding rows
+    uint32_t nb;                   // 1 = main pass with epilogue-side norms (scan_tc_kernel<.., NB>): eight MMAs per 128-d tile instead of nine
     const uint4* a_tiles;          // D > 512 only (tc_streams_a): every work item's query tile as fp16 in operand layout (launch_tc_atiles)
 };
 
@@ -124,8 +128,10 @@ int tc_dh(int D);  // chunks per vector of the shadow store (dimension padded to
 void launch_row_norms(const float4* vecs, int Dq, const uint32_t* row_src, size_t nrows, float* vn_true, uint32_t* stats,
                       cudaStream_t st);
 // The fp16 shadow store and the norm terms, given the index scale sv and the norm shift g.
+// perm (optional): shadow row -> store row; vnorm32 / gmin (optional): fp32 norm term per shadow row / its minimum per group of 32.
 void launch_convert16(const float4* vecs, int Dq, int Dh, const uint32_t* row_src, size_t nrows, const float* vn_true, int sv, int g,
-                      uint4* vecs16, uint4* vnorm, cudaStream_t st);
+                      uint4* vecs16, uint4* vnorm, cudaStream_t st, const uint32_t* perm = nullptr, float* vnorm32 = nullptr,
+                      float* gmin = nullptr);
 // stats[0..1]: float bits of max |q component| and max |q|^2 over the batch (zeroed by the caller).
 void launch_query_norms(const float4* xq4, int Dq, uint32_t nq, uint32_t k, float* qn, uint32_t* gthr_bits, uint32_t* cand_cnt,
                         uint32_t* overflow, float* gtop, uint32_t* glock, uint32_t* stats, cudaStream_t st);
