@@ -893,9 +893,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(const __grid_con
             constexpr int kSetupThreads = kTcThreads - 32;
             if (tid == 352) {  // (a selector warp) empty queues for this item
                 s_misc[4] = 0;
-                s_misc[8] = 0;
-                s_misc[9] = 0;
-                for (int i = 10; i < 8 + 2 * kTcSelectors; i++) s_misc[i] = 0;
+                for (int i = 8; i < 16; i++) s_misc[i] = 0;  // queue tail / head
             }
             const int row = tid - 32;  // warps 1-4 own the 128 query rows during set-up
             uint2 qi = make_uint2(kNoRow, 0);
