@@ -14,6 +14,10 @@
  * are ordered against each other only through those contexts: results are ready when
  * the stream given to the call reaches that point.  build / load / set_* are exclusive
  * (they wait for running searches and block new ones).
+ * Repeated searches: the second call with the same arguments (pointers, sizes, k, n_probe) on
+ * a context is captured into a CUDA graph and later ones replay it with one launch
+ * (DESIGN.md 4.4); the buffers may hold new contents, results are those of a plain call.
+ * A caller stream that is itself being captured is left alone.  VIDX_GRAPH=0 disables it.
  * There is NO CPU fallback: every compute entry point fails with VIDX_ERR_CUDA when
  * no sm_100 device is usable.
  */
@@ -299,7 +303,8 @@ typedef struct vidx_search_stats {
 /* Enable per-stage CUDA-event timing (adds stream synchronisation at the end of a
  * search); stats describe the last completed search on this handle. */
 int vidx_set_profiling(vidx_index* idx, int enabled);
-/* Scan algorithm: 0 (default) = tcgen05 FP16 filter + exact re-check whenever the shape allows (k <= 32, finite data).
+/* Scan algorithm: 0 (default) = tcgen05 FP16 filter + exact re-check whenever the shape allows (k <= 32, D <= 2048, finite data;
+ * up to D = 512 the query tile stays in shared memory, beyond it is streamed through the ring with the list tiles).
  * The filter runs a bounds pass (minima only) and a main pass: when a query visits many 128-vector tiles (tensor-bound) the
  * bounds pass covers the heads of its nearest lists and the main pass keeps tightening the bounds; when it visits at most
  * 2048 tiles (the HBM-bound regime) the bounds pass covers everything and the main pass only collects.
