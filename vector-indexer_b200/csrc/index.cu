@@ -1297,9 +1297,9 @@ void Index::search_device(SearchCtx& ctx, const float* d_xq, uint64_t nq, uint64
                     nb++;
                     for (int i = 0; i < 16; i++) acc[i] += (double)h[16 * b + i];
                 }
-                const char* names[16] = {"prod0 wait empty", "prod1 wait empty", "w2 hit episodes", "w2 hit lanes", "mma0 wait tempty",
+                const char* names[16] = {"prod0 wait empty", "prod1 wait empty", "push: thread-cyc no room", "values queued", "mma0 wait tempty",
                                          "mma1 wait tempty", "mma0 wait full", "mma1 wait full", "epi(w2) wait tfull", "w2 drain wait",
-                                         "w2 item setup", "items", "tiles", "kernel cycles", "w2 LDTM+wait", "w2 min tree + hits"};
+                                         "w2 item setup", "items", "tiles", "kernel cycles", "w2 LDTM+wait", "rare path thread-cyc"};
                 fprintf(stderr, "[tc timing] %d CTAs\n", nb);
                 for (int i = 0; i < 16; i++) fprintf(stderr, "  %-20s %12.0f per CTA  (%.1f%% of kernel)\n", names[i], acc[i] / nb, 100.0 * acc[i] / acc[13]);
             }

@@ -1275,6 +1275,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(const __grid_con
                 if (n == 0) {
                     if (lds_volatile(&s_misc[4]) == (uint32_t)kTcEpiWarps && lds_volatile(q_tail) == head) break;
                     if (++idle > (1u << 21)) __trap();  // an item never takes this long
+#ifdef VIDX_TC_ABLATE
+                    if (p.flags & 0x20000u) __nanosleep(256);  // (valid answers) an idle selector leaves the issue slots alone
+                    if ((p.flags & 0x40000u) && (idle & 7u)) continue;  // (valid answers) ... and adopts published bounds every eighth poll only
+#endif
                     for (int a4 = 0; a4 < 4; a4++) adopt(a4 * 32 + lane);
                     continue;
                 }
@@ -1376,10 +1380,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(const __grid_con
                 if (p.flags & 0x4000u) return;  // timing only: the hit path runs, nothing is queued
 #endif
                 const uint32_t idx = atomicAdd(q_tail, 1u);
+#ifdef VIDX_TC_TIMING
+                const long long _tp0 = clock64();
+                bool _spun = false;
+#endif
                 for (uint32_t spins = 0; idx - lds_volatile(q_head) >= (uint32_t)kTcQueueCap; spins++) {
                     __nanosleep(32);
+#ifdef VIDX_TC_TIMING
+                    _spun = true;
+#endif
                     if (spins > (1u << 22)) __trap();  // the selector always drains: a protocol bug, do not hang the GPU
                 }
+#ifdef VIDX_TC_TIMING
+                if (p.dbg) {
+                    if (_spun) atomicAdd(&p.dbg[16 * blockIdx.x + 2], (unsigned long long)(clock64() - _tp0));  // thread-cycles waiting for queue room
+                    atomicAdd(&p.dbg[16 * blockIdx.x + 3], 1ull);                                                  // values queued
+                }
+#endif
                 sts_volatile_v2(&s_queue[idx & (kTcQueueCap - 1)], make_uint2(info, __float_as_uint(v)));
             };
             const uint32_t eskip = (grp ^ it) & 1u;  // first tile of this item that belongs to this group
@@ -1430,6 +1447,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(const __grid_con
 #endif
                     if (active && cb < ng && (NB ? m + gmn : m) <= P) {
                         // rare path: this row has columns inside its bound (as of the latest bound)
+#ifdef VIDX_TC_TIMING
+                        const long long _th0 = clock64();
+#endif
                         P = fminf(P, lds_volatile_f(&s_P[row]));
                         uint32_t mask = 0;
 #pragma unroll
@@ -1468,6 +1488,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(const __grid_con
                                 }
                             }
                         }
+#ifdef VIDX_TC_TIMING
+                        if (p.dbg) atomicAdd(&p.dbg[16 * blockIdx.x + 15], (unsigned long long)(clock64() - _th0));  // thread-cycles in the rare path
+#endif
                     }
                     return m;
                 };
@@ -1528,6 +1551,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(const __grid_con
               }
               const int merge_tries = ((p.flags >> 4) & 0xffu) ? (int)((p.flags >> 4) & 0xffu) : kTcMergeTries;  // (flags bits 4-11: A/B override)
               bool done = false;
+#ifdef VIDX_TC_ABLATE
+              if (p.flags & 0x10000u) done = true;  // (valid answers) no union with the other CTAs' sets at item end
+#endif
               for (int tries = 0; !done && tries < merge_tries; tries++) {
                 // the critical section runs INSIDE the retry loop: a lane that holds a lock always finishes
                 // and releases it before it waits for the other lanes of its warp
