@@ -18,6 +18,7 @@
  * a context is captured into a CUDA graph and later ones replay it with one launch
  * (DESIGN.md 4.4); the buffers may hold new contents, results are those of a plain call.
  * A caller stream that is itself being captured is left alone.  VIDX_GRAPH=0 disables it.
+ * vidx_search_multi replays too when the index is replicated (partition world 1).
  * There is NO CPU fallback: every compute entry point fails with VIDX_ERR_CUDA when
  * no sm_100 device is usable.
  */

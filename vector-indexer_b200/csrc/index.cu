@@ -730,11 +730,15 @@ static void run_cached(Index& ix, SearchCtx& c, GraphKey key, cudaStream_t st, F
     VIDX_CUDA(cudaGraphLaunch(exec, st));
 }
 // The collective search: its two all-gathers are captured with the kernels (NCCL supports stream capture; every rank runs
-// the same call sequence, so all of them capture on the same call).  VIDX_GRAPH_MULTI=0 keeps the multi-GPU path launch by launch.
+// the same call sequence, so all of them capture on the same call).  Measured and tested on 2 / 4 / 8 GPUs with the index
+// replicated (the rank grid's P = 1: the case that is launch-bound); a PARTITIONED index keeps the launch-by-launch path
+// until the replay has been through the sharded configurations on hardware too -- VIDX_GRAPH_MULTI=2 switches it on there,
+// VIDX_GRAPH_MULTI=0 off everywhere.  (Every rank must use the same setting.)
 template <class F>
 static void run_cached_multi(Index& ix, SearchCtx& c, const GraphKey& key, cudaStream_t st, F&& enqueue) {
     const char* v = getenv("VIDX_GRAPH_MULTI");
-    if (v && *v && atoi(v) == 0) {
+    const int mode = v && *v ? atoi(v) : 1;
+    if (mode == 0 || (mode == 1 && ix.part_world > 1)) {
         enqueue();
         return;
     }
