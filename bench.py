@@ -711,7 +711,10 @@ def run_ours(args):
                 "details": {"recall_at_10": R["recall"], "recall_curve": R["curve"],
                             "ground_truth": "float64 brute force (torch, blocks of 32768 rows), independent of the library",
                             "l2": "inputs larger than L2 (index 512 MB)",
-                            "parallelism": R["parallelism"], "grid": R["grid"], "residency": R["residency"], "parity": parity},
+                            "parallelism": R["parallelism"], "grid": R["grid"], "residency": R["residency"], "parity": parity,
+                            "graph_replay": ("off (VIDX_GRAPH=0)" if os.environ.get("VIDX_GRAPH", "1") == "0" else
+                                             "on: the timed steps repeat one search, which the library replays as a CUDA graph from the "
+                                             "third call (gpu_launches counts the kernels of the replayed graphs)")},
                 "e2e": {"value": R["e2e_qps"], "unit": UNIT, "h2d_bytes_per_step": int(xq.nbytes // R["grid"]["query_groups"]),
                         "d2h_bytes_per_step": int(nq * k * 12), "ms_per_step": 1e3 * R["e2e_s"] / args.steps},
                 "gpu_launches": int(R["launches"]), "clocks": R["clocks"], "roofline": roofline, "roofline_hbm": roofline_hbm,
