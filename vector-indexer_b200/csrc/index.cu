@@ -699,8 +699,14 @@ static void run_cached(Index& ix, SearchCtx& c, GraphKey key, cudaStream_t st, F
     }
     if (c.gexec) cudaGraphExecDestroy(c.gexec);
     c.gexec = nullptr;
+    // Replay is best effort: whatever goes wrong with the capture itself, the search runs launch by launch instead.
     const uint64_t allocs0 = devbuf_allocs(), launches0 = g_kernel_launches.load();
-    VIDX_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+    if (cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+        cudaGetLastError();
+        c.seen = GraphKey{};
+        enqueue();
+        return;
+    }
     cudaGraph_t graph = nullptr;
     try {
         enqueue();
@@ -711,13 +717,13 @@ static void run_cached(Index& ix, SearchCtx& c, GraphKey key, cudaStream_t st, F
         c.seen = GraphKey{};
         throw;
     }
-    VIDX_CUDA(cudaStreamEndCapture(st, &graph));
+    const cudaError_t end_err = cudaStreamEndCapture(st, &graph);
     const uint64_t nl = g_kernel_launches.load() - launches0;
     cudaGraphExec_t exec = nullptr;
     const bool moved = devbuf_allocs() != allocs0;  // (cannot happen after an identical call; the captured addresses would be stale)
-    if (moved || cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
+    if (end_err != cudaSuccess || !graph || moved || cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
         cudaGetLastError();
-        cudaGraphDestroy(graph);
+        if (graph) cudaGraphDestroy(graph);
         c.seen = GraphKey{};
         g_kernel_launches.fetch_sub(nl);
         enqueue();
